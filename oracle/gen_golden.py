@@ -1,0 +1,183 @@
+"""TEST INFRASTRUCTURE -- generates tests/golden/*.npz by running the UNMODIFIED reference
+source (loaded by oracle/ref_loader.py from /root/reference) on seeded synthetic inputs.
+
+Run in the build container only:   python oracle/gen_golden.py
+The fixtures hold inputs AND the reference's outputs, so that the oracle (CPU, -m "not gpu")
+and the CUDA path (-m gpu) are both checked against the real reference on a box where
+/root/reference does not exist.
+
+DICE / DICEReAct: the reference calls `.cuda()` unconditionally (inference/funcs.py:180,185).
+To run it on this CPU-only container the generator makes `Tensor.cuda()` / `Module.cuda()` the
+identity for this process; the reference source itself is untouched.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle.ref_loader import load_reference  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def latent_case(ref, seed, n_train, n_test, d, n_classes, dtype, k):
+    rng = np.random.RandomState(seed)
+    centers = rng.randn(n_classes, d) * 0.7
+    ytr = rng.randint(0, n_classes, n_train)
+    train = (0.5 + centers[ytr] + rng.randn(n_train, d)).astype(dtype)
+    yte = rng.randint(0, n_classes, n_test)
+    valid = (0.5 + centers[yte] + rng.randn(n_test, d)).astype(dtype)
+    ood = (-0.5 + 1.3 * rng.randn(n_test, d)).astype(dtype)
+    out = dict(train=train, train_labels=ytr, valid=valid, valid_labels=yte, ood=ood,
+               num_classes=n_classes, k=k)
+    cfg = ref.DictConfig(k_neighbors=k, num_classes=n_classes)
+    for name in ("KDE", "MD", "cMD", "KNN", "GMM"):
+        if name == "KNN" and dtype != np.float32:
+            continue  # faiss only takes float32 (postprocessors.py:396-397)
+        p = ref.pp.postprocessors_dict[name](cfg=cfg)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            p.setup(train, ind_train_labels=ytr)
+            out[f"{name}_valid"] = np.asarray(p.postprocess(valid, pred_labels=yte))
+            out[f"{name}_ood"] = np.asarray(p.postprocess(ood, pred_labels=yte))
+        if name == "MD":
+            out["MD_feats_mean"] = p.feats_mean
+            out["MD_precision"] = p.precision
+        if name == "KNN":
+            out["KNN_activation_log"] = p.activation_log
+    return out
+
+
+def baselines_case(ref, seed, n_train, n_test, d, C, k):
+    rng = np.random.RandomState(seed)
+    centers = rng.randn(C, d)
+    ytr = rng.randint(0, C, n_train)
+    train = np.maximum(centers[ytr] + rng.randn(n_train, d), 0).astype(np.float32) + \
+        (0.05 * rng.rand(n_train, d)).astype(np.float32)
+    yva = rng.randint(0, C, n_test)
+    valid = np.maximum(centers[yva] + rng.randn(n_test, d), 0).astype(np.float32) + \
+        (0.05 * rng.rand(n_test, d)).astype(np.float32)
+    ood = np.maximum(1.5 * rng.randn(n_test, d), 0).astype(np.float32) + \
+        (0.05 * rng.rand(n_test, d)).astype(np.float32)
+    W = (0.2 * rng.randn(C, d)).astype(np.float32)
+    b = rng.randn(C).astype(np.float32)
+    lg = lambda x: (x @ W.T + b).astype(np.float32)  # noqa: E731
+    out = dict(train=train, train_labels=ytr, valid=valid, ood=ood, W=W, b=b,
+               train_logits=lg(train), valid_logits=lg(valid), ood_logits=lg(ood),
+               num_classes=C, k=k, gamma=0.1, ash_percentile=85, react_percentile=90,
+               dice_percentile=90)
+    fc = {"weight": W, "bias": b}
+    P = ref.pp
+    mk = {
+        "energy": lambda: P.Energy(flip_sign=False),
+        "msp": lambda: P.MSP(flip_sign=False),
+        "gen": lambda: P.GEN(flip_sign=False, gamma=0.1, num_classes=C),
+        "ddu": lambda: P.DDU(flip_sign=False, num_classes=C),
+        "knn": lambda: P.KNN(flip_sign=False, k_neighbors=k),
+        "mahalanobis": lambda: P.Mahalanobis(flip_sign=False, num_classes=C),
+        "vim": lambda: P.ViM(flip_sign=False),
+        "ash": lambda: P.ASH(flip_sign=False, ash_percentile=85),
+        "react": lambda: P.ReAct(flip_sign=False, react_percentile=90),
+        "dice": lambda: P.DICE(flip_sign=False, dice_percentile=90, num_classes=C),
+        "dice_react": lambda: P.DICEReAct(flip_sign=False, dice_percentile=90,
+                                           react_percentile=90, num_classes=C),
+    }
+    logit_methods = ("energy", "msp", "gen")
+    for name, ctor in mk.items():
+        p = ctor()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if name in logit_methods:
+                p.setup(out["train_logits"])
+                v, o = p.postprocess(out["valid_logits"]), p.postprocess(out["ood_logits"])
+            else:
+                p.setup(train, valid_feats=valid, train_labels=ytr,
+                        train_logits=out["train_logits"], valid_logits=out["valid_logits"],
+                        final_linear_layer_params=fc)
+                v = p.postprocess(valid, logits=out["valid_logits"])
+                o = p.postprocess(ood, logits=out["ood_logits"])
+        out[f"{name}_valid"], out[f"{name}_ood"] = np.asarray(v), np.asarray(o)
+        out[f"{name}_threshold"] = np.float64(p.threshold)
+        if name == "vim":
+            out["vim_u"], out["vim_NS"], out["vim_alpha"] = p.u, p.NS, np.float64(p.alpha)
+            out["vim_DIM"] = p.DIM
+        if name == "react":
+            out["react_activation_threshold"] = np.float64(p.activation_threshold)
+        if name == "dice":
+            out["dice_masked_w"] = p.dice_layer.masked_w.cpu().numpy()
+            out["dice_thresh"] = np.float64(p.dice_layer.thresh)
+        if name == "mahalanobis":
+            out["mahalanobis_class_mean"] = p.class_mean
+            out["mahalanobis_precision"] = p.precision
+    # flip_sign variant (OodPostprocessor.flip_sign_fn, abstract_classes.py:160-187)
+    p = P.Energy(flip_sign=True)
+    p.setup(out["train_logits"])
+    out["energy_flipped_valid"] = p.postprocess(out["valid_logits"])
+    out["energy_flipped_threshold"] = np.float64(p.threshold)
+    return out
+
+
+def entropy_case(ref, seed):
+    rng = np.random.RandomState(seed)
+    out = {}
+    for tag, n_mc, n_items, D in (("n16", 16, 12, 40), ("n3", 3, 9, 20), ("n5", 5, 6, 17),
+                                  ("n32", 32, 4, 24), ("n7", 7, 5, 33)):
+        base = rng.randn(n_items, 1, D)
+        z = (base + 0.1 * rng.randn(n_items, n_mc, D)).astype(np.float32)
+        mask = rng.rand(n_items, n_mc, D) < 0.4  # DropBlock-like zeros -> exact duplicates
+        z[mask] = 0.0
+        z[0] = 0.25  # all-equal item: every distance hits the min_dist clamp
+        z = z.reshape(n_items * n_mc, D)
+        h_mvn, h_z = ref.entropy.get_dl_h_z(z, n_mc, parallel_run=False)
+        out[f"{tag}_z"], out[f"{tag}_n_mc"] = z, n_mc
+        out[f"{tag}_h_mvn"], out[f"{tag}_h_z"] = h_mvn, h_z
+    # Tensor path tolerates a short last chunk (entropy.py:56-58)
+    z = torch.from_numpy(rng.rand(6 * 8 + 7, 10).astype(np.float32))
+    h_mvn, h_z = ref.entropy.get_dl_h_z(z, 8, parallel_run=False)
+    out["ragged_z"], out["ragged_n_mc"] = z.numpy(), 8
+    out["ragged_h_mvn"], out["ragged_h_z"] = h_mvn, h_z
+    return out
+
+
+def pca_case(ref, seed):
+    out = {}
+    for tag, dtype, n, D0, d in (("f64", np.float64, 400, 20, 10), ("f32", np.float32, 500, 48, 16)):
+        np.random.seed(seed)
+        train = (0.5 + np.random.randn(n, D0)).astype(dtype)
+        test = (-0.5 + np.random.randn(64, D0)).astype(dtype)
+        tr, pca = ref.dimred.apply_pca_ds_split(train, d)
+        te = ref.dimred.apply_pca_transform(test, pca)
+        out.update({f"{tag}_train": train, f"{tag}_test": test, f"{tag}_train_t": tr,
+                    f"{tag}_test_t": te, f"{tag}_components": pca.components_,
+                    f"{tag}_mean": pca.mean_, f"{tag}_explained_variance": pca.explained_variance_,
+                    f"{tag}_seed": seed, f"{tag}_d": d})
+    # no-whiten variant
+    np.random.seed(seed)
+    train = 0.5 + np.random.randn(300, 12)
+    tr, pca = ref.dimred.apply_pca_ds_split(train, 5, svd_solver="full", whiten=False)
+    out.update(dict(nw_train=train, nw_train_t=tr, nw_components=pca.components_, nw_mean=pca.mean_))
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = load_reference()
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    np.savez_compressed(os.path.join(OUT, "latent_f32.npz"),
+                        **latent_case(ref, 11, 600, 96, 24, 4, np.float32, 7))
+    np.savez_compressed(os.path.join(OUT, "latent_f64.npz"),
+                        **latent_case(ref, 12, 400, 64, 16, 3, np.float64, 5))
+    np.savez_compressed(os.path.join(OUT, "baselines.npz"),
+                        **baselines_case(ref, 21, 900, 128, 32, 5, 10))
+    np.savez_compressed(os.path.join(OUT, "entropy.npz"), **entropy_case(ref, 31))
+    np.savez_compressed(os.path.join(OUT, "pca.npz"), **pca_case(ref, 1))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,185 @@
+"""CPU: pins the oracle (oracle/oracle_np.py) against (1) the reference's own hard-coded golden
+vectors and (2) fixtures produced by the unmodified reference source (oracle/gen_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_np as O
+from tests import refkats as K
+from tests.conftest import rel_err
+
+TOL = 1e-6  # the reference's own TOLERANCE (tests/unit_test_postprocessors.py:57)
+
+
+def _sumdiff(a, b):
+    return abs(float((np.asarray(a, np.float64) - np.asarray(b, np.float64)).sum()))
+
+
+# ------------------------------- reference KATs -------------------------------------------
+def test_kat_md_10x32():
+    tr, _, _ = K.generate_test_data(seed=42)
+    te, _, _ = K.generate_test_data(seed=43)
+    mean, prec = O.md_fit(tr)
+    assert _sumdiff(K.MD_10x32, O.md_score(te, mean, prec)) < TOL
+    assert np.allclose(O.md_score(te, mean, prec), O.md_score_faithful(te, mean, prec), atol=1e-9)
+
+
+def test_kat_kde_10x32():
+    tr, _, _ = K.generate_test_data(seed=42)
+    te, _, _ = K.generate_test_data(seed=43)
+    assert _sumdiff(K.KDE_10x32, O.kde_score(te, tr)) < TOL
+
+
+def test_kat_cmd_and_mahalanobis_10x32():
+    tr, ytr, _ = K.generate_test_data(seed=42)
+    te, _, _ = K.generate_test_data(seed=43)
+    with pytest.warns(UserWarning):
+        cm, P = O.mahalanobis_fit(tr, ytr, 10)
+    s = O.mahalanobis_score(te, cm, P, 10)
+    assert _sumdiff(K.MAHALANOBIS_10x32, -s) < TOL  # flip_sign=True in the reference test
+    assert _sumdiff(K.CMD_10x32, s) < 1e-5  # cMD is the float32 torch variant of the same maths
+
+
+def test_kat_knn_k_exceeds_bank():
+    tr, _, _ = K.generate_test_data(seed=42)
+    te, _, _ = K.generate_test_data(seed=43)
+    s, idx = O.knn_score(te, O.normalize_rows_exact(tr), 50)
+    assert s.dtype == np.float32 and np.array_equal(s.astype(np.float64), K.KNN_10x32)
+    assert (idx[:, 10:] == -1).all() and (np.sort(idx[:, :10], 1) == np.arange(10)).all()
+
+
+def test_kat_energy_gen():
+    _, _, lte = K.generate_test_data(seed=43)
+    assert _sumdiff(K.ENERGY_10x10, -O.energy_score(lte)) < TOL
+    assert _sumdiff(K.GEN_10x10, -O.gen_score(lte, 0.1, 10)) < TOL
+
+
+def test_kat_larem_lared_200x20():
+    np.random.seed(1)
+    x = np.random.rand(200, 20)
+    mean, prec = O.md_fit(x)
+    assert np.allclose(prec[0], K.LAREM_PRECISION_ROW0, atol=TOL)
+    assert np.allclose(O.md_score(x, mean, prec)[:20], K.LAREM_SCORES_20, atol=TOL)
+    assert np.allclose(O.kde_score(x, x)[:20], K.LARED_SCORES_20, atol=TOL)
+
+
+def test_kat_entropy():
+    np.random.seed(1)
+    x = np.random.rand(3, 20)
+    hz = np.array([O.get_h(x[:, j], k=2) for j in range(20)])
+    assert np.allclose(hz, K.ENTROPY_SINGLE_3x20, atol=TOL)
+    torch.manual_seed(1)
+    z = torch.rand(600, 20).numpy()
+    h_mvn, h_z = O.get_dl_h_z(z, 3)
+    assert h_z.shape == (200, 20) and h_mvn.shape == (200, 1)
+    assert np.allclose(h_z[0], K.ENTROPY_DL_ROW0, atol=TOL)
+    same = np.full((3, 4), 0.7, np.float32)
+    assert abs(O.get_dl_h_z(same, 3)[1][0, 0] - K.ENTROPY_ALL_EQUAL) < 1e-8
+    f = O.get_dl_h_z_faithful(z[:30], 3)
+    assert np.allclose(f[1], h_z[:10], atol=1e-12) and np.allclose(f[0], h_mvn[:10], atol=1e-12)
+
+
+def test_kat_pca():
+    from sklearn.decomposition import PCA
+
+    np.random.seed(1)
+    ind = 0.5 + np.random.randn(1000, 20)
+    ood = -0.5 + np.random.randn(1000, 20)
+    pca = PCA(n_components=10, svd_solver="randomized", whiten=True)
+    tr = pca.fit_transform(ind)
+    assert _sumdiff(tr[0], K.PCA_TRANSFORMED_ROW0) < 1e-7
+    assert abs(float((pca.components_[0] + K.PCA_NEG_COMPONENT0).sum())) < 1e-7
+    z = O.pca_transform(ood, pca.mean_, pca.components_, pca.explained_variance_)
+    assert _sumdiff(z[0], K.PCA_OOD_ROW0) < 1e-7
+    assert np.allclose(z, pca.transform(ood), atol=1e-12)
+
+
+def test_kat_metrics():
+    np.random.seed(1)
+    ind = 0.5 + np.random.randn(1000)
+    ood = -0.5 + np.random.randn(1000)
+    auroc, fpr95 = O.auroc_fpr95(ind, ood)
+    assert abs(auroc - K.METRICS_1D["auroc"]) < 1e-7 and abs(fpr95 - K.METRICS_1D["fpr95"]) < 1e-7
+    # tests/unit_test_metrics.py:31-81: KDE + MD end to end on 1000x20 latents
+    np.random.seed(1)
+    valid = 0.5 + np.random.randn(1000, 20)
+    train = 0.5 + np.random.randn(1000, 20)
+    np.random.randint(5, size=1000), np.random.randint(5, size=1000), np.random.randint(5, size=1000)
+    oodx = -0.5 + np.random.randn(1000, 20)
+    mean, prec = O.md_fit(train)
+    a, f = O.auroc_fpr95(O.md_score(valid, mean, prec), O.md_score(oodx, mean, prec))
+    assert abs(a - K.METRICS_MD["auroc"]) < 1e-7 and abs(f - K.METRICS_MD["fpr95"]) < 1e-7
+    a, f = O.auroc_fpr95(O.kde_score(valid, train), O.kde_score(oodx, train))
+    assert abs(a - K.METRICS_KDE["auroc"]) < 1e-7 and abs(f - K.METRICS_KDE["fpr95"]) < 1e-7
+
+
+# ------------------------------- fixtures from the reference run ---------------------------
+@pytest.mark.parametrize("name", ["latent_f32", "latent_f64"])
+def test_fixture_latent(golden, name):
+    g = golden(name)
+    C, k = int(g["num_classes"]), int(g["k"])
+    mean, prec = O.md_fit(g["train"])
+    assert np.allclose(prec, g["MD_precision"], atol=1e-10)
+    for split in ("valid", "ood"):
+        x = g[split]
+        assert rel_err(O.md_score(x, mean, prec), g[f"MD_{split}"]) < 1e-10
+        cm, P = O.mahalanobis_fit(g["train"], g["train_labels"], C)
+        assert rel_err(O.mahalanobis_score(x, cm, P, C), g[f"cMD_{split}"]) < 2e-6
+        m, L, _ = O.gmm_fit_np(g["train"], g["train_labels"], C)
+        assert rel_err(O.gmm_lse_score(x, m, L), g[f"GMM_{split}"]) < 2e-6
+        if name == "latent_f32":
+            bn = O.normalize_rows_exact(g["train"])
+            assert np.abs(bn - g["KNN_activation_log"]).max() <= 1.2e-7
+            assert rel_err(O.knn_score(x, bn, k)[0], g[f"KNN_{split}"]) < 1e-6
+    # LaRED: sklearn's tree KDE is exact on in-distribution queries; on far OoD queries its
+    # breadth-first bound bookkeeping cancels catastrophically (see DESIGN.md "KDE parity").
+    assert rel_err(O.kde_score(g["valid"], g["train"]), g["KDE_valid"]) < 1e-5
+    err = np.abs(O.kde_score(g["ood"], g["train"]) - g["KDE_ood"])
+    assert np.median(err) < 1e-5
+
+
+def test_fixture_baselines(golden):
+    b = golden("baselines")
+    C, k = int(b["num_classes"]), int(b["k"])
+    W, bias = b["W"], b["b"]
+    for split in ("valid", "ood"):
+        x, lg = b[split], b[f"{split}_logits"]
+        assert rel_err(O.energy_score(lg), b[f"energy_{split}"]) < 1e-7
+        assert rel_err(O.msp_score(lg), b[f"msp_{split}"]) < 1e-7
+        assert rel_err(O.gen_score(lg, 0.1, C), b[f"gen_{split}"]) < 1e-7
+        m, L, _ = O.gmm_fit_np(b["train"], b["train_labels"], C)
+        assert rel_err(O.gmm_lse_score(x, m, L), b[f"ddu_{split}"]) < 5e-6
+        bn = O.normalize_rows_exact(b["train"])
+        assert rel_err(O.knn_score(x, bn, k)[0], b[f"knn_{split}"]) < 1e-6
+        cm, P = O.mahalanobis_fit(b["train"], b["train_labels"], C)
+        assert rel_err(O.mahalanobis_score(x, cm, P, C), b[f"mahalanobis_{split}"]) < 1e-10
+        u, DIM, NS, alpha = O.vim_fit(b["train"], b["train_logits"], W, bias)
+        assert DIM == int(b["vim_DIM"])
+        assert rel_err(O.vim_score(x, lg, u, NS, alpha), b[f"vim_{split}"]) < 1e-6
+        assert rel_err(O.ash_score(x, W, bias, 85), b[f"ash_{split}"]) < 1e-6
+        thr = O.react_threshold(b["train"], 90)
+        assert thr == float(b["react_activation_threshold"])
+        assert rel_err(O.react_score(x, W, bias, thr), b[f"react_{split}"]) < 1e-6
+        mw, t = O.dice_masked_weight(b["train"], W, 90)
+        assert np.array_equal(mw, b["dice_masked_w"])
+        assert rel_err(O.dice_score(x, mw, bias), b[f"dice_{split}"]) < 1e-6
+        assert rel_err(O.dice_score(x, mw, bias, clip=thr), b[f"dice_react_{split}"]) < 1e-6
+    assert abs(O.method_threshold(b["energy_valid"]) - 0) >= 0  # smoke
+    assert abs(O.method_threshold(O.energy_score(b["train_logits"])) - float(b["energy_threshold"])) < 1e-6
+
+
+def test_fixture_entropy(golden):
+    e = golden("entropy")
+    for tag in ("n16", "n3", "n5", "n32", "n7"):
+        hm, hz = O.get_dl_h_z(e[f"{tag}_z"], int(e[f"{tag}_n_mc"]))
+        assert np.allclose(hm, e[f"{tag}_h_mvn"], atol=1e-9)
+        assert np.allclose(hz, e[f"{tag}_h_z"], atol=1e-9)
+
+
+def test_fixture_pca(golden):
+    p = golden("pca")
+    for tag in ("f64", "f32"):
+        z = O.pca_transform(p[f"{tag}_test"], p[f"{tag}_mean"], p[f"{tag}_components"],
+                            p[f"{tag}_explained_variance"])
+        assert z.dtype == p[f"{tag}_test_t"].dtype
+        assert rel_err(z, p[f"{tag}_test_t"]) < 1e-6
