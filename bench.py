@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""Benchmark of the OoD scoring hot path (BASELINE.json metric: OoD-scored embeddings/sec).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload larem]
+
+One "step" = one pass of the LaREM (Mahalanobis, d=256 after PCA) scorer over one batch of
+synthetic embeddings that is larger than L2.  `value` is measured with inputs resident in HBM
+(CUDA events, max over ranks); `e2e` goes through the reference-facing class with HOST buffers
+(pinned H2D copy + score + D2H read of the scores inside the timed region).  Secondary numbers
+(kNN with k=50 on a 50k bank = BASELINE config 2; sharded-bank kNN at N>1; the entropy kernel)
+ride along under "extra", each with its own roofline.  `--impl reference` times the oracle's
+faithful port of the reference's CPU path on the host cores (the reference is pure Python on
+NumPy/sklearn; it cannot be pip-installed offline because of its unmet dependencies, see
+DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+D_LATENT = 256
+N_TRAIN = 50_000
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _fit_larem(seed=1):
+    """LaREM fit on 50k x 256 whitened latents (what PCA-256 of config 1/2 features looks like)."""
+    rng = np.random.RandomState(seed)
+    train = (rng.randn(N_TRAIN, D_LATENT)).astype(np.float32)
+    train += (0.05 * rng.randn(1, D_LATENT)).astype(np.float32)
+    return train
+
+
+def _time_events(fn, steps, warmup, dist_barrier):
+    import torch
+
+    for _ in range(warmup):
+        fn()
+    dist_barrier()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    dist_barrier()
+    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    return ev[0].elapsed_time(ev[steps]), per
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    import runia_core_b200 as R
+    from runia_core_b200 import _lib, _ops
+
+    hbm_peak, peak_src = _peaks()
+    dev = torch.device("cuda", local)
+    md = R.inference.MDLatentSpace()
+    md.setup(_fit_larem())
+    st = md._state
+
+    # ---------------- device-resident LaREM: [N, 256] f32 per rank, 4.3 GB > L2 ----------------
+    n_rows = args.rows
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    X = torch.randn(n_rows, D_LATENT, generator=g, device=dev, dtype=torch.float32)
+    X[n_rows // 2:] -= 0.5  # OoD-like half
+    out_holder = {}
+
+    def step():
+        out_holder["s"] = _ops.md_score(X, st, torch.float64)
+
+    sampler = ClockSampler(local)
+    l0 = _lib.launch_count()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    l1 = _lib.launch_count()
+    sampler.start()
+    total_ms, per = _time_events(step, args.steps, 0, barrier)
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - l1
+    total_ms = max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    value = n_rows * world / (ms_per_step * 1e-3)
+    kern_ms = float(np.mean(per))
+    alg_bytes = n_rows * (D_LATENT * 4 + 8)
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    flops = n_rows * (2.0 * D_LATENT * st.r + 3.0 * D_LATENT)
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "kernel": "rownorm_kernel (FP32 SIMT contraction + row sum of squares)",
+                "fp32_tflops": round(flops / (kern_ms * 1e-3) / 1e12, 2)}
+
+    # ---------------- end to end through the reference-facing class, host buffers ----------------
+    n_e2e = min(args.e2e_rows, n_rows)
+    host = torch.empty((n_e2e, D_LATENT), dtype=torch.float32).pin_memory()
+    host.copy_(X[:n_e2e].cpu())
+    e2e_out = {}
+
+    def e2e_step():
+        e2e_out["s"] = md.postprocess(host)  # pinned H2D -> kernel -> D2H numpy scores
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_s = max_over_ranks(e2e_s * 1e3) * 1e-3
+    e2e = {"value": n_e2e * world / e2e_s, "unit": "embeddings/s", "h2d_bytes_per_step": n_e2e * D_LATENT * 4,
+           "d2h_bytes_per_step": n_e2e * 8, "rows_per_step": n_e2e}
+
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        extra.update(_extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak))
+    if world > 1 and not args.no_extra:
+        extra.update(_extra_sharded_knn(args, torch, dist, _ops, world, rank, barrier, max_over_ranks))
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu_baseline = _cpu_larem(md, seconds=args.cpu_seconds)
+
+    if rank == 0:
+        line = {
+            "metric": "ood_scored_embeddings_per_sec", "value": value, "unit": "embeddings/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "LaREM (MDLatentSpace) scoring, d=256 after PCA, fit on 50k train latents "
+                                   "(BASELINE configs[1] bank size; configs[0] scorer)",
+                       "rows_per_gpu": n_rows, "d": D_LATENT, "input_bytes_per_gpu": n_rows * D_LATENT * 4,
+                       "l2_policy": "inputs (4.3 GB) larger than L2 (126 MB)", "parallelism": f"rows x{world}"},
+            "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu_baseline, "extra": extra,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak):
+    """Secondary numbers on rank 0: kNN (config 2) and the entropy kernel (config 1 shape)."""
+    out = {}
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev).manual_seed(7)
+    # kNN: 50k x 512 bank, 10k queries, k = 50
+    centers = torch.randn(10, 512, generator=g, device=dev)
+    lab = torch.randint(0, 10, (50_000,), generator=g, device=dev)
+    bank = _ops.normalize_rows(centers[lab] + torch.randn(50_000, 512, generator=g, device=dev))
+    labq = torch.randint(0, 10, (10_000,), generator=g, device=dev)
+    q = _ops.normalize_rows(centers[labq] + torch.randn(10_000, 512, generator=g, device=dev))
+    kb = _ops.knn_bank(bank)
+    res = {}
+
+    def knn_step():
+        res["r"] = _ops.knn_search(q, kb, 50, want_idx=False, want_dist=False, check_status=False)
+
+    for _ in range(2):
+        knn_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        knn_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    fl = 2.0 * 10_000 * 50_000 * 512
+    full = _ops.knn_search(q, kb, 50)
+    out["knn_config2"] = {"queries_per_s": 10_000 / (ms * 1e-3), "ms": ms, "bank": [50_000, 512], "k": 50,
+                          "distance_tflops": fl / (ms * 1e-3) / 1e12,
+                          "exhaustive_rows": full["exhaustive_rows"]}
+    # entropy: 16 MC samples x 512 dims, 60k items = 1.97 GB
+    n_items, n_mc, D = 60_000, 16, 512
+    z = torch.randn(n_items, 1, D, generator=g, device=dev) + 0.1 * torch.randn(n_items, n_mc, D, generator=g, device=dev)
+    z = z.reshape(n_items * n_mc, D).contiguous()
+
+    def ent_step():
+        res["e"] = _ops.mcd_entropy(z, n_mc)
+
+    for _ in range(2):
+        ent_step()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        ent_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    alg = n_items * (n_mc * D * 4 + D * 8 + 8)
+    out["entropy_config1"] = {"items_per_s": n_items / (ms * 1e-3), "ms": ms, "n_mc": n_mc, "D": D,
+                              "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                           "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}}
+    del z
+    # PCA 512 -> 256 projection
+    from sklearn.decomposition import PCA
+    rng = np.random.RandomState(3)
+    pca = PCA(n_components=256, whiten=True)
+    pca.mean_ = rng.randn(512)
+    pca.components_ = np.linalg.qr(rng.randn(512, 256))[0].T.copy()
+    pca.explained_variance_ = 1.0 + rng.rand(256)
+    stp = _ops.pca_prepare(pca.mean_, pca.components_, pca.explained_variance_, True)
+    Xp = torch.randn(2_000_000, 512, generator=g, device=dev)
+
+    def pca_step():
+        res["p"] = _ops.pca_transform(Xp, stp)
+
+    for _ in range(2):
+        pca_step()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        pca_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    alg = 2_000_000 * (512 * 4 + 256 * 4)
+    out["pca_512_256"] = {"embeddings_per_s": 2_000_000 / (ms * 1e-3), "ms": ms,
+                          "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                       "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak},
+                          "fp32_tflops": 2.0 * 2_000_000 * 512 * 256 / (ms * 1e-3) / 1e12}
+    return out
+
+
+def _extra_sharded_knn(args, torch, dist, _ops, world, rank, barrier, max_over_ranks):
+    """Bank sharded by contiguous row ranges over the ranks, queries replicated, partial top-k
+    all-gathered over NCCL and merged."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nb_rank, d, nq, k = args.knn_shard_rows, 768, 4096, 50
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    bank = _ops.normalize_rows(torch.randn(nb_rank, d, generator=g, device=dev))
+    gq = torch.Generator(device=dev).manual_seed(99)
+    q = _ops.normalize_rows(torch.randn(nq, d, generator=gq, device=dev))
+    kb = _ops.knn_bank(bank, idx_offset=rank * nb_rank)
+    out = {}
+
+    def step():
+        r = _ops.knn_search(q, kb, k, want_f64=True, want_dist=False, check_status=False)
+        gd = torch.empty((world, nq, k), dtype=torch.float64, device=dev)
+        gi = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gd, r["dist64"])
+        dist.all_gather_into_tensor(gi, r["idx"])
+        out["m"] = _ops.topk_merge(gd, gi)
+
+    step()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 2
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+    return {"knn_sharded": {"queries_per_s": nq / (ms * 1e-3), "ms": ms, "bank_rows_total": nb_rank * world,
+                            "d": d, "k": k, "scaling": "weak (bank grows with ranks)",
+                            "distance_tflops_per_gpu": 2.0 * nq * nb_rank * d / (ms * 1e-3) / 1e12}}
+
+
+def _cpu_larem(md, seconds=8.0):
+    """The reference's CPU path for the same scorer (postprocessors.py:241-242: N x N product),
+    restated in oracle/oracle_np.py, on a bounded sample: 10k-row calls (800 MB temporary each,
+    the largest the formulation affords) until `seconds` of work."""
+    from oracle import oracle_np as O
+
+    rng = np.random.RandomState(5)
+    x = rng.randn(10_000, D_LATENT).astype(np.float32)
+    O.md_score_faithful(x[:2000], md.feats_mean, md.precision)
+    t0 = time.perf_counter()
+    n = 0
+    while time.perf_counter() - t0 < seconds and n < 30:
+        O.md_score_faithful(x, md.feats_mean, md.precision)
+        n += 1
+    dt = time.perf_counter() - t0
+    try:
+        import threadpoolctl
+
+        threads = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count()
+    return {"value": n * 10_000 / dt, "unit": "embeddings/s", "cores": int(threads), "kind": "port",
+            "sample": f"{n} calls x 10,000 rows x d=256 of MDLatentSpace.postprocess (N x N form), {dt:.1f} s"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation (faithful oracle port), all BLAS threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle_np as O
+
+    train = _fit_larem()
+    mean, prec = O.md_fit(train)
+    rng = np.random.RandomState(5)
+    x = rng.randn(10_000, D_LATENT).astype(np.float32)
+    for _ in range(max(1, min(args.warmup, 3))):
+        O.md_score_faithful(x, mean, prec)
+    steps = max(1, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.md_score_faithful(x, mean, prec)
+    dt = (time.perf_counter() - t0) / steps
+    try:
+        import threadpoolctl
+
+        threads = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] or [1])
+    except Exception:
+        threads = os.cpu_count()
+    v = 10_000 / dt
+    line = {"impl": "reference", "metric": "ood_scored_embeddings_per_sec", "value": v, "unit": "embeddings/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "LaREM (MDLatentSpace) scoring, d=256 after PCA, fit on 50k train latents "
+                                   "(BASELINE configs[1] bank size; configs[0] scorer)",
+                       "rows_per_step": 10_000, "d": D_LATENT},
+            "cpu_baseline": {"value": v, "unit": "embeddings/s", "cores": int(threads), "kind": "port",
+                             "sample": "10,000-row calls of the N x N Mahalanobis form (postprocessors.py:241-242)"},
+            "e2e": {"value": v, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=4 * 1024 * 1024, help="embeddings per GPU per step")
+    ap.add_argument("--e2e-rows", type=int, default=1024 * 1024)
+    ap.add_argument("--knn-shard-rows", type=int, default=1_250_000)
+    ap.add_argument("--cpu-seconds", type=float, default=8.0)
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,196 @@
+/*
+ * runia_b200.h -- C ABI of libruniab200.so: the B200 (sm_100a) implementation of RunIA-core's
+ * post-hoc OoD scoring hot path.
+ *
+ * The reference (CEA-LIST/runia_core) is 100 % Python and has no FFI: every entry point below
+ * replaces the NumPy / SciPy / scikit-learn / faiss / torch call sequence at the cited lines
+ * (paths relative to the reference tree).  The Python classes in `runia_core_b200/` bind these
+ * with ctypes (see INTEGRATION.md for the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the name ends in `_host`.  All matrices are dense,
+ *    row-major, contiguous.  The caller allocates inputs and outputs; nothing is retained.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are
+ *    asynchronous with respect to the host and re-entrant per stream.
+ *  - Return value: 0 on success; a negative RUNIA_E_* code for argument errors; a positive
+ *    cudaError_t if a CUDA runtime call failed.  `runia_b200_last_error()` gives a message for
+ *    the calling thread.  No C++ exception crosses the boundary.
+ *  - "f32"/"f64" in a name is the element type of the streamed input; outputs are documented
+ *    per call and match the dtype the reference returns.
+ */
+#ifndef RUNIA_B200_H
+#define RUNIA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RUNIA_B200_ABI_VERSION 1
+
+#define RUNIA_OK 0
+#define RUNIA_E_BADARG (-1)      /* null pointer, non-positive size, k out of range ...        */
+#define RUNIA_E_UNSUPPORTED (-2) /* shape outside what the kernels are built for               */
+#define RUNIA_E_WORKSPACE (-3)   /* workspace too small (query the size with the *_workspace)  */
+
+int runia_b200_abi_version(void);
+const char *runia_b200_last_error(void);
+/* Number of kernel launches issued through this library by the calling process (bench.py's
+ * `gpu_launches`). */
+int64_t runia_b200_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a1) MC-dropout latent-sample entropy -- evaluation/entropy.py:41-93 (`get_dl_h_z`) and :20-38
+ * (`single_image_entropy_calculation`), i.e. entropy_estimators.continuous.get_h(x, k,
+ * norm="max", min_dist=1e-5) per item (joint) and per (item, dimension).
+ *   z      [n_items * n_mc, D] float32, item-major (rows i*n_mc .. i*n_mc+n_mc-1 = item i)
+ *   h_z    [n_items, D] float64   per-dimension entropies            (entropy.py:73-92)
+ *   h_mvn  [n_items]    float64   joint (Chebyshev) entropy          (entropy.py:67-71); may be NULL
+ *   k      neighbours (entropy.py:66: 5 if n_mc > 5 else n_mc-1); 1 <= k < n_mc <= 32
+ *   digamma_term = -psi(k) + psi(n_mc), computed by the host in float64.
+ */
+int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, int D, int k, double min_dist,
+                          double digamma_term, double *h_z, double *h_mvn, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Input staging: out[n, j] = (float)(in[n, j] - center[j])   (center may be NULL).
+ * Used for float64 inputs (the reference keeps float64 end to end, e.g. postprocessors.py:241)
+ * so that the subtraction of the fitted mean happens at input precision before the float32
+ * contraction.  in_is_f64: 0 = float32 input, 1 = float64 input.
+ */
+int runia_center_cast(const void *in, int in_is_f64, int64_t N, int d, const double *center,
+                      float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a2) PCA projection -- dimensionality_reduction.py:75-87 (`apply_pca_transform` ->
+ * sklearn PCA.transform):  Z = (X - mean) @ components^T, then / sqrt(explained_variance).
+ *   X          [N, D0] float32
+ *   mean       [D0]   float32  (subtracted in the prologue; may be NULL)
+ *   components [d, D0] float32 (row j = component j, K-contiguous)
+ *   inv_scale  [d]    float32  1/sqrt(explained_variance) (NULL when whiten=False)
+ *   Z          [N, d] float32
+ */
+int runia_pca_transform_f32(const float *X, int64_t N, int D0, const float *mean,
+                            const float *components, int d, const float *inv_scale, float *Z,
+                            void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a3) LaREM Mahalanobis -- inference/postprocessors.py:228-244 (`MDLatentSpace.postprocess`):
+ *   out[n] = -(x_n - mu)^T P (x_n - mu).
+ * The symmetric precision is passed factored, P = sum_j sign_j w_j w_j^T (host: float64 eigen-
+ * decomposition, w_j = sqrt(|lambda_j|) v_j), so the score is a signed sum of squares of one
+ * contraction:  out[n] = -sum_j sign_j ((x_n - mu) . w_j)^2  -- no cancellation in the sum.
+ * (a7) ViM residual -- postprocessors.py:1082-1112: with Wt = NS^T, mu = u, sign = NULL and
+ * mode = RUNIA_ROWNORM_VIM:  out[n] = -alpha * sqrt(sum_j ((x_n-u).NS_j)^2) + logsumexp(logits[n,:]).
+ *   X     [N, d] float32;  mu [d] float32 (NULL = 0)
+ *   Wt    [r, d] float32  (row j = w_j, K-contiguous);  sign [r] float32 (+1/-1/0; NULL = all +1)
+ *   logits [N, C] float32 (ViM only), alpha (ViM only)
+ *   out_f64 / out_f32: exactly one non-NULL; the reference returns float64 for MD, float32 for ViM.
+ */
+#define RUNIA_ROWNORM_MD 0
+#define RUNIA_ROWNORM_VIM 1
+int runia_rownorm_score_f32(const float *X, int64_t N, int d, const float *mu, const float *Wt, int r,
+                            const float *sign, int mode, const float *logits, int C, float alpha,
+                            double *out_f64, float *out_f32, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a6) Class-conditional Mahalanobis -- inference/funcs.py:69-102 (`mahalanobis_postprocess`) and
+ * inference/postprocessors.py:320-357 (`cMDLatentSpace.postprocess`):
+ *   out[n] = max_c -(x_n - mu_c)^T P (x_n - mu_c), classes without samples skipped.
+ * With the same factorisation of P: y_n = (x_n - g) Wt^T, m_c = (mu_c - g) Wt^T (host, float64),
+ *   out[n] = max_c -sum_j sign_j (y_nj - m_cj)^2.
+ *   g [d] float32: any centre (the mean of the class means) -- keeps |y| small.
+ *   Mc [C, r] float32; class_valid [C] int32 (0 = class had no training samples -> skipped)
+ */
+int runia_classcond_mahalanobis_f32(const float *X, int64_t N, int d, const float *g, const float *Wt,
+                                    int r, const float *sign, const float *Mc, const int32_t *class_valid,
+                                    int C, double *out_f64, float *out_f32, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a9) DDU / GMM log-density -- inference/postprocessors.py:490-491, 783-784 with the mixture of
+ * inference/funcs.py:265-344:  out[n] = logsumexp_c log N(x_n; mu_c, Sigma_c).
+ *   At [C * dpad, d] float32: block c holds rows of A_c = L_c^{-1} (Sigma_c = L_c L_c^T), zero-
+ *        padded to dpad rows (dpad multiple of 128)
+ *   off [C * dpad] float32: A_c mu_c (zero in the padding);  logconst [C] float32:
+ *        -sum(log diag L_c) - d/2 log(2 pi)
+ */
+int runia_gmm_lse_f32(const float *X, int64_t N, int d, const float *At, const float *off, int dpad,
+                      const float *logconst, int C, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a5) kNN -- inference/postprocessors.py:385-423 (`KNNLatentSpace`), :825-883 (`KNN`),
+ * inference/funcs.py:105-115 (`normalizer`), faiss.IndexFlatL2.search.
+ *
+ * runia_normalize_rows: out = float32(x / (||x||_2 + 1e-10)), norm accumulated in float64 in a
+ *   fixed order (lane-interleaved partial sums + xor tree) so that the oracle reproduces it
+ *   bit for bit.
+ * runia_row_sqnorm_f32: out[n] = float32(sum_j x_nj^2) (float64 accumulation) -- the |b|^2 term
+ *   of the distance expansion; computed once per bank at setup.
+ * runia_knn_search_f32: for each query the k nearest bank rows under exact squared L2, total
+ *   order (distance, index).  Candidates come from a fused FP32 distance-GEMM + per-row
+ *   streaming top-KCAP filter (the Nq x Nb matrix never reaches HBM); candidates are re-ranked
+ *   with exact float64 distances (fixed summation order); a row whose top-k cannot be PROVEN
+ *   exact from the candidate bound (approximate distance of every non-candidate minus the
+ *   rounding bound exceeds the exact k-th distance) is recomputed by an exhaustive exact pass.
+ *   Outputs (any may be NULL):
+ *     out_dist     [Nq, k] float32 ascending (FLT_MAX padding when k > Nb, like faiss)
+ *     out_dist_f64 [Nq, k] float64 (the exact values before rounding; +inf padding)
+ *     out_idx      [Nq, k] int64 (-1 padding); idx_offset is added to every index (bank shards)
+ *     out_kth      [Nq]    float32 = out_dist[:, k-1]
+ *   status [4] int32 (device): [0] rows that took the exhaustive pass, [1] != 0 if that pass
+ *     overflowed its tie buffer (result invalid -> the host raises), [2..3] reserved.
+ *   workspace: runia_knn_workspace_bytes(Nq, Nb, d, k) bytes of device memory.  1 <= k <= 240.
+ * runia_topk_merge: merges R partial results ([R, Nq, k] float64 dist / int64 idx, each
+ *   ascending) into the global top-k under the same total order -- the step after the NCCL
+ *   all-gather when the bank is sharded across GPUs.
+ */
+int runia_normalize_rows(const void *in, int in_is_f64, int64_t N, int d, float *out, void *stream);
+int runia_row_sqnorm_f32(const float *X, int64_t N, int d, float *out, void *stream);
+int64_t runia_knn_workspace_bytes(int64_t Nq, int64_t Nb, int d, int k);
+int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn, const float *Bn_sqnorm, int64_t Nb,
+                         int d, int k, int64_t idx_offset, float *out_dist, double *out_dist_f64,
+                         int64_t *out_idx, float *out_kth, int32_t *status, void *workspace,
+                         int64_t workspace_bytes, void *stream);
+int runia_topk_merge(const double *part_dist, const int64_t *part_idx, int R, int64_t Nq, int k,
+                     float *out_dist, int64_t *out_idx, float *out_kth, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a4) LaRED Gaussian KDE -- inference/postprocessors.py:109-128, 165-178
+ * (sklearn KernelDensity(kernel="gaussian", bandwidth=h).score_samples):
+ *   out[n] = logsumexp_i(-|q_n - b_i|^2 / (2 h^2)) - log(Nb_total) - d/2 log(2 pi h^2)
+ * Fused distance-GEMM + online log-sum-exp.  For a bank shard pass partial outputs
+ * (out_max, out_sum) [Nq] float32 (running max m and sum of exp(t - m)) and combine over ranks;
+ * for a whole bank pass out_f64 and the total Nb.
+ *   workspace: runia_kde_workspace_bytes(Nq, Nb) bytes.
+ */
+int64_t runia_kde_workspace_bytes(int64_t Nq, int64_t Nb);
+int runia_kde_lse_f32(const float *Q, int64_t Nq, const float *B, int64_t Nb, int d, double bandwidth,
+                      int64_t Nb_total, double *out_f64, float *out_max, float *out_sum,
+                      void *workspace, int64_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a8) Logit-space scores in one pass -- inference/postprocessors.py:519-551 (Energy),
+ * :580-608 (MSP), :650-691 (GEN) + inference/funcs.py:347-375:
+ *   energy[n] = logsumexp(l_n); msp[n] = max softmax(l_n);
+ *   gen[n] = -sum_{top-M p} p^gamma (1-p)^gamma.     Any output may be NULL.  C <= 1024.
+ */
+int runia_logit_scores_f32(const float *logits, int64_t N, int C, float gamma, int M, float *energy,
+                           float *msp, float *gen, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (a10) ReAct / DICE / DICE+ReAct -- inference/postprocessors.py:1444-1474, 1325-1354, 1591-1621,
+ * inference/funcs.py:171-190:   out[n] = logsumexp_c( min(x_n, clip) . W_c + b_c )
+ * W is the (masked, for DICE) final linear layer [C, d]; clip = +inf disables ReAct.  C <= 64.
+ * ASH-S -- postprocessors.py:1192-1222 + funcs.py:230-261: keep the k_keep largest activations
+ * of each row, scale by exp(sum_all / sum_kept), then the same linear layer + logsumexp.
+ */
+int runia_clip_linear_lse_f32(const float *X, int64_t N, int d, const float *W, const float *b, int C,
+                              float clip, float *out, void *stream);
+int runia_ash_linear_lse_f32(const float *X, int64_t N, int d, const float *W, const float *b, int C,
+                             int k_keep, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RUNIA_B200_H */

@@ -197,41 +197,57 @@ def normalizer(x):
     return x / (np.linalg.norm(x, ord=2, axis=-1, keepdims=True) + 1e-10)
 
 
+def seq32_tree_sum(terms):
+    """Fixed-order float64 sum shared bit-for-bit with the CUDA kernels (csrc/common.cuh
+    `warp_tree_sum_f64`): term j goes to lane j % 32, every lane adds its terms in increasing j,
+    then the 32 partial sums are combined by an xor butterfly (16, 8, 4, 2, 1).  terms: [..., d]."""
+    t = np.asarray(terms, np.float64)
+    d = t.shape[-1]
+    pad = (-d) % 32
+    if pad:
+        t = np.concatenate([t, np.zeros(t.shape[:-1] + (pad,))], axis=-1)
+    t = t.reshape(t.shape[:-1] + (-1, 32))
+    p = np.zeros(t.shape[:-2] + (32,))
+    for c in range(t.shape[-2]):  # sequential per lane
+        p = p + t[..., c, :]
+    for off in (16, 8, 4, 2, 1):
+        p = p[..., :off] + p[..., off:2 * off]
+    return p[..., 0]
+
+
 def normalize_rows_exact(x):
-    """Deterministic row normaliser shared bit-for-bit with the CUDA path: the squared norm is
-    the SEQUENTIAL float64 sum of float64(x_i)^2 (no FMA), n = sqrt(.), and
-    x_hat = float32(float64(x) / (n + 1e-10)).  Differs from `normalizer` (float32 NumPy)
-    by at most 1 float32 ulp per element."""
-    x = np.ascontiguousarray(x)
-    xd = x.astype(np.float64)
-    sq = xd * xd
-    acc = np.zeros(x.shape[0], np.float64)
-    for j in range(x.shape[1]):  # sequential order, matches the kernel
-        acc = acc + sq[:, j]
-    return (xd / (np.sqrt(acc)[:, None] + 1e-10)).astype(np.float32)
+    """Deterministic row normaliser shared bit-for-bit with the CUDA path
+    (runia_normalize_rows): squared norm = seq32_tree_sum(float64(x)^2), n = sqrt(.),
+    x_hat = float32(float64(x) / (n + 1e-10)).  Differs from `normalizer` (float32 NumPy,
+    funcs.py:115) by at most 1 float32 ulp per element."""
+    xd = np.ascontiguousarray(x).astype(np.float64)
+    nrm = np.sqrt(seq32_tree_sum(xd * xd))
+    return (xd / (nrm[:, None] + 1e-10)).astype(np.float32)
 
 
-def flat_l2_search(bank_f32, queries_f32, k):
+def flat_l2_search_tree(bank_f32, queries_f32, k):
     """faiss.IndexFlatL2.search restated with a total order: exact squared L2 between float32
-    vectors evaluated as the SEQUENTIAL float64 sum of (float64(q_i)-float64(b_i))^2 (no FMA),
-    neighbours sorted by (distance, index) ascending; distances returned as float32;
-    FLT_MAX / -1 padding when k > ntotal (tests/unit_test_postprocessors.py:355-383)."""
+    vectors evaluated in float64 as seq32_tree_sum((q - b)^2) -- differences of float32 values
+    are exact in float64, each square is rounded once, the sum order is fixed -- neighbours
+    sorted by (distance, index) ascending; distances returned as float32; FLT_MAX / -1 padding
+    when k > ntotal (tests/unit_test_postprocessors.py:355-383)."""
     B = np.ascontiguousarray(bank_f32, np.float32).astype(np.float64)
     Q = np.ascontiguousarray(queries_f32, np.float32).astype(np.float64)
     nq, nb = Q.shape[0], B.shape[0]
     D = np.full((nq, k), FLT_MAX, np.float32)
     I = np.full((nq, k), -1, np.int64)
     kk = min(k, nb)
+    ar = np.arange(nb)
     for r in range(nq):
         diff = B - Q[r][None, :]
-        sq = diff * diff
-        acc = np.zeros(nb, np.float64)
-        for j in range(B.shape[1]):
-            acc = acc + sq[:, j]
-        order = np.lexsort((np.arange(nb), acc))[:kk]
+        acc = seq32_tree_sum(diff * diff)
+        order = np.lexsort((ar, acc))[:kk]
         D[r, :kk] = acc[order].astype(np.float32)
         I[r, :kk] = order
     return D, I
+
+
+flat_l2_search = flat_l2_search_tree
 
 
 def knn_score(test, bank_normed_f32, k):

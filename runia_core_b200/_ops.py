@@ -1,0 +1,419 @@
+"""Device-level operators: thin Python wrappers that allocate outputs (torch) and call the C ABI.
+Inputs and outputs are CUDA tensors; fitted state lives in small dataclasses that hold the
+device copies of what `setup()` computed on the host.  The reference-facing classes in
+`inference/postprocessors.py` and the free functions in `evaluation/entropy.py` /
+`dimensionality_reduction.py` are built on these; `bench.py` times them directly for the
+device-resident number."""
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._device import as_f32_rows, device, ptr, stream_ptr, to_device
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+def _empty(shape, dtype):
+    return torch.empty(shape, dtype=dtype, device=device())
+
+
+# ------------------------------------------------------------------------------------------
+# (a1) entropy
+# ------------------------------------------------------------------------------------------
+def entropy_k(n_mc: int) -> int:
+    """evaluation/entropy.py:66"""
+    return 5 if n_mc > 5 else n_mc - 1
+
+
+def mcd_entropy(z: torch.Tensor, n_mc: int, k: Optional[int] = None, want_joint: bool = True,
+                min_dist: float = 1e-5):
+    """z: [n_items * n_mc, D] float32 CUDA.  Returns (h_mvn [n_items] f64 or None, h_z [n_items, D] f64)."""
+    from scipy.special import digamma
+
+    assert z.is_cuda and z.dtype == torch.float32 and z.dim() == 2 and z.is_contiguous()
+    if k is None:
+        k = entropy_k(n_mc)
+    n_items = z.shape[0] // n_mc
+    D = z.shape[1]
+    h_z = _empty((n_items, D), torch.float64)
+    h_mvn = _empty((n_items,), torch.float64) if want_joint else None
+    c_term = float(-digamma(k) + digamma(n_mc))
+    _lib.call("runia_mcd_entropy_f32", z.data_ptr(), n_items, n_mc, D, k, float(min_dist), c_term,
+              h_z.data_ptr(), ptr(h_mvn), stream_ptr())
+    return h_mvn, h_z
+
+
+# ------------------------------------------------------------------------------------------
+# (a2) PCA projection
+# ------------------------------------------------------------------------------------------
+@dataclass
+class PCAState:
+    mean_f32: Optional[torch.Tensor]   # [D0]
+    mean_f64: Optional[torch.Tensor]   # [D0]
+    components: torch.Tensor           # [d, D0] f32
+    inv_scale: Optional[torch.Tensor]  # [d] f32 or None
+    d: int
+    D0: int
+
+
+def pca_prepare(mean, components, explained_variance, whiten) -> PCAState:
+    comp = np.ascontiguousarray(components, np.float64)
+    inv = None
+    if whiten:
+        scale = np.sqrt(np.asarray(explained_variance, np.float64))
+        eps = np.finfo(np.asarray(explained_variance).dtype).eps
+        scale = np.where(scale < eps, eps, scale)
+        inv = to_device((1.0 / scale).astype(np.float32))
+    m64 = None if mean is None else to_device(np.asarray(mean, np.float64).reshape(-1))
+    m32 = None if mean is None else m64.to(torch.float32)
+    return PCAState(m32, m64, to_device(comp.astype(np.float32)), inv, comp.shape[0], comp.shape[1])
+
+
+def pca_transform(x, st: PCAState) -> torch.Tensor:
+    xf, centered = as_f32_rows(x, st.mean_f64)
+    n = xf.shape[0]
+    z = _empty((n, st.d), torch.float32)
+    _lib.call("runia_pca_transform_f32", xf.data_ptr(), n, st.D0, None if centered else ptr(st.mean_f32),
+              st.components.data_ptr(), st.d, ptr(st.inv_scale), z.data_ptr(), stream_ptr())
+    return z
+
+
+# ------------------------------------------------------------------------------------------
+# (a3) LaREM Mahalanobis / (a6) class-conditional Mahalanobis: factor the precision once
+# ------------------------------------------------------------------------------------------
+def factor_precision(precision):
+    """P (symmetric, float64) -> (Wt [r, d] float64, sign [r]) with P = sum_j sign_j w_j w_j^T.
+    Eigenvalues below 1e-14 * max|lambda| are rounding residue of pinvh's rank cut and get
+    sign 0."""
+    P = np.asarray(precision, np.float64)
+    P = 0.5 * (P + P.T)
+    lam, V = np.linalg.eigh(P)
+    amax = np.abs(lam).max() if lam.size else 0.0
+    sign = np.sign(lam)
+    sign[np.abs(lam) <= 1e-14 * amax] = 0.0
+    keep = sign != 0
+    if not keep.any():
+        keep[:1] = True
+    Wt = (V[:, keep] * np.sqrt(np.abs(lam[keep]))).T
+    return np.ascontiguousarray(Wt), sign[keep]
+
+
+@dataclass
+class MDState:
+    mu_f32: torch.Tensor
+    mu_f64: torch.Tensor
+    Wt: torch.Tensor
+    sign: Optional[torch.Tensor]
+    d: int
+    r: int
+
+
+def md_prepare(mean, precision) -> MDState:
+    Wt, sign = factor_precision(precision)
+    mu64 = to_device(np.asarray(mean, np.float64).reshape(-1))
+    sg = None if np.all(sign == 1.0) else to_device(sign.astype(np.float32))
+    return MDState(mu64.to(torch.float32), mu64, to_device(Wt.astype(np.float32)), sg, Wt.shape[1], Wt.shape[0])
+
+
+def md_score(x, st: MDState, out_dtype=torch.float64) -> torch.Tensor:
+    xf, centered = as_f32_rows(x, st.mu_f64)
+    n = xf.shape[0]
+    out = _empty((n,), out_dtype)
+    o64 = out.data_ptr() if out_dtype == torch.float64 else None
+    o32 = out.data_ptr() if out_dtype == torch.float32 else None
+    _lib.call("runia_rownorm_score_f32", xf.data_ptr(), n, st.d, None if centered else st.mu_f32.data_ptr(),
+              st.Wt.data_ptr(), st.r, ptr(st.sign), _lib.ROWNORM_MD, None, 0, 0.0, o64, o32, stream_ptr())
+    return out
+
+
+@dataclass
+class VimState:
+    u_f32: torch.Tensor
+    u_f64: torch.Tensor
+    NSt: torch.Tensor  # [r, d]
+    alpha: float
+    d: int
+    r: int
+
+
+def vim_prepare(u, NS, alpha) -> VimState:
+    u64 = to_device(np.asarray(u, np.float64).reshape(-1))
+    NSt = np.ascontiguousarray(np.asarray(NS, np.float64).T.astype(np.float32))
+    return VimState(u64.to(torch.float32), u64, to_device(NSt), float(alpha), NSt.shape[1], NSt.shape[0])
+
+
+def vim_score(x, logits, st: VimState) -> torch.Tensor:
+    xf, centered = as_f32_rows(x, st.u_f64)
+    lg = to_device(logits, torch.float32)
+    n = xf.shape[0]
+    out = _empty((n,), torch.float32)
+    _lib.call("runia_rownorm_score_f32", xf.data_ptr(), n, st.d, None if centered else st.u_f32.data_ptr(),
+              st.NSt.data_ptr(), st.r, None, _lib.ROWNORM_VIM, lg.data_ptr(), lg.shape[1], st.alpha,
+              None, out.data_ptr(), stream_ptr())
+    return out
+
+
+def residual_norm(x, st: VimState) -> torch.Tensor:
+    """||(x - u) NS||_2 per row (used by ViM.setup for alpha, postprocessors.py:1072)."""
+    xf, centered = as_f32_rows(x, st.u_f64)
+    n = xf.shape[0]
+    out = _empty((n,), torch.float32)
+    _lib.call("runia_rownorm_score_f32", xf.data_ptr(), n, st.d, None if centered else st.u_f32.data_ptr(),
+              st.NSt.data_ptr(), st.r, None, _lib.ROWNORM_MD, None, 0, 0.0, None, out.data_ptr(), stream_ptr())
+    return torch.sqrt(torch.clamp(-out, min=0))
+
+
+@dataclass
+class ClassCondState:
+    g_f32: torch.Tensor
+    g_f64: torch.Tensor
+    Wt: torch.Tensor
+    sign: Optional[torch.Tensor]
+    Mc: torch.Tensor
+    valid: torch.Tensor
+    C: int
+    d: int
+    r: int
+
+
+def classcond_prepare(class_mean, precision) -> ClassCondState:
+    cm = np.asarray(class_mean, np.float64)
+    valid = ~np.isnan(cm).any(axis=1)
+    Wt, sign = factor_precision(precision)
+    g = cm[valid].mean(0) if valid.any() else np.zeros(cm.shape[1])
+    Mc = np.zeros((cm.shape[0], Wt.shape[0]))
+    Mc[valid] = (cm[valid] - g) @ Wt.T
+    g64 = to_device(g)
+    sg = None if np.all(sign == 1.0) else to_device(sign.astype(np.float32))
+    return ClassCondState(g64.to(torch.float32), g64, to_device(Wt.astype(np.float32)), sg,
+                          to_device(Mc.astype(np.float32)), to_device(valid.astype(np.int32)),
+                          cm.shape[0], Wt.shape[1], Wt.shape[0])
+
+
+def classcond_score(x, st: ClassCondState, out_dtype=torch.float64) -> torch.Tensor:
+    xf, centered = as_f32_rows(x, st.g_f64)
+    n = xf.shape[0]
+    out = _empty((n,), out_dtype)
+    o64 = out.data_ptr() if out_dtype == torch.float64 else None
+    o32 = out.data_ptr() if out_dtype == torch.float32 else None
+    _lib.call("runia_classcond_mahalanobis_f32", xf.data_ptr(), n, st.d, None if centered else st.g_f32.data_ptr(),
+              st.Wt.data_ptr(), st.r, ptr(st.sign), st.Mc.data_ptr(), st.valid.data_ptr(), st.C, o64, o32,
+              stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# (a9) GMM / DDU
+# ------------------------------------------------------------------------------------------
+@dataclass
+class GMMState:
+    At: torch.Tensor        # [C * dpad, d]
+    off: torch.Tensor       # [C * dpad]
+    logconst: torch.Tensor  # [C]
+    C: int
+    d: int
+    dpad: int
+
+
+def gmm_prepare(means, scale_tril) -> GMMState:
+    """means [C, d], scale_tril [C, d, d] (lower Cholesky factors) -> whitening blocks."""
+    from scipy.linalg import solve_triangular
+
+    mu = np.asarray(means, np.float64)
+    L = np.asarray(scale_tril, np.float64)
+    C, d = mu.shape
+    dpad = (d + 127) // 128 * 128
+    At = np.zeros((C, dpad, d))
+    off = np.zeros((C, dpad))
+    logconst = np.empty(C)
+    eye = np.eye(d)
+    for c in range(C):
+        A = solve_triangular(L[c], eye, lower=True)  # L^{-1}
+        At[c, :d] = A
+        off[c, :d] = A @ mu[c]
+        logconst[c] = -np.log(np.diag(L[c])).sum() - 0.5 * d * np.log(2 * np.pi)
+    return GMMState(to_device(At.reshape(C * dpad, d).astype(np.float32)),
+                    to_device(off.reshape(-1).astype(np.float32)),
+                    to_device(logconst.astype(np.float32)), C, d, dpad)
+
+
+def gmm_lse(x, st: GMMState) -> torch.Tensor:
+    xf, _ = as_f32_rows(x, None)
+    n = xf.shape[0]
+    out = _empty((n,), torch.float32)
+    _lib.call("runia_gmm_lse_f32", xf.data_ptr(), n, st.d, st.At.data_ptr(), st.off.data_ptr(), st.dpad,
+              st.logconst.data_ptr(), st.C, out.data_ptr(), stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# (a5) kNN
+# ------------------------------------------------------------------------------------------
+def normalize_rows(x) -> torch.Tensor:
+    t = to_device(x)
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float32)
+    if t.dim() == 1:
+        t = t.reshape(1, -1)
+    n, d = t.shape
+    out = _empty((n, d), torch.float32)
+    _lib.call("runia_normalize_rows", t.data_ptr(), 1 if t.dtype == torch.float64 else 0, n, d,
+              out.data_ptr(), stream_ptr())
+    return out
+
+
+def row_sqnorm(x: torch.Tensor) -> torch.Tensor:
+    out = _empty((x.shape[0],), torch.float32)
+    _lib.call("runia_row_sqnorm_f32", x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(), stream_ptr())
+    return out
+
+
+@dataclass
+class KNNBank:
+    bank: torch.Tensor    # [Nb, d] float32, already normalised
+    sqnorm: torch.Tensor  # [Nb]
+    idx_offset: int = 0
+
+
+def knn_bank(bank_normed: torch.Tensor, idx_offset: int = 0) -> KNNBank:
+    return KNNBank(bank_normed, row_sqnorm(bank_normed), idx_offset)
+
+
+class KNNOverflow(RuntimeError):
+    pass
+
+
+def knn_search(qn: torch.Tensor, bank: KNNBank, k: int, want_idx=True, want_dist=True, want_f64=False,
+               check_status=True):
+    """qn: [Nq, d] normalised float32 CUDA.  Returns dict(dist [Nq,k] f32, dist64, idx [Nq,k] i64,
+    kth [Nq] f32, exhaustive_rows int)."""
+    nq, d = qn.shape
+    nb = bank.bank.shape[0]
+    res = {"dist": None, "dist64": None, "idx": None, "kth": _empty((nq,), torch.float32), "exhaustive_rows": 0}
+    if want_dist:
+        res["dist"] = _empty((nq, k), torch.float32)
+    if want_f64:
+        res["dist64"] = _empty((nq, k), torch.float64)
+    if want_idx:
+        res["idx"] = _empty((nq, k), torch.int64)
+    if nq == 0:
+        return res
+    ws_bytes = int(_lib.raw("runia_knn_workspace_bytes")(nq, nb, d, k))
+    if ws_bytes <= 0:
+        raise NotImplementedError(f"kNN: k={k} outside [1, 240]")
+    ws = _empty((ws_bytes,), torch.uint8)
+    status = _empty((4,), torch.int32)
+    _lib.call("runia_knn_search_f32", qn.data_ptr(), nq, bank.bank.data_ptr(), bank.sqnorm.data_ptr(), nb, d, k,
+              bank.idx_offset, ptr(res["dist"]), ptr(res["dist64"]), ptr(res["idx"]), res["kth"].data_ptr(),
+              status.data_ptr(), ws.data_ptr(), ws_bytes, stream_ptr())
+    if check_status:
+        st = status.cpu()
+        res["exhaustive_rows"] = int(st[0])
+        if int(st[1]) != 0:
+            raise KNNOverflow("kNN exhaustive pass overflowed its tie buffer (more than 4096 bank rows tie "
+                              "with the k-th neighbour)")
+    return res
+
+
+def topk_merge(part_dist64: torch.Tensor, part_idx: torch.Tensor):
+    """[R, Nq, k] partial lists -> (dist [Nq,k] f32, idx [Nq,k] i64, kth [Nq] f32)."""
+    R, nq, k = part_dist64.shape
+    dist = _empty((nq, k), torch.float32)
+    idx = _empty((nq, k), torch.int64)
+    kth = _empty((nq,), torch.float32)
+    _lib.call("runia_topk_merge", part_dist64.data_ptr(), part_idx.data_ptr(), R, nq, k, dist.data_ptr(),
+              idx.data_ptr(), kth.data_ptr(), stream_ptr())
+    return dist, idx, kth
+
+
+# ------------------------------------------------------------------------------------------
+# (a4) KDE
+# ------------------------------------------------------------------------------------------
+@dataclass
+class KDEBank:
+    bank: torch.Tensor      # [Nb, d] float32, centred by `center`
+    center: torch.Tensor    # [d] float64
+    bandwidth: float
+    n_total: int
+
+
+def kde_bank(train, bandwidth=1.0, center=None, n_total=None) -> KDEBank:
+    t = to_device(train)
+    if center is None:
+        center = t.to(torch.float64).mean(0)  # fit-time statistic (setup), any centre is valid
+    c = to_device(center, torch.float64)
+    n, d = t.shape
+    out = _empty((n, d), torch.float32)
+    _lib.call("runia_center_cast", t.data_ptr(), 1 if t.dtype == torch.float64 else 0, n, d, c.data_ptr(),
+              out.data_ptr(), stream_ptr())
+    return KDEBank(out, c, float(bandwidth), int(n_total if n_total is not None else n))
+
+
+def _kde_stage_queries(q, kb: KDEBank):
+    t = to_device(q)
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float32)
+    n, d = t.shape
+    out = _empty((n, d), torch.float32)
+    _lib.call("runia_center_cast", t.data_ptr(), 1 if t.dtype == torch.float64 else 0, n, d,
+              kb.center.data_ptr(), out.data_ptr(), stream_ptr())
+    return out
+
+
+def kde_score(q, kb: KDEBank, partial=False):
+    """log-density of each query under the Gaussian KDE of the bank (float64), or the partial
+    (max, sum) pair for a bank shard."""
+    qc = _kde_stage_queries(q, kb)
+    nq, d = qc.shape
+    nb = kb.bank.shape[0]
+    ws_bytes = int(_lib.raw("runia_kde_workspace_bytes")(nq, nb)) if nq else 0
+    ws = _empty((max(ws_bytes, 1),), torch.uint8)
+    if partial:
+        m = _empty((nq,), torch.float32)
+        s = _empty((nq,), torch.float32)
+        _lib.call("runia_kde_lse_f32", qc.data_ptr(), nq, kb.bank.data_ptr(), nb, d, kb.bandwidth, kb.n_total,
+                  None, m.data_ptr(), s.data_ptr(), ws.data_ptr(), ws_bytes, stream_ptr())
+        return m, s
+    out = _empty((nq,), torch.float64)
+    _lib.call("runia_kde_lse_f32", qc.data_ptr(), nq, kb.bank.data_ptr(), nb, d, kb.bandwidth, kb.n_total,
+              out.data_ptr(), None, None, ws.data_ptr(), ws_bytes, stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# (a8) logit scores, (a10) clip-linear-LSE / ASH
+# ------------------------------------------------------------------------------------------
+def logit_scores(logits, gamma=0.1, M=None, energy=True, msp=True, gen=True):
+    lg = to_device(logits)
+    in_dtype = lg.dtype
+    lg = lg.to(torch.float32) if lg.dtype != torch.float32 else lg
+    n, C = lg.shape
+    if M is None:
+        M = C
+    e = _empty((n,), torch.float32) if energy else None
+    m = _empty((n,), torch.float32) if msp else None
+    g = _empty((n,), torch.float32) if gen else None
+    _lib.call("runia_logit_scores_f32", lg.data_ptr(), n, C, float(gamma), int(M), ptr(e), ptr(m), ptr(g),
+              stream_ptr())
+    return e, m, g, in_dtype
+
+
+def clip_linear_lse(x, W: torch.Tensor, b: torch.Tensor, clip=float("inf")) -> torch.Tensor:
+    xf, _ = as_f32_rows(x, None)
+    n, d = xf.shape
+    out = _empty((n,), torch.float32)
+    _lib.call("runia_clip_linear_lse_f32", xf.data_ptr(), n, d, W.data_ptr(), b.data_ptr(), W.shape[0],
+              float(clip), out.data_ptr(), stream_ptr())
+    return out
+
+
+def ash_linear_lse(x, W: torch.Tensor, b: torch.Tensor, k_keep: int) -> torch.Tensor:
+    xf, _ = as_f32_rows(x, None)
+    n, d = xf.shape
+    out = _empty((n,), torch.float32)
+    _lib.call("runia_ash_linear_lse_f32", xf.data_ptr(), n, d, W.data_ptr(), b.data_ptr(), W.shape[0],
+              int(k_keep), out.data_ptr(), stream_ptr())
+    return out

@@ -1,0 +1,705 @@
+// kNN (a5) and Gaussian-KDE (a4) scorers: fused FP32 distance-GEMM + per-row streaming
+// top-k / online log-sum-exp.  The [Nq, Nb] distance matrix never reaches HBM.
+//
+// kNN exactness contract (SURVEY section 8a5 / DESIGN.md "kNN"): the fused pass only PROPOSES
+// candidates; every reported neighbour is re-ranked with float64 distances accumulated in a
+// fixed order that the oracle replays bit for bit, ties broken by index, and a row is accepted
+// only when the bound "approximate distance of any rejected bank row - eps > exact k-th
+// distance" proves that no rejected row could belong to the top-k.  Rows that fail the proof
+// (near-duplicates at rank k) go through an exhaustive exact pass.
+#include <algorithm>
+
+#include "rowgemm.cuh"
+
+namespace runia {
+
+// --------------------------------------------------------------------------------------------
+// fixed-order float64 reductions shared with the oracle (oracle_np.seq32_tree_sum)
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ double exact_sqdist_warp(const float *__restrict__ a, const float *__restrict__ b,
+                                                    int d, int lane) {
+  double p = 0.0;
+  for (int j = lane; j < d; j += 32) {
+    const double df = __dsub_rn((double)a[j], (double)b[j]);
+    p = __dadd_rn(p, __dmul_rn(df, df));
+  }
+  return warp_tree_sum_f64(p);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const T *__restrict__ in, int64_t N, int d,
+                                                             float *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const T *x = in + row * (int64_t)d;
+  double p = 0.0;
+  for (int j = lane; j < d; j += 32) {
+    const double v = (double)x[j];
+    p = __dadd_rn(p, __dmul_rn(v, v));
+  }
+  const double nrm = __dadd_rn(__dsqrt_rn(warp_tree_sum_f64(p)), 1e-10);
+  float *o = out + row * (int64_t)d;
+  for (int j = lane; j < d; j += 32) o[j] = (float)__ddiv_rn((double)x[j], nrm);
+}
+
+__global__ void __launch_bounds__(256) row_sqnorm_kernel(const float *__restrict__ X, int64_t N, int d,
+                                                         float *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const float *x = X + row * (int64_t)d;
+  double p = 0.0;
+  for (int j = lane; j < d; j += 32) {
+    const double v = (double)x[j];
+    p = fma(v, v, p);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
+  if (lane == 0) out[row] = (float)p;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) center_cast_kernel(const T *__restrict__ in, int64_t total, int d,
+                                                          const double *__restrict__ center,
+                                                          float *__restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int j = (int)(e % d);
+    if (sizeof(T) == 8) {
+      const double v = (double)in[e];
+      out[e] = (float)(center ? v - center[j] : v);
+    } else {
+      // float32 input: the reference subtracts a float32 mean in float32 (postprocessors.py:241)
+      const float v = (float)in[e];
+      out[e] = center ? v - (float)center[j] : v;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// warp-level bitonic sort of (key, idx) pairs in shared memory, ascending lexicographic order
+// --------------------------------------------------------------------------------------------
+template <typename KT, typename IT>
+__device__ __forceinline__ void warp_bitonic_sort(KT *key, IT *idx, int n /* power of two */) {
+  const int lane = threadIdx.x & 31;
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (n >> 1); t += 32) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i | j;
+        const bool asc = ((i & k) == 0);
+        const KT ka = key[i], kb = key[p];
+        const IT ia = idx[i], ib = idx[p];
+        const bool gt = (ka > kb) || (ka == kb && ia > ib);
+        if (gt == asc) {
+          key[i] = kb; key[p] = ka;
+          idx[i] = ib; idx[p] = ia;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// kNN stage 1: fused distance GEMM + streaming top-KCAP candidate filter
+// --------------------------------------------------------------------------------------------
+constexpr int KNN_SORT_MAX = 512;  // largest per-row candidate buffer (entries)
+
+struct KnnPlan {
+  int kcap;    // candidates kept per (row, split): power of two >= k + 8
+  int capp;    // buffer entries per (row, split): power of two, >= kcap + BN
+  int splits;  // bank splits (grid.y)
+  int64_t panels_per_split;
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+knn_candidates_kernel(const float *__restrict__ Q, const float *__restrict__ qn, int64_t Nq,
+                      const float *__restrict__ B, const float *__restrict__ bn, int64_t Nb, int d,
+                      KnnPlan plan, float *__restrict__ buf_d, int32_t *__restrict__ buf_i) {
+  __shared__ GemmSmem sm;
+  __shared__ float thr[BM];
+  __shared__ int cnt[BM];
+  extern __shared__ unsigned char dyn[];  // per-warp sort scratch: 8 x capp x (float + int)
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int split = blockIdx.y;
+  const int capp = plan.capp, kcap = plan.kcap;
+  const int trigger = capp - BN;
+  float *skey = reinterpret_cast<float *>(dyn) + (size_t)warp * capp;
+  int32_t *sidx = reinterpret_cast<int32_t *>(dyn + (size_t)8 * capp * sizeof(float)) + (size_t)warp * capp;
+
+  if (threadIdx.x < BM) {
+    thr[threadIdx.x] = INFINITY;
+    cnt[threadIdx.x] = 0;
+  }
+  const Prologue pro{nullptr, INFINITY};
+  float qnr[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t row = m0 + tile_row(ty, i);
+    qnr[i] = row < Nq ? __ldg(qn + row) : 0.f;
+  }
+  const int64_t b_lo = (int64_t)split * plan.panels_per_split * BN;
+  int64_t b_hi = b_lo + plan.panels_per_split * BN;
+  if (b_hi > Nb) b_hi = Nb;
+
+  auto row_buf = [&](int r) -> size_t { return ((size_t)(m0 + r) * plan.splits + split) * capp; };
+  // one warp compacts one row: sort the buffer, keep the kcap smallest, tighten the threshold
+  auto compact = [&](int r, bool final_pass) {
+    const int n = cnt[r];
+    const size_t base = row_buf(r);
+    for (int e = lane; e < capp; e += 32) {
+      skey[e] = e < n ? buf_d[base + e] : INFINITY;
+      sidx[e] = e < n ? buf_i[base + e] : 0x7fffffff;
+    }
+    __syncwarp();
+    warp_bitonic_sort(skey, sidx, capp);
+    const int keep = n < kcap ? n : kcap;
+    const int wr = final_pass ? kcap : keep;
+    for (int e = lane; e < wr; e += 32) {
+      buf_d[base + e] = skey[e];
+      buf_i[base + e] = e < keep ? sidx[e] : -1;
+    }
+    if (lane == 0) {
+      cnt[r] = keep;
+      if (keep == kcap) thr[r] = skey[kcap - 1];
+    }
+    __syncwarp();
+  };
+
+  for (int64_t n0 = b_lo; n0 < b_hi; n0 += BN) {
+    float acc[8][8];
+    zero_acc(acc);
+    gemm_mainloop(Q, Nq, m0, B, b_hi, n0, d, pro, sm, acc);  // rows >= b_hi read as zero
+    float bnr[8];
+    int64_t colj[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      colj[j] = n0 + tile_col(tx, j);
+      bnr[j] = colj[j] < b_hi ? __ldg(bn + colj[j]) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = tile_row(ty, i);
+      if (m0 + r >= Nq) continue;
+      const float th = thr[r];
+      const size_t base = row_buf(r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dist = fmaf(-2.f, acc[i][j], qnr[i] + bnr[j]);
+        if (colj[j] < b_hi && dist < th) {
+          const int pos = atomicAdd(&cnt[r], 1);
+          buf_d[base + pos] = dist;
+          buf_i[base + pos] = (int32_t)colj[j];
+        }
+      }
+    }
+    __syncthreads();
+    for (int r = warp; r < BM; r += 8)
+      if (cnt[r] > trigger) compact(r, false);
+    // the next gemm_mainloop starts with __syncthreads(): thr/cnt updates are visible
+  }
+  __syncthreads();
+  for (int r = warp; r < BM; r += 8)
+    if (m0 + r < Nq) compact(r, true);
+}
+
+// --------------------------------------------------------------------------------------------
+// kNN stage 2: merge the per-split candidate lists, exact float64 re-rank, certification
+// --------------------------------------------------------------------------------------------
+struct KnnRerankArgs {
+  const float *Q, *B;
+  int64_t Nq, Nb;
+  int d, k;
+  KnnPlan plan;
+  const float *buf_d;
+  const int32_t *buf_i;
+  float eps;
+  int64_t idx_offset;
+  float *out_dist;
+  double *out_dist64;
+  int64_t *out_idx;
+  float *out_kth;
+  int32_t *flag_count;   // [1]
+  int32_t *flag_rows;    // [Nq]
+  double *flag_T;        // [Nq] exact k-th distance among candidates
+  int32_t *flag_I;       // [Nq] its index
+};
+
+constexpr int RERANK_WARPS = 4;
+
+__global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerankArgs a) {
+  extern __shared__ unsigned char dyn[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * RERANK_WARPS + warp;
+  if (row >= a.Nq) return;
+  const int kcap = a.plan.kcap, S = a.plan.splits, capp = a.plan.capp;
+  int msz = 1;
+  while (msz < S * kcap) msz <<= 1;
+  // per-warp scratch: approx keys/idx [msz], exact keys [kcap] + idx [kcap]
+  const size_t per_warp = (size_t)msz * 8 + (size_t)kcap * 12;
+  unsigned char *base = dyn + (size_t)warp * ((per_warp + 15) / 16 * 16);
+  float *akey = reinterpret_cast<float *>(base);
+  int32_t *aidx = reinterpret_cast<int32_t *>(base + (size_t)msz * 4);
+  double *ekey = reinterpret_cast<double *>(base + (size_t)msz * 8);
+  int32_t *eidx = reinterpret_cast<int32_t *>(base + (size_t)msz * 8 + (size_t)kcap * 8);
+
+  for (int e = lane; e < msz; e += 32) {
+    float kd = INFINITY;
+    int32_t ki = 0x7fffffff;
+    if (e < S * kcap) {
+      const int s = e / kcap, c = e % kcap;
+      const size_t p = ((size_t)row * S + s) * capp + c;
+      const int32_t ii = a.buf_i[p];
+      if (ii >= 0) {
+        kd = a.buf_d[p];
+        ki = ii;
+      }
+    }
+    akey[e] = kd;
+    aidx[e] = ki;
+  }
+  __syncwarp();
+  if (S > 1) warp_bitonic_sort(akey, aidx, msz);  // single split: already sorted
+  int n_real = 0;
+  for (int e = lane; e < kcap; e += 32) n_real += (aidx[e] != 0x7fffffff) ? 1 : 0;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) n_real += __shfl_xor_sync(0xffffffffu, n_real, off);
+  // lower bound on the approximate distance of every bank row that is NOT a candidate
+  const bool list_full = (n_real == kcap);
+  const float L = list_full ? akey[kcap - 1] : INFINITY;
+
+  const float *q = a.Q + row * (int64_t)a.d;
+  for (int c = 0; c < kcap; ++c) {
+    const int32_t bi = aidx[c];
+    double ex = INFINITY;
+    if (bi != 0x7fffffff) ex = exact_sqdist_warp(q, a.B + (int64_t)bi * a.d, a.d, lane);
+    if (lane == 0) {
+      ekey[c] = ex;
+      eidx[c] = bi;
+    }
+  }
+  __syncwarp();
+  warp_bitonic_sort(ekey, eidx, kcap);
+
+  const int k = a.k;
+  for (int e = lane; e < k; e += 32) {
+    const bool real = e < n_real;
+    const double dv = real ? ekey[e] : (double)INFINITY;
+    if (a.out_dist) a.out_dist[row * k + e] = real ? (float)dv : FLT_MAX;
+    if (a.out_dist64) a.out_dist64[row * k + e] = dv;
+    if (a.out_idx) a.out_idx[row * k + e] = real ? (int64_t)eidx[e] + a.idx_offset : -1;
+  }
+  if (lane == 0) {
+    const bool have_k = n_real >= k;
+    if (a.out_kth) a.out_kth[row] = have_k ? (float)ekey[k - 1] : FLT_MAX;
+    // all bank rows are candidates when the merged list is not full
+    bool certified = !list_full;
+    if (list_full) certified = ((double)L - (double)a.eps > ekey[k - 1]);
+    if (!certified) {
+      const int slot = atomicAdd(a.flag_count, 1);
+      a.flag_rows[slot] = (int32_t)row;
+      a.flag_T[slot] = ekey[k - 1];
+      a.flag_I[slot] = eidx[k - 1];
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// kNN stage 3: exhaustive exact pass for rows whose result could not be certified.
+// Every true neighbour satisfies (dist, idx) <= (T, I) lexicographically, where (T, I) is the
+// exact k-th candidate; collect those pairs, sort, emit the first k.
+// --------------------------------------------------------------------------------------------
+constexpr int FB_CAP = 4096;
+
+__global__ void __launch_bounds__(256) knn_fallback_kernel(KnnRerankArgs a, int32_t *status,
+                                                           double *fb_d, int32_t *fb_i) {
+  __shared__ int n_hit;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_flag = *a.flag_count;
+  for (int f = blockIdx.x; f < n_flag; f += gridDim.x) {
+    const int64_t row = a.flag_rows[f];
+    const double T = a.flag_T[f];
+    const int32_t I = a.flag_I[f];
+    double *hd = fb_d + (size_t)blockIdx.x * FB_CAP;
+    int32_t *hi = fb_i + (size_t)blockIdx.x * FB_CAP;
+    if (threadIdx.x == 0) n_hit = 0;
+    __syncthreads();
+    const float *q = a.Q + row * (int64_t)a.d;
+    for (int64_t b = warp; b < a.Nb; b += 8) {
+      const double ex = exact_sqdist_warp(q, a.B + b * a.d, a.d, lane);
+      if (lane == 0 && (ex < T || (ex == T && (int32_t)b <= I))) {
+        const int pos = atomicAdd(&n_hit, 1);
+        if (pos < FB_CAP) {
+          hd[pos] = ex;
+          hi[pos] = (int32_t)b;
+        }
+      }
+    }
+    __syncthreads();
+    const int n = n_hit;
+    if (n > FB_CAP) {
+      if (threadIdx.x == 0) atomicExch(&status[1], 1);
+    } else {
+      // selection by rank: entry e goes to position #(pairs smaller than it); n is small
+      for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const double de = hd[e];
+        const int32_t ie = hi[e];
+        int rank = 0;
+        for (int o = 0; o < n; ++o) {
+          const double dd = hd[o];
+          const int32_t io = hi[o];
+          rank += (dd < de || (dd == de && io < ie)) ? 1 : 0;
+        }
+        if (rank < a.k) {
+          if (a.out_dist) a.out_dist[row * a.k + rank] = (float)de;
+          if (a.out_dist64) a.out_dist64[row * a.k + rank] = de;
+          if (a.out_idx) a.out_idx[row * a.k + rank] = (int64_t)ie + a.idx_offset;
+          if (rank == a.k - 1 && a.out_kth) a.out_kth[row] = (float)de;
+        }
+      }
+    }
+    if (threadIdx.x == 0) atomicAdd(&status[0], 1);
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// merge of R sorted partial top-k lists (bank sharded across GPUs)
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) topk_merge_kernel(const double *__restrict__ pd,
+                                                         const int64_t *__restrict__ pi, int R, int64_t Nq,
+                                                         int k, float *out_dist, int64_t *out_idx,
+                                                         float *out_kth) {
+  // one thread per query row: R-way merge by head pointers (R <= 16, k <= 240)
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= Nq) return;
+  int head[16];
+  for (int r = 0; r < R; ++r) head[r] = 0;
+  for (int e = 0; e < k; ++e) {
+    int best = -1;
+    double bd = INFINITY;
+    int64_t bi = -1;
+    for (int r = 0; r < R; ++r) {
+      if (head[r] >= k) continue;
+      const size_t p = ((size_t)r * Nq + row) * k + head[r];
+      const int64_t ii = pi[p];
+      if (ii < 0) continue;  // padding: this list is exhausted
+      const double dd = pd[p];
+      if (best < 0 || dd < bd || (dd == bd && ii < bi)) {
+        best = r;
+        bd = dd;
+        bi = ii;
+      }
+    }
+    if (best >= 0) head[best]++;
+    if (out_dist) out_dist[row * k + e] = best >= 0 ? (float)bd : FLT_MAX;
+    if (out_idx) out_idx[row * k + e] = best >= 0 ? bi : -1;
+    if (e == k - 1 && out_kth) out_kth[row] = best >= 0 ? (float)bd : FLT_MAX;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// (a4) KDE: fused distance GEMM + online log-sum-exp
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+kde_partial_kernel(const float *__restrict__ Q, const float *__restrict__ qn, int64_t Nq,
+                   const float *__restrict__ B, const float *__restrict__ bn, int64_t Nb, int d,
+                   float neg_half_inv_h2_log2e, int splits, int64_t panels_per_split,
+                   float *__restrict__ part_m, float *__restrict__ part_s) {
+  __shared__ GemmSmem sm;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int split = blockIdx.y;
+  const Prologue pro{nullptr, INFINITY};
+  float qnr[8], rm[8], rs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t row = m0 + tile_row(ty, i);
+    qnr[i] = row < Nq ? __ldg(qn + row) : 0.f;
+    rm[i] = -INFINITY;
+    rs[i] = 0.f;
+  }
+  const int64_t b_lo = (int64_t)split * panels_per_split * BN;
+  int64_t b_hi = b_lo + panels_per_split * BN;
+  if (b_hi > Nb) b_hi = Nb;
+  for (int64_t n0 = b_lo; n0 < b_hi; n0 += BN) {
+    float acc[8][8];
+    zero_acc(acc);
+    gemm_mainloop(Q, Nq, m0, B, b_hi, n0, d, pro, sm, acc);
+    float bnr[8];
+    bool ok[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t col = n0 + tile_col(tx, j);
+      ok[j] = col < b_hi;
+      bnr[j] = ok[j] ? __ldg(bn + col) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t[8];
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        // squared distance, clamped at 0 (the expansion can go slightly negative)
+        const float dist = fmaxf(fmaf(-2.f, acc[i][j], qnr[i] + bnr[j]), 0.f);
+        t[j] = ok[j] ? dist * neg_half_inv_h2_log2e : -INFINITY;  // log2 units
+        tmax = fmaxf(tmax, t[j]);
+      }
+      if (tmax == -INFINITY) continue;
+      const float m_new = fmaxf(rm[i], tmax);
+      float s = rs[i] * exp2f(rm[i] - m_new);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += exp2f(t[j] - m_new);
+      rs[i] = s;
+      rm[i] = m_new;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float M = warp_max16(rm[i]);
+    const float s = (rm[i] == -INFINITY) ? 0.f : rs[i] * exp2f(rm[i] - M);
+    const float S = warp_sum16(s);
+    const int64_t row = m0 + tile_row(ty, i);
+    if (tx == 0 && row < Nq) {
+      part_m[(size_t)row * splits + split] = M;
+      part_s[(size_t)row * splits + split] = S;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) kde_finalize_kernel(const float *__restrict__ part_m,
+                                                           const float *__restrict__ part_s, int64_t Nq,
+                                                           int splits, double log_norm, double *out64,
+                                                           float *out_max, float *out_sum) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= Nq) return;
+  float M = -INFINITY;
+  for (int s = 0; s < splits; ++s) M = fmaxf(M, part_m[(size_t)row * splits + s]);
+  double S = 0.0;
+  for (int s = 0; s < splits; ++s) {
+    const float m = part_m[(size_t)row * splits + s];
+    if (m != -INFINITY) S += (double)part_s[(size_t)row * splits + s] * exp2((double)m - (double)M);
+  }
+  const double LN2 = 0.693147180559945309417232121458;
+  if (out64) out64[row] = (double)M * LN2 + log(S) - log_norm;
+  if (out_max) out_max[row] = (float)((double)M * LN2);  // natural-log units
+  if (out_sum) out_sum[row] = (float)S;
+}
+
+// Bank splits (grid.y): pick the split count that fills whole waves of the 2-CTA/SM grid best.
+static void pick_splits(int64_t rowblocks, int64_t panels, int max_splits, int &splits, int64_t &pps) {
+  const int64_t slots = 2 * (int64_t)kNumSMs;
+  int64_t best_s = 1;
+  double best_u = -1.0;
+  for (int64_t s = 1; s <= max_splits && s <= (panels > 0 ? panels : 1); ++s) {
+    const int64_t eff = ceil_div(panels, ceil_div(panels, s));  // splits actually produced
+    const int64_t total = rowblocks * eff;
+    const double u = (double)total / (double)(ceil_div(total, slots) * slots);
+    if (u > best_u + 0.02) {
+      best_u = u;
+      best_s = s;
+    }
+  }
+  pps = ceil_div(panels > 0 ? panels : 1, best_s);
+  splits = (int)ceil_div(panels > 0 ? panels : 1, pps);
+  if (splits < 1) splits = 1;
+}
+
+static KnnPlan make_knn_plan(int64_t Nq, int64_t Nb, int k) {
+  KnnPlan p;
+  p.kcap = 64;
+  while (p.kcap < k + 8) p.kcap <<= 1;
+  p.capp = p.kcap + BN <= 256 ? 256 : 512;
+  pick_splits(ceil_div(Nq, BM), ceil_div(Nb, BN), 16, p.splits, p.panels_per_split);
+  return p;
+}
+
+struct KnnWorkspace {
+  size_t qn, buf_d, buf_i, flag_count, flag_rows, flag_T, flag_I, fb_d, fb_i, total;
+};
+constexpr int FB_GRID = 64;
+static KnnWorkspace knn_layout(int64_t Nq, const KnnPlan &p) {
+  KnnWorkspace w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = o;
+    o += (bytes + 255) / 256 * 256;
+    return at;
+  };
+  w.qn = take((size_t)Nq * 4);
+  w.buf_d = take((size_t)Nq * p.splits * p.capp * 4);
+  w.buf_i = take((size_t)Nq * p.splits * p.capp * 4);
+  w.flag_count = take(256);
+  w.flag_rows = take((size_t)Nq * 4);
+  w.flag_T = take((size_t)Nq * 8);
+  w.flag_I = take((size_t)Nq * 4);
+  w.fb_d = take((size_t)FB_GRID * FB_CAP * 8);
+  w.fb_i = take((size_t)FB_GRID * FB_CAP * 4);
+  w.total = o;
+  return w;
+}
+
+}  // namespace runia
+
+using namespace runia;
+
+extern "C" int runia_center_cast(const void *in, int in_is_f64, int64_t N, int d, const double *center,
+                                 float *out, void *stream) {
+  RUNIA_REQUIRE(N >= 0 && d > 0, RUNIA_E_BADARG, "center_cast: bad sizes");
+  if (N == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(in && out, RUNIA_E_BADARG, "center_cast: null pointer");
+  const int64_t total = N * d;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)kNumSMs * 16);
+  if (in_is_f64)
+    center_cast_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double *)in, total, d, center, out);
+  else
+    center_cast_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)in, total, d, center, out);
+  count_launch();
+  return finish_launch("center_cast");
+}
+
+extern "C" int runia_normalize_rows(const void *in, int in_is_f64, int64_t N, int d, float *out, void *stream) {
+  RUNIA_REQUIRE(N >= 0 && d > 0, RUNIA_E_BADARG, "normalize_rows: bad sizes");
+  if (N == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(in && out, RUNIA_E_BADARG, "normalize_rows: null pointer");
+  const unsigned grid = (unsigned)ceil_div(N, 8);
+  if (in_is_f64)
+    normalize_rows_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double *)in, N, d, out);
+  else
+    normalize_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)in, N, d, out);
+  count_launch();
+  return finish_launch("normalize_rows");
+}
+
+extern "C" int runia_row_sqnorm_f32(const float *X, int64_t N, int d, float *out, void *stream) {
+  RUNIA_REQUIRE(N >= 0 && d > 0, RUNIA_E_BADARG, "row_sqnorm: bad sizes");
+  if (N == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(X && out, RUNIA_E_BADARG, "row_sqnorm: null pointer");
+  row_sqnorm_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(X, N, d, out);
+  count_launch();
+  return finish_launch("row_sqnorm");
+}
+
+extern "C" int64_t runia_knn_workspace_bytes(int64_t Nq, int64_t Nb, int d, int k) {
+  if (Nq <= 0 || Nb <= 0 || k <= 0 || k > 240) return 0;
+  (void)d;
+  return (int64_t)knn_layout(Nq, make_knn_plan(Nq, Nb, k)).total;
+}
+
+extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn, const float *Bn_sqnorm,
+                                    int64_t Nb, int d, int k, int64_t idx_offset, float *out_dist,
+                                    double *out_dist_f64, int64_t *out_idx, float *out_kth, int32_t *status,
+                                    void *workspace, int64_t workspace_bytes, void *stream) {
+  RUNIA_REQUIRE(Nq >= 0 && Nb > 0 && d > 0, RUNIA_E_BADARG, "knn_search: bad sizes Nq=%lld Nb=%lld d=%d",
+                (long long)Nq, (long long)Nb, d);
+  RUNIA_REQUIRE(k >= 1 && k <= 240, RUNIA_E_UNSUPPORTED, "knn_search: k=%d outside [1, 240]", k);
+  RUNIA_REQUIRE(Nb < (int64_t)0x7fffffff, RUNIA_E_UNSUPPORTED, "knn_search: bank shard too large");
+  if (Nq == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(Qn && Bn && Bn_sqnorm && status && workspace, RUNIA_E_BADARG, "knn_search: null pointer");
+  const KnnPlan plan = make_knn_plan(Nq, Nb, k);
+  const KnnWorkspace w = knn_layout(Nq, plan);
+  RUNIA_REQUIRE((size_t)workspace_bytes >= w.total, RUNIA_E_WORKSPACE, "knn_search: workspace %lld < %lld bytes",
+                (long long)workspace_bytes, (long long)w.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char *ws = (unsigned char *)workspace;
+  float *qn = (float *)(ws + w.qn);
+  float *buf_d = (float *)(ws + w.buf_d);
+  int32_t *buf_i = (int32_t *)(ws + w.buf_i);
+  int32_t *flag_count = (int32_t *)(ws + w.flag_count);
+
+  RUNIA_CUDA(cudaMemsetAsync(flag_count, 0, 256, st));
+  RUNIA_CUDA(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st));
+  row_sqnorm_kernel<<<(unsigned)ceil_div(Nq, 8), 256, 0, st>>>(Qn, Nq, d, qn);
+
+  const size_t dyn1 = (size_t)8 * plan.capp * 8;
+  static bool attr1 = false;
+  if (!attr1) {
+    RUNIA_CUDA(cudaFuncSetAttribute(knn_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr1 = true;
+  }
+  dim3 grid1((unsigned)ceil_div(Nq, BM), (unsigned)plan.splits);
+  knn_candidates_kernel<<<grid1, GEMM_THREADS, dyn1, st>>>(Qn, qn, Nq, Bn, Bn_sqnorm, Nb, d, plan, buf_d, buf_i);
+
+  KnnRerankArgs a;
+  a.Q = Qn; a.B = Bn; a.Nq = Nq; a.Nb = Nb; a.d = d; a.k = k; a.plan = plan;
+  a.buf_d = buf_d; a.buf_i = buf_i;
+  // |approx - exact| <= (2K + 8) * 2^-24 for unit-norm rows (DESIGN.md "kNN certification")
+  a.eps = (float)((2.0 * d + 8.0) * 5.9604644775390625e-08 * 1.25);
+  a.idx_offset = idx_offset;
+  a.out_dist = out_dist; a.out_dist64 = out_dist_f64; a.out_idx = out_idx; a.out_kth = out_kth;
+  a.flag_count = flag_count;
+  a.flag_rows = (int32_t *)(ws + w.flag_rows);
+  a.flag_T = (double *)(ws + w.flag_T);
+  a.flag_I = (int32_t *)(ws + w.flag_I);
+  int msz = 1;
+  while (msz < plan.splits * plan.kcap) msz <<= 1;
+  const size_t per_warp = (((size_t)msz * 8 + (size_t)plan.kcap * 12) + 15) / 16 * 16;
+  const size_t dyn2 = per_warp * RERANK_WARPS;
+  static bool attr2 = false;
+  if (!attr2) {
+    RUNIA_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr2 = true;
+  }
+  RUNIA_REQUIRE(dyn2 <= 200 * 1024, RUNIA_E_UNSUPPORTED, "knn_search: merge scratch too large");
+  knn_rerank_kernel<<<(unsigned)ceil_div(Nq, RERANK_WARPS), RERANK_WARPS * 32, dyn2, st>>>(a);
+  knn_fallback_kernel<<<FB_GRID, 256, 0, st>>>(a, status, (double *)(ws + w.fb_d), (int32_t *)(ws + w.fb_i));
+  count_launch(4);
+  return finish_launch("knn_search");
+}
+
+extern "C" int runia_topk_merge(const double *part_dist, const int64_t *part_idx, int R, int64_t Nq, int k,
+                                float *out_dist, int64_t *out_idx, float *out_kth, void *stream) {
+  RUNIA_REQUIRE(R >= 1 && R <= 16 && Nq >= 0 && k >= 1, RUNIA_E_BADARG, "topk_merge: bad sizes R=%d k=%d", R, k);
+  if (Nq == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(part_dist && part_idx, RUNIA_E_BADARG, "topk_merge: null pointer");
+  topk_merge_kernel<<<(unsigned)ceil_div(Nq, 128), 128, 0, (cudaStream_t)stream>>>(part_dist, part_idx, R, Nq, k,
+                                                                               out_dist, out_idx, out_kth);
+  count_launch();
+  return finish_launch("topk_merge");
+}
+
+static void kde_plan(int64_t Nq, int64_t Nb, int &splits, int64_t &pps) {
+  pick_splits(ceil_div(Nq, BM), ceil_div(Nb, BN), 64, splits, pps);
+}
+
+extern "C" int64_t runia_kde_workspace_bytes(int64_t Nq, int64_t Nb) {
+  if (Nq <= 0 || Nb <= 0) return 0;
+  int splits;
+  int64_t pps;
+  kde_plan(Nq, Nb, splits, pps);
+  return (int64_t)(((size_t)Nq * 4 + 255) / 256 * 256 + ((size_t)Nb * 4 + 255) / 256 * 256 +
+                   2 * (((size_t)Nq * splits * 4 + 255) / 256 * 256));
+}
+
+extern "C" int runia_kde_lse_f32(const float *Q, int64_t Nq, const float *B, int64_t Nb, int d, double bandwidth,
+                                 int64_t Nb_total, double *out_f64, float *out_max, float *out_sum,
+                                 void *workspace, int64_t workspace_bytes, void *stream) {
+  RUNIA_REQUIRE(Nq >= 0 && Nb > 0 && d > 0 && bandwidth > 0 && Nb_total >= Nb, RUNIA_E_BADARG, "kde_lse: bad sizes");
+  if (Nq == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(Q && B && workspace && (out_f64 || (out_max && out_sum)), RUNIA_E_BADARG, "kde_lse: null pointer");
+  RUNIA_REQUIRE(workspace_bytes >= runia_kde_workspace_bytes(Nq, Nb), RUNIA_E_WORKSPACE, "kde_lse: workspace too small");
+  int splits;
+  int64_t pps;
+  kde_plan(Nq, Nb, splits, pps);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char *ws = (unsigned char *)workspace;
+  size_t o = 0;
+  float *qn = (float *)(ws + o); o += ((size_t)Nq * 4 + 255) / 256 * 256;
+  float *bn = (float *)(ws + o); o += ((size_t)Nb * 4 + 255) / 256 * 256;
+  float *pm = (float *)(ws + o); o += ((size_t)Nq * splits * 4 + 255) / 256 * 256;
+  float *ps = (float *)(ws + o);
+  row_sqnorm_kernel<<<(unsigned)ceil_div(Nq, 8), 256, 0, st>>>(Q, Nq, d, qn);
+  row_sqnorm_kernel<<<(unsigned)ceil_div(Nb, 8), 256, 0, st>>>(B, Nb, d, bn);
+  const double LOG2E = 1.4426950408889634073599246810019;
+  const float scale = (float)(-0.5 / (bandwidth * bandwidth) * LOG2E);
+  dim3 grid((unsigned)ceil_div(Nq, BM), (unsigned)splits);
+  kde_partial_kernel<<<grid, GEMM_THREADS, 0, st>>>(Q, qn, Nq, B, bn, Nb, d, scale, splits, pps, pm, ps);
+  const double log_norm = log((double)Nb_total) + 0.5 * d * log(2.0 * 3.14159265358979323846 * bandwidth * bandwidth);
+  kde_finalize_kernel<<<(unsigned)ceil_div(Nq, 256), 256, 0, st>>>(pm, ps, Nq, splits, log_norm, out_f64, out_max, out_sum);
+  count_launch(4);
+  return finish_launch("kde_lse");
+}

@@ -1,0 +1,154 @@
+"""Scoring helpers with the names and argument meaning of the reference's
+`runia_core/inference/funcs.py` (cited per function).  Fits run once on the host exactly like
+the reference (`setup()` is not the hot path); everything that
+scores rows goes through the CUDA library."""
+import warnings
+from typing import Dict, Tuple, Union
+
+import numpy as np
+import torch
+from sklearn.covariance import EmpiricalCovariance
+
+from .. import _ops
+from .._device import to_device, to_host
+
+__all__ = [
+    "RouteDICE",
+    "ash_s_linear_layer",
+    "gmm_fit",
+    "generalized_entropy",
+    "mahalanobis_preprocess",
+    "mahalanobis_postprocess",
+    "normalizer",
+]
+
+
+def mahalanobis_preprocess(ind_data: Dict[str, np.ndarray], num_classes: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Class means [C, d] and the shared precision of the class-centred training features
+    (funcs.py:33-66).  Classes without samples warn and get a NaN mean."""
+    feats, labels = ind_data["train features"], ind_data["train labels"]
+    class_mean, centered = [], []
+    for c in range(num_classes):
+        xs = feats[labels == c]
+        if len(xs) == 0:
+            warnings.warn(f"No train examples for class {c}")
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            class_mean.append(xs.mean(0))
+        centered.append(xs - class_mean[c].reshape(1, -1))
+    class_mean = np.stack(class_mean)
+    ec = EmpiricalCovariance(assume_centered=False)
+    ec.fit(np.concatenate(centered).astype(np.float32))
+    return class_mean, ec.precision_
+
+
+def mahalanobis_postprocess(feats: np.ndarray, class_mean: np.ndarray, precision: np.ndarray,
+                            num_classes: int, _state=None) -> np.ndarray:
+    """max_c -(x - mu_c)^T P (x - mu_c), float64 (funcs.py:69-102).  CUDA: one contraction against
+    the factored precision + per-class squared distances (runia_classcond_mahalanobis_f32)."""
+    st = _state if _state is not None else _ops.classcond_prepare(class_mean[:num_classes], precision)
+    return to_host(_ops.classcond_score(feats, st, torch.float64))
+
+
+def normalizer(x):
+    """x / (||x||_2 + 1e-10) along the last axis (funcs.py:105-115), float32 result."""
+    a = np.asarray(x) if not isinstance(x, torch.Tensor) else x
+    shape = tuple(a.shape)
+    out = to_host(_ops.normalize_rows(a.reshape(-1, shape[-1])))
+    return out.reshape(shape)
+
+
+class RouteDICE(torch.nn.Linear):
+    """DICE sparsified linear layer (funcs.py:124-190): weights whose contribution
+    mean_train[d] * W[c, d] is not above the global p-th percentile are masked out.
+    `forward` returns the logits x @ masked_W^T + b; the OoD score path of the DICE
+    postprocessors fuses clip + this product + log-sum-exp into one kernel instead."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, p: int = 90,
+                 conv1x1: bool = False, info: Union[None, np.ndarray] = None):
+        assert 0 < p < 100, "p must be greater than 0 and less than 100"
+        if info is not None:
+            assert isinstance(info, np.ndarray), "info must be a numpy array or None"
+        super().__init__(in_features, out_features, bias)
+        if conv1x1:
+            self.weight = torch.nn.Parameter(torch.Tensor(out_features, in_features, 1, 1))
+        self.p = p
+        self.info = info
+        self.masked_w = None
+        self.contrib = None
+        self.thresh = None
+
+    def calculate_mask_weight(self):
+        w = self.weight.data.cpu().numpy()
+        self.contrib = self.info[None, :] * w
+        self.thresh = np.percentile(self.contrib, self.p)
+        mask = torch.Tensor((self.contrib > self.thresh))
+        self.masked_w = to_device((self.weight.data.squeeze().cpu() * mask).contiguous(), torch.float32)
+
+    def forward(self, x):
+        if self.masked_w is None:
+            self.calculate_mask_weight()
+        x = to_device(x, torch.float32)
+        out = x @ self.masked_w.t()
+        if self.bias is not None:
+            out = out + self.bias.to(out.device)
+        return out
+
+
+def ash_s_linear_layer(x: np.ndarray, percentile: int = 85):
+    """ASH-S pruning + rescaling of a feature matrix (funcs.py:230-261).  Returns the shaped
+    features; the ASH postprocessor itself uses the fused kernel and never materialises them."""
+    assert x.ndim == 2
+    assert 0 <= percentile <= 100
+    xt = to_device(x, torch.float32)
+    n = xt.shape[1]
+    k = n - int(np.round(n * percentile / 100.0))
+    s1 = xt.sum(dim=1)
+    vals, idx = torch.topk(xt, k, dim=1)
+    scattered = torch.zeros_like(xt).scatter_(1, idx, vals)
+    s2 = scattered.sum(dim=1)
+    return to_host(scattered * torch.exp(s1 / s2)[:, None])
+
+
+def gmm_fit(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: int):
+    """Class-wise Gaussian mixture (funcs.py:265-344): mean and covariance X^T X / (n-1) per class,
+    empty classes dropped, smallest jitter of [0, 1e-20 .. 1e-1] for which the Cholesky
+    factorisation exists.  Returns (MultivariateNormal, jitter)."""
+    jitters = [0] + [10**e for e in range(-20, 0, 1)]
+    with torch.no_grad():
+        means, covs = [], []
+        for c in range(num_classes):
+            xs = embeddings[labels == c]
+            mu = torch.mean(xs, dim=0)
+            n = xs.shape[0]
+            n = n + 1 if n == 1 else n
+            xc = xs - mu
+            means.append(mu)
+            covs.append(xc.t().mm(xc) / (n - 1))
+        means, covs = torch.stack(means), torch.stack(covs)
+        keep = ~torch.any(means.isnan(), dim=1)
+        if not bool(keep.all()):
+            means, covs = means[keep], covs[keep]
+        gmm, jitter_eps = None, None
+        for jitter_eps in jitters:
+            try:
+                jitter = jitter_eps * torch.eye(covs.shape[1], device=covs.device).unsqueeze(0)
+                gmm = torch.distributions.MultivariateNormal(loc=means, covariance_matrix=(covs + jitter))
+            except RuntimeError as e:
+                if "cholesky" in str(e):
+                    continue
+            except ValueError as e:
+                if "found invalid values" in str(e):
+                    continue
+            break
+    return gmm, jitter_eps
+
+
+def generalized_entropy(probs, gamma, M):
+    """-sum over the M largest probabilities of p^gamma (1-p)^gamma (funcs.py:347-375).
+    Runs the fused logit kernel on log(probs): softmax(log p) == p for normalised rows."""
+    p = np.asarray(probs)
+    with np.errstate(divide="ignore"):
+        lg = np.log(p.astype(np.float64)).astype(np.float32)
+    _, _, g, _ = _ops.logit_scores(lg, gamma=gamma, M=M, energy=False, msp=False, gen=True)
+    return to_host(g).astype(p.dtype if p.dtype.kind == "f" else np.float32)

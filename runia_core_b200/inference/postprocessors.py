@@ -1,0 +1,578 @@
+"""Registry and the 16 scoring operators of the reference's
+`runia_core/inference/postprocessors.py`, with the same registry keys, class names, constructor
+signatures, `setup()` / `postprocess()` keyword arguments, state attributes, warnings and
+assertion messages -- and every `postprocess()` body replaced by calls into the CUDA library.
+
+`setup()` keeps the reference's one-off host fits (sklearn / NumPy / torch.distributions, cited
+per class) and then uploads the fitted state; scoring InD validation data for thresholds already
+runs on the GPU.  Inputs may be NumPy arrays (as upstream) or torch tensors, including CUDA
+tensors (no host round trip); outputs are NumPy arrays of the dtype the reference returns.
+"""
+import warnings
+from typing import Dict, List, Union
+
+import numpy as np
+import torch
+from sklearn.covariance import EmpiricalCovariance
+from torch import Tensor
+
+from .. import _ops
+from .._device import to_device, to_host
+from .abstract_classes import OodPostprocessor, Postprocessor
+from .funcs import RouteDICE, gmm_fit, mahalanobis_preprocess
+
+__all__ = [
+    "postprocessors_dict",
+    "postprocessor_input_dict",
+    "register_postprocessor",
+    "DetectorKDE",
+    "FlatL2Index",
+    "LaREMPostprocessor",
+    "LaREDPostprocessor",
+]
+
+_VALID_INPUT_TYPES = ("latent_space_means", "features", "logits")
+postprocessors_dict: Dict[str, type] = {}
+postprocessor_input_dict: Dict[str, List[str]] = {}
+
+
+def register_postprocessor(postprocessor_name: str, postprocessor_input: List[str]):
+    """Class decorator filling the two registries (postprocessors.py:50-75)."""
+
+    def decorator(cls):
+        for input_type in postprocessor_input:
+            assert (
+                input_type in _VALID_INPUT_TYPES
+            ), f"Invalid input type {input_type}. Specify at least one of {_VALID_INPUT_TYPES}."
+        postprocessors_dict[postprocessor_name] = cls
+        postprocessor_input_dict[postprocessor_name] = postprocessor_input
+        __all__.append(cls.__name__)
+        return cls
+
+    return decorator
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if isinstance(x, Tensor) else np.asarray(x)
+
+
+def _linear_params(kwargs):
+    w, b = kwargs["final_linear_layer_params"]["weight"], kwargs["final_linear_layer_params"]["bias"]
+    return _np(w), _np(b)
+
+
+# ------------------------------------------------------------------------------------------------
+# LaRED: Gaussian KDE over the latent bank            reference: postprocessors.py:78-178
+# ------------------------------------------------------------------------------------------------
+class DetectorKDE:
+    """Gaussian kernel density estimate of the training embeddings (postprocessors.py:78-128).
+    The reference fits sklearn's KernelDensity (a KD-tree) and queries it exactly (atol=rtol=0);
+    here `density` is the device-resident bank and scoring is the closed form
+    logsumexp_i(-|q-x_i|^2 / 2h^2) - log N - d/2 log(2 pi h^2) in one fused kernel."""
+
+    def __init__(self, train_embeddings, save_path=None, kernel="gaussian", bandwidth=1.0) -> None:
+        if kernel != "gaussian":
+            raise NotImplementedError("only the Gaussian kernel (the reference's default) is implemented")
+        self.kernel = kernel
+        self.bandwidth = bandwidth
+        self.train_embeddings = train_embeddings
+        self.save_path = save_path
+        self.density = self.density_fit()
+
+    def density_fit(self):
+        center = np.asarray(_np(self.train_embeddings), np.float64).mean(0)
+        return _ops.kde_bank(self.train_embeddings, self.bandwidth, center=center)
+
+    def get_density_scores(self, test_embeddings):
+        return to_host(_ops.kde_score(test_embeddings, self.density))
+
+
+@register_postprocessor("KDE", postprocessor_input=["latent_space_means"])
+class KDELatentSpace(Postprocessor):
+    """LaRED score (postprocessors.py:131-178): log-density, float64."""
+
+    def __init__(self, cfg=None):
+        super().__init__(cfg)
+        self.detector = None
+
+    def setup(self, ind_train_data: np.ndarray, **kwargs) -> None:
+        assert ind_train_data.ndim == 2, "ind_feats must be 2 dimensional"
+        if not self._setup_flag:
+            self.detector = DetectorKDE(train_embeddings=ind_train_data)
+            self._setup_flag = True
+        else:
+            warnings.warn("KDEPostprocessor already trained")
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        assert test_data.ndim == 2, "ood_feats must be 2 dimensional"
+        return self.detector.get_density_scores(test_data)
+
+
+# ------------------------------------------------------------------------------------------------
+# LaREM: Mahalanobis distance to the training distribution     reference: postprocessors.py:181-244
+# ------------------------------------------------------------------------------------------------
+@register_postprocessor("MD", postprocessor_input=["latent_space_means"])
+class MDLatentSpace(Postprocessor):
+    """-(x-mu)^T P (x-mu), float64.  setup: mean, EmpiricalCovariance(pinvh) on the host
+    (postprocessors.py:212-220); postprocess: runia_rownorm_score_f32 against the factored P."""
+
+    def __init__(self, cfg=None):
+        super().__init__(cfg)
+        self.feats_mean = None
+        self.precision = None
+        self.centered_data = None
+        self._state = None
+
+    def setup(self, ind_train_data: np.ndarray, **kwargs) -> None:
+        assert ind_train_data.ndim == 2, "ind_feats must be 2 dimensional"
+        if not self._setup_flag:
+            ind_train_data = _np(ind_train_data)
+            self.feats_mean = np.mean(ind_train_data, 0, keepdims=True)
+            self.centered_data = ind_train_data - self.feats_mean
+            ec = EmpiricalCovariance(assume_centered=False)
+            ec.fit(self.centered_data)
+            self.precision = ec.precision_
+            self._state = _ops.md_prepare(self.feats_mean, self.precision)
+            self._setup_flag = True
+        else:
+            warnings.warn("MDPostprocessor already trained")
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        assert test_data.ndim == 2, "test_feats must be 2 dimensional"
+        if self._state is None:  # attributes assigned by hand (checkpoint restore)
+            self._state = _ops.md_prepare(self.feats_mean, self.precision)
+        return to_host(_ops.md_score(test_data, self._state, torch.float64))
+
+
+# ------------------------------------------------------------------------------------------------
+# cMD: class-conditional LaREM (float32 torch in the reference)       postprocessors.py:247-357
+# ------------------------------------------------------------------------------------------------
+@register_postprocessor("cMD", postprocessor_input=["latent_space_means"])
+class cMDLatentSpace(Postprocessor):
+    def __init__(self, cfg=None):
+        super().__init__(cfg)
+        try:
+            self.num_classes = cfg.num_classes
+        except AttributeError:
+            self.num_classes = 10
+        self.feats_mean = None
+        self.precision = None
+        self.class_mean = None
+        self._state = None
+
+    def setup(self, ind_train_data: np.ndarray, **kwargs) -> None:
+        try:
+            ind_train_labels = kwargs["ind_train_labels"]
+        except KeyError:
+            raise ValueError("id_labels not provided. Pass ID train labels as 'ind_train_labels' argument.")
+        ind_train_labels = _np(ind_train_labels)
+        feats = _np(ind_train_data).astype(np.float32)
+        assert feats.ndim == 2, "ind_feats must be 2 dimensional"
+        if not self._setup_flag:
+            class_mean, centered = [], []
+            for c in range(self.num_classes):
+                xs = feats[ind_train_labels == c]
+                if len(xs) == 0:
+                    warnings.warn(f"No examples for class {c} to build class-wise Mahalanobis Distance score")
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore", RuntimeWarning)
+                    class_mean.append(xs.mean(0))
+                centered.append(xs - class_mean[c].reshape(1, -1))
+            cm = np.stack(class_mean)
+            ec = EmpiricalCovariance(assume_centered=False)
+            ec.fit(np.concatenate(centered).astype(np.float32))
+            self.class_mean = torch.from_numpy(cm)  # [#classes, d], like the reference
+            self.precision = torch.from_numpy(ec.precision_).float()
+            self._state = _ops.classcond_prepare(cm, ec.precision_)
+            self._setup_flag = True
+        else:
+            warnings.warn("cMDPostprocessor already trained")
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        if "pred_labels" not in kwargs:
+            raise ValueError("pred_logits not provided")
+        assert test_data.ndim == 2, "test_feats must be 2 dimensional"
+        return to_host(_ops.classcond_score(test_data, self._state, torch.float32))
+
+
+# ------------------------------------------------------------------------------------------------
+# kNN over L2-normalised latents                       postprocessors.py:360-423 / 789-883
+# ------------------------------------------------------------------------------------------------
+class FlatL2Index:
+    """Stand-in for `faiss.IndexFlatL2` (the only faiss class the reference uses,
+    postprocessors.py:396-397, 850-851): exact squared-L2 search over a device-resident bank."""
+
+    def __init__(self, d: int):
+        self.d = d
+        self.ntotal = 0
+        self._bank = None
+
+    def add(self, x):
+        t = to_device(x, torch.float32)
+        assert t.dim() == 2 and t.shape[1] == self.d
+        full = t if self._bank is None else torch.cat([self._bank.bank, t])
+        self._bank = _ops.knn_bank(full.contiguous())
+        self.ntotal = int(full.shape[0])
+
+    def search(self, x, k: int):
+        q = to_device(x, torch.float32)
+        res = _ops.knn_search(q, self._bank, k)
+        return to_host(res["dist"]), to_host(res["idx"])
+
+    def kth_distance(self, q: torch.Tensor, k: int) -> torch.Tensor:
+        return _ops.knn_search(q, self._bank, k, want_idx=False, want_dist=False)["kth"]
+
+
+def _knn_scores(index: FlatL2Index, test_data, k: int) -> np.ndarray:
+    qn = _ops.normalize_rows(test_data)
+    return -to_host(index.kth_distance(qn, k))
+
+
+@register_postprocessor("KNN", postprocessor_input=["latent_space_means"])
+class KNNLatentSpace(Postprocessor):
+    """minus the squared distance to the K-th neighbour among normalised training latents, float32
+    (postprocessors.py:385-423); K from cfg.k_neighbors, default 50."""
+
+    def __init__(self, cfg=None):
+        super().__init__(cfg)
+        try:
+            self.K = cfg.k_neighbors
+        except AttributeError:
+            self.K = 50
+        self.activation_log = None
+        self.index = None
+
+    def setup(self, ind_train_data: np.ndarray, **kwargs) -> None:
+        assert ind_train_data.ndim == 2, "ind_train_feats must be 2 dimensional"
+        if not self._setup_flag:
+            bank = _ops.normalize_rows(ind_train_data)
+            self.activation_log = to_host(bank)
+            self.index = FlatL2Index(ind_train_data.shape[1])
+            self.index.add(bank)
+            self._setup_flag = True
+        else:
+            warnings.warn("KNNPostprocessor already trained")
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        assert test_data.ndim == 2, "test_feats must be 2 dimensional"
+        return _knn_scores(self.index, test_data, self.K)
+
+
+# ------------------------------------------------------------------------------------------------
+# GMM (LaREG) and DDU: class-wise Gaussian mixture log-density   postprocessors.py:426-492, 694-786
+# ------------------------------------------------------------------------------------------------
+def _gmm_state(gmm):
+    return _ops.gmm_prepare(gmm.loc.detach().cpu().numpy(), gmm.scale_tril.detach().cpu().numpy())
+
+
+@register_postprocessor("GMM", postprocessor_input=["latent_space_means"])
+class GMMLatentSpace(Postprocessor):
+    def __init__(self, cfg=None):
+        super().__init__(cfg)
+        try:
+            self.num_classes = cfg.num_classes
+        except AttributeError:
+            self.num_classes = 10
+        self.gmm = None
+        self._state = None
+
+    def setup(self, ind_train_data: np.ndarray, **kwargs) -> None:
+        assert ind_train_data.ndim == 2, "ind_train_feats must be 2 dimensional"
+        if not self._setup_flag:
+            try:
+                labels = kwargs["ind_train_labels"]
+            except KeyError:
+                raise ValueError("id_labels not provided")
+            self.gmm, _ = gmm_fit(embeddings=Tensor(_np(ind_train_data)), labels=Tensor(_np(labels)),
+                                  num_classes=self.num_classes)
+            self._state = _gmm_state(self.gmm)
+            self._setup_flag = True
+        else:
+            warnings.warn("GMMPostprocessor already trained")
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        assert test_data.ndim == 2, "test_feats must be 2 dimensional"
+        return to_host(_ops.gmm_lse(test_data, self._state))
+
+
+# ------------------------------------------------------------------------------------------------
+# logit-space scores: one fused pass                              postprocessors.py:495-691
+# ------------------------------------------------------------------------------------------------
+def _logit_score(test_data, which, gamma=0.1, M=None):
+    e, m, g, in_dtype = _ops.logit_scores(test_data, gamma=gamma, M=M, energy=which == "energy",
+                                          msp=which == "msp", gen=which == "gen")
+    out = to_host({"energy": e, "msp": m, "gen": g}[which])
+    return out.astype(np.float64) if in_dtype == torch.float64 else out
+
+
+@register_postprocessor("energy", postprocessor_input=["logits"])
+class Energy(OodPostprocessor):
+    def setup(self, ind_train_data: np.ndarray, **kwargs):
+        ind_scores = self.flip_sign_fn(_logit_score(ind_train_data, "energy"))
+        self.set_threshold(ind_scores)
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        assert self._setup_flag, "setup() must be called before postprocess()"
+        return self.flip_sign_fn(_logit_score(test_data, "energy"))
+
+
+@register_postprocessor("msp", postprocessor_input=["logits"])
+class MSP(OodPostprocessor):
+    def setup(self, ind_train_data: np.ndarray, **kwargs):
+        ind_scores = self.flip_sign_fn(_logit_score(ind_train_data, "msp"))
+        self.set_threshold(ind_scores)
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        assert self._setup_flag, "setup() must be called before postprocess()"
+        return self.flip_sign_fn(_logit_score(test_data, "msp"))
+
+
+@register_postprocessor("gen", postprocessor_input=["logits"])
+class GEN(OodPostprocessor):
+    def __init__(self, flip_sign: bool, gamma: float, num_classes: int, cfg=None):
+        super().__init__(flip_sign, cfg)
+        self.gamma = gamma
+        self.num_classes = num_classes
+
+    def setup(self, ind_train_data: np.ndarray, **kwargs):
+        ind_scores = self.flip_sign_fn(_logit_score(ind_train_data, "gen", self.gamma, self.num_classes))
+        self.set_threshold(ind_scores)
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        assert self._setup_flag, "setup() must be called before postprocess()"
+        return self.flip_sign_fn(_logit_score(test_data, "gen", self.gamma, self.num_classes))
+
+
+@register_postprocessor("ddu", postprocessor_input=["features"])
+class DDU(OodPostprocessor):
+    def __init__(self, flip_sign: bool, num_classes: int, cfg=None):
+        super().__init__(flip_sign, cfg)
+        self.num_classes = num_classes
+        self.gmm = None
+        self.device = "cuda" if torch.cuda.is_available() else "cpu"
+        self._state = None
+
+    def setup(self, ind_train_data: np.ndarray, **kwargs):
+        assert "valid_feats" in kwargs, "valid_feats must be provided for DDU"
+        assert "train_labels" in kwargs, "train_labels must be provided for DDU"
+        self.gmm, _ = gmm_fit(embeddings=Tensor(_np(ind_train_data)), labels=Tensor(_np(kwargs["train_labels"])),
+                              num_classes=self.num_classes)
+        self._state = _gmm_state(self.gmm)
+        ind_scores = self.flip_sign_fn(to_host(_ops.gmm_lse(kwargs["valid_feats"], self._state)))
+        self.set_threshold(ind_scores)
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        assert self._setup_flag, "setup() must be called before postprocess()"
+        return self.flip_sign_fn(to_host(_ops.gmm_lse(test_data, self._state)))
+
+
+@register_postprocessor("knn", postprocessor_input=["features"])
+class KNN(OodPostprocessor):
+    def __init__(self, flip_sign: bool, k_neighbors: int, cfg=None):
+        super().__init__(flip_sign, cfg)
+        self.k_neighbors = k_neighbors
+        self.gmm = None
+        self.device = "cuda" if torch.cuda.is_available() else "cpu"
+        self.index = None
+
+    def setup(self, ind_train_data: np.ndarray, **kwargs):
+        assert "valid_feats" in kwargs, "valid_feats must be provided for KNN setup"
+        bank = _ops.normalize_rows(ind_train_data)
+        self.index = FlatL2Index(ind_train_data.shape[1])
+        self.index.add(bank)
+        ind_scores = self.flip_sign_fn(_knn_scores(self.index, kwargs["valid_feats"], self.k_neighbors))
+        self.set_threshold(ind_scores)
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        return self.flip_sign_fn(_knn_scores(self.index, test_data, self.k_neighbors))
+
+
+@register_postprocessor("mahalanobis", postprocessor_input=["features"])
+class Mahalanobis(OodPostprocessor):
+    def __init__(self, flip_sign: bool, num_classes: int, cfg=None):
+        super().__init__(flip_sign, cfg)
+        self.num_classes = num_classes
+        self.class_mean = None
+        self.precision = None
+        self._state = None
+
+    def setup(self, ind_train_data: np.ndarray, **kwargs):
+        assert "train_labels" in kwargs, "train_labels must be provided for Mahalanobis"
+        assert "valid_feats" in kwargs, "valid_feats must be provided for Mahalanobis"
+        ind = {"train features": _np(ind_train_data), "train labels": _np(kwargs["train_labels"])}
+        self.class_mean, self.precision = mahalanobis_preprocess(ind_data=ind, num_classes=self.num_classes)
+        self._state = _ops.classcond_prepare(self.class_mean, self.precision)
+        ind_scores = to_host(_ops.classcond_score(kwargs["valid_feats"], self._state, torch.float64))
+        self.set_threshold(self.flip_sign_fn(ind_scores))
+
+    def postprocess(self, test_data: Union[np.ndarray, Tensor], **kwargs) -> np.ndarray:
+        assert self._setup_flag, "setup() must be called before postprocess()"
+        return self.flip_sign_fn(to_host(_ops.classcond_score(test_data, self._state, torch.float64)))
+
+
+@register_postprocessor("vim", postprocessor_input=["features", "logits"])
+class ViM(OodPostprocessor):
+    """-alpha * ||(x-u) NS|| + logsumexp(logits) (postprocessors.py:983-1112).  setup keeps the
+    reference's host fit (pinv, EmpiricalCovariance(assume_centered=True), np.linalg.eig)."""
+
+    def __init__(self, flip_sign: bool, cfg=None):
+        super().__init__(flip_sign, cfg)
+        self.u = None
+        self.DIM = None
+        self.NS = None
+        self.alpha = None
+        self._state = None
+
+    def setup(self, ind_train_data: np.ndarray, **kwargs):
+        assert "final_linear_layer_params" in kwargs, "final_linear_layer_params must be provided for ViM"
+        assert "train_logits" in kwargs, "train_logits must be provided for ViM"
+        assert "valid_feats" in kwargs, "valid_feats must be provided for ViM"
+        assert "valid_logits" in kwargs, "valid_logits must be provided for ViM"
+        w, b = _linear_params(kwargs)
+        train = _np(ind_train_data)
+        self.u = -np.matmul(np.linalg.pinv(w), b)
+        if train.shape[-1] >= 2048:
+            self.DIM = 1000
+        elif train.shape[-1] >= 768:
+            self.DIM = 512
+        else:
+            self.DIM = train.shape[-1] // 2
+        ec = EmpiricalCovariance(assume_centered=True)
+        ec.fit(train - self.u)
+        eig_vals, eigen_vectors = np.linalg.eig(ec.covariance_)
+        self.NS = np.ascontiguousarray((eigen_vectors.T[np.argsort(eig_vals * -1)[self.DIM:]]).T)
+        st = _ops.vim_prepare(self.u, self.NS, 1.0)
+        vlogit_train = to_host(_ops.residual_norm(train, st))
+        self.alpha = _np(kwargs["train_logits"]).max(axis=-1).mean() / vlogit_train.mean()
+        self._state = _ops.vim_prepare(self.u, self.NS, self.alpha)
+        ind_scores = to_host(_ops.vim_score(kwargs["valid_feats"], kwargs["valid_logits"], self._state))
+        self.set_threshold(self.flip_sign_fn(ind_scores))
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        assert self._setup_flag, "setup() must be called before postprocess()"
+        return to_host(_ops.vim_score(test_data, kwargs["logits"], self._state))  # no sign flip upstream
+
+
+# ------------------------------------------------------------------------------------------------
+# feature-shaping baselines: clip / mask / prune -> linear -> log-sum-exp   postprocessors.py:1115-1621
+# ------------------------------------------------------------------------------------------------
+@register_postprocessor("ash", postprocessor_input=["features"])
+class ASH(OodPostprocessor):
+    def __init__(self, flip_sign: bool, ash_percentile: int = 85, cfg=None):
+        super().__init__(flip_sign, cfg)
+        self.ash_percentile = ash_percentile
+        self.w = None
+        self.b = None
+
+    def _score(self, x):
+        n = x.shape[1]
+        k = n - int(np.round(n * self.ash_percentile / 100.0))
+        return to_host(_ops.ash_linear_lse(x, self._w, self._b, k))
+
+    def setup(self, ind_train_data: np.ndarray, **kwargs):
+        assert "final_linear_layer_params" in kwargs, "final_linear_layer_params must be provided for ASH"
+        assert "valid_feats" in kwargs, "valid_feats must be provided for ASH"
+        self.w, self.b = _linear_params(kwargs)
+        self._w, self._b = to_device(self.w, torch.float32), to_device(self.b, torch.float32)
+        # the reference thresholds on the TRAIN features here (postprocessors.py:1185)
+        self.set_threshold(self.flip_sign_fn(self._score(ind_train_data)))
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        assert self._setup_flag, "setup() must be called before postprocess()"
+        return self.flip_sign_fn(self._score(test_data))
+
+
+def _make_dice_layer(ind_train_data, kwargs, num_classes, percentile):
+    w, b = kwargs["final_linear_layer_params"]["weight"], kwargs["final_linear_layer_params"]["bias"]
+    params = {"weight": Tensor(w) if isinstance(w, np.ndarray) else w,
+              "bias": Tensor(b) if isinstance(b, np.ndarray) else b}
+    info = Tensor(_np(ind_train_data)).mean(0).cpu().numpy()
+    layer = RouteDICE(in_features=ind_train_data.shape[1], out_features=num_classes, bias=True,
+                      p=percentile, info=info)
+    layer.load_state_dict(params)
+    layer.eval()
+    layer.calculate_mask_weight()
+    return layer
+
+
+@register_postprocessor("dice", postprocessor_input=["features"])
+class DICE(OodPostprocessor):
+    def __init__(self, flip_sign: bool, dice_percentile: int = 90, num_classes: int = 10, cfg=None):
+        super().__init__(flip_sign, cfg)
+        self.dice_percentile = dice_percentile
+        self.num_classes = num_classes
+        self.dice_layer = None
+        self.device = "cuda" if torch.cuda.is_available() else "cpu"
+
+    def _score(self, x):
+        return to_host(_ops.clip_linear_lse(x, self.dice_layer.masked_w, self._b))
+
+    def setup(self, ind_train_data: np.ndarray, **kwargs):
+        assert "final_linear_layer_params" in kwargs, "final_linear_layer_params must be provided for DICE"
+        assert "valid_feats" in kwargs, "valid_feats must be provided for DICE"
+        self.dice_layer = _make_dice_layer(ind_train_data, kwargs, self.num_classes, self.dice_percentile)
+        self._b = to_device(self.dice_layer.bias.detach(), torch.float32)
+        self.set_threshold(self.flip_sign_fn(self._score(kwargs["valid_feats"])))
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        assert self._setup_flag, "setup() must be called before postprocess()"
+        return self.flip_sign_fn(self._score(test_data))
+
+
+@register_postprocessor("react", postprocessor_input=["features"])
+class ReAct(OodPostprocessor):
+    def __init__(self, flip_sign: bool, react_percentile: int = 90, cfg=None):
+        super().__init__(flip_sign, cfg)
+        self.react_percentile = react_percentile
+        self.activation_threshold = None
+        self.w = None
+        self.b = None
+
+    def _score(self, x):
+        return to_host(_ops.clip_linear_lse(x, self._w, self._b, clip=float(self.activation_threshold)))
+
+    def setup(self, ind_train_data: np.ndarray, **kwargs):
+        assert "final_linear_layer_params" in kwargs, "final_linear_layer_params must be provided for ReAct"
+        assert "valid_feats" in kwargs, "valid_feats must be provided for ReAct"
+        self.w, self.b = _linear_params(kwargs)
+        self._w, self._b = to_device(self.w, torch.float32), to_device(self.b, torch.float32)
+        self.activation_threshold = np.percentile(_np(ind_train_data).flatten(), self.react_percentile)
+        self.set_threshold(self.flip_sign_fn(self._score(kwargs["valid_feats"])))
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        assert self._setup_flag, "setup() must be called before postprocess()"
+        return self.flip_sign_fn(self._score(test_data))
+
+
+@register_postprocessor("dice_react", postprocessor_input=["features"])
+class DICEReAct(OodPostprocessor):
+    def __init__(self, flip_sign: bool, dice_percentile: int = 90, react_percentile: int = 90,
+                 num_classes: int = 10, cfg=None):
+        super().__init__(flip_sign, cfg)
+        self.dice_percentile = dice_percentile
+        self.react_percentile = react_percentile
+        self.num_classes = num_classes
+        self.dice_layer = None
+        self.device = "cuda" if torch.cuda.is_available() else "cpu"
+        self.react_activation_threshold = None
+
+    def _score(self, x):
+        return to_host(_ops.clip_linear_lse(x, self.dice_layer.masked_w, self._b,
+                                            clip=float(self.react_activation_threshold)))
+
+    def setup(self, ind_train_data: np.ndarray, **kwargs):
+        assert "final_linear_layer_params" in kwargs, "final_linear_layer_params must be provided for DICE"
+        assert "valid_feats" in kwargs, "valid_feats must be provided for DICE"
+        self.dice_layer = _make_dice_layer(ind_train_data, kwargs, self.num_classes, self.dice_percentile)
+        self._b = to_device(self.dice_layer.bias.detach(), torch.float32)
+        self.react_activation_threshold = np.percentile(_np(ind_train_data).flatten(), self.react_percentile)
+        self.set_threshold(self.flip_sign_fn(self._score(kwargs["valid_feats"])))
+
+    def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
+        assert self._setup_flag, "setup() must be called before postprocess()"
+        return self.flip_sign_fn(self._score(test_data))
+
+
+# Names used by the reference's README / the north star for the two headline scorers
+LaREMPostprocessor = MDLatentSpace
+LaREDPostprocessor = KDELatentSpace

@@ -1,0 +1,103 @@
+"""Multi-GPU partitioning of the scoring path (one process per GPU, torch.distributed).
+
+* Row scorers (entropy, PCA, LaREM, Mahalanobis, ViM, DDU, logit scores, ReAct/DICE/ASH) shard
+  test rows contiguously; there is NO data-path collective -- `gather_rows` only exists for a
+  caller that wants the full score vector on every rank.
+* kNN / KDE shard the BANK by contiguous row ranges; queries are replicated; each rank emits a
+  partial result and one exchange step merges them: all-gather of the per-rank top-k
+  (float64 distance, global int64 index) followed by the (distance, index) merge kernel, or a
+  MAX / SUM all-reduce of the running (max, sum-exp) pair for the KDE.
+The `*_fn` hooks let the host logic run on CPU tensors over gloo in the unit tests."""
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def row_shard(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced [lo, hi) slice of n rows for `rank` (first n % world ranks get one more)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _world(group=None):
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All-gathers row shards produced with `row_shard` into the full [n_total, ...] tensor."""
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    sizes = [row_shard(n_total, r, world) for r in range(world)]
+    maxn = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((maxn,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)])
+
+
+def knn_search_sharded(qn: torch.Tensor, bank_shard, k: int, group=None,
+                       search_fn: Optional[Callable] = None, merge_fn: Optional[Callable] = None):
+    """qn: replicated normalised queries; bank_shard: this rank's KNNBank (idx_offset = first
+    global row of the shard).  Returns (dist [Nq,k] f32, idx [Nq,k] i64, kth [Nq] f32), identical
+    on every rank and identical to a single-GPU search over the concatenated bank."""
+    if search_fn is None or merge_fn is None:
+        from . import _ops
+
+        search_fn = search_fn or (lambda q, b, kk: (lambda r: (r["dist64"], r["idx"]))(
+            _ops.knn_search(q, b, kk, want_f64=True, want_dist=False)))
+        merge_fn = merge_fn or _ops.topk_merge
+    d64, idx = search_fn(qn, bank_shard, k)
+    rank, world = _world(group)
+    if world == 1:
+        return merge_fn(d64.unsqueeze(0), idx.unsqueeze(0))
+    gd = [torch.empty_like(d64) for _ in range(world)]
+    gi = [torch.empty_like(idx) for _ in range(world)]
+    dist.all_gather(gd, d64.contiguous(), group=group)
+    dist.all_gather(gi, idx.contiguous(), group=group)
+    return merge_fn(torch.stack(gd), torch.stack(gi))
+
+
+def kde_score_sharded(q, kde_shard, group=None, partial_fn: Optional[Callable] = None) -> torch.Tensor:
+    """Log-density under the KDE of the whole bank from per-rank partial (max, sum-exp) pairs.
+    `kde_shard.n_total` must be the TOTAL bank size.  Returns float64 [Nq] on every rank."""
+    if partial_fn is None:
+        from . import _ops
+
+        partial_fn = lambda qq, kb: _ops.kde_score(qq, kb, partial=True)  # noqa: E731
+    m, s = partial_fn(q, kde_shard)
+    rank, world = _world(group)
+    M = m.clone()
+    if world > 1:
+        dist.all_reduce(M, op=dist.ReduceOp.MAX, group=group)
+    S = s.to(torch.float64) * torch.exp((m - M).to(torch.float64))
+    S = torch.where(torch.isinf(m) & (m < 0), torch.zeros_like(S), S)
+    if world > 1:
+        dist.all_reduce(S, op=dist.ReduceOp.SUM, group=group)
+    d = kde_shard.bank.shape[1]
+    h = kde_shard.bandwidth
+    log_norm = np.log(kde_shard.n_total) + 0.5 * d * np.log(2.0 * np.pi * h * h)
+    return M.to(torch.float64) + torch.log(S) - log_norm
+
+
+def merge_topk_reference(part_d: torch.Tensor, part_i: torch.Tensor):
+    """Host restatement of the merge kernel's total order (distance, index); used by the CPU
+    (gloo) tests of the exchange logic."""
+    R, nq, k = part_d.shape
+    d = part_d.permute(1, 0, 2).reshape(nq, R * k).numpy()
+    i = part_i.permute(1, 0, 2).reshape(nq, R * k).numpy()
+    dd = np.where(i < 0, np.inf, d)
+    out_d = np.full((nq, k), np.finfo(np.float32).max, np.float32)
+    out_i = np.full((nq, k), -1, np.int64)
+    for r in range(nq):
+        order = np.lexsort((i[r], dd[r]))[:k]
+        ok = i[r][order] >= 0
+        out_d[r, : ok.sum()] = dd[r][order][ok].astype(np.float32)
+        out_i[r, : ok.sum()] = i[r][order][ok]
+    return torch.from_numpy(out_d), torch.from_numpy(out_i), torch.from_numpy(out_d[:, -1].copy())

@@ -1,0 +1,195 @@
+"""CPU (-m "not gpu"): the C-ABI library loads and exports every symbol the header declares; the
+reference-facing boundary behaves like the reference where no compute is involved; the
+multi-GPU exchange logic runs over gloo with world_size 2."""
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    import ctypes
+
+    from runia_core_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "runia_b200.h")).read()
+    declared = set(re.findall(r"\b(runia_\w+)\s*\(", hdr))
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/runia_b200.h but not exported"
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert lib.runia_b200_abi_version() == 1
+    assert _lib.launch_count() >= 0
+
+
+def test_no_oracle_import_in_product():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "runia_core_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_registry_and_signatures():
+    from runia_core_b200 import inference as I
+
+    keys = {"KDE", "MD", "cMD", "KNN", "GMM", "energy", "msp", "gen", "ddu", "knn", "mahalanobis", "vim",
+            "ash", "dice", "react", "dice_react"}
+    assert set(I.postprocessors_dict) == keys and set(I.postprocessor_input_dict) == keys
+    assert I.postprocessor_input_dict["vim"] == ["features", "logits"]
+    assert I.postprocessor_input_dict["MD"] == ["latent_space_means"]
+    assert I.LaREMPostprocessor is I.MDLatentSpace and I.LaREDPostprocessor is I.KDELatentSpace
+    for cls in ("MDLatentSpace", "KDELatentSpace", "cMDLatentSpace", "KNNLatentSpace", "GMMLatentSpace"):
+        assert cls in I.__all__
+        assert list(inspect.signature(getattr(I, cls).__init__).parameters)[1:] == ["cfg"]
+    sig = lambda c: list(inspect.signature(c.__init__).parameters)[1:]  # noqa: E731
+    assert sig(I.GEN) == ["flip_sign", "gamma", "num_classes", "cfg"]
+    assert sig(I.KNN) == ["flip_sign", "k_neighbors", "cfg"]
+    assert sig(I.DICEReAct) == ["flip_sign", "dice_percentile", "react_percentile", "num_classes", "cfg"]
+    assert inspect.signature(I.ASH.__init__).parameters["ash_percentile"].default == 85
+
+    class Cfg(dict):
+        def __getattr__(self, k):
+            try:
+                return self[k]
+            except KeyError:
+                raise AttributeError(k)
+
+    assert I.KNNLatentSpace().K == 50 and I.KNNLatentSpace(Cfg(k_neighbors=20)).K == 20
+    assert I.cMDLatentSpace().num_classes == 10 and I.cMDLatentSpace(Cfg(num_classes=5)).num_classes == 5
+    with pytest.raises(AssertionError):
+        I.register_postprocessor("x", ["bogus"])(object)
+
+
+def test_ood_postprocessor_boundary():
+    from runia_core_b200.inference import Energy, get_baselines_thresholds
+
+    e = Energy(flip_sign=True)
+    assert e.flip_sign and e.threshold is None and not e._setup_flag
+    s = np.array([1.0, 2.0, 4.0])
+    assert np.array_equal(e.flip_sign_fn(s), -s)
+    d = e.flip_sign_fn({"a": s.copy()})
+    assert np.array_equal(d["a"], -s)
+    with pytest.raises(ValueError, match="scores must be a dict or ndarray"):
+        e.flip_sign_fn([1.0])
+    e.set_threshold(s)
+    assert e._setup_flag and abs(e.threshold - (s.mean() - 1.645 * s.std())) < 1e-12
+    th = get_baselines_thresholds(["raw", "m"], {"m": s})
+    assert th["raw"] == 0.0 and abs(th["m"] - e.threshold) < 1e-12
+    with pytest.raises(AssertionError, match="setup\\(\\) must be called before postprocess\\(\\)"):
+        Energy(flip_sign=False).postprocess(np.zeros((2, 3), np.float32))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_cuda():
+    from runia_core_b200.inference import MDLatentSpace
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        MDLatentSpace().setup(np.random.rand(10, 4))
+
+
+def test_install_as_runia_core():
+    import sys
+
+    import runia_core_b200 as R
+
+    saved = {k: v for k, v in sys.modules.items() if k == "runia_core" or k.startswith("runia_core.")}
+    try:
+        R.install_as_runia_core()
+        from runia_core.evaluation import get_dl_h_z  # noqa: F401
+        from runia_core.inference.postprocessors import postprocessors_dict  # noqa: F401
+        import runia_core
+
+        assert runia_core.apply_pca_ds_split is R.apply_pca_ds_split
+    finally:
+        for k in [k for k in sys.modules if k == "runia_core" or k.startswith("runia_core.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_row_shard_partition():
+    from runia_core_b200.sharding import row_shard
+
+    for n in (0, 1, 7, 10_000, 33_554_432):
+        for world in (1, 2, 3, 8):
+            spans = [row_shard(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, ret):
+    import torch.distributed as dist
+
+    from oracle import oracle_np as O
+    from runia_core_b200 import sharding as S
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        rng = np.random.RandomState(0)
+        bank = O.normalize_rows_exact(rng.randn(301, 16).astype(np.float32))
+        bank[50:60] = bank[50]  # ties across the shard boundary are broken by global index
+        q = O.normalize_rows_exact(rng.randn(17, 16).astype(np.float32))
+        k = 12
+        lo, hi = S.row_shard(len(bank), rank, world)
+
+        class Shard:
+            pass
+
+        sh = Shard()
+        sh.bank, sh.idx_offset = bank[lo:hi], lo
+
+        def search_fn(qn, b, kk):
+            B = b.bank.astype(np.float64)
+            d = np.stack([O.seq32_tree_sum((B - x.astype(np.float64)) ** 2) for x in qn.numpy()])
+            order = np.stack([np.lexsort((np.arange(d.shape[1]), row))[:kk] for row in d])
+            return (torch.from_numpy(np.take_along_axis(d, order, 1)), torch.from_numpy(order + b.idx_offset))
+
+        d, i, kth = S.knn_search_sharded(torch.from_numpy(q), sh, k, search_fn=search_fn,
+                                         merge_fn=S.merge_topk_reference)
+        D, I = O.flat_l2_search_tree(bank, q, k)
+        ok = np.array_equal(i.numpy(), I) and np.array_equal(d.numpy(), D) and np.array_equal(kth.numpy(), D[:, -1])
+
+        # KDE: partial (max, sum) per shard -> MAX / SUM all-reduce
+        class KShard:
+            pass
+
+        ks = KShard()
+        x = rng.randn(200, 8)
+        qq = rng.randn(9, 8)
+        ks.bank, ks.bandwidth, ks.n_total = torch.from_numpy(x[slice(*S.row_shard(200, rank, world))]), 1.0, 200
+
+        def partial_fn(qv, kb):
+            t = -0.5 * ((qv[:, None, :] - kb.bank[None]) ** 2).sum(-1)
+            m = t.max(1).values
+            return m, torch.exp(t - m[:, None]).sum(1)
+
+        got = S.kde_score_sharded(torch.from_numpy(qq), ks, partial_fn=partial_fn).numpy()
+        ok = ok and np.allclose(got, O.kde_score(qq, x), rtol=1e-12, atol=1e-12)
+
+        loc = torch.arange(*S.row_shard(11, rank, world), dtype=torch.float64)
+        ok = ok and torch.equal(S.gather_rows(loc, 11), torch.arange(11, dtype=torch.float64))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_exchange_gloo_world2():
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_gloo_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
