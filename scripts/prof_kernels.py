@@ -1,0 +1,70 @@
+"""Runs each hot kernel a few times at its bench shape (for `ncu --set full -k regex:...`).
+usage: python scripts/prof_kernels.py [larem] [entropy] [knn] [pca] [kde] [linear] [logits]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from runia_core_b200 import _ops  # noqa: E402
+
+which = set(sys.argv[1:]) or {"larem", "entropy", "knn", "pca"}
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev).manual_seed(0)
+REPS = 3
+
+if "larem" in which:
+    rng = np.random.RandomState(1)
+    train = rng.randn(20000, 256).astype(np.float32)
+    mean = train.mean(0, keepdims=True)
+    prec = np.linalg.inv(np.cov((train - mean).T.astype(np.float64), bias=True))
+    st = _ops.md_prepare(mean, prec)
+    X = torch.randn(4 * 1024 * 1024, 256, generator=g, device=dev)
+    for _ in range(REPS):
+        s = _ops.md_score(X, st)
+    torch.cuda.synchronize()
+    del X
+if "entropy" in which:
+    n_items, n_mc, D = 60_000, 16, 512
+    z = (torch.randn(n_items, 1, D, generator=g, device=dev) + 0.1 * torch.randn(n_items, n_mc, D, generator=g, device=dev))
+    z = z.reshape(-1, D).contiguous()
+    for _ in range(REPS):
+        h = _ops.mcd_entropy(z, n_mc)
+    torch.cuda.synchronize()
+    del z
+if "knn" in which:
+    bank = _ops.normalize_rows(torch.randn(50_000, 512, generator=g, device=dev))
+    q = _ops.normalize_rows(torch.randn(10_000, 512, generator=g, device=dev))
+    kb = _ops.knn_bank(bank)
+    for _ in range(REPS):
+        r = _ops.knn_search(q, kb, 50, check_status=False)
+    torch.cuda.synchronize()
+if "kde" in which:
+    bank = torch.randn(50_000, 256, generator=g, device=dev)
+    q = torch.randn(10_000, 256, generator=g, device=dev)
+    kb = _ops.kde_bank(bank)
+    for _ in range(REPS):
+        r = _ops.kde_score(q, kb)
+    torch.cuda.synchronize()
+if "pca" in which:
+    rng = np.random.RandomState(3)
+    stp = _ops.pca_prepare(rng.randn(512), np.linalg.qr(rng.randn(512, 256))[0].T.copy(), 1.0 + rng.rand(256), True)
+    Xp = torch.randn(2_000_000, 512, generator=g, device=dev)
+    for _ in range(REPS):
+        zz = _ops.pca_transform(Xp, stp)
+    torch.cuda.synchronize()
+if "linear" in which:
+    X = torch.relu(torch.randn(2_000_000, 512, generator=g, device=dev))
+    W = 0.05 * torch.randn(10, 512, generator=g, device=dev)
+    b = torch.randn(10, generator=g, device=dev)
+    for _ in range(REPS):
+        o = _ops.clip_linear_lse(X, W, b, clip=1.0)
+        o = _ops.ash_linear_lse(X, W, b, 77)
+    torch.cuda.synchronize()
+if "logits" in which:
+    L = torch.randn(20_000_000, 10, generator=g, device=dev)
+    for _ in range(REPS):
+        o = _ops.logit_scores(L)
+    torch.cuda.synchronize()
+print("done")
