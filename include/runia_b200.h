@@ -94,6 +94,21 @@ int runia_rownorm_score_f32(const float *X, int64_t N, int d, const float *mu, c
                             const float *sign, int mode, const float *logits, int C, float alpha,
                             double *out_f64, float *out_f32, void *stream);
 
+/* Tensor-core (tcgen05, 3xTF32, FP32 accumulation in TMEM) versions of (a2) and (a3)/(a7).
+ * runia_split_tf32: hi = tf32(x), lo = tf32(x - hi) -- the two operand planes of a fitted matrix
+ *   (factored precision, PCA components, kNN / KDE bank), computed once at setup.
+ * The streamed operand X is read as raw fp32 and split inside the kernel; products issued are
+ *   X_lo*W_hi + X_hi*W_lo + X_hi*W_hi, so the result is FP32-faithful (~2^-21 relative per product).
+ * Require K % 4 == 0 and 16-byte aligned pointers (RUNIA_E_UNSUPPORTED otherwise: use the FP32
+ * SIMT entry points above).  Arguments as for the SIMT versions, with W / components replaced by
+ * their two planes. */
+int runia_split_tf32(const float *x, int64_t total, float *hi, float *lo, void *stream);
+int runia_rownorm_score_tc(const float *X, int64_t N, int d, const float *mu, const float *Wt_hi,
+                           const float *Wt_lo, int r, const float *sign, int mode, const float *logits, int C,
+                           float alpha, double *out_f64, float *out_f32, void *stream);
+int runia_pca_transform_tc(const float *X, int64_t N, int D0, const float *mean, const float *components_hi,
+                           const float *components_lo, int d, const float *inv_scale, float *Z, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (a6) Class-conditional Mahalanobis -- inference/funcs.py:69-102 (`mahalanobis_postprocess`) and
  * inference/postprocessors.py:320-357 (`cMDLatentSpace.postprocess`):
@@ -140,6 +155,9 @@ int runia_gmm_lse_f32(const float *X, int64_t N, int d, const float *At, const f
  *     out_kth      [Nq]    float32 = out_dist[:, k-1]
  *   status [4] int32 (device): [0] rows that took the exhaustive pass, [1] != 0 if that pass
  *     overflowed its tie buffer (result invalid -> the host raises), [2..3] reserved.
+ *   Bn_tf32_hi / Bn_tf32_lo: optional pre-split planes of the bank (runia_split_tf32).  When both
+ *     are given and d % 4 == 0 the candidate pass runs on the tcgen05 tensor cores (3xTF32, TMA-fed);
+ *     NULL selects the FP32 SIMT pass.  The result is identical either way (exact re-rank).
  *   workspace: runia_knn_workspace_bytes(Nq, Nb, d, k) bytes of device memory.  1 <= k <= 240.
  * runia_topk_merge: merges R partial results ([R, Nq, k] float64 dist / int64 idx, each
  *   ascending) into the global top-k under the same total order -- the step after the NCCL
@@ -148,8 +166,9 @@ int runia_gmm_lse_f32(const float *X, int64_t N, int d, const float *At, const f
 int runia_normalize_rows(const void *in, int in_is_f64, int64_t N, int d, float *out, void *stream);
 int runia_row_sqnorm_f32(const float *X, int64_t N, int d, float *out, void *stream);
 int64_t runia_knn_workspace_bytes(int64_t Nq, int64_t Nb, int d, int k);
-int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn, const float *Bn_sqnorm, int64_t Nb,
-                         int d, int k, int64_t idx_offset, float *out_dist, double *out_dist_f64,
+int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn, const float *Bn_sqnorm,
+                         const float *Bn_tf32_hi, const float *Bn_tf32_lo, int64_t Nb, int d, int k,
+                         int64_t idx_offset, float *out_dist, double *out_dist_f64,
                          int64_t *out_idx, float *out_kth, int32_t *status, void *workspace,
                          int64_t workspace_bytes, void *stream);
 int runia_topk_merge(const double *part_dist, const int64_t *part_idx, int R, int64_t Nq, int k,
@@ -162,11 +181,12 @@ int runia_topk_merge(const double *part_dist, const int64_t *part_idx, int R, in
  * Fused distance-GEMM + online log-sum-exp.  For a bank shard pass partial outputs
  * (out_max, out_sum) [Nq] float32 (running max m and sum of exp(t - m)) and combine over ranks;
  * for a whole bank pass out_f64 and the total Nb.
+ *   B_tf32_hi / B_tf32_lo: optional pre-split planes of the bank -> tcgen05 3xTF32 pass (as for kNN).
  *   workspace: runia_kde_workspace_bytes(Nq, Nb) bytes.
  */
 int64_t runia_kde_workspace_bytes(int64_t Nq, int64_t Nb);
-int runia_kde_lse_f32(const float *Q, int64_t Nq, const float *B, int64_t Nb, int d, double bandwidth,
-                      int64_t Nb_total, double *out_f64, float *out_max, float *out_sum,
+int runia_kde_lse_f32(const float *Q, int64_t Nq, const float *B, const float *B_tf32_hi, const float *B_tf32_lo,
+                      int64_t Nb, int d, double bandwidth, int64_t Nb_total, double *out_f64, float *out_max, float *out_sum,
                       void *workspace, int64_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------

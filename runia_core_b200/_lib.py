@@ -50,11 +50,16 @@ _SIGS = {
     "runia_normalize_rows": (c_int, [_P, c_int, c_int64, c_int, _P, _P]),
     "runia_row_sqnorm_f32": (c_int, [_P, c_int64, c_int, _P, _P]),
     "runia_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int, c_int]),
-    "runia_knn_search_f32": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int, c_int64, _P, _P, _P, _P, _P,
-                                     _P, c_int64, _P]),
+    "runia_knn_search_f32": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int, c_int, c_int64, _P, _P, _P, _P,
+                                     _P, _P, c_int64, _P]),
+    "runia_split_tf32": (c_int, [_P, c_int64, _P, _P, _P]),
+    "runia_rownorm_score_tc": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int, _P, c_int, _P, c_int, c_float,
+                                       _P, _P, _P]),
+    "runia_pca_transform_tc": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int, _P, _P, _P]),
     "runia_topk_merge": (c_int, [_P, _P, c_int, c_int64, c_int, _P, _P, _P, _P]),
     "runia_kde_workspace_bytes": (c_int64, [c_int64, c_int64]),
-    "runia_kde_lse_f32": (c_int, [_P, c_int64, _P, c_int64, c_int, c_double, c_int64, _P, _P, _P, _P, c_int64, _P]),
+    "runia_kde_lse_f32": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int, c_double, c_int64, _P, _P, _P, _P,
+                                  c_int64, _P]),
     "runia_logit_scores_f32": (c_int, [_P, c_int64, c_int, c_float, c_int, _P, _P, _P, _P]),
     "runia_clip_linear_lse_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, c_float, _P, _P]),
     "runia_ash_linear_lse_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, c_int, _P, _P]),

@@ -4,6 +4,7 @@ device copies of what `setup()` computed on the host.  The reference-facing clas
 `inference/postprocessors.py` and the free functions in `evaluation/entropy.py` /
 `dimensionality_reduction.py` are built on these; `bench.py` times them directly for the
 device-resident number."""
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -14,6 +15,33 @@ from . import _lib
 from ._device import as_f32_rows, device, ptr, stream_ptr, to_device
 
 FLT_MAX = float(np.finfo(np.float32).max)
+
+# Contraction engine: "tc" = tcgen05 tensor cores, 3xTF32 operand split, FP32 accumulation in TMEM
+# (default); "simt" = FP32 FFMA kernels.  Both are FP32-faithful; the choice is by measured error
+# and speed.  The tensor-core kernels need K % 4 == 0; other shapes use "simt".
+_ENGINE = os.environ.get("RUNIA_B200_ENGINE", "tc").lower()
+
+
+def set_engine(name: str):
+    global _ENGINE
+    assert name in ("tc", "simt")
+    _ENGINE = name
+
+
+def get_engine() -> str:
+    return _ENGINE
+
+
+def split_tf32(w: torch.Tensor):
+    """fp32 matrix -> (hi, lo) tf32 planes for the tensor-core kernels."""
+    w = w.contiguous()
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    _lib.call("runia_split_tf32", w.data_ptr(), w.numel(), hi.data_ptr(), lo.data_ptr(), stream_ptr())
+    return hi, lo
+
+
+def _tc_ok(k: int) -> bool:
+    return _ENGINE == "tc" and k % 4 == 0
 
 
 def _empty(shape, dtype):
@@ -57,6 +85,7 @@ class PCAState:
     inv_scale: Optional[torch.Tensor]  # [d] f32 or None
     d: int
     D0: int
+    planes: Optional[tuple] = None     # (hi, lo) tf32 planes of `components`
 
 
 def pca_prepare(mean, components, explained_variance, whiten) -> PCAState:
@@ -69,15 +98,22 @@ def pca_prepare(mean, components, explained_variance, whiten) -> PCAState:
         inv = to_device((1.0 / scale).astype(np.float32))
     m64 = None if mean is None else to_device(np.asarray(mean, np.float64).reshape(-1))
     m32 = None if mean is None else m64.to(torch.float32)
-    return PCAState(m32, m64, to_device(comp.astype(np.float32)), inv, comp.shape[0], comp.shape[1])
+    c32 = to_device(comp.astype(np.float32))
+    return PCAState(m32, m64, c32, inv, comp.shape[0], comp.shape[1],
+                    split_tf32(c32) if comp.shape[1] % 4 == 0 else None)
 
 
 def pca_transform(x, st: PCAState) -> torch.Tensor:
     xf, centered = as_f32_rows(x, st.mean_f64)
     n = xf.shape[0]
     z = _empty((n, st.d), torch.float32)
-    _lib.call("runia_pca_transform_f32", xf.data_ptr(), n, st.D0, None if centered else ptr(st.mean_f32),
-              st.components.data_ptr(), st.d, ptr(st.inv_scale), z.data_ptr(), stream_ptr())
+    mean = None if centered else ptr(st.mean_f32)
+    if _tc_ok(st.D0) and st.planes is not None:
+        _lib.call("runia_pca_transform_tc", xf.data_ptr(), n, st.D0, mean, st.planes[0].data_ptr(),
+                  st.planes[1].data_ptr(), st.d, ptr(st.inv_scale), z.data_ptr(), stream_ptr())
+    else:
+        _lib.call("runia_pca_transform_f32", xf.data_ptr(), n, st.D0, mean, st.components.data_ptr(), st.d,
+                  ptr(st.inv_scale), z.data_ptr(), stream_ptr())
     return z
 
 
@@ -109,13 +145,25 @@ class MDState:
     sign: Optional[torch.Tensor]
     d: int
     r: int
+    planes: Optional[tuple] = None
 
 
 def md_prepare(mean, precision) -> MDState:
     Wt, sign = factor_precision(precision)
     mu64 = to_device(np.asarray(mean, np.float64).reshape(-1))
     sg = None if np.all(sign == 1.0) else to_device(sign.astype(np.float32))
-    return MDState(mu64.to(torch.float32), mu64, to_device(Wt.astype(np.float32)), sg, Wt.shape[1], Wt.shape[0])
+    w32 = to_device(Wt.astype(np.float32))
+    return MDState(mu64.to(torch.float32), mu64, w32, sg, Wt.shape[1], Wt.shape[0],
+                   split_tf32(w32) if Wt.shape[1] % 4 == 0 else None)
+
+
+def _rownorm(xf, n, d, mu, W, planes, r, sign, mode, logits, C, alpha, o64, o32):
+    if _tc_ok(d) and planes is not None:
+        _lib.call("runia_rownorm_score_tc", xf.data_ptr(), n, d, mu, planes[0].data_ptr(), planes[1].data_ptr(), r,
+                  sign, mode, logits, C, alpha, o64, o32, stream_ptr())
+    else:
+        _lib.call("runia_rownorm_score_f32", xf.data_ptr(), n, d, mu, W.data_ptr(), r, sign, mode, logits, C, alpha,
+                  o64, o32, stream_ptr())
 
 
 def md_score(x, st: MDState, out_dtype=torch.float64) -> torch.Tensor:
@@ -124,8 +172,8 @@ def md_score(x, st: MDState, out_dtype=torch.float64) -> torch.Tensor:
     out = _empty((n,), out_dtype)
     o64 = out.data_ptr() if out_dtype == torch.float64 else None
     o32 = out.data_ptr() if out_dtype == torch.float32 else None
-    _lib.call("runia_rownorm_score_f32", xf.data_ptr(), n, st.d, None if centered else st.mu_f32.data_ptr(),
-              st.Wt.data_ptr(), st.r, ptr(st.sign), _lib.ROWNORM_MD, None, 0, 0.0, o64, o32, stream_ptr())
+    _rownorm(xf, n, st.d, None if centered else st.mu_f32.data_ptr(), st.Wt, st.planes, st.r, ptr(st.sign),
+             _lib.ROWNORM_MD, None, 0, 0.0, o64, o32)
     return out
 
 
@@ -137,12 +185,15 @@ class VimState:
     alpha: float
     d: int
     r: int
+    planes: Optional[tuple] = None
 
 
 def vim_prepare(u, NS, alpha) -> VimState:
     u64 = to_device(np.asarray(u, np.float64).reshape(-1))
     NSt = np.ascontiguousarray(np.asarray(NS, np.float64).T.astype(np.float32))
-    return VimState(u64.to(torch.float32), u64, to_device(NSt), float(alpha), NSt.shape[1], NSt.shape[0])
+    n32 = to_device(NSt)
+    return VimState(u64.to(torch.float32), u64, n32, float(alpha), NSt.shape[1], NSt.shape[0],
+                    split_tf32(n32) if NSt.shape[1] % 4 == 0 else None)
 
 
 def vim_score(x, logits, st: VimState) -> torch.Tensor:
@@ -150,9 +201,8 @@ def vim_score(x, logits, st: VimState) -> torch.Tensor:
     lg = to_device(logits, torch.float32)
     n = xf.shape[0]
     out = _empty((n,), torch.float32)
-    _lib.call("runia_rownorm_score_f32", xf.data_ptr(), n, st.d, None if centered else st.u_f32.data_ptr(),
-              st.NSt.data_ptr(), st.r, None, _lib.ROWNORM_VIM, lg.data_ptr(), lg.shape[1], st.alpha,
-              None, out.data_ptr(), stream_ptr())
+    _rownorm(xf, n, st.d, None if centered else st.u_f32.data_ptr(), st.NSt, st.planes, st.r, None,
+             _lib.ROWNORM_VIM, lg.data_ptr(), lg.shape[1], st.alpha, None, out.data_ptr())
     return out
 
 
@@ -161,8 +211,8 @@ def residual_norm(x, st: VimState) -> torch.Tensor:
     xf, centered = as_f32_rows(x, st.u_f64)
     n = xf.shape[0]
     out = _empty((n,), torch.float32)
-    _lib.call("runia_rownorm_score_f32", xf.data_ptr(), n, st.d, None if centered else st.u_f32.data_ptr(),
-              st.NSt.data_ptr(), st.r, None, _lib.ROWNORM_MD, None, 0, 0.0, None, out.data_ptr(), stream_ptr())
+    _rownorm(xf, n, st.d, None if centered else st.u_f32.data_ptr(), st.NSt, st.planes, st.r, None,
+             _lib.ROWNORM_MD, None, 0, 0.0, None, out.data_ptr())
     return torch.sqrt(torch.clamp(-out, min=0))
 
 
@@ -276,10 +326,14 @@ class KNNBank:
     bank: torch.Tensor    # [Nb, d] float32, already normalised
     sqnorm: torch.Tensor  # [Nb]
     idx_offset: int = 0
+    planes: Optional[tuple] = None  # tf32 (hi, lo) planes for the tensor-core candidate pass
 
 
-def knn_bank(bank_normed: torch.Tensor, idx_offset: int = 0) -> KNNBank:
-    return KNNBank(bank_normed, row_sqnorm(bank_normed), idx_offset)
+def knn_bank(bank_normed: torch.Tensor, idx_offset: int = 0, planes: Optional[bool] = None) -> KNNBank:
+    if planes is None:
+        planes = _ENGINE == "tc"
+    pl = split_tf32(bank_normed) if (planes and bank_normed.shape[1] % 4 == 0) else None
+    return KNNBank(bank_normed, row_sqnorm(bank_normed), idx_offset, pl)
 
 
 class KNNOverflow(RuntimeError):
@@ -306,8 +360,10 @@ def knn_search(qn: torch.Tensor, bank: KNNBank, k: int, want_idx=True, want_dist
         raise NotImplementedError(f"kNN: k={k} outside [1, 240]")
     ws = _empty((ws_bytes,), torch.uint8)
     status = _empty((4,), torch.int32)
-    _lib.call("runia_knn_search_f32", qn.data_ptr(), nq, bank.bank.data_ptr(), bank.sqnorm.data_ptr(), nb, d, k,
-              bank.idx_offset, ptr(res["dist"]), ptr(res["dist64"]), ptr(res["idx"]), res["kth"].data_ptr(),
+    use_tc = _tc_ok(d) and bank.planes is not None
+    _lib.call("runia_knn_search_f32", qn.data_ptr(), nq, bank.bank.data_ptr(), bank.sqnorm.data_ptr(),
+              bank.planes[0].data_ptr() if use_tc else None, bank.planes[1].data_ptr() if use_tc else None,
+              nb, d, k, bank.idx_offset, ptr(res["dist"]), ptr(res["dist64"]), ptr(res["idx"]), res["kth"].data_ptr(),
               status.data_ptr(), ws.data_ptr(), ws_bytes, stream_ptr())
     if check_status:
         st = status.cpu()
@@ -338,6 +394,7 @@ class KDEBank:
     center: torch.Tensor    # [d] float64
     bandwidth: float
     n_total: int
+    planes: Optional[tuple] = None
 
 
 def kde_bank(train, bandwidth=1.0, center=None, n_total=None) -> KDEBank:
@@ -349,7 +406,8 @@ def kde_bank(train, bandwidth=1.0, center=None, n_total=None) -> KDEBank:
     out = _empty((n, d), torch.float32)
     _lib.call("runia_center_cast", t.data_ptr(), 1 if t.dtype == torch.float64 else 0, n, d, c.data_ptr(),
               out.data_ptr(), stream_ptr())
-    return KDEBank(out, c, float(bandwidth), int(n_total if n_total is not None else n))
+    pl = split_tf32(out) if (_ENGINE == "tc" and d % 4 == 0) else None
+    return KDEBank(out, c, float(bandwidth), int(n_total if n_total is not None else n), pl)
 
 
 def _kde_stage_queries(q, kb: KDEBank):
@@ -371,14 +429,17 @@ def kde_score(q, kb: KDEBank, partial=False):
     nb = kb.bank.shape[0]
     ws_bytes = int(_lib.raw("runia_kde_workspace_bytes")(nq, nb)) if nq else 0
     ws = _empty((max(ws_bytes, 1),), torch.uint8)
+    use_tc = _tc_ok(d) and kb.planes is not None
+    hi = kb.planes[0].data_ptr() if use_tc else None
+    lo = kb.planes[1].data_ptr() if use_tc else None
     if partial:
         m = _empty((nq,), torch.float32)
         s = _empty((nq,), torch.float32)
-        _lib.call("runia_kde_lse_f32", qc.data_ptr(), nq, kb.bank.data_ptr(), nb, d, kb.bandwidth, kb.n_total,
+        _lib.call("runia_kde_lse_f32", qc.data_ptr(), nq, kb.bank.data_ptr(), hi, lo, nb, d, kb.bandwidth, kb.n_total,
                   None, m.data_ptr(), s.data_ptr(), ws.data_ptr(), ws_bytes, stream_ptr())
         return m, s
     out = _empty((nq,), torch.float64)
-    _lib.call("runia_kde_lse_f32", qc.data_ptr(), nq, kb.bank.data_ptr(), nb, d, kb.bandwidth, kb.n_total,
+    _lib.call("runia_kde_lse_f32", qc.data_ptr(), nq, kb.bank.data_ptr(), hi, lo, nb, d, kb.bandwidth, kb.n_total,
               out.data_ptr(), None, None, ws.data_ptr(), ws_bytes, stream_ptr())
     return out
 

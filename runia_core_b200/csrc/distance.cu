@@ -490,9 +490,8 @@ __global__ void __launch_bounds__(256) kde_finalize_kernel(const float *__restri
   if (out_sum) out_sum[row] = (float)S;
 }
 
-// Bank splits (grid.y): pick the split count that fills whole waves of the 2-CTA/SM grid best.
-static void pick_splits(int64_t rowblocks, int64_t panels, int max_splits, int &splits, int64_t &pps) {
-  const int64_t slots = 2 * (int64_t)kNumSMs;
+// Bank splits (grid.y): pick the split count that fills whole waves of the resident-CTA grid best.
+static void pick_splits(int64_t rowblocks, int64_t panels, int max_splits, int64_t slots, int &splits, int64_t &pps) {
   int64_t best_s = 1;
   double best_u = -1.0;
   for (int64_t s = 1; s <= max_splits && s <= (panels > 0 ? panels : 1); ++s) {
@@ -509,12 +508,15 @@ static void pick_splits(int64_t rowblocks, int64_t panels, int max_splits, int &
   if (splits < 1) splits = 1;
 }
 
-static KnnPlan make_knn_plan(int64_t Nq, int64_t Nb, int k) {
+// tensor-core pass: 128 x 256 panels, 1 CTA / SM;  SIMT pass: 128 x 128 panels, 2 CTAs / SM
+static KnnPlan make_knn_plan(int64_t Nq, int64_t Nb, int k, bool tensor) {
   KnnPlan p;
   p.kcap = 64;
   while (p.kcap < k + 8) p.kcap <<= 1;
-  p.capp = p.kcap + BN <= 256 ? 256 : 512;
-  pick_splits(ceil_div(Nq, BM), ceil_div(Nb, BN), 16, p.splits, p.panels_per_split);
+  const int pw = tensor ? 256 : BN;
+  p.capp = 256;
+  while (p.capp < p.kcap + pw) p.capp <<= 1;
+  pick_splits(ceil_div(Nq, BM), ceil_div(Nb, pw), 16, tensor ? kNumSMs : 2 * kNumSMs, p.splits, p.panels_per_split);
   return p;
 }
 
@@ -542,6 +544,16 @@ static KnnWorkspace knn_layout(int64_t Nq, const KnnPlan &p) {
   w.total = o;
   return w;
 }
+
+namespace tc {
+bool usable(const void *A, int K, const void *B_hi, const void *B_lo);
+int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
+                             const float *bn, int64_t Nb, int d, int kcap, int capp, int splits,
+                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, cudaStream_t st);
+int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
+                          const float *bn, int64_t Nb, int d, float scale, int splits, int64_t panels_per_split,
+                          float *part_m, float *part_s, cudaStream_t st);
+}  // namespace tc
 
 }  // namespace runia
 
@@ -587,11 +599,14 @@ extern "C" int runia_row_sqnorm_f32(const float *X, int64_t N, int d, float *out
 extern "C" int64_t runia_knn_workspace_bytes(int64_t Nq, int64_t Nb, int d, int k) {
   if (Nq <= 0 || Nb <= 0 || k <= 0 || k > 240) return 0;
   (void)d;
-  return (int64_t)knn_layout(Nq, make_knn_plan(Nq, Nb, k)).total;
+  const size_t a = knn_layout(Nq, make_knn_plan(Nq, Nb, k, false)).total;
+  const size_t b = knn_layout(Nq, make_knn_plan(Nq, Nb, k, true)).total;
+  return (int64_t)(a > b ? a : b);
 }
 
 extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn, const float *Bn_sqnorm,
-                                    int64_t Nb, int d, int k, int64_t idx_offset, float *out_dist,
+                                    const float *Bn_hi, const float *Bn_lo, int64_t Nb, int d, int k,
+                                    int64_t idx_offset, float *out_dist,
                                     double *out_dist_f64, int64_t *out_idx, float *out_kth, int32_t *status,
                                     void *workspace, int64_t workspace_bytes, void *stream) {
   RUNIA_REQUIRE(Nq >= 0 && Nb > 0 && d > 0, RUNIA_E_BADARG, "knn_search: bad sizes Nq=%lld Nb=%lld d=%d",
@@ -600,7 +615,8 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   RUNIA_REQUIRE(Nb < (int64_t)0x7fffffff, RUNIA_E_UNSUPPORTED, "knn_search: bank shard too large");
   if (Nq == 0) return RUNIA_OK;
   RUNIA_REQUIRE(Qn && Bn && Bn_sqnorm && status && workspace, RUNIA_E_BADARG, "knn_search: null pointer");
-  const KnnPlan plan = make_knn_plan(Nq, Nb, k);
+  const bool tensor = Bn_hi && Bn_lo && tc::usable(Qn, d, Bn_hi, Bn_lo);
+  const KnnPlan plan = make_knn_plan(Nq, Nb, k, tensor);
   const KnnWorkspace w = knn_layout(Nq, plan);
   RUNIA_REQUIRE((size_t)workspace_bytes >= w.total, RUNIA_E_WORKSPACE, "knn_search: workspace %lld < %lld bytes",
                 (long long)workspace_bytes, (long long)w.total);
@@ -615,20 +631,27 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   RUNIA_CUDA(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st));
   row_sqnorm_kernel<<<(unsigned)ceil_div(Nq, 8), 256, 0, st>>>(Qn, Nq, d, qn);
 
-  const size_t dyn1 = (size_t)8 * plan.capp * 8;
-  static bool attr1 = false;
-  if (!attr1) {
-    RUNIA_CUDA(cudaFuncSetAttribute(knn_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr1 = true;
+  if (tensor) {
+    const int rc = tc::launch_knn_candidates_tc(Qn, qn, Nq, Bn_hi, Bn_lo, Bn_sqnorm, Nb, d, plan.kcap, plan.capp,
+                                                plan.splits, plan.panels_per_split, buf_d, buf_i, st);
+    if (rc) return rc;
+  } else {
+    const size_t dyn1 = (size_t)8 * plan.capp * 8;
+    static bool attr1 = false;
+    if (!attr1) {
+      RUNIA_CUDA(cudaFuncSetAttribute(knn_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr1 = true;
+    }
+    dim3 grid1((unsigned)ceil_div(Nq, BM), (unsigned)plan.splits);
+    knn_candidates_kernel<<<grid1, GEMM_THREADS, dyn1, st>>>(Qn, qn, Nq, Bn, Bn_sqnorm, Nb, d, plan, buf_d, buf_i);
   }
-  dim3 grid1((unsigned)ceil_div(Nq, BM), (unsigned)plan.splits);
-  knn_candidates_kernel<<<grid1, GEMM_THREADS, dyn1, st>>>(Qn, qn, Nq, Bn, Bn_sqnorm, Nb, d, plan, buf_d, buf_i);
 
   KnnRerankArgs a;
   a.Q = Qn; a.B = Bn; a.Nq = Nq; a.Nb = Nb; a.d = d; a.k = k; a.plan = plan;
   a.buf_d = buf_d; a.buf_i = buf_i;
   // |approx - exact| <= (2K + 8) * 2^-24 for unit-norm rows (DESIGN.md "kNN certification")
-  a.eps = (float)((2.0 * d + 8.0) * 5.9604644775390625e-08 * 1.25);
+  //   3xTF32: operand split error 2^-20 per unit of sum|q_i b_i| plus FP32 accumulation -> doubled bound
+  a.eps = (float)((2.0 * d + 8.0) * 5.9604644775390625e-08 * (tensor ? 2.5 : 1.25));
   a.idx_offset = idx_offset;
   a.out_dist = out_dist; a.out_dist64 = out_dist_f64; a.out_idx = out_idx; a.out_kth = out_kth;
   a.flag_count = flag_count;
@@ -662,29 +685,33 @@ extern "C" int runia_topk_merge(const double *part_dist, const int64_t *part_idx
   return finish_launch("topk_merge");
 }
 
-static void kde_plan(int64_t Nq, int64_t Nb, int &splits, int64_t &pps) {
-  pick_splits(ceil_div(Nq, BM), ceil_div(Nb, BN), 64, splits, pps);
+static void kde_plan(int64_t Nq, int64_t Nb, bool tensor, int &splits, int64_t &pps) {
+  pick_splits(ceil_div(Nq, BM), ceil_div(Nb, tensor ? 256 : BN), 64, tensor ? kNumSMs : 2 * kNumSMs, splits, pps);
 }
 
 extern "C" int64_t runia_kde_workspace_bytes(int64_t Nq, int64_t Nb) {
   if (Nq <= 0 || Nb <= 0) return 0;
-  int splits;
+  int splits, s2;
   int64_t pps;
-  kde_plan(Nq, Nb, splits, pps);
+  kde_plan(Nq, Nb, false, splits, pps);
+  kde_plan(Nq, Nb, true, s2, pps);
+  if (s2 > splits) splits = s2;
   return (int64_t)(((size_t)Nq * 4 + 255) / 256 * 256 + ((size_t)Nb * 4 + 255) / 256 * 256 +
                    2 * (((size_t)Nq * splits * 4 + 255) / 256 * 256));
 }
 
-extern "C" int runia_kde_lse_f32(const float *Q, int64_t Nq, const float *B, int64_t Nb, int d, double bandwidth,
+extern "C" int runia_kde_lse_f32(const float *Q, int64_t Nq, const float *B, const float *B_hi, const float *B_lo,
+                                 int64_t Nb, int d, double bandwidth,
                                  int64_t Nb_total, double *out_f64, float *out_max, float *out_sum,
                                  void *workspace, int64_t workspace_bytes, void *stream) {
   RUNIA_REQUIRE(Nq >= 0 && Nb > 0 && d > 0 && bandwidth > 0 && Nb_total >= Nb, RUNIA_E_BADARG, "kde_lse: bad sizes");
   if (Nq == 0) return RUNIA_OK;
   RUNIA_REQUIRE(Q && B && workspace && (out_f64 || (out_max && out_sum)), RUNIA_E_BADARG, "kde_lse: null pointer");
   RUNIA_REQUIRE(workspace_bytes >= runia_kde_workspace_bytes(Nq, Nb), RUNIA_E_WORKSPACE, "kde_lse: workspace too small");
+  const bool tensor = B_hi && B_lo && tc::usable(Q, d, B_hi, B_lo);
   int splits;
   int64_t pps;
-  kde_plan(Nq, Nb, splits, pps);
+  kde_plan(Nq, Nb, tensor, splits, pps);
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char *ws = (unsigned char *)workspace;
   size_t o = 0;
@@ -696,8 +723,13 @@ extern "C" int runia_kde_lse_f32(const float *Q, int64_t Nq, const float *B, int
   row_sqnorm_kernel<<<(unsigned)ceil_div(Nb, 8), 256, 0, st>>>(B, Nb, d, bn);
   const double LOG2E = 1.4426950408889634073599246810019;
   const float scale = (float)(-0.5 / (bandwidth * bandwidth) * LOG2E);
-  dim3 grid((unsigned)ceil_div(Nq, BM), (unsigned)splits);
-  kde_partial_kernel<<<grid, GEMM_THREADS, 0, st>>>(Q, qn, Nq, B, bn, Nb, d, scale, splits, pps, pm, ps);
+  if (tensor) {
+    const int rc = tc::launch_kde_partial_tc(Q, qn, Nq, B_hi, B_lo, bn, Nb, d, scale, splits, pps, pm, ps, st);
+    if (rc) return rc;
+  } else {
+    dim3 grid((unsigned)ceil_div(Nq, BM), (unsigned)splits);
+    kde_partial_kernel<<<grid, GEMM_THREADS, 0, st>>>(Q, qn, Nq, B, bn, Nb, d, scale, splits, pps, pm, ps);
+  }
   const double log_norm = log((double)Nb_total) + 0.5 * d * log(2.0 * 3.14159265358979323846 * bandwidth * bandwidth);
   kde_finalize_kernel<<<(unsigned)ceil_div(Nq, 256), 256, 0, st>>>(pm, ps, Nq, splits, log_norm, out_f64, out_max, out_sum);
   count_launch(4);

@@ -1,0 +1,370 @@
+// 3xTF32 tensor-core contraction for sm_100a: tcgen05.mma (kind::tf32) with FP32 accumulators in
+// TMEM, operands staged in 128B-swizzled shared memory.
+//
+//   acc[m, n] = sum_k f(A[m0+m, k]) * B[n0+n, k]       A: [M, K] fp32 (streamed), B: [NB, K] fp32
+//
+// FP32-faithful by operand splitting: x = hi + lo with hi = tf32(x), lo = tf32(x - hi); the kernel
+// issues  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is ~2^-22 relative).
+//
+// Roles inside one CTA (384 threads, 1 CTA / SM, 128 x 256 output panel):
+//   warp 0      TMA producer for the two B planes (pre-split in HBM: setup-time for weights/banks)
+//   warp 1      MMA issuer (one elected lane), 12 tcgen05.mma per 32-wide k-block
+//   warp 2      TMEM allocator (512 columns = two 128 x 256 accumulators, double buffered)
+//   warps 4-7   epilogue: tcgen05.ld 32 columns at a time; thread t owns output row t, so every
+//               row-wise reduction (sum of squares, log-sum-exp, top-k filter) is thread-local
+//   warps 8-11  A converters: coalesced fp32 global loads -> fused prologue (subtract centre,
+//               clip) -> hi/lo split -> st.shared in the UMMA 128B-swizzle layout.  The streamed
+//               operand is therefore read from HBM exactly once, as raw fp32.
+// Pipelines: smem ring (full/empty mbarriers; `full` collects the TMA bytes and the 128 converter
+// arrivals), TMEM ring (tmem_full via tcgen05.commit, tmem_empty from the epilogue warps).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace runia {
+namespace tc {
+
+constexpr int TM = 128;        // rows per CTA tile (UMMA M)
+constexpr int TN = 256;        // columns per panel (UMMA N)
+constexpr int TK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int STAGES = 2;
+constexpr int THREADS = 384;
+constexpr int A_PLANE_BYTES = TM * TK * 4;  // 16 KB
+constexpr int B_PLANE_BYTES = TN * TK * 4;  // 32 KB
+constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;  // 96 KB
+constexpr int SMEM_BAR_BYTES = 256;
+constexpr int SMEM_ALIGN = 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, one CTA
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 consecutive columns -> 32 registers per thread (thread t <-> lane base + t)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128B-swizzle shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address
+  d |= (uint64_t)1 << 16;                   // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                   // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=TN
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+struct Prologue {
+  const float *sub;  // [K] or nullptr
+  float clip;        // +inf = none
+};
+
+struct Tile {
+  int64_t m0;       // first row of this CTA
+  int panel_lo;     // first TN-wide panel of B
+  int panel_hi;     // one past the last panel
+};
+
+// The epilogue policy E provides:
+//   __device__ void begin(int row_in_tile, int64_t row)          -- once per thread
+//   __device__ void consume(int64_t col0, const float (&v)[32], int warp_in_epi, int lane)
+//       32 consecutive columns col0.. of this thread's row
+//   __device__ void panel_done(int panel)                        -- after a whole panel
+//   __device__ void finish()                                     -- after the last panel
+template <class E>
+__device__ __forceinline__ void run_tile(const float *__restrict__ A, int64_t M, int K, const Prologue pro,
+                                         const CUtensorMap *tmB_hi, const CUtensorMap *tmB_lo, const Tile tile,
+                                         E &epi, unsigned char *smem_raw) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // carve shared memory (1024-byte aligned for the 128B swizzle)
+  const uint32_t base = (smem_u32(smem_raw) + SMEM_ALIGN - 1) & ~(uint32_t)(SMEM_ALIGN - 1);
+  unsigned char *gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar0 = base + STAGES * STAGE_BYTES;
+  auto sA_hi = [&](int s) { return base + s * STAGE_BYTES; };
+  auto sA_lo = [&](int s) { return base + s * STAGE_BYTES + A_PLANE_BYTES; };
+  auto sB_hi = [&](int s) { return base + s * STAGE_BYTES + 2 * A_PLANE_BYTES; };
+  auto sB_lo = [&](int s) { return base + s * STAGE_BYTES + 2 * A_PLANE_BYTES + B_PLANE_BYTES; };
+  auto full_bar = [&](int s) { return bar0 + 8 * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8 * (STAGES + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8 * (2 * STAGES + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8 * (2 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar0 + 8 * (2 * STAGES + 4);
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(gbase + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int nkb = (K + TK - 1) / TK;
+  const int n_panels = tile.panel_hi - tile.panel_lo;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(tmB_hi);
+    tma_prefetch_desc(tmB_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1 + 128);  // TMA expect_tx arrival + 128 converter threads
+      mbar_init(empty_bar(s), 1);       // tcgen05.commit
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);    // tcgen05.commit
+      mbar_init(tempty_bar(b), 128);  // epilogue threads
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (B planes) ------------------------------
+    if (lane == 0) {
+      int it = 0;
+      for (int p = 0; p < n_panels; ++p) {
+        const int n0 = (tile.panel_lo + p) * TN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), 2 * B_PLANE_BYTES);
+          tma_load_2d(sB_hi(s), tmB_hi, full_bar(s), kb * TK, n0);
+          tma_load_2d(sB_lo(s), tmB_lo, full_bar(s), kb * TK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    int it = 0;
+    for (int p = 0; p < n_panels; ++p) {
+      const int ab = p & 1;
+      const uint32_t aph = (p >> 1) & 1;
+      mbar_wait(tempty_bar(ab), aph ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)(ab * TN);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t dA_hi = make_smem_desc(sA_hi(s)), dA_lo = make_smem_desc(sA_lo(s));
+          const uint64_t dB_hi = make_smem_desc(sB_hi(s)), dB_lo = make_smem_desc(sB_lo(s));
+#pragma unroll
+          for (int k4 = 0; k4 < TK / 8; ++k4) {
+            const uint64_t adv = (uint64_t)((k4 * 8 * 4) >> 4);  // 32 bytes per UMMA_K=8 step
+            umma_tf32(tacc, dA_lo + adv, dB_hi + adv, kInstrDesc, (kb | k4) != 0 ? 1u : 0u);
+            umma_tf32(tacc, dA_hi + adv, dB_lo + adv, kInstrDesc, 1u);
+            umma_tf32(tacc, dA_hi + adv, dB_hi + adv, kInstrDesc, 1u);
+          }
+          umma_commit(empty_bar(s));                       // smem slot reusable when these MMAs retire
+          if (kb == nkb - 1) umma_commit(tfull_bar(ab));   // accumulator ready for the epilogue
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------ epilogue ------------------------------
+    const int ew = warp - 4;  // == warp % 4: TMEM lane quadrant this warp may read
+    const int row_in_tile = ew * 32 + lane;
+    epi.begin(row_in_tile, tile.m0 + row_in_tile);
+    for (int p = 0; p < n_panels; ++p) {
+      const int ab = p & 1;
+      const uint32_t aph = (p >> 1) & 1;
+      mbar_wait(tfull_bar(ab), aph);
+      tc_fence_after();
+      const int64_t n0 = (int64_t)(tile.panel_lo + p) * TN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * TN + c0), v);
+        epi.consume(n0 + c0, v, ew, lane);
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(ab));
+      epi.panel_done(tile.panel_lo + p);
+    }
+    epi.finish();
+  } else if (warp >= 8) {
+    // ------------------------------ A converters ------------------------------
+    const int ct = threadIdx.x - 256;  // 0..127
+    const int chunk = ct & 7;          // 16-byte chunk inside the 128-byte k-block row
+    const int r0 = ct >> 3;            // rows r0, r0+16, ..., r0+112
+    const bool vec_ok = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    auto load_block = [&](int kb, float4 (&x)[8]) {
+      const int k = kb * TK + chunk * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t row = tile.m0 + r0 + 16 * i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < M) {
+          const float *src = A + row * (int64_t)K + k;
+          if (vec_ok && k + 3 < K) {
+            v = __ldg(reinterpret_cast<const float4 *>(src));
+          } else {
+            if (k + 0 < K) v.x = __ldg(src + 0);
+            if (k + 1 < K) v.y = __ldg(src + 1);
+            if (k + 2 < K) v.z = __ldg(src + 2);
+            if (k + 3 < K) v.w = __ldg(src + 3);
+          }
+        }
+        x[i] = v;
+      }
+    };
+    int it = 0;
+    for (int p = 0; p < n_panels; ++p) {
+      float4 x[8];
+      load_block(0, x);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        // prologue + split in registers while waiting for the slot
+        const int k = kb * TK + chunk * 4;
+        float4 sub = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pro.sub) {
+          if (k + 0 < K) sub.x = __ldg(pro.sub + k + 0);
+          if (k + 1 < K) sub.y = __ldg(pro.sub + k + 1);
+          if (k + 2 < K) sub.z = __ldg(pro.sub + k + 2);
+          if (k + 3 < K) sub.w = __ldg(pro.sub + k + 3);
+        }
+        float4 hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float e[4] = {x[i].x - sub.x, x[i].y - sub.y, x[i].z - sub.z, x[i].w - sub.w};
+          float h[4], l[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (pro.clip < INFINITY) e[q] = e[q] > pro.clip ? pro.clip : e[q];
+            if (k + q >= K) e[q] = 0.f;
+            h[q] = to_tf32(e[q]);
+            l[q] = to_tf32(e[q] - h[q]);
+          }
+          hi[i] = make_float4(h[0], h[1], h[2], h[3]);
+          lo[i] = make_float4(l[0], l[1], l[2], l[3]);
+        }
+        if (kb + 1 < nkb) load_block(kb + 1, x);  // next block's loads in flight during the wait
+        mbar_wait(empty_bar(s), ph ^ 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + 16 * i;
+          const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sA_hi(s) + off), "f"(hi[i].x), "f"(hi[i].y),
+                       "f"(hi[i].z), "f"(hi[i].w)
+                       : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sA_lo(s) + off), "f"(lo[i].x), "f"(lo[i].y),
+                       "f"(lo[i].z), "f"(lo[i].w)
+                       : "memory");
+        }
+        fence_proxy_async();  // make the generic-proxy stores visible to the tensor core
+        mbar_arrive(full_bar(s));
+      }
+    }
+  }
+  // ------------------------------ teardown ------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+constexpr size_t kSmemBytes = (size_t)STAGES * STAGE_BYTES + SMEM_BAR_BYTES + SMEM_ALIGN;
+
+}  // namespace tc
+}  // namespace runia

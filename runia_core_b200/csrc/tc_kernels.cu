@@ -1,0 +1,476 @@
+// tcgen05 (3xTF32) versions of the contraction-shaped scorers: LaREM / ViM row norm (a3, a7),
+// PCA projection (a2), kNN candidate filter (a5) and KDE log-sum-exp (a4).  See tc_gemm.cuh for the
+// kernel anatomy.  The SIMT kernels in score_gemm.cu / distance.cu stay as the FP32 reference
+// path (K % 4 != 0, unaligned pointers) and as the accuracy yardstick (DESIGN.md "3xTF32 vs FP32").
+#include <cuda.h>
+
+#include <mutex>
+
+#include "tc_gemm.cuh"
+
+namespace runia {
+namespace tc {
+
+// ---------------------------------------------------------------------------------------------
+// operand split: hi = tf32(x), lo = tf32(x - hi)          (weights / banks, once at setup)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ x, int64_t total,
+                                                         float *__restrict__ hi, float *__restrict__ lo) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const float v = x[e];
+    const float h = to_tf32(v);
+    hi[e] = h;
+    lo[e] = to_tf32(v - h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogues
+// ---------------------------------------------------------------------------------------------
+struct RowNormEpi {  // MD: -sum sign*v^2 ; ViM: -alpha*sqrt(sum v^2) + lse(logits)
+  const float *sign;
+  int r, mode, C;
+  const float *logits;
+  float alpha;
+  double *out64;
+  float *out32;
+  int64_t M;
+  int64_t row;
+  float acc;
+  __device__ void begin(int, int64_t row_) {
+    row = row_;
+    acc = 0.f;
+  }
+  __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
+    if (sign) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float s = (col0 + j < r) ? __ldg(sign + col0 + j) : 0.f;
+        acc = fmaf(s * v[j], v[j], acc);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc = fmaf(v[j], v[j], acc);  // columns >= r are exact zeros (TMA zero fill)
+    }
+  }
+  __device__ void panel_done(int) {}
+  __device__ void finish() {
+    if (row >= M) return;
+    float sc;
+    if (mode == RUNIA_ROWNORM_MD) {
+      sc = -acc;
+    } else {
+      const float *l = logits + row * (int64_t)C;
+      float m = -INFINITY;
+      for (int c = 0; c < C; ++c) m = fmaxf(m, l[c]);
+      float s = 0.f;
+      for (int c = 0; c < C; ++c) s += expf(l[c] - m);
+      sc = -alpha * sqrtf(fmaxf(acc, 0.f)) + (m + logf(s));
+    }
+    if (out64) out64[row] = (double)sc;
+    if (out32) out32[row] = sc;
+  }
+};
+
+struct PcaEpi {  // Z[row, col] = v * inv_scale[col]
+  const float *inv_scale;
+  float *Z;
+  int d;
+  int64_t M;
+  int64_t row;
+  __device__ void begin(int, int64_t row_) { row = row_; }
+  __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
+    if (row >= M) return;
+    float *z = Z + row * (int64_t)d + col0;
+    if (col0 + 31 < d && (d % 4 == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o;
+        o.x = v[j + 0] * (inv_scale ? __ldg(inv_scale + col0 + j + 0) : 1.f);
+        o.y = v[j + 1] * (inv_scale ? __ldg(inv_scale + col0 + j + 1) : 1.f);
+        o.z = v[j + 2] * (inv_scale ? __ldg(inv_scale + col0 + j + 2) : 1.f);
+        o.w = v[j + 3] * (inv_scale ? __ldg(inv_scale + col0 + j + 3) : 1.f);
+        *reinterpret_cast<float4 *>(z + j) = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < d) z[j] = v[j] * (inv_scale ? __ldg(inv_scale + col0 + j) : 1.f);
+    }
+  }
+  __device__ void panel_done(int) {}
+  __device__ void finish() {}
+};
+
+struct KdeEpi {  // online log-sum-exp of -|q-b|^2/(2h^2) in log2 units
+  const float *qn, *bn;
+  int64_t Nq, b_hi;
+  float scale;  // -0.5/h^2 * log2(e)
+  float *part_m, *part_s;
+  int splits, split;
+  int64_t row;
+  float q2, m, s;
+  __device__ void begin(int, int64_t row_) {
+    row = row_;
+    q2 = row < Nq ? __ldg(qn + row) : 0.f;
+    m = -INFINITY;
+    s = 0.f;
+  }
+  __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
+    float t[32];
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int64_t col = col0 + j;
+      const float b2 = col < b_hi ? __ldg(bn + col) : 0.f;
+      const float dist = fmaxf(fmaf(-2.f, v[j], q2 + b2), 0.f);
+      t[j] = col < b_hi ? dist * scale : -INFINITY;
+      tmax = fmaxf(tmax, t[j]);
+    }
+    if (tmax == -INFINITY) return;
+    const float m_new = fmaxf(m, tmax);
+    float acc = s * exp2f(m - m_new);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc += exp2f(t[j] - m_new);
+    s = acc;
+    m = m_new;
+  }
+  __device__ void panel_done(int) {}
+  __device__ void finish() {
+    if (row < Nq) {
+      part_m[(size_t)row * splits + split] = m;
+      part_s[(size_t)row * splits + split] = s;
+    }
+  }
+};
+
+// kNN candidate filter: thread-owned row, register threshold / count, global candidate buffer,
+// warp-cooperative bitonic compaction through shared-memory scratch.
+struct KnnEpi {
+  const float *qn, *bn;
+  int64_t Nq, b_hi;
+  float *buf_d;
+  int32_t *buf_i;
+  int kcap, capp, splits, split;
+  float *skey;     // per-warp scratch [capp]
+  int32_t *sidx;   // per-warp scratch [capp]
+  int64_t row;
+  size_t base;
+  float q2, thr;
+  int cnt;
+  bool live;
+  __device__ void begin(int, int64_t row_) {
+    row = row_;
+    live = row < Nq;
+    q2 = live ? __ldg(qn + row) : 0.f;
+    thr = INFINITY;
+    cnt = 0;
+    base = live ? ((size_t)row * splits + split) * capp : 0;
+  }
+  __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
+    if (!live) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int64_t col = col0 + j;
+      const float b2 = col < b_hi ? __ldg(bn + col) : 0.f;
+      const float dist = fmaf(-2.f, v[j], q2 + b2);
+      if (col < b_hi && dist < thr) {
+        buf_d[base + cnt] = dist;
+        buf_i[base + cnt] = (int32_t)col;
+        ++cnt;
+      }
+    }
+  }
+  // all 32 lanes of the warp must call this together
+  __device__ void compact_rows(unsigned mask, bool final_pass) {
+    const int lane = threadIdx.x & 31;
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int n = __shfl_sync(0xffffffffu, cnt, src);
+      const size_t b0 = ((size_t)__shfl_sync(0xffffffffu, (unsigned long long)base, src));
+      __syncwarp();
+      for (int e = lane; e < capp; e += 32) {
+        skey[e] = e < n ? buf_d[b0 + e] : INFINITY;
+        sidx[e] = e < n ? buf_i[b0 + e] : 0x7fffffff;
+      }
+      __syncwarp();
+      for (int k = 2; k <= capp; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int t = lane; t < (capp >> 1); t += 32) {
+            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+            const int p = i | j;
+            const bool asc = ((i & k) == 0);
+            const float ka = skey[i], kb = skey[p];
+            const int32_t ia = sidx[i], ib = sidx[p];
+            const bool gt = (ka > kb) || (ka == kb && ia > ib);
+            if (gt == asc) {
+              skey[i] = kb; skey[p] = ka;
+              sidx[i] = ib; sidx[p] = ia;
+            }
+          }
+          __syncwarp();
+        }
+      }
+      const int keep = n < kcap ? n : kcap;
+      const int wr = final_pass ? kcap : keep;
+      for (int e = lane; e < wr; e += 32) {
+        buf_d[b0 + e] = skey[e];
+        buf_i[b0 + e] = e < keep ? sidx[e] : -1;
+      }
+      const float new_thr = skey[kcap - 1];
+      __syncwarp();
+      if (lane == src) {
+        cnt = keep;
+        if (keep == kcap) thr = new_thr;
+      }
+    }
+  }
+  __device__ void panel_done(int) {
+    const unsigned mask = __ballot_sync(0xffffffffu, live && cnt > capp - TN);
+    compact_rows(mask, false);
+  }
+  __device__ void finish() {
+    const unsigned mask = __ballot_sync(0xffffffffu, live);
+    compact_rows(mask, true);
+  }
+};
+
+template <class E>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_kernel(const float *__restrict__ A, int64_t M, int K, Prologue pro, const __grid_constant__ CUtensorMap tmB_hi,
+          const __grid_constant__ CUtensorMap tmB_lo, int panels_total, int panels_per_split, E epi) {
+  extern __shared__ unsigned char smem_raw[];
+  Tile tile;
+  tile.m0 = (int64_t)blockIdx.x * TM;
+  tile.panel_lo = blockIdx.y * panels_per_split;
+  tile.panel_hi = min(panels_total, tile.panel_lo + panels_per_split);
+  run_tile(A, M, K, pro, &tmB_hi, &tmB_lo, tile, epi, smem_raw);
+}
+
+// kNN / KDE variants fix up the per-split fields of their epilogue inside the kernel
+template <class E>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_split_kernel(const float *__restrict__ A, int64_t M, int K, const __grid_constant__ CUtensorMap tmB_hi,
+                const __grid_constant__ CUtensorMap tmB_lo, int panels_total, int panels_per_split, int64_t NB, E epi) {
+  extern __shared__ unsigned char smem_raw[];
+  Tile tile;
+  tile.m0 = (int64_t)blockIdx.x * TM;
+  tile.panel_lo = blockIdx.y * panels_per_split;
+  tile.panel_hi = min(panels_total, tile.panel_lo + panels_per_split);
+  epi.split = blockIdx.y;
+  int64_t hi = (int64_t)tile.panel_hi * TN;
+  epi.b_hi = hi < NB ? hi : NB;
+  if constexpr (sizeof(E) == sizeof(KnnEpi)) {
+    // sort scratch lives behind the pipeline buffers
+  }
+  const Prologue pro{nullptr, INFINITY};
+  run_tile(A, M, K, pro, &tmB_hi, &tmB_lo, tile, epi, smem_raw);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+tc_knn_kernel(const float *__restrict__ A, int64_t M, int K, const __grid_constant__ CUtensorMap tmB_hi,
+              const __grid_constant__ CUtensorMap tmB_lo, int panels_total, int panels_per_split, int64_t NB,
+              KnnEpi epi) {
+  extern __shared__ unsigned char smem_raw[];
+  Tile tile;
+  tile.m0 = (int64_t)blockIdx.x * TM;
+  tile.panel_lo = blockIdx.y * panels_per_split;
+  tile.panel_hi = min(panels_total, tile.panel_lo + panels_per_split);
+  epi.split = blockIdx.y;
+  const int64_t hi = (int64_t)tile.panel_hi * TN;
+  epi.b_hi = hi < NB ? hi : NB;
+  // per-warp sort scratch behind the pipeline buffers (epilogue warps 4..7)
+  const int warp = threadIdx.x >> 5;
+  unsigned char *scratch = smem_raw + kSmemBytes;
+  const int ew = (warp >= 4 && warp < 8) ? warp - 4 : 0;
+  epi.skey = reinterpret_cast<float *>(scratch) + (size_t)ew * epi.capp;
+  epi.sidx = reinterpret_cast<int32_t *>(scratch + (size_t)4 * epi.capp * 4) + (size_t)ew * epi.capp;
+  const Prologue pro{nullptr, INFINITY};
+  run_tile(A, M, K, pro, &tmB_hi, &tmB_lo, tile, epi, smem_raw);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// [rows, K] fp32 row-major -> box of TN rows x 32 floats, 128B swizzle, zero fill out of bounds
+static int make_b_map(CUtensorMap *map, const float *ptr, int64_t rows, int K) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return (int)cudaErrorNotSupported;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)TN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld K=%d)", (int)r, (long long)rows, K);
+    return (int)cudaErrorInvalidValue;
+  }
+  return RUNIA_OK;
+}
+
+template <class Kern>
+static int set_smem(Kern kern, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return RUNIA_OK;
+}
+
+bool usable(const void *A, int K, const void *B_hi, const void *B_lo) {
+  return (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+         ((reinterpret_cast<uintptr_t>(B_hi) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B_lo) & 15) == 0);
+}
+
+}  // namespace tc
+}  // namespace runia
+
+using namespace runia;
+using namespace runia::tc;
+
+extern "C" int runia_split_tf32(const float *x, int64_t total, float *hi, float *lo, void *stream) {
+  RUNIA_REQUIRE(total >= 0, RUNIA_E_BADARG, "split_tf32: bad size");
+  if (total == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(x && hi && lo, RUNIA_E_BADARG, "split_tf32: null pointer");
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)kNumSMs * 16);
+  split_tf32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, total, hi, lo);
+  count_launch();
+  return finish_launch("split_tf32");
+}
+
+extern "C" int runia_rownorm_score_tc(const float *X, int64_t N, int d, const float *mu, const float *Wt_hi,
+                                      const float *Wt_lo, int r, const float *sign, int mode, const float *logits,
+                                      int C, float alpha, double *out_f64, float *out_f32, void *stream) {
+  RUNIA_REQUIRE(N >= 0 && d > 0 && r > 0, RUNIA_E_BADARG, "rownorm_score_tc: bad sizes");
+  RUNIA_REQUIRE(mode == RUNIA_ROWNORM_MD || mode == RUNIA_ROWNORM_VIM, RUNIA_E_BADARG, "rownorm_score_tc: bad mode");
+  if (N == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(X && Wt_hi && Wt_lo && (out_f64 || out_f32), RUNIA_E_BADARG, "rownorm_score_tc: null pointer");
+  RUNIA_REQUIRE(mode != RUNIA_ROWNORM_VIM || (logits && C > 0), RUNIA_E_BADARG, "rownorm_score_tc: ViM needs logits");
+  RUNIA_REQUIRE(usable(X, d, Wt_hi, Wt_lo) && (!mu || (reinterpret_cast<uintptr_t>(mu) & 15) == 0), RUNIA_E_UNSUPPORTED,
+                "rownorm_score_tc: needs d %% 4 == 0 and 16-byte aligned pointers");
+  CUtensorMap mh, ml;
+  int rc = make_b_map(&mh, Wt_hi, r, d);
+  if (rc) return rc;
+  rc = make_b_map(&ml, Wt_lo, r, d);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    rc = set_smem(tc_kernel<RowNormEpi>, kSmemBytes);
+    if (rc) return rc;
+    attr = true;
+  }
+  RowNormEpi epi{sign, r, mode, C, logits, alpha, out_f64, out_f32, N, 0, 0.f};
+  const int panels = (int)ceil_div(r, TN);
+  dim3 grid((unsigned)ceil_div(N, TM), 1);
+  tc_kernel<RowNormEpi><<<grid, THREADS, kSmemBytes, (cudaStream_t)stream>>>(X, N, d, Prologue{mu, INFINITY}, mh, ml,
+                                                                          panels, panels, epi);
+  count_launch();
+  return finish_launch("rownorm_score_tc");
+}
+
+extern "C" int runia_pca_transform_tc(const float *X, int64_t N, int D0, const float *mean, const float *C_hi,
+                                      const float *C_lo, int d, const float *inv_scale, float *Z, void *stream) {
+  RUNIA_REQUIRE(N >= 0 && D0 > 0 && d > 0, RUNIA_E_BADARG, "pca_transform_tc: bad sizes");
+  if (N == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(X && C_hi && C_lo && Z, RUNIA_E_BADARG, "pca_transform_tc: null pointer");
+  RUNIA_REQUIRE(usable(X, D0, C_hi, C_lo) && (!mean || (reinterpret_cast<uintptr_t>(mean) & 15) == 0) &&
+                    (reinterpret_cast<uintptr_t>(Z) & 15) == 0,
+                RUNIA_E_UNSUPPORTED, "pca_transform_tc: needs D0 %% 4 == 0 and 16-byte aligned pointers");
+  CUtensorMap mh, ml;
+  int rc = make_b_map(&mh, C_hi, d, D0);
+  if (rc) return rc;
+  rc = make_b_map(&ml, C_lo, d, D0);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    rc = set_smem(tc_kernel<PcaEpi>, kSmemBytes);
+    if (rc) return rc;
+    attr = true;
+  }
+  PcaEpi epi{inv_scale, Z, d, N, 0};
+  const int panels = (int)ceil_div(d, TN);
+  dim3 grid((unsigned)ceil_div(N, TM), 1);
+  tc_kernel<PcaEpi><<<grid, THREADS, kSmemBytes, (cudaStream_t)stream>>>(X, N, D0, Prologue{mean, INFINITY}, mh, ml,
+                                                                      panels, panels, epi);
+  count_launch();
+  return finish_launch("pca_transform_tc");
+}
+
+namespace runia {
+namespace tc {
+// shared with distance.cu
+int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
+                             const float *bn, int64_t Nb, int d, int kcap, int capp, int splits,
+                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, cudaStream_t st) {
+  CUtensorMap mh, ml;
+  int rc = make_b_map(&mh, B_hi, Nb, d);
+  if (rc) return rc;
+  rc = make_b_map(&ml, B_lo, Nb, d);
+  if (rc) return rc;
+  const size_t smem = kSmemBytes + (size_t)4 * capp * 8;
+  static size_t attr = 0;
+  if (attr < smem) {
+    rc = set_smem(tc_knn_kernel, smem);
+    if (rc) return rc;
+    attr = smem;
+  }
+  KnnEpi epi{};
+  epi.qn = qn; epi.bn = bn; epi.Nq = Nq; epi.b_hi = Nb;
+  epi.buf_d = buf_d; epi.buf_i = buf_i;
+  epi.kcap = kcap; epi.capp = capp; epi.splits = splits; epi.split = 0;
+  dim3 grid((unsigned)ceil_div(Nq, TM), (unsigned)splits);
+  tc_knn_kernel<<<grid, THREADS, smem, st>>>(Q, Nq, d, mh, ml, (int)ceil_div(Nb, TN), (int)panels_per_split, Nb, epi);
+  count_launch();
+  return finish_launch("knn_candidates_tc");
+}
+
+int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
+                          const float *bn, int64_t Nb, int d, float scale, int splits, int64_t panels_per_split,
+                          float *part_m, float *part_s, cudaStream_t st) {
+  CUtensorMap mh, ml;
+  int rc = make_b_map(&mh, B_hi, Nb, d);
+  if (rc) return rc;
+  rc = make_b_map(&ml, B_lo, Nb, d);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    rc = set_smem(tc_split_kernel<KdeEpi>, kSmemBytes);
+    if (rc) return rc;
+    attr = true;
+  }
+  KdeEpi epi{};
+  epi.qn = qn; epi.bn = bn; epi.Nq = Nq; epi.b_hi = Nb; epi.scale = scale;
+  epi.part_m = part_m; epi.part_s = part_s; epi.splits = splits; epi.split = 0;
+  dim3 grid((unsigned)ceil_div(Nq, TM), (unsigned)splits);
+  tc_split_kernel<KdeEpi><<<grid, THREADS, kSmemBytes, st>>>(Q, Nq, d, mh, ml, (int)ceil_div(Nb, TN),
+                                                            (int)panels_per_split, Nb, epi);
+  count_launch();
+  return finish_launch("kde_partial_tc");
+}
+}  // namespace tc
+}  // namespace runia
