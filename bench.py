@@ -178,8 +178,10 @@ def run_b200(args):
     flops = n_rows * (2.0 * D_LATENT * st.r + 3.0 * D_LATENT)
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                 "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
-                "kernel": "rownorm_kernel (FP32 SIMT contraction + row sum of squares)",
-                "fp32_tflops": round(flops / (kern_ms * 1e-3) / 1e12, 2)}
+                "kernel": ("tc_kernel<RowNormEpi> (tcgen05 3xTF32 contraction, TMEM row sum of squares)"
+                           if _ops.get_engine() == "tc" else "rownorm_kernel (FP32 SIMT contraction)"),
+                "fp32_equiv_tflops": round(flops / (kern_ms * 1e-3) / 1e12, 2),
+                "tensor_tf32_tflops_issued": round(3 * flops / (kern_ms * 1e-3) / 1e12, 2)}
 
     # ---------------- end to end through the reference-facing class, host buffers ----------------
     n_e2e = min(args.e2e_rows, n_rows)

@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerank
     aidx[e] = ki;
   }
   __syncwarp();
-  if (S > 1) warp_bitonic_sort(akey, aidx, msz);  // single split: already sorted
+  warp_bitonic_sort(akey, aidx, msz);  // per-split lists arrive unsorted from the tensor-core pass
   int n_real = 0;
   for (int e = lane; e < kcap; e += 32) n_real += (aidx[e] != 0x7fffffff) ? 1 : 0;
 #pragma unroll

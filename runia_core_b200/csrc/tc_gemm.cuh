@@ -156,22 +156,25 @@ struct Prologue {
   float clip;        // +inf = none
 };
 
-struct Tile {
-  int64_t m0;       // first row of this CTA
-  int panel_lo;     // first TN-wide panel of B
-  int panel_hi;     // one past the last panel
+// Work assigned to one CTA: row tiles  tile_first, tile_first + tile_step, ... < tile_end, each
+// crossed with the B panels [panel_lo, panel_hi).  Row scorers run persistently (grid = #SMs,
+// tile_step = gridDim.x) so that the smem ring, the TMEM double buffer and the converters'
+// prefetch keep flowing across tiles; kNN / KDE give each CTA one row tile and one bank split.
+struct Work {
+  int64_t tile_first, tile_end, tile_step;
+  int panel_lo, panel_hi;
 };
 
 // The epilogue policy E provides:
-//   __device__ void begin(int row_in_tile, int64_t row)          -- once per thread
+//   __device__ void begin(int row_in_tile, int64_t row)          -- once per thread per row tile
 //   __device__ void consume(int64_t col0, const float (&v)[32], int warp_in_epi, int lane)
 //       32 consecutive columns col0.. of this thread's row
 //   __device__ void panel_done(int panel)                        -- after a whole panel
-//   __device__ void finish()                                     -- after the last panel
+//   __device__ void finish()                                     -- after the last panel of a row tile
 template <class E>
-__device__ __forceinline__ void run_tile(const float *__restrict__ A, int64_t M, int K, const Prologue pro,
-                                         const CUtensorMap *tmB_hi, const CUtensorMap *tmB_lo, const Tile tile,
-                                         E &epi, unsigned char *smem_raw) {
+__device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M, int K, const Prologue pro,
+                                          const CUtensorMap *tmB_hi, const CUtensorMap *tmB_lo, const Work work,
+                                          E &epi, unsigned char *smem_raw) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // carve shared memory (1024-byte aligned for the 128B swizzle)
   const uint32_t base = (smem_u32(smem_raw) + SMEM_ALIGN - 1) & ~(uint32_t)(SMEM_ALIGN - 1);
@@ -189,7 +192,7 @@ __device__ __forceinline__ void run_tile(const float *__restrict__ A, int64_t M,
   volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(gbase + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
 
   const int nkb = (K + TK - 1) / TK;
-  const int n_panels = tile.panel_hi - tile.panel_lo;
+  const int n_panels = work.panel_hi - work.panel_lo;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(tmB_hi);
@@ -216,24 +219,27 @@ __device__ __forceinline__ void run_tile(const float *__restrict__ A, int64_t M,
     // ------------------------------ TMA producer (B planes) ------------------------------
     if (lane == 0) {
       int it = 0;
-      for (int p = 0; p < n_panels; ++p) {
-        const int n0 = (tile.panel_lo + p) * TN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), 2 * B_PLANE_BYTES);
-          tma_load_2d(sB_hi(s), tmB_hi, full_bar(s), kb * TK, n0);
-          tma_load_2d(sB_lo(s), tmB_lo, full_bar(s), kb * TK, n0);
+      for (int64_t t = work.tile_first; t < work.tile_end; t += work.tile_step) {
+        for (int p = 0; p < n_panels; ++p) {
+          const int n0 = (work.panel_lo + p) * TN;
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(empty_bar(s), ph ^ 1);
+            mbar_expect_tx(full_bar(s), 2 * B_PLANE_BYTES);
+            tma_load_2d(sB_hi(s), tmB_hi, full_bar(s), kb * TK, n0);
+            tma_load_2d(sB_lo(s), tmB_lo, full_bar(s), kb * TK, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    int it = 0;
-    for (int p = 0; p < n_panels; ++p) {
-      const int ab = p & 1;
-      const uint32_t aph = (p >> 1) & 1;
+    int it = 0, pc = 0;
+    for (int64_t t = work.tile_first; t < work.tile_end; t += work.tile_step)
+    for (int p = 0; p < n_panels; ++p, ++pc) {
+      const int ab = pc & 1;
+      const uint32_t aph = (pc >> 1) & 1;
       mbar_wait(tempty_bar(ab), aph ^ 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + (uint32_t)(ab * TN);
@@ -262,13 +268,15 @@ __device__ __forceinline__ void run_tile(const float *__restrict__ A, int64_t M,
     // ------------------------------ epilogue ------------------------------
     const int ew = warp - 4;  // == warp % 4: TMEM lane quadrant this warp may read
     const int row_in_tile = ew * 32 + lane;
-    epi.begin(row_in_tile, tile.m0 + row_in_tile);
-    for (int p = 0; p < n_panels; ++p) {
-      const int ab = p & 1;
-      const uint32_t aph = (p >> 1) & 1;
+    int pc = 0;
+    for (int64_t t = work.tile_first; t < work.tile_end; t += work.tile_step) {
+    epi.begin(row_in_tile, t * TM + row_in_tile);
+    for (int p = 0; p < n_panels; ++p, ++pc) {
+      const int ab = pc & 1;
+      const uint32_t aph = (pc >> 1) & 1;
       mbar_wait(tfull_bar(ab), aph);
       tc_fence_after();
-      const int64_t n0 = (int64_t)(tile.panel_lo + p) * TN;
+      const int64_t n0 = (int64_t)(work.panel_lo + p) * TN;
 #pragma unroll 1
       for (int c0 = 0; c0 < TN; c0 += 32) {
         float v[32];
@@ -277,20 +285,21 @@ __device__ __forceinline__ void run_tile(const float *__restrict__ A, int64_t M,
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(ab));
-      epi.panel_done(tile.panel_lo + p);
+      epi.panel_done(work.panel_lo + p);
     }
     epi.finish();
+    }
   } else if (warp >= 8) {
     // ------------------------------ A converters ------------------------------
     const int ct = threadIdx.x - 256;  // 0..127
     const int chunk = ct & 7;          // 16-byte chunk inside the 128-byte k-block row
     const int r0 = ct >> 3;            // rows r0, r0+16, ..., r0+112
     const bool vec_ok = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-    auto load_block = [&](int kb, float4 (&x)[8]) {
+    auto load_block = [&](int64_t t, int kb, float4 (&x)[8]) {
       const int k = kb * TK + chunk * 4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int64_t row = tile.m0 + r0 + 16 * i;
+        const int64_t row = t * TM + r0 + 16 * i;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < M) {
           const float *src = A + row * (int64_t)K + k;
@@ -307,9 +316,10 @@ __device__ __forceinline__ void run_tile(const float *__restrict__ A, int64_t M,
       }
     };
     int it = 0;
+    float4 x[8];
+    if (work.tile_first < work.tile_end) load_block(work.tile_first, 0, x);
+    for (int64_t t = work.tile_first; t < work.tile_end; t += work.tile_step)
     for (int p = 0; p < n_panels; ++p) {
-      float4 x[8];
-      load_block(0, x);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
@@ -337,7 +347,10 @@ __device__ __forceinline__ void run_tile(const float *__restrict__ A, int64_t M,
           hi[i] = make_float4(h[0], h[1], h[2], h[3]);
           lo[i] = make_float4(l[0], l[1], l[2], l[3]);
         }
-        if (kb + 1 < nkb) load_block(kb + 1, x);  // next block's loads in flight during the wait
+        // next block's loads (same panel, next panel, or next row tile) in flight during the wait
+        if (kb + 1 < nkb) load_block(t, kb + 1, x);
+        else if (p + 1 < n_panels) load_block(t, 0, x);
+        else if (t + work.tile_step < work.tile_end) load_block(t + work.tile_step, 0, x);
         mbar_wait(empty_bar(s), ph ^ 1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

@@ -4,6 +4,7 @@
 // path (K % 4 != 0, unaligned pointers) and as the accuracy yardstick (DESIGN.md "3xTF32 vs FP32").
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "tc_gemm.cuh"
@@ -145,16 +146,27 @@ struct KdeEpi {  // online log-sum-exp of -|q-b|^2/(2h^2) in log2 units
   }
 };
 
-// kNN candidate filter: thread-owned row, register threshold / count, global candidate buffer,
-// warp-cooperative bitonic compaction through shared-memory scratch.
+// kNN candidate filter.  Thread t owns query row t of the tile: threshold and count live in
+// registers, candidates (approximate distance, bank index) are appended to the row's buffer in
+// global memory (L2-resident).  When a buffer could overflow during the next panel, the owning
+// thread tightens its threshold by bisection on the order-preserving integer key of the distance
+// until between kcap and 2*kcap entries lie below it, and compacts its buffer in place -- 128
+// rows shrink in parallel, no sorting.  Entries dropped at any time have distance >= the row's
+// final threshold, which is what the certification in the re-rank kernel relies on.
+__device__ __forceinline__ uint32_t ord_key(float v) {
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_val(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 struct KnnEpi {
   const float *qn, *bn;
   int64_t Nq, b_hi;
   float *buf_d;
   int32_t *buf_i;
   int kcap, capp, splits, split;
-  float *skey;     // per-warp scratch [capp]
-  int32_t *sidx;   // per-warp scratch [capp]
   int64_t row;
   size_t base;
   float q2, thr;
@@ -182,91 +194,116 @@ struct KnnEpi {
       }
     }
   }
-  // all 32 lanes of the warp must call this together
-  __device__ void compact_rows(unsigned mask, bool final_pass) {
-    const int lane = threadIdx.x & 31;
-    while (mask) {
-      const int src = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int n = __shfl_sync(0xffffffffu, cnt, src);
-      const size_t b0 = ((size_t)__shfl_sync(0xffffffffu, (unsigned long long)base, src));
-      __syncwarp();
-      for (int e = lane; e < capp; e += 32) {
-        skey[e] = e < n ? buf_d[b0 + e] : INFINITY;
-        sidx[e] = e < n ? buf_i[b0 + e] : 0x7fffffff;
+  // shrink this thread's buffer to between kcap and `target` entries (exactly kcap if target == kcap)
+  __device__ void shrink(int target) {
+    const int n = cnt;
+    if (n <= target) return;
+    // bisection on integer keys: invariant count(key < hi) >= kcap > count(key < lo)
+    uint32_t lo = 0u, hi = 0xffffffffu;
+    int c_hi = n;
+    {
+      uint32_t kmin = 0xffffffffu, kmax = 0u;
+      for (int e = 0; e < n; ++e) {
+        const uint32_t k = ord_key(buf_d[base + e]);
+        kmin = k < kmin ? k : kmin;
+        kmax = k > kmax ? k : kmax;
       }
-      __syncwarp();
-      for (int k = 2; k <= capp; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int t = lane; t < (capp >> 1); t += 32) {
-            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-            const int p = i | j;
-            const bool asc = ((i & k) == 0);
-            const float ka = skey[i], kb = skey[p];
-            const int32_t ia = sidx[i], ib = sidx[p];
-            const bool gt = (ka > kb) || (ka == kb && ia > ib);
-            if (gt == asc) {
-              skey[i] = kb; skey[p] = ka;
-              sidx[i] = ib; sidx[p] = ia;
-            }
-          }
-          __syncwarp();
-        }
-      }
-      const int keep = n < kcap ? n : kcap;
-      const int wr = final_pass ? kcap : keep;
-      for (int e = lane; e < wr; e += 32) {
-        buf_d[b0 + e] = skey[e];
-        buf_i[b0 + e] = e < keep ? sidx[e] : -1;
-      }
-      const float new_thr = skey[kcap - 1];
-      __syncwarp();
-      if (lane == src) {
-        cnt = keep;
-        if (keep == kcap) thr = new_thr;
+      lo = kmin;  // count(key < kmin) = 0 < kcap
+      hi = kmax == 0xffffffffu ? kmax : kmax + 1u;
+    }
+    while (c_hi > target && hi - lo > 1u) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      int c = 0;
+      for (int e = 0; e < n; ++e) c += (ord_key(buf_d[base + e]) < mid) ? 1 : 0;
+      if (c >= kcap) {
+        hi = mid;
+        c_hi = c;
+      } else {
+        lo = mid;
       }
     }
+    int w = 0;
+    if (c_hi <= target) {
+      for (int e = 0; e < n; ++e) {
+        const float dv = buf_d[base + e];
+        const int32_t iv = buf_i[base + e];
+        if (ord_key(dv) < hi) {
+          buf_d[base + w] = dv;
+          buf_i[base + w] = iv;
+          ++w;
+        }
+      }
+      thr = fminf(thr, ord_val(hi));
+    } else {
+      // more than `target` entries share the key `lo` around rank kcap: keep everything below it and
+      // just enough of the ties; later ties are rejected by the strict `< thr` filter
+      int c_lt = 0;
+      for (int e = 0; e < n; ++e) c_lt += (ord_key(buf_d[base + e]) < lo) ? 1 : 0;
+      int ties_left = kcap - c_lt;
+      for (int e = 0; e < n; ++e) {
+        const float dv = buf_d[base + e];
+        const int32_t iv = buf_i[base + e];
+        const uint32_t k = ord_key(dv);
+        const bool keep = k < lo || (k == lo && ties_left > 0);
+        if (k == lo && ties_left > 0) --ties_left;
+        if (keep) {
+          buf_d[base + w] = dv;
+          buf_i[base + w] = iv;
+          ++w;
+        }
+      }
+      thr = fminf(thr, ord_val(lo));
+    }
+    cnt = w;
   }
   __device__ void panel_done(int) {
-    const unsigned mask = __ballot_sync(0xffffffffu, live && cnt > capp - TN);
-    compact_rows(mask, false);
+    if (live && cnt > capp - TN) shrink(2 * kcap);
   }
   __device__ void finish() {
-    const unsigned mask = __ballot_sync(0xffffffffu, live);
-    compact_rows(mask, true);
+    if (!live) return;
+    shrink(kcap);
+    for (int e = cnt; e < kcap; ++e) {  // pad: the re-rank kernel reads kcap entries per (row, split)
+      buf_d[base + e] = INFINITY;
+      buf_i[base + e] = -1;
+    }
   }
 };
 
 template <class E>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_kernel(const float *__restrict__ A, int64_t M, int K, Prologue pro, const __grid_constant__ CUtensorMap tmB_hi,
-          const __grid_constant__ CUtensorMap tmB_lo, int panels_total, int panels_per_split, E epi) {
+          const __grid_constant__ CUtensorMap tmB_lo, int panels_total, E epi) {
   extern __shared__ unsigned char smem_raw[];
-  Tile tile;
-  tile.m0 = (int64_t)blockIdx.x * TM;
-  tile.panel_lo = blockIdx.y * panels_per_split;
-  tile.panel_hi = min(panels_total, tile.panel_lo + panels_per_split);
-  run_tile(A, M, K, pro, &tmB_hi, &tmB_lo, tile, epi, smem_raw);
+  Work w;  // persistent: row tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+  w.tile_first = blockIdx.x;
+  w.tile_end = (M + TM - 1) / TM;
+  w.tile_step = gridDim.x;
+  w.panel_lo = 0;
+  w.panel_hi = panels_total;
+  run_tiles(A, M, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
-// kNN / KDE variants fix up the per-split fields of their epilogue inside the kernel
-template <class E>
+__device__ __forceinline__ Work split_work(int panels_total, int panels_per_split) {
+  Work w;  // one row tile x one bank split per CTA
+  w.tile_first = blockIdx.x;
+  w.tile_end = (int64_t)blockIdx.x + 1;
+  w.tile_step = 1;
+  w.panel_lo = blockIdx.y * panels_per_split;
+  w.panel_hi = min(panels_total, w.panel_lo + panels_per_split);
+  return w;
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
-tc_split_kernel(const float *__restrict__ A, int64_t M, int K, const __grid_constant__ CUtensorMap tmB_hi,
-                const __grid_constant__ CUtensorMap tmB_lo, int panels_total, int panels_per_split, int64_t NB, E epi) {
+tc_kde_kernel(const float *__restrict__ A, int64_t M, int K, const __grid_constant__ CUtensorMap tmB_hi,
+              const __grid_constant__ CUtensorMap tmB_lo, int panels_total, int panels_per_split, int64_t NB,
+              KdeEpi epi) {
   extern __shared__ unsigned char smem_raw[];
-  Tile tile;
-  tile.m0 = (int64_t)blockIdx.x * TM;
-  tile.panel_lo = blockIdx.y * panels_per_split;
-  tile.panel_hi = min(panels_total, tile.panel_lo + panels_per_split);
+  const Work w = split_work(panels_total, panels_per_split);
   epi.split = blockIdx.y;
-  int64_t hi = (int64_t)tile.panel_hi * TN;
+  const int64_t hi = (int64_t)w.panel_hi * TN;
   epi.b_hi = hi < NB ? hi : NB;
-  if constexpr (sizeof(E) == sizeof(KnnEpi)) {
-    // sort scratch lives behind the pipeline buffers
-  }
   const Prologue pro{nullptr, INFINITY};
-  run_tile(A, M, K, pro, &tmB_hi, &tmB_lo, tile, epi, smem_raw);
+  run_tiles(A, M, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -274,21 +311,12 @@ tc_knn_kernel(const float *__restrict__ A, int64_t M, int K, const __grid_consta
               const __grid_constant__ CUtensorMap tmB_lo, int panels_total, int panels_per_split, int64_t NB,
               KnnEpi epi) {
   extern __shared__ unsigned char smem_raw[];
-  Tile tile;
-  tile.m0 = (int64_t)blockIdx.x * TM;
-  tile.panel_lo = blockIdx.y * panels_per_split;
-  tile.panel_hi = min(panels_total, tile.panel_lo + panels_per_split);
+  const Work w = split_work(panels_total, panels_per_split);
   epi.split = blockIdx.y;
-  const int64_t hi = (int64_t)tile.panel_hi * TN;
+  const int64_t hi = (int64_t)w.panel_hi * TN;
   epi.b_hi = hi < NB ? hi : NB;
-  // per-warp sort scratch behind the pipeline buffers (epilogue warps 4..7)
-  const int warp = threadIdx.x >> 5;
-  unsigned char *scratch = smem_raw + kSmemBytes;
-  const int ew = (warp >= 4 && warp < 8) ? warp - 4 : 0;
-  epi.skey = reinterpret_cast<float *>(scratch) + (size_t)ew * epi.capp;
-  epi.sidx = reinterpret_cast<int32_t *>(scratch + (size_t)4 * epi.capp * 4) + (size_t)ew * epi.capp;
   const Prologue pro{nullptr, INFINITY};
-  run_tile(A, M, K, pro, &tmB_hi, &tmB_lo, tile, epi, smem_raw);
+  run_tiles(A, M, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -386,9 +414,9 @@ extern "C" int runia_rownorm_score_tc(const float *X, int64_t N, int d, const fl
   }
   RowNormEpi epi{sign, r, mode, C, logits, alpha, out_f64, out_f32, N, 0, 0.f};
   const int panels = (int)ceil_div(r, TN);
-  dim3 grid((unsigned)ceil_div(N, TM), 1);
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(N, TM), kNumSMs), 1);
   tc_kernel<RowNormEpi><<<grid, THREADS, kSmemBytes, (cudaStream_t)stream>>>(X, N, d, Prologue{mu, INFINITY}, mh, ml,
-                                                                          panels, panels, epi);
+                                                                          panels, epi);
   count_launch();
   return finish_launch("rownorm_score_tc");
 }
@@ -414,9 +442,9 @@ extern "C" int runia_pca_transform_tc(const float *X, int64_t N, int D0, const f
   }
   PcaEpi epi{inv_scale, Z, d, N, 0};
   const int panels = (int)ceil_div(d, TN);
-  dim3 grid((unsigned)ceil_div(N, TM), 1);
+  dim3 grid((unsigned)std::min<int64_t>(ceil_div(N, TM), kNumSMs), 1);
   tc_kernel<PcaEpi><<<grid, THREADS, kSmemBytes, (cudaStream_t)stream>>>(X, N, D0, Prologue{mean, INFINITY}, mh, ml,
-                                                                      panels, panels, epi);
+                                                                      panels, epi);
   count_launch();
   return finish_launch("pca_transform_tc");
 }
@@ -432,12 +460,12 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
   if (rc) return rc;
   rc = make_b_map(&ml, B_lo, Nb, d);
   if (rc) return rc;
-  const size_t smem = kSmemBytes + (size_t)4 * capp * 8;
-  static size_t attr = 0;
-  if (attr < smem) {
+  const size_t smem = kSmemBytes;
+  static bool attr = false;
+  if (!attr) {
     rc = set_smem(tc_knn_kernel, smem);
     if (rc) return rc;
-    attr = smem;
+    attr = true;
   }
   KnnEpi epi{};
   epi.qn = qn; epi.bn = bn; epi.Nq = Nq; epi.b_hi = Nb;
@@ -459,7 +487,7 @@ int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const flo
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
-    rc = set_smem(tc_split_kernel<KdeEpi>, kSmemBytes);
+    rc = set_smem(tc_kde_kernel, kSmemBytes);
     if (rc) return rc;
     attr = true;
   }
@@ -467,8 +495,8 @@ int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const flo
   epi.qn = qn; epi.bn = bn; epi.Nq = Nq; epi.b_hi = Nb; epi.scale = scale;
   epi.part_m = part_m; epi.part_s = part_s; epi.splits = splits; epi.split = 0;
   dim3 grid((unsigned)ceil_div(Nq, TM), (unsigned)splits);
-  tc_split_kernel<KdeEpi><<<grid, THREADS, kSmemBytes, st>>>(Q, Nq, d, mh, ml, (int)ceil_div(Nb, TN),
-                                                            (int)panels_per_split, Nb, epi);
+  tc_kde_kernel<<<grid, THREADS, kSmemBytes, st>>>(Q, Nq, d, mh, ml, (int)ceil_div(Nb, TN), (int)panels_per_split, Nb,
+                                                  epi);
   count_launch();
   return finish_launch("kde_partial_tc");
 }
