@@ -112,6 +112,7 @@ struct KnnPlan {
   int capp;    // buffer entries per (row, split): power of two, >= kcap + BN
   int splits;  // bank splits (grid.y)
   int64_t panels_per_split;
+  int interleaved;  // 1: candidate buffers are [32-row group][split][entry][lane] (tensor-core pass)
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
@@ -247,12 +248,15 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerank
   double *ekey = reinterpret_cast<double *>(base + (size_t)msz * 8);
   int32_t *eidx = reinterpret_cast<int32_t *>(base + (size_t)msz * 8 + (size_t)kcap * 8);
 
+  const int n_all = S * kcap;
   for (int e = lane; e < msz; e += 32) {
     float kd = INFINITY;
     int32_t ki = 0x7fffffff;
-    if (e < S * kcap) {
+    if (e < n_all) {
       const int s = e / kcap, c = e % kcap;
-      const size_t p = ((size_t)row * S + s) * capp + c;
+      const size_t p = a.plan.interleaved
+                           ? (((size_t)(row >> 5)) * S + s) * ((size_t)capp * 32) + (size_t)c * 32 + (size_t)(row & 31)
+                           : ((size_t)row * S + s) * capp + c;
       const int32_t ii = a.buf_i[p];
       if (ii >= 0) {
         kd = a.buf_d[p];
@@ -263,7 +267,80 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerank
     aidx[e] = ki;
   }
   __syncwarp();
-  warp_bitonic_sort(akey, aidx, msz);  // per-split lists arrive unsorted from the tensor-core pass
+  if (S > 1) {
+    // keep the kcap smallest (approximate distance, index) pairs of the S per-split lists: warp
+    // bisection on the order-preserving key, then a stable compaction to the front
+    auto okey = [](float v) -> uint32_t {
+      const uint32_t u = __float_as_uint(v);
+      return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    };
+    int n_fin = 0;
+    for (int e = lane; e < n_all; e += 32) n_fin += (aidx[e] != 0x7fffffff) ? 1 : 0;
+    n_fin = __reduce_add_sync(0xffffffffu, n_fin);
+    if (n_fin > kcap) {
+      uint32_t lo = 0u, hi = 0xffffffffu;  // count(key < lo) < kcap <= count(key < hi)
+      int c_hi = n_fin;
+      while (c_hi > kcap && hi - lo > 1u) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        int c = 0;
+        for (int e = lane; e < n_all; e += 32) c += (aidx[e] != 0x7fffffff && okey(akey[e]) < mid) ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= kcap) {
+          hi = mid;
+          c_hi = c;
+        } else {
+          lo = mid;
+        }
+      }
+      const bool ties = c_hi > kcap;
+      const uint32_t bound = ties ? lo : hi;
+      int c_lt = 0;
+      if (ties) {
+        for (int e = lane; e < n_all; e += 32) c_lt += (aidx[e] != 0x7fffffff && okey(akey[e]) < lo) ? 1 : 0;
+        c_lt = __reduce_add_sync(0xffffffffu, c_lt);
+      }
+      int ties_left = ties ? kcap - c_lt : 0;
+      // stable in-place compaction, 32 entries at a time: positions come from a ballot scan
+      int w = 0;
+      for (int e0 = 0; e0 < n_all; e0 += 32) {
+        const int e = e0 + lane;
+        float kd = INFINITY;
+        int32_t ki = 0x7fffffff;
+        bool keep = false, tie = false;
+        if (e < n_all) {
+          kd = akey[e];
+          ki = aidx[e];
+          const uint32_t k = okey(kd);
+          keep = ki != 0x7fffffff && k < bound;
+          tie = ties && ki != 0x7fffffff && k == lo;
+        }
+        const unsigned tmask = __ballot_sync(0xffffffffu, tie);
+        if (tie && __popc(tmask & ((1u << lane) - 1u)) < ties_left) keep = true;
+        ties_left -= __popc(tmask);
+        if (ties_left < 0) ties_left = 0;
+        const unsigned kmask = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();
+        // survivors of this 32-chunk go to [w, w + popc): w <= e0 always, and the whole chunk is
+        // already in registers, so writing in place is safe
+        if (keep) {
+          const int pos = w + __popc(kmask & ((1u << lane) - 1u));
+          akey[pos] = kd;
+          aidx[pos] = ki;
+        }
+        w += __popc(kmask);
+        __syncwarp();
+      }
+      for (int e = w + lane; e < kcap; e += 32) {
+        akey[e] = INFINITY;
+        aidx[e] = 0x7fffffff;
+      }
+      __syncwarp();
+    }
+    // order the survivors (the bound L below needs the largest approximate distance)
+    warp_bitonic_sort(akey, aidx, kcap);
+  } else {
+    warp_bitonic_sort(akey, aidx, kcap);
+  }
   int n_real = 0;
   for (int e = lane; e < kcap; e += 32) n_real += (aidx[e] != 0x7fffffff) ? 1 : 0;
 #pragma unroll
@@ -516,6 +593,7 @@ static KnnPlan make_knn_plan(int64_t Nq, int64_t Nb, int k, bool tensor) {
   const int pw = tensor ? 256 : BN;
   p.capp = 256;
   while (p.capp < p.kcap + pw) p.capp <<= 1;
+  p.interleaved = tensor ? 1 : 0;
   pick_splits(ceil_div(Nq, BM), ceil_div(Nb, pw), 16, tensor ? kNumSMs : 2 * kNumSMs, p.splits, p.panels_per_split);
   return p;
 }
@@ -533,8 +611,9 @@ static KnnWorkspace knn_layout(int64_t Nq, const KnnPlan &p) {
     return at;
   };
   w.qn = take((size_t)Nq * 4);
-  w.buf_d = take((size_t)Nq * p.splits * p.capp * 4);
-  w.buf_i = take((size_t)Nq * p.splits * p.capp * 4);
+  const size_t rows32 = (size_t)ceil_div(Nq, 32) * 32;
+  w.buf_d = take(rows32 * p.splits * p.capp * 4);
+  w.buf_i = take(rows32 * p.splits * p.capp * 4);
   w.flag_count = take(256);
   w.flag_rows = take((size_t)Nq * 4);
   w.flag_T = take((size_t)Nq * 8);

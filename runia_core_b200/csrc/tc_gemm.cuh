@@ -6,15 +6,16 @@
 // FP32-faithful by operand splitting: x = hi + lo with hi = tf32(x), lo = tf32(x - hi); the kernel
 // issues  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is ~2^-22 relative).
 //
-// Roles inside one CTA (384 threads, 1 CTA / SM, 128 x 256 output panel):
+// Roles inside one CTA (512 threads, 1 CTA / SM, 128 x 256 output panel):
 //   warp 0      TMA producer for the two B planes (pre-split in HBM: setup-time for weights/banks)
 //   warp 1      MMA issuer (one elected lane), 12 tcgen05.mma per 32-wide k-block
 //   warp 2      TMEM allocator (512 columns = two 128 x 256 accumulators, double buffered)
 //   warps 4-7   epilogue: tcgen05.ld 32 columns at a time; thread t owns output row t, so every
 //               row-wise reduction (sum of squares, log-sum-exp, top-k filter) is thread-local
-//   warps 8-11  A converters: coalesced fp32 global loads -> fused prologue (subtract centre,
-//               clip) -> hi/lo split -> st.shared in the UMMA 128B-swizzle layout.  The streamed
-//               operand is therefore read from HBM exactly once, as raw fp32.
+//   warps 8-15  A converters: coalesced fp32 global loads (three k-blocks in flight per thread to
+//               cover HBM latency) -> fused prologue (subtract centre, clip) -> hi/lo split ->
+//               st.shared in the UMMA 128B-swizzle layout.  The streamed operand is therefore
+//               read from HBM exactly once, as raw fp32.
 // Pipelines: smem ring (full/empty mbarriers; `full` collects the TMA bytes and the 128 converter
 // arrivals), TMEM ring (tmem_full via tcgen05.commit, tmem_empty from the epilogue warps).
 #pragma once
@@ -29,7 +30,9 @@ constexpr int TM = 128;        // rows per CTA tile (UMMA M)
 constexpr int TN = 256;        // columns per panel (UMMA N)
 constexpr int TK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int STAGES = 2;
-constexpr int THREADS = 384;
+constexpr int THREADS = 512;
+constexpr int CONV_THREADS = 256;  // warps 8..15
+constexpr int CONV_DEPTH = 3;      // k-blocks of A kept in flight per converter thread (registers)
 constexpr int A_PLANE_BYTES = TM * TK * 4;  // 16 KB
 constexpr int B_PLANE_BYTES = TN * TK * 4;  // 32 KB
 constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;  // 96 KB
@@ -41,17 +44,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// Blocking wait on an mbarrier phase.  The suspend-time hint lets the hardware park the thread until
+// the phase flips (or the hint expires) instead of spinning: spinning waiters share issue slots with
+// the MMA issuer and the epilogue warps of the same SM sub-partition.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
       "@P1 bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
       "}" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -200,7 +206,7 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1 + 128);  // TMA expect_tx arrival + 128 converter threads
+      mbar_init(full_bar(s), 1 + CONV_THREADS);  // TMA expect_tx arrival + converter threads
       mbar_init(empty_bar(s), 1);       // tcgen05.commit
     }
     for (int b = 0; b < 2; ++b) {
@@ -291,17 +297,23 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
     }
   } else if (warp >= 8) {
     // ------------------------------ A converters ------------------------------
-    const int ct = threadIdx.x - 256;  // 0..127
+    const int ct = threadIdx.x - 256;  // 0..255
     const int chunk = ct & 7;          // 16-byte chunk inside the 128-byte k-block row
-    const int r0 = ct >> 3;            // rows r0, r0+16, ..., r0+112
+    const int r0 = ct >> 3;            // rows r0, r0+32, r0+64, r0+96
     const bool vec_ok = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
-    auto load_block = [&](int64_t t, int kb, float4 (&x)[8]) {
+    const int64_t n_my_tiles =
+        work.tile_first < work.tile_end ? (work.tile_end - work.tile_first + work.tile_step - 1) / work.tile_step : 0;
+    const int64_t per_tile = (int64_t)n_panels * nkb;
+    const int64_t n_items = n_my_tiles * per_tile;  // flat sequence of (tile, panel, k-block)
+    auto load_item = [&](int64_t item, float4 (&x)[4]) {
+      const int64_t t = work.tile_first + (item / per_tile) * work.tile_step;
+      const int kb = (int)(item % nkb);
       const int k = kb * TK + chunk * 4;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t row = t * TM + r0 + 16 * i;
+      for (int i = 0; i < 4; ++i) {
+        const int64_t row = t * TM + r0 + 32 * i;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < M) {
+        if (row < M && item < n_items) {
           const float *src = A + row * (int64_t)K + k;
           if (vec_ok && k + 3 < K) {
             v = __ldg(reinterpret_cast<const float4 *>(src));
@@ -315,56 +327,64 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
         x[i] = v;
       }
     };
-    int it = 0;
-    float4 x[8];
-    if (work.tile_first < work.tile_end) load_block(work.tile_first, 0, x);
-    for (int64_t t = work.tile_first; t < work.tile_end; t += work.tile_step)
-    for (int p = 0; p < n_panels; ++p) {
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        // prologue + split in registers while waiting for the slot
-        const int k = kb * TK + chunk * 4;
-        float4 sub = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pro.sub) {
-          if (k + 0 < K) sub.x = __ldg(pro.sub + k + 0);
-          if (k + 1 < K) sub.y = __ldg(pro.sub + k + 1);
-          if (k + 2 < K) sub.z = __ldg(pro.sub + k + 2);
-          if (k + 3 < K) sub.w = __ldg(pro.sub + k + 3);
-        }
-        float4 hi[8], lo[8];
+    auto convert_store = [&](int64_t item, const float4 (&x)[4]) {
+      const int it = (int)(item % (2 * STAGES)) ;  // only parity and slot matter
+      const int s = (int)(item % STAGES);
+      const uint32_t ph = (uint32_t)((item / STAGES) & 1);
+      (void)it;
+      const int kb = (int)(item % nkb);
+      const int k = kb * TK + chunk * 4;
+      float4 sub = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pro.sub) {
+        if (k + 0 < K) sub.x = __ldg(pro.sub + k + 0);
+        if (k + 1 < K) sub.y = __ldg(pro.sub + k + 1);
+        if (k + 2 < K) sub.z = __ldg(pro.sub + k + 2);
+        if (k + 3 < K) sub.w = __ldg(pro.sub + k + 3);
+      }
+      float4 hi[4], lo[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float e[4] = {x[i].x - sub.x, x[i].y - sub.y, x[i].z - sub.z, x[i].w - sub.w};
-          float h[4], l[4];
+      for (int i = 0; i < 4; ++i) {
+        float e[4] = {x[i].x - sub.x, x[i].y - sub.y, x[i].z - sub.z, x[i].w - sub.w};
+        float h[4], l[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (pro.clip < INFINITY) e[q] = e[q] > pro.clip ? pro.clip : e[q];
-            if (k + q >= K) e[q] = 0.f;
-            h[q] = to_tf32(e[q]);
-            l[q] = to_tf32(e[q] - h[q]);
-          }
-          hi[i] = make_float4(h[0], h[1], h[2], h[3]);
-          lo[i] = make_float4(l[0], l[1], l[2], l[3]);
+        for (int q = 0; q < 4; ++q) {
+          if (pro.clip < INFINITY) e[q] = e[q] > pro.clip ? pro.clip : e[q];
+          if (k + q >= K) e[q] = 0.f;
+          h[q] = to_tf32(e[q]);
+          l[q] = to_tf32(e[q] - h[q]);
         }
-        // next block's loads (same panel, next panel, or next row tile) in flight during the wait
-        if (kb + 1 < nkb) load_block(t, kb + 1, x);
-        else if (p + 1 < n_panels) load_block(t, 0, x);
-        else if (t + work.tile_step < work.tile_end) load_block(t + work.tile_step, 0, x);
-        mbar_wait(empty_bar(s), ph ^ 1);
+        hi[i] = make_float4(h[0], h[1], h[2], h[3]);
+        lo[i] = make_float4(l[0], l[1], l[2], l[3]);
+      }
+      mbar_wait(empty_bar(s), ph ^ 1);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + 16 * i;
-          const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sA_hi(s) + off), "f"(hi[i].x), "f"(hi[i].y),
-                       "f"(hi[i].z), "f"(hi[i].w)
-                       : "memory");
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sA_lo(s) + off), "f"(lo[i].x), "f"(lo[i].y),
-                       "f"(lo[i].z), "f"(lo[i].w)
-                       : "memory");
-        }
-        fence_proxy_async();  // make the generic-proxy stores visible to the tensor core
-        mbar_arrive(full_bar(s));
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 32 * i;
+        const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sA_hi(s) + off), "f"(hi[i].x), "f"(hi[i].y),
+                     "f"(hi[i].z), "f"(hi[i].w)
+                     : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sA_lo(s) + off), "f"(lo[i].x), "f"(lo[i].y),
+                     "f"(lo[i].z), "f"(lo[i].w)
+                     : "memory");
+      }
+      fence_proxy_async();  // make the generic-proxy stores visible to the tensor core
+      mbar_arrive(full_bar(s));
+    };
+    float4 xa[4], xb[4], xc[4];  // CONV_DEPTH = 3 register slots, statically indexed
+    load_item(0, xa);
+    load_item(1, xb);
+    load_item(2, xc);
+    for (int64_t item = 0; item < n_items; item += CONV_DEPTH) {
+      convert_store(item, xa);
+      load_item(item + 3, xa);
+      if (item + 1 < n_items) {
+        convert_store(item + 1, xb);
+        load_item(item + 4, xb);
+      }
+      if (item + 2 < n_items) {
+        convert_store(item + 2, xc);
+        load_item(item + 5, xc);
       }
     }
   }

@@ -148,7 +148,8 @@ struct KdeEpi {  // online log-sum-exp of -|q-b|^2/(2h^2) in log2 units
 
 // kNN candidate filter.  Thread t owns query row t of the tile: threshold and count live in
 // registers, candidates (approximate distance, bank index) are appended to the row's buffer in
-// global memory (L2-resident).  When a buffer could overflow during the next panel, the owning
+// global memory (L2-resident).  The 32 rows of a warp share one buffer block, entry-major
+// ([entry][lane]), so that the lock-step scans below touch one 128-byte line per instruction.  When a buffer could overflow during the next panel, the owning
 // thread tightens its threshold by bisection on the order-preserving integer key of the distance
 // until between kcap and 2*kcap entries lie below it, and compacts its buffer in place -- 128
 // rows shrink in parallel, no sorting.  Entries dropped at any time have distance >= the row's
@@ -178,7 +179,8 @@ struct KnnEpi {
     q2 = live ? __ldg(qn + row) : 0.f;
     thr = INFINITY;
     cnt = 0;
-    base = live ? ((size_t)row * splits + split) * capp : 0;
+    // block of the 32-row group this row belongs to, + lane; entry e lives at base + 32 * e
+    base = (((size_t)(row >> 5)) * splits + split) * ((size_t)capp * 32) + (size_t)(row & 31);
   }
   __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
     if (!live) return;
@@ -188,33 +190,54 @@ struct KnnEpi {
       const float b2 = col < b_hi ? __ldg(bn + col) : 0.f;
       const float dist = fmaf(-2.f, v[j], q2 + b2);
       if (col < b_hi && dist < thr) {
-        buf_d[base + cnt] = dist;
-        buf_i[base + cnt] = (int32_t)col;
+        buf_d[base + 32 * (size_t)cnt] = dist;
+        buf_i[base + 32 * (size_t)cnt] = (int32_t)col;
         ++cnt;
       }
     }
+  }
+  // buffer entry e of this thread, read through L2 (the entries were written by this thread)
+  __device__ __forceinline__ float ld_d(int e) const { return __ldcg(buf_d + base + 32 * (size_t)e); }
+  __device__ __forceinline__ int32_t ld_i(int e) const { return __ldcg(buf_i + base + 32 * (size_t)e); }
+  // number of buffered keys below `bound`; 8 independent loads in flight per step
+  __device__ __forceinline__ int count_below(int n, uint32_t bound) const {
+    int c = 0;
+    for (int e0 = 0; e0 < n; e0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (e0 + j < n) ? ld_d(e0 + j) : INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c += (e0 + j < n && ord_key(v[j]) < bound) ? 1 : 0;
+    }
+    return c;
   }
   // shrink this thread's buffer to between kcap and `target` entries (exactly kcap if target == kcap)
   __device__ void shrink(int target) {
     const int n = cnt;
     if (n <= target) return;
     // bisection on integer keys: invariant count(key < hi) >= kcap > count(key < lo)
-    uint32_t lo = 0u, hi = 0xffffffffu;
+    uint32_t lo, hi;
     int c_hi = n;
     {
       uint32_t kmin = 0xffffffffu, kmax = 0u;
-      for (int e = 0; e < n; ++e) {
-        const uint32_t k = ord_key(buf_d[base + e]);
-        kmin = k < kmin ? k : kmin;
-        kmax = k > kmax ? k : kmax;
+      for (int e0 = 0; e0 < n; e0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (e0 + j < n) ? ld_d(e0 + j) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (e0 + j < n) {
+            const uint32_t k = ord_key(v[j]);
+            kmin = k < kmin ? k : kmin;
+            kmax = k > kmax ? k : kmax;
+          }
       }
       lo = kmin;  // count(key < kmin) = 0 < kcap
       hi = kmax == 0xffffffffu ? kmax : kmax + 1u;
     }
     while (c_hi > target && hi - lo > 1u) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
-      int c = 0;
-      for (int e = 0; e < n; ++e) c += (ord_key(buf_d[base + e]) < mid) ? 1 : 0;
+      const int c = count_below(n, mid);
       if (c >= kcap) {
         hi = mid;
         c_hi = c;
@@ -222,49 +245,53 @@ struct KnnEpi {
         lo = mid;
       }
     }
+    // in-place compaction (write index never passes the read index; reads are batched first)
+    const bool ties = c_hi > target;  // more than `target` entries share the key `lo` around rank kcap:
+    int ties_left = 0;                // keep everything below it and just enough of the ties
+    if (ties) ties_left = kcap - count_below(n, lo);
+    const uint32_t bound = ties ? lo : hi;
     int w = 0;
-    if (c_hi <= target) {
-      for (int e = 0; e < n; ++e) {
-        const float dv = buf_d[base + e];
-        const int32_t iv = buf_i[base + e];
-        if (ord_key(dv) < hi) {
-          buf_d[base + w] = dv;
-          buf_i[base + w] = iv;
-          ++w;
-        }
+    for (int e0 = 0; e0 < n; e0 += 8) {
+      float v[8];
+      int32_t ix[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = (e0 + j < n) ? ld_d(e0 + j) : INFINITY;
+        ix[j] = (e0 + j < n) ? ld_i(e0 + j) : -1;
       }
-      thr = fminf(thr, ord_val(hi));
-    } else {
-      // more than `target` entries share the key `lo` around rank kcap: keep everything below it and
-      // just enough of the ties; later ties are rejected by the strict `< thr` filter
-      int c_lt = 0;
-      for (int e = 0; e < n; ++e) c_lt += (ord_key(buf_d[base + e]) < lo) ? 1 : 0;
-      int ties_left = kcap - c_lt;
-      for (int e = 0; e < n; ++e) {
-        const float dv = buf_d[base + e];
-        const int32_t iv = buf_i[base + e];
-        const uint32_t k = ord_key(dv);
-        const bool keep = k < lo || (k == lo && ties_left > 0);
-        if (k == lo && ties_left > 0) --ties_left;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (e0 + j >= n) continue;
+        const uint32_t k = ord_key(v[j]);
+        bool keep = k < bound;
+        if (ties && k == lo && ties_left > 0) {
+          keep = true;
+          --ties_left;
+        }
         if (keep) {
-          buf_d[base + w] = dv;
-          buf_i[base + w] = iv;
+          buf_d[base + 32 * (size_t)w] = v[j];
+          buf_i[base + 32 * (size_t)w] = ix[j];
           ++w;
         }
       }
-      thr = fminf(thr, ord_val(lo));
     }
+    // later ties are rejected by the strict `< thr` filter
+    thr = fminf(thr, ord_val(bound));
     cnt = w;
   }
   __device__ void panel_done(int) {
-    if (live && cnt > capp - TN) shrink(2 * kcap);
+    // warp-uniform trigger: when any row of the warp is about to overflow, every row that holds more
+    // than the target shrinks in the same (coalesced, lock-step) passes
+    if (__any_sync(0xffffffffu, live && cnt > capp - TN)) {
+      if (live) shrink(2 * kcap);
+    }
   }
   __device__ void finish() {
     if (!live) return;
     shrink(kcap);
     for (int e = cnt; e < kcap; ++e) {  // pad: the re-rank kernel reads kcap entries per (row, split)
-      buf_d[base + e] = INFINITY;
-      buf_i[base + e] = -1;
+      buf_d[base + 32 * (size_t)e] = INFINITY;
+      buf_i[base + 32 * (size_t)e] = -1;
     }
   }
 };
