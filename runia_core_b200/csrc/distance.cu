@@ -599,7 +599,7 @@ static KnnPlan make_knn_plan(int64_t Nq, int64_t Nb, int k, bool tensor) {
 }
 
 struct KnnWorkspace {
-  size_t qn, buf_d, buf_i, flag_count, flag_rows, flag_T, flag_I, fb_d, fb_i, total;
+  size_t qn, thr_seed, seed_d, seed_i, buf_d, buf_i, flag_count, flag_rows, flag_T, flag_I, fb_d, fb_i, total;
 };
 constexpr int FB_GRID = 64;
 static KnnWorkspace knn_layout(int64_t Nq, const KnnPlan &p) {
@@ -611,7 +611,10 @@ static KnnWorkspace knn_layout(int64_t Nq, const KnnPlan &p) {
     return at;
   };
   w.qn = take((size_t)Nq * 4);
+  w.thr_seed = take((size_t)Nq * 4);
   const size_t rows32 = (size_t)ceil_div(Nq, 32) * 32;
+  w.seed_d = take(rows32 * p.capp * 4);
+  w.seed_i = take(rows32 * p.capp * 4);
   w.buf_d = take(rows32 * p.splits * p.capp * 4);
   w.buf_i = take(rows32 * p.splits * p.capp * 4);
   w.flag_count = take(256);
@@ -628,7 +631,8 @@ namespace tc {
 bool usable(const void *A, int K, const void *B_hi, const void *B_lo);
 int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                              const float *bn, int64_t Nb, int d, int kcap, int capp, int splits,
-                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, cudaStream_t st);
+                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, float *thr_seed,
+                             float *seed_d, int32_t *seed_i, cudaStream_t st);
 int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                           const float *bn, int64_t Nb, int d, float scale, int splits, int64_t panels_per_split,
                           float *part_m, float *part_s, cudaStream_t st);
@@ -712,7 +716,9 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
 
   if (tensor) {
     const int rc = tc::launch_knn_candidates_tc(Qn, qn, Nq, Bn_hi, Bn_lo, Bn_sqnorm, Nb, d, plan.kcap, plan.capp,
-                                                plan.splits, plan.panels_per_split, buf_d, buf_i, st);
+                                                plan.splits, plan.panels_per_split, buf_d, buf_i,
+                                                (float *)(ws + w.thr_seed), (float *)(ws + w.seed_d),
+                                                (int32_t *)(ws + w.seed_i), st);
     if (rc) return rc;
   } else {
     const size_t dyn1 = (size_t)8 * plan.capp * 8;

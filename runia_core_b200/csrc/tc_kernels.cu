@@ -168,6 +168,8 @@ struct KnnEpi {
   float *buf_d;
   int32_t *buf_i;
   int kcap, capp, splits, split;
+  const float *thr_in;  // [Nq] initial threshold per row (from the seed split) or nullptr
+  float *thr_out;       // [Nq] final threshold of this split (seed split only) or nullptr
   int64_t row;
   size_t base;
   float q2, thr;
@@ -177,7 +179,7 @@ struct KnnEpi {
     row = row_;
     live = row < Nq;
     q2 = live ? __ldg(qn + row) : 0.f;
-    thr = INFINITY;
+    thr = (live && thr_in) ? __ldg(thr_in + row) : INFINITY;
     cnt = 0;
     // block of the 32-row group this row belongs to, + lane; entry e lives at base + 32 * e
     base = (((size_t)(row >> 5)) * splits + split) * ((size_t)capp * 32) + (size_t)(row & 31);
@@ -289,6 +291,9 @@ struct KnnEpi {
   __device__ void finish() {
     if (!live) return;
     shrink(kcap);
+    // after shrink(kcap) on a full buffer, thr bounds the kcap-th smallest distance of this split:
+    // the other splits start from it, so they only ever buffer rows that can still matter
+    if (thr_out) thr_out[row] = (cnt >= kcap) ? thr : INFINITY;
     for (int e = cnt; e < kcap; ++e) {  // pad: the re-rank kernel reads kcap entries per (row, split)
       buf_d[base + 32 * (size_t)e] = INFINITY;
       buf_i[base + 32 * (size_t)e] = -1;
@@ -336,10 +341,16 @@ tc_kde_kernel(const float *__restrict__ A, int64_t M, int K, const __grid_consta
 __global__ void __launch_bounds__(THREADS, 1)
 tc_knn_kernel(const float *__restrict__ A, int64_t M, int K, const __grid_constant__ CUtensorMap tmB_hi,
               const __grid_constant__ CUtensorMap tmB_lo, int panels_total, int panels_per_split, int64_t NB,
-              KnnEpi epi) {
+              int split_offset, KnnEpi epi) {
   extern __shared__ unsigned char smem_raw[];
-  const Work w = split_work(panels_total, panels_per_split);
-  epi.split = blockIdx.y;
+  Work w;
+  w.tile_first = blockIdx.x;
+  w.tile_end = (int64_t)blockIdx.x + 1;
+  w.tile_step = 1;
+  const int split = (int)blockIdx.y + split_offset;
+  w.panel_lo = split * panels_per_split;
+  w.panel_hi = min(panels_total, w.panel_lo + panels_per_split);
+  epi.split = split;
   const int64_t hi = (int64_t)w.panel_hi * TN;
   epi.b_hi = hi < NB ? hi : NB;
   const Prologue pro{nullptr, INFINITY};
@@ -481,7 +492,8 @@ namespace tc {
 // shared with distance.cu
 int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                              const float *bn, int64_t Nb, int d, int kcap, int capp, int splits,
-                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, cudaStream_t st) {
+                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, float *thr_seed,
+                             float *seed_d, int32_t *seed_i, cudaStream_t st) {
   CUtensorMap mh, ml;
   int rc = make_b_map(&mh, B_hi, Nb, d);
   if (rc) return rc;
@@ -498,9 +510,28 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
   epi.qn = qn; epi.bn = bn; epi.Nq = Nq; epi.b_hi = Nb;
   epi.buf_d = buf_d; epi.buf_i = buf_i;
   epi.kcap = kcap; epi.capp = capp; epi.splits = splits; epi.split = 0;
-  dim3 grid((unsigned)ceil_div(Nq, TM), (unsigned)splits);
-  tc_knn_kernel<<<grid, THREADS, smem, st>>>(Q, Nq, d, mh, ml, (int)ceil_div(Nb, TN), (int)panels_per_split, Nb, epi);
-  count_launch();
+  const int panels = (int)ceil_div(Nb, TN);
+  constexpr int kSeedPanels = 4;
+  if (panels <= 2 * kSeedPanels) {
+    epi.thr_in = nullptr; epi.thr_out = nullptr;
+    dim3 grid((unsigned)ceil_div(Nq, TM), (unsigned)splits);
+    tc_knn_kernel<<<grid, THREADS, smem, st>>>(Q, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
+    count_launch();
+  } else {
+    // Seed pass over the first few panels of the bank: its per-row kcap-th smallest distance is a
+    // valid upper bound on the global kcap-th smallest, so it becomes the initial threshold of the
+    // main pass and no split ever floods its buffer.  The seed writes to scratch buffers only;
+    // the main pass sees those bank rows again.
+    KnnEpi seed = epi;
+    seed.buf_d = seed_d; seed.buf_i = seed_i; seed.splits = 1;
+    seed.thr_in = nullptr; seed.thr_out = thr_seed;
+    dim3 grid0((unsigned)ceil_div(Nq, TM), 1);
+    tc_knn_kernel<<<grid0, THREADS, smem, st>>>(Q, Nq, d, mh, ml, kSeedPanels, kSeedPanels, Nb, 0, seed);
+    epi.thr_in = thr_seed; epi.thr_out = nullptr;
+    dim3 grid1((unsigned)ceil_div(Nq, TM), (unsigned)splits);
+    tc_knn_kernel<<<grid1, THREADS, smem, st>>>(Q, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
+    count_launch(2);
+  }
   return finish_launch("knn_candidates_tc");
 }
 
