@@ -585,7 +585,7 @@ static void pick_splits(int64_t rowblocks, int64_t panels, int max_splits, int64
   if (splits < 1) splits = 1;
 }
 
-// tensor-core pass: 128 x 256 panels, 1 CTA / SM;  SIMT pass: 128 x 128 panels, 2 CTAs / SM
+// tensor-core pass: 256 x 256 panels per CTA pair, 74 pairs;  SIMT pass: 128 x 128 panels, 2 CTAs / SM
 static KnnPlan make_knn_plan(int64_t Nq, int64_t Nb, int k, bool tensor) {
   KnnPlan p;
   p.kcap = 64;
@@ -594,7 +594,8 @@ static KnnPlan make_knn_plan(int64_t Nq, int64_t Nb, int k, bool tensor) {
   p.capp = 256;
   while (p.capp < p.kcap + pw) p.capp <<= 1;
   p.interleaved = tensor ? 1 : 0;
-  pick_splits(ceil_div(Nq, BM), ceil_div(Nb, pw), 16, tensor ? kNumSMs : 2 * kNumSMs, p.splits, p.panels_per_split);
+  pick_splits(ceil_div(Nq, tensor ? 256 : BM), ceil_div(Nb, pw), 16, tensor ? kNumSMs / 2 : 2 * kNumSMs, p.splits,
+              p.panels_per_split);
   return p;
 }
 
@@ -771,7 +772,8 @@ extern "C" int runia_topk_merge(const double *part_dist, const int64_t *part_idx
 }
 
 static void kde_plan(int64_t Nq, int64_t Nb, bool tensor, int &splits, int64_t &pps) {
-  pick_splits(ceil_div(Nq, BM), ceil_div(Nb, tensor ? 256 : BN), 64, tensor ? kNumSMs : 2 * kNumSMs, splits, pps);
+  pick_splits(ceil_div(Nq, tensor ? 256 : BM), ceil_div(Nb, tensor ? 256 : BN), 64, tensor ? kNumSMs / 2 : 2 * kNumSMs,
+              splits, pps);
 }
 
 extern "C" int64_t runia_kde_workspace_bytes(int64_t Nq, int64_t Nb) {

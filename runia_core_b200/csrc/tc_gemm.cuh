@@ -6,18 +6,27 @@
 // FP32-faithful by operand splitting: x = hi + lo with hi = tf32(x), lo = tf32(x - hi); the kernel
 // issues  A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (the dropped lo*lo term is ~2^-22 relative).
 //
-// Roles inside one CTA (512 threads, 1 CTA / SM, 128 x 256 output panel):
-//   warp 0      TMA producer for the two B planes (pre-split in HBM: setup-time for weights/banks)
-//   warp 1      MMA issuer (one elected lane), 12 tcgen05.mma per 32-wide k-block
-//   warp 2      TMEM allocator (512 columns = two 128 x 256 accumulators, double buffered)
+// The kernel runs as CTA PAIRS (thread-block cluster of 2, tcgen05 cta_group::2): one UMMA covers a
+// 256 x 256 output panel, CTA r of the pair owns rows [128 r, 128 r + 128) of it (its A tile, its
+// TMEM accumulator, its epilogue) and stages HALF of the B panel (128 of the 256 B rows) in its own
+// shared memory.  Per MMA each SM therefore reads 4 KB of A and 4 KB of B instead of 4 + 8, the
+// L2 -> SM traffic for B halves, and a stage shrinks to 64 KB so that three stages fit.
+//
+// Roles inside one CTA (512 threads, 1 CTA / SM):
+//   warp 0      TMA producer for this CTA's half of the two B planes (pre-split in HBM at setup
+//               time); completion bytes are posted on the LEADER CTA's `full` barrier
+//   warp 1      MMA issuer (leader CTA only, one elected lane): 12 tcgen05.mma.cta_group::2 per
+//               32-wide k-block; tcgen05.commit multicasts the `empty` / `tmem_full` arrivals to both CTAs
+//   warp 2      TMEM allocator (512 columns = two 128 x 256 accumulators per CTA, double buffered)
 //   warps 4-7   epilogue: tcgen05.ld 32 columns at a time; thread t owns output row t, so every
 //               row-wise reduction (sum of squares, log-sum-exp, top-k filter) is thread-local
 //   warps 8-15  A converters: coalesced fp32 global loads (three k-blocks in flight per thread to
 //               cover HBM latency) -> fused prologue (subtract centre, clip) -> hi/lo split ->
 //               st.shared in the UMMA 128B-swizzle layout.  The streamed operand is therefore
 //               read from HBM exactly once, as raw fp32.
-// Pipelines: smem ring (full/empty mbarriers; `full` collects the TMA bytes and the 128 converter
-// arrivals), TMEM ring (tmem_full via tcgen05.commit, tmem_empty from the epilogue warps).
+// Pipelines: smem ring (full/empty mbarriers; the leader's `full` collects the TMA bytes of both
+// CTAs and one arrival per converter warp of both CTAs), TMEM ring (tmem_full via tcgen05.commit,
+// the leader's tmem_empty collects the epilogue threads of both CTAs).
 #pragma once
 #include <cuda.h>
 
@@ -26,16 +35,19 @@
 namespace runia {
 namespace tc {
 
-constexpr int TM = 128;        // rows per CTA tile (UMMA M)
+constexpr int TM = 128;        // rows per CTA
+constexpr int TM2 = 256;       // rows per CTA pair (UMMA M with cta_group::2)
 constexpr int TN = 256;        // columns per panel (UMMA N)
+constexpr int TNH = TN / 2;    // B rows staged by each CTA of the pair
 constexpr int TK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int STAGES = 2;
+constexpr int STAGES = 3;
 constexpr int THREADS = 512;
 constexpr int CONV_THREADS = 256;  // warps 8..15
+constexpr int CONV_WARPS = CONV_THREADS / 32;
 constexpr int CONV_DEPTH = 3;      // k-blocks of A kept in flight per converter thread (registers)
 constexpr int A_PLANE_BYTES = TM * TK * 4;  // 16 KB
-constexpr int B_PLANE_BYTES = TN * TK * 4;  // 32 KB
-constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;  // 96 KB
+constexpr int B_PLANE_BYTES = TNH * TK * 4;  // 16 KB (this CTA's half of the panel)
+constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;  // 64 KB
 constexpr int SMEM_BAR_BYTES = 256;
 constexpr int SMEM_ALIGN = 1024;
 
@@ -44,9 +56,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-// Blocking wait on an mbarrier phase.  The suspend-time hint lets the hardware park the thread until
-// the phase flips (or the hint expires) instead of spinning: spinning waiters share issue slots with
-// the MMA issuer and the epilogue warps of the same SM sub-partition.
+// Blocking wait on a (local) mbarrier phase.  The suspend-time hint lets the hardware park the
+// thread until the phase flips (or the hint expires) instead of spinning: spinning waiters share
+// issue slots with the MMA issuer and the epilogue warps of the same SM sub-partition.
+// Default (.acquire.cta) semantics on purpose, also for barriers the peer CTA signals: what crosses
+// the pair is shared / tensor memory handed to the async proxy (ordered by fence.proxy.async resp.
+// tcgen05.fence on the producer side), never global memory, and a cluster-scope acquire / release
+// costs an L1 invalidate (CCTL.IVALL) resp. MEMBAR.GPU that would drain the converters' prefetch.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -60,8 +76,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity), "r"(0x989680u)
       : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// arrive on a barrier given by its shared::cluster address (own or peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -72,6 +95,15 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of both CTAs
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
@@ -85,38 +117,45 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y) {
+// 2-CTA TMA load: the box lands in THIS CTA's shared memory, the bytes are posted on `leader_bar`
+// (shared::cluster address of the pair leader's barrier)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int x, int y) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(x), "r"(y)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(leader_bar), "r"(x), "r"(y)
       : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// executed by the same warp of BOTH CTAs of the pair
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-// D[tmem] (+)= A[smem] * B[smem], kind::tf32, one CTA
+// D[tmem of both CTAs] (+)= A[smem of both CTAs] * B[smem halves of both CTAs], kind::tf32; leader only
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// arrives (once the MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
 }
 
 // 32 lanes x 32 consecutive columns -> 32 registers per thread (thread t <-> lane base + t)
@@ -148,8 +187,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
-// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=TN
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=256 (pair), N=TN
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM2 >> 4) << 24);
 
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
@@ -162,10 +201,11 @@ struct Prologue {
   float clip;        // +inf = none
 };
 
-// Work assigned to one CTA: row tiles  tile_first, tile_first + tile_step, ... < tile_end, each
-// crossed with the B panels [panel_lo, panel_hi).  Row scorers run persistently (grid = #SMs,
-// tile_step = gridDim.x) so that the smem ring, the TMEM double buffer and the converters'
-// prefetch keep flowing across tiles; kNN / KDE give each CTA one row tile and one bank split.
+// Work assigned to one CTA PAIR: row tiles (256 rows each)  tile_first, tile_first + tile_step, ...
+// < tile_end, each crossed with the B panels [panel_lo, panel_hi).  Row scorers run persistently
+// (one pair per TPC, tile_step = number of pairs) so that the smem ring, the TMEM double buffer and
+// the converters' prefetch keep flowing across tiles; kNN / KDE give each pair one row tile and one
+// bank split.  Both CTAs of a pair must be given the SAME Work.
 struct Work {
   int64_t tile_first, tile_end, tile_step;
   int panel_lo, panel_hi;
@@ -182,7 +222,8 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
                                           const CUtensorMap *tmB_hi, const CUtensorMap *tmB_lo, const Work work,
                                           E &epi, unsigned char *smem_raw) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // carve shared memory (1024-byte aligned for the 128B swizzle)
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
+  // carve shared memory (1024-byte aligned for the 128B swizzle); identical offsets in both CTAs
   const uint32_t base = (smem_u32(smem_raw) + SMEM_ALIGN - 1) & ~(uint32_t)(SMEM_ALIGN - 1);
   unsigned char *gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar0 = base + STAGES * STAGE_BYTES;
@@ -190,10 +231,10 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
   auto sA_lo = [&](int s) { return base + s * STAGE_BYTES + A_PLANE_BYTES; };
   auto sB_hi = [&](int s) { return base + s * STAGE_BYTES + 2 * A_PLANE_BYTES; };
   auto sB_lo = [&](int s) { return base + s * STAGE_BYTES + 2 * A_PLANE_BYTES + B_PLANE_BYTES; };
-  auto full_bar = [&](int s) { return bar0 + 8 * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8 * (STAGES + s); };
-  auto tfull_bar = [&](int b) { return bar0 + 8 * (2 * STAGES + b); };
-  auto tempty_bar = [&](int b) { return bar0 + 8 * (2 * STAGES + 2 + b); };
+  auto full_bar = [&](int s) { return bar0 + 8 * s; };                      // used in the leader only
+  auto empty_bar = [&](int s) { return bar0 + 8 * (STAGES + s); };          // one per CTA
+  auto tfull_bar = [&](int b) { return bar0 + 8 * (2 * STAGES + b); };      // one per CTA
+  auto tempty_bar = [&](int b) { return bar0 + 8 * (2 * STAGES + 2 + b); }; // used in the leader only
   const uint32_t tmem_slot = bar0 + 8 * (2 * STAGES + 4);
   volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(gbase + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
 
@@ -206,68 +247,72 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1 + CONV_THREADS);  // TMA expect_tx arrival + converter threads
-      mbar_init(empty_bar(s), 1);       // tcgen05.commit
+      mbar_init(full_bar(s), 1 + 2 * CONV_WARPS);  // leader's expect_tx arrival + converter warps of both CTAs
+      mbar_init(empty_bar(s), 1);                  // tcgen05.commit (multicast)
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull_bar(b), 1);    // tcgen05.commit
-      mbar_init(tempty_bar(b), 128);  // epilogue threads
+      mbar_init(tfull_bar(b), 1);         // tcgen05.commit (multicast)
+      mbar_init(tempty_bar(b), 2 * 128);  // epilogue threads of both CTAs
     }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
+  __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs initialised before anyone signals across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ------------------------------ TMA producer (B planes) ------------------------------
+    // ------------------------------ TMA producer (this CTA's half of the B planes) ------------------------------
     if (lane == 0) {
       int it = 0;
       for (int64_t t = work.tile_first; t < work.tile_end; t += work.tile_step) {
         for (int p = 0; p < n_panels; ++p) {
-          const int n0 = (work.panel_lo + p) * TN;
+          const int n0 = (work.panel_lo + p) * TN + (int)rank * TNH;
           for (int kb = 0; kb < nkb; ++kb, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             mbar_wait(empty_bar(s), ph ^ 1);
-            mbar_expect_tx(full_bar(s), 2 * B_PLANE_BYTES);
-            tma_load_2d(sB_hi(s), tmB_hi, full_bar(s), kb * TK, n0);
-            tma_load_2d(sB_lo(s), tmB_lo, full_bar(s), kb * TK, n0);
+            if (rank == 0) mbar_expect_tx(full_bar(s), 4 * B_PLANE_BYTES);  // both planes, both CTAs
+            const uint32_t lbar = map_to_cta(full_bar(s), 0);
+            tma_load_2d_pair(sB_hi(s), tmB_hi, lbar, kb * TK, n0);
+            tma_load_2d_pair(sB_lo(s), tmB_lo, lbar, kb * TK, n0);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
-    int it = 0, pc = 0;
-    for (int64_t t = work.tile_first; t < work.tile_end; t += work.tile_step)
-    for (int p = 0; p < n_panels; ++p, ++pc) {
-      const int ab = pc & 1;
-      const uint32_t aph = (pc >> 1) & 1;
-      mbar_wait(tempty_bar(ab), aph ^ 1);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + (uint32_t)(ab * TN);
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(full_bar(s), ph);
+    // ------------------------------ MMA issuer (leader CTA) ------------------------------
+    if (rank == 0) {
+      int it = 0, pc = 0;
+      for (int64_t t = work.tile_first; t < work.tile_end; t += work.tile_step)
+      for (int p = 0; p < n_panels; ++p, ++pc) {
+        const int ab = pc & 1;
+        const uint32_t aph = (pc >> 1) & 1;
+        mbar_wait(tempty_bar(ab), aph ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint64_t dA_hi = make_smem_desc(sA_hi(s)), dA_lo = make_smem_desc(sA_lo(s));
-          const uint64_t dB_hi = make_smem_desc(sB_hi(s)), dB_lo = make_smem_desc(sB_lo(s));
+        const uint32_t tacc = tmem_base + (uint32_t)(ab * TN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t dA_hi = make_smem_desc(sA_hi(s)), dA_lo = make_smem_desc(sA_lo(s));
+            const uint64_t dB_hi = make_smem_desc(sB_hi(s)), dB_lo = make_smem_desc(sB_lo(s));
 #pragma unroll
-          for (int k4 = 0; k4 < TK / 8; ++k4) {
-            const uint64_t adv = (uint64_t)((k4 * 8 * 4) >> 4);  // 32 bytes per UMMA_K=8 step
-            umma_tf32(tacc, dA_lo + adv, dB_hi + adv, kInstrDesc, (kb | k4) != 0 ? 1u : 0u);
-            umma_tf32(tacc, dA_hi + adv, dB_lo + adv, kInstrDesc, 1u);
-            umma_tf32(tacc, dA_hi + adv, dB_hi + adv, kInstrDesc, 1u);
+            for (int k4 = 0; k4 < TK / 8; ++k4) {
+              const uint64_t adv = (uint64_t)((k4 * 8 * 4) >> 4);  // 32 bytes per UMMA_K=8 step
+              umma_tf32(tacc, dA_lo + adv, dB_hi + adv, kInstrDesc, (kb | k4) != 0 ? 1u : 0u);
+              umma_tf32(tacc, dA_hi + adv, dB_lo + adv, kInstrDesc, 1u);
+              umma_tf32(tacc, dA_hi + adv, dB_hi + adv, kInstrDesc, 1u);
+            }
+            umma_commit(empty_bar(s));                       // smem slot reusable (both CTAs) when these MMAs retire
+            if (kb == nkb - 1) umma_commit(tfull_bar(ab));   // accumulators ready for both epilogues
           }
-          umma_commit(empty_bar(s));                       // smem slot reusable when these MMAs retire
-          if (kb == nkb - 1) umma_commit(tfull_bar(ab));   // accumulator ready for the epilogue
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -276,7 +321,7 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
     const int row_in_tile = ew * 32 + lane;
     int pc = 0;
     for (int64_t t = work.tile_first; t < work.tile_end; t += work.tile_step) {
-    epi.begin(row_in_tile, t * TM + row_in_tile);
+    epi.begin(row_in_tile, t * TM2 + (int64_t)rank * TM + row_in_tile);
     for (int p = 0; p < n_panels; ++p, ++pc) {
       const int ab = pc & 1;
       const uint32_t aph = (pc >> 1) & 1;
@@ -290,7 +335,7 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
         epi.consume(n0 + c0, v, ew, lane);
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(ab));
+      mbar_arrive_cluster(map_to_cta(tempty_bar(ab), 0));
       epi.panel_done(work.panel_lo + p);
     }
     epi.finish();
@@ -305,13 +350,14 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
         work.tile_first < work.tile_end ? (work.tile_end - work.tile_first + work.tile_step - 1) / work.tile_step : 0;
     const int64_t per_tile = (int64_t)n_panels * nkb;
     const int64_t n_items = n_my_tiles * per_tile;  // flat sequence of (tile, panel, k-block)
+    const uint32_t lfull0 = map_to_cta(full_bar(0), 0);  // leader's full barriers, 8 bytes apart
     auto load_item = [&](int64_t item, float4 (&x)[4]) {
       const int64_t t = work.tile_first + (item / per_tile) * work.tile_step;
       const int kb = (int)(item % nkb);
       const int k = kb * TK + chunk * 4;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int64_t row = t * TM + r0 + 32 * i;
+        const int64_t row = t * TM2 + (int64_t)rank * TM + r0 + 32 * i;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row < M && item < n_items) {
           const float *src = A + row * (int64_t)K + k;
@@ -328,10 +374,8 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
       }
     };
     auto convert_store = [&](int64_t item, const float4 (&x)[4]) {
-      const int it = (int)(item % (2 * STAGES)) ;  // only parity and slot matter
       const int s = (int)(item % STAGES);
       const uint32_t ph = (uint32_t)((item / STAGES) & 1);
-      (void)it;
       const int kb = (int)(item % nkb);
       const int k = kb * TK + chunk * 4;
       float4 sub = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -369,7 +413,8 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
                      : "memory");
       }
       fence_proxy_async();  // make the generic-proxy stores visible to the tensor core
-      mbar_arrive(full_bar(s));
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lfull0 + 8 * (uint32_t)s);  // one arrival per converter warp
     };
     float4 xa[4], xb[4], xc[4];  // CONV_DEPTH = 3 register slots, statically indexed
     load_item(0, xa);
@@ -389,8 +434,10 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
     }
   }
   // ------------------------------ teardown ------------------------------
+  // no CTA of the pair may exit (or free TMEM) while the other can still signal its barriers
+  __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

@@ -302,30 +302,30 @@ struct KnnEpi {
 };
 
 template <class E>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tc_kernel(const float *__restrict__ A, int64_t M, int K, Prologue pro, const __grid_constant__ CUtensorMap tmB_hi,
           const __grid_constant__ CUtensorMap tmB_lo, int panels_total, E epi) {
   extern __shared__ unsigned char smem_raw[];
-  Work w;  // persistent: row tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-  w.tile_first = blockIdx.x;
-  w.tile_end = (M + TM - 1) / TM;
-  w.tile_step = gridDim.x;
+  Work w;  // persistent: CTA pair p takes the 256-row tiles p, p + #pairs, ...
+  w.tile_first = blockIdx.x >> 1;
+  w.tile_end = (M + TM2 - 1) / TM2;
+  w.tile_step = gridDim.x >> 1;
   w.panel_lo = 0;
   w.panel_hi = panels_total;
   run_tiles(A, M, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
 __device__ __forceinline__ Work split_work(int panels_total, int panels_per_split) {
-  Work w;  // one row tile x one bank split per CTA
-  w.tile_first = blockIdx.x;
-  w.tile_end = (int64_t)blockIdx.x + 1;
+  Work w;  // one 256-row tile x one bank split per CTA pair
+  w.tile_first = blockIdx.x >> 1;
+  w.tile_end = (int64_t)(blockIdx.x >> 1) + 1;
   w.tile_step = 1;
   w.panel_lo = blockIdx.y * panels_per_split;
   w.panel_hi = min(panels_total, w.panel_lo + panels_per_split);
   return w;
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tc_kde_kernel(const float *__restrict__ A, int64_t M, int K, const __grid_constant__ CUtensorMap tmB_hi,
               const __grid_constant__ CUtensorMap tmB_lo, int panels_total, int panels_per_split, int64_t NB,
               KdeEpi epi) {
@@ -338,14 +338,14 @@ tc_kde_kernel(const float *__restrict__ A, int64_t M, int K, const __grid_consta
   run_tiles(A, M, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tc_knn_kernel(const float *__restrict__ A, int64_t M, int K, const __grid_constant__ CUtensorMap tmB_hi,
               const __grid_constant__ CUtensorMap tmB_lo, int panels_total, int panels_per_split, int64_t NB,
               int split_offset, KnnEpi epi) {
   extern __shared__ unsigned char smem_raw[];
   Work w;
-  w.tile_first = blockIdx.x;
-  w.tile_end = (int64_t)blockIdx.x + 1;
+  w.tile_first = blockIdx.x >> 1;
+  w.tile_end = (int64_t)(blockIdx.x >> 1) + 1;
   w.tile_step = 1;
   const int split = (int)blockIdx.y + split_offset;
   w.panel_lo = split * panels_per_split;
@@ -377,7 +377,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// [rows, K] fp32 row-major -> box of TN rows x 32 floats, 128B swizzle, zero fill out of bounds
+// [rows, K] fp32 row-major -> box of TNH rows x 32 floats (one CTA's half of a panel), 128B swizzle,
+// zero fill out of bounds
 static int make_b_map(CUtensorMap *map, const float *ptr, int64_t rows, int K) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
@@ -386,7 +387,7 @@ static int make_b_map(CUtensorMap *map, const float *ptr, int64_t rows, int K) {
   }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)TN};
+  cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)TNH};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -452,7 +453,7 @@ extern "C" int runia_rownorm_score_tc(const float *X, int64_t N, int d, const fl
   }
   RowNormEpi epi{sign, r, mode, C, logits, alpha, out_f64, out_f32, N, 0, 0.f};
   const int panels = (int)ceil_div(r, TN);
-  dim3 grid((unsigned)std::min<int64_t>(ceil_div(N, TM), kNumSMs), 1);
+  dim3 grid(2 * (unsigned)std::min<int64_t>(ceil_div(N, TM2), kNumSMs / 2), 1);  // CTA pairs, one per TPC
   tc_kernel<RowNormEpi><<<grid, THREADS, kSmemBytes, (cudaStream_t)stream>>>(X, N, d, Prologue{mu, INFINITY}, mh, ml,
                                                                           panels, epi);
   count_launch();
@@ -480,7 +481,7 @@ extern "C" int runia_pca_transform_tc(const float *X, int64_t N, int D0, const f
   }
   PcaEpi epi{inv_scale, Z, d, N, 0};
   const int panels = (int)ceil_div(d, TN);
-  dim3 grid((unsigned)std::min<int64_t>(ceil_div(N, TM), kNumSMs), 1);
+  dim3 grid(2 * (unsigned)std::min<int64_t>(ceil_div(N, TM2), kNumSMs / 2), 1);
   tc_kernel<PcaEpi><<<grid, THREADS, kSmemBytes, (cudaStream_t)stream>>>(X, N, D0, Prologue{mean, INFINITY}, mh, ml,
                                                                       panels, epi);
   count_launch();
@@ -514,7 +515,7 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
   constexpr int kSeedPanels = 4;
   if (panels <= 2 * kSeedPanels) {
     epi.thr_in = nullptr; epi.thr_out = nullptr;
-    dim3 grid((unsigned)ceil_div(Nq, TM), (unsigned)splits);
+    dim3 grid(2 * (unsigned)ceil_div(Nq, TM2), (unsigned)splits);
     tc_knn_kernel<<<grid, THREADS, smem, st>>>(Q, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
     count_launch();
   } else {
@@ -525,10 +526,10 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
     KnnEpi seed = epi;
     seed.buf_d = seed_d; seed.buf_i = seed_i; seed.splits = 1;
     seed.thr_in = nullptr; seed.thr_out = thr_seed;
-    dim3 grid0((unsigned)ceil_div(Nq, TM), 1);
+    dim3 grid0(2 * (unsigned)ceil_div(Nq, TM2), 1);
     tc_knn_kernel<<<grid0, THREADS, smem, st>>>(Q, Nq, d, mh, ml, kSeedPanels, kSeedPanels, Nb, 0, seed);
     epi.thr_in = thr_seed; epi.thr_out = nullptr;
-    dim3 grid1((unsigned)ceil_div(Nq, TM), (unsigned)splits);
+    dim3 grid1(2 * (unsigned)ceil_div(Nq, TM2), (unsigned)splits);
     tc_knn_kernel<<<grid1, THREADS, smem, st>>>(Q, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
     count_launch(2);
   }
@@ -552,7 +553,7 @@ int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const flo
   KdeEpi epi{};
   epi.qn = qn; epi.bn = bn; epi.Nq = Nq; epi.b_hi = Nb; epi.scale = scale;
   epi.part_m = part_m; epi.part_s = part_s; epi.splits = splits; epi.split = 0;
-  dim3 grid((unsigned)ceil_div(Nq, TM), (unsigned)splits);
+  dim3 grid(2 * (unsigned)ceil_div(Nq, TM2), (unsigned)splits);
   tc_kde_kernel<<<grid, THREADS, kSmemBytes, st>>>(Q, Nq, d, mh, ml, (int)ceil_div(Nb, TN), (int)panels_per_split, Nb,
                                                   epi);
   count_launch();
