@@ -40,8 +40,11 @@ def split_tf32(w: torch.Tensor):
     return hi, lo
 
 
+TC_MAX_K = 4096  # tc_gemm.cuh kMaxK: the centre of the streamed operand is staged in shared memory
+
+
 def _tc_ok(k: int) -> bool:
-    return _ENGINE == "tc" and k % 4 == 0
+    return _ENGINE == "tc" and k % 4 == 0 and k <= TC_MAX_K
 
 
 def _empty(shape, dtype):

@@ -13,6 +13,8 @@
 // of the joint (Chebyshev) estimator, reduced across the warp through a transposed
 // shared-memory pass once per item -- so z is read from HBM exactly once.
 // Generic path (any 2 <= n_mc <= 32, 1 <= k < n_mc): same numbers, local-memory arrays.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace runia {
@@ -143,6 +145,227 @@ entropy_fast_kernel(const float *__restrict__ z, int64_t n_items, int D, float m
   if (lane == 0) h_mvn[item] = c_term + (double)D * (double)(kLn2 * (1.f + lg * (1.f / N)));
 }
 
+// ------------------------------ n_mc = 16, k = 5, D % 4 == 0 ---------------------------------
+// The estimator is bound by the min/max (ALU) pipe, not by HBM: per (item, dimension) it needs
+// 120 pair maxima, a 16-element sort and 66 window radii.  This kernel spends as few ALU-pipe
+// instructions on them as the ISA allows:
+//  * a lane owns TWO adjacent dimensions per step; the 120 pair differences of both are one packed
+//    FADD2 each (FMA pipe) and fold into the running Chebyshev maxima with one 3-input FMNMX3
+//    max(pm, |d.x|, |d.y|);
+//  * the sort is the 60-comparator, 10-layer network (optimal size for 16 keys);
+//  * the k-th neighbour distance of sample i is min over the windows [a, a+5] containing it of
+//    max(s_i - s_a, s_{a+5} - s_i); the two end points of a window need no max at all, the four
+//    interior points fold the min_dist clamp into a 3-input max, and the min over (up to) six
+//    windows is a chain of 3-input mins; the differences are packed FADD2 over the two dimensions;
+//  * log2 is the bare MUFU (the radii are >= min_dist > 0: no denormal fix-up).
+// z is streamed HBM -> shared memory with 16-byte cp.async into a per-warp 3-deep ring (one step =
+// 16 samples x 64 dimensions = 4 KB), two steps ahead of the arithmetic, so that no register is spent
+// on prefetch (the 120 maxima + 32 samples already need ~250) and HBM latency never reaches a warp.
+// Warps are persistent over items; the ring runs across item boundaries.
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float lg2_pos(float x) {  // x >= min_dist > 0, normal
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float warp_max_f32(float v) {  // CREDUX on sm_100a
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+#define RUNIA_CE(a, b)                   \
+  {                                      \
+    const float lo_ = fminf(v[a], v[b]); \
+    const float hi_ = fmaxf(v[a], v[b]); \
+    v[a] = lo_;                          \
+    v[b] = hi_;                          \
+  }
+// 60 compare-exchanges in 10 layers; tests/test_cabi_and_host.py checks the comparator list with the 0-1 principle
+__device__ __forceinline__ void sort16(float (&v)[16]) {
+  RUNIA_CE(0, 13) RUNIA_CE(1, 12) RUNIA_CE(2, 15) RUNIA_CE(3, 14) RUNIA_CE(4, 8) RUNIA_CE(5, 6) RUNIA_CE(7, 11) RUNIA_CE(9, 10)
+  RUNIA_CE(0, 5) RUNIA_CE(1, 7) RUNIA_CE(2, 9) RUNIA_CE(3, 4) RUNIA_CE(6, 13) RUNIA_CE(8, 14) RUNIA_CE(10, 15) RUNIA_CE(11, 12)
+  RUNIA_CE(0, 1) RUNIA_CE(2, 3) RUNIA_CE(4, 5) RUNIA_CE(6, 8) RUNIA_CE(7, 9) RUNIA_CE(10, 11) RUNIA_CE(12, 13) RUNIA_CE(14, 15)
+  RUNIA_CE(0, 2) RUNIA_CE(1, 3) RUNIA_CE(4, 10) RUNIA_CE(5, 11) RUNIA_CE(6, 7) RUNIA_CE(8, 9) RUNIA_CE(12, 14) RUNIA_CE(13, 15)
+  RUNIA_CE(1, 2) RUNIA_CE(3, 12) RUNIA_CE(4, 6) RUNIA_CE(5, 7) RUNIA_CE(8, 10) RUNIA_CE(9, 11) RUNIA_CE(13, 14)
+  RUNIA_CE(1, 4) RUNIA_CE(2, 6) RUNIA_CE(5, 8) RUNIA_CE(7, 10) RUNIA_CE(9, 13) RUNIA_CE(11, 14)
+  RUNIA_CE(2, 4) RUNIA_CE(3, 6) RUNIA_CE(9, 12) RUNIA_CE(11, 13)
+  RUNIA_CE(3, 5) RUNIA_CE(6, 8) RUNIA_CE(7, 9) RUNIA_CE(10, 12)
+  RUNIA_CE(3, 4) RUNIA_CE(5, 6) RUNIA_CE(7, 8) RUNIA_CE(9, 10) RUNIA_CE(11, 12)
+  RUNIA_CE(6, 7) RUNIA_CE(8, 9)
+}
+#undef RUNIA_CE
+
+constexpr int E16_WARPS = 4;
+constexpr int E16_RING = 3;
+constexpr int E16_STEP_FLOATS = 16 * 64;                                    // one step: 16 samples x 64 dims
+constexpr int E16_WARP_FLOATS = E16_RING * E16_STEP_FLOATS + 16 * 16;       // ring + Chebyshev matrix
+constexpr size_t kEntropy16Smem = (size_t)E16_WARPS * E16_WARP_FLOATS * sizeof(float);
+
+__global__ void __launch_bounds__(E16_WARPS * 32, 2)
+entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_dist, double c_term,
+                 double *__restrict__ h_z, double *__restrict__ h_mvn) {
+  constexpr int N = 16, K = 5, NPAIR = N * (N - 1) / 2;
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *ring = smem + (size_t)warp * E16_WARP_FLOATS;
+  float *dm = ring + E16_RING * E16_STEP_FLOATS;
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  const int64_t gw = (int64_t)blockIdx.x * E16_WARPS + warp;  // this warp's first item
+  const int64_t GW = (int64_t)gridDim.x * E16_WARPS;          // item stride
+  const int spi = (D + 63) >> 6;                              // steps per item
+  const int64_t n_my = gw < n_items ? (n_items - gw + GW - 1) / GW : 0;
+  const int64_t n_steps = n_my * spi;
+
+  // copy stream (runs two steps ahead of the compute stream)
+  int64_t c_item = gw;
+  int c_j = 0, c_buf = 0;
+  int64_t c_step = 0;
+  auto issue = [&]() {
+    if (c_step < n_steps) {
+      const float *src0 = z + c_item * (int64_t)N * D;
+      const int col = c_j * 64 + (lane & 15) * 4;
+      const uint32_t dst0 = ring_u32 + (uint32_t)(c_buf * E16_STEP_FLOATS + (lane & 15) * 4) * 4u;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int row = 2 * r + (lane >> 4);
+        const bool in = col < D;  // D % 4 == 0: a 16-byte chunk is entirely inside or outside the row
+        const float *src = in ? src0 + (int64_t)row * D + col : z;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)row * 256u), "l"(src),
+                     "r"(in ? 16 : 0)
+                     : "memory");
+      }
+      if (++c_j == spi) {
+        c_j = 0;
+        c_item += GW;
+      }
+      if (++c_buf == E16_RING) c_buf = 0;
+      ++c_step;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue();
+  issue();
+
+  float pm[NPAIR];
+#pragma unroll
+  for (int p = 0; p < NPAIR; ++p) pm[p] = 0.f;
+  int64_t item = gw;
+  int jstep = 0, buf = 0;
+  for (int64_t step = 0; step < n_steps; ++step) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    float2 x[N];
+    {
+      const float2 *b2 = reinterpret_cast<const float2 *>(ring + buf * E16_STEP_FLOATS) + lane;
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] = b2[i * 32];
+    }
+    issue();  // refills the buffer read one step ago (every lane is past that step: __syncwarp above)
+    const int j = jstep * 32 + lane;  // float2 column: dimensions 2j, 2j+1
+    {
+      int p = 0;
+#pragma unroll
+      for (int a = 0; a < N; ++a)
+#pragma unroll
+        for (int b = a + 1; b < N; ++b) {
+          const float2 d = sub2(x[a], x[b]);
+          pm[p] = fmaxf(fmaxf(pm[p], fabsf(d.x)), fabsf(d.y));
+          ++p;
+        }
+    }
+    float2 s[N];
+    {
+      float v[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = x[i].x;
+      sort16(v);
+#pragma unroll
+      for (int i = 0; i < N; ++i) s[i].x = v[i];
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = x[i].y;
+      sort16(v);
+#pragma unroll
+      for (int i = 0; i < N; ++i) s[i].y = v[i];
+    }
+    float2 wc[N - K];  // window widths, clamped
+#pragma unroll
+    for (int a = 0; a < N - K; ++a) {
+      const float2 d = sub2(s[a + K], s[a]);
+      wc[a] = make_float2(fmaxf(d.x, min_dist), fmaxf(d.y, min_dist));
+    }
+    float ax = 0.f, ay = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float rx = INFINITY, ry = INFINITY;
+#pragma unroll
+      for (int a = 0; a < N - K; ++a) {
+        if (a <= i && i <= a + K) {
+          if (i == a || i == a + K) {
+            rx = fminf(rx, wc[a].x);
+            ry = fminf(ry, wc[a].y);
+          } else {
+            const float2 L = sub2(s[i], s[a]);
+            const float2 R = sub2(s[a + K], s[i]);
+            rx = fminf(rx, fmaxf(fmaxf(L.x, R.x), min_dist));
+            ry = fminf(ry, fmaxf(fmaxf(L.y, R.y), min_dist));
+          }
+        }
+      }
+      ax += lg2_pos(rx);
+      ay += lg2_pos(ry);
+    }
+    if (2 * j < D) {
+      double2 o;  // h = -psi(k) + psi(n) + (1/n) sum log(2 r)   [d = 1]
+      o.x = c_term + (double)(kLn2 * (1.f + ax * (1.f / N)));
+      o.y = c_term + (double)(kLn2 * (1.f + ay * (1.f / N)));
+      reinterpret_cast<double2 *>(h_z + item * (int64_t)D)[j] = o;
+    }
+    if (++buf == E16_RING) buf = 0;
+    if (++jstep == spi) {
+      // ---- item complete: joint (Chebyshev) estimator from the 120 pair maxima ----
+      if (h_mvn != nullptr) {
+        __syncwarp();
+        int p = 0;
+#pragma unroll
+        for (int a = 0; a < N; ++a) {
+          if (lane == 0) dm[a * N + a] = 0.f;
+#pragma unroll
+          for (int b = a + 1; b < N; ++b) {
+            const float m = warp_max_f32(pm[p]);
+            if (lane == 0) {
+              dm[a * N + b] = m;
+              dm[b * N + a] = m;
+            }
+            ++p;
+          }
+        }
+        __syncwarp();
+        float lg = 0.f;
+        if (lane < N) {
+          float v[N];
+#pragma unroll
+          for (int b = 0; b < N; ++b) v[b] = dm[lane * N + b];
+          sort16(v);  // v[0] = 0 (self); v[K] = k-th neighbour
+          lg = lg2_pos(fmaxf(v[K], min_dist));
+        }
+        lg = warp_sum32(lg);
+        if (lane == 0) h_mvn[item] = c_term + (double)D * (double)(kLn2 * (1.f + lg * (1.f / N)));
+      }
+#pragma unroll
+      for (int p = 0; p < NPAIR; ++p) pm[p] = 0.f;
+      jstep = 0;
+      item += GW;
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------- generic path ------------------------------------------
 __global__ void __launch_bounds__(128)
 entropy_generic_dim_kernel(const float *__restrict__ z, int64_t n_items, int n, int D, int k, float min_dist,
@@ -228,6 +451,21 @@ extern "C" int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, 
   if (n_items == 0) return RUNIA_OK;
   RUNIA_REQUIRE(z && h_z, RUNIA_E_BADARG, "mcd_entropy: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (n_mc == 16 && k == 5 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(h_z) & 15) == 0) {
+    static bool attr16 = false;
+    if (!attr16) {
+      RUNIA_CUDA(cudaFuncSetAttribute(entropy16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kEntropy16Smem));
+      attr16 = true;
+    }
+    // persistent warps: two CTAs of four warps per SM (register-limited), items round-robin over warps
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n_items, E16_WARPS), (int64_t)2 * kNumSMs);
+    entropy16_kernel<<<grid, E16_WARPS * 32, kEntropy16Smem, st>>>(z, n_items, D, (float)min_dist, digamma_term, h_z,
+                                                                   h_mvn);
+    count_launch();
+    return finish_launch("mcd_entropy(16)");
+  }
   if (n_mc == 16 && k == 5) {
     constexpr int WARPS = 4;
     constexpr size_t smem = (size_t)WARPS * 120 * 32 * sizeof(float);

@@ -20,10 +20,14 @@
 //   warp 2      TMEM allocator (512 columns = two 128 x 256 accumulators per CTA, double buffered)
 //   warps 4-7   epilogue: tcgen05.ld 32 columns at a time; thread t owns output row t, so every
 //               row-wise reduction (sum of squares, log-sum-exp, top-k filter) is thread-local
-//   warps 8-15  A converters: coalesced fp32 global loads (three k-blocks in flight per thread to
-//               cover HBM latency) -> fused prologue (subtract centre, clip) -> hi/lo split ->
-//               st.shared in the UMMA 128B-swizzle layout.  The streamed operand is therefore
-//               read from HBM exactly once, as raw fp32.
+//   warps 8-15  A converters.  The TMA warp streams the RAW fp32 A tile of a k-block straight into the
+//               stage's A_hi plane (128B-swizzled by the TMA unit, i.e. already in UMMA layout, rows
+//               and columns out of bounds zero-filled); the converters read it back with LDS.128,
+//               apply the fused prologue (subtract centre, clip), split into hi / lo, overwrite the
+//               hi plane in place and write the lo plane.  The streamed operand is therefore read
+//               from HBM exactly once, as raw fp32, by the copy engine: no thread of the CTA has a
+//               global load in flight, so the fence.proxy.async each converter needs before handing
+//               the stage to the tensor core (a MEMBAR in SASS) never waits on HBM latency.
 // Pipelines: smem ring (full/empty mbarriers; the leader's `full` collects the TMA bytes of both
 // CTAs and one arrival per converter warp of both CTAs), TMEM ring (tmem_full via tcgen05.commit,
 // the leader's tmem_empty collects the epilogue threads of both CTAs).
@@ -44,7 +48,6 @@ constexpr int STAGES = 3;
 constexpr int THREADS = 512;
 constexpr int CONV_THREADS = 256;  // warps 8..15
 constexpr int CONV_WARPS = CONV_THREADS / 32;
-constexpr int CONV_DEPTH = 3;      // k-blocks of A kept in flight per converter thread (registers)
 constexpr int A_PLANE_BYTES = TM * TK * 4;  // 16 KB
 constexpr int B_PLANE_BYTES = TNH * TK * 4;  // 16 KB (this CTA's half of the panel)
 constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;  // 64 KB
@@ -123,6 +126,13 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(map), "r"(leader_bar), "r"(x), "r"(y)
+      : "memory");
+}
+// plain TMA load into this CTA's shared memory, bytes posted on this CTA's own barrier
+__device__ __forceinline__ void tma_load_2d_local(uint32_t dst, const CUtensorMap *map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(x), "r"(y)
       : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
@@ -218,7 +228,7 @@ struct Work {
 //   __device__ void panel_done(int panel)                        -- after a whole panel
 //   __device__ void finish()                                     -- after the last panel of a row tile
 template <class E>
-__device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M, int K, const Prologue pro,
+__device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const Prologue pro,
                                           const CUtensorMap *tmB_hi, const CUtensorMap *tmB_lo, const Work work,
                                           E &epi, unsigned char *smem_raw) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -235,20 +245,27 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
   auto empty_bar = [&](int s) { return bar0 + 8 * (STAGES + s); };          // one per CTA
   auto tfull_bar = [&](int b) { return bar0 + 8 * (2 * STAGES + b); };      // one per CTA
   auto tempty_bar = [&](int b) { return bar0 + 8 * (2 * STAGES + 2 + b); }; // used in the leader only
-  const uint32_t tmem_slot = bar0 + 8 * (2 * STAGES + 4);
-  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(gbase + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+  auto raw_bar = [&](int s) { return bar0 + 8 * (2 * STAGES + 4 + s); };    // one per CTA: raw A tile landed
+  const uint32_t tmem_slot = bar0 + 8 * (3 * STAGES + 4);
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(gbase + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 4));
+  const uint32_t sub_smem = bar0 + SMEM_BAR_BYTES;  // [nkb * TK] floats: the centre, zero-padded
+  float *sub_ptr = reinterpret_cast<float *>(gbase + STAGES * STAGE_BYTES + SMEM_BAR_BYTES);
 
   const int nkb = (K + TK - 1) / TK;
   const int n_panels = work.panel_hi - work.panel_lo;
 
   if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(tmA);
     tma_prefetch_desc(tmB_hi);
     tma_prefetch_desc(tmB_lo);
   }
+  if (pro.sub)
+    for (int k = threadIdx.x; k < nkb * TK; k += THREADS) sub_ptr[k] = k < K ? __ldg(pro.sub + k) : 0.f;
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1 + 2 * CONV_WARPS);  // leader's expect_tx arrival + converter warps of both CTAs
       mbar_init(empty_bar(s), 1);                  // tcgen05.commit (multicast)
+      mbar_init(raw_bar(s), 1);                    // this CTA's TMA warp (expect_tx)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);         // tcgen05.commit (multicast)
@@ -259,21 +276,25 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   __syncwarp();
   tc_fence_before();
+  __syncthreads();  // sub_ptr visible to the converters
   cluster_sync_all();  // barriers of both CTAs initialised before anyone signals across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ------------------------------ TMA producer (this CTA's half of the B planes) ------------------------------
+    // -------------- TMA producer (this CTA's raw A tile and its half of the B planes) --------------
     if (lane == 0) {
       int it = 0;
       for (int64_t t = work.tile_first; t < work.tile_end; t += work.tile_step) {
+        const int row0 = (int)(t * TM2 + (int64_t)rank * TM);
         for (int p = 0; p < n_panels; ++p) {
           const int n0 = (work.panel_lo + p) * TN + (int)rank * TNH;
           for (int kb = 0; kb < nkb; ++kb, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
             mbar_wait(empty_bar(s), ph ^ 1);
+            mbar_expect_tx(raw_bar(s), A_PLANE_BYTES);
+            tma_load_2d_local(sA_hi(s), tmA, raw_bar(s), kb * TK, row0);
             if (rank == 0) mbar_expect_tx(full_bar(s), 4 * B_PLANE_BYTES);  // both planes, both CTAs
             const uint32_t lbar = map_to_cta(full_bar(s), 0);
             tma_load_2d_pair(sB_hi(s), tmB_hi, lbar, kb * TK, n0);
@@ -343,93 +364,55 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
   } else if (warp >= 8) {
     // ------------------------------ A converters ------------------------------
     const int ct = threadIdx.x - 256;  // 0..255
-    const int chunk = ct & 7;          // 16-byte chunk inside the 128-byte k-block row
-    const int r0 = ct >> 3;            // rows r0, r0+32, r0+64, r0+96
-    const bool vec_ok = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    const int chunk = ct & 7;          // 16-byte chunk (4 floats) inside the 128-byte k-block row
+    const int r0 = ct >> 3;            // rows r0, r0+32, r0+64, r0+96 (all share r & 7, hence the swizzle)
+    const uint32_t off0 = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((chunk ^ (r0 & 7)) << 4));
     const int64_t n_my_tiles =
         work.tile_first < work.tile_end ? (work.tile_end - work.tile_first + work.tile_step - 1) / work.tile_step : 0;
-    const int64_t per_tile = (int64_t)n_panels * nkb;
-    const int64_t n_items = n_my_tiles * per_tile;  // flat sequence of (tile, panel, k-block)
+    const int64_t n_items = n_my_tiles * (int64_t)n_panels * nkb;  // flat sequence of (tile, panel, k-block)
     const uint32_t lfull0 = map_to_cta(full_bar(0), 0);  // leader's full barriers, 8 bytes apart
-    auto load_item = [&](int64_t item, float4 (&x)[4]) {
-      const int64_t t = work.tile_first + (item / per_tile) * work.tile_step;
-      const int kb = (int)(item % nkb);
-      const int k = kb * TK + chunk * 4;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int64_t row = t * TM2 + (int64_t)rank * TM + r0 + 32 * i;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < M && item < n_items) {
-          const float *src = A + row * (int64_t)K + k;
-          if (vec_ok && k + 3 < K) {
-            v = __ldg(reinterpret_cast<const float4 *>(src));
-          } else {
-            if (k + 0 < K) v.x = __ldg(src + 0);
-            if (k + 1 < K) v.y = __ldg(src + 1);
-            if (k + 2 < K) v.z = __ldg(src + 2);
-            if (k + 3 < K) v.w = __ldg(src + 3);
-          }
-        }
-        x[i] = v;
-      }
-    };
-    auto convert_store = [&](int64_t item, const float4 (&x)[4]) {
-      const int s = (int)(item % STAGES);
-      const uint32_t ph = (uint32_t)((item / STAGES) & 1);
-      const int kb = (int)(item % nkb);
-      const int k = kb * TK + chunk * 4;
+    const bool has_sub = pro.sub != nullptr;
+    const bool has_clip = pro.clip < INFINITY;
+    int s = 0, kb = 0;
+    uint32_t ph = 0;
+    for (int64_t item = 0; item < n_items; ++item) {
       float4 sub = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (pro.sub) {
-        if (k + 0 < K) sub.x = __ldg(pro.sub + k + 0);
-        if (k + 1 < K) sub.y = __ldg(pro.sub + k + 1);
-        if (k + 2 < K) sub.z = __ldg(pro.sub + k + 2);
-        if (k + 3 < K) sub.w = __ldg(pro.sub + k + 3);
-      }
-      float4 hi[4], lo[4];
+      if (has_sub)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(sub.x), "=f"(sub.y), "=f"(sub.z), "=f"(sub.w)
+                     : "r"(sub_smem + (uint32_t)(kb * TK + chunk * 4) * 4));
+      mbar_wait(raw_bar(s), ph);  // raw fp32 tile of this k-block is in the A_hi plane
+      const uint32_t a_hi = sA_hi(s) + off0, a_lo = sA_lo(s) + off0;
+      float4 x[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
+                     : "r"(a_hi + (uint32_t)i * 4096u));
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float e[4] = {x[i].x - sub.x, x[i].y - sub.y, x[i].z - sub.z, x[i].w - sub.w};
         float h[4], l[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          if (pro.clip < INFINITY) e[q] = e[q] > pro.clip ? pro.clip : e[q];
-          if (k + q >= K) e[q] = 0.f;
+          if (has_clip) e[q] = e[q] > pro.clip ? pro.clip : e[q];
           h[q] = to_tf32(e[q]);
           l[q] = to_tf32(e[q] - h[q]);
         }
-        hi[i] = make_float4(h[0], h[1], h[2], h[3]);
-        lo[i] = make_float4(l[0], l[1], l[2], l[3]);
-      }
-      mbar_wait(empty_bar(s), ph ^ 1);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = r0 + 32 * i;
-        const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sA_hi(s) + off), "f"(hi[i].x), "f"(hi[i].y),
-                     "f"(hi[i].z), "f"(hi[i].w)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + (uint32_t)i * 4096u), "f"(h[0]), "f"(h[1]),
+                     "f"(h[2]), "f"(h[3])
                      : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sA_lo(s) + off), "f"(lo[i].x), "f"(lo[i].y),
-                     "f"(lo[i].z), "f"(lo[i].w)
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + (uint32_t)i * 4096u), "f"(l[0]), "f"(l[1]),
+                     "f"(l[2]), "f"(l[3])
                      : "memory");
       }
       fence_proxy_async();  // make the generic-proxy stores visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(lfull0 + 8 * (uint32_t)s);  // one arrival per converter warp
-    };
-    float4 xa[4], xb[4], xc[4];  // CONV_DEPTH = 3 register slots, statically indexed
-    load_item(0, xa);
-    load_item(1, xb);
-    load_item(2, xc);
-    for (int64_t item = 0; item < n_items; item += CONV_DEPTH) {
-      convert_store(item, xa);
-      load_item(item + 3, xa);
-      if (item + 1 < n_items) {
-        convert_store(item + 1, xb);
-        load_item(item + 4, xb);
-      }
-      if (item + 2 < n_items) {
-        convert_store(item + 2, xc);
-        load_item(item + 5, xc);
+      if (++kb == nkb) kb = 0;
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1;
       }
     }
   }
@@ -444,7 +427,11 @@ __device__ __forceinline__ void run_tiles(const float *__restrict__ A, int64_t M
   }
 }
 
-constexpr size_t kSmemBytes = (size_t)STAGES * STAGE_BYTES + SMEM_BAR_BYTES + SMEM_ALIGN;
+// dynamic shared memory: stages + barriers + the zero-padded centre [ceil(K / TK) * TK floats] + alignment slack
+static inline size_t smem_bytes(int K) {
+  return (size_t)STAGES * STAGE_BYTES + SMEM_BAR_BYTES + (size_t)((K + TK - 1) / TK) * TK * 4 + SMEM_ALIGN;
+}
+constexpr int kMaxK = 4096;  // keeps the centre within the shared-memory budget
 
 }  // namespace tc
 }  // namespace runia

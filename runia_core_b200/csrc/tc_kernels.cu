@@ -303,7 +303,7 @@ struct KnnEpi {
 
 template <class E>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-tc_kernel(const float *__restrict__ A, int64_t M, int K, Prologue pro, const __grid_constant__ CUtensorMap tmB_hi,
+tc_kernel(const __grid_constant__ CUtensorMap tmA, int64_t M, int K, Prologue pro, const __grid_constant__ CUtensorMap tmB_hi,
           const __grid_constant__ CUtensorMap tmB_lo, int panels_total, E epi) {
   extern __shared__ unsigned char smem_raw[];
   Work w;  // persistent: CTA pair p takes the 256-row tiles p, p + #pairs, ...
@@ -312,7 +312,7 @@ tc_kernel(const float *__restrict__ A, int64_t M, int K, Prologue pro, const __g
   w.tile_step = gridDim.x >> 1;
   w.panel_lo = 0;
   w.panel_hi = panels_total;
-  run_tiles(A, M, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
+  run_tiles(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
 __device__ __forceinline__ Work split_work(int panels_total, int panels_per_split) {
@@ -326,7 +326,7 @@ __device__ __forceinline__ Work split_work(int panels_total, int panels_per_spli
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-tc_kde_kernel(const float *__restrict__ A, int64_t M, int K, const __grid_constant__ CUtensorMap tmB_hi,
+tc_kde_kernel(const __grid_constant__ CUtensorMap tmA, int64_t M, int K, const __grid_constant__ CUtensorMap tmB_hi,
               const __grid_constant__ CUtensorMap tmB_lo, int panels_total, int panels_per_split, int64_t NB,
               KdeEpi epi) {
   extern __shared__ unsigned char smem_raw[];
@@ -335,11 +335,11 @@ tc_kde_kernel(const float *__restrict__ A, int64_t M, int K, const __grid_consta
   const int64_t hi = (int64_t)w.panel_hi * TN;
   epi.b_hi = hi < NB ? hi : NB;
   const Prologue pro{nullptr, INFINITY};
-  run_tiles(A, M, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
+  run_tiles(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-tc_knn_kernel(const float *__restrict__ A, int64_t M, int K, const __grid_constant__ CUtensorMap tmB_hi,
+tc_knn_kernel(const __grid_constant__ CUtensorMap tmA, int64_t M, int K, const __grid_constant__ CUtensorMap tmB_hi,
               const __grid_constant__ CUtensorMap tmB_lo, int panels_total, int panels_per_split, int64_t NB,
               int split_offset, KnnEpi epi) {
   extern __shared__ unsigned char smem_raw[];
@@ -354,7 +354,7 @@ tc_knn_kernel(const float *__restrict__ A, int64_t M, int K, const __grid_consta
   const int64_t hi = (int64_t)w.panel_hi * TN;
   epi.b_hi = hi < NB ? hi : NB;
   const Prologue pro{nullptr, INFINITY};
-  run_tiles(A, M, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
+  run_tiles(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -379,7 +379,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // [rows, K] fp32 row-major -> box of TNH rows x 32 floats (one CTA's half of a panel), 128B swizzle,
 // zero fill out of bounds
-static int make_b_map(CUtensorMap *map, const float *ptr, int64_t rows, int K) {
+static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int K, int box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -387,7 +387,7 @@ static int make_b_map(CUtensorMap *map, const float *ptr, int64_t rows, int K) {
   }
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)TNH};
+  cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -398,6 +398,12 @@ static int make_b_map(CUtensorMap *map, const float *ptr, int64_t rows, int K) {
   }
   return RUNIA_OK;
 }
+
+static int make_b_map(CUtensorMap *map, const float *ptr, int64_t rows, int K) { return make_map(map, ptr, rows, K, TNH); }
+// streamed operand: box of TM rows x 32 floats, lands in the A_hi plane of a stage as raw fp32
+static int make_a_map(CUtensorMap *map, const float *ptr, int64_t rows, int K) { return make_map(map, ptr, rows, K, TM); }
+
+constexpr size_t kSmemMax = (size_t)STAGES * STAGE_BYTES + SMEM_BAR_BYTES + (size_t)kMaxK * 4 + SMEM_ALIGN;
 
 template <class Kern>
 static int set_smem(Kern kern, size_t bytes) {
@@ -410,7 +416,7 @@ static int set_smem(Kern kern, size_t bytes) {
 }
 
 bool usable(const void *A, int K, const void *B_hi, const void *B_lo) {
-  return (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+  return (K % 4 == 0) && K <= kMaxK && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
          ((reinterpret_cast<uintptr_t>(B_hi) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B_lo) & 15) == 0);
 }
 
@@ -440,21 +446,23 @@ extern "C" int runia_rownorm_score_tc(const float *X, int64_t N, int d, const fl
   RUNIA_REQUIRE(mode != RUNIA_ROWNORM_VIM || (logits && C > 0), RUNIA_E_BADARG, "rownorm_score_tc: ViM needs logits");
   RUNIA_REQUIRE(usable(X, d, Wt_hi, Wt_lo) && (!mu || (reinterpret_cast<uintptr_t>(mu) & 15) == 0), RUNIA_E_UNSUPPORTED,
                 "rownorm_score_tc: needs d %% 4 == 0 and 16-byte aligned pointers");
-  CUtensorMap mh, ml;
-  int rc = make_b_map(&mh, Wt_hi, r, d);
+  CUtensorMap ma, mh, ml;
+  int rc = make_a_map(&ma, X, N, d);
+  if (rc) return rc;
+  rc = make_b_map(&mh, Wt_hi, r, d);
   if (rc) return rc;
   rc = make_b_map(&ml, Wt_lo, r, d);
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
-    rc = set_smem(tc_kernel<RowNormEpi>, kSmemBytes);
+    rc = set_smem(tc_kernel<RowNormEpi>, kSmemMax);
     if (rc) return rc;
     attr = true;
   }
   RowNormEpi epi{sign, r, mode, C, logits, alpha, out_f64, out_f32, N, 0, 0.f};
   const int panels = (int)ceil_div(r, TN);
   dim3 grid(2 * (unsigned)std::min<int64_t>(ceil_div(N, TM2), kNumSMs / 2), 1);  // CTA pairs, one per TPC
-  tc_kernel<RowNormEpi><<<grid, THREADS, kSmemBytes, (cudaStream_t)stream>>>(X, N, d, Prologue{mu, INFINITY}, mh, ml,
+  tc_kernel<RowNormEpi><<<grid, THREADS, smem_bytes(d), (cudaStream_t)stream>>>(ma, N, d, Prologue{mu, INFINITY}, mh, ml,
                                                                           panels, epi);
   count_launch();
   return finish_launch("rownorm_score_tc");
@@ -468,21 +476,23 @@ extern "C" int runia_pca_transform_tc(const float *X, int64_t N, int D0, const f
   RUNIA_REQUIRE(usable(X, D0, C_hi, C_lo) && (!mean || (reinterpret_cast<uintptr_t>(mean) & 15) == 0) &&
                     (reinterpret_cast<uintptr_t>(Z) & 15) == 0,
                 RUNIA_E_UNSUPPORTED, "pca_transform_tc: needs D0 %% 4 == 0 and 16-byte aligned pointers");
-  CUtensorMap mh, ml;
-  int rc = make_b_map(&mh, C_hi, d, D0);
+  CUtensorMap ma, mh, ml;
+  int rc = make_a_map(&ma, X, N, D0);
+  if (rc) return rc;
+  rc = make_b_map(&mh, C_hi, d, D0);
   if (rc) return rc;
   rc = make_b_map(&ml, C_lo, d, D0);
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
-    rc = set_smem(tc_kernel<PcaEpi>, kSmemBytes);
+    rc = set_smem(tc_kernel<PcaEpi>, kSmemMax);
     if (rc) return rc;
     attr = true;
   }
   PcaEpi epi{inv_scale, Z, d, N, 0};
   const int panels = (int)ceil_div(d, TN);
   dim3 grid(2 * (unsigned)std::min<int64_t>(ceil_div(N, TM2), kNumSMs / 2), 1);
-  tc_kernel<PcaEpi><<<grid, THREADS, kSmemBytes, (cudaStream_t)stream>>>(X, N, D0, Prologue{mean, INFINITY}, mh, ml,
+  tc_kernel<PcaEpi><<<grid, THREADS, smem_bytes(D0), (cudaStream_t)stream>>>(ma, N, D0, Prologue{mean, INFINITY}, mh, ml,
                                                                       panels, epi);
   count_launch();
   return finish_launch("pca_transform_tc");
@@ -495,15 +505,17 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
                              const float *bn, int64_t Nb, int d, int kcap, int capp, int splits,
                              int64_t panels_per_split, float *buf_d, int32_t *buf_i, float *thr_seed,
                              float *seed_d, int32_t *seed_i, cudaStream_t st) {
-  CUtensorMap mh, ml;
-  int rc = make_b_map(&mh, B_hi, Nb, d);
+  CUtensorMap ma, mh, ml;
+  int rc = make_a_map(&ma, Q, Nq, d);
+  if (rc) return rc;
+  rc = make_b_map(&mh, B_hi, Nb, d);
   if (rc) return rc;
   rc = make_b_map(&ml, B_lo, Nb, d);
   if (rc) return rc;
-  const size_t smem = kSmemBytes;
+  const size_t smem = smem_bytes(d);
   static bool attr = false;
   if (!attr) {
-    rc = set_smem(tc_knn_kernel, smem);
+    rc = set_smem(tc_knn_kernel, kSmemMax);
     if (rc) return rc;
     attr = true;
   }
@@ -516,7 +528,7 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
   if (panels <= 2 * kSeedPanels) {
     epi.thr_in = nullptr; epi.thr_out = nullptr;
     dim3 grid(2 * (unsigned)ceil_div(Nq, TM2), (unsigned)splits);
-    tc_knn_kernel<<<grid, THREADS, smem, st>>>(Q, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
+    tc_knn_kernel<<<grid, THREADS, smem, st>>>(ma, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
     count_launch();
   } else {
     // Seed pass over the first few panels of the bank: its per-row kcap-th smallest distance is a
@@ -527,10 +539,10 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
     seed.buf_d = seed_d; seed.buf_i = seed_i; seed.splits = 1;
     seed.thr_in = nullptr; seed.thr_out = thr_seed;
     dim3 grid0(2 * (unsigned)ceil_div(Nq, TM2), 1);
-    tc_knn_kernel<<<grid0, THREADS, smem, st>>>(Q, Nq, d, mh, ml, kSeedPanels, kSeedPanels, Nb, 0, seed);
+    tc_knn_kernel<<<grid0, THREADS, smem, st>>>(ma, Nq, d, mh, ml, kSeedPanels, kSeedPanels, Nb, 0, seed);
     epi.thr_in = thr_seed; epi.thr_out = nullptr;
     dim3 grid1(2 * (unsigned)ceil_div(Nq, TM2), (unsigned)splits);
-    tc_knn_kernel<<<grid1, THREADS, smem, st>>>(Q, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
+    tc_knn_kernel<<<grid1, THREADS, smem, st>>>(ma, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
     count_launch(2);
   }
   return finish_launch("knn_candidates_tc");
@@ -539,14 +551,16 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
 int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                           const float *bn, int64_t Nb, int d, float scale, int splits, int64_t panels_per_split,
                           float *part_m, float *part_s, cudaStream_t st) {
-  CUtensorMap mh, ml;
-  int rc = make_b_map(&mh, B_hi, Nb, d);
+  CUtensorMap ma, mh, ml;
+  int rc = make_a_map(&ma, Q, Nq, d);
+  if (rc) return rc;
+  rc = make_b_map(&mh, B_hi, Nb, d);
   if (rc) return rc;
   rc = make_b_map(&ml, B_lo, Nb, d);
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
-    rc = set_smem(tc_kde_kernel, kSmemBytes);
+    rc = set_smem(tc_kde_kernel, kSmemMax);
     if (rc) return rc;
     attr = true;
   }
@@ -554,7 +568,7 @@ int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const flo
   epi.qn = qn; epi.bn = bn; epi.Nq = Nq; epi.b_hi = Nb; epi.scale = scale;
   epi.part_m = part_m; epi.part_s = part_s; epi.splits = splits; epi.split = 0;
   dim3 grid(2 * (unsigned)ceil_div(Nq, TM2), (unsigned)splits);
-  tc_kde_kernel<<<grid, THREADS, kSmemBytes, st>>>(Q, Nq, d, mh, ml, (int)ceil_div(Nb, TN), (int)panels_per_split, Nb,
+  tc_kde_kernel<<<grid, THREADS, smem_bytes(d), st>>>(ma, Nq, d, mh, ml, (int)ceil_div(Nb, TN), (int)panels_per_split, Nb,
                                                   epi);
   count_launch();
   return finish_launch("kde_partial_tc");
