@@ -252,115 +252,111 @@ entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_
   issue();
   issue();
 
-  float pm[NPAIR];
+  int buf = 0;
+  for (int64_t item = gw; item < n_items; item += GW) {
+    float pm[NPAIR];
 #pragma unroll
-  for (int p = 0; p < NPAIR; ++p) pm[p] = 0.f;
-  int64_t item = gw;
-  int jstep = 0, buf = 0;
-  for (int64_t step = 0; step < n_steps; ++step) {
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncwarp();
-    float2 x[N];
-    {
-      const float2 *b2 = reinterpret_cast<const float2 *>(ring + buf * E16_STEP_FLOATS) + lane;
+    for (int p = 0; p < NPAIR; ++p) pm[p] = 0.f;
+#pragma unroll 1
+    for (int jstep = 0; jstep < spi; ++jstep) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncwarp();
+      float2 x[N];
+      {
+        const float2 *b2 = reinterpret_cast<const float2 *>(ring + buf * E16_STEP_FLOATS) + lane;
 #pragma unroll
-      for (int i = 0; i < N; ++i) x[i] = b2[i * 32];
-    }
-    issue();  // refills the buffer read one step ago (every lane is past that step: __syncwarp above)
-    const int j = jstep * 32 + lane;  // float2 column: dimensions 2j, 2j+1
-    {
-      int p = 0;
-#pragma unroll
-      for (int a = 0; a < N; ++a)
-#pragma unroll
-        for (int b = a + 1; b < N; ++b) {
-          const float2 d = sub2(x[a], x[b]);
-          pm[p] = fmaxf(fmaxf(pm[p], fabsf(d.x)), fabsf(d.y));
-          ++p;
-        }
-    }
-    float2 s[N];
-    {
-      float v[N];
-#pragma unroll
-      for (int i = 0; i < N; ++i) v[i] = x[i].x;
-      sort16(v);
-#pragma unroll
-      for (int i = 0; i < N; ++i) s[i].x = v[i];
-#pragma unroll
-      for (int i = 0; i < N; ++i) v[i] = x[i].y;
-      sort16(v);
-#pragma unroll
-      for (int i = 0; i < N; ++i) s[i].y = v[i];
-    }
-    float2 wc[N - K];  // window widths, clamped
-#pragma unroll
-    for (int a = 0; a < N - K; ++a) {
-      const float2 d = sub2(s[a + K], s[a]);
-      wc[a] = make_float2(fmaxf(d.x, min_dist), fmaxf(d.y, min_dist));
-    }
-    float ax = 0.f, ay = 0.f;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      float rx = INFINITY, ry = INFINITY;
-#pragma unroll
-      for (int a = 0; a < N - K; ++a) {
-        if (a <= i && i <= a + K) {
-          if (i == a || i == a + K) {
-            rx = fminf(rx, wc[a].x);
-            ry = fminf(ry, wc[a].y);
-          } else {
-            const float2 L = sub2(s[i], s[a]);
-            const float2 R = sub2(s[a + K], s[i]);
-            rx = fminf(rx, fmaxf(fmaxf(L.x, R.x), min_dist));
-            ry = fminf(ry, fmaxf(fmaxf(L.y, R.y), min_dist));
-          }
-        }
+        for (int i = 0; i < N; ++i) x[i] = b2[i * 32];
       }
-      ax += lg2_pos(rx);
-      ay += lg2_pos(ry);
-    }
-    if (2 * j < D) {
-      double2 o;  // h = -psi(k) + psi(n) + (1/n) sum log(2 r)   [d = 1]
-      o.x = c_term + (double)(kLn2 * (1.f + ax * (1.f / N)));
-      o.y = c_term + (double)(kLn2 * (1.f + ay * (1.f / N)));
-      reinterpret_cast<double2 *>(h_z + item * (int64_t)D)[j] = o;
-    }
-    if (++buf == E16_RING) buf = 0;
-    if (++jstep == spi) {
-      // ---- item complete: joint (Chebyshev) estimator from the 120 pair maxima ----
-      if (h_mvn != nullptr) {
-        __syncwarp();
+      issue();  // refills the buffer read one step ago (every lane is past that step: __syncwarp above)
+      if (++buf == E16_RING) buf = 0;
+      const int j = jstep * 32 + lane;  // float2 column: dimensions 2j, 2j+1
+      {
         int p = 0;
 #pragma unroll
-        for (int a = 0; a < N; ++a) {
-          if (lane == 0) dm[a * N + a] = 0.f;
+        for (int a = 0; a < N; ++a)
 #pragma unroll
           for (int b = a + 1; b < N; ++b) {
-            const float m = warp_max_f32(pm[p]);
-            if (lane == 0) {
-              dm[a * N + b] = m;
-              dm[b * N + a] = m;
-            }
+            const float2 d = sub2(x[a], x[b]);
+            pm[p] = fmaxf(fmaxf(pm[p], fabsf(d.x)), fabsf(d.y));
             ++p;
           }
-        }
-        __syncwarp();
-        float lg = 0.f;
-        if (lane < N) {
-          float v[N];
-#pragma unroll
-          for (int b = 0; b < N; ++b) v[b] = dm[lane * N + b];
-          sort16(v);  // v[0] = 0 (self); v[K] = k-th neighbour
-          lg = lg2_pos(fmaxf(v[K], min_dist));
-        }
-        lg = warp_sum32(lg);
-        if (lane == 0) h_mvn[item] = c_term + (double)D * (double)(kLn2 * (1.f + lg * (1.f / N)));
       }
+      float2 s[N];
+      {
+        float v[N];
 #pragma unroll
-      for (int p = 0; p < NPAIR; ++p) pm[p] = 0.f;
-      jstep = 0;
-      item += GW;
+        for (int i = 0; i < N; ++i) v[i] = x[i].x;
+        sort16(v);
+#pragma unroll
+        for (int i = 0; i < N; ++i) s[i].x = v[i];
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = x[i].y;
+        sort16(v);
+#pragma unroll
+        for (int i = 0; i < N; ++i) s[i].y = v[i];
+      }
+      float2 wc[N - K];  // window widths, clamped
+#pragma unroll
+      for (int a = 0; a < N - K; ++a) {
+        const float2 d = sub2(s[a + K], s[a]);
+        wc[a] = make_float2(fmaxf(d.x, min_dist), fmaxf(d.y, min_dist));
+      }
+      float ax = 0.f, ay = 0.f;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        float rx = INFINITY, ry = INFINITY;
+#pragma unroll
+        for (int a = 0; a < N - K; ++a) {
+          if (a <= i && i <= a + K) {
+            if (i == a || i == a + K) {
+              rx = fminf(rx, wc[a].x);
+              ry = fminf(ry, wc[a].y);
+            } else {
+              const float2 L = sub2(s[i], s[a]);
+              const float2 R = sub2(s[a + K], s[i]);
+              rx = fminf(rx, fmaxf(fmaxf(L.x, R.x), min_dist));
+              ry = fminf(ry, fmaxf(fmaxf(L.y, R.y), min_dist));
+            }
+          }
+        }
+        ax += lg2_pos(rx);
+        ay += lg2_pos(ry);
+      }
+      if (2 * j < D) {
+        double2 o;  // h = -psi(k) + psi(n) + (1/n) sum log(2 r)   [d = 1]
+        o.x = c_term + (double)(kLn2 * (1.f + ax * (1.f / N)));
+        o.y = c_term + (double)(kLn2 * (1.f + ay * (1.f / N)));
+        reinterpret_cast<double2 *>(h_z + item * (int64_t)D)[j] = o;
+      }
+    }
+    // ---- item complete: joint (Chebyshev) estimator from the 120 pair maxima ----
+    if (h_mvn != nullptr) {
+      __syncwarp();
+      int p = 0;
+#pragma unroll
+      for (int a = 0; a < N; ++a) {
+        if (lane == 0) dm[a * N + a] = 0.f;
+#pragma unroll
+        for (int b = a + 1; b < N; ++b) {
+          const float m = warp_max_f32(pm[p]);
+          if (lane == 0) {
+            dm[a * N + b] = m;
+            dm[b * N + a] = m;
+          }
+          ++p;
+        }
+      }
+      __syncwarp();
+      float lg = 0.f;
+      if (lane < N) {
+        float v[N];
+#pragma unroll
+        for (int b = 0; b < N; ++b) v[b] = dm[lane * N + b];
+        sort16(v);  // v[0] = 0 (self); v[K] = k-th neighbour
+        lg = lg2_pos(fmaxf(v[K], min_dist));
+      }
+      lg = warp_sum32(lg);
+      if (lane == 0) h_mvn[item] = c_term + (double)D * (double)(kLn2 * (1.f + lg * (1.f / N)));
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");

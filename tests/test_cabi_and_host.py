@@ -193,3 +193,18 @@ def test_sharded_exchange_gloo_world2():
     ret = mp.Manager().dict()
     mp.spawn(_gloo_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def test_entropy_sorting_network_sorts_every_input():
+    """The 16-key comparator network of csrc/entropy.cu (sort16) is checked with the 0-1 principle:
+    a comparator network sorts every input iff it sorts all 2^16 binary inputs."""
+    src = open(os.path.join(ROOT, "runia_core_b200", "csrc", "entropy.cu")).read()
+    body = src[src.index("void sort16("):]
+    body = body[:body.index("#undef RUNIA_CE")]
+    ces = [(int(a), int(b)) for a, b in re.findall(r"RUNIA_CE\((\d+),\s*(\d+)\)", body)]
+    assert len(ces) == 60 and all(0 <= a < b < 16 for a, b in ces)
+    x = ((np.arange(1 << 16)[:, None] >> np.arange(16)) & 1).astype(np.int8)
+    for a, b in ces:
+        lo, hi = np.minimum(x[:, a], x[:, b]), np.maximum(x[:, a], x[:, b])
+        x[:, a], x[:, b] = lo, hi
+    assert (np.diff(x, axis=1) >= 0).all()
