@@ -32,12 +32,23 @@ N_TRAIN = 50_000
 
 
 def _peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s burst, source).  MEASURED_PEAKS.json is driver-written."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
             j = json.load(f)
-        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(j["hbm_gbs"]), float(j["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def _traffic(kernel):
+    """DRAM bytes per launch of `kernel` at the bench shape, from the committed ncu --set full
+    capture (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(kernel)
+    return None
 
 
 class ClockSampler:
@@ -143,7 +154,7 @@ def run_b200(args):
     import runia_core_b200 as R
     from runia_core_b200 import _lib, _ops
 
-    hbm_peak, peak_src = _peaks()
+    hbm_peak, bf16_peak, peak_src = _peaks()
     dev = torch.device("cuda", local)
     md = R.inference.MDLatentSpace()
     md.setup(_fit_larem())
@@ -173,15 +184,26 @@ def run_b200(args):
     ms_per_step = total_ms / args.steps
     value = n_rows * world / (ms_per_step * 1e-3)
     kern_ms = float(np.mean(per))
+    # 1,032 algorithmic bytes and 2 d^2 + 3 d = 131,840 FLOP per embedding at d = 256
+    # (128 FLOP/B).  FP32-faithful on the tensor cores = three TF32 products per FLOP, so the
+    # kernel is tensor-bound: ceiling = TF32 peak / 3, TF32 peak = measured dense bf16 / 2 (no TF32
+    # figure is measured; TF32 runs at half the bf16 rate on this part).
     alg_bytes = n_rows * (D_LATENT * 4 + 8)
-    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    hbm_achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     flops = n_rows * (2.0 * D_LATENT * st.r + 3.0 * D_LATENT)
-    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
-                "kernel": ("tc_kernel<RowNormEpi> (tcgen05 3xTF32 contraction, TMEM row sum of squares)"
-                           if _ops.get_engine() == "tc" else "rownorm_kernel (FP32 SIMT contraction)"),
-                "fp32_equiv_tflops": round(flops / (kern_ms * 1e-3) / 1e12, 2),
-                "tensor_tf32_tflops_issued": round(3 * flops / (kern_ms * 1e-3) / 1e12, 2)}
+    tflops = flops / (kern_ms * 1e-3) / 1e12
+    tc = _ops.get_engine() == "tc"
+    peak_tf = bf16_peak / 2.0 / 3.0
+    roofline = {"bound": "tensor", "achieved": round(tflops, 2), "peak": round(peak_tf, 2), "unit": "TFLOP/s",
+                "frac": round(tflops / peak_tf, 4), "traffic": _traffic("tc_kernel<RowNormEpi>"),
+                "peak_source": peak_src + ": dense bf16 burst / 2 (TF32 rate) / 3 (3xTF32 products per FP32-faithful FLOP)",
+                "kernel": ("tc_kernel<RowNormEpi> (tcgen05 cta_group::2 3xTF32 contraction, TMEM row sum of squares)"
+                           if tc else "rownorm_kernel (FP32 SIMT contraction)"),
+                "algorithmic_flop_per_embedding": 2 * D_LATENT * st.r + 3 * D_LATENT,
+                "algorithmic_bytes_per_embedding": D_LATENT * 4 + 8,
+                "tensor_tf32_tflops_issued": round(3 * tflops, 2),
+                "hbm": {"achieved": round(hbm_achieved, 1), "peak": hbm_peak, "unit": "GB/s",
+                        "frac": round(hbm_achieved / hbm_peak, 4)}}
 
     # ---------------- end to end through the reference-facing class, host buffers ----------------
     n_e2e = min(args.e2e_rows, n_rows)

@@ -201,15 +201,17 @@ struct KnnEpi {
   // buffer entry e of this thread, read through L2 (the entries were written by this thread)
   __device__ __forceinline__ float ld_d(int e) const { return __ldcg(buf_d + base + 32 * (size_t)e); }
   __device__ __forceinline__ int32_t ld_i(int e) const { return __ldcg(buf_i + base + 32 * (size_t)e); }
-  // number of buffered keys below `bound`; 8 independent loads in flight per step
+  // number of buffered keys below `bound`; SCAN independent loads in flight per step (the buffers
+  // live in L2: a scan is latency-bound, so its cost is ~ n / SCAN round trips)
+  static constexpr int SCAN = 32;
   __device__ __forceinline__ int count_below(int n, uint32_t bound) const {
     int c = 0;
-    for (int e0 = 0; e0 < n; e0 += 8) {
-      float v[8];
+    for (int e0 = 0; e0 < n; e0 += SCAN) {
+      float v[SCAN];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (e0 + j < n) ? ld_d(e0 + j) : INFINITY;
+      for (int j = 0; j < SCAN; ++j) v[j] = (e0 + j < n) ? ld_d(e0 + j) : INFINITY;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) c += (e0 + j < n && ord_key(v[j]) < bound) ? 1 : 0;
+      for (int j = 0; j < SCAN; ++j) c += (e0 + j < n && ord_key(v[j]) < bound) ? 1 : 0;
     }
     return c;
   }
@@ -222,12 +224,12 @@ struct KnnEpi {
     int c_hi = n;
     {
       uint32_t kmin = 0xffffffffu, kmax = 0u;
-      for (int e0 = 0; e0 < n; e0 += 8) {
-        float v[8];
+      for (int e0 = 0; e0 < n; e0 += SCAN) {
+        float v[SCAN];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (e0 + j < n) ? ld_d(e0 + j) : 0.f;
+        for (int j = 0; j < SCAN; ++j) v[j] = (e0 + j < n) ? ld_d(e0 + j) : 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < SCAN; ++j)
           if (e0 + j < n) {
             const uint32_t k = ord_key(v[j]);
             kmin = k < kmin ? k : kmin;
@@ -253,16 +255,17 @@ struct KnnEpi {
     if (ties) ties_left = kcap - count_below(n, lo);
     const uint32_t bound = ties ? lo : hi;
     int w = 0;
-    for (int e0 = 0; e0 < n; e0 += 8) {
-      float v[8];
-      int32_t ix[8];
+    constexpr int CB = 16;  // compaction batch (value + index registers)
+    for (int e0 = 0; e0 < n; e0 += CB) {
+      float v[CB];
+      int32_t ix[CB];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < CB; ++j) {
         v[j] = (e0 + j < n) ? ld_d(e0 + j) : INFINITY;
         ix[j] = (e0 + j < n) ? ld_i(e0 + j) : -1;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < CB; ++j) {
         if (e0 + j >= n) continue;
         const uint32_t k = ord_key(v[j]);
         bool keep = k < bound;
