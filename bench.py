@@ -195,7 +195,7 @@ def run_b200(args):
     tc = _ops.get_engine() == "tc"
     peak_tf = bf16_peak / 2.0 / 3.0
     roofline = {"bound": "tensor", "achieved": round(tflops, 2), "peak": round(peak_tf, 2), "unit": "TFLOP/s",
-                "frac": round(tflops / peak_tf, 4), "traffic": _traffic("tc_kernel<RowNormEpi>"),
+                "frac": round(tflops / peak_tf, 4), "traffic": _traffic("tc_kernel<tc::RowNormEpi>") if n_rows == 4 * 1024 * 1024 else None,
                 "peak_source": peak_src + ": dense bf16 burst / 2 (TF32 rate) / 3 (3xTF32 products per FP32-faithful FLOP)",
                 "kernel": ("tc_kernel<RowNormEpi> (tcgen05 cta_group::2 3xTF32 contraction, TMEM row sum of squares)"
                            if tc else "rownorm_kernel (FP32 SIMT contraction)"),

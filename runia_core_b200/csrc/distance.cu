@@ -108,8 +108,9 @@ __device__ __forceinline__ void warp_bitonic_sort(KT *key, IT *idx, int n /* pow
 constexpr int KNN_SORT_MAX = 512;  // largest per-row candidate buffer (entries)
 
 struct KnnPlan {
-  int kcap;    // candidates kept per (row, split): power of two >= k + 8
-  int capp;    // buffer entries per (row, split): power of two, >= kcap + BN
+  int kcap;    // candidates that survive the merge: power of two >= k + 8
+  int klist;   // entries the candidate pass leaves per (row, split): kcap (SIMT) or 2 * kcap (tensor)
+  int capp;    // buffer entries per (row, split): power of two, >= klist + panel width
   int splits;  // bank splits (grid.y)
   int64_t panels_per_split;
   int interleaved;  // 1: candidate buffers are [32-row group][split][entry][lane] (tensor-core pass)
@@ -237,9 +238,10 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerank
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * RERANK_WARPS + warp;
   if (row >= a.Nq) return;
-  const int kcap = a.plan.kcap, S = a.plan.splits, capp = a.plan.capp;
+  const int kcap = a.plan.kcap, klist = a.plan.klist, S = a.plan.splits, capp = a.plan.capp;
   int msz = 1;
-  while (msz < S * kcap) msz <<= 1;
+  while (msz < S * klist) msz <<= 1;
+  if (msz < kcap) msz = kcap;
   // per-warp scratch: approx keys/idx [msz], exact keys [kcap] + idx [kcap]
   const size_t per_warp = (size_t)msz * 8 + (size_t)kcap * 12;
   unsigned char *base = dyn + (size_t)warp * ((per_warp + 15) / 16 * 16);
@@ -248,12 +250,12 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerank
   double *ekey = reinterpret_cast<double *>(base + (size_t)msz * 8);
   int32_t *eidx = reinterpret_cast<int32_t *>(base + (size_t)msz * 8 + (size_t)kcap * 8);
 
-  const int n_all = S * kcap;
+  const int n_all = S * klist;
   for (int e = lane; e < msz; e += 32) {
     float kd = INFINITY;
     int32_t ki = 0x7fffffff;
     if (e < n_all) {
-      const int s = e / kcap, c = e % kcap;
+      const int s = e / klist, c = e % klist;
       const size_t p = a.plan.interleaved
                            ? (((size_t)(row >> 5)) * S + s) * ((size_t)capp * 32) + (size_t)c * 32 + (size_t)(row & 31)
                            : ((size_t)row * S + s) * capp + c;
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerank
     aidx[e] = ki;
   }
   __syncwarp();
-  if (S > 1) {
+  if (n_all > kcap) {
     // keep the kcap smallest (approximate distance, index) pairs of the S per-split lists: warp
     // bisection on the order-preserving key, then a stable compaction to the front
     auto okey = [](float v) -> uint32_t {
@@ -591,16 +593,18 @@ static KnnPlan make_knn_plan(int64_t Nq, int64_t Nb, int k, bool tensor) {
   p.kcap = 64;
   while (p.kcap < k + 8) p.kcap <<= 1;
   const int pw = tensor ? 256 : BN;
+  p.klist = tensor ? 2 * p.kcap : p.kcap;
   p.capp = 256;
-  while (p.capp < p.kcap + pw) p.capp <<= 1;
+  while (p.capp < p.klist + pw) p.capp <<= 1;
   p.interleaved = tensor ? 1 : 0;
-  pick_splits(ceil_div(Nq, tensor ? 256 : BM), ceil_div(Nb, pw), 16, tensor ? kNumSMs / 2 : 2 * kNumSMs, p.splits,
-              p.panels_per_split);
+  const int max_splits = std::min(16, 4096 / p.klist);  // bounds the merge scratch of the re-rank kernel
+  pick_splits(ceil_div(Nq, tensor ? 256 : BM), ceil_div(Nb, pw), max_splits, tensor ? kNumSMs / 2 : 2 * kNumSMs,
+              p.splits, p.panels_per_split);
   return p;
 }
 
 struct KnnWorkspace {
-  size_t qn, thr_seed, seed_d, seed_i, buf_d, buf_i, flag_count, flag_rows, flag_T, flag_I, fb_d, fb_i, total;
+  size_t qn, thr_key, buf_d, buf_i, flag_count, flag_rows, flag_T, flag_I, fb_d, fb_i, total;
 };
 constexpr int FB_GRID = 64;
 static KnnWorkspace knn_layout(int64_t Nq, const KnnPlan &p) {
@@ -612,10 +616,8 @@ static KnnWorkspace knn_layout(int64_t Nq, const KnnPlan &p) {
     return at;
   };
   w.qn = take((size_t)Nq * 4);
-  w.thr_seed = take((size_t)Nq * 4);
+  w.thr_key = take((size_t)Nq * 4);
   const size_t rows32 = (size_t)ceil_div(Nq, 32) * 32;
-  w.seed_d = take(rows32 * p.capp * 4);
-  w.seed_i = take(rows32 * p.capp * 4);
   w.buf_d = take(rows32 * p.splits * p.capp * 4);
   w.buf_i = take(rows32 * p.splits * p.capp * 4);
   w.flag_count = take(256);
@@ -631,9 +633,9 @@ static KnnWorkspace knn_layout(int64_t Nq, const KnnPlan &p) {
 namespace tc {
 bool usable(const void *A, int K, const void *B_hi, const void *B_lo);
 int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
-                             const float *bn, int64_t Nb, int d, int kcap, int capp, int splits,
-                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, float *thr_seed,
-                             float *seed_d, int32_t *seed_i, cudaStream_t st);
+                             const float *bn, int64_t Nb, int d, int kcap, int klist, int capp, int splits,
+                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, uint32_t *thr_key,
+                             cudaStream_t st);
 int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                           const float *bn, int64_t Nb, int d, float scale, int splits, int64_t panels_per_split,
                           float *part_m, float *part_s, cudaStream_t st);
@@ -716,10 +718,9 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   row_sqnorm_kernel<<<(unsigned)ceil_div(Nq, 8), 256, 0, st>>>(Qn, Nq, d, qn);
 
   if (tensor) {
-    const int rc = tc::launch_knn_candidates_tc(Qn, qn, Nq, Bn_hi, Bn_lo, Bn_sqnorm, Nb, d, plan.kcap, plan.capp,
-                                                plan.splits, plan.panels_per_split, buf_d, buf_i,
-                                                (float *)(ws + w.thr_seed), (float *)(ws + w.seed_d),
-                                                (int32_t *)(ws + w.seed_i), st);
+    const int rc = tc::launch_knn_candidates_tc(Qn, qn, Nq, Bn_hi, Bn_lo, Bn_sqnorm, Nb, d, plan.kcap, plan.klist,
+                                                plan.capp, plan.splits, plan.panels_per_split, buf_d, buf_i,
+                                                (uint32_t *)(ws + w.thr_key), st);
     if (rc) return rc;
   } else {
     const size_t dyn1 = (size_t)8 * plan.capp * 8;
@@ -745,7 +746,8 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   a.flag_T = (double *)(ws + w.flag_T);
   a.flag_I = (int32_t *)(ws + w.flag_I);
   int msz = 1;
-  while (msz < plan.splits * plan.kcap) msz <<= 1;
+  while (msz < plan.splits * plan.klist) msz <<= 1;
+  if (msz < plan.kcap) msz = plan.kcap;
   const size_t per_warp = (((size_t)msz * 8 + (size_t)plan.kcap * 12) + 15) / 16 * 16;
   const size_t dyn2 = per_warp * RERANK_WARPS;
   static bool attr2 = false;

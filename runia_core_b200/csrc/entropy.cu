@@ -214,6 +214,29 @@ constexpr size_t kEntropy16Smem = (size_t)E16_PAIRS * E16_PAIR_FLOATS * sizeof(f
 // maxima a warp carries brings the kernel from 255 to <= 168 registers, i.e. from 8 to 12 resident
 // warps per SM: the first version issued 0.55 instructions per cycle per scheduler with the ALU pipe
 // 61 % busy (ncu, profiles/), limited by dependent-issue latency with only two warps per scheduler.
+struct constexpr_pair {
+  int a, b;
+};
+// p-th pair (a < b) of 16 samples in row-major upper-triangle order
+__host__ __device__ constexpr constexpr_pair pair_of(int p) {
+  int a = 0;
+  while (p >= 15 - a) {
+    p -= 15 - a;
+    ++a;
+  }
+  return constexpr_pair{a, a + 1 + p};
+}
+
+// named barrier of one warp pair; literal ids so that ptxas reserves 4 barriers per CTA, not all 16
+__device__ __forceinline__ void pair_barrier(int id) {
+  if (id == 1)
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+  else if (id == 2)
+    asm volatile("bar.sync 2, 64;" ::: "memory");
+  else
+    asm volatile("bar.sync 3, 64;" ::: "memory");
+}
+
 template <int H>
 __device__ __forceinline__ void entropy16_pair_body(const float *__restrict__ z, int64_t n_items, int D, float min_dist,
                                                     double c_term, double *__restrict__ h_z,
@@ -263,7 +286,7 @@ __device__ __forceinline__ void entropy16_pair_body(const float *__restrict__ z,
 #pragma unroll 1
     for (int jstep = 0; jstep < spi; ++jstep) {
       asm volatile("cp.async.wait_group 1;" ::: "memory");
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");  // both warps' halves of this step have landed
+      pair_barrier(bar_id);  // both warps' halves of this step have landed
       float2 x[N];
       {
         const float2 *b2 = reinterpret_cast<const float2 *>(ring + buf * E16_STEP_FLOATS) + lane;
@@ -315,23 +338,23 @@ __device__ __forceinline__ void entropy16_pair_body(const float *__restrict__ z,
     }
     // ---- item complete: joint (Chebyshev) estimator from the 120 pair maxima ----
     if (h_mvn != nullptr) {
-      int p = 0;
+      // all indices below are compile-time constants after unrolling (pm must stay in registers)
+      float red[NMINE];
 #pragma unroll
-      for (int a = 0; a < N; ++a) {
-        if (H == 0 && lane == 0) dm[a * N + a] = 0.f;
+      for (int q = 0; q < NMINE; ++q) red[q] = warp_max_f32(pm[q]);
+      if (lane == 0) {
 #pragma unroll
-        for (int b = a + 1; b < N; ++b) {
-          if ((p & 1) == H) {
-            const float m = warp_max_f32(pm[p >> 1]);
-            if (lane == 0) {
-              dm[a * N + b] = m;
-              dm[b * N + a] = m;
-            }
-          }
-          ++p;
+        for (int q = 0; q < NMINE; ++q) {
+          constexpr_pair ab = pair_of(2 * q + H);
+          dm[ab.a * N + ab.b] = red[q];
+          dm[ab.b * N + ab.a] = red[q];
+        }
+        if (H == 0) {
+#pragma unroll
+          for (int a = 0; a < N; ++a) dm[a * N + a] = 0.f;
         }
       }
-      asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+      pair_barrier(bar_id);
       if (H == 0) {
         float lg = 0.f;
         if (lane < N) {

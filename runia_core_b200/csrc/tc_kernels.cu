@@ -167,9 +167,8 @@ struct KnnEpi {
   int64_t Nq, b_hi;
   float *buf_d;
   int32_t *buf_i;
-  int kcap, capp, splits, split;
-  const float *thr_in;  // [Nq] initial threshold per row (from the seed split) or nullptr
-  float *thr_out;       // [Nq] final threshold of this split (seed split only) or nullptr
+  int kcap, klist, capp, splits, split;
+  const uint32_t *thr_key;  // [Nq] seed: order-preserving key of an upper bound on the kcap-th distance (0 = none)
   int64_t row;
   size_t base;
   float q2, thr;
@@ -179,7 +178,11 @@ struct KnnEpi {
     row = row_;
     live = row < Nq;
     q2 = live ? __ldg(qn + row) : 0.f;
-    thr = (live && thr_in) ? __ldg(thr_in + row) : INFINITY;
+    thr = INFINITY;
+    if (live && thr_key) {
+      const uint32_t key = __ldg(thr_key + row);
+      if (key != 0u && key < ord_key(INFINITY)) thr = ord_val(key);
+    }
     cnt = 0;
     // block of the 32-row group this row belongs to, + lane; entry e lives at base + 32 * e
     base = (((size_t)(row >> 5)) * splits + split) * ((size_t)capp * 32) + (size_t)(row & 31);
@@ -288,21 +291,83 @@ struct KnnEpi {
     // warp-uniform trigger: when any row of the warp is about to overflow, every row that holds more
     // than the target shrinks in the same (coalesced, lock-step) passes
     if (__any_sync(0xffffffffu, live && cnt > capp - TN)) {
-      if (live) shrink(2 * kcap);
+      if (live) shrink(klist);
     }
   }
   __device__ void finish() {
     if (!live) return;
-    shrink(kcap);
-    // after shrink(kcap) on a full buffer, thr bounds the kcap-th smallest distance of this split:
-    // the other splits start from it, so they only ever buffer rows that can still matter
-    if (thr_out) thr_out[row] = (cnt >= kcap) ? thr : INFINITY;
-    for (int e = cnt; e < kcap; ++e) {  // pad: the re-rank kernel reads kcap entries per (row, split)
+    shrink(klist);                       // no-op for most rows: the seed threshold keeps the lists short
+    for (int e = cnt; e < klist; ++e) {  // pad: the re-rank kernel reads klist entries per (row, split)
       buf_d[base + 32 * (size_t)e] = INFINITY;
       buf_i[base + 32 * (size_t)e] = -1;
     }
   }
 };
+
+// Seed: an upper bound on every query's kcap-th smallest distance, with no buffers at all.  The seed
+// columns are cut into kcap / 4 groups of one panel (256 bank rows); per group the thread keeps the 4
+// smallest distances it has seen in registers.  B = max over groups of the 4th smallest has at least
+// kcap bank rows at distance <= B, so the main pass starts with the threshold nextafter(B) and only
+// ever buffers rows that can still matter.  Groups are independent: they are split over several CTA
+// pairs and combined with an atomic max on the order-preserving key.
+struct KnnSeedEpi {
+  const float *qn, *bn;
+  int64_t Nq, b_hi;
+  uint32_t *thr_key;
+  int64_t row;
+  float q2, m0, m1, m2, m3, bound;
+  bool live;
+  __device__ void begin(int, int64_t row_) {
+    row = row_;
+    live = row < Nq;
+    q2 = live ? __ldg(qn + row) : 0.f;
+    m0 = m1 = m2 = m3 = INFINITY;
+    bound = -INFINITY;
+  }
+  __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int64_t col = col0 + j;
+      const float b2 = col < b_hi ? __ldg(bn + col) : INFINITY;
+      float t = fmaf(-2.f, v[j], q2 + b2);
+      if (t < m3) {  // rare after the first few columns of a group
+        float a = fminf(m0, t);
+        t = fmaxf(m0, t);
+        m0 = a;
+        a = fminf(m1, t);
+        t = fmaxf(m1, t);
+        m1 = a;
+        a = fminf(m2, t);
+        t = fmaxf(m2, t);
+        m2 = a;
+        m3 = fminf(m3, t);
+      }
+    }
+  }
+  __device__ void panel_done(int) {
+    bound = fmaxf(bound, m3);
+    m0 = m1 = m2 = m3 = INFINITY;
+  }
+  __device__ void finish() {
+    if (!live) return;
+    const uint32_t key = ord_key(bound);
+    atomicMax(thr_key + row, key < 0xfffffffeu ? key + 1u : key);  // exclusive bound: the filter is strict
+  }
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+tc_knn_seed_kernel(const __grid_constant__ CUtensorMap tmA, int K, const __grid_constant__ CUtensorMap tmB_hi,
+                   const __grid_constant__ CUtensorMap tmB_lo, int seed_panels, int panels_per_split, KnnSeedEpi epi) {
+  extern __shared__ unsigned char smem_raw[];
+  Work w;
+  w.tile_first = blockIdx.x >> 1;
+  w.tile_end = (int64_t)(blockIdx.x >> 1) + 1;
+  w.tile_step = 1;
+  w.panel_lo = (int)blockIdx.y * panels_per_split;
+  w.panel_hi = min(seed_panels, w.panel_lo + panels_per_split);
+  const Prologue pro{nullptr, INFINITY};
+  run_tiles(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
+}
 
 template <class E>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -505,9 +570,9 @@ namespace runia {
 namespace tc {
 // shared with distance.cu
 int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
-                             const float *bn, int64_t Nb, int d, int kcap, int capp, int splits,
-                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, float *thr_seed,
-                             float *seed_d, int32_t *seed_i, cudaStream_t st) {
+                             const float *bn, int64_t Nb, int d, int kcap, int klist, int capp, int splits,
+                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, uint32_t *thr_key,
+                             cudaStream_t st) {
   CUtensorMap ma, mh, ml;
   int rc = make_a_map(&ma, Q, Nq, d);
   if (rc) return rc;
@@ -520,34 +585,34 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
   if (!attr) {
     rc = set_smem(tc_knn_kernel, kSmemMax);
     if (rc) return rc;
+    rc = set_smem(tc_knn_seed_kernel, kSmemMax);
+    if (rc) return rc;
     attr = true;
+  }
+  const int64_t tiles = ceil_div(Nq, TM2);
+  const int panels = (int)ceil_div(Nb, TN);
+  // seed over kcap / 4 full panels when the bank is at least twice that large
+  const int seed_panels = kcap / 4;
+  const bool seeded = (Nb / TN) >= 2 * (int64_t)seed_panels;
+  if (seeded) {
+    RUNIA_CUDA(cudaMemsetAsync(thr_key, 0, (size_t)Nq * sizeof(uint32_t), st));
+    int ss = (int)std::min<int64_t>(seed_panels, std::max<int64_t>(1, ceil_div(kNumSMs, tiles)));
+    const int pps = (int)ceil_div(seed_panels, ss);
+    ss = (int)ceil_div(seed_panels, pps);
+    KnnSeedEpi seed{};
+    seed.qn = qn; seed.bn = bn; seed.Nq = Nq; seed.b_hi = Nb; seed.thr_key = thr_key;
+    dim3 grid0(2 * (unsigned)tiles, (unsigned)ss);
+    tc_knn_seed_kernel<<<grid0, THREADS, smem, st>>>(ma, d, mh, ml, seed_panels, pps, seed);
+    count_launch();
   }
   KnnEpi epi{};
   epi.qn = qn; epi.bn = bn; epi.Nq = Nq; epi.b_hi = Nb;
   epi.buf_d = buf_d; epi.buf_i = buf_i;
-  epi.kcap = kcap; epi.capp = capp; epi.splits = splits; epi.split = 0;
-  const int panels = (int)ceil_div(Nb, TN);
-  constexpr int kSeedPanels = 4;
-  if (panels <= 2 * kSeedPanels) {
-    epi.thr_in = nullptr; epi.thr_out = nullptr;
-    dim3 grid(2 * (unsigned)ceil_div(Nq, TM2), (unsigned)splits);
-    tc_knn_kernel<<<grid, THREADS, smem, st>>>(ma, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
-    count_launch();
-  } else {
-    // Seed pass over the first few panels of the bank: its per-row kcap-th smallest distance is a
-    // valid upper bound on the global kcap-th smallest, so it becomes the initial threshold of the
-    // main pass and no split ever floods its buffer.  The seed writes to scratch buffers only;
-    // the main pass sees those bank rows again.
-    KnnEpi seed = epi;
-    seed.buf_d = seed_d; seed.buf_i = seed_i; seed.splits = 1;
-    seed.thr_in = nullptr; seed.thr_out = thr_seed;
-    dim3 grid0(2 * (unsigned)ceil_div(Nq, TM2), 1);
-    tc_knn_kernel<<<grid0, THREADS, smem, st>>>(ma, Nq, d, mh, ml, kSeedPanels, kSeedPanels, Nb, 0, seed);
-    epi.thr_in = thr_seed; epi.thr_out = nullptr;
-    dim3 grid1(2 * (unsigned)ceil_div(Nq, TM2), (unsigned)splits);
-    tc_knn_kernel<<<grid1, THREADS, smem, st>>>(ma, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
-    count_launch(2);
-  }
+  epi.kcap = kcap; epi.klist = klist; epi.capp = capp; epi.splits = splits; epi.split = 0;
+  epi.thr_key = seeded ? thr_key : nullptr;
+  dim3 grid(2 * (unsigned)tiles, (unsigned)splits);
+  tc_knn_kernel<<<grid, THREADS, smem, st>>>(ma, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
+  count_launch();
   return finish_launch("knn_candidates_tc");
 }
 
