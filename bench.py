@@ -231,6 +231,8 @@ def run_b200(args):
     extra = {}
     if rank == 0 and not args.no_extra:
         extra.update(_extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak))
+        if world == 1 and not args.no_sweep:
+            extra["sweep_config2"] = _extra_sweep_config2(R)
     if world > 1 and not args.no_extra:
         extra.update(_extra_sharded_knn(args, torch, dist, _ops, world, rank, barrier, max_over_ranks))
 
@@ -338,6 +340,63 @@ def _extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak):
                           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak,
                                        "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak},
                           "fp32_tflops": 2.0 * 2_000_000 * 512 * 256 / (ms * 1e-3) / 1e12}
+    return out
+
+
+def _extra_sweep_config2(R):
+    """BASELINE configs[1]: the full baseline sweep on ResNet-18 / CIFAR-10 shapes (50k x 512 train
+    bank, 10 classes, 10k test rows), through the reference-facing classes with NumPy in / NumPy
+    out (H2D + kernels + D2H inside the timed call).  setup() (host-side fits, as in the
+    reference) is timed separately."""
+    rng = np.random.RandomState(11)
+    C, d, ntr, nte = 10, 512, 50_000, 10_000
+    means = rng.randn(C, d).astype(np.float32)
+    ytr = rng.randint(0, C, ntr)
+    train = (means[ytr] + rng.randn(ntr, d)).astype(np.float32)
+    yv = rng.randint(0, C, nte)
+    valid = (means[yv] + rng.randn(nte, d)).astype(np.float32)
+    test = np.concatenate([valid[: nte // 2], (1.5 * rng.randn(nte - nte // 2, d)).astype(np.float32)])
+    W = (0.05 * rng.randn(C, d)).astype(np.float32)
+    b = rng.randn(C).astype(np.float32)
+    lg = lambda x: (x @ W.T + b).astype(np.float32)  # noqa: E731
+    tr_l, va_l, te_l = lg(train), lg(valid), lg(test)
+    fc = {"weight": W, "bias": b}
+    I = R.inference
+    mk = {
+        "msp": lambda: I.MSP(flip_sign=False),
+        "energy": lambda: I.Energy(flip_sign=False),
+        "mahalanobis": lambda: I.Mahalanobis(flip_sign=False, num_classes=C),
+        "knn": lambda: I.KNN(flip_sign=False, k_neighbors=50),
+        "vim": lambda: I.ViM(flip_sign=False),
+        "ddu": lambda: I.DDU(flip_sign=False, num_classes=C),
+        "react": lambda: I.ReAct(flip_sign=False, react_percentile=90),
+        "dice": lambda: I.DICE(flip_sign=False, dice_percentile=90, num_classes=C),
+    }
+    out = {}
+    import torch
+
+    for name, ctor in mk.items():
+        p = ctor()
+        t0 = time.perf_counter()
+        if name in ("msp", "energy"):
+            p.setup(tr_l)
+            call = lambda: p.postprocess(te_l)  # noqa: E731
+        else:
+            p.setup(train, valid_feats=valid, train_labels=ytr, train_logits=tr_l, valid_logits=va_l,
+                    final_linear_layer_params=fc)
+            call = lambda: p.postprocess(test, logits=te_l)  # noqa: E731
+        torch.cuda.synchronize()
+        t_setup = time.perf_counter() - t0
+        call()
+        torch.cuda.synchronize()
+        reps = 5
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sc = call()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        out[name] = {"embeddings_per_s": nte / dt, "ms": dt * 1e3, "setup_s": round(t_setup, 3),
+                     "finite": bool(np.isfinite(sc).all())}
     return out
 
 
@@ -451,6 +510,7 @@ def main():
     ap.add_argument("--knn-shard-rows", type=int, default=1_250_000)
     ap.add_argument("--cpu-seconds", type=float, default=8.0)
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the configs[1] baseline sweep (host-side fits take ~20 s)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -105,15 +105,14 @@ __device__ __forceinline__ void warp_bitonic_sort(KT *key, IT *idx, int n /* pow
 // --------------------------------------------------------------------------------------------
 // kNN stage 1: fused distance GEMM + streaming top-KCAP candidate filter
 // --------------------------------------------------------------------------------------------
-constexpr int KNN_SORT_MAX = 512;  // largest per-row candidate buffer (entries)
 
 struct KnnPlan {
-  int kcap;    // candidates that survive the merge: power of two >= k + 8
-  int klist;   // entries the candidate pass leaves per (row, split): kcap (SIMT) or 2 * kcap (tensor)
-  int capp;    // buffer entries per (row, split): power of two, >= klist + panel width
+  int kcap;     // candidates that survive the merge: power of two >= k + 8
+  int fin_max;  // most entries the candidate pass may leave per (row, split); SIMT pass: exactly kcap (padded)
+  int capp;     // buffer entries per (row, split): power of two, >= max(fin_max, 2 kcap + panel width)
   int splits;  // bank splits (grid.y)
   int64_t panels_per_split;
-  int interleaved;  // 1: candidate buffers are [32-row group][split][entry][lane] (tensor-core pass)
+  int counted;  // 1: the pass wrote the list lengths to `counts` (tensor-core pass); 0: lists are padded to kcap
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
@@ -219,6 +218,7 @@ struct KnnRerankArgs {
   KnnPlan plan;
   const float *buf_d;
   const int32_t *buf_i;
+  const int32_t *counts;  // [Nq, splits] list lengths (plan.counted) or nullptr
   float eps;
   int64_t idx_offset;
   float *out_dist;
@@ -231,118 +231,76 @@ struct KnnRerankArgs {
   int32_t *flag_I;       // [Nq] its index
 };
 
-constexpr int RERANK_WARPS = 4;
+constexpr int RERANK_WARPS = 8;
 
 __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerankArgs a) {
   extern __shared__ unsigned char dyn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * RERANK_WARPS + warp;
   if (row >= a.Nq) return;
-  const int kcap = a.plan.kcap, klist = a.plan.klist, S = a.plan.splits, capp = a.plan.capp;
-  int msz = 1;
-  while (msz < S * klist) msz <<= 1;
-  if (msz < kcap) msz = kcap;
-  // per-warp scratch: approx keys/idx [msz], exact keys [kcap] + idx [kcap]
-  const size_t per_warp = (size_t)msz * 8 + (size_t)kcap * 12;
+  const int kcap = a.plan.kcap, S = a.plan.splits, capp = a.plan.capp;
+  const int nbuf_max = 2 * kcap;
+  // per-warp scratch: running selection buffer keys/idx [2 kcap], exact keys [kcap] + idx [kcap]
+  const size_t per_warp = (size_t)nbuf_max * 8 + (size_t)kcap * 12;
   unsigned char *base = dyn + (size_t)warp * ((per_warp + 15) / 16 * 16);
   float *akey = reinterpret_cast<float *>(base);
-  int32_t *aidx = reinterpret_cast<int32_t *>(base + (size_t)msz * 4);
-  double *ekey = reinterpret_cast<double *>(base + (size_t)msz * 8);
-  int32_t *eidx = reinterpret_cast<int32_t *>(base + (size_t)msz * 8 + (size_t)kcap * 8);
+  int32_t *aidx = reinterpret_cast<int32_t *>(base + (size_t)nbuf_max * 4);
+  double *ekey = reinterpret_cast<double *>(base + (size_t)nbuf_max * 8);
+  int32_t *eidx = reinterpret_cast<int32_t *>(base + (size_t)nbuf_max * 8 + (size_t)kcap * 8);
 
-  const int n_all = S * klist;
-  for (int e = lane; e < msz; e += 32) {
-    float kd = INFINITY;
-    int32_t ki = 0x7fffffff;
-    if (e < n_all) {
-      const int s = e / klist, c = e % klist;
-      const size_t p = a.plan.interleaved
-                           ? (((size_t)(row >> 5)) * S + s) * ((size_t)capp * 32) + (size_t)c * 32 + (size_t)(row & 31)
-                           : ((size_t)row * S + s) * capp + c;
-      const int32_t ii = a.buf_i[p];
-      if (ii >= 0) {
-        kd = a.buf_d[p];
-        ki = ii;
-      }
-    }
-    akey[e] = kd;
-    aidx[e] = ki;
+  // Streaming selection of the kcap smallest approximate distances over the row's per-split lists
+  // (row-major [row][split][entry]: coalesced loads).  Entries below the running threshold are
+  // appended to a 2*kcap buffer in shared memory; when it would overflow it is sorted, cut back to
+  // its kcap smallest and the threshold drops to the largest of them.  Entries equal to the
+  // threshold are rejected: they tie with the kcap-th kept value L, which is all the certification
+  // below needs (every rejected entry has approximate distance >= L).
+  for (int e = lane; e < nbuf_max; e += 32) {
+    akey[e] = INFINITY;
+    aidx[e] = 0x7fffffff;
   }
   __syncwarp();
-  if (n_all > kcap) {
-    // keep the kcap smallest (approximate distance, index) pairs of the S per-split lists: warp
-    // bisection on the order-preserving key, then a stable compaction to the front
-    auto okey = [](float v) -> uint32_t {
-      const uint32_t u = __float_as_uint(v);
-      return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-    };
-    int n_fin = 0;
-    for (int e = lane; e < n_all; e += 32) n_fin += (aidx[e] != 0x7fffffff) ? 1 : 0;
-    n_fin = __reduce_add_sync(0xffffffffu, n_fin);
-    if (n_fin > kcap) {
-      uint32_t lo = 0u, hi = 0xffffffffu;  // count(key < lo) < kcap <= count(key < hi)
-      int c_hi = n_fin;
-      while (c_hi > kcap && hi - lo > 1u) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        int c = 0;
-        for (int e = lane; e < n_all; e += 32) c += (aidx[e] != 0x7fffffff && okey(akey[e]) < mid) ? 1 : 0;
-        c = __reduce_add_sync(0xffffffffu, c);
-        if (c >= kcap) {
-          hi = mid;
-          c_hi = c;
-        } else {
-          lo = mid;
-        }
-      }
-      const bool ties = c_hi > kcap;
-      const uint32_t bound = ties ? lo : hi;
-      int c_lt = 0;
-      if (ties) {
-        for (int e = lane; e < n_all; e += 32) c_lt += (aidx[e] != 0x7fffffff && okey(akey[e]) < lo) ? 1 : 0;
-        c_lt = __reduce_add_sync(0xffffffffu, c_lt);
-      }
-      int ties_left = ties ? kcap - c_lt : 0;
-      // stable in-place compaction, 32 entries at a time: positions come from a ballot scan
-      int w = 0;
-      for (int e0 = 0; e0 < n_all; e0 += 32) {
-        const int e = e0 + lane;
-        float kd = INFINITY;
-        int32_t ki = 0x7fffffff;
-        bool keep = false, tie = false;
-        if (e < n_all) {
-          kd = akey[e];
-          ki = aidx[e];
-          const uint32_t k = okey(kd);
-          keep = ki != 0x7fffffff && k < bound;
-          tie = ties && ki != 0x7fffffff && k == lo;
-        }
-        const unsigned tmask = __ballot_sync(0xffffffffu, tie);
-        if (tie && __popc(tmask & ((1u << lane) - 1u)) < ties_left) keep = true;
-        ties_left -= __popc(tmask);
-        if (ties_left < 0) ties_left = 0;
-        const unsigned kmask = __ballot_sync(0xffffffffu, keep);
-        __syncwarp();
-        // survivors of this 32-chunk go to [w, w + popc): w <= e0 always, and the whole chunk is
-        // already in registers, so writing in place is safe
-        if (keep) {
-          const int pos = w + __popc(kmask & ((1u << lane) - 1u));
-          akey[pos] = kd;
-          aidx[pos] = ki;
-        }
-        w += __popc(kmask);
-        __syncwarp();
-      }
-      for (int e = w + lane; e < kcap; e += 32) {
+  int n_buf = 0;
+  float thr = INFINITY;
+  auto cut = [&]() {  // sort the buffer, keep its kcap smallest
+    warp_bitonic_sort(akey, aidx, nbuf_max);
+    if (n_buf >= kcap) {
+      n_buf = kcap;
+      thr = akey[kcap - 1];
+      for (int e = kcap + lane; e < nbuf_max; e += 32) {
         akey[e] = INFINITY;
         aidx[e] = 0x7fffffff;
       }
+    }
+    __syncwarp();
+  };
+  for (int s = 0; s < S; ++s) {
+    const size_t p0 = ((size_t)row * S + s) * capp;
+    const int n_s = a.counts ? a.counts[(size_t)row * S + s] : kcap;
+    for (int c0 = 0; c0 < n_s; c0 += 32) {
+      const int c = c0 + lane;
+      float kd = INFINITY;
+      int32_t ki = -1;
+      if (c < n_s) {
+        ki = a.buf_i[p0 + c];  // the SIMT pass pads its lists with index -1
+        kd = a.buf_d[p0 + c];
+      }
+      bool take = ki >= 0 && kd < thr;
+      unsigned m = __ballot_sync(0xffffffffu, take);
+      if (n_buf + __popc(m) > nbuf_max) {
+        cut();
+        take = ki >= 0 && kd < thr;
+        m = __ballot_sync(0xffffffffu, take);
+      }
+      if (take) {
+        const int pos = n_buf + __popc(m & ((1u << lane) - 1u));
+        akey[pos] = kd;
+        aidx[pos] = ki;
+      }
+      n_buf += __popc(m);
       __syncwarp();
     }
-    // order the survivors (the bound L below needs the largest approximate distance)
-    warp_bitonic_sort(akey, aidx, kcap);
-  } else {
-    warp_bitonic_sort(akey, aidx, kcap);
   }
+  cut();  // survivors sorted ascending in [0, min(n_buf, kcap))
   int n_real = 0;
   for (int e = lane; e < kcap; e += 32) n_real += (aidx[e] != 0x7fffffff) ? 1 : 0;
 #pragma unroll
@@ -351,14 +309,34 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerank
   const bool list_full = (n_real == kcap);
   const float L = list_full ? akey[kcap - 1] : INFINITY;
 
+  // exact float64 distances of the survivors, four candidates at a time (independent loads in
+  // flight); per candidate the summation order is that of exact_sqdist_warp / the oracle
   const float *q = a.Q + row * (int64_t)a.d;
-  for (int c = 0; c < kcap; ++c) {
-    const int32_t bi = aidx[c];
-    double ex = INFINITY;
-    if (bi != 0x7fffffff) ex = exact_sqdist_warp(q, a.B + (int64_t)bi * a.d, a.d, lane);
-    if (lane == 0) {
-      ekey[c] = ex;
-      eidx[c] = bi;
+  for (int c0 = 0; c0 < kcap; c0 += 4) {
+    const float *bp[4];
+    int32_t bi[4];
+    double acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      bi[u] = aidx[c0 + u];
+      bp[u] = a.B + (int64_t)(bi[u] != 0x7fffffff ? bi[u] : 0) * a.d;
+      acc[u] = 0.0;
+    }
+    for (int j = lane; j < a.d; j += 32) {
+      const double qa = (double)q[j];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double df = __dsub_rn(qa, (double)bp[u][j]);
+        acc[u] = __dadd_rn(acc[u], __dmul_rn(df, df));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double ex = warp_tree_sum_f64(acc[u]);
+      if (lane == 0) {
+        ekey[c0 + u] = bi[u] != 0x7fffffff ? ex : (double)INFINITY;
+        eidx[c0 + u] = bi[u];
+      }
     }
   }
   __syncwarp();
@@ -593,18 +571,18 @@ static KnnPlan make_knn_plan(int64_t Nq, int64_t Nb, int k, bool tensor) {
   p.kcap = 64;
   while (p.kcap < k + 8) p.kcap <<= 1;
   const int pw = tensor ? 256 : BN;
-  p.klist = tensor ? 2 * p.kcap : p.kcap;
   p.capp = 256;
-  while (p.capp < p.klist + pw) p.capp <<= 1;
-  p.interleaved = tensor ? 1 : 0;
-  const int max_splits = std::min(16, 4096 / p.klist);  // bounds the merge scratch of the re-rank kernel
-  pick_splits(ceil_div(Nq, tensor ? 256 : BM), ceil_div(Nb, pw), max_splits, tensor ? kNumSMs / 2 : 2 * kNumSMs,
-              p.splits, p.panels_per_split);
+  while (p.capp < (tensor ? 2 * p.kcap : p.kcap) + pw) p.capp <<= 1;
+  if (tensor && p.capp < 512) p.capp = 512;
+  p.counted = tensor ? 1 : 0;
+  pick_splits(ceil_div(Nq, tensor ? 256 : BM), ceil_div(Nb, pw), 16, tensor ? kNumSMs / 2 : 2 * kNumSMs, p.splits,
+              p.panels_per_split);
+  p.fin_max = tensor ? p.capp : p.kcap;
   return p;
 }
 
 struct KnnWorkspace {
-  size_t qn, thr_key, buf_d, buf_i, flag_count, flag_rows, flag_T, flag_I, fb_d, fb_i, total;
+  size_t qn, thr_key, counts, buf_d, buf_i, flag_count, flag_rows, flag_T, flag_I, fb_d, fb_i, total;
 };
 constexpr int FB_GRID = 64;
 static KnnWorkspace knn_layout(int64_t Nq, const KnnPlan &p) {
@@ -617,6 +595,7 @@ static KnnWorkspace knn_layout(int64_t Nq, const KnnPlan &p) {
   };
   w.qn = take((size_t)Nq * 4);
   w.thr_key = take((size_t)Nq * 4);
+  w.counts = take((size_t)Nq * p.splits * 4);
   const size_t rows32 = (size_t)ceil_div(Nq, 32) * 32;
   w.buf_d = take(rows32 * p.splits * p.capp * 4);
   w.buf_i = take(rows32 * p.splits * p.capp * 4);
@@ -633,9 +612,9 @@ static KnnWorkspace knn_layout(int64_t Nq, const KnnPlan &p) {
 namespace tc {
 bool usable(const void *A, int K, const void *B_hi, const void *B_lo);
 int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
-                             const float *bn, int64_t Nb, int d, int kcap, int klist, int capp, int splits,
-                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, uint32_t *thr_key,
-                             cudaStream_t st);
+                             const float *bn, int64_t Nb, int d, int kcap, int fin_max, int capp, int splits,
+                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, int32_t *counts,
+                             uint32_t *thr_key, cudaStream_t st);
 int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                           const float *bn, int64_t Nb, int d, float scale, int splits, int64_t panels_per_split,
                           float *part_m, float *part_s, cudaStream_t st);
@@ -718,9 +697,9 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   row_sqnorm_kernel<<<(unsigned)ceil_div(Nq, 8), 256, 0, st>>>(Qn, Nq, d, qn);
 
   if (tensor) {
-    const int rc = tc::launch_knn_candidates_tc(Qn, qn, Nq, Bn_hi, Bn_lo, Bn_sqnorm, Nb, d, plan.kcap, plan.klist,
+    const int rc = tc::launch_knn_candidates_tc(Qn, qn, Nq, Bn_hi, Bn_lo, Bn_sqnorm, Nb, d, plan.kcap, plan.fin_max,
                                                 plan.capp, plan.splits, plan.panels_per_split, buf_d, buf_i,
-                                                (uint32_t *)(ws + w.thr_key), st);
+                                                (int32_t *)(ws + w.counts), (uint32_t *)(ws + w.thr_key), st);
     if (rc) return rc;
   } else {
     const size_t dyn1 = (size_t)8 * plan.capp * 8;
@@ -736,6 +715,7 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   KnnRerankArgs a;
   a.Q = Qn; a.B = Bn; a.Nq = Nq; a.Nb = Nb; a.d = d; a.k = k; a.plan = plan;
   a.buf_d = buf_d; a.buf_i = buf_i;
+  a.counts = plan.counted ? (const int32_t *)(ws + w.counts) : nullptr;
   // |approx - exact| <= (2K + 8) * 2^-24 for unit-norm rows (DESIGN.md "kNN certification")
   //   3xTF32: operand split error 2^-20 per unit of sum|q_i b_i| plus FP32 accumulation -> doubled bound
   a.eps = (float)((2.0 * d + 8.0) * 5.9604644775390625e-08 * (tensor ? 2.5 : 1.25));
@@ -745,17 +725,13 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   a.flag_rows = (int32_t *)(ws + w.flag_rows);
   a.flag_T = (double *)(ws + w.flag_T);
   a.flag_I = (int32_t *)(ws + w.flag_I);
-  int msz = 1;
-  while (msz < plan.splits * plan.klist) msz <<= 1;
-  if (msz < plan.kcap) msz = plan.kcap;
-  const size_t per_warp = (((size_t)msz * 8 + (size_t)plan.kcap * 12) + 15) / 16 * 16;
+  const size_t per_warp = (((size_t)2 * plan.kcap * 8 + (size_t)plan.kcap * 12) + 15) / 16 * 16;
   const size_t dyn2 = per_warp * RERANK_WARPS;
   static bool attr2 = false;
   if (!attr2) {
-    RUNIA_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    RUNIA_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr2 = true;
   }
-  RUNIA_REQUIRE(dyn2 <= 200 * 1024, RUNIA_E_UNSUPPORTED, "knn_search: merge scratch too large");
   knn_rerank_kernel<<<(unsigned)ceil_div(Nq, RERANK_WARPS), RERANK_WARPS * 32, dyn2, st>>>(a);
   knn_fallback_kernel<<<FB_GRID, 256, 0, st>>>(a, status, (double *)(ws + w.fb_d), (int32_t *)(ws + w.fb_i));
   count_launch(4);

@@ -201,66 +201,40 @@ __device__ __forceinline__ void sort16(float (&v)[16]) {
 }
 #undef RUNIA_CE
 
-constexpr int E16_PAIRS = 3;                                             // warp pairs per CTA
-constexpr int E16_THREADS = E16_PAIRS * 64;
+constexpr int E16_WARPS = 4;
 constexpr int E16_RING = 3;
-constexpr int E16_STEP_FLOATS = 16 * 64;                                 // one step: 16 samples x 64 dims
-constexpr int E16_PAIR_FLOATS = E16_RING * E16_STEP_FLOATS + 16 * 16;    // ring + Chebyshev matrix
-constexpr size_t kEntropy16Smem = (size_t)E16_PAIRS * E16_PAIR_FLOATS * sizeof(float);
+constexpr int E16_STEP_FLOATS = 16 * 64;                                    // one step: 16 samples x 64 dims
+constexpr int E16_WARP_FLOATS = E16_RING * E16_STEP_FLOATS + 16 * 16;       // ring + Chebyshev matrix
+constexpr size_t kEntropy16Smem = (size_t)E16_WARPS * E16_WARP_FLOATS * sizeof(float);
 
-// Two warps (a "pair") share one item: both read the same 16 x 64 step from the pair's ring; warp h
-// folds the pair maxima p with p % 2 == h (60 of the 120, over both dimensions of its lanes) and
-// runs the sort / window estimator for component h of every lane's two dimensions.  Halving the
-// maxima a warp carries brings the kernel from 255 to <= 168 registers, i.e. from 8 to 12 resident
-// warps per SM: the first version issued 0.55 instructions per cycle per scheduler with the ALU pipe
-// 61 % busy (ncu, profiles/), limited by dependent-issue latency with only two warps per scheduler.
-struct constexpr_pair {
-  int a, b;
-};
-// p-th pair (a < b) of 16 samples in row-major upper-triangle order
-__host__ __device__ constexpr constexpr_pair pair_of(int p) {
-  int a = 0;
-  while (p >= 15 - a) {
-    p -= 15 - a;
-    ++a;
-  }
-  return constexpr_pair{a, a + 1 + p};
-}
-
-// named barrier of one warp pair; literal ids so that ptxas reserves 4 barriers per CTA, not all 16
-__device__ __forceinline__ void pair_barrier(int id) {
-  if (id == 1)
-    asm volatile("bar.sync 1, 64;" ::: "memory");
-  else if (id == 2)
-    asm volatile("bar.sync 2, 64;" ::: "memory");
-  else
-    asm volatile("bar.sync 3, 64;" ::: "memory");
-}
-
-template <int H>
-__device__ __forceinline__ void entropy16_pair_body(const float *__restrict__ z, int64_t n_items, int D, float min_dist,
-                                                    double c_term, double *__restrict__ h_z,
-                                                    double *__restrict__ h_mvn, float *ring, float *dm, int bar_id,
-                                                    int64_t gp, int64_t GP) {
-  constexpr int N = 16, K = 5, NPAIR = N * (N - 1) / 2, NMINE = NPAIR / 2;
-  const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(E16_WARPS * 32, 2)
+entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_dist, double c_term,
+                 double *__restrict__ h_z, double *__restrict__ h_mvn) {
+  constexpr int N = 16, K = 5, NPAIR = N * (N - 1) / 2;
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *ring = smem + (size_t)warp * E16_WARP_FLOATS;
+  float *dm = ring + E16_RING * E16_STEP_FLOATS;
   const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
-  const int spi = (D + 63) >> 6;  // steps per item
-  const int64_t n_my = gp < n_items ? (n_items - gp + GP - 1) / GP : 0;
+  const int64_t gw = (int64_t)blockIdx.x * E16_WARPS + warp;  // this warp's first item
+  const int64_t GW = (int64_t)gridDim.x * E16_WARPS;          // item stride
+  const int spi = (D + 63) >> 6;                              // steps per item
+  const int64_t n_my = gw < n_items ? (n_items - gw + GW - 1) / GW : 0;
   const int64_t n_steps = n_my * spi;
 
-  // copy stream (two steps ahead of the arithmetic); this warp brings rows 8H .. 8H+7 of every step
-  int64_t c_item = gp, c_step = 0;
+  // copy stream (runs two steps ahead of the compute stream)
+  int64_t c_item = gw;
   int c_j = 0, c_buf = 0;
+  int64_t c_step = 0;
   auto issue = [&]() {
     if (c_step < n_steps) {
       const float *src0 = z + c_item * (int64_t)N * D;
       const int col = c_j * 64 + (lane & 15) * 4;
       const uint32_t dst0 = ring_u32 + (uint32_t)(c_buf * E16_STEP_FLOATS + (lane & 15) * 4) * 4u;
-      const bool in = col < D;  // D % 4 == 0: a 16-byte chunk is entirely inside or outside the row
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int row = 8 * H + 2 * r + (lane >> 4);
+      for (int r = 0; r < 8; ++r) {
+        const int row = 2 * r + (lane >> 4);
+        const bool in = col < D;  // D % 4 == 0: a 16-byte chunk is entirely inside or outside the row
         const float *src = in ? src0 + (int64_t)row * D + col : z;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)row * 256u), "l"(src),
                      "r"(in ? 16 : 0)
@@ -268,7 +242,7 @@ __device__ __forceinline__ void entropy16_pair_body(const float *__restrict__ z,
       }
       if (++c_j == spi) {
         c_j = 0;
-        c_item += GP;
+        c_item += GW;
       }
       if (++c_buf == E16_RING) c_buf = 0;
       ++c_step;
@@ -279,21 +253,21 @@ __device__ __forceinline__ void entropy16_pair_body(const float *__restrict__ z,
   issue();
 
   int buf = 0;
-  for (int64_t item = gp; item < n_items; item += GP) {
-    float pm[NMINE];
+  for (int64_t item = gw; item < n_items; item += GW) {
+    float pm[NPAIR];
 #pragma unroll
-    for (int p = 0; p < NMINE; ++p) pm[p] = 0.f;
+    for (int p = 0; p < NPAIR; ++p) pm[p] = 0.f;
 #pragma unroll 1
     for (int jstep = 0; jstep < spi; ++jstep) {
       asm volatile("cp.async.wait_group 1;" ::: "memory");
-      pair_barrier(bar_id);  // both warps' halves of this step have landed
+      __syncwarp();
       float2 x[N];
       {
         const float2 *b2 = reinterpret_cast<const float2 *>(ring + buf * E16_STEP_FLOATS) + lane;
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] = b2[i * 32];
       }
-      issue();  // refills the buffer both warps read one step ago (they are past it: barrier above)
+      issue();  // refills the buffer read one step ago (every lane is past that step: __syncwarp above)
       if (++buf == E16_RING) buf = 0;
       const int j = jstep * 32 + lane;  // float2 column: dimensions 2j, 2j+1
       {
@@ -302,91 +276,90 @@ __device__ __forceinline__ void entropy16_pair_body(const float *__restrict__ z,
         for (int a = 0; a < N; ++a)
 #pragma unroll
           for (int b = a + 1; b < N; ++b) {
-            if ((p & 1) == H) {
-              const float2 d = sub2(x[a], x[b]);
-              pm[p >> 1] = fmaxf(fmaxf(pm[p >> 1], fabsf(d.x)), fabsf(d.y));
-            }
+            const float2 d = sub2(x[a], x[b]);
+            pm[p] = fmaxf(fmaxf(pm[p], fabsf(d.x)), fabsf(d.y));
             ++p;
           }
       }
-      float v[N];
+      float2 s[N];
+      {
+        float v[N];
 #pragma unroll
-      for (int i = 0; i < N; ++i) v[i] = H == 0 ? x[i].x : x[i].y;
-      sort16(v);
-      // k-th neighbour distance of every sample: min over the windows [a, a+K] that contain it of
-      // max(s_i - s_a, s_{a+K} - s_i); end points need no max, interior points fold the clamp in
-      float wc[N - K];
+        for (int i = 0; i < N; ++i) v[i] = x[i].x;
+        sort16(v);
 #pragma unroll
-      for (int a = 0; a < N - K; ++a) wc[a] = fmaxf(v[a + K] - v[a], min_dist);
-      float acc = 0.f;
+        for (int i = 0; i < N; ++i) s[i].x = v[i];
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = x[i].y;
+        sort16(v);
+#pragma unroll
+        for (int i = 0; i < N; ++i) s[i].y = v[i];
+      }
+      float2 wc[N - K];  // window widths, clamped
+#pragma unroll
+      for (int a = 0; a < N - K; ++a) {
+        const float2 d = sub2(s[a + K], s[a]);
+        wc[a] = make_float2(fmaxf(d.x, min_dist), fmaxf(d.y, min_dist));
+      }
+      float ax = 0.f, ay = 0.f;
 #pragma unroll
       for (int i = 0; i < N; ++i) {
-        float r = INFINITY;
+        float rx = INFINITY, ry = INFINITY;
 #pragma unroll
         for (int a = 0; a < N - K; ++a) {
           if (a <= i && i <= a + K) {
-            if (i == a || i == a + K)
-              r = fminf(r, wc[a]);
-            else
-              r = fminf(r, fmaxf(fmaxf(v[i] - v[a], v[a + K] - v[i]), min_dist));
+            if (i == a || i == a + K) {
+              rx = fminf(rx, wc[a].x);
+              ry = fminf(ry, wc[a].y);
+            } else {
+              const float2 L = sub2(s[i], s[a]);
+              const float2 R = sub2(s[a + K], s[i]);
+              rx = fminf(rx, fmaxf(fmaxf(L.x, R.x), min_dist));
+              ry = fminf(ry, fmaxf(fmaxf(L.y, R.y), min_dist));
+            }
           }
         }
-        acc += lg2_pos(r);
+        ax += lg2_pos(rx);
+        ay += lg2_pos(ry);
       }
-      // h = -psi(k) + psi(n) + (1/n) sum log(2 r)   [d = 1]
-      if (2 * j + H < D) h_z[item * (int64_t)D + 2 * j + H] = c_term + (double)(kLn2 * (1.f + acc * (1.f / N)));
+      if (2 * j < D) {
+        double2 o;  // h = -psi(k) + psi(n) + (1/n) sum log(2 r)   [d = 1]
+        o.x = c_term + (double)(kLn2 * (1.f + ax * (1.f / N)));
+        o.y = c_term + (double)(kLn2 * (1.f + ay * (1.f / N)));
+        reinterpret_cast<double2 *>(h_z + item * (int64_t)D)[j] = o;
+      }
     }
     // ---- item complete: joint (Chebyshev) estimator from the 120 pair maxima ----
     if (h_mvn != nullptr) {
-      // all indices below are compile-time constants after unrolling (pm must stay in registers)
-      float red[NMINE];
+      __syncwarp();
+      int p = 0;
 #pragma unroll
-      for (int q = 0; q < NMINE; ++q) red[q] = warp_max_f32(pm[q]);
-      if (lane == 0) {
+      for (int a = 0; a < N; ++a) {
+        if (lane == 0) dm[a * N + a] = 0.f;
 #pragma unroll
-        for (int q = 0; q < NMINE; ++q) {
-          constexpr_pair ab = pair_of(2 * q + H);
-          dm[ab.a * N + ab.b] = red[q];
-          dm[ab.b * N + ab.a] = red[q];
-        }
-        if (H == 0) {
-#pragma unroll
-          for (int a = 0; a < N; ++a) dm[a * N + a] = 0.f;
+        for (int b = a + 1; b < N; ++b) {
+          const float m = warp_max_f32(pm[p]);
+          if (lane == 0) {
+            dm[a * N + b] = m;
+            dm[b * N + a] = m;
+          }
+          ++p;
         }
       }
-      pair_barrier(bar_id);
-      if (H == 0) {
-        float lg = 0.f;
-        if (lane < N) {
-          float w[N];
+      __syncwarp();
+      float lg = 0.f;
+      if (lane < N) {
+        float v[N];
 #pragma unroll
-          for (int b = 0; b < N; ++b) w[b] = dm[lane * N + b];
-          sort16(w);  // w[0] = 0 (self); w[K] = k-th neighbour
-          lg = lg2_pos(fmaxf(w[K], min_dist));
-        }
-        lg = warp_sum32(lg);
-        if (lane == 0) h_mvn[item] = c_term + (double)D * (double)(kLn2 * (1.f + lg * (1.f / N)));
+        for (int b = 0; b < N; ++b) v[b] = dm[lane * N + b];
+        sort16(v);  // v[0] = 0 (self); v[K] = k-th neighbour
+        lg = lg2_pos(fmaxf(v[K], min_dist));
       }
-      // dm is rewritten only at the end of the next item, at least one step barrier from here
+      lg = warp_sum32(lg);
+      if (lane == 0) h_mvn[item] = c_term + (double)D * (double)(kLn2 * (1.f + lg * (1.f / N)));
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
-__global__ void __launch_bounds__(E16_THREADS, 2)
-entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_dist, double c_term,
-                 double *__restrict__ h_z, double *__restrict__ h_mvn) {
-  extern __shared__ __align__(16) float smem[];
-  const int warp = threadIdx.x >> 5;
-  const int pair = warp >> 1;
-  float *ring = smem + (size_t)pair * E16_PAIR_FLOATS;
-  float *dm = ring + E16_RING * E16_STEP_FLOATS;
-  const int64_t gp = (int64_t)blockIdx.x * E16_PAIRS + pair;  // this pair's first item
-  const int64_t GP = (int64_t)gridDim.x * E16_PAIRS;          // item stride
-  if ((warp & 1) == 0)
-    entropy16_pair_body<0>(z, n_items, D, min_dist, c_term, h_z, h_mvn, ring, dm, 1 + pair, gp, GP);
-  else
-    entropy16_pair_body<1>(z, n_items, D, min_dist, c_term, h_z, h_mvn, ring, dm, 1 + pair, gp, GP);
 }
 
 // ---------------------------------- generic path ------------------------------------------
@@ -482,9 +455,9 @@ extern "C" int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, 
                                       (int)kEntropy16Smem));
       attr16 = true;
     }
-    // persistent warp pairs: two CTAs of three pairs per SM (register-limited), items round-robin over pairs
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n_items, E16_PAIRS), (int64_t)2 * kNumSMs);
-    entropy16_kernel<<<grid, E16_THREADS, kEntropy16Smem, st>>>(z, n_items, D, (float)min_dist, digamma_term, h_z,
+    // persistent warps: two CTAs of four warps per SM (register-limited), items round-robin over warps
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n_items, E16_WARPS), (int64_t)2 * kNumSMs);
+    entropy16_kernel<<<grid, E16_WARPS * 32, kEntropy16Smem, st>>>(z, n_items, D, (float)min_dist, digamma_term, h_z,
                                                                    h_mvn);
     count_launch();
     return finish_launch("mcd_entropy(16)");

@@ -148,12 +148,13 @@ struct KdeEpi {  // online log-sum-exp of -|q-b|^2/(2h^2) in log2 units
 
 // kNN candidate filter.  Thread t owns query row t of the tile: threshold and count live in
 // registers, candidates (approximate distance, bank index) are appended to the row's buffer in
-// global memory (L2-resident).  The 32 rows of a warp share one buffer block, entry-major
-// ([entry][lane]), so that the lock-step scans below touch one 128-byte line per instruction.  When a buffer could overflow during the next panel, the owning
+// global memory, row-major [row][split][entry] so that the re-rank kernel gathers a row's lists with
+// coalesced loads.  With the seed threshold (below) a split appends a few hundred entries per row
+// and never shrinks; the shrink is the overflow guard for long splits (large banks): the owning
 // thread tightens its threshold by bisection on the order-preserving integer key of the distance
-// until between kcap and 2*kcap entries lie below it, and compacts its buffer in place -- 128
-// rows shrink in parallel, no sorting.  Entries dropped at any time have distance >= the row's
-// final threshold, which is what the certification in the re-rank kernel relies on.
+// until between kcap and `target` entries lie below it, and compacts its buffer in place.  Entries
+// dropped at any time have distance >= the row's final threshold, which is what the certification
+// in the re-rank kernel relies on.
 __device__ __forceinline__ uint32_t ord_key(float v) {
   const uint32_t u = __float_as_uint(v);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -167,7 +168,8 @@ struct KnnEpi {
   int64_t Nq, b_hi;
   float *buf_d;
   int32_t *buf_i;
-  int kcap, klist, capp, splits, split;
+  int32_t *counts;          // [Nq, splits] entries left in each list
+  int kcap, fin_max, capp, splits, split;
   const uint32_t *thr_key;  // [Nq] seed: order-preserving key of an upper bound on the kcap-th distance (0 = none)
   int64_t row;
   size_t base;
@@ -184,8 +186,7 @@ struct KnnEpi {
       if (key != 0u && key < ord_key(INFINITY)) thr = ord_val(key);
     }
     cnt = 0;
-    // block of the 32-row group this row belongs to, + lane; entry e lives at base + 32 * e
-    base = (((size_t)(row >> 5)) * splits + split) * ((size_t)capp * 32) + (size_t)(row & 31);
+    base = ((size_t)row * splits + split) * (size_t)capp;
   }
   __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
     if (!live) return;
@@ -195,18 +196,16 @@ struct KnnEpi {
       const float b2 = col < b_hi ? __ldg(bn + col) : 0.f;
       const float dist = fmaf(-2.f, v[j], q2 + b2);
       if (col < b_hi && dist < thr) {
-        buf_d[base + 32 * (size_t)cnt] = dist;
-        buf_i[base + 32 * (size_t)cnt] = (int32_t)col;
+        buf_d[base + cnt] = dist;
+        buf_i[base + cnt] = (int32_t)col;
         ++cnt;
       }
     }
   }
-  // buffer entry e of this thread, read through L2 (the entries were written by this thread)
-  __device__ __forceinline__ float ld_d(int e) const { return __ldcg(buf_d + base + 32 * (size_t)e); }
-  __device__ __forceinline__ int32_t ld_i(int e) const { return __ldcg(buf_i + base + 32 * (size_t)e); }
-  // number of buffered keys below `bound`; SCAN independent loads in flight per step (the buffers
-  // live in L2: a scan is latency-bound, so its cost is ~ n / SCAN round trips)
-  static constexpr int SCAN = 32;
+  // the entries were written by this thread: plain loads (its own stores are visible to it)
+  __device__ __forceinline__ float ld_d(int e) const { return buf_d[base + e]; }
+  __device__ __forceinline__ int32_t ld_i(int e) const { return buf_i[base + e]; }
+  static constexpr int SCAN = 32;  // independent loads in flight per scan step (one 128-byte line per lane)
   __device__ __forceinline__ int count_below(int n, uint32_t bound) const {
     int c = 0;
     for (int e0 = 0; e0 < n; e0 += SCAN) {
@@ -218,7 +217,7 @@ struct KnnEpi {
     }
     return c;
   }
-  // shrink this thread's buffer to between kcap and `target` entries (exactly kcap if target == kcap)
+  // shrink this thread's buffer to between kcap and `target` entries
   __device__ void shrink(int target) {
     const int n = cnt;
     if (n <= target) return;
@@ -277,8 +276,8 @@ struct KnnEpi {
           --ties_left;
         }
         if (keep) {
-          buf_d[base + 32 * (size_t)w] = v[j];
-          buf_i[base + 32 * (size_t)w] = ix[j];
+          buf_d[base + w] = v[j];
+          buf_i[base + w] = ix[j];
           ++w;
         }
       }
@@ -288,24 +287,18 @@ struct KnnEpi {
     cnt = w;
   }
   __device__ void panel_done(int) {
-    // warp-uniform trigger: when any row of the warp is about to overflow, every row that holds more
-    // than the target shrinks in the same (coalesced, lock-step) passes
-    if (__any_sync(0xffffffffu, live && cnt > capp - TN)) {
-      if (live) shrink(klist);
-    }
+    // overflow guard: the next panel can append at most TN entries
+    if (live && cnt > capp - TN) shrink(2 * kcap);
   }
   __device__ void finish() {
     if (!live) return;
-    shrink(klist);                       // no-op for most rows: the seed threshold keeps the lists short
-    for (int e = cnt; e < klist; ++e) {  // pad: the re-rank kernel reads klist entries per (row, split)
-      buf_d[base + 32 * (size_t)e] = INFINITY;
-      buf_i[base + 32 * (size_t)e] = -1;
-    }
+    shrink(fin_max);  // no-op unless the list is longer than the re-rank kernel's merge scratch allows
+    counts[(size_t)row * splits + split] = cnt;
   }
 };
 
 // Seed: an upper bound on every query's kcap-th smallest distance, with no buffers at all.  The seed
-// columns are cut into kcap / 4 groups of one panel (256 bank rows); per group the thread keeps the 4
+// columns are cut into kcap / 4 groups of `ppg` panels (256 bank rows each); per group the thread keeps the 4
 // smallest distances it has seen in registers.  B = max over groups of the 4th smallest has at least
 // kcap bank rows at distance <= B, so the main pass starts with the threshold nextafter(B) and only
 // ever buffers rows that can still matter.  Groups are independent: they are split over several CTA
@@ -314,8 +307,10 @@ struct KnnSeedEpi {
   const float *qn, *bn;
   int64_t Nq, b_hi;
   uint32_t *thr_key;
+  int ppg;  // panels per group
   int64_t row;
   float q2, m0, m1, m2, m3, bound;
+  int in_group;
   bool live;
   __device__ void begin(int, int64_t row_) {
     row = row_;
@@ -323,6 +318,7 @@ struct KnnSeedEpi {
     q2 = live ? __ldg(qn + row) : 0.f;
     m0 = m1 = m2 = m3 = INFINITY;
     bound = -INFINITY;
+    in_group = 0;
   }
   __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
 #pragma unroll
@@ -345,11 +341,15 @@ struct KnnSeedEpi {
     }
   }
   __device__ void panel_done(int) {
-    bound = fmaxf(bound, m3);
-    m0 = m1 = m2 = m3 = INFINITY;
+    if (++in_group == ppg) {
+      bound = fmaxf(bound, m3);
+      m0 = m1 = m2 = m3 = INFINITY;
+      in_group = 0;
+    }
   }
   __device__ void finish() {
     if (!live) return;
+    if (in_group != 0) bound = INFINITY;  // a partial group proves nothing (the launcher never produces one)
     const uint32_t key = ord_key(bound);
     atomicMax(thr_key + row, key < 0xfffffffeu ? key + 1u : key);  // exclusive bound: the filter is strict
   }
@@ -570,9 +570,9 @@ namespace runia {
 namespace tc {
 // shared with distance.cu
 int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
-                             const float *bn, int64_t Nb, int d, int kcap, int klist, int capp, int splits,
-                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, uint32_t *thr_key,
-                             cudaStream_t st) {
+                             const float *bn, int64_t Nb, int d, int kcap, int fin_max, int capp, int splits,
+                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, int32_t *counts,
+                             uint32_t *thr_key, cudaStream_t st) {
   CUtensorMap ma, mh, ml;
   int rc = make_a_map(&ma, Q, Nq, d);
   if (rc) return rc;
@@ -591,16 +591,22 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
   }
   const int64_t tiles = ceil_div(Nq, TM2);
   const int panels = (int)ceil_div(Nb, TN);
-  // seed over kcap / 4 full panels when the bank is at least twice that large
-  const int seed_panels = kcap / 4;
+  // Seed: kcap / 4 groups of `ppg` full panels each.  The bound admits a fraction p ~ 10 / (256 ppg)
+  // of the bank, i.e. ~ p Nb / splits appends per (row, split); ppg is chosen to keep that near 200
+  // (no shrink in the main pass with 512-entry buffers) while the seed stays under a quarter of the bank.
+  const int groups = kcap / 4;
+  int ppg = (int)std::max<int64_t>(1, ceil_div(Nb, (int64_t)5120 * splits));
+  ppg = (int)std::min<int64_t>(ppg, std::max<int64_t>(1, (Nb / TN) / (4 * (int64_t)groups)));
+  const int seed_panels = groups * ppg;
   const bool seeded = (Nb / TN) >= 2 * (int64_t)seed_panels;
   if (seeded) {
     RUNIA_CUDA(cudaMemsetAsync(thr_key, 0, (size_t)Nq * sizeof(uint32_t), st));
-    int ss = (int)std::min<int64_t>(seed_panels, std::max<int64_t>(1, ceil_div(kNumSMs, tiles)));
-    const int pps = (int)ceil_div(seed_panels, ss);
-    ss = (int)ceil_div(seed_panels, pps);
+    int ss = (int)std::min<int64_t>(groups, std::max<int64_t>(1, ceil_div(kNumSMs, tiles)));
+    const int gps = (int)ceil_div(groups, ss);  // whole groups per seed split
+    ss = (int)ceil_div(groups, gps);
+    const int pps = gps * ppg;
     KnnSeedEpi seed{};
-    seed.qn = qn; seed.bn = bn; seed.Nq = Nq; seed.b_hi = Nb; seed.thr_key = thr_key;
+    seed.qn = qn; seed.bn = bn; seed.Nq = Nq; seed.b_hi = Nb; seed.thr_key = thr_key; seed.ppg = ppg;
     dim3 grid0(2 * (unsigned)tiles, (unsigned)ss);
     tc_knn_seed_kernel<<<grid0, THREADS, smem, st>>>(ma, d, mh, ml, seed_panels, pps, seed);
     count_launch();
@@ -608,7 +614,8 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
   KnnEpi epi{};
   epi.qn = qn; epi.bn = bn; epi.Nq = Nq; epi.b_hi = Nb;
   epi.buf_d = buf_d; epi.buf_i = buf_i;
-  epi.kcap = kcap; epi.klist = klist; epi.capp = capp; epi.splits = splits; epi.split = 0;
+  epi.counts = counts;
+  epi.kcap = kcap; epi.fin_max = fin_max; epi.capp = capp; epi.splits = splits; epi.split = 0;
   epi.thr_key = seeded ? thr_key : nullptr;
   dim3 grid(2 * (unsigned)tiles, (unsigned)splits);
   tc_knn_kernel<<<grid, THREADS, smem, st>>>(ma, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
