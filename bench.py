@@ -129,7 +129,22 @@ def _time_events(fn, steps, warmup, dist_barrier):
     return ev[0].elapsed_time(ev[steps]), per
 
 
+def _all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arms are supposed to use every host core."""
+    n = os.cpu_count() or 1
+    try:
+        import threadpoolctl
+
+        threadpoolctl.threadpool_limits(limits=n)
+        return max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] or [1])
+    except Exception:
+        return n
+
+
 def run_b200(args):
+    # keep stdout to the one JSON line: the image sets NCCL_DEBUG=VERSION, which prints a banner there
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
 
@@ -231,6 +246,7 @@ def run_b200(args):
     extra = {}
     if rank == 0 and not args.no_extra:
         extra.update(_extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak))
+        extra.update(_extra_other_kernels(torch, _ops, hbm_peak, bf16_peak))
         if world == 1 and not args.no_sweep:
             extra["sweep_config2"] = _extra_sweep_config2(R)
     if world > 1 and not args.no_extra:
@@ -343,6 +359,81 @@ def _extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak):
     return out
 
 
+def _time_op(torch, fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak):
+    """The remaining rows of SURVEY 8(a), device-resident, each against the roofline SURVEY 8(d)
+    names for it: logit scores / ReAct / ASH (HBM), ViM / class-conditional Mahalanobis / DDU / KDE
+    (contractions; FP32-equivalent TFLOP/s against bf16/2/3 for the tensor-core ones)."""
+    out = {}
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev).manual_seed(21)
+    rng = np.random.RandomState(21)
+    hbm = lambda alg, ms: {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",  # noqa: E731
+                           "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}
+    # (a8) Energy + MSP + GEN in one pass: 20M x 10 logits, 52 B/sample
+    n = 20_000_000
+    L = torch.randn(n, 10, generator=g, device=dev)
+    ms = _time_op(torch, lambda: _ops.logit_scores(L, gamma=0.1, M=10))
+    out["logit_scores_c10"] = {"samples_per_s": n / (ms * 1e-3), "ms": ms, "roofline": hbm(n * 52, ms)}
+    del L
+    # (a10) ReAct / DICE (clip -> linear -> LSE) and ASH-S: 2M x 512, 2,052 B/embedding
+    n, d, C = 2_000_000, 512, 10
+    X = torch.relu(torch.randn(n, d, generator=g, device=dev))
+    W = 0.05 * torch.randn(C, d, generator=g, device=dev)
+    b = torch.randn(C, generator=g, device=dev)
+    ms = _time_op(torch, lambda: _ops.clip_linear_lse(X, W, b, clip=1.0))
+    out["react_512"] = {"embeddings_per_s": n / (ms * 1e-3), "ms": ms, "roofline": hbm(n * (d * 4 + 4), ms)}
+    ms = _time_op(torch, lambda: _ops.ash_linear_lse(X, W, b, 77))
+    out["ash_512"] = {"embeddings_per_s": n / (ms * 1e-3), "ms": ms, "roofline": hbm(n * (d * 4 + 4), ms)}
+    # (a7) ViM: d = 512, residual space 256, C = 10 logits
+    NS = np.linalg.qr(rng.randn(d, d))[0][:, :256]
+    vst = _ops.vim_prepare(rng.randn(d) * 0.1, NS, 1.7)
+    Lg = torch.randn(n, C, generator=g, device=dev)
+    ms = _time_op(torch, lambda: _ops.vim_score(X, Lg, vst))
+    fl = n * (2.0 * d * 256 + 3 * C)
+    out["vim_512"] = {"embeddings_per_s": n / (ms * 1e-3), "ms": ms, "fp32_equiv_tflops": fl / (ms * 1e-3) / 1e12,
+                      "tensor_frac_of_bf16_over_6": fl / (ms * 1e-3) / 1e12 / (bf16_peak / 6.0), "roofline": hbm(n * (d + C) * 4, ms)}
+    del Lg
+    # (a6) class-conditional Mahalanobis: d = 512, C = 10 (FP32 SIMT contraction)
+    A = rng.randn(d, d)
+    prec = A @ A.T / d + np.eye(d)
+    cst = _ops.classcond_prepare(rng.randn(C, d), prec)
+    n6 = 500_000
+    ms = _time_op(torch, lambda: _ops.classcond_score(X[:n6], cst))
+    fl = n6 * (2.0 * d * cst.r + 3.0 * cst.r * C)
+    out["mahalanobis_512_c10"] = {"embeddings_per_s": n6 / (ms * 1e-3), "ms": ms, "fp32_tflops": fl / (ms * 1e-3) / 1e12}
+    # (a9) DDU / GMM: C = 10 whitening contractions of 512 x 512
+    mus = rng.randn(C, d)
+    Ls = np.stack([np.linalg.cholesky(prec) for _ in range(C)])
+    gst = _ops.gmm_prepare(mus, Ls)
+    n9 = 200_000
+    ms = _time_op(torch, lambda: _ops.gmm_lse(X[:n9], gst))
+    fl = n9 * C * 2.0 * d * d
+    out["ddu_512_c10"] = {"embeddings_per_s": n9 / (ms * 1e-3), "ms": ms, "fp32_tflops": fl / (ms * 1e-3) / 1e12}
+    del X
+    # (a4) LaRED KDE: 50k x 256 bank, 100k queries
+    bank = 0.5 + torch.randn(50_000, 256, generator=g, device=dev)
+    q = torch.randn(100_000, 256, generator=g, device=dev)
+    kb = _ops.kde_bank(bank)
+    ms = _time_op(torch, lambda: _ops.kde_score(q, kb), reps=3)
+    fl = 2.0 * 100_000 * 50_000 * 256
+    out["kde_50k_256"] = {"queries_per_s": 100_000 / (ms * 1e-3), "ms": ms, "fp32_equiv_tflops": fl / (ms * 1e-3) / 1e12,
+                          "tensor_frac_of_bf16_over_6": fl / (ms * 1e-3) / 1e12 / (bf16_peak / 6.0)}
+    return out
+
+
 def _extra_sweep_config2(R):
     """BASELINE configs[1]: the full baseline sweep on ResNet-18 / CIFAR-10 shapes (50k x 512 train
     bank, 10 classes, 10k test rows), through the reference-facing classes with NumPy in / NumPy
@@ -442,6 +533,7 @@ def _cpu_larem(md, seconds=8.0):
     the largest the formulation affords) until `seconds` of work."""
     from oracle import oracle_np as O
 
+    threads = _all_host_threads()
     rng = np.random.RandomState(5)
     x = rng.randn(10_000, D_LATENT).astype(np.float32)
     O.md_score_faithful(x[:2000], md.feats_mean, md.precision)
@@ -451,12 +543,6 @@ def _cpu_larem(md, seconds=8.0):
         O.md_score_faithful(x, md.feats_mean, md.precision)
         n += 1
     dt = time.perf_counter() - t0
-    try:
-        import threadpoolctl
-
-        threads = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count()
     return {"value": n * 10_000 / dt, "unit": "embeddings/s", "cores": int(threads), "kind": "port",
             "sample": f"{n} calls x 10,000 rows x d=256 of MDLatentSpace.postprocess (N x N form), {dt:.1f} s"}
 
@@ -468,6 +554,7 @@ def run_reference(args):
         return
     from oracle import oracle_np as O
 
+    threads = _all_host_threads()
     train = _fit_larem()
     mean, prec = O.md_fit(train)
     rng = np.random.RandomState(5)
@@ -479,12 +566,6 @@ def run_reference(args):
     for _ in range(steps):
         O.md_score_faithful(x, mean, prec)
     dt = (time.perf_counter() - t0) / steps
-    try:
-        import threadpoolctl
-
-        threads = max([p.get("num_threads", 1) for p in threadpoolctl.threadpool_info()] or [1])
-    except Exception:
-        threads = os.cpu_count()
     v = 10_000 / dt
     line = {"impl": "reference", "metric": "ood_scored_embeddings_per_sec", "value": v, "unit": "embeddings/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": args.warmup,

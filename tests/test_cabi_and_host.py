@@ -208,3 +208,46 @@ def test_entropy_sorting_network_sorts_every_input():
         lo, hi = np.minimum(x[:, a], x[:, b]), np.maximum(x[:, a], x[:, b])
         x[:, a], x[:, b] = lo, hi
     assert (np.diff(x, axis=1) >= 0).all()
+
+
+def test_cabi_argument_errors_without_gpu():
+    """Argument validation happens before any CUDA call, so the error contract of
+    include/runia_b200.h (0 / RUNIA_E_BADARG / RUNIA_E_UNSUPPORTED + last_error text) and the pure
+    host-side workspace queries can be checked on a box without a GPU."""
+    import ctypes
+
+    from runia_core_b200 import _lib
+
+    raw = _lib.raw
+    fake = ctypes.c_void_p(0x1000)  # never dereferenced: every call below returns before a launch
+    err = lambda: raw("runia_b200_last_error")().decode()  # noqa: E731
+    # empty inputs are a no-op
+    assert raw("runia_mcd_entropy_f32")(None, 0, 16, 64, 5, 1e-5, 0.0, None, None, None) == 0
+    assert raw("runia_rownorm_score_f32")(None, 0, 8, None, None, 8, None, 0, None, 0, 0.0, None, None, None) == 0
+    assert raw("runia_logit_scores_f32")(None, 0, 10, 0.1, 10, None, None, None, None) == 0
+    # entropy: n_mc outside [2, 32] is unsupported, k >= n_mc is a bad argument
+    assert raw("runia_mcd_entropy_f32")(fake, 4, 33, 64, 5, 1e-5, 0.0, fake, None, None) == -2
+    assert "n_mc=33" in err()
+    assert raw("runia_mcd_entropy_f32")(fake, 4, 4, 64, 4, 1e-5, 0.0, fake, None, None) == -1
+    assert raw("runia_mcd_entropy_f32")(None, 4, 16, 64, 5, 1e-5, 0.0, None, None, None) == -1
+    # kNN: k outside [1, 240] unsupported; empty bank bad argument; workspace query is host-only
+    assert raw("runia_knn_search_f32")(fake, 4, fake, fake, None, None, 100, 8, 0, 0, None, None, None, None, fake,
+                                       fake, 1 << 20, None) == -2
+    assert raw("runia_knn_search_f32")(fake, 4, fake, fake, None, None, 0, 8, 5, 0, None, None, None, None, fake,
+                                       fake, 1 << 20, None) == -1
+    ws = raw("runia_knn_workspace_bytes")(10_000, 50_000, 512, 50)
+    assert ws > 10_000 * 4 and raw("runia_knn_workspace_bytes")(10, 10, 8, 241) == 0
+    assert raw("runia_knn_search_f32")(fake, 10_000, fake, fake, None, None, 50_000, 512, 50, 0, None, None, None, None,
+                                       fake, fake, 1024, None) == -3
+    assert "workspace" in err()
+    assert raw("runia_kde_workspace_bytes")(1000, 5000) > 0
+    # tensor-core entry points refuse shapes they are not built for (K % 4 != 0) instead of mis-computing
+    assert raw("runia_rownorm_score_tc")(fake, 4, 7, None, fake, fake, 7, None, 0, None, 0, 0.0, fake, None, None) == -2
+    assert raw("runia_pca_transform_tc")(fake, 4, 10, None, fake, fake, 4, None, fake, None) == -2
+    # ViM mode needs logits; unknown mode is a bad argument
+    assert raw("runia_rownorm_score_f32")(fake, 4, 8, None, fake, 8, None, 1, None, 0, 1.0, None, fake, None) == -1
+    assert raw("runia_rownorm_score_f32")(fake, 4, 8, None, fake, 8, None, 7, None, 0, 1.0, None, fake, None) == -1
+    # linear heads: more classes than the shared-memory weight tile holds; ASH keep count outside [1, d]
+    assert raw("runia_clip_linear_lse_f32")(fake, 4, 512, fake, fake, 65, float("inf"), fake, None) == -2
+    assert raw("runia_ash_linear_lse_f32")(fake, 4, 16, fake, fake, 4, 17, fake, None) == -1
+    assert raw("runia_topk_merge")(fake, fake, 17, 4, 5, None, None, None, None) == -1
