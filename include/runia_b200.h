@@ -122,6 +122,11 @@ int runia_classcond_mahalanobis_f32(const float *X, int64_t N, int d, const floa
                                     int r, const float *sign, const float *Mc, const int32_t *class_valid,
                                     int C, double *out_f64, float *out_f32, void *stream);
 
+/* Tensor-core (3xTF32) version of (a6): Wt replaced by its two planes; C <= 16, d % 4 == 0, r % 4 == 0. */
+int runia_classcond_mahalanobis_tc(const float *X, int64_t N, int d, const float *g, const float *Wt_hi,
+                                   const float *Wt_lo, int r, const float *sign, const float *Mc,
+                                   const int32_t *class_valid, int C, double *out_f64, float *out_f32, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (a9) DDU / GMM log-density -- inference/postprocessors.py:490-491, 783-784 with the mixture of
  * inference/funcs.py:265-344:  out[n] = logsumexp_c log N(x_n; mu_c, Sigma_c).
@@ -132,6 +137,9 @@ int runia_classcond_mahalanobis_f32(const float *X, int64_t N, int d, const floa
  */
 int runia_gmm_lse_f32(const float *X, int64_t N, int d, const float *At, const float *off, int dpad,
                       const float *logconst, int C, float *out, void *stream);
+/* Tensor-core (3xTF32) version: At replaced by its two planes; d % 4 == 0. */
+int runia_gmm_lse_tc(const float *X, int64_t N, int d, const float *At_hi, const float *At_lo, const float *off,
+                     int dpad, const float *logconst, int C, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a5) kNN -- inference/postprocessors.py:385-423 (`KNNLatentSpace`), :825-883 (`KNN`),

@@ -20,16 +20,16 @@ class RuniaB200Error(RuntimeError):
 
 
 def _load():
-    if not os.path.exists(LIB_PATH):
-        # developer convenience: build in-tree when a CUDA toolkit is present; never fall back
-        if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
-            from .build import build_library
+    from .build import _stale, build_library
 
-            build_library()
-        else:
+    have_nvcc = bool(shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"))
+    if not os.path.exists(LIB_PATH) or (_stale() and have_nvcc):
+        # developer convenience: (re)build in-tree when a CUDA toolkit is present; never fall back
+        if not have_nvcc:
             raise ImportError(
                 f"{LIB_PATH} is missing and nvcc is not available: build it with "
                 "`python -m runia_core_b200.build` (this package has no CPU fallback)")
+        build_library()
     return ctypes.CDLL(LIB_PATH)
 
 
@@ -47,6 +47,8 @@ _SIGS = {
                                         _P, _P, _P]),
     "runia_classcond_mahalanobis_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, _P]),
     "runia_gmm_lse_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, c_int, _P, _P]),
+    "runia_classcond_mahalanobis_tc": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, _P]),
+    "runia_gmm_lse_tc": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int, _P, c_int, _P, _P]),
     "runia_normalize_rows": (c_int, [_P, c_int, c_int64, c_int, _P, _P]),
     "runia_row_sqnorm_f32": (c_int, [_P, c_int64, c_int, _P, _P]),
     "runia_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int, c_int]),

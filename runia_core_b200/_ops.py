@@ -40,6 +40,7 @@ def split_tf32(w: torch.Tensor):
     return hi, lo
 
 
+TC_MAX_CLASSES = 16  # tc_kernels.cu kClassMax: per-class accumulators live in registers
 TC_MAX_K = 4096  # tc_gemm.cuh kMaxK: the centre of the streamed operand is staged in shared memory
 
 
@@ -230,6 +231,7 @@ class ClassCondState:
     C: int
     d: int
     r: int
+    planes: Optional[tuple] = None
 
 
 def classcond_prepare(class_mean, precision) -> ClassCondState:
@@ -241,9 +243,11 @@ def classcond_prepare(class_mean, precision) -> ClassCondState:
     Mc[valid] = (cm[valid] - g) @ Wt.T
     g64 = to_device(g)
     sg = None if np.all(sign == 1.0) else to_device(sign.astype(np.float32))
-    return ClassCondState(g64.to(torch.float32), g64, to_device(Wt.astype(np.float32)), sg,
+    w32 = to_device(Wt.astype(np.float32))
+    return ClassCondState(g64.to(torch.float32), g64, w32, sg,
                           to_device(Mc.astype(np.float32)), to_device(valid.astype(np.int32)),
-                          cm.shape[0], Wt.shape[1], Wt.shape[0])
+                          cm.shape[0], Wt.shape[1], Wt.shape[0],
+                          split_tf32(w32) if (Wt.shape[1] % 4 == 0 and Wt.shape[0] % 4 == 0) else None)
 
 
 def classcond_score(x, st: ClassCondState, out_dtype=torch.float64) -> torch.Tensor:
@@ -252,9 +256,14 @@ def classcond_score(x, st: ClassCondState, out_dtype=torch.float64) -> torch.Ten
     out = _empty((n,), out_dtype)
     o64 = out.data_ptr() if out_dtype == torch.float64 else None
     o32 = out.data_ptr() if out_dtype == torch.float32 else None
-    _lib.call("runia_classcond_mahalanobis_f32", xf.data_ptr(), n, st.d, None if centered else st.g_f32.data_ptr(),
-              st.Wt.data_ptr(), st.r, ptr(st.sign), st.Mc.data_ptr(), st.valid.data_ptr(), st.C, o64, o32,
-              stream_ptr())
+    g = None if centered else st.g_f32.data_ptr()
+    if _tc_ok(st.d) and st.planes is not None and st.C <= TC_MAX_CLASSES:
+        _lib.call("runia_classcond_mahalanobis_tc", xf.data_ptr(), n, st.d, g, st.planes[0].data_ptr(),
+                  st.planes[1].data_ptr(), st.r, ptr(st.sign), st.Mc.data_ptr(), st.valid.data_ptr(), st.C, o64, o32,
+                  stream_ptr())
+    else:
+        _lib.call("runia_classcond_mahalanobis_f32", xf.data_ptr(), n, st.d, g, st.Wt.data_ptr(), st.r, ptr(st.sign),
+                  st.Mc.data_ptr(), st.valid.data_ptr(), st.C, o64, o32, stream_ptr())
     return out
 
 
@@ -269,6 +278,7 @@ class GMMState:
     C: int
     d: int
     dpad: int
+    planes: Optional[tuple] = None
 
 
 def gmm_prepare(means, scale_tril) -> GMMState:
@@ -288,17 +298,21 @@ def gmm_prepare(means, scale_tril) -> GMMState:
         At[c, :d] = A
         off[c, :d] = A @ mu[c]
         logconst[c] = -np.log(np.diag(L[c])).sum() - 0.5 * d * np.log(2 * np.pi)
-    return GMMState(to_device(At.reshape(C * dpad, d).astype(np.float32)),
-                    to_device(off.reshape(-1).astype(np.float32)),
-                    to_device(logconst.astype(np.float32)), C, d, dpad)
+    a32 = to_device(At.reshape(C * dpad, d).astype(np.float32))
+    return GMMState(a32, to_device(off.reshape(-1).astype(np.float32)),
+                    to_device(logconst.astype(np.float32)), C, d, dpad, split_tf32(a32) if d % 4 == 0 else None)
 
 
 def gmm_lse(x, st: GMMState) -> torch.Tensor:
     xf, _ = as_f32_rows(x, None)
     n = xf.shape[0]
     out = _empty((n,), torch.float32)
-    _lib.call("runia_gmm_lse_f32", xf.data_ptr(), n, st.d, st.At.data_ptr(), st.off.data_ptr(), st.dpad,
-              st.logconst.data_ptr(), st.C, out.data_ptr(), stream_ptr())
+    if _tc_ok(st.d) and st.planes is not None:
+        _lib.call("runia_gmm_lse_tc", xf.data_ptr(), n, st.d, st.planes[0].data_ptr(), st.planes[1].data_ptr(),
+                  st.off.data_ptr(), st.dpad, st.logconst.data_ptr(), st.C, out.data_ptr(), stream_ptr())
+    else:
+        _lib.call("runia_gmm_lse_f32", xf.data_ptr(), n, st.d, st.At.data_ptr(), st.off.data_ptr(), st.dpad,
+                  st.logconst.data_ptr(), st.C, out.data_ptr(), stream_ptr())
     return out
 
 

@@ -2,6 +2,8 @@
 //  (a8)  Energy / MSP / GEN from logits in one read           postprocessors.py:519-691
 //  (a10) ReAct / DICE / DICE+ReAct: clip -> linear -> LSE      postprocessors.py:1325-1621
 //        ASH-S: per-row top-k pruning + rescale -> linear -> LSE   funcs.py:230-261
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace runia {
@@ -17,41 +19,58 @@ __device__ __forceinline__ float gen_term(float p, float gamma) {
   return powf(p, gamma) * powf(1.f - p, gamma);
 }
 
+constexpr float kLog2e = 1.4426950408889634f, kLn2f = 0.6931471805599453f;
+
+// Softmax statistics in log2 units on the MUFU pipe: t_c = (l_c - max) log2 e, e_c = 2^t_c,
+// s = sum e_c; energy = max + ln2 * log2 s; msp = 1 / s; log2 p_c = t_c - log2 s (no MUFU);
+// GEN term (p (1 - p))^gamma = 2^(gamma (log2 p + log2(1 - p))).  32 MUFU per 10-class sample keeps the
+// kernel under the HBM time (52 B/sample); powf / expf / logf would make it compute-bound 4x over.
 __global__ void __launch_bounds__(LS_ROWS)
 logit_scores_small_kernel(const float *__restrict__ logits, int64_t N, int C, float gamma, int M,
                           float *__restrict__ energy, float *__restrict__ msp, float *__restrict__ gen) {
-  extern __shared__ float tile[];  // [LS_ROWS][C + pad]
-  const int ldc = C | 1;           // odd stride -> conflict-free row reads
+  extern __shared__ __align__(16) float tile[];  // [LS_ROWS * C] logits, then (GEN) [LS_ROWS * C] exponentials
   const int64_t r0 = (int64_t)blockIdx.x * LS_ROWS;
-  const int64_t rows = (N - r0 < LS_ROWS) ? (N - r0) : LS_ROWS;
-  const int64_t total = rows * C;
+  const int rows = (int)((N - r0 < LS_ROWS) ? (N - r0) : LS_ROWS);
+  const int total = rows * C;
   const float *src = logits + r0 * C;
-  for (int64_t e = threadIdx.x; e < total; e += LS_ROWS) {
-    const int rr = (int)(e / C), cc = (int)(e % C);
-    tile[rr * ldc + cc] = __ldg(src + e);
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int n4 = total >> 2;
+    for (int i = threadIdx.x; i < n4; i += LS_ROWS)
+      reinterpret_cast<float4 *>(tile)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
+    for (int e = (n4 << 2) + threadIdx.x; e < total; e += LS_ROWS) tile[e] = __ldg(src + e);
+  } else {
+    for (int e = threadIdx.x; e < total; e += LS_ROWS) tile[e] = __ldg(src + e);
   }
   __syncthreads();
-  if (threadIdx.x >= rows) return;
-  const float *l = tile + threadIdx.x * ldc;
+  if ((int)threadIdx.x >= rows) return;
+  const float *l = tile + threadIdx.x * C;
+  float *ex = tile + LS_ROWS * C + threadIdx.x * C;  // only touched when gen != nullptr
   float m = -INFINITY;
   for (int c = 0; c < C; ++c) m = fmaxf(m, l[c]);
   float s = 0.f;
-  for (int c = 0; c < C; ++c) s += expf(l[c] - m);
+  for (int c = 0; c < C; ++c) {
+    const float e = exp2f((l[c] - m) * kLog2e);
+    s += e;
+    if (gen) ex[c] = e;
+  }
+  const float lg2s = __log2f(s);
   const int64_t row = r0 + threadIdx.x;
-  if (energy) energy[row] = logf(s) + m;
-  if (msp) msp[row] = 1.f / s;  // exp(m - m) / s
+  if (energy) energy[row] = fmaf(lg2s, kLn2f, m);
+  const float inv_s = 1.f / s;
+  if (msp) msp[row] = inv_s;  // exp(m - m) / s
   if (gen) {
     float g = 0.f;
-    if (M >= C) {
-      for (int c = 0; c < C; ++c) g += gen_term(expf(l[c] - m) / s, gamma);
-    } else {
-      // the M largest probabilities under the total order (value, index)
-      for (int c = 0; c < C; ++c) {
-        const float lc = l[c];
+    for (int c = 0; c < C; ++c) {
+      const float lc = l[c];
+      if (M < C) {
+        // only the M largest probabilities under the total order (value, index)
         int greater = 0;
         for (int o = 0; o < C; ++o) greater += (l[o] > lc || (l[o] == lc && o > c)) ? 1 : 0;
-        if (greater < M) g += gen_term(expf(lc - m) / s, gamma);
+        if (greater >= M) continue;
       }
+      const float p = ex[c] * inv_s;
+      const float lp = fmaf(lc - m, kLog2e, -lg2s);  // log2 p
+      g += exp2f(gamma * (lp + __log2f(1.f - p)));
     }
     gen[row] = -g;
   }
@@ -80,6 +99,130 @@ logit_scores_wide_kernel(const float *__restrict__ logits, int64_t N, int C, flo
     if (energy) energy[row] = logf(s) + m;
     if (msp) msp[row] = 1.f / s;
     if (gen) gen[row] = -g;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// clip -> linear -> log-sum-exp for C <= 16 classes (ReAct / DICE / DICE+ReAct heads): HBM-bound.
+// One warp per row, two rows per step.  Lane l owns elements 4l + 128 i + {0..3} of a row: four
+// coalesced LDG.128 bring 512 elements into registers; the weight rows come from shared memory as
+// conflict-free LDS.128, shared by the two rows.  The 16 per-lane partial dot products are reduced
+// across the warp with a halving butterfly (8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5): after
+// it lane l holds the full dot product of class (l >> 1) & 15, and the log-sum-exp is one more
+// warp reduction.
+// ------------------------------------------------------------------------------------------
+constexpr int LH_C = 16;
+
+__device__ __forceinline__ float butterfly16(float (&p)[LH_C], int lane) {
+  // step off = 16: lanes with bit 4 clear keep classes 0..7, the others 8..15
+  float q8[8];
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? p[i] : p[i + 8];
+      const float keep = up ? p[i + 8] : p[i];
+      q8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  float q4[4];
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? q8[i] : q8[i + 4];
+      const float keep = up ? q8[i + 4] : q8[i];
+      q4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  float q2[2];
+  {
+    const bool up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? q4[i] : q4[i + 2];
+      const float keep = up ? q4[i + 2] : q4[i];
+      q2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  float q1;
+  {
+    const bool up = lane & 2;
+    const float send = up ? q2[0] : q2[1];
+    const float keep = up ? q2[1] : q2[0];
+    q1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return q1 + __shfl_xor_sync(0xffffffffu, q1, 1);  // class ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1)
+}
+
+__global__ void __launch_bounds__(256)
+linear_lse_c16_kernel(const float *__restrict__ X, int64_t N, int d, const float *__restrict__ W,
+                      const float *__restrict__ b, int C, float clip, float *__restrict__ out) {
+  extern __shared__ __align__(16) float sW[];  // [LH_C][dpad], rows >= C and columns >= d are zero
+  const int dpad = (d + 127) & ~127;
+  for (int e = threadIdx.x; e < LH_C * dpad; e += blockDim.x) {
+    const int c = e / dpad, j = e - c * dpad;
+    sW[e] = (c < C && j < d) ? __ldg(W + (size_t)c * d + j) : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int my_class = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+  const float my_bias = my_class < C ? __ldg(b + my_class) : 0.f;
+  const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  const int64_t pairs = (N + 1) >> 1;
+  const int64_t wstride = (int64_t)gridDim.x * 8;
+  for (int64_t pr = (int64_t)blockIdx.x * 8 + warp; pr < pairs; pr += wstride) {
+    const int64_t row0 = 2 * pr, row1 = 2 * pr + 1;
+    const bool has1 = row1 < N;
+    const float *x0 = X + row0 * (int64_t)d;
+    const float *x1 = X + (has1 ? row1 : row0) * (int64_t)d;
+    float p0[LH_C], p1[LH_C];
+#pragma unroll
+    for (int c = 0; c < LH_C; ++c) p0[c] = p1[c] = 0.f;
+    for (int j0 = 0; j0 < dpad; j0 += 512) {
+      float4 a0[4], a1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = j0 + 128 * i + 4 * lane;
+        float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
+        if (vec && j + 3 < d) {
+          u = __ldg(reinterpret_cast<const float4 *>(x0 + j));
+          v = __ldg(reinterpret_cast<const float4 *>(x1 + j));
+        } else {
+          if (j + 0 < d) { u.x = __ldg(x0 + j + 0); v.x = __ldg(x1 + j + 0); }
+          if (j + 1 < d) { u.y = __ldg(x0 + j + 1); v.y = __ldg(x1 + j + 1); }
+          if (j + 2 < d) { u.z = __ldg(x0 + j + 2); v.z = __ldg(x1 + j + 2); }
+          if (j + 3 < d) { u.w = __ldg(x0 + j + 3); v.w = __ldg(x1 + j + 3); }
+        }
+        a0[i] = make_float4(fminf(u.x, clip), fminf(u.y, clip), fminf(u.z, clip), fminf(u.w, clip));
+        a1[i] = make_float4(fminf(v.x, clip), fminf(v.y, clip), fminf(v.z, clip), fminf(v.w, clip));
+      }
+#pragma unroll
+      for (int c = 0; c < LH_C; ++c) {
+        if (c < C) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int j = j0 + 128 * i + 4 * lane;
+            if (j < dpad) {
+              const float4 w = *reinterpret_cast<const float4 *>(sW + c * dpad + j);
+              p0[c] = fmaf(a0[i].x, w.x, fmaf(a0[i].y, w.y, fmaf(a0[i].z, w.z, fmaf(a0[i].w, w.w, p0[c]))));
+              p1[c] = fmaf(a1[i].x, w.x, fmaf(a1[i].y, w.y, fmaf(a1[i].z, w.z, fmaf(a1[i].w, w.w, p1[c]))));
+            }
+          }
+        }
+      }
+    }
+    const float d0 = butterfly16(p0, lane), d1 = butterfly16(p1, lane);  // all lanes take part
+    const float l0 = my_class < C ? d0 + my_bias : -INFINITY;
+    const float l1 = my_class < C ? d1 + my_bias : -INFINITY;
+    const float m0 = warp_max32(l0), m1 = warp_max32(l1);
+    // every class is held by two lanes (l, l ^ 1): halve the sum
+    const float s0 = 0.5f * warp_sum32(exp2f((l0 - m0) * kLog2e));
+    const float s1 = 0.5f * warp_sum32(exp2f((l1 - m1) * kLog2e));
+    if (lane == 0) {
+      out[row0] = fmaf(__log2f(s0), kLn2f, m0);
+      if (has1) out[row1] = fmaf(__log2f(s1), kLn2f, m1);
+    }
   }
 }
 
@@ -187,10 +330,10 @@ extern "C" int runia_logit_scores_f32(const float *logits, int64_t N, int C, flo
   RUNIA_REQUIRE(logits && (energy || msp || gen), RUNIA_E_BADARG, "logit_scores: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 64) {
-    const size_t smem = (size_t)LS_ROWS * (C | 1) * sizeof(float);
+    const size_t smem = (size_t)LS_ROWS * C * sizeof(float) * (gen ? 2 : 1);
     static bool attr = false;
     if (!attr) {
-      RUNIA_CUDA(cudaFuncSetAttribute(logit_scores_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+      RUNIA_CUDA(cudaFuncSetAttribute(logit_scores_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024));
       attr = true;
     }
     logit_scores_small_kernel<<<(unsigned)ceil_div(N, LS_ROWS), LS_ROWS, smem, st>>>(logits, N, C, gamma, M, energy,
@@ -217,6 +360,19 @@ static int launch_linear_lse(bool ash, const float *X, int64_t N, int d, const f
     RUNIA_CUDA(cudaFuncSetAttribute(linear_lse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     RUNIA_CUDA(cudaFuncSetAttribute(linear_lse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
+  }
+  if (!ash && C <= LH_C && (size_t)LH_C * ((d + 127) & ~127) * 4 <= 200 * 1024) {
+    const size_t smem16 = (size_t)LH_C * ((d + 127) & ~127) * sizeof(float);
+    static bool attr16 = false;
+    if (!attr16) {
+      RUNIA_CUDA(cudaFuncSetAttribute(linear_lse_c16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr16 = true;
+    }
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / (smem16 + 1024)));  // 92 registers
+    int64_t blocks16 = std::min<int64_t>(ceil_div((N + 1) / 2, 8), (int64_t)kNumSMs * per_sm);
+    linear_lse_c16_kernel<<<(unsigned)blocks16, 256, smem16, (cudaStream_t)stream>>>(X, N, d, W, b, C, clip, out);
+    count_launch();
+    return finish_launch("linear_lse(c16)");
   }
   int64_t blocks = ceil_div(N, 8);
   const int64_t cap = (int64_t)kNumSMs * 8;

@@ -104,6 +104,112 @@ struct PcaEpi {  // Z[row, col] = v * inv_scale[col]
   __device__ void finish() {}
 };
 
+// (a6) class-conditional Mahalanobis: out = max_c -sum_j sign_j (y_j - m_cj)^2 over the classes that
+// had training samples; one accumulator per class in registers (C <= kClassMax)
+constexpr int kClassMax = 16;
+struct ClassCondEpi {
+  const float *sign, *Mc;  // [r] or nullptr; [C, r]
+  const int32_t *valid;    // [C]
+  int r, C;
+  double *out64;
+  float *out32;
+  int64_t M;
+  int64_t row;
+  float cls[kClassMax];
+  __device__ void begin(int, int64_t row_) {
+    row = row_;
+#pragma unroll
+    for (int c = 0; c < kClassMax; ++c) cls[c] = 0.f;
+  }
+  __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
+#pragma unroll
+    for (int c = 0; c < kClassMax; ++c) {
+      if (c < C) {
+        const float *mc = Mc + (size_t)c * r + col0;
+        float acc = cls[c];
+        if (col0 + 31 < r) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 m4 = __ldg(reinterpret_cast<const float4 *>(mc + j));  // same address in every lane
+            float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (sign) s4 = __ldg(reinterpret_cast<const float4 *>(sign + col0 + j));
+            const float d0 = v[j] - m4.x, d1 = v[j + 1] - m4.y, d2 = v[j + 2] - m4.z, d3 = v[j + 3] - m4.w;
+            acc = fmaf(s4.x * d0, d0, acc);
+            acc = fmaf(s4.y * d1, d1, acc);
+            acc = fmaf(s4.z * d2, d2, acc);
+            acc = fmaf(s4.w * d3, d3, acc);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (col0 + j < r) {
+              const float dlt = v[j] - __ldg(mc + j);
+              acc = fmaf((sign ? __ldg(sign + col0 + j) : 1.f) * dlt, dlt, acc);
+            }
+          }
+        }
+        cls[c] = acc;
+      }
+    }
+  }
+  __device__ void panel_done(int) {}
+  __device__ void finish() {
+    if (row >= M) return;
+    float best = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < kClassMax; ++c)
+      if (c < C && valid[c]) {
+        const float sc = -cls[c];
+        if (sc > best) best = sc;  // NaN never wins, like np.max after NaN -> -inf
+      }
+    if (out64) out64[row] = (double)best;
+    if (out32) out32[row] = best;
+  }
+};
+
+// (a9) DDU / GMM: columns are C blocks of dpad whitened coordinates; per class
+// lp_c = -0.5 sum_j (v_j - off_j)^2 + logconst_c, out = logsumexp_c lp_c (online, per thread)
+struct GmmEpi {
+  const float *off, *logconst;
+  int dpad, C;
+  float *out;
+  int64_t M;
+  int64_t row;
+  float acc, run_m, run_s;
+  __device__ void begin(int, int64_t row_) {
+    row = row_;
+    acc = 0.f;
+    run_m = -INFINITY;
+    run_s = 0.f;
+  }
+  __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
+    if (col0 >= (int64_t)C * dpad) return;  // zero-filled tail of the last panel
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 o4 = __ldg(reinterpret_cast<const float4 *>(off + col0 + j));
+      const float d0 = v[j] - o4.x, d1 = v[j + 1] - o4.y, d2 = v[j + 2] - o4.z, d3 = v[j + 3] - o4.w;
+      acc = fmaf(d0, d0, acc);
+      acc = fmaf(d1, d1, acc);
+      acc = fmaf(d2, d2, acc);
+      acc = fmaf(d3, d3, acc);
+    }
+    if ((col0 + 32) % dpad == 0) {  // dpad is a multiple of 128: a class always ends on a 32-column chunk
+      const int c = (int)(col0 / dpad);
+      const float lp = fmaf(-0.5f, acc, __ldg(logconst + c));
+      const float m_new = fmaxf(run_m, lp);
+      if (m_new != -INFINITY) {
+        run_s = run_s * expf(run_m - m_new) + expf(lp - m_new);
+        run_m = m_new;
+      }
+      acc = 0.f;
+    }
+  }
+  __device__ void panel_done(int) {}
+  __device__ void finish() {
+    if (row < M) out[row] = run_m + logf(run_s);
+  }
+};
+
 struct KdeEpi {  // online log-sum-exp of -|q-b|^2/(2h^2) in log2 units
   const float *qn, *bn;
   int64_t Nq, b_hi;
@@ -564,6 +670,71 @@ extern "C" int runia_pca_transform_tc(const float *X, int64_t N, int D0, const f
                                                                       panels, epi);
   count_launch();
   return finish_launch("pca_transform_tc");
+}
+
+extern "C" int runia_classcond_mahalanobis_tc(const float *X, int64_t N, int d, const float *g, const float *Wt_hi,
+                                              const float *Wt_lo, int r, const float *sign, const float *Mc,
+                                              const int32_t *class_valid, int C, double *out_f64, float *out_f32,
+                                              void *stream) {
+  RUNIA_REQUIRE(N >= 0 && d > 0 && r > 0 && C > 0, RUNIA_E_BADARG, "classcond_mahalanobis_tc: bad sizes");
+  if (N == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(X && Wt_hi && Wt_lo && Mc && class_valid && (out_f64 || out_f32), RUNIA_E_BADARG,
+                "classcond_mahalanobis_tc: null pointer");
+  RUNIA_REQUIRE(C <= kClassMax, RUNIA_E_UNSUPPORTED, "classcond_mahalanobis_tc: C=%d > %d classes", C, kClassMax);
+  RUNIA_REQUIRE(usable(X, d, Wt_hi, Wt_lo) && (!g || (reinterpret_cast<uintptr_t>(g) & 15) == 0) && r % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(Mc) & 15) == 0 && (!sign || (reinterpret_cast<uintptr_t>(sign) & 15) == 0),
+                RUNIA_E_UNSUPPORTED, "classcond_mahalanobis_tc: needs d %% 4 == 0, r %% 4 == 0 and 16-byte aligned pointers");
+  CUtensorMap ma, mh, ml;
+  int rc = make_a_map(&ma, X, N, d);
+  if (rc) return rc;
+  rc = make_b_map(&mh, Wt_hi, r, d);
+  if (rc) return rc;
+  rc = make_b_map(&ml, Wt_lo, r, d);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    rc = set_smem(tc_kernel<ClassCondEpi>, kSmemMax);
+    if (rc) return rc;
+    attr = true;
+  }
+  ClassCondEpi epi{};
+  epi.sign = sign; epi.Mc = Mc; epi.valid = class_valid; epi.r = r; epi.C = C;
+  epi.out64 = out_f64; epi.out32 = out_f32; epi.M = N;
+  dim3 grid(2 * (unsigned)std::min<int64_t>(ceil_div(N, TM2), kNumSMs / 2), 1);
+  tc_kernel<ClassCondEpi><<<grid, THREADS, smem_bytes(d), (cudaStream_t)stream>>>(ma, N, d, Prologue{g, INFINITY}, mh,
+                                                                                ml, (int)ceil_div(r, TN), epi);
+  count_launch();
+  return finish_launch("classcond_mahalanobis_tc");
+}
+
+extern "C" int runia_gmm_lse_tc(const float *X, int64_t N, int d, const float *At_hi, const float *At_lo,
+                                const float *off, int dpad, const float *logconst, int C, float *out, void *stream) {
+  RUNIA_REQUIRE(N >= 0 && d > 0 && C > 0 && dpad >= d && dpad % 128 == 0, RUNIA_E_BADARG, "gmm_lse_tc: bad sizes");
+  if (N == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(X && At_hi && At_lo && off && logconst && out, RUNIA_E_BADARG, "gmm_lse_tc: null pointer");
+  RUNIA_REQUIRE(usable(X, d, At_hi, At_lo) && (reinterpret_cast<uintptr_t>(off) & 15) == 0, RUNIA_E_UNSUPPORTED,
+                "gmm_lse_tc: needs d %% 4 == 0 and 16-byte aligned pointers");
+  const int64_t cols = (int64_t)C * dpad;
+  CUtensorMap ma, mh, ml;
+  int rc = make_a_map(&ma, X, N, d);
+  if (rc) return rc;
+  rc = make_b_map(&mh, At_hi, cols, d);
+  if (rc) return rc;
+  rc = make_b_map(&ml, At_lo, cols, d);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    rc = set_smem(tc_kernel<GmmEpi>, kSmemMax);
+    if (rc) return rc;
+    attr = true;
+  }
+  GmmEpi epi{};
+  epi.off = off; epi.logconst = logconst; epi.dpad = dpad; epi.C = C; epi.out = out; epi.M = N;
+  dim3 grid(2 * (unsigned)std::min<int64_t>(ceil_div(N, TM2), kNumSMs / 2), 1);
+  tc_kernel<GmmEpi><<<grid, THREADS, smem_bytes(d), (cudaStream_t)stream>>>(ma, N, d, Prologue{nullptr, INFINITY}, mh, ml,
+                                                                          (int)ceil_div(cols, TN), epi);
+  count_launch();
+  return finish_launch("gmm_lse_tc");
 }
 
 namespace runia {
