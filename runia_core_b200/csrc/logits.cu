@@ -23,12 +23,27 @@ constexpr float kLog2e = 1.4426950408889634f, kLn2f = 0.6931471805599453f;
 
 // Softmax statistics in log2 units on the MUFU pipe: t_c = (l_c - max) log2 e, e_c = 2^t_c,
 // s = sum e_c; energy = max + ln2 * log2 s; msp = 1 / s; log2 p_c = t_c - log2 s (no MUFU);
-// GEN term (p (1 - p))^gamma = 2^(gamma (log2 p + log2(1 - p))).  32 MUFU per 10-class sample keeps the
+// GEN term (p (1 - p))^gamma = 2^(gamma (log2 p + log2(1 - p))).  31 MUFU per 10-class sample keeps the
 // kernel under the HBM time (52 B/sample); powf / expf / logf would make it compute-bound 4x over.
+// The approximate, flush-to-zero forms are safe here: e_c <= 1 only feeds s >= 1 and 1 - p, log2 p comes
+// from the logits themselves, 1 - p is never denormal, and a flushed 2^x is below 1e-38.
+__device__ __forceinline__ float ex2_fast(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_fast(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// CMAX = 16: the row lives in registers (fully unrolled, guarded by c < C); CMAX = 64: in shared memory
+template <int CMAX>
 __global__ void __launch_bounds__(LS_ROWS)
 logit_scores_small_kernel(const float *__restrict__ logits, int64_t N, int C, float gamma, int M,
                           float *__restrict__ energy, float *__restrict__ msp, float *__restrict__ gen) {
-  extern __shared__ __align__(16) float tile[];  // [LS_ROWS * C] logits, then (GEN) [LS_ROWS * C] exponentials
+  extern __shared__ __align__(16) float tile[];  // [LS_ROWS * C] logits (CMAX = 64 + GEN: then the t_c)
   const int64_t r0 = (int64_t)blockIdx.x * LS_ROWS;
   const int rows = (int)((N - r0 < LS_ROWS) ? (N - r0) : LS_ROWS);
   const int total = rows * C;
@@ -43,36 +58,72 @@ logit_scores_small_kernel(const float *__restrict__ logits, int64_t N, int C, fl
   }
   __syncthreads();
   if ((int)threadIdx.x >= rows) return;
-  const float *l = tile + threadIdx.x * C;
-  float *ex = tile + LS_ROWS * C + threadIdx.x * C;  // only touched when gen != nullptr
-  float m = -INFINITY;
-  for (int c = 0; c < C; ++c) m = fmaxf(m, l[c]);
-  float s = 0.f;
-  for (int c = 0; c < C; ++c) {
-    const float e = exp2f((l[c] - m) * kLog2e);
-    s += e;
-    if (gen) ex[c] = e;
-  }
-  const float lg2s = __log2f(s);
+  float *l = tile + threadIdx.x * C;
   const int64_t row = r0 + threadIdx.x;
-  if (energy) energy[row] = fmaf(lg2s, kLn2f, m);
-  const float inv_s = 1.f / s;
-  if (msp) msp[row] = inv_s;  // exp(m - m) / s
-  if (gen) {
-    float g = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float lc = l[c];
-      if (M < C) {
-        // only the M largest probabilities under the total order (value, index)
-        int greater = 0;
-        for (int o = 0; o < C; ++o) greater += (l[o] > lc || (l[o] == lc && o > c)) ? 1 : 0;
-        if (greater >= M) continue;
-      }
-      const float p = ex[c] * inv_s;
-      const float lp = fmaf(lc - m, kLog2e, -lg2s);  // log2 p
-      g += exp2f(gamma * (lp + __log2f(1.f - p)));
+  if (CMAX <= 16) {
+    float t[CMAX], e[CMAX];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      t[c] = c < C ? l[c] : -INFINITY;
+      m = fmaxf(m, t[c]);
     }
-    gen[row] = -g;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      t[c] = (t[c] - m) * kLog2e;  // -inf for c >= C
+      e[c] = ex2_fast(t[c]);
+      s += e[c];
+    }
+    const float lg2s = lg2_fast(s);
+    if (energy) energy[row] = fmaf(lg2s, kLn2f, m);
+    const float inv_s = 1.f / s;
+    if (msp) msp[row] = inv_s;  // exp(m - m) / s
+    if (gen) {
+      float g = 0.f;
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        if (c < C) {
+          bool take = true;
+          if (M < C) {  // only the M largest probabilities under the total order (value, index)
+            int greater = 0;
+#pragma unroll
+            for (int o = 0; o < CMAX; ++o) greater += (o < C && (t[o] > t[c] || (t[o] == t[c] && o > c))) ? 1 : 0;
+            take = greater < M;
+          }
+          const float lp = t[c] - lg2s;  // log2 p, straight from the logits
+          const float term = ex2_fast(gamma * (lp + lg2_fast(1.f - e[c] * inv_s)));
+          g += take ? term : 0.f;
+        }
+      }
+      gen[row] = -g;
+    }
+  } else {
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) m = fmaxf(m, l[c]);
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float tc = (l[c] - m) * kLog2e;
+      s += ex2_fast(tc);
+      if (gen) l[c] = tc;  // this thread's row only
+    }
+    const float lg2s = lg2_fast(s);
+    if (energy) energy[row] = fmaf(lg2s, kLn2f, m);
+    if (msp) msp[row] = 1.f / s;
+    if (gen) {
+      float g = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float tc = l[c];
+        if (M < C) {
+          int greater = 0;
+          for (int o = 0; o < C; ++o) greater += (l[o] > tc || (l[o] == tc && o > c)) ? 1 : 0;
+          if (greater >= M) continue;
+        }
+        const float lp = tc - lg2s;
+        g += ex2_fast(gamma * (lp + lg2_fast(1.f - ex2_fast(lp))));
+      }
+      gen[row] = -g;
+    }
   }
 }
 
@@ -155,12 +206,15 @@ __device__ __forceinline__ float butterfly16(float (&p)[LH_C], int lane) {
   return q1 + __shfl_xor_sync(0xffffffffu, q1, 1);  // class ((lane>>4)&1)*8 + ((lane>>3)&1)*4 + ((lane>>2)&1)*2 + ((lane>>1)&1)
 }
 
-__global__ void __launch_bounds__(256)
+// CN = number of classes rounded up to a multiple of 4 (weight rows >= C are zero): no guards in the
+// inner loops.  The next pair of rows is fetched into registers while the current one is reduced.
+template <int CN>
+__global__ void __launch_bounds__(256, 2)
 linear_lse_c16_kernel(const float *__restrict__ X, int64_t N, int d, const float *__restrict__ W,
                       const float *__restrict__ b, int C, float clip, float *__restrict__ out) {
-  extern __shared__ __align__(16) float sW[];  // [LH_C][dpad], rows >= C and columns >= d are zero
-  const int dpad = (d + 127) & ~127;
-  for (int e = threadIdx.x; e < LH_C * dpad; e += blockDim.x) {
+  extern __shared__ __align__(16) float sW[];  // [CN][dpad], rows >= C and columns >= d are zero
+  const int dpad = (d + 511) & ~511;
+  for (int e = threadIdx.x; e < CN * dpad; e += blockDim.x) {
     const int c = e / dpad, j = e - c * dpad;
     sW[e] = (c < C && j < d) ? __ldg(W + (size_t)c * d + j) : 0.f;
   }
@@ -171,20 +225,15 @@ linear_lse_c16_kernel(const float *__restrict__ X, int64_t N, int d, const float
   const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
   const int64_t pairs = (N + 1) >> 1;
   const int64_t wstride = (int64_t)gridDim.x * 8;
-  for (int64_t pr = (int64_t)blockIdx.x * 8 + warp; pr < pairs; pr += wstride) {
-    const int64_t row0 = 2 * pr, row1 = 2 * pr + 1;
-    const bool has1 = row1 < N;
-    const float *x0 = X + row0 * (int64_t)d;
-    const float *x1 = X + (has1 ? row1 : row0) * (int64_t)d;
-    float p0[LH_C], p1[LH_C];
+  const int nchunk = dpad >> 9;
+  auto load_chunk = [&](int64_t pr, int ch, float4 (&a0)[4], float4 (&a1)[4]) {
+    const int64_t row0 = 2 * pr, row1 = (2 * pr + 1 < N) ? 2 * pr + 1 : 2 * pr;
+    const float *x0 = X + row0 * (int64_t)d, *x1 = X + row1 * (int64_t)d;
 #pragma unroll
-    for (int c = 0; c < LH_C; ++c) p0[c] = p1[c] = 0.f;
-    for (int j0 = 0; j0 < dpad; j0 += 512) {
-      float4 a0[4], a1[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int j = j0 + 128 * i + 4 * lane;
-        float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
+    for (int i = 0; i < 4; ++i) {
+      const int j = ch * 512 + 128 * i + 4 * lane;
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f), v = u;
+      if (pr < pairs) {
         if (vec && j + 3 < d) {
           u = __ldg(reinterpret_cast<const float4 *>(x0 + j));
           v = __ldg(reinterpret_cast<const float4 *>(x1 + j));
@@ -194,21 +243,37 @@ linear_lse_c16_kernel(const float *__restrict__ X, int64_t N, int d, const float
           if (j + 2 < d) { u.z = __ldg(x0 + j + 2); v.z = __ldg(x1 + j + 2); }
           if (j + 3 < d) { u.w = __ldg(x0 + j + 3); v.w = __ldg(x1 + j + 3); }
         }
-        a0[i] = make_float4(fminf(u.x, clip), fminf(u.y, clip), fminf(u.z, clip), fminf(u.w, clip));
-        a1[i] = make_float4(fminf(v.x, clip), fminf(v.y, clip), fminf(v.z, clip), fminf(v.w, clip));
       }
+      a0[i] = u;
+      a1[i] = v;
+    }
+  };
+  float4 n0[4], n1[4];  // prefetched chunk
+  int64_t pr = (int64_t)blockIdx.x * 8 + warp;
+  load_chunk(pr, 0, n0, n1);
+  for (; pr < pairs; pr += wstride) {
+    float p0[LH_C], p1[LH_C];
 #pragma unroll
-      for (int c = 0; c < LH_C; ++c) {
-        if (c < C) {
+    for (int c = 0; c < LH_C; ++c) p0[c] = p1[c] = 0.f;
+    for (int ch = 0; ch < nchunk; ++ch) {
+      float4 a0[4], a1[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = j0 + 128 * i + 4 * lane;
-            if (j < dpad) {
-              const float4 w = *reinterpret_cast<const float4 *>(sW + c * dpad + j);
-              p0[c] = fmaf(a0[i].x, w.x, fmaf(a0[i].y, w.y, fmaf(a0[i].z, w.z, fmaf(a0[i].w, w.w, p0[c]))));
-              p1[c] = fmaf(a1[i].x, w.x, fmaf(a1[i].y, w.y, fmaf(a1[i].z, w.z, fmaf(a1[i].w, w.w, p1[c]))));
-            }
-          }
+      for (int i = 0; i < 4; ++i) {
+        a0[i] = make_float4(fminf(n0[i].x, clip), fminf(n0[i].y, clip), fminf(n0[i].z, clip), fminf(n0[i].w, clip));
+        a1[i] = make_float4(fminf(n1[i].x, clip), fminf(n1[i].y, clip), fminf(n1[i].z, clip), fminf(n1[i].w, clip));
+      }
+      if (ch + 1 < nchunk)
+        load_chunk(pr, ch + 1, n0, n1);
+      else
+        load_chunk(pr + wstride, 0, n0, n1);
+      const float *wbase = sW + ch * 512 + 4 * lane;
+#pragma unroll
+      for (int c = 0; c < CN; ++c) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 w = *reinterpret_cast<const float4 *>(wbase + c * dpad + 128 * i);
+          p0[c] = fmaf(a0[i].x, w.x, fmaf(a0[i].y, w.y, fmaf(a0[i].z, w.z, fmaf(a0[i].w, w.w, p0[c]))));
+          p1[c] = fmaf(a1[i].x, w.x, fmaf(a1[i].y, w.y, fmaf(a1[i].z, w.z, fmaf(a1[i].w, w.w, p1[c]))));
         }
       }
     }
@@ -220,8 +285,8 @@ linear_lse_c16_kernel(const float *__restrict__ X, int64_t N, int d, const float
     const float s0 = 0.5f * warp_sum32(exp2f((l0 - m0) * kLog2e));
     const float s1 = 0.5f * warp_sum32(exp2f((l1 - m1) * kLog2e));
     if (lane == 0) {
-      out[row0] = fmaf(__log2f(s0), kLn2f, m0);
-      if (has1) out[row1] = fmaf(__log2f(s1), kLn2f, m1);
+      out[2 * pr] = fmaf(__log2f(s0), kLn2f, m0);
+      if (2 * pr + 1 < N) out[2 * pr + 1] = fmaf(__log2f(s1), kLn2f, m1);
     }
   }
 }
@@ -330,14 +395,17 @@ extern "C" int runia_logit_scores_f32(const float *logits, int64_t N, int C, flo
   RUNIA_REQUIRE(logits && (energy || msp || gen), RUNIA_E_BADARG, "logit_scores: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 64) {
-    const size_t smem = (size_t)LS_ROWS * C * sizeof(float) * (gen ? 2 : 1);
+    const size_t smem = (size_t)LS_ROWS * C * sizeof(float);
     static bool attr = false;
     if (!attr) {
-      RUNIA_CUDA(cudaFuncSetAttribute(logit_scores_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024));
+      RUNIA_CUDA(cudaFuncSetAttribute(logit_scores_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024));
       attr = true;
     }
-    logit_scores_small_kernel<<<(unsigned)ceil_div(N, LS_ROWS), LS_ROWS, smem, st>>>(logits, N, C, gamma, M, energy,
-                                                                                 msp, gen);
+    const unsigned grid = (unsigned)ceil_div(N, LS_ROWS);
+    if (C <= 16)
+      logit_scores_small_kernel<16><<<grid, LS_ROWS, smem, st>>>(logits, N, C, gamma, M, energy, msp, gen);
+    else
+      logit_scores_small_kernel<64><<<grid, LS_ROWS, smem, st>>>(logits, N, C, gamma, M, energy, msp, gen);
   } else {
     RUNIA_REQUIRE(!gen || M >= C, RUNIA_E_UNSUPPORTED, "logit_scores: GEN with M=%d < C=%d needs C <= 64", M, C);
     logit_scores_wide_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(logits, N, C, gamma, energy, msp, gen);
@@ -361,16 +429,23 @@ static int launch_linear_lse(bool ash, const float *X, int64_t N, int d, const f
     RUNIA_CUDA(cudaFuncSetAttribute(linear_lse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  if (!ash && C <= LH_C && (size_t)LH_C * ((d + 127) & ~127) * 4 <= 200 * 1024) {
-    const size_t smem16 = (size_t)LH_C * ((d + 127) & ~127) * sizeof(float);
+  const int cn = (C + 3) & ~3;
+  const size_t smem16 = (size_t)cn * ((d + 511) & ~511) * sizeof(float);
+  if (!ash && C <= LH_C && smem16 <= 100 * 1024) {
     static bool attr16 = false;
     if (!attr16) {
-      RUNIA_CUDA(cudaFuncSetAttribute(linear_lse_c16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      RUNIA_CUDA(cudaFuncSetAttribute(linear_lse_c16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      RUNIA_CUDA(cudaFuncSetAttribute(linear_lse_c16_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      RUNIA_CUDA(cudaFuncSetAttribute(linear_lse_c16_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      RUNIA_CUDA(cudaFuncSetAttribute(linear_lse_c16_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       attr16 = true;
     }
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / (smem16 + 1024)));  // 92 registers
-    int64_t blocks16 = std::min<int64_t>(ceil_div((N + 1) / 2, 8), (int64_t)kNumSMs * per_sm);
-    linear_lse_c16_kernel<<<(unsigned)blocks16, 256, smem16, (cudaStream_t)stream>>>(X, N, d, W, b, C, clip, out);
+    const unsigned blocks16 = (unsigned)std::min<int64_t>(ceil_div((N + 1) / 2, 8), (int64_t)kNumSMs * 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cn == 4) linear_lse_c16_kernel<4><<<blocks16, 256, smem16, st>>>(X, N, d, W, b, C, clip, out);
+    else if (cn == 8) linear_lse_c16_kernel<8><<<blocks16, 256, smem16, st>>>(X, N, d, W, b, C, clip, out);
+    else if (cn == 12) linear_lse_c16_kernel<12><<<blocks16, 256, smem16, st>>>(X, N, d, W, b, C, clip, out);
+    else linear_lse_c16_kernel<16><<<blocks16, 256, smem16, st>>>(X, N, d, W, b, C, clip, out);
     count_launch();
     return finish_launch("linear_lse(c16)");
   }
