@@ -292,6 +292,151 @@ linear_lse_c16_kernel(const float *__restrict__ X, int64_t N, int d, const float
 }
 
 // ------------------------------------------------------------------------------------------
+// ASH-S head for C <= 16, d <= 1024: keep the k largest activations of the row, scale by
+// exp(sum_all / sum_kept), linear layer, log-sum-exp (funcs.py:230-261 + postprocessors.py:1212-1220).
+// The row lives in registers (lane l owns elements 4l + 128 i + q); the k-th largest value is found by
+// a radix select on order-preserving integer keys, one warp-wide REDUX per bit, which stops at the
+// first bit where exactly k keys lie at or above the candidate (distinct activations: ~12-16 bits);
+// only when the k-th value is tied does it run all 32 bits and rank the ties by index.
+// ------------------------------------------------------------------------------------------
+template <int CN, int NCH>
+__global__ void __launch_bounds__(256, 2)
+ash_lse_c16_kernel(const float *__restrict__ X, int64_t N, int d, const float *__restrict__ W,
+                   const float *__restrict__ b, int C, int k_keep, float *__restrict__ out) {
+  constexpr int NV = NCH * 16;
+  extern __shared__ __align__(16) float sW[];  // [CN][dpad], rows >= C and columns >= d are zero
+  constexpr int dpad = NCH * 512;
+  for (int e = threadIdx.x; e < CN * dpad; e += blockDim.x) {
+    const int c = e / dpad, j = e - c * dpad;
+    sW[e] = (c < C && j < d) ? __ldg(W + (size_t)c * d + j) : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int my_class = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+  const float my_bias = my_class < C ? __ldg(b + my_class) : 0.f;
+  const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  const int64_t wstride = (int64_t)gridDim.x * 8;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < N; row += wstride) {
+    const float *x = X + row * (int64_t)d;
+    float v[NV];
+    uint32_t key[NV];
+#pragma unroll
+    for (int g = 0; g < NV / 4; ++g) {  // g = 4 ch + i: elements 128 g + 4 lane + q
+      const int j = 128 * g + 4 * lane;
+      float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vec && j + 3 < d) {
+        u = __ldg(reinterpret_cast<const float4 *>(x + j));
+      } else {
+        if (j + 0 < d) u.x = __ldg(x + j + 0);
+        if (j + 1 < d) u.y = __ldg(x + j + 1);
+        if (j + 2 < d) u.z = __ldg(x + j + 2);
+        if (j + 3 < d) u.w = __ldg(x + j + 3);
+      }
+      v[4 * g + 0] = u.x; v[4 * g + 1] = u.y; v[4 * g + 2] = u.z; v[4 * g + 3] = u.w;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t bits = __float_as_uint(v[4 * g + q]);
+        const uint32_t k = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+        key[4 * g + q] = (j + q < d) ? k : 0u;  // padding can never be selected (real keys are > 0)
+      }
+    }
+    float s1 = 0.f;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) s1 += v[e];
+    s1 = warp_sum32(s1);
+    // radix select of the k-th largest key
+    uint32_t prefix = 0;
+    bool exact = false;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = prefix | (1u << bit);
+      int cnt = 0;
+#pragma unroll
+      for (int e = 0; e < NV; ++e) cnt += (key[e] >= cand) ? 1 : 0;
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt >= k_keep) prefix = cand;
+      if (cnt == k_keep) {
+        exact = true;  // exactly the top k lie at or above cand
+        break;
+      }
+    }
+    float s2 = 0.f;
+    if (exact) {
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        v[e] = key[e] >= prefix ? v[e] : 0.f;
+        s2 += v[e];
+      }
+    } else {
+      // prefix is the k-th largest key and it is tied: keep everything above it and the ties with the
+      // lowest indices (index order: block of 128, then lane, then q)
+      int n_gt = 0;
+#pragma unroll
+      for (int e = 0; e < NV; ++e) n_gt += (key[e] > prefix) ? 1 : 0;
+      n_gt = __reduce_add_sync(0xffffffffu, n_gt);
+      int ties_left = k_keep - n_gt;
+#pragma unroll
+      for (int g = 0; g < NV / 4; ++g) {
+        int mine = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mine += (key[4 * g + q] == prefix) ? 1 : 0;
+        int incl = mine;  // inclusive scan over lanes
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += t;
+        }
+        int rank = incl - mine;  // ties of this block in lower lanes
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int e = 4 * g + q;
+          const bool tie = key[e] == prefix;
+          const bool keep = key[e] > prefix || (tie && rank < ties_left);
+          rank += tie ? 1 : 0;
+          v[e] = keep ? v[e] : 0.f;
+          s2 += v[e];
+        }
+        ties_left -= total;  // may go negative: no more ties are kept
+      }
+    }
+    s2 = warp_sum32(s2);
+    const float scale = expf(s1 / s2);
+    float p[LH_C];
+#pragma unroll
+    for (int c = 0; c < LH_C; ++c) p[c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < CN; ++c) {
+#pragma unroll
+      for (int g = 0; g < NV / 4; ++g) {
+        const float4 w = *reinterpret_cast<const float4 *>(sW + c * dpad + 128 * g + 4 * lane);
+        p[c] = fmaf(v[4 * g], w.x, fmaf(v[4 * g + 1], w.y, fmaf(v[4 * g + 2], w.z, fmaf(v[4 * g + 3], w.w, p[c]))));
+      }
+    }
+    const float dot = butterfly16(p, lane);
+    const float lg = my_class < C ? fmaf(scale, dot, my_bias) : -INFINITY;
+    const float m = warp_max32(lg);
+    const float sm = 0.5f * warp_sum32(exp2f((lg - m) * kLog2e));  // every class sits in two lanes
+    if (lane == 0) out[row] = fmaf(__log2f(sm), kLn2f, m);
+  }
+}
+
+template <int CN>
+static int launch_ash16(int nch, unsigned blocks, size_t smem, cudaStream_t st, const float *X, int64_t N, int d,
+                        const float *W, const float *b, int C, int k_keep, float *out) {
+  static bool attr = false;
+  if (!attr) {
+    RUNIA_CUDA(cudaFuncSetAttribute(ash_lse_c16_kernel<CN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    RUNIA_CUDA(cudaFuncSetAttribute(ash_lse_c16_kernel<CN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  if (nch == 1)
+    ash_lse_c16_kernel<CN, 1><<<blocks, 256, smem, st>>>(X, N, d, W, b, C, k_keep, out);
+  else
+    ash_lse_c16_kernel<CN, 2><<<blocks, 256, smem, st>>>(X, N, d, W, b, C, k_keep, out);
+  return RUNIA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // clip -> linear -> log-sum-exp, one warp per row, W (C x d) staged in shared memory
 // ------------------------------------------------------------------------------------------
 constexpr int CL_MAXC = 64;
@@ -448,6 +593,20 @@ static int launch_linear_lse(bool ash, const float *X, int64_t N, int d, const f
     else linear_lse_c16_kernel<16><<<blocks16, 256, smem16, st>>>(X, N, d, W, b, C, clip, out);
     count_launch();
     return finish_launch("linear_lse(c16)");
+  }
+  if (ash && C <= LH_C && d <= 1024) {
+    const int nch = d <= 512 ? 1 : 2;
+    const size_t smem_a = (size_t)cn * nch * 512 * sizeof(float);
+    const unsigned blocks_a = (unsigned)std::min<int64_t>(ceil_div(N, 8), (int64_t)kNumSMs * 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (cn == 4) rc = launch_ash16<4>(nch, blocks_a, smem_a, st, X, N, d, W, b, C, k_keep, out);
+    else if (cn == 8) rc = launch_ash16<8>(nch, blocks_a, smem_a, st, X, N, d, W, b, C, k_keep, out);
+    else if (cn == 12) rc = launch_ash16<12>(nch, blocks_a, smem_a, st, X, N, d, W, b, C, k_keep, out);
+    else rc = launch_ash16<16>(nch, blocks_a, smem_a, st, X, N, d, W, b, C, k_keep, out);
+    if (rc) return rc;
+    count_launch();
+    return finish_launch("ash_lse(c16)");
   }
   int64_t blocks = ceil_div(N, 8);
   const int64_t cap = (int64_t)kNumSMs * 8;
