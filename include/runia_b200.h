@@ -218,6 +218,22 @@ int runia_clip_linear_lse_f32(const float *X, int64_t N, int d, const float *W, 
 int runia_ash_linear_lse_f32(const float *X, int64_t N, int d, const float *W, const float *b, int C,
                              int k_keep, float *out, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (f1) OoD detection metrics -- evaluation/metrics.py:37-100 (`get_auroc_results`: torchmetrics 1.8.2
+ * binary auroc / roc / precision_recall_curve + sklearn.metrics.auc), InD = positive class.
+ *   ind [n_ind], ood [n_ood]  scores, float32 (is_f64 = 0) or float64 (is_f64 = 1), device
+ *   out4 [4] float64: auroc, fpr@95, aupr, number of ROC points (including the prepended origin)
+ *   fpr_out / tpr_out [n_ind + n_ood + 1] float32 (optional): the ROC curve, one point per distinct
+ *     score in descending order after (0, 0); only the first out4[3] entries are written
+ *   workspace: runia_ood_metrics_workspace_bytes(n_ind, n_ood) bytes (keys, radix-sort double buffer,
+ *     digit histograms, scan state).  n_ind + n_ood < 2^31.
+ * Device-side LSD radix sort (8 bits per pass, stable) + one fused scan; the AUROC numerator is an exact
+ * integer sum.
+ */
+int64_t runia_ood_metrics_workspace_bytes(int64_t n_ind, int64_t n_ood);
+int runia_ood_metrics(const void *ind, int64_t n_ind, const void *ood, int64_t n_ood, int is_f64, double *out4,
+                      float *fpr_out, float *tpr_out, void *workspace, int64_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -469,6 +469,41 @@ def binary_roc(scores, labels):
     return fpr.astype(np.float64), tpr.astype(np.float64)
 
 
+def binary_clf_curve(scores, labels):
+    """torchmetrics `_binary_clf_curve` after `_binary_precision_recall_curve_format` (sigmoid when
+    any score is outside [0, 1]): (fps, tps) at every distinct score, descending."""
+    s = np.asarray(scores).reshape(-1)
+    y = np.asarray(labels).reshape(-1).astype(np.int64)
+    if not ((s >= 0).all() and (s <= 1).all()):
+        with np.errstate(over="ignore"):
+            s = (1.0 / (1.0 + np.exp(-s.astype(s.dtype)))).astype(s.dtype)
+    order = np.argsort(-s, kind="stable")
+    s, y = s[order], y[order]
+    idx = np.concatenate([np.nonzero(s[1:] - s[:-1])[0], [y.size - 1]])
+    tps = np.cumsum(y)[idx]
+    return 1 + idx - tps, tps
+
+
+def ood_metrics(ind_scores, ood_scores):
+    """evaluation/metrics.py:60-81 (`get_auroc_results`): (auroc, fpr@95, aupr) with InD as the
+    positive class.  AUPR = sklearn.metrics.auc over torchmetrics' precision_recall_curve (points
+    reversed, (recall 0, precision 1) appended)."""
+    ind = np.asarray(ind_scores).reshape(-1)
+    ood = np.asarray(ood_scores).reshape(-1)
+    scores = np.concatenate([ind, ood])
+    labels = np.concatenate([np.ones(ind.size, np.int64), np.zeros(ood.size, np.int64)])
+    fps, tps = binary_clf_curve(scores, labels)
+    fpr = np.concatenate([[0.0], fps / fps[-1]])
+    tpr = np.concatenate([[0.0], tps / tps[-1]])
+    trapz = np.trapezoid if hasattr(np, "trapezoid") else np.trapz
+    auroc = float(trapz(tpr, fpr))
+    fpr95 = float(fpr[np.where(tpr >= 0.95)[0][0]])
+    precision = np.concatenate([(tps / (tps + fps))[::-1], [1.0]])
+    recall = np.concatenate([(tps / tps[-1])[::-1], [0.0]])
+    aupr = float(-trapz(precision, recall))  # recall decreases: sklearn's auc flips the sign
+    return auroc, fpr95, aupr
+
+
 def auroc_fpr95(ind_scores, ood_scores):
     """evaluation/metrics.py:60-76: InD is the positive class."""
     ind = np.asarray(ind_scores).reshape(-1)

@@ -495,3 +495,31 @@ def ash_linear_lse(x, W: torch.Tensor, b: torch.Tensor, k_keep: int) -> torch.Te
     _lib.call("runia_ash_linear_lse_f32", xf.data_ptr(), n, d, W.data_ptr(), b.data_ptr(), W.shape[0],
               int(k_keep), out.data_ptr(), stream_ptr())
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# (f1) OoD detection metrics (AUROC, FPR@95, AUPR, ROC curve)
+# ------------------------------------------------------------------------------------------
+def ood_metrics(ind_scores, ood_scores, want_curve: bool = True):
+    """InD (positive) vs OoD scores -> dict(auroc, fpr95, aupr, fpr, tpr).  Scores may live on the
+    host or the device; float64 stays float64 (the sigmoid torchmetrics applies to scores outside
+    [0, 1] runs in the score dtype), everything else is scored as float32.  `fpr` / `tpr` are float32
+    CUDA tensors (one point per distinct score after the origin) or None."""
+    a, b = to_device(ind_scores).reshape(-1), to_device(ood_scores).reshape(-1)
+    f64 = a.dtype == torch.float64 or b.dtype == torch.float64
+    dt = torch.float64 if f64 else torch.float32
+    a, b = a.to(dt).contiguous(), b.to(dt).contiguous()
+    n_ind, n_ood = a.numel(), b.numel()
+    if n_ind == 0 or n_ood == 0:
+        raise ValueError("ood_metrics: both score arrays must be non-empty")
+    ws_bytes = int(_lib.raw("runia_ood_metrics_workspace_bytes")(n_ind, n_ood))
+    ws = _empty((ws_bytes,), torch.uint8)
+    out4 = _empty((4,), torch.float64)
+    fpr = _empty((n_ind + n_ood + 1,), torch.float32) if want_curve else None
+    tpr = _empty((n_ind + n_ood + 1,), torch.float32) if want_curve else None
+    _lib.call("runia_ood_metrics", a.data_ptr(), n_ind, b.data_ptr(), n_ood, 1 if f64 else 0, out4.data_ptr(),
+              ptr(fpr), ptr(tpr), ws.data_ptr(), ws_bytes, stream_ptr())
+    o = out4.cpu()
+    npts = int(o[3])
+    return {"auroc": float(o[0]), "fpr95": float(o[1]), "aupr": float(o[2]), "n_points": npts,
+            "fpr": fpr[:npts] if want_curve else None, "tpr": tpr[:npts] if want_curve else None}

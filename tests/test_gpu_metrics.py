@@ -1,0 +1,89 @@
+"""GPU parity of the OoD detection metrics (-m gpu): `get_auroc_results` against the reference's golden
+values (tests/unit_test_metrics.py:21-29), the oracle's restatement of torchmetrics / sklearn on seeded
+inputs with ties, saturating sigmoids and scores already inside [0, 1], and at 2e7 scores through
+properties (exact Mann-Whitney AUROC from an independent count, invariance under shuffling)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_np as O
+from tests import refkats as K
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def M():
+    from runia_core_b200 import _ops
+    from runia_core_b200.evaluation import get_auroc_results
+
+    return _ops, get_auroc_results
+
+
+def test_kat_get_auroc_results(M):
+    _, get_auroc_results = M
+    np.random.seed(1)
+    ind = 0.5 + np.random.randn(1000)
+    ood = -0.5 + np.random.randn(1000)
+    res, ml = get_auroc_results("test", ind, ood, True)
+    assert list(res.columns) == ["auroc", "fpr@95", "aupr", "fpr", "tpr"] and res.index[0] == "test"
+    assert abs(res["fpr@95"].values[0] - K.METRICS_1D["fpr95"]) < 1e-7
+    assert abs(res["aupr"].values[0] - K.METRICS_1D["aupr"]) < 1e-7
+    assert abs(res["auroc"].values[0] - K.METRICS_1D["auroc"]) < 1e-7
+    assert set(ml) == {"auroc", "aupr", "fpr_95"}
+    fpr, tpr = np.asarray(res["fpr"].values[0]), np.asarray(res["tpr"].values[0])
+    y = np.concatenate([np.ones(1000, np.int64), np.zeros(1000, np.int64)])
+    rf, rt = O.binary_roc(np.concatenate([ind, ood]), y)
+    assert fpr.shape == rf.shape and np.abs(fpr - rf).max() < 1e-6 and np.abs(tpr - rt).max() < 1e-6
+
+
+@pytest.mark.parametrize("case", ["f64_sigmoid", "f32_sigmoid", "ties", "saturating", "unit_interval", "unbalanced"])
+def test_metrics_vs_oracle(M, case):
+    ops, _ = M
+    rng = np.random.RandomState(sum(map(ord, case)))
+    n1, n0 = 30_011, 20_003
+    ind = 0.7 + rng.randn(n1)
+    ood = -0.3 + 1.3 * rng.randn(n0)
+    if case == "f32_sigmoid":
+        ind, ood = ind.astype(np.float32), ood.astype(np.float32)
+    elif case == "ties":
+        ind, ood = np.round(ind * 4) / 4, np.round(ood * 4) / 4  # ~40 distinct values
+    elif case == "saturating":
+        ind, ood = ind * 30, ood * 30  # sigmoid(x) == 1.0 / 0.0 for many: distinct scores merge
+    elif case == "unit_interval":
+        ind, ood = rng.beta(5, 2, n1), rng.beta(2, 5, n0)  # already in [0, 1]: no sigmoid
+    elif case == "unbalanced":
+        ood = ood[:37]
+    got = ops.ood_metrics(ind, ood)
+    ref = O.ood_metrics(ind, ood)
+    assert abs(got["auroc"] - ref[0]) < 1e-6 and abs(got["fpr95"] - ref[1]) < 1e-6 and abs(got["aupr"] - ref[2]) < 1e-6
+    y = np.concatenate([np.ones(ind.size, np.int64), np.zeros(ood.size, np.int64)])
+    rf, rt = O.binary_roc(np.concatenate([ind, ood]), y)
+    if case == "f32_sigmoid":
+        # which float32 sigmoids collide depends on the last ulp of exp (NumPy, torch and CUDA differ):
+        # the number of distinct scores may move by a few in 50k; the metrics above do not
+        assert abs(got["n_points"] - rf.size) <= 50
+    else:
+        assert got["n_points"] == rf.size
+        assert np.abs(got["fpr"].cpu().numpy() - rf).max() < 1e-6 and np.abs(got["tpr"].cpu().numpy() - rt).max() < 1e-6
+
+
+def test_metrics_2e7_scores(M):
+    """1e7 + 1e7 float32 scores on the device: AUROC must equal the Mann-Whitney statistic counted
+    independently (torch.searchsorted on the sorted OoD scores), and must not depend on the order of the
+    inputs."""
+    ops, _ = M
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = 10_000_000
+    ind = torch.sigmoid(0.5 + torch.randn(n, generator=g, device="cuda"))
+    ood = torch.sigmoid(-0.5 + torch.randn(n, generator=g, device="cuda"))
+    ood[: n // 10] = ind[: n // 10]  # exact cross-class ties
+    got = ops.ood_metrics(ind, ood, want_curve=False)
+    so = torch.sort(ood).values
+    less = torch.searchsorted(so, ind, right=False).double()
+    leq = torch.searchsorted(so, ind, right=True).double()
+    mw = float(((less + leq) * 0.5).sum() / (float(n) * float(n)))
+    assert abs(got["auroc"] - mw) < 1e-9
+    perm = torch.randperm(n, generator=g, device="cuda")
+    again = ops.ood_metrics(ind[perm], ood.flip(0), want_curve=False)
+    assert again["auroc"] == got["auroc"] and again["fpr95"] == got["fpr95"] and abs(again["aupr"] - got["aupr"]) < 1e-12

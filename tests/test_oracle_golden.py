@@ -100,6 +100,8 @@ def test_kat_metrics():
     ood = -0.5 + np.random.randn(1000)
     auroc, fpr95 = O.auroc_fpr95(ind, ood)
     assert abs(auroc - K.METRICS_1D["auroc"]) < 1e-7 and abs(fpr95 - K.METRICS_1D["fpr95"]) < 1e-7
+    a3 = O.ood_metrics(ind, ood)
+    assert abs(a3[0] - auroc) < 1e-12 and abs(a3[1] - fpr95) < 1e-12 and abs(a3[2] - K.METRICS_1D["aupr"]) < 1e-7
     # tests/unit_test_metrics.py:31-81: KDE + MD end to end on 1000x20 latents
     np.random.seed(1)
     valid = 0.5 + np.random.randn(1000, 20)
@@ -109,8 +111,10 @@ def test_kat_metrics():
     mean, prec = O.md_fit(train)
     a, f = O.auroc_fpr95(O.md_score(valid, mean, prec), O.md_score(oodx, mean, prec))
     assert abs(a - K.METRICS_MD["auroc"]) < 1e-7 and abs(f - K.METRICS_MD["fpr95"]) < 1e-7
+    assert abs(O.ood_metrics(O.md_score(valid, mean, prec), O.md_score(oodx, mean, prec))[2] - K.METRICS_MD["aupr"]) < 1e-7
     a, f = O.auroc_fpr95(O.kde_score(valid, train), O.kde_score(oodx, train))
     assert abs(a - K.METRICS_KDE["auroc"]) < 1e-7 and abs(f - K.METRICS_KDE["fpr95"]) < 1e-7
+    assert abs(O.ood_metrics(O.kde_score(valid, train), O.kde_score(oodx, train))[2] - K.METRICS_KDE["aupr"]) < 1e-7
 
 
 # ------------------------------- fixtures from the reference run ---------------------------
