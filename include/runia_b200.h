@@ -234,6 +234,14 @@ int64_t runia_ood_metrics_workspace_bytes(int64_t n_ind, int64_t n_ood);
 int runia_ood_metrics(const void *ind, int64_t n_ind, const void *ood, int64_t n_ood, int is_f64, double *out4,
                       float *fpr_out, float *tpr_out, void *workspace, int64_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (f4) EigenScore -- llm_uncertainty/scores.py:49-66 (`eigen_score`): mean log singular value of
+ * cov(E^T) + alpha I, E [n, d] float32 (n sampled generations x d hidden units), computed from the
+ * n x n Gram matrix of the centred samples in float64 (Jacobi) instead of a d x d SVD.
+ *   out [1] float64.  2 <= n <= 32, n <= d <= 25600.
+ */
+int runia_eigen_score_f32(const float *E, int n, int d, double alpha, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -514,3 +514,27 @@ def auroc_fpr95(ind_scores, ood_scores):
     auroc = float(np.trapezoid(tpr, fpr)) if hasattr(np, "trapezoid") else float(np.trapz(tpr, fpr))
     fpr95 = float(fpr[np.where(tpr >= 0.95)[0][0]])
     return auroc, fpr95
+
+
+# --------------------------------------------------------------------------------------
+# (f4) EigenScore.  llm_uncertainty/scores.py:49-66
+# --------------------------------------------------------------------------------------
+def eigen_score_faithful(E, alpha=1e-3):
+    """The reference's own route: d x d covariance of the float32 embeddings (torch.cov keeps
+    float32), cast to float64, full SVD of cov + alpha I, mean log singular value."""
+    E = np.asarray(E, np.float32)
+    Ec = E - E.mean(0, keepdims=True, dtype=np.float32)
+    cov = (Ec.T @ Ec / np.float32(E.shape[0] - 1)).astype(np.float64)
+    sv = np.linalg.svd(cov + alpha * np.eye(cov.shape[0]), compute_uv=False)
+    return float(np.mean(np.log(sv)))
+
+
+def eigen_score(E, alpha=1e-3):
+    """Same quantity from the n x n Gram matrix of the centred samples in float64: the d x d covariance has
+    rank <= n - 1 and shares its non-zero eigenvalues with the Gram matrix; the other d - n singular values
+    of cov + alpha I are alpha."""
+    E = np.asarray(E, np.float64)
+    n, d = E.shape
+    Ec = E - E.mean(0, keepdims=True)
+    lam = np.linalg.eigvalsh(Ec @ Ec.T / (n - 1))
+    return float((np.log(np.maximum(lam, 0.0) + alpha).sum() + (d - n) * np.log(alpha)) / d)

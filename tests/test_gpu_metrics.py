@@ -87,3 +87,23 @@ def test_metrics_2e7_scores(M):
     perm = torch.randperm(n, generator=g, device="cuda")
     again = ops.ood_metrics(ind[perm], ood.flip(0), want_curve=False)
     assert again["auroc"] == got["auroc"] and again["fpr95"] == got["fpr95"] and abs(again["aupr"] - got["aupr"]) < 1e-12
+
+
+def test_eigen_score_kat_and_config5():
+    """Reference golden (unit_test_llm_uncertainty.py:69-92) through the public function, and BASELINE
+    configs[4]: 10 samples x 4096-d hidden states against the oracle."""
+    from runia_core_b200.llm_uncertainty import eigen_score
+
+    np.random.seed(42)
+    torch.manual_seed(42)
+    hs = tuple(tuple(torch.randn(1, 10, 768) for _ in range(20)) for _ in range(5))
+    got = eigen_score(hs, alpha=1e-3)
+    assert isinstance(got, float) and abs(got - K.EIGEN_SCORE) < 1e-6
+    rng = np.random.RandomState(42)
+    E = rng.randn(10, 4096).astype(np.float32)
+    E[3] = E[2]  # duplicated generation: rank drops, one more eigenvalue at alpha
+    hs2 = ((None,) * 15 + (torch.from_numpy(E)[None],),)
+    for alpha in (1e-3, 1e-1):
+        assert abs(eigen_score(hs2, alpha=alpha) - O.eigen_score(E, alpha)) < 1e-9
+    E32 = rng.randn(32, 64).astype(np.float32)
+    assert abs(eigen_score(((None,) * 15 + (torch.from_numpy(E32),),), 1e-3) - O.eigen_score(E32, 1e-3)) < 1e-9

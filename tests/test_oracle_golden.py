@@ -187,3 +187,16 @@ def test_fixture_pca(golden):
                             p[f"{tag}_explained_variance"])
         assert z.dtype == p[f"{tag}_test_t"].dtype
         assert rel_err(z, p[f"{tag}_test_t"]) < 1e-6
+
+
+def test_kat_eigen_score():
+    """tests/unit_test_llm_uncertainty.py:69-92: seed 42, 5 tokens x 20 layers of randn(1, 10, 768),
+    alpha 1e-3 -> -6.775187082486514 (TOL 1e-6).  Both the faithful SVD route and the Gram route."""
+    import torch
+
+    np.random.seed(42)
+    torch.manual_seed(42)
+    hs = tuple(tuple(torch.randn(1, 10, 768) for _ in range(20)) for _ in range(5))
+    E = hs[-1][15].squeeze().numpy()
+    assert abs(O.eigen_score_faithful(E, 1e-3) - K.EIGEN_SCORE) < 1e-6
+    assert abs(O.eigen_score(E, 1e-3) - K.EIGEN_SCORE) < 1e-6
