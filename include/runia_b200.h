@@ -242,6 +242,15 @@ int runia_ood_metrics(const void *ind, int64_t n_ind, const void *ood, int64_t n
  */
 int runia_eigen_score_f32(const float *E, int n, int d, double alpha, double *out, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (f4) Predictive entropy / mutual information of MC-dropout logits -- inference/funcs.py:430-465
+ * (`get_predictive_uncertainty_score`).
+ *   logits [n_items * n_mc, C] float32, item-major;  pred_h [n_items], mi [n_items] float32 (either may be NULL)
+ *   pred_h = -sum_c mean_s(p) log mean_s(p), mi = pred_h - mean_s(-sum_c p log p), p = softmax per row.
+ */
+int runia_pred_uncertainty_f32(const float *logits, int64_t n_items, int n_mc, int C, float *pred_h, float *mi,
+                               void *stream);
+
 #ifdef __cplusplus
 }
 #endif

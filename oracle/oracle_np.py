@@ -538,3 +538,18 @@ def eigen_score(E, alpha=1e-3):
     Ec = E - E.mean(0, keepdims=True)
     lam = np.linalg.eigvalsh(Ec @ Ec.T / (n - 1))
     return float((np.log(np.maximum(lam, 0.0) + alpha).sum() + (d - n) * np.log(alpha)) / d)
+
+
+# --------------------------------------------------------------------------------------
+# (f4) predictive entropy / mutual information.  inference/funcs.py:430-465
+# --------------------------------------------------------------------------------------
+def predictive_uncertainty(logits, n_mc):
+    """float32 like the torch original: softmax per row, mean over the n_mc rows of an item,
+    pred_h = -sum q log q, mi = pred_h - mean_s(-sum p log p)."""
+    x = np.asarray(logits, np.float32)
+    p = softmax(x, axis=1).astype(np.float32).reshape(-1, n_mc, x.shape[1])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = p.mean(1, dtype=np.float32)
+        pred_h = -(q * np.log(q)).sum(1, dtype=np.float32)
+        exp_h = (-(p * np.log(p)).sum(-1, dtype=np.float32)).mean(1, dtype=np.float32)
+    return pred_h, pred_h - exp_h

@@ -629,3 +629,109 @@ extern "C" int runia_ash_linear_lse_f32(const float *X, int64_t N, int d, const 
   RUNIA_REQUIRE(k_keep >= 1 && k_keep <= d, RUNIA_E_BADARG, "ash_linear_lse: k_keep=%d outside [1, d=%d]", k_keep, d);
   return launch_linear_lse(true, X, N, d, W, b, C, INFINITY, k_keep, out, stream);
 }
+
+// ------------------------------------------------------------------------------------------
+// (f4) predictive entropy and mutual information of MC-dropout logits -- inference/funcs.py:430-465
+// (`get_predictive_uncertainty_score`): logits [N * n_mc, C] item-major; p = softmax per row;
+//   pred_h = -sum_c mean_s(p) log mean_s(p);   mi = pred_h - mean_s( -sum_c p log p ).
+// One warp per item; a group of CP = 2^ceil(log2 C) <= 32 lanes owns one MC sample at a time (32 / CP samples
+// per pass), or the whole warp strides over the classes when C > 32.  Like upstream, a probability that
+// underflows to exactly 0 gives NaN (0 * log 0).
+// ------------------------------------------------------------------------------------------
+namespace runia {
+
+__global__ void __launch_bounds__(256)
+pred_uncertainty_kernel(const float *__restrict__ logits, int64_t n_items, int n_mc, int C, float *__restrict__ pred_h,
+                        float *__restrict__ mi) {
+  const int lane = threadIdx.x & 31;
+  const int64_t item = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (item >= n_items) return;
+  const float *base = logits + item * (int64_t)n_mc * C;
+  if (C <= 32) {
+    int cp = 1;
+    while (cp < C) cp <<= 1;
+    const int groups = 32 / cp, g = lane / cp, c = lane % cp;
+    const bool act = c < C;
+    float mean_p = 0.f, ent = 0.f;  // this lane: running sum over its samples of p_c and of -sum_c p log p (group-reduced)
+    for (int s0 = 0; s0 < n_mc; s0 += groups) {
+      const int s = s0 + g;
+      const bool ok = act && s < n_mc;
+      const float l = ok ? __ldg(base + (int64_t)s * C + c) : -INFINITY;
+      float m = l;
+      for (int off = cp >> 1; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+      const float e = ok ? expf(l - m) : 0.f;
+      float sum = e;
+      for (int off = cp >> 1; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+      const float p = ok ? e / sum : 0.f;
+      float t = ok ? p * logf(p) : 0.f;  // NaN when p == 0, like torch
+      for (int off = cp >> 1; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+      mean_p += p;
+      if (s < n_mc) ent -= t;
+    }
+    // combine the groups: lanes with the same class c
+    for (int off = cp; off < 32; off <<= 1) {
+      mean_p += __shfl_xor_sync(0xffffffffu, mean_p, off);
+      ent += __shfl_xor_sync(0xffffffffu, ent, off);
+    }
+    mean_p /= (float)n_mc;
+    float h = act ? mean_p * logf(mean_p) : 0.f;
+    for (int off = cp >> 1; off > 0; off >>= 1) h += __shfl_xor_sync(0xffffffffu, h, off);
+    if (lane == 0) {
+      const float ph = -h;
+      if (pred_h) pred_h[item] = ph;
+      if (mi) mi[item] = ph - ent / (float)n_mc;
+    }
+  } else {
+    // wide rows: the mean probabilities of the item are accumulated in shared memory (8 warps x C floats)
+    extern __shared__ float acc[];
+    float *mp = acc + (size_t)(threadIdx.x >> 5) * C;
+    for (int c = lane; c < C; c += 32) mp[c] = 0.f;
+    float ent = 0.f;
+    for (int s = 0; s < n_mc; ++s) {
+      const float *l = base + (int64_t)s * C;
+      float m = -INFINITY;
+      for (int c = lane; c < C; c += 32) m = fmaxf(m, __ldg(l + c));
+      m = warp_max32(m);
+      float sum = 0.f;
+      for (int c = lane; c < C; c += 32) sum += expf(__ldg(l + c) - m);
+      sum = warp_sum32(sum);
+      float t = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float p = expf(__ldg(l + c) - m) / sum;
+        t += p * logf(p);
+        mp[c] += p;
+      }
+      ent -= warp_sum32(t);
+    }
+    float h = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float q = mp[c] / (float)n_mc;
+      h += q * logf(q);
+    }
+    h = warp_sum32(h);
+    if (lane == 0) {
+      if (pred_h) pred_h[item] = -h;
+      if (mi) mi[item] = -h - ent / (float)n_mc;
+    }
+  }
+}
+
+}  // namespace runia
+
+extern "C" int runia_pred_uncertainty_f32(const float *logits, int64_t n_items, int n_mc, int C, float *pred_h, float *mi,
+                                          void *stream) {
+  RUNIA_REQUIRE(n_items >= 0 && n_mc >= 1 && C >= 1, RUNIA_E_BADARG, "pred_uncertainty: bad sizes");
+  RUNIA_REQUIRE(C <= 4096, RUNIA_E_UNSUPPORTED, "pred_uncertainty: C=%d > 4096", C);
+  if (n_items == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(logits && (pred_h || mi), RUNIA_E_BADARG, "pred_uncertainty: null pointer");
+  const size_t smem = C > 32 ? (size_t)8 * C * sizeof(float) : 0;
+  static bool attr = false;
+  if (!attr) {
+    RUNIA_CUDA(cudaFuncSetAttribute(runia::pred_uncertainty_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024));
+    attr = true;
+  }
+  runia::pred_uncertainty_kernel<<<(unsigned)runia::ceil_div(n_items, 8), 256, smem, (cudaStream_t)stream>>>(
+      logits, n_items, n_mc, C, pred_h, mi);
+  runia::count_launch();
+  return runia::finish_launch("pred_uncertainty");
+}

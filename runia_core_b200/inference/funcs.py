@@ -17,6 +17,7 @@ __all__ = [
     "ash_s_linear_layer",
     "gmm_fit",
     "generalized_entropy",
+    "get_predictive_uncertainty_score",
     "mahalanobis_preprocess",
     "mahalanobis_postprocess",
     "normalizer",
@@ -152,3 +153,24 @@ def generalized_entropy(probs, gamma, M):
         lg = np.log(p.astype(np.float64)).astype(np.float32)
     _, _, g, _ = _ops.logit_scores(lg, gamma=gamma, M=M, energy=False, msp=False, gen=True)
     return to_host(g).astype(p.dtype if p.dtype.kind == "f" else np.float32)
+
+
+def get_predictive_uncertainty_score(input_samples: torch.Tensor, mcd_nro_samples: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Predictive entropy and mutual information of MC-dropout logits (funcs.py:430-465):
+    input_samples [N * mcd_nro_samples, C] -> (pred_h [N], mi [N]) float32 tensors on the input's device.
+    One fused kernel (softmax, mean over the MC samples, both entropies) instead of five passes."""
+    assert input_samples.shape[0] % mcd_nro_samples == 0, (
+        "Input tensor first dimension must be " "divisible by the mcd_nro_samples"
+    )
+    from .. import _lib
+    from .._device import stream_ptr
+
+    x = to_device(input_samples, torch.float32)
+    n_items, C = x.shape[0] // int(mcd_nro_samples), x.shape[1]
+    pred_h = torch.empty((n_items,), dtype=torch.float32, device=x.device)
+    mi = torch.empty((n_items,), dtype=torch.float32, device=x.device)
+    _lib.call("runia_pred_uncertainty_f32", x.data_ptr(), n_items, int(mcd_nro_samples), C, pred_h.data_ptr(),
+              mi.data_ptr(), stream_ptr())
+    if isinstance(input_samples, torch.Tensor) and not input_samples.is_cuda:
+        return pred_h.cpu(), mi.cpu()
+    return pred_h, mi

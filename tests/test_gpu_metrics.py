@@ -107,3 +107,32 @@ def test_eigen_score_kat_and_config5():
         assert abs(eigen_score(hs2, alpha=alpha) - O.eigen_score(E, alpha)) < 1e-9
     E32 = rng.randn(32, 64).astype(np.float32)
     assert abs(eigen_score(((None,) * 15 + (torch.from_numpy(E32),),), 1e-3) - O.eigen_score(E32, 1e-3)) < 1e-9
+
+
+@pytest.mark.parametrize("C,n_mc", [(10, 16), (3, 5), (32, 2), (100, 8), (1000, 4)])
+def test_predictive_uncertainty_vs_reference_formula(C, n_mc):
+    """get_predictive_uncertainty_score against the torch expression of funcs.py:448-463 evaluated on the
+    same device tensor (and the NumPy oracle), including the NaN upstream produces when a probability
+    underflows to 0."""
+    from runia_core_b200.inference.funcs import get_predictive_uncertainty_score
+
+    g = torch.Generator(device="cuda").manual_seed(C * 100 + n_mc)
+    n_items = 2049
+    x = 3.0 * torch.randn(n_items * n_mc, C, generator=g, device="cuda")
+    x[7 * n_mc, 0] = 200.0  # softmax underflow -> 0 * log 0 = NaN upstream
+    ph, mi = get_predictive_uncertainty_score(x, n_mc)
+    sm = torch.softmax(x, dim=1)
+    st = torch.stack(torch.split(sm, n_mc))
+    ep = st.mean(1)
+    rph = -(ep * torch.log(ep)).sum(1)
+    rmi = rph - (-(st * torch.log(st)).sum(-1)).mean(1)
+    ok = torch.isfinite(rph) & torch.isfinite(rmi)
+    assert ph.shape == (n_items,) and ph.dtype == torch.float32 and ph.is_cuda
+    assert bool(torch.isnan(ph[7]) or torch.isnan(mi[7])) == bool(~ok[7])
+    assert torch.allclose(ph[ok], rph[ok], rtol=1e-4, atol=1e-5) and torch.allclose(mi[ok], rmi[ok], rtol=1e-4, atol=2e-5)
+    oh, om = O.predictive_uncertainty(x.cpu().numpy(), n_mc)
+    okn = ok.cpu().numpy()
+    assert np.allclose(ph.cpu().numpy()[okn], oh[okn], rtol=1e-4, atol=1e-5)
+    assert np.allclose(mi.cpu().numpy()[okn], om[okn], rtol=1e-4, atol=2e-5)
+    ph_c, mi_c = get_predictive_uncertainty_score(x.cpu(), n_mc)
+    assert not ph_c.is_cuda and torch.equal(ph_c[okn], ph.cpu()[okn])
