@@ -112,7 +112,7 @@ def pca_transform(x, st: PCAState) -> torch.Tensor:
     n = xf.shape[0]
     z = _empty((n, st.d), torch.float32)
     mean = None if centered else ptr(st.mean_f32)
-    if _tc_ok(st.D0) and st.planes is not None:
+    if _tc_ok(st.D0) and st.planes is not None and st.d % 4 == 0:
         _lib.call("runia_pca_transform_tc", xf.data_ptr(), n, st.D0, mean, st.planes[0].data_ptr(),
                   st.planes[1].data_ptr(), st.d, ptr(st.inv_scale), z.data_ptr(), stream_ptr())
     else:

@@ -52,6 +52,7 @@ constexpr int A_PLANE_BYTES = TM * TK * 4;  // 16 KB
 constexpr int B_PLANE_BYTES = TNH * TK * 4;  // 16 KB (this CTA's half of the panel)
 constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;  // 64 KB
 constexpr int SMEM_BAR_BYTES = 256;
+constexpr int EPI_STAGE_BYTES = 4 * 4096;  // one 32 x 32 fp32 sub-tile per epilogue warp (TMA-store staging)
 constexpr int SMEM_ALIGN = 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -222,6 +223,7 @@ struct Work {
 };
 
 // The epilogue policy E provides:
+//   __device__ void set_stage(uint32_t smem)                     -- this warp's 4 KB staging buffer (once)
 //   __device__ void begin(int row_in_tile, int64_t row)          -- once per thread per row tile
 //   __device__ void consume(int64_t col0, const float (&v)[32], int warp_in_epi, int lane)
 //       32 consecutive columns col0.. of this thread's row
@@ -236,7 +238,8 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
   // carve shared memory (1024-byte aligned for the 128B swizzle); identical offsets in both CTAs
   const uint32_t base = (smem_u32(smem_raw) + SMEM_ALIGN - 1) & ~(uint32_t)(SMEM_ALIGN - 1);
   unsigned char *gbase = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar0 = base + STAGES * STAGE_BYTES;
+  const uint32_t epi_stage0 = base + STAGES * STAGE_BYTES;  // 1024-byte aligned (128B-swizzled boxes)
+  const uint32_t bar0 = epi_stage0 + EPI_STAGE_BYTES;
   auto sA_hi = [&](int s) { return base + s * STAGE_BYTES; };
   auto sA_lo = [&](int s) { return base + s * STAGE_BYTES + A_PLANE_BYTES; };
   auto sB_hi = [&](int s) { return base + s * STAGE_BYTES + 2 * A_PLANE_BYTES; };
@@ -247,9 +250,9 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
   auto tempty_bar = [&](int b) { return bar0 + 8 * (2 * STAGES + 2 + b); }; // used in the leader only
   auto raw_bar = [&](int s) { return bar0 + 8 * (2 * STAGES + 4 + s); };    // one per CTA: raw A tile landed
   const uint32_t tmem_slot = bar0 + 8 * (3 * STAGES + 4);
-  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(gbase + STAGES * STAGE_BYTES + 8 * (3 * STAGES + 4));
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(gbase + STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 8 * (3 * STAGES + 4));
   const uint32_t sub_smem = bar0 + SMEM_BAR_BYTES;  // [nkb * TK] floats: the centre, zero-padded
-  float *sub_ptr = reinterpret_cast<float *>(gbase + STAGES * STAGE_BYTES + SMEM_BAR_BYTES);
+  float *sub_ptr = reinterpret_cast<float *>(gbase + STAGES * STAGE_BYTES + EPI_STAGE_BYTES + SMEM_BAR_BYTES);
 
   const int nkb = (K + TK - 1) / TK;
   const int n_panels = work.panel_hi - work.panel_lo;
@@ -341,6 +344,7 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
     const int ew = warp - 4;  // == warp % 4: TMEM lane quadrant this warp may read
     const int row_in_tile = ew * 32 + lane;
     int pc = 0;
+    epi.set_stage(epi_stage0 + (uint32_t)ew * 4096u);
     for (int64_t t = work.tile_first; t < work.tile_end; t += work.tile_step) {
     epi.begin(row_in_tile, t * TM2 + (int64_t)rank * TM + row_in_tile);
     for (int p = 0; p < n_panels; ++p, ++pc) {
@@ -429,7 +433,7 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
 
 // dynamic shared memory: stages + barriers + the zero-padded centre [ceil(K / TK) * TK floats] + alignment slack
 static inline size_t smem_bytes(int K) {
-  return (size_t)STAGES * STAGE_BYTES + SMEM_BAR_BYTES + (size_t)((K + TK - 1) / TK) * TK * 4 + SMEM_ALIGN;
+  return (size_t)STAGES * STAGE_BYTES + EPI_STAGE_BYTES + SMEM_BAR_BYTES + (size_t)((K + TK - 1) / TK) * TK * 4 + SMEM_ALIGN;
 }
 constexpr int kMaxK = 4096;  // keeps the centre within the shared-memory budget
 

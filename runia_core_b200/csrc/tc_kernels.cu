@@ -39,6 +39,8 @@ struct RowNormEpi {  // MD: -sum sign*v^2 ; ViM: -alpha*sqrt(sum v^2) + lse(logi
   int64_t M;
   int64_t row;
   float acc;
+  __device__ void set_stage(uint32_t) {}
+  template <class P> __device__ void bind(const P *) {}
   __device__ void begin(int, int64_t row_) {
     row = row_;
     acc = 0.f;
@@ -74,34 +76,56 @@ struct RowNormEpi {  // MD: -sum sign*v^2 ; ViM: -alpha*sqrt(sum v^2) + lse(logi
   }
 };
 
-struct PcaEpi {  // Z[row, col] = v * inv_scale[col]
+struct PcaEpi {  // Z[row, col] = v * inv_scale[col], written with TMA stores (full 128-byte lines, clipped at the edges)
+  alignas(64) CUtensorMap tmZ;  // [N, d] fp32, box 32 x 32, 128B swizzle
   const float *inv_scale;
-  float *Z;
   int d;
   int64_t M;
+  const CUtensorMap *mapZ;
+  uint32_t stage;
   int64_t row;
+  bool pending;
+  __device__ void set_stage(uint32_t smem) {
+    stage = smem;
+    pending = false;
+  }
+  template <class P>
+  __device__ void bind(const P *param) { mapZ = &param->tmZ; }
   __device__ void begin(int, int64_t row_) { row = row_; }
-  __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
-    if (row >= M) return;
-    float *z = Z + row * (int64_t)d + col0;
-    if (col0 + 31 < d && (d % 4 == 0)) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 o;
-        o.x = v[j + 0] * (inv_scale ? __ldg(inv_scale + col0 + j + 0) : 1.f);
-        o.y = v[j + 1] * (inv_scale ? __ldg(inv_scale + col0 + j + 1) : 1.f);
-        o.z = v[j + 2] * (inv_scale ? __ldg(inv_scale + col0 + j + 2) : 1.f);
-        o.w = v[j + 3] * (inv_scale ? __ldg(inv_scale + col0 + j + 3) : 1.f);
-        *reinterpret_cast<float4 *>(z + j) = o;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < d) z[j] = v[j] * (inv_scale ? __ldg(inv_scale + col0 + j) : 1.f);
+  __device__ void consume(int64_t col0, const float (&v)[32], int, int lane) {
+    const int64_t row0 = row - lane;  // warp-uniform
+    if (row0 >= M || col0 >= d) return;
+    if (pending) {  // the previous box must have been read out of the staging buffer
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
     }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float4 o;
+      const int j = 4 * c;
+      o.x = v[j + 0] * ((inv_scale && col0 + j + 0 < d) ? __ldg(inv_scale + col0 + j + 0) : 1.f);
+      o.y = v[j + 1] * ((inv_scale && col0 + j + 1 < d) ? __ldg(inv_scale + col0 + j + 1) : 1.f);
+      o.z = v[j + 2] * ((inv_scale && col0 + j + 2 < d) ? __ldg(inv_scale + col0 + j + 2) : 1.f);
+      o.w = v[j + 3] * ((inv_scale && col0 + j + 3 < d) ? __ldg(inv_scale + col0 + j + 3) : 1.f);
+      const uint32_t addr = stage + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(mapZ),
+                   "r"((int)col0), "r"((int)row0), "r"(stage)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    pending = true;
   }
   __device__ void panel_done(int) {}
-  __device__ void finish() {}
+  __device__ void finish() {  // the staging buffer must outlive the last store's read (tile end / kernel exit)
+    if (pending && (threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    pending = false;
+  }
 };
 
 // (a6) class-conditional Mahalanobis: out = max_c -sum_j sign_j (y_j - m_cj)^2 over the classes that
@@ -116,6 +140,8 @@ struct ClassCondEpi {
   int64_t M;
   int64_t row;
   float cls[kClassMax];
+  __device__ void set_stage(uint32_t) {}
+  template <class P> __device__ void bind(const P *) {}
   __device__ void begin(int, int64_t row_) {
     row = row_;
 #pragma unroll
@@ -176,6 +202,8 @@ struct GmmEpi {
   int64_t M;
   int64_t row;
   float acc, run_m, run_s;
+  __device__ void set_stage(uint32_t) {}
+  template <class P> __device__ void bind(const P *) {}
   __device__ void begin(int, int64_t row_) {
     row = row_;
     acc = 0.f;
@@ -218,6 +246,8 @@ struct KdeEpi {  // online log-sum-exp of -|q-b|^2/(2h^2) in log2 units
   int splits, split;
   int64_t row;
   float q2, m, s;
+  __device__ void set_stage(uint32_t) {}
+  template <class P> __device__ void bind(const P *) {}
   __device__ void begin(int, int64_t row_) {
     row = row_;
     q2 = row < Nq ? __ldg(qn + row) : 0.f;
@@ -282,6 +312,8 @@ struct KnnEpi {
   float q2, thr;
   int cnt;
   bool live;
+  __device__ void set_stage(uint32_t) {}
+  template <class P> __device__ void bind(const P *) {}
   __device__ void begin(int, int64_t row_) {
     row = row_;
     live = row < Nq;
@@ -418,6 +450,8 @@ struct KnnSeedEpi {
   float q2, m0, m1, m2, m3, bound;
   int in_group;
   bool live;
+  __device__ void set_stage(uint32_t) {}
+  template <class P> __device__ void bind(const P *) {}
   __device__ void begin(int, int64_t row_) {
     row = row_;
     live = row < Nq;
@@ -478,8 +512,10 @@ tc_knn_seed_kernel(const __grid_constant__ CUtensorMap tmA, int K, const __grid_
 template <class E>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmA, int64_t M, int K, Prologue pro, const __grid_constant__ CUtensorMap tmB_hi,
-          const __grid_constant__ CUtensorMap tmB_lo, int panels_total, E epi) {
+          const __grid_constant__ CUtensorMap tmB_lo, int panels_total, const __grid_constant__ E epi_param) {
   extern __shared__ unsigned char smem_raw[];
+  E epi = epi_param;
+  epi.bind(&epi_param);  // policies that own a tensor map need its address in parameter space
   Work w;  // persistent: CTA pair p takes the 256-row tiles p, p + #pairs, ...
   w.tile_first = blockIdx.x >> 1;
   w.tile_end = (M + TM2 - 1) / TM2;
@@ -577,7 +613,7 @@ static int make_b_map(CUtensorMap *map, const float *ptr, int64_t rows, int K) {
 // streamed operand: box of TM rows x 32 floats, lands in the A_hi plane of a stage as raw fp32
 static int make_a_map(CUtensorMap *map, const float *ptr, int64_t rows, int K) { return make_map(map, ptr, rows, K, TM); }
 
-constexpr size_t kSmemMax = (size_t)STAGES * STAGE_BYTES + SMEM_BAR_BYTES + (size_t)kMaxK * 4 + SMEM_ALIGN;
+constexpr size_t kSmemMax = (size_t)STAGES * STAGE_BYTES + EPI_STAGE_BYTES + SMEM_BAR_BYTES + (size_t)kMaxK * 4 + SMEM_ALIGN;
 
 template <class Kern>
 static int set_smem(Kern kern, size_t bytes) {
@@ -648,8 +684,8 @@ extern "C" int runia_pca_transform_tc(const float *X, int64_t N, int D0, const f
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(X && C_hi && C_lo && Z, RUNIA_E_BADARG, "pca_transform_tc: null pointer");
   RUNIA_REQUIRE(usable(X, D0, C_hi, C_lo) && (!mean || (reinterpret_cast<uintptr_t>(mean) & 15) == 0) &&
-                    (reinterpret_cast<uintptr_t>(Z) & 15) == 0,
-                RUNIA_E_UNSUPPORTED, "pca_transform_tc: needs D0 %% 4 == 0 and 16-byte aligned pointers");
+                    (reinterpret_cast<uintptr_t>(Z) & 15) == 0 && d % 4 == 0,
+                RUNIA_E_UNSUPPORTED, "pca_transform_tc: needs D0 %% 4 == 0, d %% 4 == 0 and 16-byte aligned pointers");
   CUtensorMap ma, mh, ml;
   int rc = make_a_map(&ma, X, N, D0);
   if (rc) return rc;
@@ -663,7 +699,10 @@ extern "C" int runia_pca_transform_tc(const float *X, int64_t N, int D0, const f
     if (rc) return rc;
     attr = true;
   }
-  PcaEpi epi{inv_scale, Z, d, N, 0};
+  PcaEpi epi{};
+  rc = make_map(&epi.tmZ, Z, N, d, 32);
+  if (rc) return rc;
+  epi.inv_scale = inv_scale; epi.d = d; epi.M = N;
   const int panels = (int)ceil_div(d, TN);
   dim3 grid(2 * (unsigned)std::min<int64_t>(ceil_div(N, TM2), kNumSMs / 2), 1);
   tc_kernel<PcaEpi><<<grid, THREADS, smem_bytes(D0), (cudaStream_t)stream>>>(ma, N, D0, Prologue{mean, INFINITY}, mh, ml,

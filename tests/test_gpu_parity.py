@@ -350,3 +350,18 @@ def test_ash_react_heads_vs_oracle(R, d, pct):
     assert rel_err(got, O.react_score(x, W, b, thr)) < RTOL
     got = _ops.clip_linear_lse(x[:1], Wd, bd).cpu().numpy()  # odd row count, no clip
     assert rel_err(got, O.react_score(x[:1], W, b, np.inf)) < RTOL
+
+
+@pytest.mark.parametrize("D", [1024, 100, 36, 30])
+def test_entropy_widths_vs_oracle(R, D):
+    """entropy16_kernel at the RoI width of configs[2] (1024), at widths that end inside a 64-dimension
+    step (100, 36) and at a width that falls back to the warp-per-item kernel (30: D % 4 != 0)."""
+    rng = np.random.RandomState(D)
+    n_items, n_mc = 257, 16
+    z = (rng.randn(n_items, 1, D) + 0.2 * rng.randn(n_items, n_mc, D)).astype(np.float32)
+    z[rng.rand(n_items, n_mc, D) < 0.3] = 0.0
+    z = z.reshape(-1, D)
+    hm, hz = R.evaluation.get_dl_h_z(z, n_mc)
+    rm, rz = O.get_dl_h_z(z, n_mc, chunk=32)
+    assert hz.shape == (n_items, D) and hm.shape == (n_items, 1)
+    assert rel_err(hz, rz) < RTOL and rel_err(hm, rm) < RTOL
