@@ -202,12 +202,14 @@ __device__ __forceinline__ void sort16(float (&v)[16]) {
 #undef RUNIA_CE
 
 constexpr int E16_WARPS = 4;
-constexpr int E16_RING = 3;
+constexpr int E16_RING = 2;
 constexpr int E16_STEP_FLOATS = 16 * 64;                                    // one step: 16 samples x 64 dims
-constexpr int E16_WARP_FLOATS = E16_RING * E16_STEP_FLOATS + 16 * 16;       // ring + Chebyshev matrix
+constexpr int E16_NREG = 60;                                                // pair maxima kept in registers
+constexpr int E16_NSM = 120 - E16_NREG;                                     // pair maxima kept in shared memory ([q][lane] float4)
+constexpr int E16_WARP_FLOATS = E16_RING * E16_STEP_FLOATS + 16 * 16 + E16_NSM * 32;  // ring + Chebyshev matrix + maxima
 constexpr size_t kEntropy16Smem = (size_t)E16_WARPS * E16_WARP_FLOATS * sizeof(float);
 
-__global__ void __launch_bounds__(E16_WARPS * 32, 2)
+__global__ void __launch_bounds__(E16_WARPS * 32, 3)
 entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_dist, double c_term,
                  double *__restrict__ h_z, double *__restrict__ h_mvn) {
   constexpr int N = 16, K = 5, NPAIR = N * (N - 1) / 2;
@@ -215,6 +217,7 @@ entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float *ring = smem + (size_t)warp * E16_WARP_FLOATS;
   float *dm = ring + E16_RING * E16_STEP_FLOATS;
+  float4 *pms = reinterpret_cast<float4 *>(dm + 16 * 16) + lane;  // this lane's maxima: pms[32 * q], q < E16_NSM / 4
   const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
   const int64_t gw = (int64_t)blockIdx.x * E16_WARPS + warp;  // this warp's first item
   const int64_t GW = (int64_t)gridDim.x * E16_WARPS;          // item stride
@@ -250,16 +253,18 @@ entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   issue();
-  issue();
 
   int buf = 0;
   for (int64_t item = gw; item < n_items; item += GW) {
-    float pm[NPAIR];
+    // half of the 120 maxima live in registers, half in shared memory: 168 registers -> 12 resident warps
+    float pm[E16_NREG];
 #pragma unroll
-    for (int p = 0; p < NPAIR; ++p) pm[p] = 0.f;
+    for (int p = 0; p < E16_NREG; ++p) pm[p] = 0.f;
+#pragma unroll
+    for (int q = 0; q < E16_NSM / 4; ++q) pms[32 * q] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
     for (int jstep = 0; jstep < spi; ++jstep) {
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
       float2 x[N];
       {
@@ -272,12 +277,23 @@ entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_
       const int j = jstep * 32 + lane;  // float2 column: dimensions 2j, 2j+1
       {
         int p = 0;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int a = 0; a < N; ++a)
 #pragma unroll
           for (int b = a + 1; b < N; ++b) {
             const float2 d = sub2(x[a], x[b]);
-            pm[p] = fmaxf(fmaxf(pm[p], fabsf(d.x)), fabsf(d.y));
+            if (p < E16_NREG) {
+              pm[p] = fmaxf(fmaxf(pm[p], fabsf(d.x)), fabsf(d.y));
+            } else {
+              const int q = (p - E16_NREG) >> 2, c = (p - E16_NREG) & 3;
+              if (c == 0) t = pms[32 * q];
+              if (c == 0) t.x = fmaxf(fmaxf(t.x, fabsf(d.x)), fabsf(d.y));
+              if (c == 1) t.y = fmaxf(fmaxf(t.y, fabsf(d.x)), fabsf(d.y));
+              if (c == 2) t.z = fmaxf(fmaxf(t.z, fabsf(d.x)), fabsf(d.y));
+              if (c == 3) t.w = fmaxf(fmaxf(t.w, fabsf(d.x)), fabsf(d.y));
+              if (c == 3) pms[32 * q] = t;
+            }
             ++p;
           }
       }
@@ -338,7 +354,15 @@ entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_
         if (lane == 0) dm[a * N + a] = 0.f;
 #pragma unroll
         for (int b = a + 1; b < N; ++b) {
-          const float m = warp_max_f32(pm[p]);
+          float mine;
+          if (p < E16_NREG) {
+            mine = pm[p];
+          } else {
+            const float4 t = pms[32 * ((p - E16_NREG) >> 2)];
+            const int c = (p - E16_NREG) & 3;
+            mine = c == 0 ? t.x : c == 1 ? t.y : c == 2 ? t.z : t.w;
+          }
+          const float m = warp_max_f32(mine);
           if (lane == 0) {
             dm[a * N + b] = m;
             dm[b * N + a] = m;
@@ -456,7 +480,7 @@ extern "C" int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, 
       attr16 = true;
     }
     // persistent warps: two CTAs of four warps per SM (register-limited), items round-robin over warps
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n_items, E16_WARPS), (int64_t)2 * kNumSMs);
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n_items, E16_WARPS), (int64_t)3 * kNumSMs);
     entropy16_kernel<<<grid, E16_WARPS * 32, kEntropy16Smem, st>>>(z, n_items, D, (float)min_dist, digamma_term, h_z,
                                                                    h_mvn);
     count_launch();
