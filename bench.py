@@ -255,6 +255,8 @@ def run_b200(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu_baseline = _cpu_larem(md, seconds=args.cpu_seconds)
+        if not args.no_extra:
+            extra["cpu_baselines"] = _cpu_other_rows()
 
     if rank == 0:
         line = {
@@ -554,6 +556,37 @@ def _cpu_larem(md, seconds=8.0):
     dt = time.perf_counter() - t0
     return {"value": n * 10_000 / dt, "unit": "embeddings/s", "cores": int(threads), "kind": "port",
             "sample": f"{n} calls x 10,000 rows x d=256 of MDLatentSpace.postprocess (N x N form), {dt:.1f} s"}
+
+
+def _cpu_other_rows():
+    """The reference's CPU path for the other measured rows (oracle ports with the reference's loop
+    structure), on bounded samples of the same shapes, all host threads: entropy (one estimator call
+    per item and per (item, dimension), evaluation/entropy.py:56-84), kNN (one brute-force search per
+    query, postprocessors.py:417-421), metrics (torchmetrics / sklearn restatement)."""
+    from oracle import oracle_np as O
+
+    threads = _all_host_threads()
+    rng = np.random.RandomState(9)
+    out = {"cores": int(threads), "kind": "port"}
+    n_items, n_mc, D = 12, 16, 512
+    z = (rng.randn(n_items, 1, D) + 0.1 * rng.randn(n_items, n_mc, D)).astype(np.float32).reshape(-1, D)
+    t0 = time.perf_counter()
+    O.get_dl_h_z_faithful(z, n_mc)
+    dt = time.perf_counter() - t0
+    out["entropy_config1"] = {"items_per_s": n_items / dt, "sample": f"{n_items} items x 16 x 512, {dt:.1f} s (single-threaded Python loops upstream)"}
+    bank = O.normalize_rows_exact(rng.randn(50_000, 512).astype(np.float32))
+    q = rng.randn(40, 512).astype(np.float32)
+    t0 = time.perf_counter()
+    O.knn_score_faithful(q, bank, 50)
+    dt = time.perf_counter() - t0
+    out["knn_config2"] = {"queries_per_s": len(q) / dt, "sample": f"{len(q)} queries x 50k x 512 bank, {dt:.1f} s"}
+    n = 1_000_000
+    ind, ood = 0.5 + rng.randn(n).astype(np.float32), -0.5 + rng.randn(n).astype(np.float32)
+    t0 = time.perf_counter()
+    O.ood_metrics(ind, ood)
+    dt = time.perf_counter() - t0
+    out["metrics_f32"] = {"scores_per_s": 2 * n / dt, "sample": f"2 x {n} scores, {dt:.1f} s"}
+    return out
 
 
 def run_reference(args):

@@ -12,7 +12,7 @@ from runia_core_b200 import _ops  # noqa: E402
 which = set(sys.argv[1:]) or {"larem", "entropy", "knn", "pca"}
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(0)
-REPS = 3
+REPS = 2
 
 if "larem" in which:
     rng = np.random.RandomState(1)
@@ -66,5 +66,11 @@ if "logits" in which:
     L = torch.randn(20_000_000, 10, generator=g, device=dev)
     for _ in range(REPS):
         o = _ops.logit_scores(L)
+    torch.cuda.synchronize()
+if "metrics" in which:
+    si = torch.sigmoid(0.5 + torch.randn(10_000_000, generator=g, device=dev))
+    so = torch.sigmoid(-0.5 + torch.randn(10_000_000, generator=g, device=dev))
+    for _ in range(2):
+        m = _ops.ood_metrics(si, so, want_curve=False)
     torch.cuda.synchronize()
 print("done")
