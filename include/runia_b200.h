@@ -251,6 +251,13 @@ int runia_eigen_score_f32(const float *E, int n, int d, double alpha, double *ou
 int runia_pred_uncertainty_f32(const float *logits, int64_t n_items, int n_mc, int C, float *pred_h, float *mi,
                                void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (f3) Spatial reduction of convolutional activation maps -- feature_extraction/utils.py:70-92
+ * (`get_mean_or_fullmean_ls_sample`), the reducer that produces the rows `get_dl_h_z` consumes.
+ *   x [P, H, W] float32 (P = batch * channels);  fullmean != 0: out [P];  fullmean == 0 ("mean"): out [P, H].
+ */
+int runia_spatial_mean_f32(const float *x, int64_t P, int H, int W, int fullmean, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,11 +12,11 @@ import the reference's paths."""
 import sys as _sys
 
 from . import _lib  # noqa: F401  (fails loudly when libruniab200.so is missing)
-from . import dimensionality_reduction, evaluation, inference, llm_uncertainty
+from . import dimensionality_reduction, evaluation, feature_extraction, inference, llm_uncertainty
 from .dimensionality_reduction import *  # noqa: F401,F403
 
 __version__ = "0.1.0"
-__all__ = ["evaluation", "inference", "llm_uncertainty", "install_as_runia_core"]
+__all__ = ["evaluation", "feature_extraction", "inference", "llm_uncertainty", "install_as_runia_core"]
 __all__ += dimensionality_reduction.__all__
 
 

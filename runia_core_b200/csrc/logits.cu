@@ -735,3 +735,58 @@ extern "C" int runia_pred_uncertainty_f32(const float *logits, int64_t n_items, 
   runia::count_launch();
   return runia::finish_launch("pred_uncertainty");
 }
+
+// ------------------------------------------------------------------------------------------
+// (f3) spatial reduction of convolutional activation maps feeding the entropy path --
+// feature_extraction/utils.py:70-92 (`get_mean_or_fullmean_ls_sample`): x [P, H, W] (P = batch * channels)
+//   fullmean: out[p] = mean_h mean_w x[p, h, w];   mean: out[p, h] = mean_w x[p, h, w].
+// One warp per plane (fullmean) or per row group (mean); every byte is read once, coalesced.
+// ------------------------------------------------------------------------------------------
+namespace runia {
+
+__global__ void __launch_bounds__(256) spatial_mean_kernel(const float *__restrict__ x, int64_t P, int H, int W, int full,
+                                                           float *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * 8;
+  if (full) {
+    const int hw = H * W;
+    const float inv_w = 1.f / (float)W, inv_h = 1.f / (float)H;
+    for (int64_t p = wid; p < P; p += nw) {
+      const float *src = x + p * hw;
+      float s = 0.f;
+      for (int e = lane; e < hw; e += 32) s += __ldg(src + e);
+      s = warp_sum32(s);
+      if (lane == 0) out[p] = (s * inv_w) * inv_h;
+    }
+  } else {
+    const int64_t rows = P * H;
+    const float inv_w = 1.f / (float)W;
+    if (W <= 32) {  // several rows per warp pass: lane l reads element l of a 32-float window, rows resolved per lane
+      for (int64_t r = wid; r < rows; r += nw) {
+        const float v = lane < W ? __ldg(x + r * W + lane) : 0.f;
+        const float s = warp_sum32(v);
+        if (lane == 0) out[r] = s * inv_w;
+      }
+    } else {
+      for (int64_t r = wid; r < rows; r += nw) {
+        float s = 0.f;
+        for (int e = lane; e < W; e += 32) s += __ldg(x + r * W + e);
+        s = warp_sum32(s);
+        if (lane == 0) out[r] = s * inv_w;
+      }
+    }
+  }
+}
+
+}  // namespace runia
+
+extern "C" int runia_spatial_mean_f32(const float *x, int64_t P, int H, int W, int fullmean, float *out, void *stream) {
+  RUNIA_REQUIRE(P >= 0 && H > 0 && W > 0, RUNIA_E_BADARG, "spatial_mean: bad sizes");
+  if (P == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(x && out, RUNIA_E_BADARG, "spatial_mean: null pointer");
+  const int64_t units = fullmean ? P : P * H;
+  const unsigned grid = (unsigned)std::min<int64_t>(runia::ceil_div(units, 8), (int64_t)runia::kNumSMs * 16);
+  runia::spatial_mean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, P, H, W, fullmean, out);
+  runia::count_launch();
+  return runia::finish_launch("spatial_mean");
+}

@@ -144,17 +144,42 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint64_t *__r
   hist[(int64_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];  // bin-major: one scan gives global offsets
 }
 
+// lanes of `vm` that hold the same 8-bit digit as this lane: eight ballots (VOTE is far cheaper than
+// MATCH.ANY, which made the scatter ADU-bound: ncu sm__throughput 75 % at 16 % issue)
+__device__ __forceinline__ unsigned same_digit_mask(unsigned vm, uint32_t d) {
+  unsigned peers = vm;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool bit = (d >> b) & 1u;
+    const unsigned bal = __ballot_sync(vm, bit);
+    peers &= bit ? bal : ~bal;
+  }
+  return peers;
+}
+
 // item order inside a tile: warp w owns items [512 w, 512 w + 512), round r of the warp covers 32
-// consecutive items -> ranks by (warp, round, lane) are the original order: the sort is stable
+// consecutive items -> ranks by (warp, round, lane) are the original order: the sort is stable.
+// The tile is first sorted by digit in shared memory, so that the global writes of a digit are one
+// contiguous run per tile (coalesced) instead of 4096 scattered 12-byte stores.
+constexpr size_t kScatterSmem = (size_t)RS_TILE * 12 + (size_t)(RS_WARPS + 2) * 256 * 4 + 64;
+
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, int64_t n, int shift,
                   const uint32_t *__restrict__ offsets, int64_t nblk, uint64_t *__restrict__ keys_out,
                   uint32_t *__restrict__ vals_out) {
-  __shared__ uint32_t cnt[RS_WARPS][256];
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  uint64_t *skey = reinterpret_cast<uint64_t *>(rs_smem);                       // [RS_TILE]
+  uint32_t *sval = reinterpret_cast<uint32_t *>(rs_smem + (size_t)RS_TILE * 8); // [RS_TILE]
+  uint32_t(*cnt)[256] = reinterpret_cast<uint32_t(*)[256]>(rs_smem + (size_t)RS_TILE * 12);  // [RS_WARPS][256]
+  uint32_t *tile_base = &cnt[0][0] + RS_WARPS * 256;  // [256] first slot of each digit in the sorted tile
+  uint32_t *gofs = tile_base + 256;                   // [256] global offset of that slot
+  uint32_t *ws = gofs + 256;                          // scan scratch
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int e = threadIdx.x; e < RS_WARPS * 256; e += RS_THREADS) (&cnt[0][0])[e] = 0;
   __syncthreads();
-  const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (32 * RS_ROUNDS);
+  const int64_t tbase = (int64_t)blockIdx.x * RS_TILE;
+  const int64_t wbase = tbase + (int64_t)warp * (32 * RS_ROUNDS);
+  const int tile_n = (int)((n - tbase < RS_TILE) ? (n - tbase) : RS_TILE);
   uint64_t k[RS_ROUNDS];
   uint32_t v[RS_ROUNDS];
 #pragma unroll
@@ -170,38 +195,55 @@ rs_scatter_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict_
     const unsigned vm = __ballot_sync(0xffffffffu, valid);
     if (valid) {
       const uint32_t d = (uint32_t)(k[r] >> shift) & 255u;
-      const unsigned m = __match_any_sync(vm, d);
+      const unsigned m = same_digit_mask(vm, d);
       if ((m & ((1u << lane) - 1u)) == 0) cnt[warp][d] += __popc(m);  // one lane per distinct digit
     }
     __syncwarp();
   }
   __syncthreads();
-  // phase 2: thread = bin: exclusive scan over the warps, plus the global offset of (bin, block)
+  // phase 2: thread = digit: offsets of each warp inside the digit's run, the run's first slot in the
+  // sorted tile (exclusive scan over the digits) and its global offset
   {
-    uint32_t run = offsets[(int64_t)threadIdx.x * nblk + blockIdx.x];
+    uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
       const uint32_t c = cnt[w][threadIdx.x];
       cnt[w][threadIdx.x] = run;
       run += c;
     }
+    uint32_t total;
+    tile_base[threadIdx.x] = block_exclusive_scan_u32(run, ws, total);
+    gofs[threadIdx.x] = offsets[(int64_t)threadIdx.x * nblk + blockIdx.x];
   }
   __syncthreads();
-  // phase 3: rank and scatter
+  // phase 3: rank every item and place it in the sorted tile
 #pragma unroll
   for (int r = 0; r < RS_ROUNDS; ++r) {
     const bool valid = wbase + r * 32 + lane < n;
     const unsigned vm = __ballot_sync(0xffffffffu, valid);
     if (valid) {
       const uint32_t d = (uint32_t)(k[r] >> shift) & 255u;
-      const unsigned m = __match_any_sync(vm, d);
-      const uint32_t pos = cnt[warp][d] + __popc(m & ((1u << lane) - 1u));
-      keys_out[pos] = k[r];
-      vals_out[pos] = v[r];
+      const unsigned m = same_digit_mask(vm, d);
+      const uint32_t pos = tile_base[d] + cnt[warp][d] + __popc(m & ((1u << lane) - 1u));
+      skey[pos] = k[r];
+      sval[pos] = v[r];
       __syncwarp(vm);
       if ((m & ((1u << lane) - 1u)) == 0) cnt[warp][d] += __popc(m);
     }
     __syncwarp();
+  }
+  __syncthreads();
+  // phase 4: coalesced copy-out: slot i of the sorted tile belongs to digit d and goes to gofs[d] + (i - tile_base[d])
+#pragma unroll 4
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    const int i = r * RS_THREADS + threadIdx.x;
+    if (i < tile_n) {
+      const uint64_t kk = skey[i];
+      const uint32_t d = (uint32_t)(kk >> shift) & 255u;
+      const uint32_t pos = gofs[d] + ((uint32_t)i - tile_base[d]);
+      keys_out[pos] = kk;
+      vals_out[pos] = sval[i];
+    }
   }
 }
 
@@ -428,6 +470,11 @@ static int ood_metrics_impl(const T *ind, int64_t n_ind, const T *ood, int64_t n
   MetricsOut *mo = (MetricsOut *)(ws + L.mo);
   uint32_t *flag = (uint32_t *)(ws + L.flag);
 
+  static bool attr = false;
+  if (!attr) {
+    RUNIA_CUDA(cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmem));
+    attr = true;
+  }
   RUNIA_CUDA(cudaMemsetAsync(flag, 0, 4, st));
   const unsigned g1 = (unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSMs * 8);
   range_flag_kernel<T><<<g1, 256, 0, st>>>(ind, n_ind, ood, n_ood, flag);
@@ -441,7 +488,7 @@ static int ood_metrics_impl(const T *ind, int64_t n_ind, const T *ood, int64_t n
     scan_u32_partial_kernel<<<(unsigned)hist_nt, SC_THREADS, 0, st>>>(hist, hist_n, hist_tiles);
     scan_u32_tiles_kernel<<<1, SC_THREADS, 0, st>>>(hist_tiles, hist_nt);
     scan_u32_final_kernel<<<(unsigned)hist_nt, SC_THREADS, 0, st>>>(hist, hist_n, hist_tiles);
-    rs_scatter_kernel<<<(unsigned)nblk, RS_THREADS, 0, st>>>(ka, va, n, shift, hist, nblk, kb, vb);
+    rs_scatter_kernel<<<(unsigned)nblk, RS_THREADS, kScatterSmem, st>>>(ka, va, n, shift, hist, nblk, kb, vb);
     std::swap(ka, kb);
     std::swap(va, vb);
     launches += 5;

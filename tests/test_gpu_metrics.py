@@ -136,3 +136,21 @@ def test_predictive_uncertainty_vs_reference_formula(C, n_mc):
     assert np.allclose(mi.cpu().numpy()[okn], om[okn], rtol=1e-4, atol=2e-5)
     ph_c, mi_c = get_predictive_uncertainty_score(x.cpu(), n_mc)
     assert not ph_c.is_cuda and torch.equal(ph_c[okn], ph.cpu()[okn])
+
+
+@pytest.mark.parametrize("shape", [(64, 512, 7, 7), (3, 5, 1, 1), (16, 64, 32, 48), (2, 1, 9, 40)])
+def test_spatial_mean_vs_torch(shape):
+    """get_mean_or_fullmean_ls_sample against the torch expression of utils.py:82-92 (mean over W, then H)."""
+    from runia_core_b200.feature_extraction import get_mean_or_fullmean_ls_sample
+
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g, device="cuda") + 0.5
+    for method in ("fullmean", "mean"):
+        ref = torch.mean(x, dim=3, keepdim=True)
+        if method == "fullmean":
+            ref = torch.mean(ref, dim=2, keepdim=True)
+        ref = torch.squeeze(ref)
+        got = get_mean_or_fullmean_ls_sample(x, method)
+        assert got.shape == ref.shape and got.is_cuda
+        assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6)
+    assert not get_mean_or_fullmean_ls_sample(x.cpu(), "fullmean").is_cuda
