@@ -412,14 +412,23 @@ curve_final_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict
 }
 
 // out[0] = auroc, out[1] = fpr@95, out[2] = aupr, out[3] = number of ROC points (incl. the prepended origin)
-__global__ void metrics_finish_kernel(const MetricsOut *__restrict__ mo, const double *__restrict__ aupr_partial,
-                                      int64_t nblk, uint32_t P, uint32_t Nn, double *__restrict__ out) {
+__global__ void __launch_bounds__(256) metrics_finish_kernel(const MetricsOut *__restrict__ mo,
+                                                             const double *__restrict__ aupr_partial, int64_t nblk,
+                                                             uint32_t P, uint32_t Nn, double *__restrict__ out) {
+  __shared__ double red[256];
   double a = 0.0;
-  for (int64_t b = 0; b < nblk; ++b) a += aupr_partial[b];  // fixed order: deterministic
+  for (int64_t b = threadIdx.x; b < nblk; b += 256) a += aupr_partial[b];  // fixed partition and tree: deterministic
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
   out[0] = (P && Nn) ? (double)mo->auroc_num / (2.0 * (double)P * (double)Nn) : 0.0;
   const uint32_t fps95 = (uint32_t)(mo->first95 & 0xffffffffull);
   out[1] = (mo->first95 != ~0ull && Nn) ? (double)__fdiv_rn((float)fps95, (float)Nn) : 1.0;
-  out[2] = a;
+  out[2] = red[0];
   out[3] = (double)mo->n_points + 1.0;
 }
 
@@ -501,7 +510,7 @@ static int ood_metrics_impl(const T *ind, int64_t n_ind, const T *ood, int64_t n
   curve_tiles_kernel<<<1, CV_THREADS, 0, st>>>(tile_state, nt);
   curve_final_kernel<<<(unsigned)nt, CV_THREADS, 0, st>>>(ka, va, n, tile_state, (uint32_t)n_ind, (uint32_t)n_ood, mo,
                                                          aupr_partial, fpr_out, tpr_out);
-  metrics_finish_kernel<<<1, 1, 0, st>>>(mo, aupr_partial, nt, (uint32_t)n_ind, (uint32_t)n_ood, out4);
+  metrics_finish_kernel<<<1, 256, 0, st>>>(mo, aupr_partial, nt, (uint32_t)n_ind, (uint32_t)n_ood, out4);
   count_launch(launches + 4);
   return finish_launch("ood_metrics");
 }
