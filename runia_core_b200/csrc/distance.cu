@@ -281,8 +281,14 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerank
       float kd = INFINITY;
       int32_t ki = -1;
       if (c < n_s) {
-        ki = a.buf_i[p0 + c];  // the SIMT pass pads its lists with index -1
-        kd = a.buf_d[p0 + c];
+        if (a.counts) {  // tensor-core pass: interleaved (distance, index) pairs
+          const float2 e = reinterpret_cast<const float2 *>(a.buf_d)[p0 + c];
+          kd = e.x;
+          ki = __float_as_int(e.y);
+        } else {         // SIMT pass: separate arrays, lists padded with index -1
+          ki = a.buf_i[p0 + c];
+          kd = a.buf_d[p0 + c];
+        }
       }
       bool take = ki >= 0 && kd < thr;
       unsigned m = __ballot_sync(0xffffffffu, take);

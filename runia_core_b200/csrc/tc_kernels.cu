@@ -302,13 +302,12 @@ __device__ __forceinline__ float ord_val(uint32_t k) {
 struct KnnEpi {
   const float *qn, *bn;
   int64_t Nq, b_hi;
-  float *buf_d;
-  int32_t *buf_i;
+  float2 *buf;              // [Nq, splits, capp] entries (approximate distance, bank index as bits)
   int32_t *counts;          // [Nq, splits] entries left in each list
   int kcap, fin_max, capp, splits, split;
   const uint32_t *thr_key;  // [Nq] seed: order-preserving key of an upper bound on the kcap-th distance (0 = none)
   int64_t row;
-  size_t base;
+  float2 *mine;             // this row's list
   float q2, thr;
   int cnt;
   bool live;
@@ -324,26 +323,45 @@ struct KnnEpi {
       if (key != 0u && key < ord_key(INFINITY)) thr = ord_val(key);
     }
     cnt = 0;
-    base = ((size_t)row * splits + split) * (size_t)capp;
+    mine = buf + ((size_t)(live ? row : 0) * splits + split) * (size_t)capp;
   }
+  // The epilogue warp runs alone on its scheduler: every instruction of this loop is on the critical path
+  // of the TMEM hand-back, so a column costs one FFMA, one compare and (predicated) one address, one
+  // 8-byte store and one increment; the |b|^2 terms come as eight broadcast LDG.128.
   __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
     if (!live) return;
+    if (col0 + 32 <= b_hi) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int64_t col = col0 + j;
-      const float b2 = col < b_hi ? __ldg(bn + col) : 0.f;
-      const float dist = fmaf(-2.f, v[j], q2 + b2);
-      if (col < b_hi && dist < thr) {
-        buf_d[base + cnt] = dist;
-        buf_i[base + cnt] = (int32_t)col;
-        ++cnt;
+      for (int g = 0; g < 8; ++g) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bn + col0) + g);  // same address in every lane
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = 4 * g + u;
+          const float dist = fmaf(-2.f, v[j], q2 + bb[u]);
+          if (dist < thr) {
+            mine[cnt] = make_float2(dist, __int_as_float((int)col0 + j));
+            ++cnt;
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int64_t col = col0 + j;
+        if (col < b_hi) {
+          const float dist = fmaf(-2.f, v[j], q2 + __ldg(bn + col));
+          if (dist < thr) {
+            mine[cnt] = make_float2(dist, __int_as_float((int)col));
+            ++cnt;
+          }
+        }
       }
     }
   }
   // the entries were written by this thread: plain loads (its own stores are visible to it)
-  __device__ __forceinline__ float ld_d(int e) const { return buf_d[base + e]; }
-  __device__ __forceinline__ int32_t ld_i(int e) const { return buf_i[base + e]; }
-  static constexpr int SCAN = 32;  // independent loads in flight per scan step (one 128-byte line per lane)
+  __device__ __forceinline__ float ld_d(int e) const { return mine[e].x; }
+  static constexpr int SCAN = 32;  // independent loads in flight per scan step
   __device__ __forceinline__ int count_below(int n, uint32_t bound) const {
     int c = 0;
     for (int e0 = 0; e0 < n; e0 += SCAN) {
@@ -395,27 +413,22 @@ struct KnnEpi {
     if (ties) ties_left = kcap - count_below(n, lo);
     const uint32_t bound = ties ? lo : hi;
     int w = 0;
-    constexpr int CB = 16;  // compaction batch (value + index registers)
+    constexpr int CB = 16;  // compaction batch
     for (int e0 = 0; e0 < n; e0 += CB) {
-      float v[CB];
-      int32_t ix[CB];
+      float2 v[CB];
 #pragma unroll
-      for (int j = 0; j < CB; ++j) {
-        v[j] = (e0 + j < n) ? ld_d(e0 + j) : INFINITY;
-        ix[j] = (e0 + j < n) ? ld_i(e0 + j) : -1;
-      }
+      for (int j = 0; j < CB; ++j) v[j] = (e0 + j < n) ? mine[e0 + j] : make_float2(INFINITY, 0.f);
 #pragma unroll
       for (int j = 0; j < CB; ++j) {
         if (e0 + j >= n) continue;
-        const uint32_t k = ord_key(v[j]);
+        const uint32_t k = ord_key(v[j].x);
         bool keep = k < bound;
         if (ties && k == lo && ties_left > 0) {
           keep = true;
           --ties_left;
         }
         if (keep) {
-          buf_d[base + w] = v[j];
-          buf_i[base + w] = ix[j];
+          mine[w] = v[j];
           ++w;
         }
       }
@@ -430,7 +443,7 @@ struct KnnEpi {
   }
   __device__ void finish() {
     if (!live) return;
-    shrink(fin_max);  // no-op unless the list is longer than the re-rank kernel's merge scratch allows
+    shrink(fin_max);  // no-op unless the list is longer than the buffer guard allows
     counts[(size_t)row * splits + split] = cnt;
   }
 };
@@ -823,7 +836,8 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
   }
   KnnEpi epi{};
   epi.qn = qn; epi.bn = bn; epi.Nq = Nq; epi.b_hi = Nb;
-  epi.buf_d = buf_d; epi.buf_i = buf_i;
+  epi.buf = reinterpret_cast<float2 *>(buf_d);  // buf_d and buf_i are contiguous: one (distance, index) pair per entry
+  (void)buf_i;
   epi.counts = counts;
   epi.kcap = kcap; epi.fin_max = fin_max; epi.capp = capp; epi.splits = splits; epi.split = 0;
   epi.thr_key = seeded ? thr_key : nullptr;
