@@ -686,7 +686,8 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   RUNIA_REQUIRE(Nb < (int64_t)0x7fffffff, RUNIA_E_UNSUPPORTED, "knn_search: bank shard too large");
   if (Nq == 0) return RUNIA_OK;
   RUNIA_REQUIRE(Qn && Bn && Bn_sqnorm && status && workspace, RUNIA_E_BADARG, "knn_search: null pointer");
-  const bool tensor = Bn_hi && Bn_lo && tc::usable(Qn, d, Bn_hi, Bn_lo);
+  const bool tensor = Bn_hi && Bn_lo && tc::usable(Qn, d, Bn_hi, Bn_lo) &&
+                      (reinterpret_cast<uintptr_t>(Bn_sqnorm) & 15) == 0;  // the epilogue reads the norms as float4
   const KnnPlan plan = make_knn_plan(Nq, Nb, k, tensor);
   const KnnWorkspace w = knn_layout(Nq, plan);
   RUNIA_REQUIRE((size_t)workspace_bytes >= w.total, RUNIA_E_WORKSPACE, "knn_search: workspace %lld < %lld bytes",

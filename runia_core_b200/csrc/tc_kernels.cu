@@ -153,12 +153,21 @@ struct ClassCondEpi {
       if (c < C) {
         const float *mc = Mc + (size_t)c * r + col0;
         float acc = cls[c];
-        if (col0 + 31 < r) {
+        if (col0 + 31 < r && !sign) {  // positive-definite precision (the usual case): no sign plane
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 m4 = __ldg(reinterpret_cast<const float4 *>(mc + j));  // same address in every lane
-            float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (sign) s4 = __ldg(reinterpret_cast<const float4 *>(sign + col0 + j));
+            const float d0 = v[j] - m4.x, d1 = v[j + 1] - m4.y, d2 = v[j + 2] - m4.z, d3 = v[j + 3] - m4.w;
+            acc = fmaf(d0, d0, acc);
+            acc = fmaf(d1, d1, acc);
+            acc = fmaf(d2, d2, acc);
+            acc = fmaf(d3, d3, acc);
+          }
+        } else if (col0 + 31 < r) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 m4 = __ldg(reinterpret_cast<const float4 *>(mc + j));
+            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(sign + col0 + j));
             const float d0 = v[j] - m4.x, d1 = v[j + 1] - m4.y, d2 = v[j + 2] - m4.z, d3 = v[j + 3] - m4.w;
             acc = fmaf(s4.x * d0, d0, acc);
             acc = fmaf(s4.y * d1, d1, acc);
@@ -257,13 +266,27 @@ struct KdeEpi {  // online log-sum-exp of -|q-b|^2/(2h^2) in log2 units
   __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
     float t[32];
     float tmax = -INFINITY;
+    if (col0 + 32 <= b_hi) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int64_t col = col0 + j;
-      const float b2 = col < b_hi ? __ldg(bn + col) : 0.f;
-      const float dist = fmaxf(fmaf(-2.f, v[j], q2 + b2), 0.f);
-      t[j] = col < b_hi ? dist * scale : -INFINITY;
-      tmax = fmaxf(tmax, t[j]);
+      for (int g = 0; g < 8; ++g) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bn + col0) + g);  // same address in every lane
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = 4 * g + u;
+          t[j] = fmaxf(fmaf(-2.f, v[j], q2 + bb[u]), 0.f) * scale;
+          tmax = fmaxf(tmax, t[j]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int64_t col = col0 + j;
+        const float b2 = col < b_hi ? __ldg(bn + col) : 0.f;
+        const float dist = fmaxf(fmaf(-2.f, v[j], q2 + b2), 0.f);
+        t[j] = col < b_hi ? dist * scale : -INFINITY;
+        tmax = fmaxf(tmax, t[j]);
+      }
     }
     if (tmax == -INFINITY) return;
     const float m_new = fmaxf(m, tmax);
@@ -473,23 +496,35 @@ struct KnnSeedEpi {
     bound = -INFINITY;
     in_group = 0;
   }
+  __device__ __forceinline__ void insert(float t) {
+    if (t < m3) {  // rare after the first few columns of a group
+      float a = fminf(m0, t);
+      t = fmaxf(m0, t);
+      m0 = a;
+      a = fminf(m1, t);
+      t = fmaxf(m1, t);
+      m1 = a;
+      a = fminf(m2, t);
+      t = fmaxf(m2, t);
+      m2 = a;
+      m3 = fminf(m3, t);
+    }
+  }
   __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
+    if (col0 + 32 <= b_hi) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int64_t col = col0 + j;
-      const float b2 = col < b_hi ? __ldg(bn + col) : INFINITY;
-      float t = fmaf(-2.f, v[j], q2 + b2);
-      if (t < m3) {  // rare after the first few columns of a group
-        float a = fminf(m0, t);
-        t = fmaxf(m0, t);
-        m0 = a;
-        a = fminf(m1, t);
-        t = fmaxf(m1, t);
-        m1 = a;
-        a = fminf(m2, t);
-        t = fmaxf(m2, t);
-        m2 = a;
-        m3 = fminf(m3, t);
+      for (int g = 0; g < 8; ++g) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bn + col0) + g);  // same address in every lane
+        insert(fmaf(-2.f, v[4 * g + 0], q2 + b4.x));
+        insert(fmaf(-2.f, v[4 * g + 1], q2 + b4.y));
+        insert(fmaf(-2.f, v[4 * g + 2], q2 + b4.z));
+        insert(fmaf(-2.f, v[4 * g + 3], q2 + b4.w));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int64_t col = col0 + j;
+        insert(fmaf(-2.f, v[j], q2 + (col < b_hi ? __ldg(bn + col) : INFINITY)));
       }
     }
   }
