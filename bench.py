@@ -31,6 +31,25 @@ D_LATENT = 256
 N_TRAIN = 50_000
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly one JSON line: everything libraries print to fd 1 while the bench runs
+    (the NCCL version banner, for one) is sent to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def _peaks():
     """(HBM GB/s, dense bf16 TFLOP/s burst, source).  MEASURED_PEAKS.json is driver-written."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -142,9 +161,6 @@ def _all_host_threads():
 
 
 def run_b200(args):
-    # keep stdout to the one JSON line: the image sets NCCL_DEBUG=VERSION, which prints a banner there
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
 
@@ -271,7 +287,7 @@ def run_b200(args):
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "cpu_baseline": cpu_baseline, "extra": extra,
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -619,7 +635,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": "embeddings/s", "cores": int(threads), "kind": "port",
                              "sample": "10,000-row calls of the N x N Mahalanobis form (postprocessors.py:241-242)"},
             "e2e": {"value": v, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def main():
@@ -636,6 +652,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the configs[1] baseline sweep (host-side fits take ~20 s)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,58 @@
+"""Multi-GPU parity of the bank-sharded scorers over NCCL (run under torchrun, one rank per GPU):
+every rank holds a contiguous slice of the bank, queries are replicated, and the merged result must be
+IDENTICAL on every rank to a single-GPU search over the whole bank (kNN: indices and float32 distances bit
+for bit; KDE: log-densities to 1e-6 relative -- the per-shard partial sums travel as float32).  Prints one JSON line on rank 0.
+
+    torchrun --nproc-per-node 2 scripts/check_sharded.py
+"""
+import json
+import os
+import sys
+
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from runia_core_b200 import _ops, sharding  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    g = torch.Generator(device=dev).manual_seed(1234)  # same stream on every rank: replicated data
+    nb, d, nq, k = 200_003, 256, 3001, 50
+    bank = torch.randn(nb, d, generator=g, device=dev)
+    bank[1000:1100] = bank[1000]  # ties across shard-local candidate lists
+    q = torch.randn(nq, d, generator=g, device=dev) + 0.2 * bank[torch.randperm(nb, generator=g, device=dev)[:nq]]
+    bn, qn = _ops.normalize_rows(bank), _ops.normalize_rows(q)
+    full = _ops.knn_search(qn, _ops.knn_bank(bn), k)
+    lo, hi = sharding.row_shard(nb, rank, world)
+    shard = _ops.knn_bank(bn[lo:hi].contiguous(), idx_offset=lo)
+    dd, ii, kth = sharding.knn_search_sharded(qn, shard, k)
+    ok_knn = bool(torch.equal(ii, full["idx"]) and torch.equal(dd, full["dist"]) and torch.equal(kth, full["kth"]))
+    kb_full = _ops.kde_bank(bank)
+    ref = _ops.kde_score(q, kb_full)
+    kb = _ops.kde_bank(bank[lo:hi].contiguous(), center=kb_full.center, n_total=nb)
+    got = sharding.kde_score_sharded(q, kb)
+    err = float(((got - ref).abs() / ref.abs().clamp(min=1.0)).max())
+    # every rank must hold the same merged answer
+    chk = torch.stack([ii.double().sum(), dd.double().sum(), got.sum()])
+    lst = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(lst, chk)
+    same = all(bool(torch.equal(lst[0][:2], t[:2])) and float((lst[0][2] - t[2]).abs()) < 1e-6 for t in lst)
+    flags = torch.tensor([int(ok_knn), int(err < 1e-6), int(same)], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(json.dumps({"world": world, "bank_rows": nb, "queries": nq, "k": k, "knn_bit_exact": bool(flags[0]),
+                          "kde_max_rel_err": err, "kde_ok": bool(flags[1]), "identical_on_all_ranks": bool(flags[2])}))
+    dist.destroy_process_group()
+    sys.exit(0 if bool(flags.min()) else 1)
+
+
+if __name__ == "__main__":
+    main()
