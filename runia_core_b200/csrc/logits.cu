@@ -46,28 +46,43 @@ logit_scores_small_kernel(const float *__restrict__ logits, int64_t N, int C, fl
   extern __shared__ __align__(16) float tile[];  // [LS_ROWS * C] logits (CMAX = 64 + GEN: then the t_c)
   const int64_t r0 = (int64_t)blockIdx.x * LS_ROWS;
   const int rows = (int)((N - r0 < LS_ROWS) ? (N - r0) : LS_ROWS);
-  const int total = rows * C;
   const float *src = logits + r0 * C;
-  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-    const int n4 = total >> 2;
-    for (int i = threadIdx.x; i < n4; i += LS_ROWS)
-      reinterpret_cast<float4 *>(tile)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
-    for (int e = (n4 << 2) + threadIdx.x; e < total; e += LS_ROWS) tile[e] = __ldg(src + e);
-  } else {
-    for (int e = threadIdx.x; e < total; e += LS_ROWS) tile[e] = __ldg(src + e);
+  // C <= 16 with 8-byte aligned rows: every thread reads its own row with LDG.64 (a warp covers a contiguous
+  // 32 * C * 4 bytes, so every sector is used); otherwise the block stages its rows through shared memory
+  const bool direct = CMAX <= 16 && (C % 2 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 7) == 0);
+  if (!direct) {
+    const int total = rows * C;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const int n4 = total >> 2;
+      for (int i = threadIdx.x; i < n4; i += LS_ROWS)
+        reinterpret_cast<float4 *>(tile)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
+      for (int e = (n4 << 2) + threadIdx.x; e < total; e += LS_ROWS) tile[e] = __ldg(src + e);
+    } else {
+      for (int e = threadIdx.x; e < total; e += LS_ROWS) tile[e] = __ldg(src + e);
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if ((int)threadIdx.x >= rows) return;
   float *l = tile + threadIdx.x * C;
   const int64_t row = r0 + threadIdx.x;
   if (CMAX <= 16) {
     float t[CMAX], e[CMAX];
     float m = -INFINITY;
+    if (direct) {
+      const float2 *g2 = reinterpret_cast<const float2 *>(src + (size_t)threadIdx.x * C);
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
-      t[c] = c < C ? l[c] : -INFINITY;
-      m = fmaxf(m, t[c]);
+      for (int c = 0; c < CMAX; c += 2) {
+        float2 u = make_float2(-INFINITY, -INFINITY);
+        if (c < C) u = __ldg(g2 + (c >> 1));
+        t[c] = u.x;
+        t[c + 1] = u.y;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) t[c] = c < C ? l[c] : -INFINITY;
     }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) m = fmaxf(m, t[c]);
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
