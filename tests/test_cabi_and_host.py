@@ -251,3 +251,24 @@ def test_cabi_argument_errors_without_gpu():
     assert raw("runia_clip_linear_lse_f32")(fake, 4, 512, fake, fake, 65, float("inf"), fake, None) == -2
     assert raw("runia_ash_linear_lse_f32")(fake, 4, 16, fake, fake, 4, 17, fake, None) == -1
     assert raw("runia_topk_merge")(fake, fake, 17, 4, 5, None, None, None, None) == -1
+
+
+def test_widening_boundary_signatures_and_argument_checks():
+    """The functions added along the path keep the reference's names, parameters and assertion texts
+    (metrics.py:37-42, llm_uncertainty/scores.py:49, inference/funcs.py:430-446, feature_extraction/utils.py:70);
+    their argument checks fire before any device work."""
+    from runia_core_b200.evaluation import get_auroc_results
+    from runia_core_b200.feature_extraction import get_mean_or_fullmean_ls_sample
+    from runia_core_b200.inference.funcs import get_predictive_uncertainty_score
+    from runia_core_b200.llm_uncertainty import eigen_score
+
+    assert list(inspect.signature(get_auroc_results).parameters) == [
+        "detect_exp_name", "ind_samples_scores", "ood_samples_scores", "return_results_for_mlflow"]
+    assert list(inspect.signature(eigen_score).parameters) == ["hidden_states", "alpha"]
+    assert inspect.signature(eigen_score).parameters["alpha"].default == 1e-3
+    assert list(inspect.signature(get_predictive_uncertainty_score).parameters) == ["input_samples", "mcd_nro_samples"]
+    assert list(inspect.signature(get_mean_or_fullmean_ls_sample).parameters) == ["latent_sample", "method"]
+    with pytest.raises(AssertionError, match="divisible by the mcd_nro_samples"):
+        get_predictive_uncertainty_score(torch.zeros(7, 3), 2)
+    with pytest.raises(AssertionError):
+        get_mean_or_fullmean_ls_sample(torch.zeros(2, 3, 4, 5), method="median")

@@ -148,3 +148,36 @@ def test_kde_50k_bank(ops):
     S = sum(p[1].double() * torch.exp((p[0] - M).double()) for p in parts)
     comb = M.double() + torch.log(S) - (np.log(50_000) + 0.5 * 256 * np.log(2 * np.pi))
     assert torch.allclose(comb, s, rtol=1e-6, atol=1e-5)
+
+
+def test_more_than_2_31_elements(ops):
+    """Inputs with more than 2^31 elements (toward configs[2] / configs[4] sizes: 1M boxes x 16 x 1024,
+    33.5M pixel embeddings): the last rows / items must score exactly like the same rows scored alone,
+    which catches any 32-bit index arithmetic in the kernels or the TMA coordinates."""
+    g = _gen(21)
+    # LaREM: 9,000,000 x 256 = 2.3e9 elements (9.2 GB)
+    rng = np.random.RandomState(1)
+    train = rng.randn(20_000, 256).astype(np.float32)
+    mean, prec = O.md_fit(train)
+    st = ops.md_prepare(mean, prec)
+    n = 9_000_000
+    X = torch.empty(n, 256, device="cuda")
+    for lo in range(0, n, 1_000_000):
+        X[lo:lo + 1_000_000].normal_(generator=g)
+    s = ops.md_score(X, st)
+    tail = slice(n - 5000, n)
+    assert torch.equal(ops.md_score(X[tail].contiguous(), st), s[tail])
+    assert rel_err(s[tail].cpu().numpy()[:512], O.md_score(X[tail][:512].cpu().numpy(), mean, prec)) < RTOL
+    del X, s
+    torch.cuda.empty_cache()
+    # entropy: 140,000 items x 16 x 1024 = 2.3e9 elements (9.2 GB in, 1.1 GB out)
+    n_items, n_mc, D = 140_000, 16, 1024
+    z = torch.empty(n_items * n_mc, D, device="cuda")
+    for lo in range(0, n_items * n_mc, 160_000):
+        z[lo:lo + 160_000].normal_(generator=g)
+    hm, hz = ops.mcd_entropy(z, n_mc)
+    lo = n_items - 300
+    hm_t, hz_t = ops.mcd_entropy(z[lo * n_mc:].contiguous(), n_mc)
+    assert torch.equal(hz_t, hz[lo:]) and torch.equal(hm_t, hm[lo:])
+    rm, rz = O.get_dl_h_z(z[(n_items - 16) * n_mc:].cpu().numpy(), n_mc, chunk=16)
+    assert rel_err(hz[-16:].cpu().numpy(), rz) < RTOL and rel_err(hm[-16:].cpu().numpy(), rm[:, 0]) < RTOL
