@@ -258,6 +258,16 @@ int runia_pred_uncertainty_f32(const float *logits, int64_t n_items, int n_mc, i
  */
 int runia_spatial_mean_f32(const float *x, int64_t P, int H, int W, int fullmean, float *out, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (f2) Ascending sort of float32 values (same LSD radix sort as the metrics): the order statistics
+ * behind np.percentile(ind_train_data.flatten(), p) in ReAct / DICE+ReAct setup
+ * (inference/postprocessors.py:1433, 1576).  NaNs sort last, -0.0 before +0.0.
+ *   workspace: runia_sort_f32_workspace_bytes(n) bytes.  n < 2^31.
+ */
+int64_t runia_sort_f32_workspace_bytes(int64_t n);
+int runia_sort_f32(const float *x, int64_t n, float *out_sorted, void *workspace, int64_t workspace_bytes,
+                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,8 @@ _SIGS = {
     "runia_eigen_score_f32": (c_int, [_P, c_int, c_int, c_double, _P, _P]),
     "runia_pred_uncertainty_f32": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P]),
     "runia_spatial_mean_f32": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P]),
+    "runia_sort_f32_workspace_bytes": (c_int64, [c_int64]),
+    "runia_sort_f32": (c_int, [_P, c_int64, _P, _P, c_int64, _P]),
     "runia_logit_scores_f32": (c_int, [_P, c_int64, c_int, c_float, c_int, _P, _P, _P, _P]),
     "runia_clip_linear_lse_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, c_float, _P, _P]),
     "runia_ash_linear_lse_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, c_int, _P, _P]),

@@ -523,3 +523,41 @@ def ood_metrics(ind_scores, ood_scores, want_curve: bool = True):
     npts = int(o[3])
     return {"auroc": float(o[0]), "fpr95": float(o[1]), "aupr": float(o[2]), "n_points": npts,
             "fpr": fpr[:npts] if want_curve else None, "tpr": tpr[:npts] if want_curve else None}
+
+
+# ------------------------------------------------------------------------------------------
+# (f2) order statistics for the ReAct threshold
+# ------------------------------------------------------------------------------------------
+def sort_f32(x) -> torch.Tensor:
+    """Ascending device sort of all elements of x (float32)."""
+    t = to_device(x, torch.float32).reshape(-1).contiguous()
+    n = t.numel()
+    out = _empty((n,), torch.float32)
+    if n == 0:
+        return out
+    ws_bytes = int(_lib.raw("runia_sort_f32_workspace_bytes")(n))
+    ws = _empty((ws_bytes,), torch.uint8)
+    _lib.call("runia_sort_f32", t.data_ptr(), n, out.data_ptr(), ws.data_ptr(), ws_bytes, stream_ptr())
+    return out
+
+
+def percentile_f32(x, q: float):
+    """np.percentile(x.flatten(), q) (method "linear") for float32 data.  The two neighbouring order
+    statistics come from the device sort; the virtual index, gamma and the lerp follow NumPy's own
+    `_quantile` / `_lerp` arithmetic (NumPy >= 2 casts q to the array dtype, so everything is float32 and
+    the index saturates for huge arrays; older NumPy keeps the index in float64)."""
+    s = sort_f32(x)
+    n = s.numel()
+    f32 = int(np.__version__.split(".")[0]) >= 2
+    ft = np.float32 if f32 else np.float64
+    vi = ft(n - 1) * np.true_divide(np.asanyarray(q, dtype=ft), ft(100))
+    if vi >= n - 1:
+        return np.float32(s[n - 1].item())
+    if vi < 0:
+        return np.float32(s[0].item())
+    lo = int(np.floor(vi))
+    a, b = (np.float32(v) for v in s[[lo, lo + 1]].cpu().numpy())
+    g = ft(vi - ft(lo))
+    diff = b - a
+    out = a + diff * g if g < 0.5 else b - diff * (ft(1) - g)
+    return np.float32(out) if f32 else out

@@ -515,9 +515,67 @@ static int ood_metrics_impl(const T *ind, int64_t n_ind, const T *ood, int64_t n
   return finish_launch("ood_metrics");
 }
 
+// ------------------------------------------------------------------------------------------------
+// (f2) ascending sort of float32 values with the same radix sort: the order statistics behind
+// np.percentile(train.flatten(), p) in ReAct / DICE+ReAct setup (postprocessors.py:1433, 1576)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sort_keys_in_kernel(const float *__restrict__ x, int64_t n,
+                                                           uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    keys[i] = ordered_key(x[i]);
+    vals[i] = 0u;
+  }
+}
+__global__ void __launch_bounds__(256) sort_keys_out_kernel(const uint64_t *__restrict__ keys, int64_t n,
+                                                            float *__restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t k = (uint32_t)(keys[i] >> 32);
+    out[i] = __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+  }
+}
+
 }  // namespace runia
 
 using namespace runia;
+
+extern "C" int64_t runia_sort_f32_workspace_bytes(int64_t n) { return n > 0 ? (int64_t)metrics_layout(n).total : 0; }
+
+extern "C" int runia_sort_f32(const float *x, int64_t n, float *out_sorted, void *workspace, int64_t workspace_bytes,
+                              void *stream) {
+  RUNIA_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, RUNIA_E_BADARG, "sort_f32: bad size");
+  if (n == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(x && out_sorted && workspace, RUNIA_E_BADARG, "sort_f32: null pointer");
+  const MetricsLayout L = metrics_layout(n);
+  RUNIA_REQUIRE((size_t)workspace_bytes >= L.total, RUNIA_E_WORKSPACE, "sort_f32: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char *ws = (unsigned char *)workspace;
+  uint64_t *ka = (uint64_t *)(ws + L.keys_a), *kb = (uint64_t *)(ws + L.keys_b);
+  uint32_t *va = (uint32_t *)(ws + L.vals_a), *vb = (uint32_t *)(ws + L.vals_b);
+  uint32_t *hist = (uint32_t *)(ws + L.hist), *hist_tiles = (uint32_t *)(ws + L.hist_tiles);
+  static bool attr = false;
+  if (!attr) {
+    RUNIA_CUDA(cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmem));
+    attr = true;
+  }
+  const unsigned g1 = (unsigned)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSMs * 8);
+  sort_keys_in_kernel<<<g1, 256, 0, st>>>(x, n, ka, va);
+  const int64_t nblk = ceil_div(n, RS_TILE);
+  const int64_t hist_n = 256 * nblk, hist_nt = ceil_div(hist_n, SC_TILE);
+  for (int shift = 32; shift < 64; shift += 8) {
+    rs_hist_kernel<<<(unsigned)nblk, RS_THREADS, 0, st>>>(ka, n, shift, hist, nblk);
+    scan_u32_partial_kernel<<<(unsigned)hist_nt, SC_THREADS, 0, st>>>(hist, hist_n, hist_tiles);
+    scan_u32_tiles_kernel<<<1, SC_THREADS, 0, st>>>(hist_tiles, hist_nt);
+    scan_u32_final_kernel<<<(unsigned)hist_nt, SC_THREADS, 0, st>>>(hist, hist_n, hist_tiles);
+    rs_scatter_kernel<<<(unsigned)nblk, RS_THREADS, kScatterSmem, st>>>(ka, va, n, shift, hist, nblk, kb, vb);
+    std::swap(ka, kb);
+    std::swap(va, vb);
+  }
+  sort_keys_out_kernel<<<g1, 256, 0, st>>>(ka, n, out_sorted);
+  count_launch(22);
+  return finish_launch("sort_f32");
+}
 
 extern "C" int64_t runia_ood_metrics_workspace_bytes(int64_t n_ind, int64_t n_ood) {
   if (n_ind <= 0 || n_ood <= 0) return 0;

@@ -482,6 +482,14 @@ class ASH(OodPostprocessor):
         return self.flip_sign_fn(self._score(test_data))
 
 
+def _train_percentile(ind_train_data, q):
+    """np.percentile(train.flatten(), q) (postprocessors.py:1433, 1576); float32 banks are sorted on the GPU."""
+    a = _np(ind_train_data)
+    if a.dtype == np.float32 and a.size >= 1 << 16:
+        return _ops.percentile_f32(a, q)
+    return np.percentile(a.flatten(), q)
+
+
 def _make_dice_layer(ind_train_data, kwargs, num_classes, percentile):
     w, b = kwargs["final_linear_layer_params"]["weight"], kwargs["final_linear_layer_params"]["bias"]
     params = {"weight": Tensor(w) if isinstance(w, np.ndarray) else w,
@@ -536,7 +544,7 @@ class ReAct(OodPostprocessor):
         assert "valid_feats" in kwargs, "valid_feats must be provided for ReAct"
         self.w, self.b = _linear_params(kwargs)
         self._w, self._b = to_device(self.w, torch.float32), to_device(self.b, torch.float32)
-        self.activation_threshold = np.percentile(_np(ind_train_data).flatten(), self.react_percentile)
+        self.activation_threshold = _train_percentile(ind_train_data, self.react_percentile)
         self.set_threshold(self.flip_sign_fn(self._score(kwargs["valid_feats"])))
 
     def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
@@ -565,7 +573,7 @@ class DICEReAct(OodPostprocessor):
         assert "valid_feats" in kwargs, "valid_feats must be provided for DICE"
         self.dice_layer = _make_dice_layer(ind_train_data, kwargs, self.num_classes, self.dice_percentile)
         self._b = to_device(self.dice_layer.bias.detach(), torch.float32)
-        self.react_activation_threshold = np.percentile(_np(ind_train_data).flatten(), self.react_percentile)
+        self.react_activation_threshold = _train_percentile(ind_train_data, self.react_percentile)
         self.set_threshold(self.flip_sign_fn(self._score(kwargs["valid_feats"])))
 
     def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:

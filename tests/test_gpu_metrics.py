@@ -154,3 +154,23 @@ def test_spatial_mean_vs_torch(shape):
         assert got.shape == ref.shape and got.is_cuda
         assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6)
     assert not get_mean_or_fullmean_ls_sample(x.cpu(), "fullmean").is_cuda
+
+
+def test_react_threshold_percentile_bit_exact():
+    """The ReAct clip threshold: np.percentile(train.flatten(), p) from the device sort must be the very
+    float NumPy returns (postprocessors.py:1433), at the configs[1] size (50k x 512 = 25.6M activations)."""
+    from runia_core_b200 import _ops
+
+    rng = np.random.RandomState(3)
+    for n, qs in ((70_001, (0, 33.3, 90, 99.99, 100)), (25_600_000, (90, 85))):
+        x = np.maximum(rng.standard_normal(n).astype(np.float32), 0)
+        srt = _ops.sort_f32(x).cpu().numpy()
+        if n < 1_000_000:
+            assert np.array_equal(srt, np.sort(x))
+        else:
+            assert bool((srt[1:] >= srt[:-1]).all()) and srt[0] == x.min() and srt[-1] == x.max()
+        for q in qs:
+            got, ref = _ops.percentile_f32(x, q), np.percentile(x, q)
+            assert got == ref, (n, q, got, ref)
+    neg = np.array([3.0, -0.0, 0.0, -2.5, np.inf, -np.inf, 1e-40, -1e-40] * 9000, np.float32)
+    assert np.array_equal(_ops.sort_f32(neg).cpu().numpy(), np.sort(neg))
