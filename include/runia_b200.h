@@ -268,6 +268,24 @@ int64_t runia_sort_f32_workspace_bytes(int64_t n);
 int runia_sort_f32(const float *x, int64_t n, float *out_sorted, void *workspace, int64_t workspace_bytes,
                    void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (f2) setup() statistics: the mean / covariance halves of MDLatentSpace.setup
+ * (inference/postprocessors.py:202-226), cMDLatentSpace.setup (:283-318) and mahalanobis_preprocess
+ * (inference/funcs.py:33-66).
+ *   runia_class_mean_f32: means[c] = X[labels == c].mean(0) for c < C, float32, accumulated row by row in
+ *     ascending order like NumPy's axis-0 reduction (bit-identical); labels NULL (C must be 1): the column
+ *     mean of all rows.  counts[c] (nullable) = rows of class c.  An empty class gives NaN like NumPy.
+ *   runia_centered_gram_f64: G [d, d] = sum_i r_i r_i^T in float64 with r_i = f32(x_i - centers[labels_i])
+ *     (centers NULL: r_i = x_i; labels NULL: every row uses centers[0]; rows whose label is outside [0, C)
+ *     are skipped), colsum [d] (nullable) = sum_i r_i.  np.cov(R.T, bias=1) = (G - n a a^T) / n, a = colsum / n.
+ *     Deterministic (fixed-order split reduction).  workspace: runia_centered_gram_workspace_bytes(N, d).
+ */
+int runia_class_mean_f32(const float *X, const int32_t *labels, int64_t N, int d, int C, float *means,
+                         int64_t *counts, void *stream);
+size_t runia_centered_gram_workspace_bytes(int64_t N, int d);
+int runia_centered_gram_f64(const float *X, const int32_t *labels, const float *centers, int64_t N, int d, int C,
+                            double *G, double *colsum, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

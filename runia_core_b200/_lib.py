@@ -5,7 +5,7 @@ there is no NumPy / PyTorch fallback behind it."""
 import ctypes
 import os
 import shutil
-from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libruniab200.so")
@@ -69,6 +69,9 @@ _SIGS = {
     "runia_spatial_mean_f32": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P]),
     "runia_sort_f32_workspace_bytes": (c_int64, [c_int64]),
     "runia_sort_f32": (c_int, [_P, c_int64, _P, _P, c_int64, _P]),
+    "runia_class_mean_f32": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P]),
+    "runia_centered_gram_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "runia_centered_gram_f64": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "runia_logit_scores_f32": (c_int, [_P, c_int64, c_int, c_float, c_int, _P, _P, _P, _P]),
     "runia_clip_linear_lse_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, c_float, _P, _P]),
     "runia_ash_linear_lse_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, c_int, _P, _P]),

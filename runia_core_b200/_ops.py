@@ -561,3 +561,49 @@ def percentile_f32(x, q: float):
     diff = b - a
     out = a + diff * g if g < 0.5 else b - diff * (ft(1) - g)
     return np.float32(out) if f32 else out
+
+
+# ------------------------------------------------------------------------------------------
+# (f2) setup() statistics: class means and the pooled class-centred covariance
+# ------------------------------------------------------------------------------------------
+def _labels_i32(labels, n):
+    lab = np.asarray(labels.detach().cpu() if isinstance(labels, torch.Tensor) else labels).reshape(-1)
+    if lab.shape[0] != n:
+        raise ValueError(f"{lab.shape[0]} labels for {n} rows")
+    if lab.dtype.kind == "f":  # float labels compare like `labels == c`: only integral values match a class
+        lab = np.where(lab == np.floor(lab), lab, -1)
+    big = np.abs(lab) >= 2 ** 31 if lab.dtype.kind in "iuf" else False
+    lab = np.where(big, -1, lab).astype(np.int32)
+    return torch.from_numpy(lab).to(device())
+
+
+def class_means(x, labels=None, num_classes: int = 1):
+    """(means [C, d] float32 device, counts [C] int64 host): `x[labels == c].mean(0)` with NumPy's own
+    row-by-row float32 accumulation (bit-identical); labels None -> the column mean of all rows, C = 1."""
+    xf = to_device(x, torch.float32)
+    n, d = xf.shape
+    lab = None if labels is None else _labels_i32(labels, n)
+    means = _empty((num_classes, d), torch.float32)
+    counts = _empty((num_classes,), torch.int64)
+    _lib.call("runia_class_mean_f32", xf.data_ptr(), ptr(lab), n, d, num_classes, means.data_ptr(), counts.data_ptr(),
+              stream_ptr())
+    return means, counts.cpu().numpy(), xf, lab
+
+
+def centered_covariance(xf: torch.Tensor, lab, centers: torch.Tensor, n_used: int) -> np.ndarray:
+    """np.cov(R.T, bias=1) in float64 for the residual rows R = f32(x - centers[label]) (what
+    sklearn's EmpiricalCovariance(assume_centered=False).fit(R).covariance_ holds): device float64 Gram
+    matrix + column sums, np.cov's re-centring and 1/n scaling on the d x d result."""
+    n, d = xf.shape
+    C = centers.shape[0]
+    G = _empty((d, d), torch.float64)
+    cs = _empty((d,), torch.float64)
+    ws_bytes = int(_lib.raw("runia_centered_gram_workspace_bytes")(n, d))
+    ws = _empty((ws_bytes,), torch.uint8)
+    _lib.call("runia_centered_gram_f64", xf.data_ptr(), ptr(lab), centers.data_ptr(), n, d, C, G.data_ptr(), cs.data_ptr(),
+              ws.data_ptr(), ws_bytes, stream_ptr())
+    G, cs = G.cpu().numpy(), cs.cpu().numpy()
+    avg = cs / n_used
+    cov = G - n_used * np.outer(avg, avg)
+    cov *= np.true_divide(1, n_used)
+    return cov

@@ -7,6 +7,7 @@ from typing import Dict, Tuple, Union
 
 import numpy as np
 import torch
+from scipy.linalg import pinvh
 from sklearn.covariance import EmpiricalCovariance
 
 from .. import _ops
@@ -28,6 +29,15 @@ def mahalanobis_preprocess(ind_data: Dict[str, np.ndarray], num_classes: int) ->
     """Class means [C, d] and the shared precision of the class-centred training features
     (funcs.py:33-66).  Classes without samples warn and get a NaN mean."""
     feats, labels = ind_data["train features"], ind_data["train labels"]
+    if isinstance(feats, np.ndarray) and feats.dtype == np.float32 and feats.ndim == 2 and feats.shape[0] > 0:
+        # device statistics (csrc/fit.cu): NumPy-ordered class means, float64 Gram matrix of the residuals
+        means, counts, xf, lab = _ops.class_means(feats, labels, num_classes)
+        for c in np.flatnonzero(counts == 0):
+            warnings.warn(f"No train examples for class {c}")
+        cov = _ops.centered_covariance(xf, lab, means, int(counts.sum()))
+        if not np.isfinite(cov).all():
+            raise ValueError("Input X contains NaN or infinity.")
+        return to_host(means), pinvh(cov, check_finite=False)
     class_mean, centered = [], []
     for c in range(num_classes):
         xs = feats[labels == c]

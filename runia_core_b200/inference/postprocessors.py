@@ -13,6 +13,7 @@ from typing import Dict, List, Union
 
 import numpy as np
 import torch
+from scipy.linalg import pinvh
 from sklearn.covariance import EmpiricalCovariance
 from torch import Tensor
 
@@ -64,6 +65,21 @@ def _linear_params(kwargs):
 # ------------------------------------------------------------------------------------------------
 # LaRED: Gaussian KDE over the latent bank            reference: postprocessors.py:78-178
 # ------------------------------------------------------------------------------------------------
+def _device_fit(feats, labels, num_classes):
+    """float32 features -> (class means [C, d] float32, counts [C], shared precision [d, d] float64) from
+    device statistics: NumPy-ordered means (bit-identical to `feats[labels == c].mean(0)`), the float64
+    covariance of the class-centred rows (np.cov(..., bias=1), what EmpiricalCovariance.fit holds) and
+    scipy's pinvh like sklearn's `_set_covariance`."""
+    means, counts, xf, lab = _ops.class_means(feats, labels, num_classes)
+    n_used = int(counts.sum())
+    if n_used == 0:
+        raise ValueError(f"Found array with 0 sample(s) (shape=(0, {xf.shape[1]})) while a minimum of 1 is required.")
+    cov = _ops.centered_covariance(xf, lab, means, n_used)
+    if not np.isfinite(cov).all():  # sklearn's validate_data refuses such rows
+        raise ValueError("Input X contains NaN or infinity.")
+    return to_host(means), counts, pinvh(cov, check_finite=False)
+
+
 class DetectorKDE:
     """Gaussian kernel density estimate of the training embeddings (postprocessors.py:78-128).
     The reference fits sklearn's KernelDensity (a KD-tree) and queries it exactly (atol=rtol=0);
@@ -127,11 +143,15 @@ class MDLatentSpace(Postprocessor):
         assert ind_train_data.ndim == 2, "ind_feats must be 2 dimensional"
         if not self._setup_flag:
             ind_train_data = _np(ind_train_data)
-            self.feats_mean = np.mean(ind_train_data, 0, keepdims=True)
-            self.centered_data = ind_train_data - self.feats_mean
-            ec = EmpiricalCovariance(assume_centered=False)
-            ec.fit(self.centered_data)
-            self.precision = ec.precision_
+            if ind_train_data.dtype == np.float32 and ind_train_data.shape[0] > 0:
+                self.feats_mean, _, self.precision = _device_fit(ind_train_data, None, 1)
+                self.centered_data = ind_train_data - self.feats_mean
+            else:  # other dtypes: the reference's own host fit
+                self.feats_mean = np.mean(ind_train_data, 0, keepdims=True)
+                self.centered_data = ind_train_data - self.feats_mean
+                ec = EmpiricalCovariance(assume_centered=False)
+                ec.fit(self.centered_data)
+                self.precision = ec.precision_
             self._state = _ops.md_prepare(self.feats_mean, self.precision)
             self._setup_flag = True
         else:
@@ -169,21 +189,12 @@ class cMDLatentSpace(Postprocessor):
         feats = _np(ind_train_data).astype(np.float32)
         assert feats.ndim == 2, "ind_feats must be 2 dimensional"
         if not self._setup_flag:
-            class_mean, centered = [], []
-            for c in range(self.num_classes):
-                xs = feats[ind_train_labels == c]
-                if len(xs) == 0:
-                    warnings.warn(f"No examples for class {c} to build class-wise Mahalanobis Distance score")
-                with warnings.catch_warnings():
-                    warnings.simplefilter("ignore", RuntimeWarning)
-                    class_mean.append(xs.mean(0))
-                centered.append(xs - class_mean[c].reshape(1, -1))
-            cm = np.stack(class_mean)
-            ec = EmpiricalCovariance(assume_centered=False)
-            ec.fit(np.concatenate(centered).astype(np.float32))
+            cm, counts, precision = _device_fit(feats, ind_train_labels, self.num_classes)
+            for c in np.flatnonzero(counts == 0):
+                warnings.warn(f"No examples for class {c} to build class-wise Mahalanobis Distance score")
             self.class_mean = torch.from_numpy(cm)  # [#classes, d], like the reference
-            self.precision = torch.from_numpy(ec.precision_).float()
-            self._state = _ops.classcond_prepare(cm, ec.precision_)
+            self.precision = torch.from_numpy(precision).float()
+            self._state = _ops.classcond_prepare(cm, precision)
             self._setup_flag = True
         else:
             warnings.warn("cMDPostprocessor already trained")

@@ -74,3 +74,23 @@ if "metrics" in which:
         m = _ops.ood_metrics(si, so, want_curve=False)
     torch.cuda.synchronize()
 print("done")
+if "fit" in which:
+    import time
+
+    C, d, n = 10, 512, 50_000
+    labels = torch.randint(0, C, (n,), generator=g, device=dev)
+    mu = torch.randn(C, d, generator=g, device=dev)
+    Xf = (mu[labels] + torch.randn(n, d, generator=g, device=dev)).contiguous()
+    lab_np = labels.cpu().numpy()
+    for _ in range(REPS + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        means, counts, xf, lab = _ops.class_means(Xf, lab_np, C)
+        ev[1].record()
+        cov = _ops.centered_covariance(xf, lab, means, int(counts.sum()))
+        ev[2].record()
+        torch.cuda.synchronize()
+        print(f"fit {n}x{d} C={C}: class means {ev[0].elapsed_time(ev[1]):.3f} ms, gram+reduce+D2H {ev[1].elapsed_time(ev[2]):.3f} ms, "
+              f"wall {1e3 * (time.perf_counter() - t0):.1f} ms", file=sys.stderr)

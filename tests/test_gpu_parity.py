@@ -313,11 +313,12 @@ def test_edge_cases(R):
         R.inference.Energy(flip_sign=True).flip_sign_fn([1.0])
 
 
-@pytest.mark.parametrize("d,pct", [(512, 85), (1000, 90), (130, 65)])
+@pytest.mark.parametrize("d,pct", [(512, 85), (512, 10), (1024, 85), (1000, 90), (130, 65)])
 def test_ash_react_heads_vs_oracle(R, d, pct):
-    """ASH-S (radix select in registers, early exit / tie path) and the ReAct / DICE head at widths
-    that hit the one-chunk, two-chunk and unaligned paths; rows with many exact zeros put the k-th
-    largest activation into a tie."""
+    """ASH-S (histogram select for full 512 / 1024 rows, radix select with early exit / tie path
+    otherwise) and the ReAct / DICE head at widths that hit the one-chunk, two-chunk and unaligned
+    paths; rows with many exact zeros put the k-th largest activation into a tie, quantised rows
+    put ties into the deciding histogram bin (kept by lowest index)."""
     from runia_core_b200 import _ops
 
     rng = np.random.RandomState(d)
@@ -325,6 +326,9 @@ def test_ash_react_heads_vs_oracle(R, d, pct):
     x = np.maximum(rng.randn(n, d), 0).astype(np.float32)
     x[::7] *= (rng.rand(d) < 0.08)  # very sparse rows: fewer positives than kept elements
     x[5] = 1.0                      # all equal: ties between non-zero activations
+    x[9::11] = np.round(x[9::11], 1)      # few distinct values: a handful of ties around the threshold
+    x[10::11] = np.round(x[10::11] * 2) / 2  # very few distinct values: dozens of ties (exact path)
+    x[11] = -x[11] - 3.0                  # negative activations
     W = (0.05 * rng.randn(C, d)).astype(np.float32)
     b = rng.randn(C).astype(np.float32)
     Wd, bd = torch.from_numpy(W).cuda(), torch.from_numpy(b).cuda()
