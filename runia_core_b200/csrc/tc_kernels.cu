@@ -131,6 +131,23 @@ struct PcaEpi {  // Z[row, col] = v * inv_scale[col], written with TMA stores (f
 // (a6) class-conditional Mahalanobis: out = max_c -sum_j sign_j (y_j - m_cj)^2 over the classes that
 // had training samples; one accumulator per class in registers (C <= kClassMax)
 constexpr int kClassMax = 16;
+// packed FP32 pairs (FADD2 / FFMA2 on sm_100a): one issue slot for two lanes of the per-class distance
+__device__ __forceinline__ float2 sub_f32x2(float2 a, float2 b) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; "
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+
 struct ClassCondEpi {
   const float *sign, *Mc;  // [r] or nullptr; [C, r]
   const int32_t *valid;    // [C]
@@ -139,52 +156,56 @@ struct ClassCondEpi {
   float *out32;
   int64_t M;
   int64_t row;
-  float cls[kClassMax];
+  float2 cls[kClassMax];  // two partial sums per class (even / odd columns)
   __device__ void set_stage(uint32_t) {}
   template <class P> __device__ void bind(const P *) {}
   __device__ void begin(int, int64_t row_) {
     row = row_;
 #pragma unroll
-    for (int c = 0; c < kClassMax; ++c) cls[c] = 0.f;
+    for (int c = 0; c < kClassMax; ++c) cls[c] = make_float2(0.f, 0.f);
   }
   __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
+    if (col0 + 31 < r && !sign) {  // positive-definite precision (the usual case): no sign plane
+      // unrolled over the classes (register accumulators): 8 LDG.128 + 16 FADD2 + 16 FFMA2 per class
 #pragma unroll
-    for (int c = 0; c < kClassMax; ++c) {
-      if (c < C) {
-        const float *mc = Mc + (size_t)c * r + col0;
-        float acc = cls[c];
-        if (col0 + 31 < r && !sign) {  // positive-definite precision (the usual case): no sign plane
+      for (int c = 0; c < kClassMax; ++c) {
+        if (c < C) {
+          const float *mc = Mc + (size_t)c * r + col0;
+          float2 a0 = cls[c], a1 = make_float2(0.f, 0.f);  // two independent FFMA2 chains
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int j = 0; j < 32; j += 8) {
             const float4 m4 = __ldg(reinterpret_cast<const float4 *>(mc + j));  // same address in every lane
-            const float d0 = v[j] - m4.x, d1 = v[j + 1] - m4.y, d2 = v[j + 2] - m4.z, d3 = v[j + 3] - m4.w;
-            acc = fmaf(d0, d0, acc);
-            acc = fmaf(d1, d1, acc);
-            acc = fmaf(d2, d2, acc);
-            acc = fmaf(d3, d3, acc);
+            const float4 n4 = __ldg(reinterpret_cast<const float4 *>(mc + j + 4));
+            const float2 d0 = sub_f32x2(make_float2(v[j], v[j + 1]), make_float2(m4.x, m4.y));
+            const float2 d1 = sub_f32x2(make_float2(v[j + 2], v[j + 3]), make_float2(m4.z, m4.w));
+            const float2 d2 = sub_f32x2(make_float2(v[j + 4], v[j + 5]), make_float2(n4.x, n4.y));
+            const float2 d3 = sub_f32x2(make_float2(v[j + 6], v[j + 7]), make_float2(n4.z, n4.w));
+            a0 = fma_f32x2(d0, d0, a0);
+            a1 = fma_f32x2(d1, d1, a1);
+            a0 = fma_f32x2(d2, d2, a0);
+            a1 = fma_f32x2(d3, d3, a1);
           }
-        } else if (col0 + 31 < r) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 m4 = __ldg(reinterpret_cast<const float4 *>(mc + j));
-            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(sign + col0 + j));
-            const float d0 = v[j] - m4.x, d1 = v[j + 1] - m4.y, d2 = v[j + 2] - m4.z, d3 = v[j + 3] - m4.w;
-            acc = fmaf(s4.x * d0, d0, acc);
-            acc = fmaf(s4.y * d1, d1, acc);
-            acc = fmaf(s4.z * d2, d2, acc);
-            acc = fmaf(s4.w * d3, d3, acc);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j < r) {
-              const float dlt = v[j] - __ldg(mc + j);
-              acc = fmaf((sign ? __ldg(sign + col0 + j) : 1.f) * dlt, dlt, acc);
-            }
-          }
+          cls[c] = make_float2(a0.x + a1.x, a0.y + a1.y);
         }
-        cls[c] = acc;
       }
+      return;
+    }
+    // indefinite precision (sign plane) or the ragged last panel: one rolled copy of the code for all
+    // classes -- the unrolled form of these paths evicted the mainloop from the instruction cache
+#pragma unroll 1
+    for (int c = 0; c < C; ++c) {
+      const float *mc = Mc + (size_t)c * r + col0;
+      float part = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (col0 + j < r) {
+          const float dlt = v[j] - __ldg(mc + j);
+          part = fmaf((sign ? __ldg(sign + col0 + j) : 1.f) * dlt, dlt, part);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kClassMax; ++k)
+        if (k == c) cls[k].x += part;
     }
   }
   __device__ void panel_done(int) {}
@@ -194,7 +215,7 @@ struct ClassCondEpi {
 #pragma unroll
     for (int c = 0; c < kClassMax; ++c)
       if (c < C && valid[c]) {
-        const float sc = -cls[c];
+        const float sc = -(cls[c].x + cls[c].y);
         if (sc > best) best = sc;  // NaN never wins, like np.max after NaN -> -inf
       }
     if (out64) out64[row] = (double)best;

@@ -94,3 +94,13 @@ if "fit" in which:
         torch.cuda.synchronize()
         print(f"fit {n}x{d} C={C}: class means {ev[0].elapsed_time(ev[1]):.3f} ms, gram+reduce+D2H {ev[1].elapsed_time(ev[2]):.3f} ms, "
               f"wall {1e3 * (time.perf_counter() - t0):.1f} ms", file=sys.stderr)
+if "mahal" in which:
+    rng = np.random.RandomState(6)
+    d, C = 512, 10
+    A = rng.randn(d, d)
+    prec = A @ A.T / d + np.eye(d)
+    cst = _ops.classcond_prepare(rng.randn(C, d), prec)
+    Xm = torch.relu(torch.randn(500_000, d, generator=g, device=dev))
+    for _ in range(REPS):
+        r = _ops.classcond_score(Xm, cst)
+    torch.cuda.synchronize()
