@@ -458,6 +458,38 @@ def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak):
                               # bytes the passes move per score: keys out 4+12, four radix passes x (8 + 12 + 12), two scan reads x 12
                               "roofline": hbm(2 * nm * (4 + 12 + 4 * 32 + 2 * 12), ms)}
     del si, so
+    # (f3) MC-DropBlock sampler + H x W mean: 1024 ResNet-18 layer-4 maps (512 x 7 x 7), 16 samples each, against
+    # the same arithmetic written with torch ops the way DropBlock2D + the reference reducer run it (16 passes)
+    import torch.nn.functional as F
+    Bm, Cm, Hm, n_mc, bs = 1024, 512, 7, 16, 3
+    xm = torch.randn(Bm, Cm, Hm, Hm, generator=g, device=dev)
+    seed = (torch.rand(n_mc, Bm, Hm, Hm, generator=g, device=dev) < 0.3 / bs**2).to(torch.uint8)
+    ms = _time_op(torch, lambda: _ops.mc_dropblock_mean(xm, seed, bs), reps=5)
+
+    def torch_chain():
+        rows = []
+        for m in range(n_mc):
+            bm = 1 - F.max_pool2d(seed[m].float()[:, None], kernel_size=bs, stride=1, padding=bs // 2).squeeze(1)
+            o = xm * bm[:, None] * (Hm * Hm) / bm.sum((1, 2))[:, None, None, None]
+            rows.append(o.mean(3).mean(2))
+        return torch.stack(rows, 1)
+
+    ms_t = _time_op(torch, torch_chain, reps=3)
+    out["mc_sampler_1024x512x7x7"] = {"images_per_s": Bm / (ms * 1e-3), "ms": ms, "torch_ops_same_gpu_ms": ms_t,
+                                      "roofline": hbm(xm.numel() * 4 + Bm * n_mc * Cm * 4, ms)}
+    del xm, seed
+    # (f2) setup() statistics: class means + float64 Gram matrix of a 50k x 512 bank with 10 classes
+    xs = torch.randn(50_000, 512, generator=g, device=dev)
+    lab = torch.randint(0, 10, (50_000,), generator=g, device=dev).cpu().numpy()
+
+    def fit():
+        means, counts, xf, lb = _ops.class_means(xs, lab, 10)
+        return _ops.centered_covariance(xf, lb, means, int(counts.sum()))
+
+    ms = _time_op(torch, fit, reps=3)
+    out["fit_stats_50k_512_c10"] = {"ms": ms, "fp64_tflops": 50_000 * 512 * 513 / (ms * 1e-3) / 1e12,
+                                    "note": "means + Gram + reduction + copy-back of the 512 x 512 result"}
+    del xs
     return out
 
 

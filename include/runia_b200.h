@@ -286,6 +286,21 @@ size_t runia_centered_gram_workspace_bytes(int64_t N, int d);
 int runia_centered_gram_f64(const float *X, const int32_t *labels, const float *centers, int64_t N, int d, int C,
                             double *G, double *colsum, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (f3) MC-DropBlock sampler fused with the spatial mean: MCSamplerModule.forward for layer_type "Conv"
+ * (feature_extraction/abstract_classes.py:81-101 = n_mc x [DropBlock2D -> get_mean_or_fullmean_ls_sample
+ * "fullmean", feature_extraction/utils.py:70-92]); DropBlock2D is dropblock==0.3.0 (published forward:
+ * seed = rand(B,H,W) < drop_prob / bs^2; block_mask = 1 - max_pool2d(seed, bs, 1, bs/2) [even bs: cropped];
+ * out = x * block_mask * numel / sum).
+ *   x [B, C, H, W] float32; seed [n_mc, B, H, W] uint8 (non-zero = Bernoulli hit, drawn by the caller so that
+ *   the RNG stream is torch's); out [B * n_mc, C] float32, row b * n_mc + m =
+ *   sum over the cells kept by mask (m, b) of x[b, c] / number of kept cells   (normalised per image).
+ *   n_mc <= 32.  workspace: runia_mc_dropblock_workspace_bytes(B, H, W, n_mc).
+ */
+size_t runia_mc_dropblock_workspace_bytes(int B, int H, int W, int n_mc);
+int runia_mc_dropblock_mean_f32(const float *x, const uint8_t *seed, int B, int C, int H, int W, int n_mc,
+                                int block_size, float *out, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -607,3 +607,24 @@ def centered_covariance(xf: torch.Tensor, lab, centers: torch.Tensor, n_used: in
     cov = G - n_used * np.outer(avg, avg)
     cov *= np.true_divide(1, n_used)
     return cov
+
+
+# ------------------------------------------------------------------------------------------
+# (f3) MC-DropBlock sampler + spatial mean
+# ------------------------------------------------------------------------------------------
+def mc_dropblock_mean(x, seed, block_size: int) -> torch.Tensor:
+    """x [B, C, H, W] float32, seed [n_mc, B, H, W] (non-zero = Bernoulli hit) -> [B * n_mc, C] float32 device rows
+    (item-major): every DropBlock2D mask applied and reduced over H x W in one pass over x."""
+    xf = to_device(x, torch.float32)
+    sd = seed.to(device=device(), dtype=torch.uint8).contiguous() if isinstance(seed, torch.Tensor) else \
+        torch.from_numpy(np.ascontiguousarray(np.asarray(seed) != 0).astype(np.uint8)).to(device())
+    B, C, H, W = xf.shape
+    n_mc = sd.shape[0]
+    if tuple(sd.shape) != (n_mc, B, H, W):
+        raise ValueError(f"seed shape {tuple(sd.shape)} does not match (n_mc, {B}, {H}, {W})")
+    out = _empty((B * n_mc, C), torch.float32)
+    ws_bytes = int(_lib.raw("runia_mc_dropblock_workspace_bytes")(B, H, W, n_mc))
+    ws = _empty((ws_bytes,), torch.uint8)
+    _lib.call("runia_mc_dropblock_mean_f32", xf.data_ptr(), sd.data_ptr(), B, C, H, W, n_mc, int(block_size), out.data_ptr(),
+              ws.data_ptr(), ws_bytes, stream_ptr())
+    return out

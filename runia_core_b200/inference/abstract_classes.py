@@ -1,6 +1,7 @@
 """Boundary types of the scoring hot path: same names, constructor signatures, flags and error
 behaviour as the reference's `runia_core/inference/abstract_classes.py:35-211, 373-424`
-(the model-running InferenceModule classes of that file are out of scope)."""
+(of the model-running classes only `InferenceModule` / `ProbabilisticInferenceModule`, :217-320, exist:
+the bases of the online LaREx chain in `image_level.py`; the object-detection ones are out of scope)."""
 from abc import ABC, abstractmethod
 from time import monotonic
 from typing import Dict, List, Union
@@ -12,6 +13,8 @@ __all__ = [
     "record_time",
     "Postprocessor",
     "OodPostprocessor",
+    "InferenceModule",
+    "ProbabilisticInferenceModule",
     "get_baselines_thresholds",
     "get_method_threshold",
 ]
@@ -76,6 +79,34 @@ class OodPostprocessor(Postprocessor):
 
     def postprocess(self, test_data: ndarray, **kwargs) -> ndarray:
         raise NotImplementedError
+
+
+class InferenceModule:
+    """Model + postprocessor holder; moves the model to CUDA when present (abstract_classes.py:217-279)."""
+
+    def __init__(self, model, postprocessor):
+        import torch
+
+        self.model = model
+        self.postprocessor = postprocessor
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        try:
+            self.model.to(self.device)
+        except AttributeError:
+            pass
+
+    def get_score(self, input_image, *args, **kwargs):
+        raise NotImplementedError
+
+
+class ProbabilisticInferenceModule(InferenceModule):
+    """Adds the MC-DropBlock parameters (abstract_classes.py:282-320)."""
+
+    def __init__(self, model, postprocessor, drop_block_prob: float, drop_block_size: int, mcd_samples_nro: int):
+        super().__init__(model, postprocessor)
+        self.drop_block_prob = drop_block_prob
+        self.drop_block_size = drop_block_size
+        self.mcd_samples_nro = mcd_samples_nro
 
 
 def get_method_threshold(scores: np.ndarray, z_score_percentile: float):

@@ -159,9 +159,13 @@ class MDLatentSpace(Postprocessor):
 
     def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
         assert test_data.ndim == 2, "test_feats must be 2 dimensional"
+        return to_host(self.postprocess_device(test_data))
+
+    def postprocess_device(self, test_data) -> Tensor:
+        """Scores as a float64 CUDA tensor (no host copy): the form the online LaREx chain consumes."""
         if self._state is None:  # attributes assigned by hand (checkpoint restore)
             self._state = _ops.md_prepare(self.feats_mean, self.precision)
-        return to_host(_ops.md_score(test_data, self._state, torch.float64))
+        return _ops.md_score(test_data, self._state, torch.float64)
 
 
 # ------------------------------------------------------------------------------------------------

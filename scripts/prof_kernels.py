@@ -104,3 +104,10 @@ if "mahal" in which:
     for _ in range(REPS):
         r = _ops.classcond_score(Xm, cst)
     torch.cuda.synchronize()
+if "sampler" in which:
+    Bm, Cm, Hm, n_mc, bs = 1024, 512, 7, 16, 3
+    xm = torch.randn(Bm, Cm, Hm, Hm, generator=g, device=dev)
+    seed = (torch.rand(n_mc, Bm, Hm, Hm, generator=g, device=dev) < 0.3 / bs**2).to(torch.uint8)
+    for _ in range(REPS):
+        rows = _ops.mc_dropblock_mean(xm, seed, bs)
+    torch.cuda.synchronize()

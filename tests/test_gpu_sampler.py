@@ -1,0 +1,108 @@
+"""(f3) MC-DropBlock sampler + spatial mean (csrc/sampler.cu) and the online LaREx chain.
+
+The torch reference below is the published forward of dropblock==0.3.0's DropBlock2D (the layer
+MCSamplerModule instantiates, feature_extraction/abstract_classes.py:72-79) followed by the reference's
+"fullmean" reducer (feature_extraction/utils.py:70-92), run on the same Bernoulli seeds."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _dropblock_fullmean(x, seed, bs):
+    """x [B, C, H, W], seed [n_mc, B, H, W] -> [B * n_mc, C]: n_mc DropBlock2D passes, each per image (B = 1 calls)."""
+    rows = []
+    for b in range(x.shape[0]):
+        for m in range(seed.shape[0]):
+            mask = seed[m, b:b + 1].float()
+            bm = F.max_pool2d(mask[:, None], kernel_size=(bs, bs), stride=(1, 1), padding=bs // 2)
+            if bs % 2 == 0:
+                bm = bm[:, :, :-1, :-1]
+            bm = 1 - bm.squeeze(1)
+            out = x[b:b + 1] * bm[:, None, :, :]
+            out = out * bm.numel() / bm.sum()
+            out = torch.mean(torch.mean(out, dim=3, keepdim=True), dim=2, keepdim=True)
+            rows.append(out.reshape(1, -1))
+    return torch.cat(rows)
+
+
+@pytest.mark.parametrize("B,C,H,W,n_mc,bs,p", [(1, 512, 7, 7, 16, 3, 0.3), (5, 100, 16, 12, 16, 4, 0.4), (3, 33, 1, 1, 5, 1, 0.5),
+                                               (2, 64, 24, 24, 32, 7, 0.5), (2, 40, 9, 9, 8, 6, 0.9), (64, 512, 7, 7, 16, 3, 0.3)])
+def test_mc_dropblock_mean_matches_dropblock2d(B, C, H, W, n_mc, bs, p):
+    from runia_core_b200 import _ops
+
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    x = (torch.randn(B, C, H, W, generator=g) + 0.5).cuda()
+    seed = (torch.rand(n_mc, B, H, W, generator=g) < p / bs**2).to(torch.uint8).cuda()
+    got = _ops.mc_dropblock_mean(x, seed, bs)
+    ref = _dropblock_fullmean(x, seed, bs)
+    assert got.shape == (B * n_mc, C)
+    fin = torch.isfinite(ref)
+    assert torch.equal(fin, torch.isfinite(got))  # every cell dropped -> 0 / 0 in both
+    scale = ref[fin].abs().mean()
+    assert (got[fin] - ref[fin]).abs().max() <= 2e-6 * scale
+
+
+def test_sampler_module_reproduces_rng_stream_and_layout():
+    from runia_core_b200.feature_extraction import MCSamplerModule
+
+    n_mc, bs, p = 16, 3, 0.3
+    smp = MCSamplerModule(mc_samples=n_mc, block_size=bs, drop_prob=p, layer_type="Conv").train()
+    x = torch.randn(1, 512, 7, 7).cuda()
+    torch.manual_seed(11)
+    got = smp(x)
+    torch.manual_seed(11)  # what n_mc DropBlock2D layers draw, in order
+    seed = torch.stack([(torch.rand(1, 7, 7) < p / bs**2) for _ in range(n_mc)]).to(torch.uint8).cuda()
+    ref = _dropblock_fullmean(x, seed, bs)
+    assert got.shape == (n_mc, 512) and got.is_cuda
+    assert (got - ref).abs().max() <= 2e-6 * ref.abs().mean()
+    smp.eval()  # DropBlock2D is the identity outside training
+    ev = smp(x)
+    assert torch.allclose(ev, x.mean((2, 3)).expand(n_mc, -1), atol=1e-6)
+
+
+def test_larex_online_chain_matches_staged_api():
+    """LaRExInference.get_score (device chain) == get_dl_h_z -> apply_pca_transform -> MD.postprocess on the same samples."""
+    import runia_core_b200 as R
+    from runia_core_b200.feature_extraction import MCSamplerModule
+
+    class Hook:
+        output = None
+
+    class Net(torch.nn.Module):
+        def __init__(self, hook):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 64, 3, padding=1)
+            self.head = torch.nn.Linear(64, 10)
+            self.hook = hook
+
+        def forward(self, x):
+            z = torch.relu(self.conv(x))
+            self.hook.output = z
+            return self.head(z.mean((2, 3)))
+
+    torch.manual_seed(0)
+    hook, n_mc = Hook(), 16
+    net = Net(hook).cuda().eval()
+    smp = MCSamplerModule(mc_samples=n_mc, block_size=3, drop_prob=0.3).train()
+    imgs = torch.randn(96, 3, 16, 16)
+    with torch.no_grad():
+        net(imgs.cuda())
+    train_rows = smp.sample_batch(hook.output)                       # [96 * 16, 64]
+    _, h_z = R.evaluation.get_dl_h_z(train_rows, n_mc)
+    np.random.seed(1)
+    z_train, pca = R.apply_pca_ds_split(h_z, nro_components=8)
+    md = R.inference.postprocessors_dict["MD"]()
+    md.setup(z_train)
+    inf = R.inference.LaRExInference(net, md, drop_block_prob=0.3, drop_block_size=3, mcd_samples_nro=n_mc,
+                                     mcd_sampler=MCSamplerModule, pca_transform=pca)
+    torch.manual_seed(5)
+    out, score = inf.get_score(imgs[:1], hook)
+    torch.manual_seed(5)
+    rows = inf.mc_sampler(hook.output)
+    _, hz1 = R.evaluation.get_dl_h_z(rows, n_mc)
+    staged = md.postprocess(R.apply_pca_transform(hz1, pca))
+    assert out.shape == (1, 10) and score.shape == (1,) and score.dtype == np.float64
+    np.testing.assert_allclose(score, staged, rtol=1e-5)
