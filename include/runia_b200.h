@@ -215,6 +215,11 @@ int runia_logit_scores_f32(const float *logits, int64_t N, int C, float gamma, i
  */
 int runia_clip_linear_lse_f32(const float *X, int64_t N, int d, const float *W, const float *b, int C,
                               float clip, float *out, void *stream);
+/* Tensor-core version for C <= 32, d % 4 == 0, d <= 4096, 16-byte aligned X: the same tcgen05 pipeline as the row
+ * scorers with a 32-column panel (TMA-streamed rows, clip + 3xTF32 split by the converters, log-sum-exp straight
+ * from TMEM).  W_hi / W_lo: TF32 planes of W zero-padded to [32, d] (runia_split_tf32). */
+int runia_clip_linear_lse_tc(const float *X, int64_t N, int d, const float *W_hi, const float *W_lo, const float *b,
+                             int C, float clip, float *out, void *stream);
 int runia_ash_linear_lse_f32(const float *X, int64_t N, int d, const float *W, const float *b, int C,
                              int k_keep, float *out, void *stream);
 

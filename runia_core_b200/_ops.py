@@ -479,10 +479,28 @@ def logit_scores(logits, gamma=0.1, M=None, energy=True, msp=True, gen=True):
     return e, m, g, in_dtype
 
 
-def clip_linear_lse(x, W: torch.Tensor, b: torch.Tensor, clip=float("inf")) -> torch.Tensor:
+LINEAR_TC_MAX_CLASSES = 32   # UMMA N of the narrow-panel kernel
+LINEAR_TC_MIN_ROWS = 16384   # below this the one-warp-per-row kernel is as fast and needs no operand planes
+
+
+def linear_planes(W: torch.Tensor):
+    """TF32 hi / lo planes of the head's weight matrix, zero-padded to [32, d], for runia_clip_linear_lse_tc."""
+    Wp = torch.zeros((LINEAR_TC_MAX_CLASSES, W.shape[1]), dtype=torch.float32, device=device())
+    Wp[: W.shape[0]] = W
+    return split_tf32(Wp)
+
+
+def clip_linear_lse(x, W: torch.Tensor, b: torch.Tensor, clip=float("inf"), planes=None) -> torch.Tensor:
+    """logsumexp(min(x, clip) @ W.T + b): the ReAct / DICE / DICE+ReAct head.  Large batches of rows with
+    d % 4 == 0 stream through the tcgen05 narrow-panel kernel; `planes` = linear_planes(W) (built here when absent)."""
     xf, _ = as_f32_rows(x, None)
     n, d = xf.shape
     out = _empty((n,), torch.float32)
+    if n >= LINEAR_TC_MIN_ROWS and _tc_ok(d) and W.shape[0] <= LINEAR_TC_MAX_CLASSES and xf.data_ptr() % 16 == 0:
+        hi, lo = planes if planes is not None else linear_planes(W)
+        _lib.call("runia_clip_linear_lse_tc", xf.data_ptr(), n, d, hi.data_ptr(), lo.data_ptr(), b.data_ptr(), W.shape[0],
+                  float(clip), out.data_ptr(), stream_ptr())
+        return out
     _lib.call("runia_clip_linear_lse_f32", xf.data_ptr(), n, d, W.data_ptr(), b.data_ptr(), W.shape[0],
               float(clip), out.data_ptr(), stream_ptr())
     return out

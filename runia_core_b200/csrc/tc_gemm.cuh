@@ -198,8 +198,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
-// instruction descriptor: D=f32, A=B=tf32, both K-major, M=256 (pair), N=TN
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM2 >> 4) << 24);
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=256 (pair), N=n
+template <int N>
+struct InstrDesc {
+  static constexpr uint32_t value = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM2 >> 4) << 24);
+};
 
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
@@ -229,30 +232,44 @@ struct Work {
 //       32 consecutive columns col0.. of this thread's row
 //   __device__ void panel_done(int panel)                        -- after a whole panel
 //   __device__ void finish()                                     -- after the last panel of a row tile
-template <class E>
+// TNV = panel width (UMMA N): 256 for the contraction-heavy scorers; 32 for the narrow linear heads (ReAct / DICE:
+// C <= 32 classes), where the B planes are 16 rows per CTA, the MMAs are a small fraction of a stage and the
+// pipeline runs at the speed of the TMA stream and the converters.  The TMEM double buffer keeps its 256-column stride.
+// NCAT (narrow panels only): the B_hi and B_lo planes of a stage are adjacent, so A_hi x [B_hi | B_lo] is ONE UMMA of
+// N = 2 TNV and A_lo x B_hi a second one into its own accumulator -- 2 instead of 3 instructions per K step (at N = 32
+// an instruction costs its fixed minimum, not its FLOPs).  Accumulator columns: [0, TNV/2) hi x classes of CTA 0,
+// [TNV/2, TNV) lo x the same classes, [TNV, 3TNV/2) hi x classes of CTA 1, [3TNV/2, 2TNV) lo x those; [2TNV, 3TNV)
+// A_lo x B_hi in class order.  The epilogue receives all 3 TNV columns and adds the three products.
+template <class E, int TNV = TN, int NSTAGES = STAGES, bool NCAT = false>
 __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const Prologue pro,
                                           const CUtensorMap *tmB_hi, const CUtensorMap *tmB_lo, const Work work,
                                           E &epi, unsigned char *smem_raw) {
+  // stage = raw/hi A plane, lo A plane, this CTA's halves of the two B planes (narrow panels: smaller B planes, more stages)
+  constexpr int BPLANE = (TNV / 2) * TK * 4;
+  constexpr int STG = 2 * A_PLANE_BYTES + 2 * BPLANE;
+  static_assert(!NCAT || 3 * TNV <= TN, "concatenated panels must fit one accumulator slot");
+  static_assert(BPLANE % 1024 == 0, "B planes must keep the 1024-byte alignment of the 128B swizzle");
+  static_assert(8 * (3 * NSTAGES + 4) + 8 <= SMEM_BAR_BYTES, "barrier block too small");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
   // carve shared memory (1024-byte aligned for the 128B swizzle); identical offsets in both CTAs
   const uint32_t base = (smem_u32(smem_raw) + SMEM_ALIGN - 1) & ~(uint32_t)(SMEM_ALIGN - 1);
   unsigned char *gbase = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t epi_stage0 = base + STAGES * STAGE_BYTES;  // 1024-byte aligned (128B-swizzled boxes)
+  const uint32_t epi_stage0 = base + NSTAGES * STG;  // 1024-byte aligned (128B-swizzled boxes)
   const uint32_t bar0 = epi_stage0 + EPI_STAGE_BYTES;
-  auto sA_hi = [&](int s) { return base + s * STAGE_BYTES; };
-  auto sA_lo = [&](int s) { return base + s * STAGE_BYTES + A_PLANE_BYTES; };
-  auto sB_hi = [&](int s) { return base + s * STAGE_BYTES + 2 * A_PLANE_BYTES; };
-  auto sB_lo = [&](int s) { return base + s * STAGE_BYTES + 2 * A_PLANE_BYTES + B_PLANE_BYTES; };
+  auto sA_hi = [&](int s) { return base + s * STG; };
+  auto sA_lo = [&](int s) { return base + s * STG + A_PLANE_BYTES; };
+  auto sB_hi = [&](int s) { return base + s * STG + 2 * A_PLANE_BYTES; };
+  auto sB_lo = [&](int s) { return base + s * STG + 2 * A_PLANE_BYTES + BPLANE; };
   auto full_bar = [&](int s) { return bar0 + 8 * s; };                      // used in the leader only
-  auto empty_bar = [&](int s) { return bar0 + 8 * (STAGES + s); };          // one per CTA
-  auto tfull_bar = [&](int b) { return bar0 + 8 * (2 * STAGES + b); };      // one per CTA
-  auto tempty_bar = [&](int b) { return bar0 + 8 * (2 * STAGES + 2 + b); }; // used in the leader only
-  auto raw_bar = [&](int s) { return bar0 + 8 * (2 * STAGES + 4 + s); };    // one per CTA: raw A tile landed
-  const uint32_t tmem_slot = bar0 + 8 * (3 * STAGES + 4);
-  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(gbase + STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 8 * (3 * STAGES + 4));
+  auto empty_bar = [&](int s) { return bar0 + 8 * (NSTAGES + s); };          // one per CTA
+  auto tfull_bar = [&](int b) { return bar0 + 8 * (2 * NSTAGES + b); };      // one per CTA
+  auto tempty_bar = [&](int b) { return bar0 + 8 * (2 * NSTAGES + 2 + b); }; // used in the leader only
+  auto raw_bar = [&](int s) { return bar0 + 8 * (2 * NSTAGES + 4 + s); };    // one per CTA: raw A tile landed
+  const uint32_t tmem_slot = bar0 + 8 * (3 * NSTAGES + 4);
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(gbase + NSTAGES * STG + EPI_STAGE_BYTES + 8 * (3 * NSTAGES + 4));
   const uint32_t sub_smem = bar0 + SMEM_BAR_BYTES;  // [nkb * TK] floats: the centre, zero-padded
-  float *sub_ptr = reinterpret_cast<float *>(gbase + STAGES * STAGE_BYTES + EPI_STAGE_BYTES + SMEM_BAR_BYTES);
+  float *sub_ptr = reinterpret_cast<float *>(gbase + NSTAGES * STG + EPI_STAGE_BYTES + SMEM_BAR_BYTES);
 
   const int nkb = (K + TK - 1) / TK;
   const int n_panels = work.panel_hi - work.panel_lo;
@@ -265,7 +282,7 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
   if (pro.sub)
     for (int k = threadIdx.x; k < nkb * TK; k += THREADS) sub_ptr[k] = k < K ? __ldg(pro.sub + k) : 0.f;
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < NSTAGES; ++s) {
       mbar_init(full_bar(s), 1 + 2 * CONV_WARPS);  // leader's expect_tx arrival + converter warps of both CTAs
       mbar_init(empty_bar(s), 1);                  // tcgen05.commit (multicast)
       mbar_init(raw_bar(s), 1);                    // this CTA's TMA warp (expect_tx)
@@ -291,14 +308,14 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
       for (int64_t t = work.tile_first; t < work.tile_end; t += work.tile_step) {
         const int row0 = (int)(t * TM2 + (int64_t)rank * TM);
         for (int p = 0; p < n_panels; ++p) {
-          const int n0 = (work.panel_lo + p) * TN + (int)rank * TNH;
+          const int n0 = (work.panel_lo + p) * TNV + (int)rank * (TNV / 2);
           for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
+            const int s = it % NSTAGES;
+            const uint32_t ph = (it / NSTAGES) & 1;
             mbar_wait(empty_bar(s), ph ^ 1);
             mbar_expect_tx(raw_bar(s), A_PLANE_BYTES);
             tma_load_2d_local(sA_hi(s), tmA, raw_bar(s), kb * TK, row0);
-            if (rank == 0) mbar_expect_tx(full_bar(s), 4 * B_PLANE_BYTES);  // both planes, both CTAs
+            if (rank == 0) mbar_expect_tx(full_bar(s), 4 * (TNV / 2) * TK * 4);  // both planes, both CTAs
             const uint32_t lbar = map_to_cta(full_bar(s), 0);
             tma_load_2d_pair(sB_hi(s), tmB_hi, lbar, kb * TK, n0);
             tma_load_2d_pair(sB_lo(s), tmB_lo, lbar, kb * TK, n0);
@@ -318,8 +335,8 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(ab * TN);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+          const int s = it % NSTAGES;
+          const uint32_t ph = (it / NSTAGES) & 1;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           if (lane == 0) {
@@ -328,9 +345,14 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
 #pragma unroll
             for (int k4 = 0; k4 < TK / 8; ++k4) {
               const uint64_t adv = (uint64_t)((k4 * 8 * 4) >> 4);  // 32 bytes per UMMA_K=8 step
-              umma_tf32(tacc, dA_lo + adv, dB_hi + adv, kInstrDesc, (kb | k4) != 0 ? 1u : 0u);
-              umma_tf32(tacc, dA_hi + adv, dB_lo + adv, kInstrDesc, 1u);
-              umma_tf32(tacc, dA_hi + adv, dB_hi + adv, kInstrDesc, 1u);
+              if constexpr (NCAT) {
+                umma_tf32(tacc, dA_hi + adv, dB_hi + adv, InstrDesc<2 * TNV>::value, (kb | k4) != 0 ? 1u : 0u);
+                umma_tf32(tacc + 2 * TNV, dA_lo + adv, dB_hi + adv, InstrDesc<TNV>::value, (kb | k4) != 0 ? 1u : 0u);
+              } else {
+                umma_tf32(tacc, dA_lo + adv, dB_hi + adv, InstrDesc<TNV>::value, (kb | k4) != 0 ? 1u : 0u);
+                umma_tf32(tacc, dA_hi + adv, dB_lo + adv, InstrDesc<TNV>::value, 1u);
+                umma_tf32(tacc, dA_hi + adv, dB_hi + adv, InstrDesc<TNV>::value, 1u);
+              }
             }
             umma_commit(empty_bar(s));                       // smem slot reusable (both CTAs) when these MMAs retire
             if (kb == nkb - 1) umma_commit(tfull_bar(ab));   // accumulators ready for both epilogues
@@ -352,9 +374,9 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
       const uint32_t aph = (pc >> 1) & 1;
       mbar_wait(tfull_bar(ab), aph);
       tc_fence_after();
-      const int64_t n0 = (int64_t)(work.panel_lo + p) * TN;
+      const int64_t n0 = (int64_t)(work.panel_lo + p) * TNV;
 #pragma unroll 1
-      for (int c0 = 0; c0 < TN; c0 += 32) {
+      for (int c0 = 0; c0 < (NCAT ? 3 * TNV : TNV); c0 += 32) {
         float v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(ab * TN + c0), v);
         epi.consume(n0 + c0, v, ew, lane);
@@ -414,7 +436,7 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(lfull0 + 8 * (uint32_t)s);  // one arrival per converter warp
       if (++kb == nkb) kb = 0;
-      if (++s == STAGES) {
+      if (++s == NSTAGES) {
         s = 0;
         ph ^= 1;
       }
@@ -434,6 +456,11 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
 // dynamic shared memory: stages + barriers + the zero-padded centre [ceil(K / TK) * TK floats] + alignment slack
 static inline size_t smem_bytes(int K) {
   return (size_t)STAGES * STAGE_BYTES + EPI_STAGE_BYTES + SMEM_BAR_BYTES + (size_t)((K + TK - 1) / TK) * TK * 4 + SMEM_ALIGN;
+}
+// same for a narrow-panel variant (panel width tn, nstages stages)
+inline size_t smem_bytes_variant(int K, int tn, int nstages) {
+  return (size_t)nstages * (2 * A_PLANE_BYTES + 2 * (tn / 2) * TK * 4) + EPI_STAGE_BYTES + SMEM_BAR_BYTES +
+         (size_t)((K + TK - 1) / TK) * TK * 4 + SMEM_ALIGN;
 }
 constexpr int kMaxK = 4096;  // keeps the centre within the shared-memory budget
 

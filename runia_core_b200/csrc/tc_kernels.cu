@@ -223,6 +223,48 @@ struct ClassCondEpi {
   }
 };
 
+// (a10) ReAct / DICE / DICE+ReAct head: the 32-column panel holds the C <= 32 class logits of the row
+// (clip applied by the converters); out = logsumexp_c (v_c + b_c)      postprocessors.py:1464-1472, 1340-1352
+constexpr int kNarrowN = 32;
+constexpr int kNarrowStages = 5;  // 36 KB stages: 80 KB of rows in flight per CTA (HBM-bound stream)
+struct LinearLseEpi {
+  const float *bias;  // [C]
+  int C;
+  float *out;
+  int64_t M;
+  int64_t row;
+  __device__ void set_stage(uint32_t) {}
+  template <class P> __device__ void bind(const P *) {}
+  __device__ void begin(int, int64_t row_) { row = row_; }
+  float l[kNarrowN];
+  // three 32-column groups per row (tc_gemm.cuh, NCAT): [hi x c 0-15 | lo x c 0-15], [hi x c 16-31 | lo x c 16-31],
+  // A_lo x B_hi for c 0-31
+  __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
+    if (col0 == 0) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) l[c] = v[c] + v[16 + c];
+    } else if (col0 == 32) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) l[16 + c] = v[c] + v[16 + c];
+    } else {
+      if (row >= M) return;
+      constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kNarrowN; ++c) {
+        l[c] = c < C ? (l[c] + v[c]) + __ldg(bias + c) : -INFINITY;
+        m = fmaxf(m, l[c]);
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < kNarrowN; ++c) s += exp2f((l[c] - m) * kLog2e);  // exp2(-inf) = 0 for the padding
+      out[row] = fmaf(__log2f(s), kLn2, m);
+    }
+  }
+  __device__ void panel_done(int) {}
+  __device__ void finish() {}
+};
+
 // (a9) DDU / GMM: columns are C blocks of dpad whitened coordinates; per class
 // lp_c = -0.5 sum_j (v_j - off_j)^2 + logconst_c, out = logsumexp_c lp_c (online, per thread)
 struct GmmEpi {
@@ -594,6 +636,24 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, int64_t M, int K, Prologue pr
   run_tiles(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
+// Narrow-panel variant (UMMA N = 32): streaming heads whose output is a handful of columns per row.
+template <class E>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+tc_narrow_kernel(const __grid_constant__ CUtensorMap tmA, int64_t M, int K, Prologue pro,
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                 const __grid_constant__ E epi_param) {
+  extern __shared__ unsigned char smem_raw[];
+  E epi = epi_param;
+  epi.bind(&epi_param);
+  Work w;
+  w.tile_first = blockIdx.x >> 1;
+  w.tile_end = (M + TM2 - 1) / TM2;
+  w.tile_step = gridDim.x >> 1;
+  w.panel_lo = 0;
+  w.panel_hi = 1;
+  run_tiles<E, kNarrowN, kNarrowStages, true>(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
+}
+
 __device__ __forceinline__ Work split_work(int panels_total, int panels_per_split) {
   Work w;  // one 256-row tile x one bank split per CTA pair
   w.tile_first = blockIdx.x >> 1;
@@ -745,6 +805,35 @@ extern "C" int runia_rownorm_score_tc(const float *X, int64_t N, int d, const fl
                                                                           panels, epi);
   count_launch();
   return finish_launch("rownorm_score_tc");
+}
+
+extern "C" int runia_clip_linear_lse_tc(const float *X, int64_t N, int d, const float *W_hi, const float *W_lo,
+                                        const float *b, int C, float clip, float *out, void *stream) {
+  RUNIA_REQUIRE(N >= 0 && d > 0 && C > 0, RUNIA_E_BADARG, "clip_linear_lse_tc: bad sizes");
+  RUNIA_REQUIRE(C <= kNarrowN, RUNIA_E_UNSUPPORTED, "clip_linear_lse_tc: C=%d classes not supported (max %d)", C, kNarrowN);
+  if (N == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(X && W_hi && W_lo && b && out, RUNIA_E_BADARG, "clip_linear_lse_tc: null pointer");
+  RUNIA_REQUIRE(usable(X, d, W_hi, W_lo), RUNIA_E_UNSUPPORTED,
+                "clip_linear_lse_tc: needs d %% 4 == 0, d <= %d and 16-byte aligned pointers", kMaxK);
+  CUtensorMap ma, mh, ml;
+  int rc = make_a_map(&ma, X, N, d);
+  if (rc) return rc;
+  rc = make_map(&mh, W_hi, kNarrowN, d, kNarrowN / 2);  // planes are [32, d], rows >= C zero
+  if (rc) return rc;
+  rc = make_map(&ml, W_lo, kNarrowN, d, kNarrowN / 2);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    rc = set_smem(tc_narrow_kernel<LinearLseEpi>, smem_bytes_variant(kMaxK, kNarrowN, kNarrowStages));
+    if (rc) return rc;
+    attr = true;
+  }
+  LinearLseEpi epi{b, C, out, N, 0};
+  dim3 grid(2 * (unsigned)std::min<int64_t>(ceil_div(N, TM2), kNumSMs / 2), 1);
+  tc_narrow_kernel<LinearLseEpi><<<grid, THREADS, smem_bytes_variant(d, kNarrowN, kNarrowStages), (cudaStream_t)stream>>>(ma, N, d, Prologue{nullptr, clip}, mh,
+                                                                                     ml, epi);
+  count_launch();
+  return finish_launch("clip_linear_lse_tc");
 }
 
 extern "C" int runia_pca_transform_tc(const float *X, int64_t N, int D0, const float *mean, const float *C_hi,

@@ -369,3 +369,27 @@ def test_entropy_widths_vs_oracle(R, D):
     rm, rz = O.get_dl_h_z(z, n_mc, chunk=32)
     assert hz.shape == (n_items, D) and hm.shape == (n_items, 1)
     assert rel_err(hz, rz) < RTOL and rel_err(hm, rm) < RTOL
+
+
+@pytest.mark.parametrize("d,C,clip", [(512, 10, 1.0), (1000, 21, np.inf), (36, 32, 0.5), (2048, 10, 1.2)])
+def test_react_head_tensor_path_vs_oracle(R, d, C, clip):
+    """ReAct / DICE head through the narrow-panel tcgen05 kernel (>= 16384 rows, d % 4 == 0, C <= 32): ragged last
+    row tile, K tails, every class count up to the panel width; same rows through the one-warp-per-row kernel."""
+    from runia_core_b200 import _lib, _ops
+
+    rng = np.random.RandomState(d + C)
+    n = 16384 + 777
+    x = np.maximum(rng.randn(n, d), 0).astype(np.float32)
+    x[3] = 0.0
+    x[7] *= 50.0
+    W = (0.05 * rng.randn(C, d)).astype(np.float32)
+    b = rng.randn(C).astype(np.float32)
+    Wd, bd = torch.from_numpy(W).cuda(), torch.from_numpy(b).cuda()
+    before = _lib.launch_count()
+    got = _ops.clip_linear_lse(x, Wd, bd, clip=clip).cpu().numpy()
+    assert _lib.launch_count() - before == 2  # split of the padded planes + the tensor kernel
+    ref = O.react_score(x, W, b, clip)
+    assert rel_err(got, ref) < RTOL
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
+    simt = _ops.clip_linear_lse(x[:5000], Wd, bd, clip=clip).cpu().numpy()
+    np.testing.assert_allclose(simt, got[:5000], rtol=2e-5, atol=2e-5)
