@@ -478,6 +478,21 @@ def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak):
     out["mc_sampler_1024x512x7x7"] = {"images_per_s": Bm / (ms * 1e-3), "ms": ms, "torch_ops_same_gpu_ms": ms_t,
                                       "roofline": hbm(xm.numel() * 4 + Bm * n_mc * Cm * 4, ms)}
     del xm, seed
+    # (a2 + a3 fused) PCA 512 -> 256 + LaREM as one contraction over the raw latents (2,056 B / embedding)
+    rngf = np.random.RandomState(5)
+    comps = np.linalg.qr(rngf.randn(512, 256))[0].T.copy()
+    var = 1.0 + rngf.rand(256)
+    Af = rngf.randn(256, 256)
+    fst = _ops.md_fold_pca(rngf.randn(512), comps, var, True, 0.01 * rngf.randn(256), Af @ Af.T / 256 + np.eye(256))
+    pst = _ops.pca_prepare(rngf.randn(512), comps, var, True)
+    mst = _ops.md_prepare(0.01 * rngf.randn(256), Af @ Af.T / 256 + np.eye(256))
+    xr = torch.randn(2_000_000, 512, generator=g, device=dev)
+    ms = _time_op(torch, lambda: _ops.md_score(xr, fst))
+    ms_st = _time_op(torch, lambda: _ops.md_score(_ops.pca_transform(xr, pst), mst))
+    out["pca_larem_fused_512_256"] = {"embeddings_per_s": 2_000_000 / (ms * 1e-3), "ms": ms, "staged_two_kernels_ms": ms_st,
+                                      "fp32_equiv_tflops": 2_000_000 * 262_656 / (ms * 1e-3) / 1e12,
+                                      "roofline": hbm(2_000_000 * 2056, ms)}
+    del xr
     # (f2) setup() statistics: class means + float64 Gram matrix of a 50k x 512 bank with 10 classes
     xs = torch.randn(50_000, 512, generator=g, device=dev)
     lab = torch.randint(0, 10, (50_000,), generator=g, device=dev).cpu().numpy()

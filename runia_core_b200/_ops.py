@@ -161,6 +161,31 @@ def md_prepare(mean, precision) -> MDState:
                    split_tf32(w32) if Wt.shape[1] % 4 == 0 else None)
 
 
+def md_fold_pca(pca_mean, components, explained_variance, whiten, md_mean, precision) -> Optional[MDState]:
+    """LaREM on PCA-reduced latents as ONE contraction over the raw latents (2,056 B and 262,656 FLOP
+    per embedding at 512 -> 256, no intermediate [N, d] array): with z = (x - m) A^T (A = components / scale) and
+    P = sum_j s_j w_j w_j^T,  (z - mu)^T P (z - mu) = sum_j s_j (w_j^T A (x - m'))^2  where  W A (m' - m) = W mu.
+    Returns None when that centre does not exist (W A without full row rank)."""
+    comp = np.ascontiguousarray(components, np.float64)
+    A = comp
+    if whiten:
+        scale = np.sqrt(np.asarray(explained_variance, np.float64))
+        eps = np.finfo(np.asarray(explained_variance).dtype).eps
+        A = comp / np.where(scale < eps, eps, scale)[:, None]
+    Wt, sign = factor_precision(precision)
+    Wf = Wt @ A                                                   # [r, D0]
+    v = Wt @ np.asarray(md_mean, np.float64).reshape(-1)          # [r]
+    delta = np.linalg.lstsq(Wf, v, rcond=None)[0]
+    if np.abs(Wf @ delta - v).max() > 1e-9 * (1.0 + np.abs(v).max()):
+        return None
+    m = (0.0 if pca_mean is None else np.asarray(pca_mean, np.float64).reshape(-1)) + delta
+    mu64 = to_device(m)
+    sg = None if np.all(sign == 1.0) else to_device(sign.astype(np.float32))
+    w32 = to_device(Wf.astype(np.float32))
+    return MDState(mu64.to(torch.float32), mu64, w32, sg, Wf.shape[1], Wf.shape[0],
+                   split_tf32(w32) if Wf.shape[1] % 4 == 0 else None)
+
+
 def _rownorm(xf, n, d, mu, W, planes, r, sign, mode, logits, C, alpha, o64, o32):
     if _tc_ok(d) and planes is not None:
         _lib.call("runia_rownorm_score_tc", xf.data_ptr(), n, d, mu, planes[0].data_ptr(), planes[1].data_ptr(), r,

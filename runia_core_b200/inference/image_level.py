@@ -14,7 +14,29 @@ from .. import _ops
 from .._device import to_device, to_host
 from .abstract_classes import ProbabilisticInferenceModule
 
-__all__ = ["LaRExInference"]
+__all__ = ["LaRExInference", "FoldedLaREM"]
+
+
+class FoldedLaREM:
+    """PCA transform + LaREM (`apply_pca_transform` -> `MDLatentSpace.postprocess`,
+    dimensionality_reduction.py:86 + postprocessors.py:241-243) as one contraction over the raw latents:
+    the fitted PCA and the factored precision are multiplied together once on the host, and the row scorer
+    reads each raw latent once -- no intermediate [N, d] array.  `postprocess` has the postprocessor's signature."""
+
+    def __init__(self, pca_transform, md_postprocessor):
+        self._state = _ops.md_fold_pca(pca_transform.mean_, pca_transform.components_, pca_transform.explained_variance_,
+                                       pca_transform.whiten, md_postprocessor.feats_mean, md_postprocessor.precision)
+        if self._state is None:
+            raise ValueError("PCA and precision cannot be folded (rank-deficient product)")
+
+    def postprocess_device(self, test_data) -> torch.Tensor:
+        return _ops.md_score(test_data, self._state, torch.float64)
+
+    def postprocess(self, test_data, **kwargs) -> np.ndarray:
+        assert test_data.ndim == 2, "test_feats must be 2 dimensional"
+        return to_host(self.postprocess_device(test_data))
+
+    __call__ = postprocess
 
 
 class LaRExInference(ProbabilisticInferenceModule):
@@ -28,6 +50,13 @@ class LaRExInference(ProbabilisticInferenceModule):
                                       drop_prob=self.drop_block_prob, block_size=self.drop_block_size)
         self.mc_sampler.to(self.device)
         self.mc_sampler.train()
+        self._folded = None
+        if pca_transform is not None and hasattr(postprocessor, "precision") and hasattr(postprocessor, "feats_mean") \
+                and hasattr(pca_transform, "components_") and getattr(postprocessor, "precision", None) is not None:
+            try:
+                self._folded = FoldedLaREM(pca_transform, postprocessor)  # PCA + LaREM as one launch
+            except ValueError:
+                self._folded = None
 
     def score_samples(self, mc_samples_t) -> np.ndarray:
         """[N * n_mc, D] MC samples (any device) -> LaREx scores [N]: entropy -> PCA -> postprocessor, on the GPU
@@ -37,6 +66,8 @@ class LaRExInference(ProbabilisticInferenceModule):
         if z.shape[0] % n_mc != 0:
             raise ValueError(f"{z.shape[0]} sample rows are not a multiple of mcd_samples_nro={n_mc}")
         _, h_z = _ops.mcd_entropy(z, n_mc, k=_ops.entropy_k(n_mc), want_joint=False)
+        if self._folded is not None:
+            return to_host(self._folded.postprocess_device(h_z))
         if self.pca_transform:
             h_z = self.pca_transform.transform_device(h_z) if hasattr(self.pca_transform, "transform_device") \
                 else self.pca_transform.transform(to_host(h_z))

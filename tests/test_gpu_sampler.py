@@ -106,3 +106,27 @@ def test_larex_online_chain_matches_staged_api():
     staged = md.postprocess(R.apply_pca_transform(hz1, pca))
     assert out.shape == (1, 10) and score.shape == (1,) and score.dtype == np.float64
     np.testing.assert_allclose(score, staged, rtol=1e-5)
+
+
+def test_folded_pca_larem_matches_staged():
+    """FoldedLaREM (one contraction over the raw latents) == apply_pca_transform -> MDLatentSpace.postprocess."""
+    import runia_core_b200 as R
+
+    rng = np.random.RandomState(3)
+    D0, d = 512, 256
+    mix = np.eye(D0) + 0.2 * rng.standard_normal((D0, D0)) / np.sqrt(D0)
+    train = (0.5 + rng.standard_normal((20_000, D0)) @ mix).astype(np.float32)
+    test = (-0.2 + rng.standard_normal((30_000, D0)) @ mix).astype(np.float32)
+    np.random.seed(1)
+    z_train, pca = R.apply_pca_ds_split(train, nro_components=d)
+    md = R.inference.postprocessors_dict["MD"]()
+    md.setup(z_train)
+    staged = md.postprocess(R.apply_pca_transform(test, pca))
+    folded = R.inference.FoldedLaREM(pca, md)
+    got = folded.postprocess(test)
+    assert got.dtype == np.float64 and got.shape == staged.shape
+    np.testing.assert_allclose(got, staged, rtol=2e-5)
+    md2 = R.inference.postprocessors_dict["MD"]()
+    md2.setup((z_train + 3.0).astype(np.float32))  # a LaREM centre away from the PCA origin
+    np.testing.assert_allclose(R.inference.FoldedLaREM(pca, md2).postprocess(test),
+                               md2.postprocess(R.apply_pca_transform(test, pca)), rtol=2e-5)
