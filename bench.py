@@ -265,7 +265,7 @@ def run_b200(args):
         extra.update(_extra_other_kernels(torch, _ops, hbm_peak, bf16_peak))
         if world == 1 and not args.no_sweep:
             extra["sweep_config2"] = _extra_sweep_config2(R)
-    if world > 1 and not args.no_extra:
+    if not args.no_extra and (world > 1 or not args.no_sweep):
         extra.update(_extra_sharded_knn(args, torch, dist, _ops, world, rank, barrier, max_over_ranks))
 
     cpu_baseline = None
@@ -493,6 +493,35 @@ def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak):
                                       "fp32_equiv_tflops": 2_000_000 * 262_656 / (ms * 1e-3) / 1e12,
                                       "roofline": hbm(2_000_000 * 2056, ms)}
     del xr
+    # (f3) online LaREx chain on one hooked map (sampler -> entropy -> folded PCA + LaREM -> score on the host),
+    # the body of LaRExInference.get_score after the model forward; wall clock per image, and the same chain batched
+    import time as _time
+    from runia_core_b200.feature_extraction import MCSamplerModule
+    smp = MCSamplerModule(mc_samples=16, block_size=3, drop_prob=0.3).train()
+    lat1 = torch.randn(1, 512, 7, 7, generator=g, device=dev)
+    latB = torch.randn(1024, 512, 7, 7, generator=g, device=dev)
+
+    def chain(lat):
+        rows = smp.sample_batch(lat)
+        _, hz = _ops.mcd_entropy(rows, 16, k=5, want_joint=False)
+        return _ops.md_score(hz, fst).cpu()
+
+    for _ in range(10):
+        chain(lat1)
+    torch.cuda.synchronize()
+    t0 = _time.perf_counter()
+    for _ in range(200):
+        chain(lat1)
+    us1 = (_time.perf_counter() - t0) / 200 * 1e6
+    chain(latB)
+    torch.cuda.synchronize()
+    t0 = _time.perf_counter()
+    for _ in range(20):
+        chain(latB)
+    msB = (_time.perf_counter() - t0) / 20 * 1e3
+    out["larex_online_chain"] = {"us_per_image_batch1": us1, "ms_per_1024_images": msB, "images_per_s_batched": 1024 / (msB * 1e-3),
+                                 "note": "wall clock incl. torch.rand seeds on the CPU generator, 16 samples, 512 x 7 x 7 map, score copied to host"}
+    del lat1, latB
     # (f2) setup() statistics: class means + float64 Gram matrix of a 50k x 512 bank with 10 classes
     xs = torch.randn(50_000, 512, generator=g, device=dev)
     lab = torch.randint(0, 10, (50_000,), generator=g, device=dev).cpu().numpy()
@@ -579,10 +608,13 @@ def _extra_sharded_knn(args, torch, dist, _ops, world, rank, barrier, max_over_r
 
     def step():
         r = _ops.knn_search(q, kb, k, want_f64=True, want_dist=False, check_status=False)
-        gd = torch.empty((world, nq, k), dtype=torch.float64, device=dev)
-        gi = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(gd, r["dist64"])
-        dist.all_gather_into_tensor(gi, r["idx"])
+        if world == 1:
+            gd, gi = r["dist64"].unsqueeze(0), r["idx"].unsqueeze(0)
+        else:
+            gd = torch.empty((world, nq, k), dtype=torch.float64, device=dev)
+            gi = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(gd, r["dist64"])
+            dist.all_gather_into_tensor(gi, r["idx"])
         out["m"] = _ops.topk_merge(gd, gi)
 
     step()
@@ -596,9 +628,31 @@ def _extra_sharded_knn(args, torch, dist, _ops, world, rank, barrier, max_over_r
     e1.record()
     torch.cuda.synchronize()
     ms = max_over_ranks(e0.elapsed_time(e1) / reps)
-    return {"knn_sharded": {"queries_per_s": nq / (ms * 1e-3), "ms": ms, "bank_rows_total": nb_rank * world,
-                            "d": d, "k": k, "scaling": "weak (bank grows with ranks)",
-                            "distance_tflops_per_gpu": 2.0 * nq * nb_rank * d / (ms * 1e-3) / 1e12}}
+    res = {"knn_sharded": {"queries_per_s": nq / (ms * 1e-3), "ms": ms, "bank_rows_total": nb_rank * world,
+                           "d": d, "k": k, "scaling": "weak (bank grows with ranks)",
+                           "distance_tflops_per_gpu": 2.0 * nq * nb_rank * d / (ms * 1e-3) / 1e12}}
+    if world == 1 and torch.cuda.mem_get_info()[0] > 130e9:
+        # strong-scaling reference point: the whole BASELINE configs[3] bank (8 shards = 10M x 768, 30.7 GB + its
+        # TF32 planes) on ONE GPU, same shards (seeds) as the 8-rank run, to set beside that run's time
+        del kb, bank
+        shards = 8
+        full = torch.empty((shards * nb_rank, d), dtype=torch.float32, device=dev)
+        for r in range(shards):
+            gr = torch.Generator(device=dev).manual_seed(100 + r)
+            full[r * nb_rank:(r + 1) * nb_rank] = _ops.normalize_rows(torch.randn(nb_rank, d, generator=gr, device=dev))
+        kbf = _ops.knn_bank(full)
+        _ops.knn_search(q, kbf, k, want_f64=True, want_dist=False, check_status=False)
+        torch.cuda.synchronize()
+        e0.record()
+        rr = _ops.knn_search(q, kbf, k, want_f64=True, want_dist=False, check_status=False)
+        e1.record()
+        torch.cuda.synchronize()
+        msf = e0.elapsed_time(e1)
+        res["knn_full_bank_1gpu"] = {"ms": msf, "queries_per_s": nq / (msf * 1e-3), "bank_rows_total": shards * nb_rank,
+                                     "distance_tflops": 2.0 * nq * shards * nb_rank * d / (msf * 1e-3) / 1e12,
+                                     "note": "same 8 shards as the 8-rank sharded run; compare with knn_sharded.ms at --gpus 8"}
+        del kbf, full
+    return res
 
 
 def _cpu_larem(md, seconds=8.0):
