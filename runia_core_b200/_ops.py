@@ -633,23 +633,35 @@ def class_means(x, labels=None, num_classes: int = 1):
     return means, counts.cpu().numpy(), xf, lab
 
 
-def centered_covariance(xf: torch.Tensor, lab, centers: torch.Tensor, n_used: int) -> np.ndarray:
-    """np.cov(R.T, bias=1) in float64 for the residual rows R = f32(x - centers[label]) (what
-    sklearn's EmpiricalCovariance(assume_centered=False).fit(R).covariance_ holds): device float64 Gram
-    matrix + column sums, np.cov's re-centring and 1/n scaling on the d x d result."""
+def centered_gram(xf: torch.Tensor, lab, centers: torch.Tensor):
+    """(G [d, d], colsum [d]) float64 device tensors: sum_i r_i r_i^T and sum_i r_i over the rows with a label in
+    [0, C), r_i = f32(x_i - centers[label_i]).  Deterministic; additive over row shards (all-reduce both)."""
     n, d = xf.shape
-    C = centers.shape[0]
     G = _empty((d, d), torch.float64)
     cs = _empty((d,), torch.float64)
     ws_bytes = int(_lib.raw("runia_centered_gram_workspace_bytes")(n, d))
     ws = _empty((ws_bytes,), torch.uint8)
-    _lib.call("runia_centered_gram_f64", xf.data_ptr(), ptr(lab), centers.data_ptr(), n, d, C, G.data_ptr(), cs.data_ptr(),
-              ws.data_ptr(), ws_bytes, stream_ptr())
-    G, cs = G.cpu().numpy(), cs.cpu().numpy()
+    _lib.call("runia_centered_gram_f64", xf.data_ptr(), ptr(lab), centers.data_ptr(), n, d, centers.shape[0], G.data_ptr(),
+              cs.data_ptr(), ws.data_ptr(), ws_bytes, stream_ptr())
+    return G, cs
+
+
+def covariance_from_gram(G, cs, n_used: int) -> np.ndarray:
+    """np.cov(R.T, bias=1) from the Gram matrix and column sums of the residual rows: np.cov's own re-centring
+    and 1/n scaling on the d x d result."""
+    G = G.cpu().numpy() if isinstance(G, torch.Tensor) else np.asarray(G)
+    cs = cs.cpu().numpy() if isinstance(cs, torch.Tensor) else np.asarray(cs)
     avg = cs / n_used
     cov = G - n_used * np.outer(avg, avg)
     cov *= np.true_divide(1, n_used)
     return cov
+
+
+def centered_covariance(xf: torch.Tensor, lab, centers: torch.Tensor, n_used: int) -> np.ndarray:
+    """np.cov(R.T, bias=1) in float64 for the residual rows R = f32(x - centers[label]) (what
+    sklearn's EmpiricalCovariance(assume_centered=False).fit(R).covariance_ holds)."""
+    G, cs = centered_gram(xf, lab, centers)
+    return covariance_from_gram(G, cs, n_used)
 
 
 # ------------------------------------------------------------------------------------------

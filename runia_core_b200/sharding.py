@@ -101,3 +101,44 @@ def merge_topk_reference(part_d: torch.Tensor, part_i: torch.Tensor):
         out_d[r, : ok.sum()] = dd[r][order][ok].astype(np.float32)
         out_i[r, : ok.sum()] = i[r][order][ok]
     return torch.from_numpy(out_d), torch.from_numpy(out_i), torch.from_numpy(out_d[:, -1].copy())
+
+
+def combine_class_means(local_means: torch.Tensor, local_counts: torch.Tensor, group=None):
+    """Per-rank class means [C, d] float32 + counts [C] -> the means of the whole bank (count-weighted, combined in
+    float64, returned as float32 [C, d]) and the global counts; identical on every rank (all-gather, fixed rank order).
+    A class that is empty everywhere keeps NaN, like `x[labels == c].mean(0)`."""
+    _, world = _world(group)
+    cnt = local_counts.to(device=local_means.device, dtype=torch.float64)
+    if world == 1:
+        return local_means, local_counts.to(torch.int64)
+    means = [torch.empty_like(local_means) for _ in range(world)]
+    cnts = [torch.empty_like(cnt) for _ in range(world)]
+    dist.all_gather(means, local_means.contiguous(), group=group)
+    dist.all_gather(cnts, cnt, group=group)
+    total = torch.stack(cnts).sum(0)                                                   # [C]
+    acc = torch.zeros_like(local_means, dtype=torch.float64)
+    for m, c in zip(means, cnts):                                                      # empty shards contribute 0, not NaN
+        acc += torch.where(c[:, None] > 0, m.to(torch.float64) * c[:, None], torch.zeros((), dtype=torch.float64, device=m.device))
+    gm = (acc / total[:, None]).to(torch.float32)                                      # 0 / 0 = NaN for an empty class
+    return gm, total.to(torch.int64)
+
+
+def fit_mean_precision_sharded(x_local, labels_local=None, num_classes: int = 1, group=None):
+    """setup() statistics of MDLatentSpace / cMD / Mahalanobis over a bank whose rows are sharded across the ranks
+    ("setup() statistics"): class means from the per-rank NumPy-ordered means, the float64 Gram
+    matrix of the class-centred residuals per rank, one all-reduce of d*d + d doubles, then `pinvh` on every rank
+    (replicated, identical).  Returns (means [C, d] float32 ndarray, counts [C], precision [d, d] float64)."""
+    from scipy.linalg import pinvh
+
+    from . import _ops
+
+    lm, lc, xf, lab = _ops.class_means(x_local, labels_local, num_classes)
+    gm, total = combine_class_means(lm, torch.from_numpy(lc), group)
+    G, cs = _ops.centered_gram(xf, lab, gm)
+    _, world = _world(group)
+    if world > 1:
+        dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM, group=group)
+    n_used = int(total.sum())
+    cov = _ops.covariance_from_gram(G, cs, n_used)
+    return gm.cpu().numpy(), total.cpu().numpy(), pinvh(cov, check_finite=False)

@@ -12,6 +12,7 @@ import sys
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -45,11 +46,33 @@ def main():
     lst = [torch.empty_like(chk) for _ in range(world)]
     dist.all_gather(lst, chk)
     same = all(bool(torch.equal(lst[0][:2], t[:2])) and float((lst[0][2] - t[2]).abs()) < 1e-6 for t in lst)
-    flags = torch.tensor([int(ok_knn), int(err < 1e-6), int(same)], device=dev)
+    # setup() statistics over a row-sharded bank vs the single-GPU fit of the whole bank
+    from scipy.linalg import pinvh
+    C, nf, df = 7, 60_001, 128
+    labels = torch.randint(0, C, (nf,), generator=g, device=dev)
+    labels[labels == 3] = 4  # an empty class
+    mu = torch.randn(C, df, generator=g, device=dev)
+    feats = (mu[labels] + torch.randn(nf, df, generator=g, device=dev)).contiguous()
+    lab_np = labels.cpu().numpy()
+    m1, c1, xf1, l1 = _ops.class_means(feats, lab_np, C)
+    cov1 = _ops.centered_covariance(xf1, l1, m1, int(c1.sum()))
+    p1 = pinvh(cov1, check_finite=False)
+    flo, fhi = sharding.row_shard(nf, rank, world)
+    m2, c2, p2 = sharding.fit_mean_precision_sharded(feats[flo:fhi].contiguous(), lab_np[flo:fhi], C)
+    m1h = m1.cpu().numpy()
+    okc = np.arange(C) != 3
+    mean_err = float(np.abs(m2[okc] - m1h[okc]).max())
+    prec_err = float(np.abs(p2 - p1).max() / np.abs(p1).max())
+    # the single-GPU means are float32 row-by-row sums (NumPy order, ~1e-5 of rounding at 8.5k rows per class); the
+    # sharded combination is at least as accurate
+    ok_fit = bool(np.array_equal(c2, c1) and np.isnan(m2[3]).all() and mean_err < 5e-5 and prec_err < 1e-6)
+    flags = torch.tensor([int(ok_knn), int(err < 1e-6), int(same), int(ok_fit)], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"world": world, "bank_rows": nb, "queries": nq, "k": k, "knn_bit_exact": bool(flags[0]),
-                          "kde_max_rel_err": err, "kde_ok": bool(flags[1]), "identical_on_all_ranks": bool(flags[2])}))
+                          "kde_max_rel_err": err, "kde_ok": bool(flags[1]), "identical_on_all_ranks": bool(flags[2]),
+                          "sharded_fit_ok": bool(flags[3]), "sharded_fit_mean_abs_err": mean_err,
+                          "sharded_fit_precision_rel_err": prec_err}))
     dist.destroy_process_group()
     sys.exit(0 if bool(flags.min()) else 1)
 

@@ -176,6 +176,22 @@ def _gloo_worker(rank, world, port, ret):
 
         loc = torch.arange(*S.row_shard(11, rank, world), dtype=torch.float64)
         ok = ok and torch.equal(S.gather_rows(loc, 11), torch.arange(11, dtype=torch.float64))
+
+        # setup() statistics over row shards: count-weighted combination of the per-rank class means
+        feats = rng.randn(101, 5).astype(np.float32)
+        labels = rng.randint(0, 4, 101)
+        labels[labels == 2] = 1                      # class 2 empty everywhere
+        labels[:51][labels[:51] == 3] = 0            # class 3 lives on rank 1 only (world 2)
+        flo, fhi = S.row_shard(101, rank, world)
+        xs, ls = feats[flo:fhi], labels[flo:fhi]
+        with np.errstate(all="ignore"):
+            lm = np.stack([xs[ls == c].mean(0) if (ls == c).any() else np.full(5, np.nan, np.float32) for c in range(4)])
+        lc = np.array([(ls == c).sum() for c in range(4)])
+        gm, total = S.combine_class_means(torch.from_numpy(lm.astype(np.float32)), torch.from_numpy(lc))
+        ref = np.stack([feats[labels == c].astype(np.float64).mean(0) if (labels == c).any() else np.full(5, np.nan)
+                        for c in range(4)])
+        ok = ok and np.array_equal(total.numpy(), [(labels == c).sum() for c in range(4)])
+        ok = ok and np.allclose(gm.numpy(), ref, rtol=0, atol=1e-6, equal_nan=True) and np.isnan(gm.numpy()[2]).all()
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
