@@ -65,6 +65,14 @@ def _linear_params(kwargs):
 # ------------------------------------------------------------------------------------------------
 # LaRED: Gaussian KDE over the latent bank            reference: postprocessors.py:78-178
 # ------------------------------------------------------------------------------------------------
+def _head_planes(W):
+    """TF32 planes of a head's weight matrix for the tensor-core linear head, built once at setup
+    (None when the head does not qualify: more than 32 classes or a width that is not a multiple of 4)."""
+    if W.shape[0] <= _ops.LINEAR_TC_MAX_CLASSES and W.shape[1] % 4 == 0:
+        return _ops.linear_planes(W)
+    return None
+
+
 def _device_fit(feats, labels, num_classes):
     """float32 features -> (class means [C, d] float32, counts [C], shared precision [d, d] float64) from
     device statistics: NumPy-ordered means (bit-identical to `feats[labels == c].mean(0)`), the float64
@@ -528,13 +536,14 @@ class DICE(OodPostprocessor):
         self.device = "cuda" if torch.cuda.is_available() else "cpu"
 
     def _score(self, x):
-        return to_host(_ops.clip_linear_lse(x, self.dice_layer.masked_w, self._b))
+        return to_host(_ops.clip_linear_lse(x, self.dice_layer.masked_w, self._b, planes=getattr(self, "_planes", None)))
 
     def setup(self, ind_train_data: np.ndarray, **kwargs):
         assert "final_linear_layer_params" in kwargs, "final_linear_layer_params must be provided for DICE"
         assert "valid_feats" in kwargs, "valid_feats must be provided for DICE"
         self.dice_layer = _make_dice_layer(ind_train_data, kwargs, self.num_classes, self.dice_percentile)
         self._b = to_device(self.dice_layer.bias.detach(), torch.float32)
+        self._planes = _head_planes(self.dice_layer.masked_w)
         self.set_threshold(self.flip_sign_fn(self._score(kwargs["valid_feats"])))
 
     def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:
@@ -552,13 +561,14 @@ class ReAct(OodPostprocessor):
         self.b = None
 
     def _score(self, x):
-        return to_host(_ops.clip_linear_lse(x, self._w, self._b, clip=float(self.activation_threshold)))
+        return to_host(_ops.clip_linear_lse(x, self._w, self._b, clip=float(self.activation_threshold), planes=getattr(self, "_planes", None)))
 
     def setup(self, ind_train_data: np.ndarray, **kwargs):
         assert "final_linear_layer_params" in kwargs, "final_linear_layer_params must be provided for ReAct"
         assert "valid_feats" in kwargs, "valid_feats must be provided for ReAct"
         self.w, self.b = _linear_params(kwargs)
         self._w, self._b = to_device(self.w, torch.float32), to_device(self.b, torch.float32)
+        self._planes = _head_planes(self._w)
         self.activation_threshold = _train_percentile(ind_train_data, self.react_percentile)
         self.set_threshold(self.flip_sign_fn(self._score(kwargs["valid_feats"])))
 
@@ -581,13 +591,14 @@ class DICEReAct(OodPostprocessor):
 
     def _score(self, x):
         return to_host(_ops.clip_linear_lse(x, self.dice_layer.masked_w, self._b,
-                                            clip=float(self.react_activation_threshold)))
+                                            clip=float(self.react_activation_threshold), planes=getattr(self, "_planes", None)))
 
     def setup(self, ind_train_data: np.ndarray, **kwargs):
         assert "final_linear_layer_params" in kwargs, "final_linear_layer_params must be provided for DICE"
         assert "valid_feats" in kwargs, "valid_feats must be provided for DICE"
         self.dice_layer = _make_dice_layer(ind_train_data, kwargs, self.num_classes, self.dice_percentile)
         self._b = to_device(self.dice_layer.bias.detach(), torch.float32)
+        self._planes = _head_planes(self.dice_layer.masked_w)
         self.react_activation_threshold = _train_percentile(ind_train_data, self.react_percentile)
         self.set_threshold(self.flip_sign_fn(self._score(kwargs["valid_feats"])))
 

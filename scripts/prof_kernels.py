@@ -58,8 +58,9 @@ if "linear" in which:
     X = torch.relu(torch.randn(2_000_000, 512, generator=g, device=dev))
     W = 0.05 * torch.randn(10, 512, generator=g, device=dev)
     b = torch.randn(10, generator=g, device=dev)
+    planes = _ops.linear_planes(W)
     for _ in range(REPS):
-        o = _ops.clip_linear_lse(X, W, b, clip=1.0)
+        o = _ops.clip_linear_lse(X, W, b, clip=1.0, planes=planes)
         o = _ops.ash_linear_lse(X, W, b, 77)
     torch.cuda.synchronize()
 if "logits" in which:
