@@ -44,10 +44,27 @@ class MCSamplerModule(torch.nn.Module):
         return _ops.mc_dropblock_mean(latent_rep, seeds, self.block_size)
 
     def forward(self, latent_rep):
-        """Reference semantics (one image per call): [1, C, H, W] -> [n_mc, C].  "FC" / "RPN" layers keep the
-        masked map unreduced in the reference; only the reduced ("Conv") form is a hot path here."""
+        """Reference semantics (one image per call): "Conv": [1, C, H, W] -> [n_mc, C] (fused kernel);
+        "FC" / "RPN": the unreduced masked maps [n_mc, numel]."""
         if self.layer_type != "Conv":
-            raise NotImplementedError("MCSamplerModule: only layer_type='Conv' (DropBlock + H x W mean) is built")
+            # "FC" / "RPN": the masked maps themselves, flattened ([n_mc, B*C*H*W]); no reduction follows, so this is
+            # DropBlock2D's published forward in torch ops on the same seeds (not a hot path: nothing downstream
+            # of it is on the scoring path of SURVEY section 8)
+            import torch.nn.functional as F
+
+            if not self.training or self.drop_prob == 0.0:
+                return latent_rep.reshape(1, -1).repeat(self.mc_samples, 1)
+            seeds = self.draw_seeds(latent_rep).to(latent_rep.device)
+            bs = self.block_size
+            out = []
+            for m in range(self.mc_samples):
+                bm = F.max_pool2d(seeds[m].float()[:, None], kernel_size=(bs, bs), stride=(1, 1), padding=bs // 2)
+                if bs % 2 == 0:
+                    bm = bm[:, :, :-1, :-1]
+                bm = 1 - bm.squeeze(1)
+                o = latent_rep * bm[:, None, :, :]
+                out.append((o * bm.numel() / bm.sum()).reshape(1, -1))
+            return torch.cat(out)
         rows = self.sample_batch(latent_rep)
         if latent_rep.shape[0] == 1:
             return rows

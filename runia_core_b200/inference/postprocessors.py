@@ -378,8 +378,9 @@ class DDU(OodPostprocessor):
     def setup(self, ind_train_data: np.ndarray, **kwargs):
         assert "valid_feats" in kwargs, "valid_feats must be provided for DDU"
         assert "train_labels" in kwargs, "train_labels must be provided for DDU"
-        self.gmm, _ = gmm_fit(embeddings=Tensor(_np(ind_train_data)), labels=Tensor(_np(kwargs["train_labels"])),
-                              num_classes=self.num_classes)
+        # like the reference (:751-755) the fit runs where self.device points: torch on the GPU when there is one
+        self.gmm, _ = gmm_fit(embeddings=Tensor(_np(ind_train_data)).to(self.device),
+                              labels=Tensor(_np(kwargs["train_labels"])).to(self.device), num_classes=self.num_classes)
         self._state = _gmm_state(self.gmm)
         ind_scores = self.flip_sign_fn(to_host(_ops.gmm_lse(kwargs["valid_feats"], self._state)))
         self.set_threshold(ind_scores)

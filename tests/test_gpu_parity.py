@@ -136,6 +136,9 @@ def test_fixture_latent(R, golden, name):
         p = P[key](cfg=Cfg())
         p._setup_flag = False
         p.setup(g["train"], ind_train_labels=g["train_labels"])
+        if key == "MD":  # fitted state against the reference's own (float32 banks: the device fit of csrc/fit.cu)
+            assert p.feats_mean.dtype == g["MD_feats_mean"].dtype and np.array_equal(p.feats_mean, g["MD_feats_mean"])
+            assert np.abs(p.precision - g["MD_precision"]).max() <= 1e-9 * np.abs(g["MD_precision"]).max()
         for split in ("valid", "ood"):
             s = p.postprocess(g[split], pred_labels=g["valid_labels"])
             ref = g[f"{key}_{split}"]
