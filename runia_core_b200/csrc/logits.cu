@@ -562,10 +562,20 @@ extern "C" int runia_logit_scores_f32(const float *logits, int64_t N, int C, flo
       attr = true;
     }
     const unsigned grid = (unsigned)ceil_div(N, LS_ROWS);
-    if (C <= 16)
-      logit_scores_small_kernel<16><<<grid, LS_ROWS, smem, st>>>(logits, N, C, gamma, M, energy, msp, gen);
-    else
+    if (C <= 16) {
+      // the register row is sized to the class count rounded up to even: no dead (-inf) columns in the unrolled body
+      switch ((C + 1) & ~1) {
+#define RUNIA_LS_CASE(CM)                                                                                   \
+  case CM:                                                                                                  \
+    logit_scores_small_kernel<CM><<<grid, LS_ROWS, smem, st>>>(logits, N, C, gamma, M, energy, msp, gen); \
+    break;
+        RUNIA_LS_CASE(2) RUNIA_LS_CASE(4) RUNIA_LS_CASE(6) RUNIA_LS_CASE(8) RUNIA_LS_CASE(10) RUNIA_LS_CASE(12)
+        RUNIA_LS_CASE(14) RUNIA_LS_CASE(16)
+#undef RUNIA_LS_CASE
+      }
+    } else {
       logit_scores_small_kernel<64><<<grid, LS_ROWS, smem, st>>>(logits, N, C, gamma, M, energy, msp, gen);
+    }
   } else {
     RUNIA_REQUIRE(!gen || M >= C, RUNIA_E_UNSUPPORTED, "logit_scores: GEN with M=%d < C=%d needs C <= 64", M, C);
     logit_scores_wide_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(logits, N, C, gamma, energy, msp, gen);
