@@ -225,8 +225,12 @@ struct ClassCondEpi {
 
 // (a10) ReAct / DICE / DICE+ReAct head: the 32-column panel holds the C <= 32 class logits of the row
 // (clip applied by the converters); out = logsumexp_c (v_c + b_c)      postprocessors.py:1464-1472, 1340-1352
-constexpr int kNarrowN = 32;
+constexpr int kNarrowN = 32;      // widest narrow panel (C <= 32); C <= 16 uses a 16-column panel
 constexpr int kNarrowStages = 5;  // 36 KB stages: 80 KB of rows in flight per CTA (HBM-bound stream)
+// NW = panel width (16 or 32).  Accumulator columns (tc_gemm.cuh, NCAT), h = NW / 2:
+//   [0, h) A_hi x B_hi for classes 0..h-1 (CTA 0's rows), [h, 2h) A_hi x B_lo for the same classes,
+//   [2h, 3h) / [3h, 4h) the same for classes h..NW-1 (CTA 1's rows), [2 NW, 3 NW) A_lo x B_hi in class order.
+template <int NW>
 struct LinearLseEpi {
   const float *bias;  // [C]
   int C;
@@ -236,29 +240,47 @@ struct LinearLseEpi {
   __device__ void set_stage(uint32_t) {}
   template <class P> __device__ void bind(const P *) {}
   __device__ void begin(int, int64_t row_) { row = row_; }
-  float l[kNarrowN];
-  // three 32-column groups per row (tc_gemm.cuh, NCAT): [hi x c 0-15 | lo x c 0-15], [hi x c 16-31 | lo x c 16-31],
-  // A_lo x B_hi for c 0-31
+  float l[NW];
+  __device__ void finalize() {
+    if (row >= M) return;
+    constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NW; ++c) {
+      l[c] = c < C ? l[c] + __ldg(bias + c) : -INFINITY;
+      m = fmaxf(m, l[c]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NW; ++c) s += exp2f((l[c] - m) * kLog2e);  // exp2(-inf) = 0 for the padding
+    out[row] = fmaf(__log2f(s), kLn2, m);
+  }
   __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
-    if (col0 == 0) {
+    constexpr int h = NW / 2;
+    if (NW == 32) {  // three 32-column groups
+      if (col0 == 0) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) l[c] = v[c] + v[16 + c];
-    } else if (col0 == 32) {
+        for (int c = 0; c < h; ++c) l[c] = v[c] + v[h + c];
+      } else if (col0 == 32) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) l[16 + c] = v[c] + v[16 + c];
-    } else {
-      if (row >= M) return;
-      constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
-      float m = -INFINITY;
+        for (int c = 0; c < h; ++c) l[h + c] = v[c] + v[h + c];
+      } else {
 #pragma unroll
-      for (int c = 0; c < kNarrowN; ++c) {
-        l[c] = c < C ? (l[c] + v[c]) + __ldg(bias + c) : -INFINITY;
-        m = fmaxf(m, l[c]);
+        for (int c = 0; c < NW; ++c) l[c] += v[c];
+        finalize();
       }
-      float s = 0.f;
+    } else {  // NW == 16: columns 0..31 hold both hi products, 32..47 the A_lo product
+      if (col0 == 0) {
 #pragma unroll
-      for (int c = 0; c < kNarrowN; ++c) s += exp2f((l[c] - m) * kLog2e);  // exp2(-inf) = 0 for the padding
-      out[row] = fmaf(__log2f(s), kLn2, m);
+        for (int c = 0; c < h; ++c) {
+          l[c] = v[c] + v[h + c];
+          l[h + c] = v[2 * h + c] + v[3 * h + c];
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NW; ++c) l[c] += v[c];
+        finalize();
+      }
     }
   }
   __device__ void panel_done(int) {}
@@ -637,7 +659,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, int64_t M, int K, Prologue pr
 }
 
 // Narrow-panel variant (UMMA N = 32): streaming heads whose output is a handful of columns per row.
-template <class E>
+template <class E, int NW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tc_narrow_kernel(const __grid_constant__ CUtensorMap tmA, int64_t M, int K, Prologue pro,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -651,7 +673,7 @@ tc_narrow_kernel(const __grid_constant__ CUtensorMap tmA, int64_t M, int K, Prol
   w.tile_step = gridDim.x >> 1;
   w.panel_lo = 0;
   w.panel_hi = 1;
-  run_tiles<E, kNarrowN, kNarrowStages, true>(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
+  run_tiles<E, NW, kNarrowStages, true>(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
 __device__ __forceinline__ Work split_work(int panels_total, int panels_per_split) {
@@ -818,20 +840,30 @@ extern "C" int runia_clip_linear_lse_tc(const float *X, int64_t N, int d, const 
   CUtensorMap ma, mh, ml;
   int rc = make_a_map(&ma, X, N, d);
   if (rc) return rc;
-  rc = make_map(&mh, W_hi, kNarrowN, d, kNarrowN / 2);  // planes are [32, d], rows >= C zero
+  const int nw = C <= 16 ? 16 : 32;                 // planes are [32, d] with rows >= C zero; the first nw are read
+  rc = make_map(&mh, W_hi, nw, d, nw / 2);
   if (rc) return rc;
-  rc = make_map(&ml, W_lo, kNarrowN, d, kNarrowN / 2);
+  rc = make_map(&ml, W_lo, nw, d, nw / 2);
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
-    rc = set_smem(tc_narrow_kernel<LinearLseEpi>, smem_bytes_variant(kMaxK, kNarrowN, kNarrowStages));
+    rc = set_smem(tc_narrow_kernel<LinearLseEpi<16>, 16>, smem_bytes_variant(kMaxK, 16, kNarrowStages));
+    if (rc) return rc;
+    rc = set_smem(tc_narrow_kernel<LinearLseEpi<32>, 32>, smem_bytes_variant(kMaxK, 32, kNarrowStages));
     if (rc) return rc;
     attr = true;
   }
-  LinearLseEpi epi{b, C, out, N, 0};
   dim3 grid(2 * (unsigned)std::min<int64_t>(ceil_div(N, TM2), kNumSMs / 2), 1);
-  tc_narrow_kernel<LinearLseEpi><<<grid, THREADS, smem_bytes_variant(d, kNarrowN, kNarrowStages), (cudaStream_t)stream>>>(ma, N, d, Prologue{nullptr, clip}, mh,
-                                                                                     ml, epi);
+  const Prologue pro{nullptr, clip};
+  if (nw == 16) {
+    LinearLseEpi<16> epi{b, C, out, N, 0};
+    tc_narrow_kernel<LinearLseEpi<16>, 16><<<grid, THREADS, smem_bytes_variant(d, 16, kNarrowStages), (cudaStream_t)stream>>>(
+        ma, N, d, pro, mh, ml, epi);
+  } else {
+    LinearLseEpi<32> epi{b, C, out, N, 0};
+    tc_narrow_kernel<LinearLseEpi<32>, 32><<<grid, THREADS, smem_bytes_variant(d, 32, kNarrowStages), (cudaStream_t)stream>>>(
+        ma, N, d, pro, mh, ml, epi);
+  }
   count_launch();
   return finish_launch("clip_linear_lse_tc");
 }
