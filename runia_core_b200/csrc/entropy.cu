@@ -386,6 +386,107 @@ entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ------------------------- any n_mc in [6, 32], k = 5 (the reference's default is 32) -------------------------
+// One warp per item, 32 dimensions per step.  NP = n_mc rounded up to a power of two; missing samples are +inf
+// sentinels (they sort to the end and every window that touches one has an infinite radius, so they drop out of
+// the minima by themselves).
+//  * per-dimension part: lane = dimension, the n samples of the lane's dimension in registers (coalesced loads,
+//    one 128-byte line per sample), bitonic network, window minima as above;
+//  * joint (Chebyshev) part: lane = SAMPLE.  The step's [n][32] block is staged in shared memory (row stride 36);
+//    lane i keeps its own 32 values in registers and walks the rows j < n as broadcast LDS.128, folding
+//    |x_i - x_j| into acc_j with FADD2 + 3-input max -- the whole row i of the distance matrix stays in lane i's
+//    registers (32 accumulators instead of n (n - 1) / 2 per lane), and the k-th neighbour of sample i is read off
+//    a sort of that row at the end.
+constexpr int ENP_WARPS = 4;
+constexpr int ENP_STRIDE = 36;  // floats per staged row: 16-byte aligned, rows land in different bank groups
+
+template <int NP>
+__global__ void __launch_bounds__(ENP_WARPS * 32, 4)
+entropy_np_kernel(const float *__restrict__ z, int64_t n_items, int n, int D, float min_dist, double c_term,
+                  double *__restrict__ h_z, double *__restrict__ h_mvn) {
+  constexpr int K = 5;
+  __shared__ __align__(16) float stage_all[ENP_WARPS][NP * ENP_STRIDE];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *stage = stage_all[warp];
+  const bool want_joint = h_mvn != nullptr;
+  for (int64_t item = (int64_t)blockIdx.x * ENP_WARPS + warp; item < n_items; item += (int64_t)gridDim.x * ENP_WARPS) {
+    const float *zi = z + item * (int64_t)n * D;
+    float acc[NP];  // lane i: running max_d |x_i[d] - x_j[d]| for j = 0 .. NP-1
+#pragma unroll
+    for (int j = 0; j < NP; ++j) acc[j] = 0.f;
+    for (int j0 = 0; j0 < D; j0 += 32) {
+      const int j = j0 + lane;
+      const bool ok = j < D;
+      float v[NP];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) v[i] = i < n ? (ok ? __ldg(zi + (int64_t)i * D + j) : 0.f) : INFINITY;
+      if (want_joint) {
+        __syncwarp();  // the previous step's readers are done with the stage
+#pragma unroll
+        for (int i = 0; i < NP; ++i)
+          if (i < n) stage[i * ENP_STRIDE + lane] = v[i];
+      }
+      // ---- per-dimension estimator (lane = dimension) ----
+      sort_network<NP>(v);
+      float sl = 0.f;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        float r = INFINITY;
+#pragma unroll
+        for (int a = 0; a + K < NP; ++a)
+          if (a <= i && i <= a + K) r = fminf(r, fmaxf(v[i] - v[a], v[a + K] - v[i]));
+        sl += i < n ? lg2_pos(fmaxf(r, min_dist)) : 0.f;
+      }
+      if (ok) h_z[item * (int64_t)D + j] = c_term + (double)(kLn2 * (1.f + sl / (float)n));
+      // ---- joint estimator: fold this step into row `lane` of the Chebyshev matrix (lane = sample) ----
+      if (want_joint) {
+        __syncwarp();
+        float4 own[8];
+        const float *mine = stage + (lane < n ? lane : 0) * ENP_STRIDE;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) own[q] = *reinterpret_cast<const float4 *>(mine + 4 * q);
+#pragma unroll
+        for (int jj = 0; jj < NP; ++jj) {
+          if (jj < n) {  // warp-uniform
+            const float *row = stage + jj * ENP_STRIDE;
+            float m = acc[jj];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 o = *reinterpret_cast<const float4 *>(row + 4 * q);  // broadcast
+              const float2 d0 = sub2(make_float2(own[q].x, own[q].y), make_float2(o.x, o.y));
+              const float2 d1 = sub2(make_float2(own[q].z, own[q].w), make_float2(o.z, o.w));
+              m = fmaxf(m, fmaxf(fabsf(d0.x), fabsf(d0.y)));
+              m = fmaxf(m, fmaxf(fabsf(d1.x), fabsf(d1.y)));
+            }
+            acc[jj] = m;
+          }
+        }
+      }
+    }
+    if (want_joint) {
+      float lg = 0.f;
+      if (lane < n) {
+        float row[NP];
+#pragma unroll
+        for (int jj = 0; jj < NP; ++jj) row[jj] = jj < n ? acc[jj] : INFINITY;  // acc[lane] = 0 (self)
+        sort_network<NP>(row);  // row[0] = 0 (self); row[K] = k-th neighbour
+        lg = lg2_pos(fmaxf(row[K], min_dist));
+      }
+      lg = warp_sum32(lg);
+      if (lane == 0) h_mvn[item] = c_term + (double)D * (double)(kLn2 * (1.f + lg / (float)n));
+    }
+  }
+}
+
+template <int NP>
+static void launch_entropy_np(const float *z, int64_t n_items, int n, int D, float min_dist, double c_term, double *h_z,
+                              double *h_mvn, cudaStream_t st) {
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, entropy_np_kernel<NP>, ENP_WARPS * 32, 0);
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n_items, ENP_WARPS), (int64_t)kNumSMs * std::max(per_sm, 1));
+  entropy_np_kernel<NP><<<grid, ENP_WARPS * 32, 0, st>>>(z, n_items, n, D, min_dist, c_term, h_z, h_mvn);
+}
+
 // ---------------------------------- generic path ------------------------------------------
 __global__ void __launch_bounds__(128)
 entropy_generic_dim_kernel(const float *__restrict__ z, int64_t n_items, int n, int D, int k, float min_dist,
@@ -499,6 +600,16 @@ extern "C" int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, 
         z, n_items, D, (float)min_dist, digamma_term, h_z, h_mvn);
     count_launch();
     return finish_launch("mcd_entropy(fast)");
+  }
+  if (k == 5 && n_mc >= 6) {  // the reference's k for every n_mc > 5 (evaluation/entropy.py:66)
+    if (n_mc <= 8)
+      launch_entropy_np<8>(z, n_items, n_mc, D, (float)min_dist, digamma_term, h_z, h_mvn, st);
+    else if (n_mc <= 16)
+      launch_entropy_np<16>(z, n_items, n_mc, D, (float)min_dist, digamma_term, h_z, h_mvn, st);
+    else
+      launch_entropy_np<32>(z, n_items, n_mc, D, (float)min_dist, digamma_term, h_z, h_mvn, st);
+    count_launch();
+    return finish_launch("mcd_entropy(np)");
   }
   const int64_t total = n_items * (int64_t)D;
   entropy_generic_dim_kernel<<<(unsigned)ceil_div(total, 128), 128, 0, st>>>(z, n_items, n_mc, D, k, (float)min_dist,

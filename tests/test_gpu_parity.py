@@ -396,3 +396,21 @@ def test_react_head_tensor_path_vs_oracle(R, d, C, clip):
     np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-5)
     simt = _ops.clip_linear_lse(x[:5000], Wd, bd, clip=clip).cpu().numpy()
     np.testing.assert_allclose(simt, got[:5000], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("n_mc,D", [(32, 512), (32, 100), (20, 36), (10, 512), (8, 65), (6, 512), (16, 510)])
+def test_entropy_any_n_mc_vs_oracle(R, n_mc, D):
+    """entropy_np_kernel: every n_mc in [6, 32] (k = 5; 32 is the reference's default mcd_samples_nro), power-of-two
+    padding with +inf sentinels, ragged last 32-dimension step, exact duplicates (min_dist clamp)."""
+    rng = np.random.RandomState(n_mc * 1000 + D)
+    n_items = 131
+    z = (rng.randn(n_items, 1, D) + 0.1 * rng.randn(n_items, n_mc, D)).astype(np.float32)
+    z[rng.rand(n_items, n_mc, D) < 0.3] = 0.0
+    z[7] = 1.25  # an item whose samples are all equal
+    z = z.reshape(-1, D)
+    hm, hz = R.evaluation.get_dl_h_z(z, n_mc)
+    rm, rz = O.get_dl_h_z(z, n_mc, chunk=32)
+    assert hz.shape == (n_items, D) and hm.shape == (n_items, 1)
+    assert rel_err(hz, rz) < RTOL and rel_err(hm, rm) < RTOL
+    np.testing.assert_allclose(hz, rz, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(hm, rm, rtol=1e-5, atol=1e-4)
