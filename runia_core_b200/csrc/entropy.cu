@@ -406,14 +406,14 @@ entropy_np_kernel(const float *__restrict__ z, int64_t n_items, int n, int D, fl
                   double *__restrict__ h_z, double *__restrict__ h_mvn) {
   constexpr int K = 5;
   __shared__ __align__(16) float stage_all[ENP_WARPS][NP * ENP_STRIDE];
+  __shared__ float acc_all[ENP_WARPS][NP * 32];  // [j][lane]: running max_d |x_lane[d] - x_j[d]| (row `lane` of the matrix)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float *stage = stage_all[warp];
+  float *acc = acc_all[warp] + lane;
   const bool want_joint = h_mvn != nullptr;
   for (int64_t item = (int64_t)blockIdx.x * ENP_WARPS + warp; item < n_items; item += (int64_t)gridDim.x * ENP_WARPS) {
     const float *zi = z + item * (int64_t)n * D;
-    float acc[NP];  // lane i: running max_d |x_i[d] - x_j[d]| for j = 0 .. NP-1
-#pragma unroll
-    for (int j = 0; j < NP; ++j) acc[j] = 0.f;
+    for (int jj = 0; jj < n; ++jj) acc[jj * 32] = 0.f;
     for (int j0 = 0; j0 < D; j0 += 32) {
       const int j = j0 + lane;
       const bool ok = j < D;
@@ -445,21 +445,21 @@ entropy_np_kernel(const float *__restrict__ z, int64_t n_items, int n, int D, fl
         const float *mine = stage + (lane < n ? lane : 0) * ENP_STRIDE;
 #pragma unroll
         for (int q = 0; q < 8; ++q) own[q] = *reinterpret_cast<const float4 *>(mine + 4 * q);
+        // a ROLLED loop over the other samples (the accumulators live in shared memory for that): unrolled 32 times
+        // this body alone was 1,300 instructions and the kernel ran out of instruction cache (stall_no_instruction 1.2)
+#pragma unroll 1
+        for (int jj = 0; jj < n; ++jj) {
+          const float *row = stage + jj * ENP_STRIDE;
+          float m = acc[jj * 32];
 #pragma unroll
-        for (int jj = 0; jj < NP; ++jj) {
-          if (jj < n) {  // warp-uniform
-            const float *row = stage + jj * ENP_STRIDE;
-            float m = acc[jj];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 o = *reinterpret_cast<const float4 *>(row + 4 * q);  // broadcast
-              const float2 d0 = sub2(make_float2(own[q].x, own[q].y), make_float2(o.x, o.y));
-              const float2 d1 = sub2(make_float2(own[q].z, own[q].w), make_float2(o.z, o.w));
-              m = fmaxf(m, fmaxf(fabsf(d0.x), fabsf(d0.y)));
-              m = fmaxf(m, fmaxf(fabsf(d1.x), fabsf(d1.y)));
-            }
-            acc[jj] = m;
+          for (int q = 0; q < 8; ++q) {
+            const float4 o = *reinterpret_cast<const float4 *>(row + 4 * q);  // broadcast
+            const float2 d0 = sub2(make_float2(own[q].x, own[q].y), make_float2(o.x, o.y));
+            const float2 d1 = sub2(make_float2(own[q].z, own[q].w), make_float2(o.z, o.w));
+            m = fmaxf(m, fmaxf(fabsf(d0.x), fabsf(d0.y)));
+            m = fmaxf(m, fmaxf(fabsf(d1.x), fabsf(d1.y)));
           }
+          acc[jj * 32] = m;
         }
       }
     }
@@ -468,7 +468,7 @@ entropy_np_kernel(const float *__restrict__ z, int64_t n_items, int n, int D, fl
       if (lane < n) {
         float row[NP];
 #pragma unroll
-        for (int jj = 0; jj < NP; ++jj) row[jj] = jj < n ? acc[jj] : INFINITY;  // acc[lane] = 0 (self)
+        for (int jj = 0; jj < NP; ++jj) row[jj] = jj < n ? acc[jj * 32] : INFINITY;  // acc[lane] = 0 (self)
         sort_network<NP>(row);  // row[0] = 0 (self); row[K] = k-th neighbour
         lg = lg2_pos(fmaxf(row[K], min_dist));
       }

@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(128) class_mean_seq_kernel(const float *__rest
 }
 
 constexpr int GT = 64;        // Gram tile edge
-constexpr int GK = 16;        // rows per staged chunk
+constexpr int GK = 32;        // rows per staged chunk (compute per chunk ~ one HBM round trip: the prefetch hides)
+constexpr int GQ = GK / 4;    // rows fetched per thread and chunk
 constexpr int G_THREADS = 256;
 
 // residual of one element: f32(x - mu_label) widened to f64; rows whose label is outside [0, C) contribute 0
@@ -99,16 +100,16 @@ __global__ void __launch_bounds__(G_THREADS) gram_f64_kernel(const float *__rest
   const int64_t r0 = (int64_t)split * rows_per_split, r1 = min(N, r0 + rows_per_split);
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   // staging assignment: element e = tid + 256 q -> (row e / 64, column e % 64)
-  const int lcol = tid & 63, lrow0 = tid >> 6;  // rows lrow0, lrow0 + 4, +8, +12
+  const int lcol = tid & 63, lrow0 = tid >> 6;  // rows lrow0, lrow0 + 4, ... (GQ of them)
   const int colA = ti * GT + lcol, colB = tj * GT + lcol;
   const bool okA = colA < d, okB = colB < d;
 
   double acc[4][4] = {};
   double cs[4] = {};
-  float ra[4], rb[4];
+  float ra[GQ], rb[GQ];
   auto fetch = [&](int64_t rbase) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < GQ; ++q) {
       const int64_t row = rbase + lrow0 + 4 * q;
       int lab = 0;
       bool in = row < r1;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(G_THREADS) gram_f64_kernel(const float *__rest
   for (int64_t rbase = r0; rbase < r1; rbase += GK) {
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < GQ; ++q) {
       As[lrow0 + 4 * q][lcol] = (double)ra[q];
       if (!diag) Bs[lrow0 + 4 * q][lcol] = (double)rb[q];
     }

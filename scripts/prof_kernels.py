@@ -33,6 +33,14 @@ if "entropy" in which:
         h = _ops.mcd_entropy(z, n_mc)
     torch.cuda.synchronize()
     del z
+if "entropy32" in which:
+    n_items, n_mc, D = 30_000, 32, 512
+    z = (torch.randn(n_items, 1, D, generator=g, device=dev) + 0.1 * torch.randn(n_items, n_mc, D, generator=g, device=dev))
+    z = z.reshape(-1, D).contiguous()
+    for _ in range(REPS):
+        h = _ops.mcd_entropy(z, n_mc)
+    torch.cuda.synchronize()
+    del z
 if "knn" in which:
     bank = _ops.normalize_rows(torch.randn(50_000, 512, generator=g, device=dev))
     q = _ops.normalize_rows(torch.randn(10_000, 512, generator=g, device=dev))
