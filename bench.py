@@ -225,6 +225,7 @@ def run_b200(args):
     tflops = flops / (kern_ms * 1e-3) / 1e12
     tc = _ops.get_engine() == "tc"
     peak_tf = bf16_peak / 2.0 / 3.0
+    tf32_probe = _tf32_probe(torch, _lib) if rank == 0 else None
     roofline = {"bound": "tensor", "achieved": round(tflops, 2), "peak": round(peak_tf, 2), "unit": "TFLOP/s",
                 "frac": round(tflops / peak_tf, 4), "traffic": _traffic("tc_kernel<tc::RowNormEpi>") if n_rows == 4 * 1024 * 1024 else None,
                 "peak_source": peak_src + ": dense bf16 burst / 2 (TF32 rate) / 3 (3xTF32 products per FP32-faithful FLOP)",
@@ -233,6 +234,10 @@ def run_b200(args):
                 "algorithmic_flop_per_embedding": 2 * D_LATENT * st.r + 3 * D_LATENT,
                 "algorithmic_bytes_per_embedding": D_LATENT * 4 + 8,
                 "tensor_tf32_tflops_issued": round(3 * tflops, 2),
+                # the same MMA instruction issued back to back from resident tiles, timed in this run: what the
+                # tensor pipe of this GPU sustains in TF32 (MEASURED_PEAKS.json has no TF32 entry)
+                "tf32_probe": None if not tf32_probe else {"tflops": round(tf32_probe, 1),
+                                                           "frac_of_probe": round(3 * tflops / tf32_probe, 4)},
                 "hbm": {"achieved": round(hbm_achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                         "frac": round(hbm_achieved / hbm_peak, 4)}}
 
@@ -388,6 +393,25 @@ def _time_op(torch, fn, reps=5, warm=2):
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
+
+
+def _tf32_probe(torch, _lib):
+    """TF32 TFLOP/s of back-to-back tcgen05.mma (256 x 256 x 8, cta_group::2) on resident tiles: CUDA events around
+    three launches of ~2 ms after one warm-up."""
+    import ctypes
+
+    flop = ctypes.c_double(0.0)
+    iters = 8192
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.call("runia_tf32_peak_probe", iters, ctypes.byref(flop), stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        _lib.call("runia_tf32_peak_probe", iters, ctypes.byref(flop), stream)
+    e1.record()
+    torch.cuda.synchronize()
+    return 3 * flop.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
 
 
 def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak):

@@ -306,6 +306,13 @@ size_t runia_mc_dropblock_workspace_bytes(int B, int H, int W, int n_mc);
 int runia_mc_dropblock_mean_f32(const float *x, const uint8_t *seed, int B, int C, int H, int W, int n_mc,
                                 int block_size, float *out, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Measurement aid (bench.py): TF32 tensor peak of this GPU.  Launches one CTA pair per TPC, each issuing
+ * iters x 4 back-to-back tcgen05.mma.cta_group::2.kind::tf32 (256 x 256 x 8) on resident shared-memory tiles;
+ * *flop_out (host pointer, nullable) receives the TF32 FLOP the launch issues.  Time it with CUDA events.
+ */
+int runia_tf32_peak_probe(int iters, double *flop_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

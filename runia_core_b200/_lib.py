@@ -76,6 +76,7 @@ _SIGS = {
     "runia_mc_dropblock_mean_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "runia_logit_scores_f32": (c_int, [_P, c_int64, c_int, c_float, c_int, _P, _P, _P, _P]),
     "runia_clip_linear_lse_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, c_float, _P, _P]),
+    "runia_tf32_peak_probe": (c_int, [c_int, _P, _P]),
     "runia_clip_linear_lse_tc": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int, c_float, _P, _P]),
     "runia_ash_linear_lse_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, c_int, _P, _P]),
 }

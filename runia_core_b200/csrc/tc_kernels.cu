@@ -676,6 +676,60 @@ tc_narrow_kernel(const __grid_constant__ CUtensorMap tmA, int64_t M, int K, Prol
   run_tiles<E, NW, kNarrowStages, true>(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
+// TF32 tensor peak probe: every CTA pair issues `iters` x 4 back-to-back UMMAs (256 x 256 x 8, kind::tf32, the
+// instruction of the scorers) on one resident pair of shared-memory tiles filled with pseudo-random values; no
+// loads, no epilogue.  MEASURED_PEAKS.json has no TF32 entry; this is the denominator the tensor-bound rooflines
+// use (bench.py), measured with CUDA events on the same box in the same run.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) tc_peak_kernel(int iters, uint32_t seed) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t base = (smem_u32(smem_raw) + SMEM_ALIGN - 1) & ~(uint32_t)(SMEM_ALIGN - 1);
+  unsigned char *gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sA = base, sB = base + A_PLANE_BYTES, bar = base + A_PLANE_BYTES + B_PLANE_BYTES, slot = bar + 16;
+  float *tiles = reinterpret_cast<float *>(gbase);
+  uint32_t x = seed * 2654435761u + (blockIdx.x * 128u + threadIdx.x) * 40503u + 1u;
+  for (int e = threadIdx.x; e < (A_PLANE_BYTES + B_PLANE_BYTES) / 4; e += 128) {
+    x = x * 1664525u + 1013904223u;
+    tiles[e] = __uint_as_float((x >> 9) | 0x3f800000u) - 1.5f;  // uniform in [-0.5, 0.5)
+  }
+  fence_proxy_async();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(slot, 512);
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(gbase + A_PLANE_BYTES + B_PLANE_BYTES + 16);
+  if (warp == 0) {
+    if (rank == 0 && lane == 0) {
+      const uint64_t dA = make_smem_desc(sA), dB = make_smem_desc(sB);
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k4 = 0; k4 < TK / 8; ++k4) {
+          const uint64_t adv = (uint64_t)((k4 * 8 * 4) >> 4);
+          umma_tf32(tmem_base + (uint32_t)((it & 1) * TN), dA + adv, dB + adv, InstrDesc<TN>::value, (it >= 2 || k4 > 0) ? 1u : 0u);
+        }
+      }
+      umma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);  // both CTAs: the multicast commit arrives on each one's barrier
+    tc_fence_after();
+  }
+  __syncthreads();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 __device__ __forceinline__ Work split_work(int panels_total, int panels_per_split) {
   Work w;  // one 256-row tile x one bank split per CTA pair
   w.tile_first = blockIdx.x >> 1;
@@ -866,6 +920,22 @@ extern "C" int runia_clip_linear_lse_tc(const float *X, int64_t N, int d, const 
   }
   count_launch();
   return finish_launch("clip_linear_lse_tc");
+}
+
+extern "C" int runia_tf32_peak_probe(int iters, double *flop_out, void *stream) {
+  RUNIA_REQUIRE(iters >= 1 && iters <= (1 << 24), RUNIA_E_BADARG, "tf32_peak_probe: iters out of range");
+  const size_t smem = (size_t)A_PLANE_BYTES + B_PLANE_BYTES + 64 + SMEM_ALIGN;
+  static bool attr = false;
+  if (!attr) {
+    int rc = set_smem(tc_peak_kernel, smem);
+    if (rc) return rc;
+    attr = true;
+  }
+  const unsigned pairs = kNumSMs / 2;
+  tc_peak_kernel<<<2 * pairs, 128, smem, (cudaStream_t)stream>>>(iters, 12345u);
+  if (flop_out) *flop_out = (double)pairs * iters * (TK / 8) * 2.0 * TM2 * TN * 8;  // TF32 FLOP issued by the launch
+  count_launch();
+  return finish_launch("tf32_peak_probe");
 }
 
 extern "C" int runia_pca_transform_tc(const float *X, int64_t N, int D0, const float *mean, const float *C_hi,
