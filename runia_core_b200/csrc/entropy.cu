@@ -23,21 +23,19 @@ constexpr float kLn2 = 0.693147180559945309f;
 
 template <int N>
 __device__ __forceinline__ void sort_network(float (&v)[N]) {
-  // bitonic network, fully unrolled: all indices are compile-time, v stays in registers
+  // Batcher's odd-even merge sort (N a power of two), fully unrolled: every index is a compile-time constant, v stays
+  // in registers.  19 / 63 / 191 comparators for N = 8 / 16 / 32 (the bitonic network needs 24 / 80 / 240).
 #pragma unroll
-  for (int k = 2; k <= N; k <<= 1) {
+  for (int p = 1; p < N; p <<= 1) {
 #pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
+    for (int k = p; k >= 1; k >>= 1) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        const int p = i ^ j;
-        if (p > i) {
-          const float lo = fminf(v[i], v[p]), hi = fmaxf(v[i], v[p]);
-          if ((i & k) == 0) {
-            v[i] = lo; v[p] = hi;
-          } else {
-            v[i] = hi; v[p] = lo;
-          }
+      for (int a = 0; a < N; ++a) {  // comparator (a, a + k) of this layer, if any
+        const int off = k % p;
+        if (a >= off && ((a - off) % (2 * k)) < k && a + k < N && (a / (2 * p)) == ((a + k) / (2 * p))) {
+          const float lo = fminf(v[a], v[a + k]), hi = fmaxf(v[a], v[a + k]);
+          v[a] = lo;
+          v[a + k] = hi;
         }
       }
     }
