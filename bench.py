@@ -71,18 +71,48 @@ def _traffic(kernel):
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    """SM clock and clock-event (throttle) reasons of one GPU while the timed region runs.  Reads NVML -- the
+    library behind nvidia-smi's clocks.sm / clocks.max.sm / clocks_event_reasons.* fields -- from a thread every
+    2 ms, so that a 40 ms timed region holds ~20 samples taken INSIDE it (an `nvidia-smi -lms` child needs longer than
+    that to print its first line); falls back to the nvidia-smi query of the profiling recipe when pynvml is missing."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+            0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, uuid=None):
         self.gpu_index = gpu_index
+        self.uuid = uuid
         self.proc = None
         self.lines = []
+        self.samples = []  # (host time, sm MHz, reasons bitmask)
+        self.nvml = None
+        self._stop = False
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                for cand in (f"GPU-{self.uuid}", str(self.uuid)):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = (pynvml, h)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
@@ -92,11 +122,35 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h = self.nvml
+        while not self._stop:
+            try:
+                self.samples.append((time.time(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                     int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, window=None):
+        """window = (t0, t1) host times of the timed region: only samples inside it count (NVML path)."""
+        if self.nvml is not None:
+            self._stop = True
+            self.thread.join(timeout=1.0)
+            inside = [x for x in self.samples if window is None or window[0] <= x[0] <= window[1]]
+            if not inside:
+                inside = self.samples[-3:]
+            mask = 0
+            for _, _, m in inside:
+                mask |= m
+            reasons = sorted(name for bit, name in self.BITS.items() if mask & bit)
+            return {"sm_mhz": float(np.median([x[1] for x in inside])) if inside else None, "sm_max_mhz": self.sm_max,
+                    "reasons": reasons, "samples": len(inside), "source": "nvml, every 2 ms inside the timed region",
+                    "reasons_mask": hex(mask)}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -119,7 +173,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 def _fit_larem(seed=1):
@@ -201,15 +255,20 @@ def run_b200(args):
     def step():
         out_holder["s"] = _ops.md_score(X, st, torch.float64)
 
-    sampler = ClockSampler(local)
+    try:
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
+    sampler.start()
     l0 = _lib.launch_count()
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
     l1 = _lib.launch_count()
-    sampler.start()
+    t_w0 = time.time()
     total_ms, per = _time_events(step, args.steps, 0, barrier)
-    clocks = sampler.stop()
+    clocks = sampler.stop(window=(t_w0, time.time()))
     launches = _lib.launch_count() - l1
     total_ms = max_over_ranks(total_ms)
     ms_per_step = total_ms / args.steps
@@ -411,22 +470,26 @@ def _time_op(torch, fn, reps=5, warm=2):
 
 
 def _tf32_probe(torch, _lib):
-    """TF32 TFLOP/s of back-to-back tcgen05.mma (256 x 256 x 8, cta_group::2) on resident tiles: CUDA events around
-    three launches of ~2 ms after one warm-up."""
+    """TF32 TFLOP/s of back-to-back tcgen05.mma (256 x 256 x 8, cta_group::2) on resident tiles.  Burst figure, like
+    MEASURED_PEAKS.json's: the best of eight separately timed ~0.5 ms launches (a multi-millisecond burn of pure MMAs
+    runs into the power cap and reads 25 % lower than the scorers themselves sustain)."""
     import ctypes
 
     flop = ctypes.c_double(0.0)
-    iters = 8192
+    iters = 2048
     stream = torch.cuda.current_stream().cuda_stream
     _lib.call("runia_tf32_peak_probe", iters, ctypes.byref(flop), stream)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
+    best = 0.0
+    for _ in range(8):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         _lib.call("runia_tf32_peak_probe", iters, ctypes.byref(flop), stream)
-    e1.record()
-    torch.cuda.synchronize()
-    return 3 * flop.value / (e0.elapsed_time(e1) * 1e-3) / 1e12
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, flop.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        time.sleep(0.01)
+    return best
 
 
 def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak):
