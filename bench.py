@@ -255,6 +255,8 @@ def run_b200(args):
     def step():
         out_holder["s"] = _ops.md_score(X, st, torch.float64)
 
+    # TF32 tensor peak of this GPU: one reading before the timed region (GPU not yet heated), one after it (clocks up)
+    tf32_probe = _tf32_probe(torch, _lib) if rank == 0 else None
     try:
         uuid = str(torch.cuda.get_device_properties(local).uuid)
     except Exception:
@@ -284,7 +286,8 @@ def run_b200(args):
     tflops = flops / (kern_ms * 1e-3) / 1e12
     tc = _ops.get_engine() == "tc"
     peak_tf = bf16_peak / 2.0 / 3.0
-    tf32_probe = _tf32_probe(torch, _lib) if rank == 0 else None
+    if rank == 0:  # and once more on the warm GPU: the burst peak is the larger of the two readings
+        tf32_probe = max(tf32_probe or 0.0, _tf32_probe(torch, _lib))
     # denominator: the TF32 rate this GPU sustains for the kernel's own MMA instruction, measured in this run
     # (runia_tf32_peak_probe), / 3 products; MEASURED_PEAKS.json has no TF32 entry, and the figure derived from its
     # dense bf16 number (/ 2 / 3) is lower than what the tensor pipe delivers (the kernel exceeds it), so it is
