@@ -426,13 +426,22 @@ entropy_np_kernel(const float *__restrict__ z, int64_t n_items, int n, int D, fl
       }
       // ---- per-dimension estimator (lane = dimension) ----
       sort_network<NP>(v);
+      float wd[NP - K];  // window widths: the radius of a window for its two end points (no max needed there)
+#pragma unroll
+      for (int a = 0; a + K < NP; ++a) wd[a] = v[a + K] - v[a];
       float sl = 0.f;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
         float r = INFINITY;
 #pragma unroll
-        for (int a = 0; a + K < NP; ++a)
-          if (a <= i && i <= a + K) r = fminf(r, fmaxf(v[i] - v[a], v[a + K] - v[i]));
+        for (int a = 0; a + K < NP; ++a) {
+          if (a <= i && i <= a + K) {
+            if (i == a || i == a + K)
+              r = fminf(r, wd[a]);
+            else
+              r = fminf(r, fmaxf(v[i] - v[a], v[a + K] - v[i]));
+          }
+        }
         sl += i < n ? lg2_pos(fmaxf(r, min_dist)) : 0.f;
       }
       if (ok) h_z[item * (int64_t)D + j] = c_term + (double)(kLn2 * (1.f + sl / (float)n));
