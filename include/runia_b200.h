@@ -47,7 +47,7 @@ int64_t runia_b200_launch_count(void);
  *   z      [n_items * n_mc, D] float32, item-major (rows i*n_mc .. i*n_mc+n_mc-1 = item i)
  *   h_z    [n_items, D] float64   per-dimension entropies            (entropy.py:73-92)
  *   h_mvn  [n_items]    float64   joint (Chebyshev) entropy          (entropy.py:67-71); may be NULL
- *   k      neighbours (entropy.py:66: 5 if n_mc > 5 else n_mc-1); 1 <= k < n_mc <= 32
+ *   k      neighbours (entropy.py:66: 5 if n_mc > 5 else n_mc-1); 1 <= k < n_mc <= 128 (tuned kernels: n_mc <= 32)
  *   digamma_term = -psi(k) + psi(n_mc), computed by the host in float64.
  */
 int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, int D, int k, double min_dist,
@@ -161,15 +161,18 @@ int runia_gmm_lse_tc(const float *X, int64_t N, int d, const float *At_hi, const
  *     out_dist_f64 [Nq, k] float64 (the exact values before rounding; +inf padding)
  *     out_idx      [Nq, k] int64 (-1 padding); idx_offset is added to every index (bank shards)
  *     out_kth      [Nq]    float32 = out_dist[:, k-1]
- *   status [4] int32 (device): [0] rows that took the exhaustive pass, [1] != 0 if that pass
- *     overflowed its tie buffer (result invalid -> the host raises), [2..3] reserved.
+ *   status [4] int32 (device): [0] rows that took the exhaustive pass; [1..3] reserved (always 0: the exhaustive
+ *     pass handles any number of bank rows tying with the k-th neighbour by cutting its hit buffer back to the
+ *     k smallest pairs whenever the next chunk of the bank could overflow it).
+ *   The rounding bound of the certification scales with (|q|^2 + max_b |b|^2) / 2, so un-normalised rows
+ *   (FlatL2Index used directly) are certified as strictly as the unit-norm rows of the postprocessors.
  *   Bn_tf32_hi / Bn_tf32_lo: optional pre-split planes of the bank (runia_split_tf32).  When both
  *     are given and d % 4 == 0 the candidate pass runs on the tcgen05 tensor cores (3xTF32, TMA-fed);
  *     NULL selects the FP32 SIMT pass.  The result is identical either way (exact re-rank).
- *   workspace: runia_knn_workspace_bytes(Nq, Nb, d, k) bytes of device memory.  1 <= k <= 240.
+ *   workspace: runia_knn_workspace_bytes(Nq, Nb, d, k) bytes of device memory.  1 <= k <= 1016.
  * runia_topk_merge: merges R partial results ([R, Nq, k] float64 dist / int64 idx, each
  *   ascending) into the global top-k under the same total order -- the step after the NCCL
- *   all-gather when the bank is sharded across GPUs.
+ *   all-gather when the bank is sharded across GPUs.  R <= 64.
  */
 int runia_normalize_rows(const void *in, int in_is_f64, int64_t N, int d, float *out, void *stream);
 int runia_row_sqnorm_f32(const float *X, int64_t N, int d, float *out, void *stream);
@@ -201,27 +204,41 @@ int runia_kde_lse_f32(const float *Q, int64_t Nq, const float *B, const float *B
  * (a8) Logit-space scores in one pass -- inference/postprocessors.py:519-551 (Energy),
  * :580-608 (MSP), :650-691 (GEN) + inference/funcs.py:347-375:
  *   energy[n] = logsumexp(l_n); msp[n] = max softmax(l_n);
- *   gen[n] = -sum_{top-M p} p^gamma (1-p)^gamma.     Any output may be NULL.  C <= 1024.
+ *   gen[n] = -sum_{top-M p} p^gamma (1-p)^gamma.     Any output may be NULL.  Any C, any M (M <= 0 or M >= C:
+ *   all classes, like NumPy's [:, -M:]).
+ * runia_gen_entropy_f32: `generalized_entropy(probs, gamma, M)` (funcs.py:347-375) on rows that already are
+ *   probabilities -- no softmax, rows need not sum to one.
  */
 int runia_logit_scores_f32(const float *logits, int64_t N, int C, float gamma, int M, float *energy,
                            float *msp, float *gen, void *stream);
+int runia_gen_entropy_f32(const float *probs, int64_t N, int C, float gamma, int M, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (a10) ReAct / DICE / DICE+ReAct -- inference/postprocessors.py:1444-1474, 1325-1354, 1591-1621,
  * inference/funcs.py:171-190:   out[n] = logsumexp_c( min(x_n, clip) . W_c + b_c )
- * W is the (masked, for DICE) final linear layer [C, d]; clip = +inf disables ReAct.  C <= 64.
+ * W is the (masked, for DICE) final linear layer [C, d]; clip = +inf disables ReAct.  Any C and d (heads
+ * that fit shared memory -- C <= 64, C*d*4 <= 200 KiB -- use the resident-weight kernels, others stream W).
  * ASH-S -- postprocessors.py:1192-1222 + funcs.py:230-261: keep the k_keep largest activations
- * of each row, scale by exp(sum_all / sum_kept), then the same linear layer + logsumexp.
+ * of each row (ties with the k-th value: lowest indices), scale by exp(sum_all / sum_kept), then the same linear
+ * layer + logsumexp.  runia_ash_linear_lse_f32 is the fused form for heads that fit shared memory;
+ * runia_ash_prune_f32 writes the pruned and scaled rows [N, d] for any width, to be followed by
+ * runia_clip_linear_lse_f32 / _tc with clip = +inf (any C).
  */
 int runia_clip_linear_lse_f32(const float *X, int64_t N, int d, const float *W, const float *b, int C,
                               float clip, float *out, void *stream);
-/* Tensor-core version for C <= 32, d % 4 == 0, d <= 4096, 16-byte aligned X: the same tcgen05 pipeline as the row
- * scorers with a 32-column panel (TMA-streamed rows, clip + 3xTF32 split by the converters, log-sum-exp straight
- * from TMEM).  W_hi / W_lo: TF32 planes of W zero-padded to [32, d] (runia_split_tf32). */
+/* Tensor-core version for d % 4 == 0, d <= 4096, 16-byte aligned X: the same tcgen05 pipeline as the row
+ * scorers (TMA-streamed rows, clip + 3xTF32 split by the converters, log-sum-exp straight from TMEM).
+ * C <= 32: a 32-column panel, W_hi / W_lo = TF32 planes of W zero-padded to [32, d] (runia_split_tf32).
+ * C > 32 (any): 256-column panels with an online log-sum-exp across them, W_hi / W_lo = planes of W [C, d],
+ * b 16-byte aligned. */
 int runia_clip_linear_lse_tc(const float *X, int64_t N, int d, const float *W_hi, const float *W_lo, const float *b,
                              int C, float clip, float *out, void *stream);
 int runia_ash_linear_lse_f32(const float *X, int64_t N, int d, const float *W, const float *b, int C,
                              int k_keep, float *out, void *stream);
+int runia_ash_prune_f32(const float *X, int64_t N, int d, int k_keep, float *out, void *stream);
+/* Plain linear layer out[N, C] = X W^T + b (b may be NULL), FP32 SIMT contraction: RouteDICE.forward
+ * (inference/funcs.py:171-190), which the reference materialises as an [N, C, d] product. */
+int runia_linear_f32(const float *X, int64_t N, int d, const float *W, const float *b, int C, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (f1) OoD detection metrics -- evaluation/metrics.py:37-100 (`get_auroc_results`: torchmetrics 1.8.2

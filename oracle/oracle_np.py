@@ -439,6 +439,30 @@ def ash_score(feats, w, b, percentile):
     return logsumexp(np.matmul(ash_s(feats, percentile), w.T) + b, axis=1)
 
 
+def ash_s_intended(x, percentile):
+    """The rule funcs.py:243-261 describes ("keeps the top-k elements per row"), made deterministic: the k largest
+    activations stay at their own positions (ties with the k-th value: lowest index first), the rest are zeroed,
+    rows are scaled by exp(s1 / s2).  `ash_s` above is the LITERAL upstream code: it scatters np.partition's values
+    to np.argpartition's indices, two calls that NumPy does not promise to order alike -- with NumPy >= 2 (SIMD
+    quickselect for np.partition) they disagree on a few per cent of wide rows, i.e. the kept VALUES land permuted
+    among the kept POSITIONS, and which rows depends on the NumPy build and the CPU.  scripts/ash_literal_delta.py
+    measures what that does to the scores and to AUROC / FPR@95; the CUDA kernels implement this function."""
+    x = np.asarray(x)
+    n, d = x.shape
+    k = d - int(np.round(d * percentile / 100.0))
+    order = np.lexsort((np.broadcast_to(np.arange(d), x.shape), -x), axis=1)[:, :k]
+    kept = np.zeros_like(x)
+    np.put_along_axis(kept, order, np.take_along_axis(x, order, axis=1), axis=1)
+    s1 = x.sum(axis=1)
+    s2 = kept.sum(axis=1)
+    with np.errstate(all="ignore"):
+        return kept * np.exp((s1 / s2)[:, None])
+
+
+def ash_score_intended(feats, w, b, percentile):
+    return logsumexp(np.matmul(ash_s_intended(feats, percentile), w.T) + b, axis=1)
+
+
 # --------------------------------------------------------------------------------------
 # thresholds and the parity metric.  abstract_classes.py:408-424; evaluation/metrics.py:60-81
 # --------------------------------------------------------------------------------------

@@ -79,6 +79,9 @@ _SIGS = {
     "runia_tf32_peak_probe": (c_int, [c_int, _P, _P]),
     "runia_clip_linear_lse_tc": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int, c_float, _P, _P]),
     "runia_ash_linear_lse_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, c_int, _P, _P]),
+    "runia_ash_prune_f32": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
+    "runia_gen_entropy_f32": (c_int, [_P, c_int64, c_int, c_float, c_int, _P, _P]),
+    "runia_linear_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)
 

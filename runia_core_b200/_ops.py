@@ -240,9 +240,10 @@ def residual_norm(x, st: VimState) -> torch.Tensor:
     xf, centered = as_f32_rows(x, st.u_f64)
     n = xf.shape[0]
     out = _empty((n,), torch.float32)
+    zero_logit = torch.zeros((n, 1), dtype=torch.float32, device=xf.device)  # logsumexp of one zero logit = 0
     _rownorm(xf, n, st.d, None if centered else st.u_f32.data_ptr(), st.NSt, st.planes, st.r, None,
-             _lib.ROWNORM_MD, None, 0, 0.0, None, out.data_ptr())
-    return torch.sqrt(torch.clamp(-out, min=0))
+             _lib.ROWNORM_VIM, zero_logit.data_ptr(), 1, -1.0, None, out.data_ptr())  # -alpha sqrt(.) with alpha = -1
+    return out
 
 
 @dataclass
@@ -379,13 +380,33 @@ def knn_bank(bank_normed: torch.Tensor, idx_offset: int = 0, planes: Optional[bo
 
 
 class KNNOverflow(RuntimeError):
-    pass
+    """Kept for API compatibility: the exhaustive pass no longer has a tie-buffer limit, nothing raises this."""
+
+
+KNN_MAX_K = 1016               # distance.cu kKnnMaxK
+KNN_WS_CHUNK_BYTES = 12 << 30  # candidate-list workspace above this is avoided by searching the queries in chunks
+
+
+def _knn_search_chunk(qn, bank, k, res, lo, hi, want_status):
+    nq, d = hi - lo, qn.shape[1]
+    nb = bank.bank.shape[0]
+    ws_bytes = int(_lib.raw("runia_knn_workspace_bytes")(nq, nb, d, k))
+    ws = _empty((ws_bytes,), torch.uint8)
+    status = _empty((4,), torch.int32)
+    use_tc = _tc_ok(d) and bank.planes is not None
+    off = lambda t, w: None if t is None else t.data_ptr() + lo * w * t.element_size()  # noqa: E731
+    _lib.call("runia_knn_search_f32", qn.data_ptr() + lo * d * 4, nq, bank.bank.data_ptr(), bank.sqnorm.data_ptr(),
+              bank.planes[0].data_ptr() if use_tc else None, bank.planes[1].data_ptr() if use_tc else None,
+              nb, d, k, bank.idx_offset, off(res["dist"], k), off(res["dist64"], k), off(res["idx"], k),
+              off(res["kth"], 1), status.data_ptr(), ws.data_ptr(), ws_bytes, stream_ptr())
+    return status if want_status else None
 
 
 def knn_search(qn: torch.Tensor, bank: KNNBank, k: int, want_idx=True, want_dist=True, want_f64=False,
                check_status=True):
-    """qn: [Nq, d] normalised float32 CUDA.  Returns dict(dist [Nq,k] f32, dist64, idx [Nq,k] i64,
-    kth [Nq] f32, exhaustive_rows int)."""
+    """qn: [Nq, d] float32 CUDA (normalised for the postprocessors; any rows for FlatL2Index).  Returns
+    dict(dist [Nq,k] f32, dist64, idx [Nq,k] i64, kth [Nq] f32, exhaustive_rows int).  `check_status` only fills
+    `exhaustive_rows` (one device -> host read); the search itself cannot fail on ties."""
     nq, d = qn.shape
     nb = bank.bank.shape[0]
     res = {"dist": None, "dist64": None, "idx": None, "kth": _empty((nq,), torch.float32), "exhaustive_rows": 0}
@@ -397,22 +418,16 @@ def knn_search(qn: torch.Tensor, bank: KNNBank, k: int, want_idx=True, want_dist
         res["idx"] = _empty((nq, k), torch.int64)
     if nq == 0:
         return res
-    ws_bytes = int(_lib.raw("runia_knn_workspace_bytes")(nq, nb, d, k))
-    if ws_bytes <= 0:
-        raise NotImplementedError(f"kNN: k={k} outside [1, 240]")
-    ws = _empty((ws_bytes,), torch.uint8)
-    status = _empty((4,), torch.int32)
-    use_tc = _tc_ok(d) and bank.planes is not None
-    _lib.call("runia_knn_search_f32", qn.data_ptr(), nq, bank.bank.data_ptr(), bank.sqnorm.data_ptr(),
-              bank.planes[0].data_ptr() if use_tc else None, bank.planes[1].data_ptr() if use_tc else None,
-              nb, d, k, bank.idx_offset, ptr(res["dist"]), ptr(res["dist64"]), ptr(res["idx"]), res["kth"].data_ptr(),
-              status.data_ptr(), ws.data_ptr(), ws_bytes, stream_ptr())
+    if not 1 <= k <= KNN_MAX_K:
+        raise NotImplementedError(f"kNN: k={k} outside [1, {KNN_MAX_K}]")
+    qn = qn.contiguous()
+    chunk = nq
+    while chunk > 256 and int(_lib.raw("runia_knn_workspace_bytes")(chunk, nb, d, k)) > KNN_WS_CHUNK_BYTES:
+        chunk = (chunk // 2 + 255) // 256 * 256
+    stats = [_knn_search_chunk(qn, bank, k, res, lo, min(nq, lo + chunk), check_status)
+             for lo in range(0, nq, chunk)]
     if check_status:
-        st = status.cpu()
-        res["exhaustive_rows"] = int(st[0])
-        if int(st[1]) != 0:
-            raise KNNOverflow("kNN exhaustive pass overflowed its tie buffer (more than 4096 bank rows tie "
-                              "with the k-th neighbour)")
+        res["exhaustive_rows"] = int(torch.stack(stats)[:, 0].sum().item())
     return res
 
 
@@ -504,39 +519,83 @@ def logit_scores(logits, gamma=0.1, M=None, energy=True, msp=True, gen=True):
     return e, m, g, in_dtype
 
 
-LINEAR_TC_MAX_CLASSES = 32   # UMMA N of the narrow-panel kernel
-LINEAR_TC_MIN_ROWS = 16384   # below this the one-warp-per-row kernel is as fast and needs no operand planes
+LINEAR_TC_NARROW_CLASSES = 32  # UMMA N of the narrow-panel kernel; wider heads use 256-column panels
+LINEAR_TC_MIN_ROWS = 16384     # narrow heads: below this the one-warp-per-row kernel is as fast and needs no planes
+LINEAR_SMEM_MAX_CLASSES = 64   # logits.cu CL_MAXC: heads with C <= 64 and C*d*4 <= 200 KiB stay resident in shared memory
 
 
 def linear_planes(W: torch.Tensor):
-    """TF32 hi / lo planes of the head's weight matrix, zero-padded to [32, d], for runia_clip_linear_lse_tc."""
-    Wp = torch.zeros((LINEAR_TC_MAX_CLASSES, W.shape[1]), dtype=torch.float32, device=device())
-    Wp[: W.shape[0]] = W
-    return split_tf32(Wp)
+    """TF32 hi / lo planes of the head's weight matrix for runia_clip_linear_lse_tc: zero-padded to [32, d] for
+    C <= 32 (narrow panel), [C, d] as it is for wider heads."""
+    if W.shape[0] <= LINEAR_TC_NARROW_CLASSES:
+        Wp = torch.zeros((LINEAR_TC_NARROW_CLASSES, W.shape[1]), dtype=torch.float32, device=device())
+        Wp[: W.shape[0]] = W
+        return split_tf32(Wp)
+    return split_tf32(W.contiguous())
+
+
+def head_fits_smem(C: int, d: int) -> bool:
+    return C <= LINEAR_SMEM_MAX_CLASSES and C * d * 4 <= 200 * 1024
 
 
 def clip_linear_lse(x, W: torch.Tensor, b: torch.Tensor, clip=float("inf"), planes=None) -> torch.Tensor:
-    """logsumexp(min(x, clip) @ W.T + b): the ReAct / DICE / DICE+ReAct head.  Large batches of rows with
-    d % 4 == 0 stream through the tcgen05 narrow-panel kernel; `planes` = linear_planes(W) (built here when absent)."""
+    """logsumexp(min(x, clip) @ W.T + b): the ReAct / DICE / DICE+ReAct head, any C and d.  Rows with d % 4 == 0
+    stream through the tcgen05 kernels (narrow panel for C <= 32 and large batches, 256-column panels with an
+    online log-sum-exp for any wider head); `planes` = linear_planes(W) (built here when absent).  Other shapes use
+    the FP32 SIMT kernels (resident head when it fits shared memory, streamed otherwise)."""
     xf, _ = as_f32_rows(x, None)
     n, d = xf.shape
+    C = W.shape[0]
     out = _empty((n,), torch.float32)
-    if n >= LINEAR_TC_MIN_ROWS and _tc_ok(d) and W.shape[0] <= LINEAR_TC_MAX_CLASSES and xf.data_ptr() % 16 == 0:
+    aligned = xf.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0
+    wide = C > LINEAR_TC_NARROW_CLASSES
+    if _tc_ok(d) and aligned and (wide or n >= LINEAR_TC_MIN_ROWS):
         hi, lo = planes if planes is not None else linear_planes(W)
-        _lib.call("runia_clip_linear_lse_tc", xf.data_ptr(), n, d, hi.data_ptr(), lo.data_ptr(), b.data_ptr(), W.shape[0],
+        _lib.call("runia_clip_linear_lse_tc", xf.data_ptr(), n, d, hi.data_ptr(), lo.data_ptr(), b.data_ptr(), C,
                   float(clip), out.data_ptr(), stream_ptr())
         return out
-    _lib.call("runia_clip_linear_lse_f32", xf.data_ptr(), n, d, W.data_ptr(), b.data_ptr(), W.shape[0],
+    _lib.call("runia_clip_linear_lse_f32", xf.data_ptr(), n, d, W.data_ptr(), b.data_ptr(), C,
               float(clip), out.data_ptr(), stream_ptr())
     return out
 
 
-def ash_linear_lse(x, W: torch.Tensor, b: torch.Tensor, k_keep: int) -> torch.Tensor:
+def ash_prune(x, k_keep: int) -> torch.Tensor:
+    """ASH-S pruned and rescaled rows [N, d] float32 (funcs.py:230-261) for any row width."""
     xf, _ = as_f32_rows(x, None)
     n, d = xf.shape
+    out = _empty((n, d), torch.float32)
+    _lib.call("runia_ash_prune_f32", xf.data_ptr(), n, d, int(k_keep), out.data_ptr(), stream_ptr())
+    return out
+
+
+def ash_linear_lse(x, W: torch.Tensor, b: torch.Tensor, k_keep: int, planes=None) -> torch.Tensor:
+    """ASH-S score.  Heads that fit shared memory run the fused prune + head kernel; any other head prunes into a
+    scratch [N, d] and goes through clip_linear_lse (tensor cores for d % 4 == 0)."""
+    xf, _ = as_f32_rows(x, None)
+    n, d = xf.shape
+    if head_fits_smem(W.shape[0], d):
+        out = _empty((n,), torch.float32)
+        _lib.call("runia_ash_linear_lse_f32", xf.data_ptr(), n, d, W.data_ptr(), b.data_ptr(), W.shape[0],
+                  int(k_keep), out.data_ptr(), stream_ptr())
+        return out
+    return clip_linear_lse(ash_prune(xf, k_keep), W, b, planes=planes)
+
+
+def gen_entropy_from_probs(probs, gamma: float, M: int) -> torch.Tensor:
+    """generalized_entropy on rows that already are probabilities (no softmax; funcs.py:347-375)."""
+    p = to_device(probs, torch.float32)
+    n, C = p.shape
     out = _empty((n,), torch.float32)
-    _lib.call("runia_ash_linear_lse_f32", xf.data_ptr(), n, d, W.data_ptr(), b.data_ptr(), W.shape[0],
-              int(k_keep), out.data_ptr(), stream_ptr())
+    _lib.call("runia_gen_entropy_f32", p.data_ptr(), n, C, float(gamma), int(M), out.data_ptr(), stream_ptr())
+    return out
+
+
+def linear(x, W: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+    """x @ W.T + b as float32 [N, C] (FP32 SIMT contraction): RouteDICE.forward."""
+    xf, _ = as_f32_rows(x, None)
+    n, d = xf.shape
+    out = _empty((n, W.shape[0]), torch.float32)
+    _lib.call("runia_linear_f32", xf.data_ptr(), n, d, W.data_ptr(), ptr(b), W.shape[0], out.data_ptr(), stream_ptr())
     return out
 
 

@@ -5,6 +5,8 @@
 #include <math.h>
 #include <float.h>
 
+#include <atomic>
+
 #include "../../include/runia_b200.h"
 
 namespace runia {
@@ -29,6 +31,26 @@ int finish_launch(const char *what);  // cudaGetLastError -> return code (+ mess
       return (int)_e;                                                             \
     }                                                                             \
   } while (0)
+
+// "Done once" flag for per-device state (cudaFuncSetAttribute is per device / context): reads as false until it
+// has been set on the CURRENT device.  A racing second thread at worst repeats an idempotent attribute call.
+struct PerDeviceFlag {
+  std::atomic<uint64_t> mask{0};
+  static int cur() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+  }
+  bool operator!() const {
+    const int dev = cur();
+    return dev >= 64 || !((mask.load(std::memory_order_acquire) >> dev) & 1ull);
+  }
+  PerDeviceFlag &operator=(bool v) {
+    const int dev = cur();
+    if (v && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_release);
+    return *this;
+  }
+};
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -219,7 +219,9 @@ struct KnnRerankArgs {
   const float *buf_d;
   const int32_t *buf_i;
   const int32_t *counts;  // [Nq, splits] list lengths (plan.counted) or nullptr
-  float eps;
+  float eps;                 // rounding bound of the approximate pass per unit of (|q|^2 + max_b |b|^2) / 2
+  const float *qn;           // [Nq] |q|^2
+  const uint32_t *bn_max;    // [1] bit pattern of max_b |b|^2 (non-negative floats order like their bits)
   int64_t idx_offset;
   float *out_dist;
   double *out_dist64;
@@ -231,12 +233,12 @@ struct KnnRerankArgs {
   int32_t *flag_I;       // [Nq] its index
 };
 
-constexpr int RERANK_WARPS = 8;
+constexpr int RERANK_WARPS = 8;  // at most; fewer for large kcap (the per-warp scratch is 28 kcap bytes)
 
 __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerankArgs a) {
   extern __shared__ unsigned char dyn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * RERANK_WARPS + warp;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= a.Nq) return;
   const int kcap = a.plan.kcap, S = a.plan.splits, capp = a.plan.capp;
   const int nbuf_max = 2 * kcap;
@@ -361,7 +363,10 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerank
     if (a.out_kth) a.out_kth[row] = have_k ? (float)ekey[k - 1] : FLT_MAX;
     // all bank rows are candidates when the merged list is not full
     bool certified = !list_full;
-    if (list_full) certified = ((double)L - (double)a.eps > ekey[k - 1]);
+    // |approx - exact| <= eps * (|q|^2 + |b|^2) / 2 (|q.b| <= (|q|^2 + |b|^2) / 2; the norms themselves are rounded
+    // once): unit-norm rows (every built-in postprocessor) give eps itself, un-normalised FlatL2Index banks scale it
+    const double scale = 0.5 * ((double)a.qn[row] + (double)__uint_as_float(*a.bn_max));
+    if (list_full) certified = ((double)L - (double)a.eps * scale > ekey[k - 1]);
     if (!certified) {
       const int slot = atomicAdd(a.flag_count, 1);
       a.flag_rows[slot] = (int32_t)row;
@@ -376,58 +381,108 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerank
 // Every true neighbour satisfies (dist, idx) <= (T, I) lexicographically, where (T, I) is the
 // exact k-th candidate; collect those pairs, sort, emit the first k.
 // --------------------------------------------------------------------------------------------
-constexpr int FB_CAP = 4096;
+constexpr int FB_CAP = 4096;    // hit buffer per block
+constexpr int FB_CHUNK = 2048;  // bank rows scanned between two overflow checks (a chunk adds at most that many hits)
+constexpr int FB_THREADS = 256;
+constexpr int FB_PER_THREAD = FB_CAP / FB_THREADS;
 
-__global__ void __launch_bounds__(256) knn_fallback_kernel(KnnRerankArgs a, int32_t *status,
-                                                           double *fb_d, int32_t *fb_i) {
+// Keeps the min(n, k) smallest (distance, index) pairs of the buffer, sorted ascending, in its first slots.
+// Rank counting: the order is total (indices are distinct), so ranks are a permutation.
+__device__ __forceinline__ void fb_select(double *hd, int32_t *hi, int n, int k) {
+  double de[FB_PER_THREAD];
+  int32_t ie[FB_PER_THREAD];
+  int rk[FB_PER_THREAD];
+#pragma unroll
+  for (int u = 0; u < FB_PER_THREAD; ++u) {
+    const int e = threadIdx.x + FB_THREADS * u;
+    de[u] = e < n ? hd[e] : (double)INFINITY;
+    ie[u] = e < n ? hi[e] : 0x7fffffff;
+    rk[u] = 0;
+  }
+  for (int o = 0; o < n; ++o) {
+    const double dd = hd[o];
+    const int32_t io = hi[o];
+#pragma unroll
+    for (int u = 0; u < FB_PER_THREAD; ++u) rk[u] += (dd < de[u] || (dd == de[u] && io < ie[u])) ? 1 : 0;
+  }
+  __syncthreads();  // every thread has read the whole buffer
+#pragma unroll
+  for (int u = 0; u < FB_PER_THREAD; ++u) {
+    const int e = threadIdx.x + FB_THREADS * u;
+    if (e < n && rk[u] < k) {
+      hd[rk[u]] = de[u];
+      hi[rk[u]] = ie[u];
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(FB_THREADS) knn_fallback_kernel(KnnRerankArgs a, int32_t *status,
+                                                                  double *fb_d, int32_t *fb_i) {
   __shared__ int n_hit;
+  __shared__ double sT;
+  __shared__ int32_t sI;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_flag = *a.flag_count;
+  double *hd = fb_d + (size_t)blockIdx.x * FB_CAP;
+  int32_t *hi = fb_i + (size_t)blockIdx.x * FB_CAP;
   for (int f = blockIdx.x; f < n_flag; f += gridDim.x) {
     const int64_t row = a.flag_rows[f];
-    const double T = a.flag_T[f];
-    const int32_t I = a.flag_I[f];
-    double *hd = fb_d + (size_t)blockIdx.x * FB_CAP;
-    int32_t *hi = fb_i + (size_t)blockIdx.x * FB_CAP;
-    if (threadIdx.x == 0) n_hit = 0;
-    __syncthreads();
+    if (threadIdx.x == 0) {
+      n_hit = 0;
+      sT = a.flag_T[f];
+      sI = a.flag_I[f];
+    }
     const float *q = a.Q + row * (int64_t)a.d;
-    for (int64_t b = warp; b < a.Nb; b += 8) {
-      const double ex = exact_sqdist_warp(q, a.B + b * a.d, a.d, lane);
-      if (lane == 0 && (ex < T || (ex == T && (int32_t)b <= I))) {
-        const int pos = atomicAdd(&n_hit, 1);
-        if (pos < FB_CAP) {
+    for (int64_t c0 = 0; c0 < a.Nb; c0 += FB_CHUNK) {
+      __syncthreads();
+      // Any number of bank rows may tie with the k-th neighbour (all-zero activations normalise to identical
+      // vectors): when the next chunk could overflow the buffer, cut it back to its k smallest pairs and tighten
+      // the bound (T, I) to the k-th of them -- every true neighbour still satisfies (dist, idx) <= (T, I).
+      if (n_hit > FB_CAP - FB_CHUNK) {  // block-uniform (read after the barrier)
+        const int n = n_hit;
+        fb_select(hd, hi, n, a.k);
+        if (threadIdx.x == 0) {
+          n_hit = a.k;
+          sT = hd[a.k - 1];
+          sI = hi[a.k - 1];
+        }
+        __syncthreads();
+      }
+      const double T = sT;
+      const int32_t I = sI;
+      const int64_t c1 = c0 + FB_CHUNK < a.Nb ? c0 + FB_CHUNK : a.Nb;
+      for (int64_t b = c0 + warp; b < c1; b += FB_THREADS / 32) {
+        const double ex = exact_sqdist_warp(q, a.B + b * a.d, a.d, lane);
+        if (lane == 0 && (ex < T || (ex == T && (int32_t)b <= I))) {
+          const int pos = atomicAdd(&n_hit, 1);
           hd[pos] = ex;
           hi[pos] = (int32_t)b;
         }
       }
     }
     __syncthreads();
-    const int n = n_hit;
-    if (n > FB_CAP) {
-      if (threadIdx.x == 0) atomicExch(&status[1], 1);
-    } else {
-      // selection by rank: entry e goes to position #(pairs smaller than it); n is small
-      for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        const double de = hd[e];
-        const int32_t ie = hi[e];
-        int rank = 0;
-        for (int o = 0; o < n; ++o) {
-          const double dd = hd[o];
-          const int32_t io = hi[o];
-          rank += (dd < de || (dd == de && io < ie)) ? 1 : 0;
-        }
-        if (rank < a.k) {
-          if (a.out_dist) a.out_dist[row * a.k + rank] = (float)de;
-          if (a.out_dist64) a.out_dist64[row * a.k + rank] = de;
-          if (a.out_idx) a.out_idx[row * a.k + rank] = (int64_t)ie + a.idx_offset;
-          if (rank == a.k - 1 && a.out_kth) a.out_kth[row] = (float)de;
-        }
-      }
+    const int n = n_hit;  // >= k: the k candidates up to (T, I) are hits themselves
+    fb_select(hd, hi, n, a.k);
+    for (int e = threadIdx.x; e < a.k && e < n; e += blockDim.x) {
+      const double de = hd[e];
+      if (a.out_dist) a.out_dist[row * a.k + e] = (float)de;
+      if (a.out_dist64) a.out_dist64[row * a.k + e] = de;
+      if (a.out_idx) a.out_idx[row * a.k + e] = (int64_t)hi[e] + a.idx_offset;
+      if (e == a.k - 1 && a.out_kth) a.out_kth[row] = (float)de;
     }
     if (threadIdx.x == 0) atomicAdd(&status[0], 1);
     __syncthreads();
   }
+}
+
+// max over the bank of |b|^2 (scales the certification bound); non-negative floats compare like their bit patterns
+__global__ void __launch_bounds__(256) max_sqnorm_kernel(const float *__restrict__ bn, int64_t Nb, uint32_t *out) {
+  float m = 0.f;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < Nb; e += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, __ldg(bn + e));
+  m = warp_max32(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
 // --------------------------------------------------------------------------------------------
@@ -437,10 +492,10 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const double *__restric
                                                          const int64_t *__restrict__ pi, int R, int64_t Nq,
                                                          int k, float *out_dist, int64_t *out_idx,
                                                          float *out_kth) {
-  // one thread per query row: R-way merge by head pointers (R <= 16, k <= 240)
+  // one thread per query row: R-way merge by head pointers (R <= 64)
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= Nq) return;
-  int head[16];
+  int head[64];
   for (int r = 0; r < R; ++r) head[r] = 0;
   for (int e = 0; e < k; ++e) {
     int best = -1;
@@ -591,6 +646,7 @@ struct KnnWorkspace {
   size_t qn, thr_key, counts, buf_d, buf_i, flag_count, flag_rows, flag_T, flag_I, fb_d, fb_i, total;
 };
 constexpr int FB_GRID = 64;
+constexpr int kKnnMaxK = 1016;  // kcap = 1024 candidates per row survive the merge
 static KnnWorkspace knn_layout(int64_t Nq, const KnnPlan &p) {
   KnnWorkspace w;
   size_t o = 0;
@@ -668,7 +724,7 @@ extern "C" int runia_row_sqnorm_f32(const float *X, int64_t N, int d, float *out
 }
 
 extern "C" int64_t runia_knn_workspace_bytes(int64_t Nq, int64_t Nb, int d, int k) {
-  if (Nq <= 0 || Nb <= 0 || k <= 0 || k > 240) return 0;
+  if (Nq <= 0 || Nb <= 0 || k <= 0 || k > kKnnMaxK) return 0;
   (void)d;
   const size_t a = knn_layout(Nq, make_knn_plan(Nq, Nb, k, false)).total;
   const size_t b = knn_layout(Nq, make_knn_plan(Nq, Nb, k, true)).total;
@@ -682,7 +738,7 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
                                     void *workspace, int64_t workspace_bytes, void *stream) {
   RUNIA_REQUIRE(Nq >= 0 && Nb > 0 && d > 0, RUNIA_E_BADARG, "knn_search: bad sizes Nq=%lld Nb=%lld d=%d",
                 (long long)Nq, (long long)Nb, d);
-  RUNIA_REQUIRE(k >= 1 && k <= 240, RUNIA_E_UNSUPPORTED, "knn_search: k=%d outside [1, 240]", k);
+  RUNIA_REQUIRE(k >= 1 && k <= kKnnMaxK, RUNIA_E_UNSUPPORTED, "knn_search: k=%d outside [1, %d]", k, kKnnMaxK);
   RUNIA_REQUIRE(Nb < (int64_t)0x7fffffff, RUNIA_E_UNSUPPORTED, "knn_search: bank shard too large");
   if (Nq == 0) return RUNIA_OK;
   RUNIA_REQUIRE(Qn && Bn && Bn_sqnorm && status && workspace, RUNIA_E_BADARG, "knn_search: null pointer");
@@ -699,9 +755,11 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   int32_t *buf_i = (int32_t *)(ws + w.buf_i);
   int32_t *flag_count = (int32_t *)(ws + w.flag_count);
 
-  RUNIA_CUDA(cudaMemsetAsync(flag_count, 0, 256, st));
+  RUNIA_CUDA(cudaMemsetAsync(flag_count, 0, 256, st));  // [0] flagged rows, [1] max_b |b|^2
   RUNIA_CUDA(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st));
   row_sqnorm_kernel<<<(unsigned)ceil_div(Nq, 8), 256, 0, st>>>(Qn, Nq, d, qn);
+  max_sqnorm_kernel<<<(unsigned)std::min<int64_t>(ceil_div(Nb, 256 * 8), 4 * kNumSMs), 256, 0, st>>>(
+      Bn_sqnorm, Nb, (uint32_t *)flag_count + 1);
 
   if (tensor) {
     const int rc = tc::launch_knn_candidates_tc(Qn, qn, Nq, Bn_hi, Bn_lo, Bn_sqnorm, Nb, d, plan.kcap, plan.fin_max,
@@ -710,9 +768,9 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
     if (rc) return rc;
   } else {
     const size_t dyn1 = (size_t)8 * plan.capp * 8;
-    static bool attr1 = false;
+    static PerDeviceFlag attr1;
     if (!attr1) {
-      RUNIA_CUDA(cudaFuncSetAttribute(knn_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      RUNIA_CUDA(cudaFuncSetAttribute(knn_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
       attr1 = true;
     }
     dim3 grid1((unsigned)ceil_div(Nq, BM), (unsigned)plan.splits);
@@ -724,8 +782,11 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   a.buf_d = buf_d; a.buf_i = buf_i;
   a.counts = plan.counted ? (const int32_t *)(ws + w.counts) : nullptr;
   // |approx - exact| <= (2K + 8) * 2^-24 for unit-norm rows (DESIGN.md "kNN certification")
-  //   3xTF32: operand split error 2^-20 per unit of sum|q_i b_i| plus FP32 accumulation -> doubled bound
+  //   3xTF32: operand split error 2^-20 per unit of sum|q_i b_i| plus FP32 accumulation -> doubled bound;
+  // the re-rank kernel scales it by (|q|^2 + max|b|^2) / 2 for rows that are not unit-norm
   a.eps = (float)((2.0 * d + 8.0) * 5.9604644775390625e-08 * (tensor ? 2.5 : 1.25));
+  a.qn = qn;
+  a.bn_max = (const uint32_t *)flag_count + 1;
   a.idx_offset = idx_offset;
   a.out_dist = out_dist; a.out_dist64 = out_dist_f64; a.out_idx = out_idx; a.out_kth = out_kth;
   a.flag_count = flag_count;
@@ -733,21 +794,22 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   a.flag_T = (double *)(ws + w.flag_T);
   a.flag_I = (int32_t *)(ws + w.flag_I);
   const size_t per_warp = (((size_t)2 * plan.kcap * 8 + (size_t)plan.kcap * 12) + 15) / 16 * 16;
-  const size_t dyn2 = per_warp * RERANK_WARPS;
-  static bool attr2 = false;
+  const int rw = plan.kcap <= 256 ? RERANK_WARPS : plan.kcap <= 512 ? 4 : 2;  // <= 56 KB of scratch per block
+  const size_t dyn2 = per_warp * rw;
+  static PerDeviceFlag attr2;
   if (!attr2) {
     RUNIA_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr2 = true;
   }
-  knn_rerank_kernel<<<(unsigned)ceil_div(Nq, RERANK_WARPS), RERANK_WARPS * 32, dyn2, st>>>(a);
-  knn_fallback_kernel<<<FB_GRID, 256, 0, st>>>(a, status, (double *)(ws + w.fb_d), (int32_t *)(ws + w.fb_i));
-  count_launch(4);
+  knn_rerank_kernel<<<(unsigned)ceil_div(Nq, rw), rw * 32, dyn2, st>>>(a);
+  knn_fallback_kernel<<<FB_GRID, FB_THREADS, 0, st>>>(a, status, (double *)(ws + w.fb_d), (int32_t *)(ws + w.fb_i));
+  count_launch(5);
   return finish_launch("knn_search");
 }
 
 extern "C" int runia_topk_merge(const double *part_dist, const int64_t *part_idx, int R, int64_t Nq, int k,
                                 float *out_dist, int64_t *out_idx, float *out_kth, void *stream) {
-  RUNIA_REQUIRE(R >= 1 && R <= 16 && Nq >= 0 && k >= 1, RUNIA_E_BADARG, "topk_merge: bad sizes R=%d k=%d", R, k);
+  RUNIA_REQUIRE(R >= 1 && R <= 64 && Nq >= 0 && k >= 1, RUNIA_E_BADARG, "topk_merge: bad sizes R=%d k=%d", R, k);
   if (Nq == 0) return RUNIA_OK;
   RUNIA_REQUIRE(part_dist && part_idx, RUNIA_E_BADARG, "topk_merge: null pointer");
   topk_merge_kernel<<<(unsigned)ceil_div(Nq, 128), 128, 0, (cudaStream_t)stream>>>(part_dist, part_idx, R, Nq, k,

@@ -90,7 +90,7 @@ extern "C" int runia_eigen_score_f32(const float *E, int n, int d, double alpha,
   RUNIA_REQUIRE(n <= EG_MAXN && n <= d && (size_t)d * 8 <= 200 * 1024, RUNIA_E_UNSUPPORTED,
                 "eigen_score: n=%d samples (max %d, at most d) or d=%d (max 25600) not supported", n, EG_MAXN, d);
   RUNIA_REQUIRE(E && out, RUNIA_E_BADARG, "eigen_score: null pointer");
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     RUNIA_CUDA(cudaFuncSetAttribute(eigen_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;

@@ -495,6 +495,9 @@ static void launch_entropy_np(const float *z, int64_t n_items, int n, int D, flo
 }
 
 // ---------------------------------- generic path ------------------------------------------
+constexpr int kEntropyMaxN = 128;  // largest n_mc of the generic kernels (local arrays / the n x n matrix in shared memory)
+
+template <int NMAX>
 __global__ void __launch_bounds__(128)
 entropy_generic_dim_kernel(const float *__restrict__ z, int64_t n_items, int n, int D, int k, float min_dist,
                            double c_term, double *__restrict__ h_z) {
@@ -504,7 +507,7 @@ entropy_generic_dim_kernel(const float *__restrict__ z, int64_t n_items, int n, 
   const int64_t item = e / D;
   const int j = (int)(e % D);
   const float *zi = z + item * (int64_t)n * D + j;
-  float s[32];
+  float s[NMAX];
   for (int i = 0; i < n; ++i) {  // insertion sort
     const float x = zi[(int64_t)i * D];
     int p = i;
@@ -566,6 +569,52 @@ entropy_generic_joint_kernel(const float *__restrict__ z, int64_t n_items, int n
   if (lane == 0) h_mvn[item] = c_term + (double)D * (double)(kLn2 * (1.f + lg / (float)n));
 }
 
+// n_mc > 32: one block per item, the n x n Chebyshev matrix in dynamic shared memory (row stride n + 1)
+__global__ void __launch_bounds__(128)
+entropy_generic_joint_big_kernel(const float *__restrict__ z, int64_t n_items, int n, int D, int k, float min_dist,
+                                 double c_term, double *__restrict__ h_mvn) {
+  extern __shared__ float dmb[];  // [n][n + 1]
+  __shared__ float part[4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t item = blockIdx.x;
+  const float *zi = z + item * (int64_t)n * D;
+  const int ld = n + 1;
+  for (int p = warp; p < n * n; p += 4) {
+    const int a = p / n, b = p - a * n;
+    if (b <= a) continue;
+    float m = 0.f;
+    for (int j = lane; j < D; j += 32) m = fmaxf(m, fabsf(zi[(int64_t)a * D + j] - zi[(int64_t)b * D + j]));
+    m = warp_max32(m);
+    if (lane == 0) {
+      dmb[a * ld + b] = m;
+      dmb[b * ld + a] = m;
+    }
+  }
+  for (int a = threadIdx.x; a < n; a += blockDim.x) dmb[a * ld + a] = 0.f;
+  __syncthreads();
+  float lg = 0.f;
+  for (int a = threadIdx.x; a < n; a += blockDim.x) {
+    float r = 0.f;  // element of row a with exactly k predecessors under the total order (value, index)
+    for (int b = 0; b < n; ++b) {
+      const float vb = dmb[a * ld + b];
+      int rank = 0;
+      for (int c = 0; c < n; ++c) {
+        const float vc = dmb[a * ld + c];
+        rank += (vc < vb || (vc == vb && c < b)) ? 1 : 0;
+      }
+      if (rank == k) r = vb;
+    }
+    lg += __log2f(fmaxf(r, min_dist));
+  }
+  lg = warp_sum32(lg);
+  if (lane == 0) part[warp] = lg;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float tot = (part[0] + part[1]) + (part[2] + part[3]);
+    h_mvn[item] = c_term + (double)D * (double)(kLn2 * (1.f + tot / (float)n));
+  }
+}
+
 }  // namespace runia
 
 using namespace runia;
@@ -574,14 +623,15 @@ extern "C" int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, 
                                      double digamma_term, double *h_z, double *h_mvn, void *stream) {
   RUNIA_REQUIRE(n_items >= 0 && D > 0, RUNIA_E_BADARG, "mcd_entropy: bad sizes n_items=%lld D=%d",
                 (long long)n_items, D);
-  RUNIA_REQUIRE(n_mc >= 2 && n_mc <= 32, RUNIA_E_UNSUPPORTED, "mcd_entropy: n_mc=%d outside [2, 32]", n_mc);
+  RUNIA_REQUIRE(n_mc >= 2 && n_mc <= kEntropyMaxN, RUNIA_E_UNSUPPORTED, "mcd_entropy: n_mc=%d outside [2, %d]", n_mc,
+                kEntropyMaxN);
   RUNIA_REQUIRE(k >= 1 && k < n_mc, RUNIA_E_BADARG, "mcd_entropy: k=%d must satisfy 1 <= k < n_mc=%d", k, n_mc);
   if (n_items == 0) return RUNIA_OK;
   RUNIA_REQUIRE(z && h_z, RUNIA_E_BADARG, "mcd_entropy: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (n_mc == 16 && k == 5 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(h_z) & 15) == 0) {
-    static bool attr16 = false;
+    static PerDeviceFlag attr16;
     if (!attr16) {
       RUNIA_CUDA(cudaFuncSetAttribute(entropy16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kEntropy16Smem));
@@ -597,7 +647,7 @@ extern "C" int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, 
   if (n_mc == 16 && k == 5) {
     constexpr int WARPS = 4;
     constexpr size_t smem = (size_t)WARPS * 120 * 32 * sizeof(float);
-    static bool attr = false;
+    static PerDeviceFlag attr;
     if (!attr) {
       RUNIA_CUDA(cudaFuncSetAttribute(entropy_fast_kernel<16, 5, WARPS>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -608,7 +658,7 @@ extern "C" int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, 
     count_launch();
     return finish_launch("mcd_entropy(fast)");
   }
-  if (k == 5 && n_mc >= 6) {  // the reference's k for every n_mc > 5 (evaluation/entropy.py:66)
+  if (k == 5 && n_mc >= 6 && n_mc <= 32) {  // the reference's k for every n_mc > 5 (evaluation/entropy.py:66)
     if (n_mc <= 8)
       launch_entropy_np<8>(z, n_items, n_mc, D, (float)min_dist, digamma_term, h_z, h_mvn, st);
     else if (n_mc <= 16)
@@ -619,12 +669,27 @@ extern "C" int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, 
     return finish_launch("mcd_entropy(np)");
   }
   const int64_t total = n_items * (int64_t)D;
-  entropy_generic_dim_kernel<<<(unsigned)ceil_div(total, 128), 128, 0, st>>>(z, n_items, n_mc, D, k, (float)min_dist,
-                                                                            digamma_term, h_z);
+  if (n_mc <= 32)
+    entropy_generic_dim_kernel<32><<<(unsigned)ceil_div(total, 128), 128, 0, st>>>(z, n_items, n_mc, D, k, (float)min_dist,
+                                                                                  digamma_term, h_z);
+  else
+    entropy_generic_dim_kernel<kEntropyMaxN><<<(unsigned)ceil_div(total, 128), 128, 0, st>>>(
+        z, n_items, n_mc, D, k, (float)min_dist, digamma_term, h_z);
   count_launch();
-  if (h_mvn) {
+  if (h_mvn && n_mc <= 32) {
     entropy_generic_joint_kernel<<<(unsigned)ceil_div(n_items, 4), 128, 0, st>>>(z, n_items, n_mc, D, k,
                                                                                 (float)min_dist, digamma_term, h_mvn);
+    count_launch();
+  } else if (h_mvn) {
+    const size_t dyn = (size_t)n_mc * (n_mc + 1) * sizeof(float);
+    static PerDeviceFlag attrb;
+    if (!attrb) {
+      RUNIA_CUDA(cudaFuncSetAttribute(entropy_generic_joint_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)((size_t)kEntropyMaxN * (kEntropyMaxN + 1) * sizeof(float))));
+      attrb = true;
+    }
+    entropy_generic_joint_big_kernel<<<(unsigned)n_items, 128, dyn, st>>>(z, n_items, n_mc, D, k, (float)min_dist,
+                                                                         digamma_term, h_mvn);
     count_launch();
   }
   return finish_launch("mcd_entropy(generic)");

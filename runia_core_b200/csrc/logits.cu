@@ -142,30 +142,91 @@ logit_scores_small_kernel(const float *__restrict__ logits, int64_t N, int C, fl
   }
 }
 
-// large C: one warp per row (M must cover all classes)
+// Any C: one warp per row.  The row is staged in shared memory when it fits (8 rows per block), else re-read from
+// global memory (L1 / L2).  GEN over the M largest probabilities (funcs.py:371: np.sort(probs)[:, -M:]): the M-th
+// largest logit is found by a radix select on order-preserving keys (softmax is monotone, so the logits order the
+// probabilities), one warp-wide count per bit, stopping at the first bit where exactly M keys lie at or above the
+// candidate; elements tied with the M-th value have equal terms, so only their number matters.
+// PROBS: the row already holds probabilities (generalized_entropy(probs, ...) called directly, funcs.py:347-375):
+// no softmax, terms p^gamma (1 - p)^gamma with powf like NumPy's float32 power.
+__device__ __forceinline__ uint32_t okey(float v) {
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+template <bool PROBS>
 __global__ void __launch_bounds__(256)
-logit_scores_wide_kernel(const float *__restrict__ logits, int64_t N, int C, float gamma,
+logit_scores_wide_kernel(const float *__restrict__ logits, int64_t N, int C, float gamma, int M, int stage_floats,
                          float *__restrict__ energy, float *__restrict__ msp, float *__restrict__ gen) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  extern __shared__ __align__(16) float srow[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * 8 + warp;
   if (row >= N) return;
   const float *l = logits + row * (int64_t)C;
-  float m = -INFINITY;
-  for (int c = lane; c < C; c += 32) m = fmaxf(m, __ldg(l + c));
-  m = warp_max32(m);
-  float s = 0.f;
-  for (int c = lane; c < C; c += 32) s += expf(__ldg(l + c) - m);
-  s = warp_sum32(s);
+  if (stage_floats) {
+    float *st = srow + (size_t)warp * stage_floats;
+    for (int c = lane; c < C; c += 32) st[c] = __ldg(l + c);
+    __syncwarp();
+    l = st;
+  }
+  float m = 0.f, lg2s = 0.f;
+  if (!PROBS) {
+    m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, l[c]);
+    m = warp_max32(m);
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += ex2_fast((l[c] - m) * kLog2e);
+    sum = warp_sum32(sum);
+    lg2s = lg2_fast(sum);
+    if (lane == 0) {
+      if (energy) energy[row] = fmaf(lg2s, kLn2f, m);
+      if (msp) msp[row] = 1.f / sum;
+    }
+  }
+  if (!gen) return;
+  auto term = [&](float x) -> float {
+    if (PROBS) return gen_term(x, gamma);
+    const float lp = (x - m) * kLog2e - lg2s;  // log2 p
+    return ex2_fast(gamma * (lp + lg2_fast(1.f - ex2_fast(lp))));
+  };
   float g = 0.f;
-  if (gen) {
-    for (int c = lane; c < C; c += 32) g += gen_term(expf(__ldg(l + c) - m) / s, gamma);
-    g = warp_sum32(g);
+  if (M <= 0 || M >= C) {  // [:, -M:] with M >= C (or M = 0) is the whole row
+    for (int c = lane; c < C; c += 32) g += term(l[c]);
+  } else {
+    uint32_t prefix = 0;
+    bool exact = false;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = prefix | (1u << bit);
+      int cnt = 0;
+      for (int c = lane; c < C; c += 32) cnt += okey(l[c]) >= cand ? 1 : 0;
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt >= M) prefix = cand;
+      if (cnt == M) {
+        exact = true;
+        break;
+      }
+    }
+    if (exact) {
+      for (int c = lane; c < C; c += 32) g += okey(l[c]) >= prefix ? term(l[c]) : 0.f;
+    } else {  // prefix = key of the M-th largest value, and it is tied
+      int n_gt = 0;
+      float tie = -INFINITY;
+      for (int c = lane; c < C; c += 32) {
+        const uint32_t k = okey(l[c]);
+        if (k > prefix) {
+          g += term(l[c]);
+          ++n_gt;
+        } else if (k == prefix) {
+          tie = term(l[c]);
+        }
+      }
+      n_gt = __reduce_add_sync(0xffffffffu, n_gt);
+      tie = warp_max32(tie);
+      if (lane == 0) g += (float)(M - n_gt) * tie;
+    }
   }
-  if (lane == 0) {
-    if (energy) energy[row] = logf(s) + m;
-    if (msp) msp[row] = 1.f / s;
-    if (gen) gen[row] = -g;
-  }
+  g = warp_sum32(g);
+  if (lane == 0) gen[row] = -g;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -438,7 +499,7 @@ ash_lse_c16_kernel(const float *__restrict__ X, int64_t N, int d, const float *_
 template <int CN>
 static int launch_ash16(int nch, unsigned blocks, size_t smem, cudaStream_t st, const float *X, int64_t N, int d,
                         const float *W, const float *b, int C, int k_keep, float *out) {
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     RUNIA_CUDA(cudaFuncSetAttribute(ash_lse_c16_kernel<CN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     RUNIA_CUDA(cudaFuncSetAttribute(ash_lse_c16_kernel<CN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -544,9 +605,145 @@ linear_lse_kernel(const float *__restrict__ X, int64_t N, int d, const float *__
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// clip -> linear -> log-sum-exp for ANY head (C, d): one warp per four rows, W and the rows streamed from
+// L1 / L2, online log-sum-exp over the classes.  The shapes the faster kernels cannot take end up here
+// (d % 4 != 0 or d > 4096 with a head that does not fit shared memory).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+linear_lse_rows4_kernel(const float *__restrict__ X, int64_t N, int d, const float *__restrict__ W,
+                        const float *__restrict__ b, int C, float clip, float *__restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t groups = (N + 3) >> 2;
+  for (int64_t gq = (int64_t)blockIdx.x * 8 + warp; gq < groups; gq += (int64_t)gridDim.x * 8) {
+    const float *x[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) x[r] = X + (4 * gq + r < N ? 4 * gq + r : 4 * gq) * (int64_t)d;
+    float mx[4], sm[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      mx[r] = -INFINITY;
+      sm[r] = 0.f;
+    }
+    for (int c = 0; c < C; ++c) {
+      const float *w = W + (size_t)c * d;
+      float p[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = lane; j < d; j += 32) {
+        const float wj = __ldg(w + j);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float v = __ldg(x[r] + j);
+          v = v > clip ? clip : v;  // NaN stays NaN like numpy.clip
+          p[r] = fmaf(v, wj, p[r]);
+        }
+      }
+      const float bc = __ldg(b + c);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float lg = warp_sum32(p[r]) + bc;
+        const float m_new = fmaxf(mx[r], lg);
+        sm[r] = sm[r] * expf(mx[r] - m_new) + expf(lg - m_new);
+        mx[r] = m_new;
+      }
+    }
+    if (lane < 4 && 4 * gq + lane < N) {
+      float mo = mx[0], so = sm[0];
+#pragma unroll
+      for (int r = 1; r < 4; ++r)
+        if (lane == r) {
+          mo = mx[r];
+          so = sm[r];
+        }
+      out[4 * gq + lane] = mo + logf(so);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// ASH-S pruning for any row width (funcs.py:230-261): keep the k largest activations of the row (ties with the
+// k-th value: lowest indices first), zero the rest, scale by exp(sum_all / sum_kept).  One warp per row; the
+// k-th largest value by radix select on order-preserving keys.  Feeds the general heads above (C > 16 or
+// d > 1024); the small heads fuse the same selection into the head kernel (ash_lse_c16_kernel).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ash_prune_kernel(const float *__restrict__ X, int64_t N, int d, int k_keep, float *__restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < N; row += (int64_t)gridDim.x * 8) {
+    const float *x = X + row * (int64_t)d;
+    uint32_t prefix = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = prefix | (1u << bit);
+      int cnt = 0;
+      for (int j = lane; j < d; j += 32) cnt += okey(__ldg(x + j)) >= cand ? 1 : 0;
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt >= k_keep) prefix = cand;
+      if (cnt == k_keep) break;  // exactly the top k lie at or above the candidate: no tie at the cut
+    }
+    int n_gt = 0;
+    float s1 = 0.f, s_gt = 0.f;
+    for (int j = lane; j < d; j += 32) {
+      const float v = __ldg(x + j);
+      s1 += v;
+      if (okey(v) > prefix) {
+        ++n_gt;
+        s_gt += v;
+      }
+    }
+    n_gt = __reduce_add_sync(0xffffffffu, n_gt);
+    s1 = warp_sum32(s1);
+    s_gt = warp_sum32(s_gt);
+    // after an early break `prefix` need not be a key of the row: then every kept element compares greater, and
+    // the number of ties to keep is k - n_gt = (elements >= prefix) - n_gt = elements == prefix, possibly 0
+    const int n_ties_keep = k_keep - n_gt;
+    // the tied value itself is the float behind `prefix` (all ties are the same float)
+    const float tv = (prefix & 0x80000000u) ? __uint_as_float(prefix & 0x7fffffffu) : __uint_as_float(~prefix);
+    const float s2 = s_gt + (n_ties_keep > 0 ? (float)n_ties_keep * tv : 0.f);
+    const float scale = expf(s1 / s2);
+    float *o = out + row * (int64_t)d;
+    int ties_before = 0;
+    for (int j0 = 0; j0 < d; j0 += 32) {
+      const int j = j0 + lane;
+      const float v = j < d ? __ldg(x + j) : 0.f;
+      const uint32_t k = j < d ? okey(v) : 0u;
+      const bool is_tie = j < d && k == prefix;
+      const unsigned tie_mask = __ballot_sync(0xffffffffu, is_tie);
+      const int my_rank = ties_before + __popc(tie_mask & ((1u << lane) - 1u));
+      const bool keep = j < d && (k > prefix || (is_tie && my_rank < n_ties_keep));
+      if (j < d) o[j] = keep ? v * scale : 0.f;
+      ties_before += __popc(tie_mask);
+    }
+  }
+}
+
 }  // namespace runia
 
 using namespace runia;
+
+template <bool PROBS>
+static cudaError_t launch_logit_wide(const float *logits, int64_t N, int C, float gamma, int M, float *energy, float *msp,
+                                     float *gen, cudaStream_t st) {
+  static PerDeviceFlag attr;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(logit_scores_wide_kernel<PROBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  const int stage = (C + 3) & ~3;  // floats per warp; 8 warps per block
+  const size_t smem = (size_t)8 * stage * sizeof(float);
+  const bool fits = smem <= 160 * 1024;
+  logit_scores_wide_kernel<PROBS><<<(unsigned)ceil_div(N, 8), 256, fits ? smem : 0, st>>>(logits, N, C, gamma, M,
+                                                                                        fits ? stage : 0, energy, msp, gen);
+  return cudaSuccess;
+}
+
+extern "C" int runia_gen_entropy_f32(const float *probs, int64_t N, int C, float gamma, int M, float *out, void *stream) {
+  RUNIA_REQUIRE(N >= 0 && C > 0, RUNIA_E_BADARG, "gen_entropy: bad sizes");
+  if (N == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(probs && out, RUNIA_E_BADARG, "gen_entropy: null pointer");
+  RUNIA_CUDA(launch_logit_wide<true>(probs, N, C, gamma, M, nullptr, nullptr, out, (cudaStream_t)stream));
+  count_launch();
+  return finish_launch("gen_entropy");
+}
 
 extern "C" int runia_logit_scores_f32(const float *logits, int64_t N, int C, float gamma, int M, float *energy,
                                       float *msp, float *gen, void *stream) {
@@ -556,7 +753,7 @@ extern "C" int runia_logit_scores_f32(const float *logits, int64_t N, int C, flo
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 64) {
     const size_t smem = (size_t)LS_ROWS * C * sizeof(float);
-    static bool attr = false;
+    static PerDeviceFlag attr;
     if (!attr) {
       RUNIA_CUDA(cudaFuncSetAttribute(logit_scores_small_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024));
       attr = true;
@@ -577,8 +774,7 @@ extern "C" int runia_logit_scores_f32(const float *logits, int64_t N, int C, flo
       logit_scores_small_kernel<64><<<grid, LS_ROWS, smem, st>>>(logits, N, C, gamma, M, energy, msp, gen);
     }
   } else {
-    RUNIA_REQUIRE(!gen || M >= C, RUNIA_E_UNSUPPORTED, "logit_scores: GEN with M=%d < C=%d needs C <= 64", M, C);
-    logit_scores_wide_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(logits, N, C, gamma, energy, msp, gen);
+    RUNIA_CUDA(launch_logit_wide<false>(logits, N, C, gamma, M, energy, msp, gen, st));
   }
   count_launch();
   return finish_launch("logit_scores");
@@ -587,13 +783,20 @@ extern "C" int runia_logit_scores_f32(const float *logits, int64_t N, int C, flo
 static int launch_linear_lse(bool ash, const float *X, int64_t N, int d, const float *W, const float *b, int C,
                              float clip, int k_keep, float *out, void *stream) {
   RUNIA_REQUIRE(N >= 0 && d > 0 && C > 0, RUNIA_E_BADARG, "linear_lse: bad sizes");
-  RUNIA_REQUIRE(C <= CL_MAXC && (size_t)C * d * 4 <= 200 * 1024, RUNIA_E_UNSUPPORTED,
-                "linear_lse: C=%d, d=%d exceed the shared-memory weight tile (C <= %d, C*d*4 <= 200 KiB)", C, d,
-                CL_MAXC);
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(X && W && b && out, RUNIA_E_BADARG, "linear_lse: null pointer");
+  const bool fits = C <= CL_MAXC && (size_t)C * d * 4 <= 200 * 1024;  // head resident in shared memory
+  if (!fits) {
+    RUNIA_REQUIRE(!ash, RUNIA_E_UNSUPPORTED,
+                  "ash_linear_lse: C=%d, d=%d exceed the fused kernel (C <= %d, C*d*4 <= 200 KiB): prune with "
+                  "runia_ash_prune_f32, then call runia_clip_linear_lse_*", C, d, CL_MAXC);
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(ceil_div(N, 4), 8), (int64_t)kNumSMs * 8);
+    linear_lse_rows4_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(X, N, d, W, b, C, clip, out);
+    count_launch();
+    return finish_launch("linear_lse(general)");
+  }
   const size_t smem = (size_t)C * d * sizeof(float);
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     RUNIA_CUDA(cudaFuncSetAttribute(linear_lse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     RUNIA_CUDA(cudaFuncSetAttribute(linear_lse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -602,7 +805,7 @@ static int launch_linear_lse(bool ash, const float *X, int64_t N, int d, const f
   const int cn = (C + 3) & ~3;
   const size_t smem16 = (size_t)cn * ((d + 511) & ~511) * sizeof(float);
   if (!ash && C <= LH_C && smem16 <= 100 * 1024) {
-    static bool attr16 = false;
+    static PerDeviceFlag attr16;
     if (!attr16) {
       RUNIA_CUDA(cudaFuncSetAttribute(linear_lse_c16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       RUNIA_CUDA(cudaFuncSetAttribute(linear_lse_c16_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -647,6 +850,17 @@ static int launch_linear_lse(bool ash, const float *X, int64_t N, int d, const f
 extern "C" int runia_clip_linear_lse_f32(const float *X, int64_t N, int d, const float *W, const float *b, int C,
                                          float clip, float *out, void *stream) {
   return launch_linear_lse(false, X, N, d, W, b, C, clip, 0, out, stream);
+}
+
+extern "C" int runia_ash_prune_f32(const float *X, int64_t N, int d, int k_keep, float *out, void *stream) {
+  RUNIA_REQUIRE(N >= 0 && d > 0, RUNIA_E_BADARG, "ash_prune: bad sizes");
+  RUNIA_REQUIRE(k_keep >= 1 && k_keep <= d, RUNIA_E_BADARG, "ash_prune: k_keep=%d outside [1, d=%d]", k_keep, d);
+  if (N == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(X && out, RUNIA_E_BADARG, "ash_prune: null pointer");
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(N, 8), (int64_t)kNumSMs * 8);
+  ash_prune_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(X, N, d, k_keep, out);
+  count_launch();
+  return finish_launch("ash_prune");
 }
 
 extern "C" int runia_ash_linear_lse_f32(const float *X, int64_t N, int d, const float *W, const float *b, int C,
@@ -750,7 +964,7 @@ extern "C" int runia_pred_uncertainty_f32(const float *logits, int64_t n_items, 
   if (n_items == 0) return RUNIA_OK;
   RUNIA_REQUIRE(logits && (pred_h || mi), RUNIA_E_BADARG, "pred_uncertainty: null pointer");
   const size_t smem = C > 32 ? (size_t)8 * C * sizeof(float) : 0;
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     RUNIA_CUDA(cudaFuncSetAttribute(runia::pred_uncertainty_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024));
     attr = true;

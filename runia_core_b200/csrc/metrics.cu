@@ -479,7 +479,7 @@ static int ood_metrics_impl(const T *ind, int64_t n_ind, const T *ood, int64_t n
   MetricsOut *mo = (MetricsOut *)(ws + L.mo);
   uint32_t *flag = (uint32_t *)(ws + L.flag);
 
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     RUNIA_CUDA(cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmem));
     attr = true;
@@ -554,7 +554,7 @@ extern "C" int runia_sort_f32(const float *x, int64_t n, float *out_sorted, void
   uint64_t *ka = (uint64_t *)(ws + L.keys_a), *kb = (uint64_t *)(ws + L.keys_b);
   uint32_t *va = (uint32_t *)(ws + L.vals_a), *vb = (uint32_t *)(ws + L.vals_b);
   uint32_t *hist = (uint32_t *)(ws + L.hist), *hist_tiles = (uint32_t *)(ws + L.hist_tiles);
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     RUNIA_CUDA(cudaFuncSetAttribute(rs_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmem));
     attr = true;

@@ -137,7 +137,7 @@ static int launch_sampler(const float *x, const float *maskT, const int *kept, i
                           cudaStream_t st) {
   const int hwc = std::min(HW, SP_HWC), stride = hwc | 1;
   const size_t smem = (size_t)SP_WARPS * (SP_CH * stride + hwc * NMC) * sizeof(float);
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     RUNIA_CUDA(cudaFuncSetAttribute(mc_dropblock_mean_kernel<NMC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)((size_t)SP_WARPS * (SP_CH * (SP_HWC | 1) + SP_HWC * NMC) * sizeof(float))));

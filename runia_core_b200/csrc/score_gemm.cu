@@ -3,6 +3,8 @@
 // Each CTA owns 128 input rows and walks ALL output columns in 128-wide panels, so every
 // row-wise reduction (sum of squares, max over classes, log-sum-exp) completes inside one CTA:
 // no atomics, deterministic, and the [N, r] intermediate never reaches HBM.
+#include <algorithm>
+
 #include "rowgemm.cuh"
 
 namespace runia {
@@ -13,7 +15,7 @@ namespace runia {
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 pca_transform_kernel(const float *__restrict__ X, int64_t N, int D0, const float *__restrict__ mean,
                      const float *__restrict__ Ct, int d, const float *__restrict__ inv_scale,
-                     float *__restrict__ Z) {
+                     const float *__restrict__ bias, float *__restrict__ Z) {
   __shared__ GemmSmem sm;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -35,6 +37,7 @@ pca_transform_kernel(const float *__restrict__ X, int64_t N, int D0, const float
         for (int q = 0; q < 4; ++q) {
           const float sc = (inv_scale && col + q < d) ? __ldg(inv_scale + col + q) : 1.f;
           v[q] = acc[i][h * 4 + q] * sc;
+          if (bias && col + q < d) v[q] += __ldg(bias + col + q);
         }
         if (vec_store && col + 3 < d) {
           *reinterpret_cast<float4 *>(Z + row * d + col) = make_float4(v[0], v[1], v[2], v[3]);
@@ -110,8 +113,10 @@ rownorm_kernel(const float *__restrict__ X, int64_t N, int d, const float *__res
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 classcond_kernel(const float *__restrict__ X, int64_t N, int d, const float *__restrict__ g,
                  const float *__restrict__ Wt, int r, const float *__restrict__ sign,
-                 const float *__restrict__ Mc, const int32_t *__restrict__ valid, int C,
+                 const float *__restrict__ Mc, const int32_t *__restrict__ valid, int C, int accumulate,
                  double *__restrict__ out64, float *__restrict__ out32) {
+  // C = classes of THIS launch (Mc / valid already point at the chunk); accumulate: fold with the score the
+  // previous chunk left in out (more than 256 classes are scored 256 at a time)
   __shared__ GemmSmem sm;
   extern __shared__ float cls[];  // [BM][C]
   const int64_t m0 = (int64_t)blockIdx.x * BM;
@@ -152,6 +157,7 @@ classcond_kernel(const float *__restrict__ X, int64_t N, int d, const float *__r
     const int64_t row = m0 + threadIdx.x;
     if (row < N) {
       float best = -INFINITY;
+      if (accumulate) best = out64 ? (float)out64[row] : out32[row];
       for (int c = 0; c < C; ++c)
         if (valid[c]) {
           const float sc = -cls[threadIdx.x * C + c];
@@ -233,9 +239,20 @@ extern "C" int runia_pca_transform_f32(const float *X, int64_t N, int D0, const 
   RUNIA_REQUIRE(X && components && Z, RUNIA_E_BADARG, "pca_transform: null pointer");
   const unsigned grid = (unsigned)ceil_div(N, BM);
   pca_transform_kernel<<<grid, GEMM_THREADS, 0, (cudaStream_t)stream>>>(X, N, D0, mean, components, d,
-                                                                      inv_scale, Z);
+                                                                      inv_scale, nullptr, Z);
   count_launch();
   return finish_launch("pca_transform");
+}
+
+extern "C" int runia_linear_f32(const float *X, int64_t N, int d, const float *W, const float *b, int C, float *out,
+                                void *stream) {
+  RUNIA_REQUIRE(N >= 0 && d > 0 && C > 0, RUNIA_E_BADARG, "linear: bad sizes N=%lld d=%d C=%d", (long long)N, d, C);
+  if (N == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(X && W && out, RUNIA_E_BADARG, "linear: null pointer");
+  const unsigned grid = (unsigned)ceil_div(N, BM);
+  pca_transform_kernel<<<grid, GEMM_THREADS, 0, (cudaStream_t)stream>>>(X, N, d, nullptr, W, C, nullptr, b, out);
+  count_launch();
+  return finish_launch("linear");
 }
 
 extern "C" int runia_rownorm_score_f32(const float *X, int64_t N, int d, const float *mu, const float *Wt,
@@ -259,19 +276,21 @@ extern "C" int runia_classcond_mahalanobis_f32(const float *X, int64_t N, int d,
                                                const int32_t *class_valid, int C, double *out_f64,
                                                float *out_f32, void *stream) {
   RUNIA_REQUIRE(N >= 0 && d > 0 && r > 0 && C > 0, RUNIA_E_BADARG, "classcond: bad sizes");
-  RUNIA_REQUIRE(C <= 256, RUNIA_E_UNSUPPORTED, "classcond: C=%d > 256 classes not supported", C);
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(X && Wt && Mc && class_valid && (out_f64 || out_f32), RUNIA_E_BADARG, "classcond: null pointer");
-  const size_t dyn = (size_t)BM * C * sizeof(float);
-  static bool attr_set = false;
+  constexpr int kChunk = 256;  // classes per launch: [BM][C] partial sums live in shared memory
+  static PerDeviceFlag attr_set;
   if (!attr_set) {
     RUNIA_CUDA(cudaFuncSetAttribute(classcond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
     attr_set = true;
   }
   const unsigned grid = (unsigned)ceil_div(N, BM);
-  classcond_kernel<<<grid, GEMM_THREADS, dyn, (cudaStream_t)stream>>>(X, N, d, g, Wt, r, sign, Mc, class_valid,
-                                                                    C, out_f64, out_f32);
-  count_launch();
+  for (int c0 = 0; c0 < C; c0 += kChunk) {
+    const int cc = std::min(kChunk, C - c0);
+    classcond_kernel<<<grid, GEMM_THREADS, (size_t)BM * cc * sizeof(float), (cudaStream_t)stream>>>(
+        X, N, d, g, Wt, r, sign, Mc + (size_t)c0 * r, class_valid + c0, cc, c0 > 0 ? 1 : 0, out_f64, out_f32);
+    count_launch();
+  }
   return finish_launch("classcond_mahalanobis");
 }
 

@@ -287,6 +287,58 @@ struct LinearLseEpi {
   __device__ void finish() {}
 };
 
+// (a10) the same head for ANY class count (ImageNet: C = 1000, COCO: C = 80): the classes are the columns of the
+// 256-wide panels, the log-sum-exp runs online across panels in log2 units (like KdeEpi); columns >= C are the TMA's
+// zero fill and are masked out.      postprocessors.py:1444-1474, 1325-1354, 1591-1621
+struct WideLinearLseEpi {
+  const float *bias;  // [C], 16-byte aligned
+  int C;
+  float *out;
+  int64_t M;
+  int64_t row;
+  float m, s;
+  __device__ void set_stage(uint32_t) {}
+  template <class P> __device__ void bind(const P *) {}
+  __device__ void begin(int, int64_t row_) {
+    row = row_;
+    m = -INFINITY;
+    s = 0.f;
+  }
+  __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
+    constexpr float kLog2e = 1.4426950408889634f;
+    if (col0 >= C) return;
+    float t[32];
+    float tmax = -INFINITY;
+    if (col0 + 32 <= C) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + col0) + g);  // same address in every lane
+        t[4 * g + 0] = (v[4 * g + 0] + b4.x) * kLog2e;
+        t[4 * g + 1] = (v[4 * g + 1] + b4.y) * kLog2e;
+        t[4 * g + 2] = (v[4 * g + 2] + b4.z) * kLog2e;
+        t[4 * g + 3] = (v[4 * g + 3] + b4.w) * kLog2e;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t[j] = col0 + j < C ? (v[j] + __ldg(bias + col0 + j)) * kLog2e : -INFINITY;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, t[j]);
+    if (tmax == -INFINITY) return;
+    const float m_new = fmaxf(m, tmax);
+    float acc = s * exp2f(m - m_new);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc += exp2f(t[j] - m_new);
+    s = acc;
+    m = m_new;
+  }
+  __device__ void panel_done(int) {}
+  __device__ void finish() {
+    constexpr float kLn2 = 0.6931471805599453f;
+    if (row < M) out[row] = (m + __log2f(s)) * kLn2;
+  }
+};
+
 // (a9) DDU / GMM: columns are C blocks of dpad whitened coordinates; per class
 // lp_c = -0.5 sum_j (v_j - off_j)^2 + logconst_c, out = logsumexp_c lp_c (online, per thread)
 struct GmmEpi {
@@ -868,7 +920,7 @@ extern "C" int runia_rownorm_score_tc(const float *X, int64_t N, int d, const fl
   if (rc) return rc;
   rc = make_b_map(&ml, Wt_lo, r, d);
   if (rc) return rc;
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     rc = set_smem(tc_kernel<RowNormEpi>, kSmemMax);
     if (rc) return rc;
@@ -886,7 +938,6 @@ extern "C" int runia_rownorm_score_tc(const float *X, int64_t N, int d, const fl
 extern "C" int runia_clip_linear_lse_tc(const float *X, int64_t N, int d, const float *W_hi, const float *W_lo,
                                         const float *b, int C, float clip, float *out, void *stream) {
   RUNIA_REQUIRE(N >= 0 && d > 0 && C > 0, RUNIA_E_BADARG, "clip_linear_lse_tc: bad sizes");
-  RUNIA_REQUIRE(C <= kNarrowN, RUNIA_E_UNSUPPORTED, "clip_linear_lse_tc: C=%d classes not supported (max %d)", C, kNarrowN);
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(X && W_hi && W_lo && b && out, RUNIA_E_BADARG, "clip_linear_lse_tc: null pointer");
   RUNIA_REQUIRE(usable(X, d, W_hi, W_lo), RUNIA_E_UNSUPPORTED,
@@ -894,12 +945,34 @@ extern "C" int runia_clip_linear_lse_tc(const float *X, int64_t N, int d, const 
   CUtensorMap ma, mh, ml;
   int rc = make_a_map(&ma, X, N, d);
   if (rc) return rc;
+  dim3 grid(2 * (unsigned)std::min<int64_t>(ceil_div(N, TM2), kNumSMs / 2), 1);
+  const Prologue pro{nullptr, clip};
+  if (C > kNarrowN) {
+    // any class count: planes are [C, d]; 256-column panels, online log-sum-exp across them
+    RUNIA_REQUIRE((reinterpret_cast<uintptr_t>(b) & 15) == 0, RUNIA_E_UNSUPPORTED,
+                  "clip_linear_lse_tc: the bias must be 16-byte aligned");
+    rc = make_b_map(&mh, W_hi, C, d);
+    if (rc) return rc;
+    rc = make_b_map(&ml, W_lo, C, d);
+    if (rc) return rc;
+    static PerDeviceFlag attrw;
+    if (!attrw) {
+      rc = set_smem(tc_kernel<WideLinearLseEpi>, kSmemMax);
+      if (rc) return rc;
+      attrw = true;
+    }
+    WideLinearLseEpi epi{b, C, out, N, 0, 0.f, 0.f};
+    tc_kernel<WideLinearLseEpi><<<grid, THREADS, smem_bytes(d), (cudaStream_t)stream>>>(ma, N, d, pro, mh, ml,
+                                                                                  (int)ceil_div(C, TN), epi);
+    count_launch();
+    return finish_launch("clip_linear_lse_tc(wide)");
+  }
   const int nw = C <= 16 ? 16 : 32;                 // planes are [32, d] with rows >= C zero; the first nw are read
   rc = make_map(&mh, W_hi, nw, d, nw / 2);
   if (rc) return rc;
   rc = make_map(&ml, W_lo, nw, d, nw / 2);
   if (rc) return rc;
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     rc = set_smem(tc_narrow_kernel<LinearLseEpi<16>, 16>, smem_bytes_variant(kMaxK, 16, kNarrowStages));
     if (rc) return rc;
@@ -907,8 +980,6 @@ extern "C" int runia_clip_linear_lse_tc(const float *X, int64_t N, int d, const 
     if (rc) return rc;
     attr = true;
   }
-  dim3 grid(2 * (unsigned)std::min<int64_t>(ceil_div(N, TM2), kNumSMs / 2), 1);
-  const Prologue pro{nullptr, clip};
   if (nw == 16) {
     LinearLseEpi<16> epi{b, C, out, N, 0};
     tc_narrow_kernel<LinearLseEpi<16>, 16><<<grid, THREADS, smem_bytes_variant(d, 16, kNarrowStages), (cudaStream_t)stream>>>(
@@ -925,7 +996,7 @@ extern "C" int runia_clip_linear_lse_tc(const float *X, int64_t N, int d, const 
 extern "C" int runia_tf32_peak_probe(int iters, double *flop_out, void *stream) {
   RUNIA_REQUIRE(iters >= 1 && iters <= (1 << 24), RUNIA_E_BADARG, "tf32_peak_probe: iters out of range");
   const size_t smem = (size_t)A_PLANE_BYTES + B_PLANE_BYTES + 64 + SMEM_ALIGN;
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     int rc = set_smem(tc_peak_kernel, smem);
     if (rc) return rc;
@@ -953,7 +1024,7 @@ extern "C" int runia_pca_transform_tc(const float *X, int64_t N, int D0, const f
   if (rc) return rc;
   rc = make_b_map(&ml, C_lo, d, D0);
   if (rc) return rc;
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     rc = set_smem(tc_kernel<PcaEpi>, kSmemMax);
     if (rc) return rc;
@@ -990,7 +1061,7 @@ extern "C" int runia_classcond_mahalanobis_tc(const float *X, int64_t N, int d, 
   if (rc) return rc;
   rc = make_b_map(&ml, Wt_lo, r, d);
   if (rc) return rc;
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     rc = set_smem(tc_kernel<ClassCondEpi>, kSmemMax);
     if (rc) return rc;
@@ -1021,7 +1092,7 @@ extern "C" int runia_gmm_lse_tc(const float *X, int64_t N, int d, const float *A
   if (rc) return rc;
   rc = make_b_map(&ml, At_lo, cols, d);
   if (rc) return rc;
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     rc = set_smem(tc_kernel<GmmEpi>, kSmemMax);
     if (rc) return rc;
@@ -1051,7 +1122,7 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
   rc = make_b_map(&ml, B_lo, Nb, d);
   if (rc) return rc;
   const size_t smem = smem_bytes(d);
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     rc = set_smem(tc_knn_kernel, kSmemMax);
     if (rc) return rc;
@@ -1104,7 +1175,7 @@ int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const flo
   if (rc) return rc;
   rc = make_b_map(&ml, B_lo, Nb, d);
   if (rc) return rc;
-  static bool attr = false;
+  static PerDeviceFlag attr;
   if (!attr) {
     rc = set_smem(tc_kde_kernel, kSmemMax);
     if (rc) return rc;

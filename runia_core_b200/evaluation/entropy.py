@@ -12,7 +12,7 @@ from .._device import to_device, to_host
 
 __all__ = ["get_dl_h_z", "single_image_entropy_calculation"]
 
-MAX_MC_SAMPLES = 32
+MAX_MC_SAMPLES = 128  # entropy.cu kEntropyMaxN; the tuned kernels cover 2..32, the generic ones the rest
 
 
 def single_image_entropy_calculation(sample: np.ndarray, neighbors: int) -> np.ndarray:

@@ -99,11 +99,8 @@ class RouteDICE(torch.nn.Linear):
     def forward(self, x):
         if self.masked_w is None:
             self.calculate_mask_weight()
-        x = to_device(x, torch.float32)
-        out = x @ self.masked_w.t()
-        if self.bias is not None:
-            out = out + self.bias.to(out.device)
-        return out
+        bias = None if self.bias is None else to_device(self.bias.detach(), torch.float32)
+        return _ops.linear(x, self.masked_w, bias)
 
 
 def ash_s_linear_layer(x: np.ndarray, percentile: int = 85):
@@ -111,14 +108,9 @@ def ash_s_linear_layer(x: np.ndarray, percentile: int = 85):
     features; the ASH postprocessor itself uses the fused kernel and never materialises them."""
     assert x.ndim == 2
     assert 0 <= percentile <= 100
-    xt = to_device(x, torch.float32)
-    n = xt.shape[1]
+    n = x.shape[1]
     k = n - int(np.round(n * percentile / 100.0))
-    s1 = xt.sum(dim=1)
-    vals, idx = torch.topk(xt, k, dim=1)
-    scattered = torch.zeros_like(xt).scatter_(1, idx, vals)
-    s2 = scattered.sum(dim=1)
-    return to_host(scattered * torch.exp(s1 / s2)[:, None])
+    return to_host(_ops.ash_prune(x, k))
 
 
 def gmm_fit(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: int):
@@ -156,13 +148,11 @@ def gmm_fit(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: int):
 
 
 def generalized_entropy(probs, gamma, M):
-    """-sum over the M largest probabilities of p^gamma (1-p)^gamma (funcs.py:347-375).
-    Runs the fused logit kernel on log(probs): softmax(log p) == p for normalised rows."""
-    p = np.asarray(probs)
-    with np.errstate(divide="ignore"):
-        lg = np.log(p.astype(np.float64)).astype(np.float32)
-    _, _, g, _ = _ops.logit_scores(lg, gamma=gamma, M=M, energy=False, msp=False, gen=True)
-    return to_host(g).astype(p.dtype if p.dtype.kind == "f" else np.float32)
+    """-sum over the M largest entries of each row of p^gamma (1-p)^gamma (funcs.py:347-375).  The rows are used as
+    they are (no re-normalisation), like upstream; float64 input is scored in float32 and widened."""
+    p = probs.detach().cpu().numpy() if isinstance(probs, torch.Tensor) else np.asarray(probs)
+    g = to_host(_ops.gen_entropy_from_probs(p, gamma, M))
+    return g.astype(p.dtype if p.dtype.kind == "f" else np.float32)
 
 
 def get_predictive_uncertainty_score(input_samples: torch.Tensor, mcd_nro_samples: int) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -67,8 +67,8 @@ def _linear_params(kwargs):
 # ------------------------------------------------------------------------------------------------
 def _head_planes(W):
     """TF32 planes of a head's weight matrix for the tensor-core linear head, built once at setup
-    (None when the head does not qualify: more than 32 classes or a width that is not a multiple of 4)."""
-    if W.shape[0] <= _ops.LINEAR_TC_MAX_CLASSES and W.shape[1] % 4 == 0:
+    (None when the head does not qualify: a width that is not a multiple of 4 or above 4096)."""
+    if W.shape[1] % 4 == 0 and W.shape[1] <= _ops.TC_MAX_K:
         return _ops.linear_planes(W)
     return None
 
@@ -239,11 +239,11 @@ class FlatL2Index:
 
     def search(self, x, k: int):
         q = to_device(x, torch.float32)
-        res = _ops.knn_search(q, self._bank, k)
+        res = _ops.knn_search(q, self._bank, k, check_status=False)
         return to_host(res["dist"]), to_host(res["idx"])
 
     def kth_distance(self, q: torch.Tensor, k: int) -> torch.Tensor:
-        return _ops.knn_search(q, self._bank, k, want_idx=False, want_dist=False)["kth"]
+        return _ops.knn_search(q, self._bank, k, want_idx=False, want_dist=False, check_status=False)["kth"]
 
 
 def _knn_scores(index: FlatL2Index, test_data, k: int) -> np.ndarray:
@@ -491,13 +491,14 @@ class ASH(OodPostprocessor):
     def _score(self, x):
         n = x.shape[1]
         k = n - int(np.round(n * self.ash_percentile / 100.0))
-        return to_host(_ops.ash_linear_lse(x, self._w, self._b, k))
+        return to_host(_ops.ash_linear_lse(x, self._w, self._b, k, planes=self._planes))
 
     def setup(self, ind_train_data: np.ndarray, **kwargs):
         assert "final_linear_layer_params" in kwargs, "final_linear_layer_params must be provided for ASH"
         assert "valid_feats" in kwargs, "valid_feats must be provided for ASH"
         self.w, self.b = _linear_params(kwargs)
         self._w, self._b = to_device(self.w, torch.float32), to_device(self.b, torch.float32)
+        self._planes = None if _ops.head_fits_smem(*self._w.shape) else _head_planes(self._w)
         # the reference thresholds on the TRAIN features here (postprocessors.py:1185)
         self.set_threshold(self.flip_sign_fn(self._score(ind_train_data)))
 

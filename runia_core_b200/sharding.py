@@ -51,7 +51,7 @@ def knn_search_sharded(qn: torch.Tensor, bank_shard, k: int, group=None,
         from . import _ops
 
         search_fn = search_fn or (lambda q, b, kk: (lambda r: (r["dist64"], r["idx"]))(
-            _ops.knn_search(q, b, kk, want_f64=True, want_dist=False)))
+            _ops.knn_search(q, b, kk, want_f64=True, want_dist=False, check_status=False)))
         merge_fn = merge_fn or _ops.topk_merge
     d64, idx = search_fn(qn, bank_shard, k)
     rank, world = _world(group)

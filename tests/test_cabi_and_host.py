@@ -241,18 +241,21 @@ def test_cabi_argument_errors_without_gpu():
     assert raw("runia_mcd_entropy_f32")(None, 0, 16, 64, 5, 1e-5, 0.0, None, None, None) == 0
     assert raw("runia_rownorm_score_f32")(None, 0, 8, None, None, 8, None, 0, None, 0, 0.0, None, None, None) == 0
     assert raw("runia_logit_scores_f32")(None, 0, 10, 0.1, 10, None, None, None, None) == 0
-    # entropy: n_mc outside [2, 32] is unsupported, k >= n_mc is a bad argument
-    assert raw("runia_mcd_entropy_f32")(fake, 4, 33, 64, 5, 1e-5, 0.0, fake, None, None) == -2
-    assert "n_mc=33" in err()
+    # entropy: n_mc outside [2, 128] is unsupported, k >= n_mc is a bad argument
+    assert raw("runia_mcd_entropy_f32")(fake, 4, 129, 64, 5, 1e-5, 0.0, fake, None, None) == -2
+    assert "n_mc=129" in err()
     assert raw("runia_mcd_entropy_f32")(fake, 4, 4, 64, 4, 1e-5, 0.0, fake, None, None) == -1
     assert raw("runia_mcd_entropy_f32")(None, 4, 16, 64, 5, 1e-5, 0.0, None, None, None) == -1
-    # kNN: k outside [1, 240] unsupported; empty bank bad argument; workspace query is host-only
+    # kNN: k outside [1, 1016] unsupported; empty bank bad argument; workspace query is host-only
     assert raw("runia_knn_search_f32")(fake, 4, fake, fake, None, None, 100, 8, 0, 0, None, None, None, None, fake,
                                        fake, 1 << 20, None) == -2
     assert raw("runia_knn_search_f32")(fake, 4, fake, fake, None, None, 0, 8, 5, 0, None, None, None, None, fake,
                                        fake, 1 << 20, None) == -1
     ws = raw("runia_knn_workspace_bytes")(10_000, 50_000, 512, 50)
-    assert ws > 10_000 * 4 and raw("runia_knn_workspace_bytes")(10, 10, 8, 241) == 0
+    assert ws > 10_000 * 4 and raw("runia_knn_workspace_bytes")(10, 10, 8, 1017) == 0
+    assert raw("runia_knn_workspace_bytes")(10, 10, 8, 500) > 0
+    assert raw("runia_knn_search_f32")(fake, 4, fake, fake, None, None, 100, 8, 1017, 0, None, None, None, None, fake,
+                                       fake, 1 << 20, None) == -2
     assert raw("runia_knn_search_f32")(fake, 10_000, fake, fake, None, None, 50_000, 512, 50, 0, None, None, None, None,
                                        fake, fake, 1024, None) == -3
     assert "workspace" in err()
@@ -263,10 +266,14 @@ def test_cabi_argument_errors_without_gpu():
     # ViM mode needs logits; unknown mode is a bad argument
     assert raw("runia_rownorm_score_f32")(fake, 4, 8, None, fake, 8, None, 1, None, 0, 1.0, None, fake, None) == -1
     assert raw("runia_rownorm_score_f32")(fake, 4, 8, None, fake, 8, None, 7, None, 0, 1.0, None, fake, None) == -1
-    # linear heads: more classes than the shared-memory weight tile holds; ASH keep count outside [1, d]
-    assert raw("runia_clip_linear_lse_f32")(fake, 4, 512, fake, fake, 65, float("inf"), fake, None) == -2
+    # linear heads: the FUSED ASH kernel needs the head in shared memory (wider heads prune with runia_ash_prune_f32
+    # and use the general head); ASH keep count outside [1, d]
+    assert raw("runia_ash_linear_lse_f32")(fake, 4, 512, fake, fake, 65, 77, fake, None) == -2
+    assert "runia_ash_prune_f32" in err()
     assert raw("runia_ash_linear_lse_f32")(fake, 4, 16, fake, fake, 4, 17, fake, None) == -1
-    assert raw("runia_topk_merge")(fake, fake, 17, 4, 5, None, None, None, None) == -1
+    assert raw("runia_ash_prune_f32")(fake, 4, 16, 0, fake, None) == -1
+    assert raw("runia_clip_linear_lse_tc")(fake, 4, 510, fake, fake, fake, 1000, 1.0, fake, None) == -2  # d % 4 != 0
+    assert raw("runia_topk_merge")(fake, fake, 65, 4, 5, None, None, None, None) == -1
 
 
 def test_widening_boundary_signatures_and_argument_checks():
