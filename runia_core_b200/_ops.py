@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._device import as_f32_rows, device, ptr, stream_ptr, to_device
+from ._device import _host_array, as_f32_rows, device, ptr, stream_ptr, stream_rows, to_device
 
 FLT_MAX = float(np.finfo(np.float32).max)
 
@@ -62,10 +62,10 @@ def entropy_k(n_mc: int) -> int:
 
 def mcd_entropy(z: torch.Tensor, n_mc: int, k: Optional[int] = None, want_joint: bool = True,
                 min_dist: float = 1e-5):
-    """z: [n_items * n_mc, D] float32 CUDA.  Returns (h_mvn [n_items] f64 or None, h_z [n_items, D] f64)."""
+    """z: [n_items * n_mc, D] float32, CUDA tensor or host array / tensor.  Returns (h_mvn [n_items] f64 or None,
+    h_z [n_items, D] f64) on the device."""
     from scipy.special import digamma
 
-    assert z.is_cuda and z.dtype == torch.float32 and z.dim() == 2 and z.is_contiguous()
     if k is None:
         k = entropy_k(n_mc)
     n_items = z.shape[0] // n_mc
@@ -73,8 +73,22 @@ def mcd_entropy(z: torch.Tensor, n_mc: int, k: Optional[int] = None, want_joint:
     h_z = _empty((n_items, D), torch.float64)
     h_mvn = _empty((n_items,), torch.float64) if want_joint else None
     c_term = float(-digamma(k) + digamma(n_mc))
-    _lib.call("runia_mcd_entropy_f32", z.data_ptr(), n_items, n_mc, D, k, float(min_dist), c_term,
-              h_z.data_ptr(), ptr(h_mvn), stream_ptr())
+
+    def run(zc, lo, hi):  # items [lo, hi): zc is the device block of their n_mc * (hi - lo) sample rows
+        _lib.call("runia_mcd_entropy_f32", zc.data_ptr(), hi - lo, n_mc, D, k, float(min_dist), c_term,
+                  h_z.data_ptr() + lo * D * 8, None if h_mvn is None else h_mvn.data_ptr() + lo * 8, stream_ptr())
+
+    if not (isinstance(z, torch.Tensor) and z.is_cuda):
+        # host samples (what get_dl_h_z receives): whole items stream through the pinned ring, the kernel of one
+        # chunk of items runs while the next chunk crosses PCIe
+        pinned_ok = isinstance(z, torch.Tensor) and z.is_pinned() and z.dtype == torch.float32 and z.is_contiguous()
+        zh = z if pinned_ok else np.ascontiguousarray(_host_array(z), np.float32)
+        if stream_rows(zh[: n_items * n_mc].reshape(n_items, n_mc * D), run, min_rows=64):
+            return h_mvn, h_z
+        z = to_device(zh, torch.float32)
+    z = z.to(torch.float32).contiguous()
+    assert z.is_cuda and z.dim() == 2
+    run(z, 0, n_items)
     return h_mvn, h_z
 
 
@@ -108,16 +122,21 @@ def pca_prepare(mean, components, explained_variance, whiten) -> PCAState:
 
 
 def pca_transform(x, st: PCAState) -> torch.Tensor:
-    xf, centered = as_f32_rows(x, st.mean_f64)
-    n = xf.shape[0]
-    z = _empty((n, st.d), torch.float32)
-    mean = None if centered else ptr(st.mean_f32)
-    if _tc_ok(st.D0) and st.planes is not None and st.d % 4 == 0:
-        _lib.call("runia_pca_transform_tc", xf.data_ptr(), n, st.D0, mean, st.planes[0].data_ptr(),
-                  st.planes[1].data_ptr(), st.d, ptr(st.inv_scale), z.data_ptr(), stream_ptr())
-    else:
-        _lib.call("runia_pca_transform_f32", xf.data_ptr(), n, st.D0, mean, st.components.data_ptr(), st.d,
-                  ptr(st.inv_scale), z.data_ptr(), stream_ptr())
+    z = _empty((x.shape[0], st.d), torch.float32)
+
+    def run(xc, lo, hi):
+        xf, centered = as_f32_rows(xc, st.mean_f64)
+        mean = None if centered else ptr(st.mean_f32)
+        zp = z.data_ptr() + lo * st.d * 4
+        if _tc_ok(st.D0) and st.planes is not None and st.d % 4 == 0:
+            _lib.call("runia_pca_transform_tc", xf.data_ptr(), hi - lo, st.D0, mean, st.planes[0].data_ptr(),
+                      st.planes[1].data_ptr(), st.d, ptr(st.inv_scale), zp, stream_ptr())
+        else:
+            _lib.call("runia_pca_transform_f32", xf.data_ptr(), hi - lo, st.D0, mean, st.components.data_ptr(), st.d,
+                      ptr(st.inv_scale), zp, stream_ptr())
+
+    if not stream_rows(x, run):
+        run(x, 0, x.shape[0])
     return z
 
 
@@ -196,13 +215,21 @@ def _rownorm(xf, n, d, mu, W, planes, r, sign, mode, logits, C, alpha, o64, o32)
 
 
 def md_score(x, st: MDState, out_dtype=torch.float64) -> torch.Tensor:
-    xf, centered = as_f32_rows(x, st.mu_f64)
-    n = xf.shape[0]
-    out = _empty((n,), out_dtype)
-    o64 = out.data_ptr() if out_dtype == torch.float64 else None
-    o32 = out.data_ptr() if out_dtype == torch.float32 else None
-    _rownorm(xf, n, st.d, None if centered else st.mu_f32.data_ptr(), st.Wt, st.planes, st.r, ptr(st.sign),
-             _lib.ROWNORM_MD, None, 0, 0.0, o64, o32)
+    """LaREM scores of the rows of x.  Host matrices (what `MDLatentSpace.postprocess` receives,
+    evaluation/metrics.py:331-340) stream through the pinned staging ring: the kernel scores chunk k while chunk
+    k + 1 crosses PCIe and chunk k + 2 is copied into its slot."""
+    out = _empty((x.shape[0],), out_dtype)
+    esz = out.element_size()
+
+    def run(xc, lo, hi):
+        xf, centered = as_f32_rows(xc, st.mu_f64)
+        o = out.data_ptr() + lo * esz
+        _rownorm(xf, hi - lo, st.d, None if centered else st.mu_f32.data_ptr(), st.Wt, st.planes, st.r, ptr(st.sign),
+                 _lib.ROWNORM_MD, None, 0, 0.0, o if out_dtype == torch.float64 else None,
+                 o if out_dtype == torch.float32 else None)
+
+    if not stream_rows(x, run):
+        run(x, 0, x.shape[0])
     return out
 
 

@@ -39,12 +39,14 @@ def get_dl_h_z(dl_z_samples: Union[Tensor, np.ndarray], mcd_samples_nro: int = 3
     rows = dl_z_samples.shape[0]
     if not is_tensor and rows % n_mc != 0:
         raise ValueError("array split does not result in an equal division")
-    z = to_device(dl_z_samples, torch.float32)
-    assert z.dim() == 2
+    z = dl_z_samples  # host arrays are staged by the operator itself (pinned ring, copy / kernel overlap)
+    if is_tensor and z.is_cuda:
+        z = to_device(z, torch.float32)
+    assert z.ndim == 2
     k = _ops.entropy_k(n_mc)
     n_full = rows // n_mc
     rem = rows - n_full * n_mc
-    h_mvn, h_z = _ops.mcd_entropy(z[: n_full * n_mc].contiguous(), n_mc, k=k)
+    h_mvn, h_z = _ops.mcd_entropy(z[: n_full * n_mc], n_mc, k=k)
     h_mvn, h_z = to_host(h_mvn), to_host(h_z)
     if rem:
         if rem <= k:
@@ -52,7 +54,7 @@ def get_dl_h_z(dl_z_samples: Union[Tensor, np.ndarray], mcd_samples_nro: int = 3
             t_mvn = np.full((1,), np.inf)
             t_z = np.full((1, z.shape[1]), np.inf)
         else:
-            tm, tz = _ops.mcd_entropy(z[n_full * n_mc:].contiguous(), rem, k=k)
+            tm, tz = _ops.mcd_entropy(z[n_full * n_mc:], rem, k=k)
             t_mvn, t_z = to_host(tm), to_host(tz)
         h_mvn = np.concatenate([h_mvn, t_mvn])
         h_z = np.concatenate([h_z, t_z])
