@@ -15,6 +15,7 @@ DESIGN.md).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -27,8 +28,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+from bench_configs import _tensor as _tensor_roofline  # noqa: E402  (tensor-bound roofline against this run's TF32 probe)
+
 D_LATENT = 256
 N_TRAIN = 50_000
+WORKLOAD = ("LaREM (MDLatentSpace) scoring, d=256 after PCA, fit on 50k train latents "
+            "(BASELINE configs[1] bank size; configs[0] scorer)")
+
+
+def _config(rows_per_gpu, world):
+    """The `config` object of BOTH arms (the reference arm times bounded samples of this workload)."""
+    return {"workload": WORKLOAD, "rows_per_gpu": rows_per_gpu, "d": D_LATENT,
+            "input_bytes_per_gpu": rows_per_gpu * D_LATENT * 4,
+            "l2_policy": "inputs (4.3 GB) larger than L2 (126 MB)", "parallelism": f"rows x{world}"}
 
 
 _REAL_STDOUT = None
@@ -318,37 +330,86 @@ def run_b200(args):
                 "hbm": {"achieved": round(hbm_achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                         "frac": round(hbm_achieved / hbm_peak, 4)}}
 
+    # ---------------- the same launch back to back for >= 2 s: the sustained figure beside the 40 ms burst ---------
+    sustained = None
+    if rank == 0 and not args.no_extra:
+        n_launch = int(max(200, math.ceil(2200.0 / max(kern_ms, 1e-3))))
+        smp = ClockSampler(local, uuid)
+        smp.start()
+        t_s0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_launch):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ck = smp.stop(window=(t_s0, time.time()))
+        ms_s = e0.elapsed_time(e1) / n_launch
+        tf_s = flops / (ms_s * 1e-3) / 1e12
+        sustained = {"launches": n_launch, "seconds": round(ms_s * n_launch * 1e-3, 2), "ms_per_step": ms_s,
+                     "embeddings_per_s": n_rows / (ms_s * 1e-3), "fp32_equiv_tflops": round(tf_s, 2),
+                     "frac_of_probe_over_3": round(tf_s / peak_tf, 4), "clocks": ck}
+
     # ---------------- end to end through the reference-facing class, host buffers ----------------
+    # `md.postprocess(host array)` = what evaluation/metrics.py:331-340 calls: H2D of the rows, kernel, D2H of the
+    # float64 scores, all inside the timed region.  Headline: a pageable NumPy array (what the reference API is
+    # handed) at --e2e-rows; variants: the same from a pinned tensor, and both at 10,000 rows -- the size of one
+    # reference call (the reference arm's step) -- so that the two arms can be compared at the same call size.
+    def e2e_measure(src, reps):
+        for _ in range(3):
+            md.postprocess(src)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            md.postprocess(src)
+        torch.cuda.synchronize()
+        return max_over_ranks((time.perf_counter() - t0) / reps * 1e3) * 1e-3
+
     n_e2e = min(args.e2e_rows, n_rows)
-    host = torch.empty((n_e2e, D_LATENT), dtype=torch.float32).pin_memory()
-    host.copy_(X[:n_e2e].cpu())
-    e2e_out = {}
-
-    def e2e_step():
-        e2e_out["s"] = md.postprocess(host)  # pinned H2D -> kernel -> D2H numpy scores
-
-    for _ in range(max(1, min(args.warmup, 3))):
-        e2e_step()
-    barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    e2e_s = max_over_ranks(e2e_s * 1e3) * 1e-3
-    e2e = {"value": n_e2e * world / e2e_s, "unit": "embeddings/s", "h2d_bytes_per_step": n_e2e * D_LATENT * 4,
-           "d2h_bytes_per_step": n_e2e * 8, "rows_per_step": n_e2e}
+    variants = {}
+    for rows_v, reps in ((n_e2e, e2e_steps), (10_000, 50)):
+        host_np = X[:rows_v].cpu().numpy()
+        pinned = torch.empty((rows_v, D_LATENT), dtype=torch.float32).pin_memory()
+        pinned.copy_(torch.from_numpy(host_np))
+        for name, src in (("pageable_ndarray", host_np), ("pinned_tensor", pinned)):
+            sec = e2e_measure(src, reps)
+            variants[f"{name}_{rows_v}"] = {"embeddings_per_s": rows_v * world / sec, "ms_per_call": sec * 1e3,
+                                            "rows_per_call": rows_v,
+                                            "h2d_GBps_per_gpu": rows_v * D_LATENT * 4 / sec / 1e9}
+        del host_np, pinned
+    head = variants[f"pageable_ndarray_{n_e2e}"]
+    e2e = {"value": head["embeddings_per_s"], "unit": "embeddings/s", "h2d_bytes_per_step": n_e2e * D_LATENT * 4,
+           "d2h_bytes_per_step": n_e2e * 8, "rows_per_step": n_e2e,
+           "source": "pageable numpy.ndarray -> MDLatentSpace.postprocess -> numpy.ndarray (pinned staging ring inside)",
+           "variants": variants}
 
     extra = {}
+    if sustained is not None:
+        extra["larem_sustained"] = sustained
+    if rank == 0:
+        extra["tf32_probe_tflops"] = tf32_probe
+    del X, out_holder
+    torch.cuda.empty_cache()
     if rank == 0 and not args.no_extra:
-        extra.update(_extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak))
-        extra.update(_extra_other_kernels(torch, _ops, hbm_peak, bf16_peak))
+        extra.update(_extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak, tf32_probe, bf16_peak))
+        extra.update(_extra_other_kernels(torch, _ops, hbm_peak, bf16_peak, tf32_probe))
         if world == 1 and not args.no_sweep:
             extra["sweep_config2"] = _extra_sweep_config2(R)
-    if not args.no_extra and (world > 1 or not args.no_sweep):
-        extra.update(_extra_sharded_knn(args, torch, dist, _ops, world, rank, barrier, max_over_ranks))
+    if not args.no_extra and not args.no_configs:
+        import bench_configs as BC
+        from runia_core_b200 import sharding
+
+        probe_all = peak_tf * 3.0  # every rank divides by the same probe (broadcast above)
+        if world in (1, 2, 4, 8):
+            extra["config4"] = BC.config4(torch, dist, _ops, world, rank, barrier, max_over_ranks, probe_all, bf16_peak,
+                                          nq=args.c4_queries)
+        extra["kde_sharded"] = BC.kde_sharded(torch, dist, _ops, sharding, world, rank, barrier, max_over_ranks,
+                                              probe_all, bf16_peak)
+        if world == 1:
+            extra["config3"] = BC.config3(torch, R, _ops, hbm_peak, probe_all, bf16_peak, n_boxes=args.c3_boxes)
+            extra["config5"] = BC.config5(torch, R, _ops, md, hbm_peak, probe_all, bf16_peak)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -362,10 +423,7 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "LaREM (MDLatentSpace) scoring, d=256 after PCA, fit on 50k train latents "
-                                   "(BASELINE configs[1] bank size; configs[0] scorer)",
-                       "rows_per_gpu": n_rows, "d": D_LATENT, "input_bytes_per_gpu": n_rows * D_LATENT * 4,
-                       "l2_policy": "inputs (4.3 GB) larger than L2 (126 MB)", "parallelism": f"rows x{world}"},
+            "config": _config(n_rows, world),
             "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "cpu_baseline": cpu_baseline, "extra": extra,
         }
@@ -374,7 +432,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def _extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak):
+def _extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak, tf32_probe=None, bf16_peak=1630.7):
     """Secondary numbers on rank 0: kNN (config 2) and the entropy kernel (config 1 shape)."""
     out = {}
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -406,6 +464,7 @@ def _extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak):
     full = _ops.knn_search(q, kb, 50)
     out["knn_config2"] = {"queries_per_s": 10_000 / (ms * 1e-3), "ms": ms, "bank": [50_000, 512], "k": 50,
                           "distance_tflops": fl / (ms * 1e-3) / 1e12,
+                          "roofline": _tensor_roofline(fl, ms, tf32_probe, bf16_peak),
                           "exhaustive_rows": full["exhaustive_rows"]}
     # entropy: 16 MC samples x 512 dims, 60k items = 1.97 GB
     n_items, n_mc, D = 60_000, 16, 512
@@ -455,7 +514,18 @@ def _extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak):
     out["pca_512_256"] = {"embeddings_per_s": 2_000_000 / (ms * 1e-3), "ms": ms,
                           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak,
                                        "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak},
-                          "fp32_tflops": 2.0 * 2_000_000 * 512 * 256 / (ms * 1e-3) / 1e12}
+                          "fp32_tflops": 2.0 * 2_000_000 * 512 * 256 / (ms * 1e-3) / 1e12,
+                          "tensor_roofline": _tensor_roofline(2.0 * 2_000_000 * 512 * 256, ms, tf32_probe, bf16_peak)}
+    # entropy at the reference's DEFAULT mcd_samples_nro = 32 (evaluation/entropy.py:41), D = 512
+    n_items, n_mc = 30_000, 32
+    z = torch.randn(n_items, 1, D, generator=g, device=dev) + 0.1 * torch.randn(n_items, n_mc, D, generator=g, device=dev)
+    z = z.reshape(n_items * n_mc, D).contiguous()
+    ms = _time_op(torch, lambda: _ops.mcd_entropy(z, n_mc))
+    alg = n_items * (n_mc * D * 4 + D * 8 + 8)
+    out["entropy_n32"] = {"items_per_s": n_items / (ms * 1e-3), "ms": ms, "n_mc": n_mc, "D": D,
+                          "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                       "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}}
+    del z
     return out
 
 
@@ -495,7 +565,7 @@ def _tf32_probe(torch, _lib):
     return best
 
 
-def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak):
+def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak, tf32_probe=None):
     """The remaining rows of SURVEY 8(a), device-resident, each against the roofline SURVEY 8(d)
     names for it: logit scores / ReAct / ASH (HBM), ViM / class-conditional Mahalanobis / DDU / KDE
     (contractions; FP32-equivalent TFLOP/s against bf16/2/3 for the tensor-core ones)."""
@@ -521,6 +591,18 @@ def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak):
     out["react_512"] = {"embeddings_per_s": n / (ms * 1e-3), "ms": ms, "roofline": hbm(n * (d * 4 + 4), ms)}
     ms = _time_op(torch, lambda: _ops.ash_linear_lse(X, W, b, 77))
     out["ash_512"] = {"embeddings_per_s": n / (ms * 1e-3), "ms": ms, "roofline": hbm(n * (d * 4 + 4), ms)}
+    # (a10) the same head at ImageNet size: C = 1000, d = 768 (256-column panels, online log-sum-exp across them)
+    nI, dI, CI = 500_000, 768, 1000
+    XI = torch.relu(torch.randn(nI, dI, generator=g, device=dev))
+    WI = 0.05 * torch.randn(CI, dI, generator=g, device=dev)
+    bI = torch.randn(CI, generator=g, device=dev)
+    plI = _ops.linear_planes(WI)
+    ms = _time_op(torch, lambda: _ops.clip_linear_lse(XI, WI, bI, clip=1.0, planes=plI), reps=3)
+    out["react_768_c1000"] = {"embeddings_per_s": nI / (ms * 1e-3), "ms": ms,
+                              "roofline": _tensor_roofline(2.0 * nI * dI * CI, ms, tf32_probe, bf16_peak)}
+    ms = _time_op(torch, lambda: _ops.ash_linear_lse(XI, WI, bI, 115, planes=plI), reps=3)
+    out["ash_768_c1000"] = {"embeddings_per_s": nI / (ms * 1e-3), "ms": ms, "note": "prune kernel + wide head"}
+    del XI, WI, bI, plI
     # (a7) ViM: d = 512, residual space 256, C = 10 logits
     NS = np.linalg.qr(rng.randn(d, d))[0][:, :256]
     vst = _ops.vim_prepare(rng.randn(d) * 0.1, NS, 1.7)
@@ -528,7 +610,7 @@ def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak):
     ms = _time_op(torch, lambda: _ops.vim_score(X, Lg, vst))
     fl = n * (2.0 * d * 256 + 3 * C)
     out["vim_512"] = {"embeddings_per_s": n / (ms * 1e-3), "ms": ms, "fp32_equiv_tflops": fl / (ms * 1e-3) / 1e12,
-                      "tensor_frac_of_bf16_over_6": fl / (ms * 1e-3) / 1e12 / (bf16_peak / 6.0), "roofline": hbm(n * (d + C) * 4, ms)}
+                      "tensor_roofline": _tensor_roofline(fl, ms, tf32_probe, bf16_peak), "roofline": hbm(n * (d + C) * 4, ms)}
     del Lg
     # (a6) class-conditional Mahalanobis: d = 512, C = 10 (FP32 SIMT contraction)
     A = rng.randn(d, d)
@@ -537,7 +619,8 @@ def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak):
     n6 = 500_000
     ms = _time_op(torch, lambda: _ops.classcond_score(X[:n6], cst))
     fl = n6 * (2.0 * d * cst.r + 3.0 * cst.r * C)
-    out["mahalanobis_512_c10"] = {"embeddings_per_s": n6 / (ms * 1e-3), "ms": ms, "fp32_tflops": fl / (ms * 1e-3) / 1e12}
+    out["mahalanobis_512_c10"] = {"embeddings_per_s": n6 / (ms * 1e-3), "ms": ms, "fp32_tflops": fl / (ms * 1e-3) / 1e12,
+                                  "roofline": _tensor_roofline(fl, ms, tf32_probe, bf16_peak)}
     # (a9) DDU / GMM: C = 10 whitening contractions of 512 x 512
     mus = rng.randn(C, d)
     Ls = np.stack([np.linalg.cholesky(prec) for _ in range(C)])
@@ -545,7 +628,8 @@ def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak):
     n9 = 200_000
     ms = _time_op(torch, lambda: _ops.gmm_lse(X[:n9], gst))
     fl = n9 * C * 2.0 * d * d
-    out["ddu_512_c10"] = {"embeddings_per_s": n9 / (ms * 1e-3), "ms": ms, "fp32_tflops": fl / (ms * 1e-3) / 1e12}
+    out["ddu_512_c10"] = {"embeddings_per_s": n9 / (ms * 1e-3), "ms": ms, "fp32_tflops": fl / (ms * 1e-3) / 1e12,
+                          "roofline": _tensor_roofline(fl, ms, tf32_probe, bf16_peak)}
     del X
     # (a4) LaRED KDE: 50k x 256 bank, 100k queries
     bank = 0.5 + torch.randn(50_000, 256, generator=g, device=dev)
@@ -554,7 +638,7 @@ def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak):
     ms = _time_op(torch, lambda: _ops.kde_score(q, kb), reps=3)
     fl = 2.0 * 100_000 * 50_000 * 256
     out["kde_50k_256"] = {"queries_per_s": 100_000 / (ms * 1e-3), "ms": ms, "fp32_equiv_tflops": fl / (ms * 1e-3) / 1e12,
-                          "tensor_frac_of_bf16_over_6": fl / (ms * 1e-3) / 1e12 / (bf16_peak / 6.0)}
+                          "roofline": _tensor_roofline(fl, ms, tf32_probe, bf16_peak)}
     # (f1) OoD metrics: AUROC + FPR@95 + AUPR of 1e7 InD vs 1e7 OoD float32 scores (radix sort + fused scan)
     nm = 10_000_000
     si = torch.sigmoid(0.5 + torch.randn(nm, generator=g, device=dev))
@@ -597,6 +681,7 @@ def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak):
     ms_st = _time_op(torch, lambda: _ops.md_score(_ops.pca_transform(xr, pst), mst))
     out["pca_larem_fused_512_256"] = {"embeddings_per_s": 2_000_000 / (ms * 1e-3), "ms": ms, "staged_two_kernels_ms": ms_st,
                                       "fp32_equiv_tflops": 2_000_000 * 262_656 / (ms * 1e-3) / 1e12,
+                                      "tensor_roofline": _tensor_roofline(2_000_000 * 262_656.0, ms, tf32_probe, bf16_peak),
                                       "roofline": hbm(2_000_000 * 2056, ms)}
     del xr
     # (f3) online LaREx chain on one hooked map (sampler -> entropy -> folded PCA + LaREM -> score on the host),
@@ -700,67 +785,6 @@ def _extra_sweep_config2(R):
     return out
 
 
-def _extra_sharded_knn(args, torch, dist, _ops, world, rank, barrier, max_over_ranks):
-    """Bank sharded by contiguous row ranges over the ranks, queries replicated, partial top-k
-    all-gathered over NCCL and merged."""
-    dev = torch.device("cuda", torch.cuda.current_device())
-    nb_rank, d, nq, k = args.knn_shard_rows, 768, 4096, 50
-    g = torch.Generator(device=dev).manual_seed(100 + rank)
-    bank = _ops.normalize_rows(torch.randn(nb_rank, d, generator=g, device=dev))
-    gq = torch.Generator(device=dev).manual_seed(99)
-    q = _ops.normalize_rows(torch.randn(nq, d, generator=gq, device=dev))
-    kb = _ops.knn_bank(bank, idx_offset=rank * nb_rank)
-    out = {}
-
-    def step():
-        r = _ops.knn_search(q, kb, k, want_f64=True, want_dist=False, check_status=False)
-        if world == 1:
-            gd, gi = r["dist64"].unsqueeze(0), r["idx"].unsqueeze(0)
-        else:
-            gd = torch.empty((world, nq, k), dtype=torch.float64, device=dev)
-            gi = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(gd, r["dist64"])
-            dist.all_gather_into_tensor(gi, r["idx"])
-        out["m"] = _ops.topk_merge(gd, gi)
-
-    step()
-    barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    reps = 2
-    for _ in range(reps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = max_over_ranks(e0.elapsed_time(e1) / reps)
-    res = {"knn_sharded": {"queries_per_s": nq / (ms * 1e-3), "ms": ms, "bank_rows_total": nb_rank * world,
-                           "d": d, "k": k, "scaling": "weak (bank grows with ranks)",
-                           "distance_tflops_per_gpu": 2.0 * nq * nb_rank * d / (ms * 1e-3) / 1e12}}
-    if world == 1 and torch.cuda.mem_get_info()[0] > 130e9:
-        # strong-scaling reference point: the whole BASELINE configs[3] bank (8 shards = 10M x 768, 30.7 GB + its
-        # TF32 planes) on ONE GPU, same shards (seeds) as the 8-rank run, to set beside that run's time
-        del kb, bank
-        shards = 8
-        full = torch.empty((shards * nb_rank, d), dtype=torch.float32, device=dev)
-        for r in range(shards):
-            gr = torch.Generator(device=dev).manual_seed(100 + r)
-            full[r * nb_rank:(r + 1) * nb_rank] = _ops.normalize_rows(torch.randn(nb_rank, d, generator=gr, device=dev))
-        kbf = _ops.knn_bank(full)
-        _ops.knn_search(q, kbf, k, want_f64=True, want_dist=False, check_status=False)
-        torch.cuda.synchronize()
-        e0.record()
-        rr = _ops.knn_search(q, kbf, k, want_f64=True, want_dist=False, check_status=False)
-        e1.record()
-        torch.cuda.synchronize()
-        msf = e0.elapsed_time(e1)
-        res["knn_full_bank_1gpu"] = {"ms": msf, "queries_per_s": nq / (msf * 1e-3), "bank_rows_total": shards * nb_rank,
-                                     "distance_tflops": 2.0 * nq * shards * nb_rank * d / (msf * 1e-3) / 1e12,
-                                     "note": "same 8 shards as the 8-rank sharded run; compare with knn_sharded.ms at --gpus 8"}
-        del kbf, full
-    return res
-
-
 def _cpu_larem(md, seconds=8.0):
     """The reference's CPU path for the same scorer (postprocessors.py:241-242: N x N product),
     restated in oracle/oracle_np.py, on a bounded sample: 10k-row calls (800 MB temporary each,
@@ -781,6 +805,14 @@ def _cpu_larem(md, seconds=8.0):
             "sample": f"{n} calls x 10,000 rows x d=256 of MDLatentSpace.postprocess (N x N form), {dt:.1f} s"}
 
 
+def _cpu_entropy_item(args):
+    """One item of get_dl_h_z(parallel_run=True) (evaluation/entropy.py:85-91: process_map over the items)."""
+    from oracle import oracle_np as O
+
+    z, n_mc = args
+    return O.get_dl_h_z_faithful(z, n_mc)[1]
+
+
 def _cpu_other_rows():
     """The reference's CPU path for the other measured rows (oracle ports with the reference's loop
     structure), on bounded samples of the same shapes, all host threads: entropy (one estimator call
@@ -797,6 +829,22 @@ def _cpu_other_rows():
     O.get_dl_h_z_faithful(z, n_mc)
     dt = time.perf_counter() - t0
     out["entropy_config1"] = {"items_per_s": n_items / dt, "sample": f"{n_items} items x 16 x 512, {dt:.1f} s (single-threaded Python loops upstream)"}
+    # the reference's parallel_run=True: a process pool over the items (chunksize 1), all host cores
+    import multiprocessing as mp
+
+    cores = os.cpu_count() or 1
+    n_par = 4 * cores
+    zp = (rng.randn(n_par, 1, D) + 0.1 * rng.randn(n_par, n_mc, D)).astype(np.float32)
+    try:
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_cpu_entropy_item, [(zp[i], n_mc) for i in range(cores)], chunksize=1)  # warm the workers
+            t0 = time.perf_counter()
+            pool.map(_cpu_entropy_item, [(zp[i], n_mc) for i in range(n_par)], chunksize=1)
+            dt = time.perf_counter() - t0
+        out["entropy_config1_parallel_run"] = {"items_per_s": n_par / dt, "processes": cores,
+                                               "sample": f"{n_par} items x 16 x 512 over a {cores}-process pool, {dt:.1f} s"}
+    except Exception as e:  # pragma: no cover
+        out["entropy_config1_parallel_run"] = {"error": repr(e)}
     bank = O.normalize_rows_exact(rng.randn(50_000, 512).astype(np.float32))
     q = rng.randn(40, 512).astype(np.float32)
     t0 = time.perf_counter()
@@ -836,11 +884,11 @@ def run_reference(args):
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "LaREM (MDLatentSpace) scoring, d=256 after PCA, fit on 50k train latents "
-                                   "(BASELINE configs[1] bank size; configs[0] scorer)",
-                       "rows_per_step": 10_000, "d": D_LATENT},
+            "config": _config(args.rows, int(os.environ.get("WORLD_SIZE", "1"))),
             "cpu_baseline": {"value": v, "unit": "embeddings/s", "cores": int(threads), "kind": "port",
-                             "sample": "10,000-row calls of the N x N Mahalanobis form (postprocessors.py:241-242)"},
+                             "sample": "each step = one 10,000-row call of MDLatentSpace.postprocess in the reference's N x N "
+                                       "form (postprocessors.py:241-242; 800 MB temporary, the largest call the formulation "
+                                       "affords): a bounded sample of the workload's rows"},
             "e2e": {"value": v, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
 
@@ -858,6 +906,9 @@ def main():
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the configs[1] baseline sweep (host-side fits take ~20 s)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs[2..4] at their stated sizes")
+    ap.add_argument("--c4-queries", type=int, default=50_000)
+    ap.add_argument("--c3-boxes", type=int, default=1_000_000)
     args = ap.parse_args()
     _claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -214,11 +214,13 @@ def _rownorm(xf, n, d, mu, W, planes, r, sign, mode, logits, C, alpha, o64, o32)
                   o64, o32, stream_ptr())
 
 
-def md_score(x, st: MDState, out_dtype=torch.float64) -> torch.Tensor:
-    """LaREM scores of the rows of x.  Host matrices (what `MDLatentSpace.postprocess` receives,
-    evaluation/metrics.py:331-340) stream through the pinned staging ring: the kernel scores chunk k while chunk
-    k + 1 crosses PCIe and chunk k + 2 is copied into its slot."""
-    out = _empty((x.shape[0],), out_dtype)
+def md_score(x, st: MDState, out_dtype=torch.float64, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LaREM scores of the rows of x (into `out` when given: a contiguous [N] device tensor of `out_dtype`).  Host
+    matrices (what `MDLatentSpace.postprocess` receives, evaluation/metrics.py:331-340) stream through the pinned
+    staging ring: the kernel scores chunk k while chunk k + 1 crosses PCIe and chunk k + 2 is copied into its slot."""
+    if out is None:
+        out = _empty((x.shape[0],), out_dtype)
+    assert out.dtype == out_dtype and out.is_contiguous() and out.shape[0] == x.shape[0]
     esz = out.element_size()
 
     def run(xc, lo, hi):
