@@ -212,7 +212,7 @@ def config3(torch, R, _ops, hbm_peak, tf32_probe, bf16_peak, n_boxes=1_000_000, 
 
     ms_e = _events(torch, ent, reps=2, warm=1)
     h_mvn, h_z = hold["e"]
-    sel = torch.linspace(0, n_boxes - 1, 64, device=dev).long()
+    sel = torch.linspace(0, n_boxes - 1, 64, device=dev, dtype=torch.float64).long()
     zs = torch.stack([z[i * n_mc:(i + 1) * n_mc] for i in sel.tolist()])
     rm, rz = ref_entropy(torch, zs)
     par_e = max(_rel(torch, h_z[sel], rz), _rel(torch, h_mvn[sel], rm))
@@ -301,7 +301,7 @@ def config5(torch, R, _ops, md, hbm_peak, tf32_probe, bf16_peak, n_pix=64 * 512 
             _ops.md_score(X[c * per:(c + 1) * per], st, torch.float64, out=out[c * per:(c + 1) * per])
 
     ms = _events(torch, run, reps=3, warm=1)
-    sel = torch.linspace(0, n_pix - 1, 4096, device=dev).long()
+    sel = torch.linspace(0, n_pix - 1, 4096, device=dev, dtype=torch.float64).long()
     mu = torch.from_numpy(np.asarray(md.feats_mean, np.float64).reshape(-1)).to(dev)
     P = torch.from_numpy(np.asarray(md.precision, np.float64)).to(dev)
     df = X[sel].double() - mu
@@ -349,7 +349,7 @@ def kde_sharded(torch, dist, _ops, sharding, world, rank, barrier, max_over_rank
     step()
     barrier()
     ms = max_over_ranks(_events(torch, step, reps=2, warm=0))
-    sel = torch.linspace(0, nq - 1, 128, device=dev).long()
+    sel = torch.linspace(0, nq - 1, 128, device=dev, dtype=torch.float64).long()
     d2 = torch.cdist(q[sel].double(), bank.double()).pow(2)
     ref = torch.logsumexp(-0.5 * d2, dim=1) - math.log(nb) - 0.5 * d * math.log(2.0 * math.pi)
     flop = 2.0 * nq * nb * d

@@ -120,6 +120,105 @@ def baselines_case(ref, seed, n_train, n_test, d, C, k):
     return out
 
 
+def flip_case(ref, seed, n_train, n_test, d, C, k):
+    """Every OodPostprocessor with flip_sign=True: scores and the threshold setup() derives (KNN.setup flips the
+    already flipped validation scores a second time, postprocessors.py:852-854; ViM.postprocess never flips,
+    :1082-1112; ASH thresholds on the train features, :1185)."""
+    rng = np.random.RandomState(seed)
+    centers = rng.randn(C, d)
+    ytr = rng.randint(0, C, n_train)
+    mk_x = lambda y, n: (np.maximum(centers[y] + rng.randn(n, d), 0) + 0.05 * rng.rand(n, d)).astype(np.float32)  # noqa: E731
+    train = mk_x(ytr, n_train)
+    yva = rng.randint(0, C, n_test)
+    valid = mk_x(yva, n_test)
+    ood = (np.maximum(1.5 * rng.randn(n_test, d), 0) + 0.05 * rng.rand(n_test, d)).astype(np.float32)
+    W = (0.2 * rng.randn(C, d)).astype(np.float32)
+    b = rng.randn(C).astype(np.float32)
+    lg = lambda x: (x @ W.T + b).astype(np.float32)  # noqa: E731
+    out = dict(train=train, train_labels=ytr, valid=valid, ood=ood, W=W, b=b, train_logits=lg(train),
+               valid_logits=lg(valid), ood_logits=lg(ood), num_classes=C, k=k)
+    fc = {"weight": W, "bias": b}
+    P = ref.pp
+    mk = {
+        "energy": lambda: P.Energy(flip_sign=True),
+        "msp": lambda: P.MSP(flip_sign=True),
+        "gen": lambda: P.GEN(flip_sign=True, gamma=0.1, num_classes=C),
+        "ddu": lambda: P.DDU(flip_sign=True, num_classes=C),
+        "knn": lambda: P.KNN(flip_sign=True, k_neighbors=k),
+        "mahalanobis": lambda: P.Mahalanobis(flip_sign=True, num_classes=C),
+        "vim": lambda: P.ViM(flip_sign=True),
+        "ash": lambda: P.ASH(flip_sign=True, ash_percentile=85),
+        "react": lambda: P.ReAct(flip_sign=True, react_percentile=90),
+        "dice": lambda: P.DICE(flip_sign=True, dice_percentile=90, num_classes=C),
+        "dice_react": lambda: P.DICEReAct(flip_sign=True, dice_percentile=90, react_percentile=90, num_classes=C),
+    }
+    for name, ctor in mk.items():
+        p = ctor()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if name in ("energy", "msp", "gen"):
+                p.setup(out["train_logits"])
+                o = p.postprocess(out["ood_logits"])
+            else:
+                p.setup(train, valid_feats=valid, train_labels=ytr, train_logits=out["train_logits"],
+                        valid_logits=out["valid_logits"], final_linear_layer_params=fc)
+                o = p.postprocess(ood, logits=out["ood_logits"])
+        out[f"{name}_ood"] = np.asarray(o)
+        out[f"{name}_threshold"] = np.float64(p.threshold)
+    return out
+
+
+def wide_case(ref, seed):
+    """Shapes beyond the CIFAR-10 defaults: a 100-class head (ReAct / DICE / DICE+ReAct / ASH / Energy / MSP /
+    GEN with M < C / Mahalanobis), kNN with k = 300, get_dl_h_z with 40 MC samples."""
+    rng = np.random.RandomState(seed)
+    C, d, n_train, n_test = 100, 64, 1200, 96
+    centers = rng.randn(C, d)
+    ytr = rng.randint(0, C, n_train)
+    ytr[:C] = np.arange(C)  # every class present
+    mk_x = lambda y, n: (np.maximum(centers[y] + rng.randn(n, d), 0) + 0.05 * rng.rand(n, d)).astype(np.float32)  # noqa: E731
+    train, valid = mk_x(ytr, n_train), mk_x(rng.randint(0, C, n_test), n_test)
+    ood = (np.maximum(1.5 * rng.randn(n_test, d), 0) + 0.05 * rng.rand(n_test, d)).astype(np.float32)
+    W = (0.2 * rng.randn(C, d)).astype(np.float32)
+    b = rng.randn(C).astype(np.float32)
+    lg = lambda x: (x @ W.T + b).astype(np.float32)  # noqa: E731
+    out = dict(train=train, train_labels=ytr, valid=valid, ood=ood, W=W, b=b, train_logits=lg(train),
+               valid_logits=lg(valid), ood_logits=lg(ood), num_classes=C, gen_M=10, k=300)
+    fc = {"weight": W, "bias": b}
+    P = ref.pp
+    mk = {
+        "energy": lambda: P.Energy(flip_sign=False),
+        "msp": lambda: P.MSP(flip_sign=False),
+        "gen": lambda: P.GEN(flip_sign=False, gamma=0.1, num_classes=10),
+        "knn": lambda: P.KNN(flip_sign=False, k_neighbors=300),
+        "mahalanobis": lambda: P.Mahalanobis(flip_sign=False, num_classes=C),
+        "ash": lambda: P.ASH(flip_sign=False, ash_percentile=85),
+        "react": lambda: P.ReAct(flip_sign=False, react_percentile=90),
+        "dice": lambda: P.DICE(flip_sign=False, dice_percentile=90, num_classes=C),
+        "dice_react": lambda: P.DICEReAct(flip_sign=False, dice_percentile=90, react_percentile=90, num_classes=C),
+    }
+    for name, ctor in mk.items():
+        p = ctor()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if name in ("energy", "msp", "gen"):
+                p.setup(out["train_logits"])
+                o = p.postprocess(out["ood_logits"])
+            else:
+                p.setup(train, valid_feats=valid, train_labels=ytr, train_logits=out["train_logits"],
+                        valid_logits=out["valid_logits"], final_linear_layer_params=fc)
+                o = p.postprocess(ood, logits=out["ood_logits"])
+        out[f"{name}_ood"] = np.asarray(o)
+        out[f"{name}_threshold"] = np.float64(p.threshold)
+    n_mc, n_items, D = 40, 5, 21
+    z = (rng.randn(n_items, 1, D) + 0.1 * rng.randn(n_items, n_mc, D)).astype(np.float32)
+    z[rng.rand(n_items, n_mc, D) < 0.4] = 0.0
+    z = z.reshape(n_items * n_mc, D)
+    h_mvn, h_z = ref.entropy.get_dl_h_z(z, n_mc, parallel_run=False)
+    out["n40_z"], out["n40_n_mc"], out["n40_h_mvn"], out["n40_h_z"] = z, n_mc, h_mvn, h_z
+    return out
+
+
 def entropy_case(ref, seed):
     rng = np.random.RandomState(seed)
     out = {}
@@ -175,6 +274,8 @@ def main():
                         **baselines_case(ref, 21, 900, 128, 32, 5, 10))
     np.savez_compressed(os.path.join(OUT, "entropy.npz"), **entropy_case(ref, 31))
     np.savez_compressed(os.path.join(OUT, "pca.npz"), **pca_case(ref, 1))
+    np.savez_compressed(os.path.join(OUT, "baselines_flip.npz"), **flip_case(ref, 22, 700, 96, 32, 5, 10))
+    np.savez_compressed(os.path.join(OUT, "wide_shapes.npz"), **wide_case(ref, 23))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -404,7 +404,9 @@ class KNN(OodPostprocessor):
         bank = _ops.normalize_rows(ind_train_data)
         self.index = FlatL2Index(ind_train_data.shape[1])
         self.index.add(bank)
-        ind_scores = self.flip_sign_fn(_knn_scores(self.index, kwargs["valid_feats"], self.k_neighbors))
+        # like the reference (postprocessors.py:852-854): postprocess() already applies flip_sign_fn and setup flips
+        # the result once more, so with flip_sign=True the threshold comes from the UN-flipped validation scores
+        ind_scores = self.flip_sign_fn(self.postprocess(kwargs["valid_feats"]))
         self.set_threshold(ind_scores)
 
     def postprocess(self, test_data: np.ndarray, **kwargs) -> np.ndarray:

@@ -291,3 +291,59 @@ def test_auroc_fpr95_identity_at_1e6_scores(R):
     assert abs(ml["auroc"] - auroc) < 1e-6, (ml["auroc"], auroc)
     assert abs(ml["fpr_95"] - fpr95) < 1e-6, (ml["fpr_95"], fpr95)
     assert abs(ml["aupr"] - aupr) < 1e-6, (ml["aupr"], aupr)
+
+
+def _ood_ctor(I, C, k, flip, gen_M=None):
+    return {
+        "energy": lambda: I.Energy(flip_sign=flip),
+        "msp": lambda: I.MSP(flip_sign=flip),
+        "gen": lambda: I.GEN(flip_sign=flip, gamma=0.1, num_classes=gen_M or C),
+        "ddu": lambda: I.DDU(flip_sign=flip, num_classes=C),
+        "knn": lambda: I.KNN(flip_sign=flip, k_neighbors=k),
+        "mahalanobis": lambda: I.Mahalanobis(flip_sign=flip, num_classes=C),
+        "vim": lambda: I.ViM(flip_sign=flip),
+        "ash": lambda: I.ASH(flip_sign=flip, ash_percentile=85),
+        "react": lambda: I.ReAct(flip_sign=flip, react_percentile=90),
+        "dice": lambda: I.DICE(flip_sign=flip, dice_percentile=90, num_classes=C),
+        "dice_react": lambda: I.DICEReAct(flip_sign=flip, dice_percentile=90, react_percentile=90, num_classes=C),
+    }
+
+
+def _run_fixture(R, f, names, flip, gen_M=None):
+    import warnings
+
+    C, k = int(f["num_classes"]), int(f["k"])
+    fc = {"weight": f["W"], "bias": f["b"]}
+    mk = _ood_ctor(R.inference, C, k, flip, gen_M)
+    for name in names:
+        p = mk[name]()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            if name in ("energy", "msp", "gen"):
+                p.setup(f["train_logits"])
+                o = p.postprocess(f["ood_logits"])
+            else:
+                p.setup(f["train"], valid_feats=f["valid"], train_labels=f["train_labels"], train_logits=f["train_logits"],
+                        valid_logits=f["valid_logits"], final_linear_layer_params=fc)
+                o = p.postprocess(f["ood"], logits=f["ood_logits"])
+        ref = f[f"{name}_ood"]
+        assert o.dtype == ref.dtype, (name, o.dtype, ref.dtype)
+        assert rel_err(o, ref) < RTOL, (name, rel_err(o, ref))
+        thr = float(f[f"{name}_threshold"])
+        assert abs(p.threshold - thr) < 1e-4 * max(1.0, abs(thr)), (name, p.threshold, thr)
+
+
+def test_fixture_flip_sign_all_postprocessors(R, golden):
+    """tests/golden/baselines_flip.npz (unmodified reference, flip_sign=True everywhere): scores AND thresholds,
+    including KNN.setup's double flip, ViM.postprocess's missing flip and ASH's train-feature threshold."""
+    _run_fixture(R, golden("baselines_flip"),
+                 ("energy", "msp", "gen", "ddu", "knn", "mahalanobis", "vim", "ash", "react", "dice", "dice_react"), True)
+
+
+def test_fixture_wide_shapes(R, golden):
+    """tests/golden/wide_shapes.npz (unmodified reference): 100-class head, GEN top-10 of 100, k = 300, 40 samples."""
+    w = golden("wide_shapes")
+    _run_fixture(R, w, ("energy", "msp", "gen", "knn", "mahalanobis", "ash", "react", "dice", "dice_react"), False,
+                 gen_M=int(w["gen_M"]))
+    hm, hz = R.evaluation.get_dl_h_z(w["n40_z"], int(w["n40_n_mc"]))
+    assert rel_err(hz, w["n40_h_z"]) < RTOL and rel_err(hm, w["n40_h_mvn"]) < RTOL

@@ -223,3 +223,45 @@ def test_ash_literal_scatter_vs_intended_rule():
     s_lit = O.logsumexp(lit @ W.T + b, axis=1)
     s_itd = O.logsumexp(itd @ W.T + b, axis=1)
     assert np.array_equal(s_lit[unperm], s_itd[unperm])
+
+
+def test_fixture_flip_sign_and_wide_shapes(golden):
+    """flip_sign=True through every OodPostprocessor (the reference's setup quirks: KNN flips the validation scores
+    twice, ViM never flips its scores, ASH thresholds on the train features) and the shapes beyond the CIFAR-10
+    defaults (100 classes, GEN with M < C, k = 300, 40 MC samples), all produced by the unmodified reference."""
+    f = golden("baselines_flip")
+    C, k, W, bias = int(f["num_classes"]), int(f["k"]), f["W"], f["b"]
+    x, lg = f["ood"], f["ood_logits"]
+    assert rel_err(-O.energy_score(lg), f["energy_ood"]) < 1e-7
+    assert rel_err(-O.msp_score(lg), f["msp_ood"]) < 1e-7
+    assert rel_err(-O.gen_score(lg, 0.1, C), f["gen_ood"]) < 1e-7
+    bn = O.normalize_rows_exact(f["train"])
+    assert rel_err(-O.knn_score(x, bn, k)[0], f["knn_ood"]) < 1e-6
+    # KNN.setup: threshold from flip(flip(valid scores)) = the un-flipped scores
+    assert abs(O.method_threshold(O.knn_score(f["valid"], bn, k)[0]) - float(f["knn_threshold"])) < 1e-6
+    u, DIM, NS, alpha = O.vim_fit(f["train"], f["train_logits"], W, bias)
+    assert rel_err(O.vim_score(x, lg, u, NS, alpha), f["vim_ood"]) < 1e-6  # no flip in ViM.postprocess
+    assert abs(O.method_threshold(-O.vim_score(f["valid"], f["valid_logits"], u, NS, alpha)) - float(f["vim_threshold"])) < 1e-5
+    assert rel_err(-O.ash_score(x, W, bias, 85), f["ash_ood"]) < 1e-6
+    assert abs(O.method_threshold(-O.ash_score(f["train"], W, bias, 85)) - float(f["ash_threshold"])) < 1e-5
+    thr = O.react_threshold(f["train"], 90)
+    assert rel_err(-O.react_score(x, W, bias, thr), f["react_ood"]) < 1e-6
+    cm, P = O.mahalanobis_fit(f["train"], f["train_labels"], C)
+    assert rel_err(-O.mahalanobis_score(x, cm, P, C), f["mahalanobis_ood"]) < 1e-10
+    w = golden("wide_shapes")
+    C, W, bias, x, lg = int(w["num_classes"]), w["W"], w["b"], w["ood"], w["ood_logits"]
+    assert rel_err(O.gen_score(lg, 0.1, int(w["gen_M"])), w["gen_ood"]) < 1e-7
+    assert rel_err(O.energy_score(lg), w["energy_ood"]) < 1e-7
+    bn = O.normalize_rows_exact(w["train"])
+    assert rel_err(O.knn_score(x, bn, int(w["k"]))[0], w["knn_ood"]) < 1e-6
+    thr = O.react_threshold(w["train"], 90)
+    assert rel_err(O.react_score(x, W, bias, thr), w["react_ood"]) < 1e-6
+    mw, _ = O.dice_masked_weight(w["train"], W, 90)
+    assert rel_err(O.dice_score(x, mw, bias), w["dice_ood"]) < 1e-6
+    assert rel_err(O.dice_score(x, mw, bias, clip=thr), w["dice_react_ood"]) < 1e-6
+    assert rel_err(O.ash_score(x, W, bias, 85), w["ash_ood"]) < 1e-6
+    assert rel_err(O.ash_score_intended(x, W, bias, 85), w["ash_ood"]) < 1e-6  # d = 64: the literal scatter is not permuted
+    cm, P = O.mahalanobis_fit(w["train"], w["train_labels"], C)
+    assert rel_err(O.mahalanobis_score(x, cm, P, C), w["mahalanobis_ood"]) < 1e-10
+    hm, hz = O.get_dl_h_z(w["n40_z"], int(w["n40_n_mc"]))
+    assert np.allclose(hm, w["n40_h_mvn"], atol=1e-9) and np.allclose(hz, w["n40_h_z"], atol=1e-9)
