@@ -324,6 +324,14 @@ int runia_mc_dropblock_mean_f32(const float *x, const uint8_t *seed, int B, int 
                                 int block_size, float *out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Host -> device staging of PAGEABLE host memory (the NumPy arrays the reference's callers hand to postprocess(),
+ * evaluation/metrics.py:322-340): pinned ring + parallel memcpy by a persistent worker pool + one cudaMemcpyAsync
+ * per 4 MiB chunk on `stream`.  Returns once every chunk is enqueued; `src_host` may be reused immediately, the
+ * device data is ready in stream order.  dst_dev is a DEVICE pointer, src_host a HOST pointer.
+ */
+int runia_stage_h2d(void *dst_dev, const void *src_host, int64_t bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Measurement aid (bench.py): TF32 tensor peak of this GPU.  Launches one CTA pair per TPC, each issuing
  * iters x 4 back-to-back tcgen05.mma.cta_group::2.kind::tf32 (256 x 256 x 8) on resident shared-memory tiles;
  * *flop_out (host pointer, nullable) receives the TF32 FLOP the launch issues.  Time it with CUDA events.

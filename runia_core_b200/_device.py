@@ -7,10 +7,9 @@ Host -> device staging.  The reference's callers hand NumPy arrays (pageable mem
 itself: a ring of pinned slots, worker threads that `memcpy` slabs of the source into a slot (NumPy releases the GIL
 for plain copies), one `cudaMemcpyAsync` per slot on a copy stream, so that the CPU copy of chunk k+1, the PCIe
 transfer of chunk k and -- for the row scorers that ask for it -- the kernel on chunk k-1 overlap.  Pinned sources
-skip the CPU copy.  Small arrays (< 1 MiB) take the plain path: the pipeline's fixed cost is not worth it."""
+skip the CPU copy.  Small arrays (< 256 KiB) take the plain path.  The engine itself is native (csrc/stage.cu)."""
 import os
 import threading
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -35,15 +34,15 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
-PIPE_MIN_BYTES = 1 << 20
-PIPE_SLOT_BYTES = int(os.environ.get("RUNIA_B200_PIPE_SLOT_BYTES", 8 << 20))
-PIPE_SLOTS = 4
-PIPE_THREADS = max(1, min(8, (os.cpu_count() or 2) // 2))
+PIPE_MIN_BYTES = 256 << 10                                                    # below this a plain copy is as fast
+PIPE_CHUNK_BYTES = int(os.environ.get("RUNIA_B200_PIPE_CHUNK_BYTES", 32 << 20))  # rows per kernel launch when streaming
 
 
 class HostPipe:
-    """Pinned staging ring of one device (see the module docstring).  One instance per device, serialised by a
-    lock: calls from several host threads queue up rather than interleave their slots."""
+    """Per-device host <-> device staging.  Uploads of pageable memory go through the native staging engine
+    (`runia_stage_h2d`, csrc/stage.cu: pinned ring, parallel memcpy by a worker pool, one cudaMemcpyAsync per 4 MiB);
+    `stream_rows` drives it chunk by chunk on a copy stream so that a row scorer's kernel on chunk k overlaps the
+    transfer of chunk k + 1; results come back through a pinned landing buffer."""
 
     _instances = {}
     _guard = threading.Lock()
@@ -59,75 +58,42 @@ class HostPipe:
     def __init__(self, dev: torch.device):
         self.dev = dev
         self.lock = threading.Lock()
-        self.slots = [torch.empty(PIPE_SLOT_BYTES, dtype=torch.uint8).pin_memory() for _ in range(PIPE_SLOTS)]
-        self.slot_np = [s.numpy() for s in self.slots]
-        self.slot_free = [None] * PIPE_SLOTS  # event: the H2D copy out of the slot has completed
         self.copy_stream = torch.cuda.Stream(dev)
-        self.pool = ThreadPoolExecutor(max_workers=PIPE_THREADS, thread_name_prefix="runia-h2d")
         self.out_slot = None  # pinned landing buffer for results (grown on demand)
 
-    def _fill(self, slot, src_u8, lo, hi):
-        """memcpy src_u8[lo:hi] into the slot, split over the worker threads."""
-        n = hi - lo
-        dst = self.slot_np[slot]
-        if n < (1 << 20) or PIPE_THREADS == 1:
-            np.copyto(dst[:n], src_u8[lo:hi])
-            return
-        cuts = [lo + (n * t) // PIPE_THREADS // 64 * 64 for t in range(PIPE_THREADS)] + [hi]
-        list(self.pool.map(lambda t: np.copyto(dst[cuts[t] - lo:cuts[t + 1] - lo], src_u8[cuts[t]:cuts[t + 1]]),
-                           range(PIPE_THREADS)))
+    @staticmethod
+    def _h2d(dst_ptr: int, src_ptr: int, nbytes: int, stream: torch.cuda.Stream):
+        from . import _lib
 
-    def upload(self, src: np.ndarray, dst: torch.Tensor, row_bytes: int, on_rows=None):
-        """Copies the C-contiguous host array `src` into the device tensor `dst` (same dtype and shape) chunk by
-        chunk.  `on_rows(lo_row, hi_row)`, if given, is called on the caller's current stream after that stream has
-        been made to wait for rows [lo_row, hi_row) -- the kernel of a row scorer on that chunk.  Without `on_rows`
-        the current stream waits for the whole copy before the call returns (the host does not block)."""
-        src_u8 = src.reshape(-1).view(np.uint8)
-        dst_u8 = dst.reshape(-1).view(torch.uint8)
-        total = src_u8.shape[0]
-        rows_per_slot = max(1, PIPE_SLOT_BYTES // row_bytes)
-        if rows_per_slot * row_bytes > PIPE_SLOT_BYTES:  # a single row wider than a slot: byte chunks, no callback
-            rows_per_slot, row_bytes, on_rows = PIPE_SLOT_BYTES, 1, None
-        chunk = rows_per_slot * row_bytes
-        cur = torch.cuda.current_stream(self.dev)
-        with self.lock:
-            self.copy_stream.wait_stream(cur)  # dst may still be in use by earlier work on the caller's stream
-            k = 0
-            for lo in range(0, total, chunk):
-                hi = min(total, lo + chunk)
-                s = k % PIPE_SLOTS
-                if self.slot_free[s] is not None:
-                    self.slot_free[s].synchronize()
-                self._fill(s, src_u8, lo, hi)
-                with torch.cuda.stream(self.copy_stream):
-                    dst_u8[lo:hi].copy_(self.slots[s][: hi - lo], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(self.copy_stream)
-                self.slot_free[s] = ev
-                if on_rows is not None:
-                    cur.wait_event(ev)
-                    on_rows(lo // row_bytes, hi // row_bytes)
-                k += 1
-            if on_rows is None:
-                cur.wait_stream(self.copy_stream)
+        _lib.call("runia_stage_h2d", dst_ptr, src_ptr, nbytes, stream.cuda_stream)
 
-    def upload_pinned(self, src: torch.Tensor, dst: torch.Tensor, row_bytes: int, on_rows):
-        """Pinned host tensor -> device in chunks with the per-chunk callback (no CPU copy needed)."""
-        src_u8 = src.reshape(-1).view(torch.uint8)
-        dst_u8 = dst.reshape(-1).view(torch.uint8)
-        total = src_u8.shape[0]
-        chunk = max(1, PIPE_SLOT_BYTES // row_bytes) * row_bytes
+    def upload(self, src: np.ndarray, dst: torch.Tensor):
+        """C-contiguous host array -> device tensor of the same dtype and shape, on the caller's current stream
+        (ready in stream order; the host returns as soon as the last chunk is enqueued)."""
+        self._h2d(dst.data_ptr(), src.ctypes.data, src.nbytes, torch.cuda.current_stream(self.dev))
+
+    def upload_rows(self, src, dst: torch.Tensor, row_bytes: int, on_rows):
+        """Row-chunked upload on the copy stream; after each chunk the caller's stream waits for it and
+        `on_rows(lo, hi)` enqueues that chunk's kernel.  `src`: C-contiguous ndarray or pinned CPU tensor."""
+        pinned = isinstance(src, torch.Tensor)
+        n_rows = dst.shape[0]
+        rows = max(1, PIPE_CHUNK_BYTES // row_bytes)
         cur = torch.cuda.current_stream(self.dev)
+        src_ptr = src.data_ptr() if pinned else src.ctypes.data
         with self.lock:
-            self.copy_stream.wait_stream(cur)
-            for lo in range(0, total, chunk):
-                hi = min(total, lo + chunk)
-                with torch.cuda.stream(self.copy_stream):
-                    dst_u8[lo:hi].copy_(src_u8[lo:hi], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(self.copy_stream)
+            self.copy_stream.wait_stream(cur)  # dst was allocated on (and may be reused by) the caller's stream
+            for lo in range(0, n_rows, rows):
+                hi = min(n_rows, lo + rows)
+                if pinned:
+                    with torch.cuda.stream(self.copy_stream):
+                        dst[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                else:
+                    self._h2d(dst.data_ptr() + lo * row_bytes, src_ptr + lo * row_bytes, (hi - lo) * row_bytes,
+                              self.copy_stream)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
                 cur.wait_event(ev)
-                on_rows(lo // row_bytes, hi // row_bytes)
+                on_rows(lo, hi)
 
     def download(self, t: torch.Tensor) -> np.ndarray:
         """Device tensor -> fresh NumPy array through the pinned landing buffer (one async copy + one sync)."""
@@ -184,7 +150,7 @@ def to_device(x, dtype=None):
         nbytes = a.nbytes
         if nbytes >= PIPE_MIN_BYTES:
             t = torch.empty(a.shape, dtype=_TORCH_DTYPE[a.dtype.type], device=dev)
-            HostPipe.get(dev).upload(a, t, row_bytes=max(1, nbytes // max(1, a.shape[0])))
+            HostPipe.get(dev).upload(a, t)
         else:
             t = torch.from_numpy(a).to(dev, non_blocking=False)
     if dtype is not None and t.dtype != dtype:
@@ -206,16 +172,11 @@ def stream_rows(x, fn, min_rows: int = 4096):
     if a.ndim != 2 or a.shape[0] < min_rows or (not pinned and a.dtype not in (np.float32, np.float64)):
         return False
     row_bytes = a.shape[1] * (a.element_size() if pinned else a.itemsize)
-    if a.shape[0] * row_bytes < 4 * PIPE_SLOT_BYTES or row_bytes > PIPE_SLOT_BYTES:
+    if a.shape[0] * row_bytes < 2 * PIPE_CHUNK_BYTES:
         return False
     tdt = a.dtype if pinned else (torch.float32 if a.dtype == np.float32 else torch.float64)
     xd = torch.empty(tuple(a.shape), dtype=tdt, device=dev)
-    pipe = HostPipe.get(dev)
-    cb = lambda lo, hi: fn(xd[lo:hi], lo, hi)  # noqa: E731
-    if pinned:
-        pipe.upload_pinned(a, xd, row_bytes, cb)
-    else:
-        pipe.upload(a, xd, row_bytes, cb)
+    HostPipe.get(dev).upload_rows(a, xd, row_bytes, lambda lo, hi: fn(xd[lo:hi], lo, hi))
     return True
 
 

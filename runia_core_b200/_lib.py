@@ -82,6 +82,7 @@ _SIGS = {
     "runia_ash_prune_f32": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     "runia_gen_entropy_f32": (c_int, [_P, c_int64, c_int, c_float, c_int, _P, _P]),
     "runia_linear_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P]),
+    "runia_stage_h2d": (c_int, [_P, _P, c_int64, _P]),
 }
 EXPORTS = tuple(_SIGS)
 

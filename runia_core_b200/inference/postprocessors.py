@@ -94,20 +94,42 @@ class DetectorKDE:
     here `density` is the device-resident bank and scoring is the closed form
     logsumexp_i(-|q-x_i|^2 / 2h^2) - log N - d/2 log(2 pi h^2) in one fused kernel."""
 
-    def __init__(self, train_embeddings, save_path=None, kernel="gaussian", bandwidth=1.0) -> None:
+    def __init__(self, train_embeddings, save_path=None, kernel="gaussian", bandwidth=1.0, bank_group=None,
+                 bank_rows_are_local=False) -> None:
+        """bank_group: torch.distributed process group over which the bank is sharded (every rank keeps a contiguous
+        slice; scoring all-reduces the running (max, sum-exp) pair: sharding.kde_score_sharded)."""
         if kernel != "gaussian":
             raise NotImplementedError("only the Gaussian kernel (the reference's default) is implemented")
         self.kernel = kernel
         self.bandwidth = bandwidth
         self.train_embeddings = train_embeddings
         self.save_path = save_path
+        self._group = bank_group
+        self._local = bank_rows_are_local
         self.density = self.density_fit()
 
     def density_fit(self):
-        center = np.asarray(_np(self.train_embeddings), np.float64).mean(0)
-        return _ops.kde_bank(self.train_embeddings, self.bandwidth, center=center)
+        emb = _np(self.train_embeddings)
+        if self._group is None:
+            center = np.asarray(emb, np.float64).mean(0)
+            return _ops.kde_bank(self.train_embeddings, self.bandwidth, center=center)
+        import torch.distributed as dist
+
+        from .. import sharding
+
+        lo, hi, total = sharding.shard_of_bank(int(emb.shape[0]), self._group, self._local)
+        mine = emb if self._local else emb[lo:hi]
+        # any common centre is valid (it only keeps |q - b| small in float32): the mean of the whole bank
+        acc = to_device(np.asarray(mine, np.float64).sum(0), torch.float64)
+        if dist.get_world_size(self._group) > 1:
+            dist.all_reduce(acc, group=self._group)
+        return _ops.kde_bank(mine, self.bandwidth, center=acc / total, n_total=total)
 
     def get_density_scores(self, test_embeddings):
+        if self._group is not None:
+            from .. import sharding
+
+            return to_host(sharding.kde_score_sharded(test_embeddings, self.density, group=self._group))
         return to_host(_ops.kde_score(test_embeddings, self.density))
 
 
@@ -122,7 +144,8 @@ class KDELatentSpace(Postprocessor):
     def setup(self, ind_train_data: np.ndarray, **kwargs) -> None:
         assert ind_train_data.ndim == 2, "ind_feats must be 2 dimensional"
         if not self._setup_flag:
-            self.detector = DetectorKDE(train_embeddings=ind_train_data)
+            self.detector = DetectorKDE(train_embeddings=ind_train_data, bank_group=kwargs.get("bank_group"),
+                                        bank_rows_are_local=bool(kwargs.get("bank_rows_are_local", False)))
             self._setup_flag = True
         else:
             warnings.warn("KDEPostprocessor already trained")
@@ -151,7 +174,17 @@ class MDLatentSpace(Postprocessor):
         assert ind_train_data.ndim == 2, "ind_feats must be 2 dimensional"
         if not self._setup_flag:
             ind_train_data = _np(ind_train_data)
-            if ind_train_data.dtype == np.float32 and ind_train_data.shape[0] > 0:
+            if kwargs.get("bank_group") is not None:
+                # training rows sharded over the ranks (bank_rows_are_local) or replicated (each rank fits its slice):
+                # per-rank sufficient statistics + one all-reduce of d*d + d doubles (sharding.fit_mean_precision_sharded)
+                from .. import sharding
+
+                group, local = kwargs["bank_group"], bool(kwargs.get("bank_rows_are_local", False))
+                lo, hi, _ = sharding.shard_of_bank(int(ind_train_data.shape[0]), group, local)
+                mine = np.ascontiguousarray(ind_train_data if local else ind_train_data[lo:hi], np.float32)
+                self.feats_mean, _, self.precision = sharding.fit_mean_precision_sharded(mine, None, 1, group=group)
+                self.centered_data = ind_train_data - self.feats_mean
+            elif ind_train_data.dtype == np.float32 and ind_train_data.shape[0] > 0:
                 self.feats_mean, _, self.precision = _device_fit(ind_train_data, None, 1)
                 self.centered_data = ind_train_data - self.feats_mean
             else:  # other dtypes: the reference's own host fit
@@ -225,25 +258,61 @@ class FlatL2Index:
     """Stand-in for `faiss.IndexFlatL2` (the only faiss class the reference uses,
     postprocessors.py:396-397, 850-851): exact squared-L2 search over a device-resident bank."""
 
-    def __init__(self, d: int):
+    def __init__(self, d: int, bank_group=None, idx_offset: int = 0, ntotal: int = None):
+        """bank_group: a torch.distributed process group whose ranks each hold a contiguous slice of the bank
+        (idx_offset = global index of this rank's first row, ntotal = rows of the whole bank); searches then merge
+        the per-rank top-k over NCCL and return the same result on every rank (sharding.knn_search_sharded)."""
         self.d = d
         self.ntotal = 0
         self._bank = None
+        self._group = bank_group
+        self._offset = int(idx_offset)
+        self._ntotal_global = ntotal
 
     def add(self, x):
         t = to_device(x, torch.float32)
         assert t.dim() == 2 and t.shape[1] == self.d
         full = t if self._bank is None else torch.cat([self._bank.bank, t])
-        self._bank = _ops.knn_bank(full.contiguous())
-        self.ntotal = int(full.shape[0])
+        self._bank = _ops.knn_bank(full.contiguous(), idx_offset=self._offset)
+        self.ntotal = int(full.shape[0]) if self._ntotal_global is None else int(self._ntotal_global)
+
+    def _search(self, q, k):
+        if self._group is None:
+            return None
+        from .. import sharding
+
+        return sharding.knn_search_sharded(q, self._bank, k, group=self._group)
 
     def search(self, x, k: int):
         q = to_device(x, torch.float32)
+        merged = self._search(q, k)
+        if merged is not None:
+            return to_host(merged[0]), to_host(merged[1])
         res = _ops.knn_search(q, self._bank, k, check_status=False)
         return to_host(res["dist"]), to_host(res["idx"])
 
     def kth_distance(self, q: torch.Tensor, k: int) -> torch.Tensor:
+        merged = self._search(q, k)
+        if merged is not None:
+            return merged[2]
         return _ops.knn_search(q, self._bank, k, want_idx=False, want_dist=False, check_status=False)["kth"]
+
+
+def _sharded_index(bank_normed: torch.Tensor, d: int, kwargs) -> FlatL2Index:
+    """FlatL2Index over the (already normalised) training rows; with `bank_group=` in the setup kwargs every rank keeps
+    only its slice of the bank (`bank_rows_are_local=True`: the rows handed in ARE this rank's slice)."""
+    group = kwargs.get("bank_group")
+    if group is None:
+        index = FlatL2Index(d)
+        index.add(bank_normed)
+        return index
+    from .. import sharding
+
+    local = bool(kwargs.get("bank_rows_are_local", False))
+    lo, hi, total = sharding.shard_of_bank(int(bank_normed.shape[0]), group, local)
+    index = FlatL2Index(d, bank_group=group, idx_offset=lo, ntotal=total)
+    index.add(bank_normed if local else bank_normed[lo:hi].contiguous())
+    return index
 
 
 def _knn_scores(index: FlatL2Index, test_data, k: int) -> np.ndarray:
@@ -270,8 +339,7 @@ class KNNLatentSpace(Postprocessor):
         if not self._setup_flag:
             bank = _ops.normalize_rows(ind_train_data)
             self.activation_log = to_host(bank)
-            self.index = FlatL2Index(ind_train_data.shape[1])
-            self.index.add(bank)
+            self.index = _sharded_index(bank, ind_train_data.shape[1], kwargs)
             self._setup_flag = True
         else:
             warnings.warn("KNNPostprocessor already trained")
@@ -402,8 +470,7 @@ class KNN(OodPostprocessor):
     def setup(self, ind_train_data: np.ndarray, **kwargs):
         assert "valid_feats" in kwargs, "valid_feats must be provided for KNN setup"
         bank = _ops.normalize_rows(ind_train_data)
-        self.index = FlatL2Index(ind_train_data.shape[1])
-        self.index.add(bank)
+        self.index = _sharded_index(bank, ind_train_data.shape[1], kwargs)
         # like the reference (postprocessors.py:852-854): postprocess() already applies flip_sign_fn and setup flips
         # the result once more, so with flip_sign=True the threshold comes from the UN-flipped validation scores
         ind_scores = self.flip_sign_fn(self.postprocess(kwargs["valid_feats"]))

@@ -42,10 +42,22 @@ def gather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
     return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)])
 
 
+def _all_ok(ok: bool, like: torch.Tensor, group=None) -> bool:
+    """True on every rank iff `ok` on every rank: one MAX all-reduce of a flag, issued BEFORE the data collectives so
+    that a rank-local failure (bad input, out of memory, unsupported shape) makes every rank raise together instead of
+    leaving the others blocked in all_gather / all_reduce."""
+    _, world = _world(group)
+    if world == 1:
+        return ok
+    flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device=like.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    return int(flag.item()) == 0
+
+
 def knn_search_sharded(qn: torch.Tensor, bank_shard, k: int, group=None,
                        search_fn: Optional[Callable] = None, merge_fn: Optional[Callable] = None):
     """qn: replicated normalised queries; bank_shard: this rank's KNNBank (idx_offset = first
-    global row of the shard).  Returns (dist [Nq,k] f32, idx [Nq,k] i64, kth [Nq] f32), identical
+    global row of the shard; may hold zero rows).  Returns (dist [Nq,k] f32, idx [Nq,k] i64, kth [Nq] f32), identical
     on every rank and identical to a single-GPU search over the concatenated bank."""
     if search_fn is None or merge_fn is None:
         from . import _ops
@@ -53,8 +65,22 @@ def knn_search_sharded(qn: torch.Tensor, bank_shard, k: int, group=None,
         search_fn = search_fn or (lambda q, b, kk: (lambda r: (r["dist64"], r["idx"]))(
             _ops.knn_search(q, b, kk, want_f64=True, want_dist=False, check_status=False)))
         merge_fn = merge_fn or _ops.topk_merge
-    d64, idx = search_fn(qn, bank_shard, k)
     rank, world = _world(group)
+    err = None
+    nq = qn.shape[0]
+    try:
+        if bank_shard.bank.shape[0] == 0:  # an empty shard contributes an exhausted list
+            d64 = torch.full((nq, k), float("inf"), dtype=torch.float64, device=qn.device)
+            idx = torch.full((nq, k), -1, dtype=torch.int64, device=qn.device)
+        else:
+            d64, idx = search_fn(qn, bank_shard, k)
+    except Exception as e:  # noqa: BLE001 -- re-raised below on every rank
+        err = e
+        d64 = torch.zeros((nq, k), dtype=torch.float64, device=qn.device)
+        idx = torch.zeros((nq, k), dtype=torch.int64, device=qn.device)
+    if not _all_ok(err is None, qn, group):
+        raise RuntimeError(f"sharded kNN: rank {rank} failed: {err!r}" if err is not None
+                           else "sharded kNN: another rank failed its local search") from err
     if world == 1:
         return merge_fn(d64.unsqueeze(0), idx.unsqueeze(0))
     gd = [torch.empty_like(d64) for _ in range(world)]
@@ -71,8 +97,22 @@ def kde_score_sharded(q, kde_shard, group=None, partial_fn: Optional[Callable] =
         from . import _ops
 
         partial_fn = lambda qq, kb: _ops.kde_score(qq, kb, partial=True)  # noqa: E731
-    m, s = partial_fn(q, kde_shard)
     rank, world = _world(group)
+    err = None
+    try:
+        if kde_shard.bank.shape[0] == 0:
+            dev = kde_shard.bank.device
+            m = torch.full((q.shape[0],), float("-inf"), dtype=torch.float32, device=dev)
+            s = torch.zeros((q.shape[0],), dtype=torch.float32, device=dev)
+        else:
+            m, s = partial_fn(q, kde_shard)
+    except Exception as e:  # noqa: BLE001
+        err = e
+        m = torch.zeros((q.shape[0],), dtype=torch.float32, device=kde_shard.bank.device)
+        s = torch.zeros_like(m)
+    if not _all_ok(err is None, m, group):
+        raise RuntimeError(f"sharded KDE: rank {rank} failed: {err!r}" if err is not None
+                           else "sharded KDE: another rank failed its local pass") from err
     M = m.clone()
     if world > 1:
         dist.all_reduce(M, op=dist.ReduceOp.MAX, group=group)
@@ -132,9 +172,21 @@ def fit_mean_precision_sharded(x_local, labels_local=None, num_classes: int = 1,
 
     from . import _ops
 
-    lm, lc, xf, lab = _ops.class_means(x_local, labels_local, num_classes)
+    n_local = int(x_local.shape[0])
+    if n_local == 0:  # an empty shard contributes zero counts and a zero Gram matrix
+        from ._device import device as _dev
+
+        d = int(x_local.shape[1])
+        lm = torch.full((num_classes, d), float("nan"), dtype=torch.float32, device=_dev())
+        lc = np.zeros(num_classes, np.int64)
+    else:
+        lm, lc, xf, lab = _ops.class_means(x_local, labels_local, num_classes)
     gm, total = combine_class_means(lm, torch.from_numpy(lc), group)
-    G, cs = _ops.centered_gram(xf, lab, gm)
+    if n_local == 0:
+        G = torch.zeros((d, d), dtype=torch.float64, device=lm.device)
+        cs = torch.zeros((d,), dtype=torch.float64, device=lm.device)
+    else:
+        G, cs = _ops.centered_gram(xf, lab, gm)
     _, world = _world(group)
     if world > 1:
         dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
@@ -142,3 +194,23 @@ def fit_mean_precision_sharded(x_local, labels_local=None, num_classes: int = 1,
     n_used = int(total.sum())
     cov = _ops.covariance_from_gram(G, cs, n_used)
     return gm.cpu().numpy(), total.cpu().numpy(), pinvh(cov, check_finite=False)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Bank sharding behind the reference-facing classes (KNNLatentSpace / KNN / KDELatentSpace / MDLatentSpace.setup take
+# `bank_group=`): what the classes call.
+# ------------------------------------------------------------------------------------------------------------------
+def shard_of_bank(n_rows: int, group=None, rows_are_local: bool = False):
+    """(lo, hi, n_total) of this rank's slice of a bank of `n_rows` rows: either the full bank is handed to every rank
+    (replicated input, the drop-in case: each rank keeps rows [lo, hi)) or every rank hands in its own rows
+    (`rows_are_local`: offsets from an all-gather of the local counts)."""
+    rank, world = _world(group)
+    if not rows_are_local:
+        lo, hi = row_shard(n_rows, rank, world)
+        return lo, hi, n_rows
+    if world == 1:
+        return 0, n_rows, n_rows
+    counts = [None] * world
+    dist.all_gather_object(counts, int(n_rows), group=group)
+    lo = sum(counts[:rank])
+    return lo, lo + n_rows, sum(counts)
