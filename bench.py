@@ -684,34 +684,45 @@ def _extra_other_kernels(torch, _ops, hbm_peak, bf16_peak, tf32_probe=None):
                                       "tensor_roofline": _tensor_roofline(2_000_000 * 262_656.0, ms, tf32_probe, bf16_peak),
                                       "roofline": hbm(2_000_000 * 2056, ms)}
     del xr
-    # (f3) online LaREx chain on one hooked map (sampler -> entropy -> folded PCA + LaREM -> score on the host),
-    # the body of LaRExInference.get_score after the model forward; wall clock per image, and the same chain batched
+    # (f3) online LaREx chain on one hooked map (sampler -> entropy -> folded PCA + LaREM -> score on the host): the body
+    # of LaRExInference.get_score after the model forward (`score_latent`), wall clock per image: ONE CUDA graph replay
+    # per image (default) and the same chain launch by launch; and the chain batched over 1024 maps
     import time as _time
+    from sklearn.decomposition import PCA as _PCA
+
     from runia_core_b200.feature_extraction import MCSamplerModule
-    smp = MCSamplerModule(mc_samples=16, block_size=3, drop_prob=0.3).train()
+    from runia_core_b200.inference import LaRExInference, MDLatentSpace
+    pca_o = _PCA(n_components=256, whiten=True)
+    pca_o.mean_, pca_o.components_, pca_o.explained_variance_ = rngf.randn(512), comps, var
+    md_o = MDLatentSpace()
+    md_o.feats_mean, md_o.precision, md_o._setup_flag = 0.01 * rngf.randn(1, 256), Af @ Af.T / 256 + np.eye(256), True
+    inf = LaRExInference(torch.nn.Identity(), md_o, drop_block_prob=0.3, drop_block_size=3, mcd_samples_nro=16,
+                         mcd_sampler=MCSamplerModule, pca_transform=pca_o)
     lat1 = torch.randn(1, 512, 7, 7, generator=g, device=dev)
     latB = torch.randn(1024, 512, 7, 7, generator=g, device=dev)
 
-    def chain(lat):
-        rows = smp.sample_batch(lat)
-        _, hz = _ops.mcd_entropy(rows, 16, k=5, want_joint=False)
-        return _ops.md_score(hz, fst).cpu()
+    def per_image(reps=300):
+        for _ in range(20):
+            inf.score_latent(lat1)
+        torch.cuda.synchronize()
+        t0 = _time.perf_counter()
+        for _ in range(reps):
+            inf.score_latent(lat1)
+        return (_time.perf_counter() - t0) / reps * 1e6
 
-    for _ in range(10):
-        chain(lat1)
-    torch.cuda.synchronize()
-    t0 = _time.perf_counter()
-    for _ in range(200):
-        chain(lat1)
-    us1 = (_time.perf_counter() - t0) / 200 * 1e6
-    chain(latB)
+    us_graph = per_image()
+    inf.use_cuda_graph = False
+    us_plain = per_image()
+    inf.score_latent(latB)
     torch.cuda.synchronize()
     t0 = _time.perf_counter()
     for _ in range(20):
-        chain(latB)
+        inf.score_latent(latB)
     msB = (_time.perf_counter() - t0) / 20 * 1e3
-    out["larex_online_chain"] = {"us_per_image_batch1": us1, "ms_per_1024_images": msB, "images_per_s_batched": 1024 / (msB * 1e-3),
-                                 "note": "wall clock incl. torch.rand seeds on the CPU generator, 16 samples, 512 x 7 x 7 map, score copied to host"}
+    out["larex_online_chain"] = {"us_per_image_batch1": us_graph, "us_per_image_batch1_launch_by_launch": us_plain,
+                                 "ms_per_1024_images": msB, "images_per_s_batched": 1024 / (msB * 1e-3),
+                                 "note": "wall clock from the hooked 512 x 7 x 7 map to the float64 score on the host: CPU-generator "
+                                         "seeds (one torch.rand), 16 samples, sampler + entropy + folded PCA/LaREM as one CUDA graph"}
     del lat1, latB
     # (f2) setup() statistics: class means + float64 Gram matrix of a 50k x 512 bank with 10 classes
     xs = torch.randn(50_000, 512, generator=g, device=dev)

@@ -7,6 +7,8 @@
 
 #include <atomic>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/runia_b200.h"
 
 namespace runia {
@@ -51,6 +53,14 @@ struct PerDeviceFlag {
     return *this;
   }
 };
+
+// NVTX range around every C-ABI entry point (header-only nvtx3: a no-op unless a profiler is attached), so that
+// nsys / ncu --nvtx timelines show the library calls by name.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define RUNIA_NVTX() ::runia::NvtxRange runia_nvtx_range_(__func__)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -688,6 +688,7 @@ using namespace runia;
 
 extern "C" int runia_center_cast(const void *in, int in_is_f64, int64_t N, int d, const double *center,
                                  float *out, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && d > 0, RUNIA_E_BADARG, "center_cast: bad sizes");
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(in && out, RUNIA_E_BADARG, "center_cast: null pointer");
@@ -702,6 +703,7 @@ extern "C" int runia_center_cast(const void *in, int in_is_f64, int64_t N, int d
 }
 
 extern "C" int runia_normalize_rows(const void *in, int in_is_f64, int64_t N, int d, float *out, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && d > 0, RUNIA_E_BADARG, "normalize_rows: bad sizes");
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(in && out, RUNIA_E_BADARG, "normalize_rows: null pointer");
@@ -715,6 +717,7 @@ extern "C" int runia_normalize_rows(const void *in, int in_is_f64, int64_t N, in
 }
 
 extern "C" int runia_row_sqnorm_f32(const float *X, int64_t N, int d, float *out, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && d > 0, RUNIA_E_BADARG, "row_sqnorm: bad sizes");
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(X && out, RUNIA_E_BADARG, "row_sqnorm: null pointer");
@@ -736,6 +739,7 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
                                     int64_t idx_offset, float *out_dist,
                                     double *out_dist_f64, int64_t *out_idx, float *out_kth, int32_t *status,
                                     void *workspace, int64_t workspace_bytes, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(Nq >= 0 && Nb > 0 && d > 0, RUNIA_E_BADARG, "knn_search: bad sizes Nq=%lld Nb=%lld d=%d",
                 (long long)Nq, (long long)Nb, d);
   RUNIA_REQUIRE(k >= 1 && k <= kKnnMaxK, RUNIA_E_UNSUPPORTED, "knn_search: k=%d outside [1, %d]", k, kKnnMaxK);
@@ -809,6 +813,7 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
 
 extern "C" int runia_topk_merge(const double *part_dist, const int64_t *part_idx, int R, int64_t Nq, int k,
                                 float *out_dist, int64_t *out_idx, float *out_kth, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(R >= 1 && R <= 64 && Nq >= 0 && k >= 1, RUNIA_E_BADARG, "topk_merge: bad sizes R=%d k=%d", R, k);
   if (Nq == 0) return RUNIA_OK;
   RUNIA_REQUIRE(part_dist && part_idx, RUNIA_E_BADARG, "topk_merge: null pointer");
@@ -838,6 +843,7 @@ extern "C" int runia_kde_lse_f32(const float *Q, int64_t Nq, const float *B, con
                                  int64_t Nb, int d, double bandwidth,
                                  int64_t Nb_total, double *out_f64, float *out_max, float *out_sum,
                                  void *workspace, int64_t workspace_bytes, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(Nq >= 0 && Nb > 0 && d > 0 && bandwidth > 0 && Nb_total >= Nb, RUNIA_E_BADARG, "kde_lse: bad sizes");
   if (Nq == 0) return RUNIA_OK;
   RUNIA_REQUIRE(Q && B && workspace && (out_f64 || (out_max && out_sum)), RUNIA_E_BADARG, "kde_lse: null pointer");

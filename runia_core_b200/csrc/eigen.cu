@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(256) eigen_score_kernel(const float *__restric
 using namespace runia;
 
 extern "C" int runia_eigen_score_f32(const float *E, int n, int d, double alpha, double *out, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(n >= 2 && d >= 1 && alpha > 0.0, RUNIA_E_BADARG, "eigen_score: needs n >= 2 samples, d >= 1, alpha > 0");
   RUNIA_REQUIRE(n <= EG_MAXN && n <= d && (size_t)d * 8 <= 200 * 1024, RUNIA_E_UNSUPPORTED,
                 "eigen_score: n=%d samples (max %d, at most d) or d=%d (max 25600) not supported", n, EG_MAXN, d);

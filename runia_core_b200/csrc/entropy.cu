@@ -621,6 +621,7 @@ using namespace runia;
 
 extern "C" int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, int D, int k, double min_dist,
                                      double digamma_term, double *h_z, double *h_mvn, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(n_items >= 0 && D > 0, RUNIA_E_BADARG, "mcd_entropy: bad sizes n_items=%lld D=%d",
                 (long long)n_items, D);
   RUNIA_REQUIRE(n_mc >= 2 && n_mc <= kEntropyMaxN, RUNIA_E_UNSUPPORTED, "mcd_entropy: n_mc=%d outside [2, %d]", n_mc,

@@ -209,6 +209,7 @@ using namespace runia;
 
 extern "C" int runia_class_mean_f32(const float *X, const int32_t *labels, int64_t N, int d, int C, float *means,
                                     int64_t *counts, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && d >= 1 && C >= 1, RUNIA_E_BADARG, "class_mean: needs N >= 0, d >= 1, C >= 1");
   RUNIA_REQUIRE(C <= 65535, RUNIA_E_UNSUPPORTED, "class_mean: C=%d classes not supported (max 65535)", C);
   RUNIA_REQUIRE(labels || C == 1, RUNIA_E_BADARG, "class_mean: C > 1 needs labels");
@@ -227,6 +228,7 @@ extern "C" size_t runia_centered_gram_workspace_bytes(int64_t N, int d) {
 
 extern "C" int runia_centered_gram_f64(const float *X, const int32_t *labels, const float *centers, int64_t N, int d, int C,
                                        double *G, double *colsum, void *ws, size_t ws_bytes, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 1 && d >= 1 && C >= 1, RUNIA_E_BADARG, "centered_gram: needs N >= 1, d >= 1, C >= 1");
   RUNIA_REQUIRE(X && G && ws, RUNIA_E_BADARG, "centered_gram: null pointer");
   RUNIA_REQUIRE(labels || C == 1, RUNIA_E_BADARG, "centered_gram: C > 1 needs labels");

@@ -737,6 +737,7 @@ static cudaError_t launch_logit_wide(const float *logits, int64_t N, int C, floa
 }
 
 extern "C" int runia_gen_entropy_f32(const float *probs, int64_t N, int C, float gamma, int M, float *out, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && C > 0, RUNIA_E_BADARG, "gen_entropy: bad sizes");
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(probs && out, RUNIA_E_BADARG, "gen_entropy: null pointer");
@@ -747,6 +748,7 @@ extern "C" int runia_gen_entropy_f32(const float *probs, int64_t N, int C, float
 
 extern "C" int runia_logit_scores_f32(const float *logits, int64_t N, int C, float gamma, int M, float *energy,
                                       float *msp, float *gen, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && C > 0, RUNIA_E_BADARG, "logit_scores: bad sizes");
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(logits && (energy || msp || gen), RUNIA_E_BADARG, "logit_scores: null pointer");
@@ -849,10 +851,12 @@ static int launch_linear_lse(bool ash, const float *X, int64_t N, int d, const f
 
 extern "C" int runia_clip_linear_lse_f32(const float *X, int64_t N, int d, const float *W, const float *b, int C,
                                          float clip, float *out, void *stream) {
+  RUNIA_NVTX();
   return launch_linear_lse(false, X, N, d, W, b, C, clip, 0, out, stream);
 }
 
 extern "C" int runia_ash_prune_f32(const float *X, int64_t N, int d, int k_keep, float *out, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && d > 0, RUNIA_E_BADARG, "ash_prune: bad sizes");
   RUNIA_REQUIRE(k_keep >= 1 && k_keep <= d, RUNIA_E_BADARG, "ash_prune: k_keep=%d outside [1, d=%d]", k_keep, d);
   if (N == 0) return RUNIA_OK;
@@ -865,6 +869,7 @@ extern "C" int runia_ash_prune_f32(const float *X, int64_t N, int d, int k_keep,
 
 extern "C" int runia_ash_linear_lse_f32(const float *X, int64_t N, int d, const float *W, const float *b, int C,
                                         int k_keep, float *out, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(k_keep >= 1 && k_keep <= d, RUNIA_E_BADARG, "ash_linear_lse: k_keep=%d outside [1, d=%d]", k_keep, d);
   return launch_linear_lse(true, X, N, d, W, b, C, INFINITY, k_keep, out, stream);
 }
@@ -959,6 +964,7 @@ pred_uncertainty_kernel(const float *__restrict__ logits, int64_t n_items, int n
 
 extern "C" int runia_pred_uncertainty_f32(const float *logits, int64_t n_items, int n_mc, int C, float *pred_h, float *mi,
                                           void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(n_items >= 0 && n_mc >= 1 && C >= 1, RUNIA_E_BADARG, "pred_uncertainty: bad sizes");
   RUNIA_REQUIRE(C <= 4096, RUNIA_E_UNSUPPORTED, "pred_uncertainty: C=%d > 4096", C);
   if (n_items == 0) return RUNIA_OK;
@@ -1020,6 +1026,7 @@ __global__ void __launch_bounds__(256) spatial_mean_kernel(const float *__restri
 }  // namespace runia
 
 extern "C" int runia_spatial_mean_f32(const float *x, int64_t P, int H, int W, int fullmean, float *out, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(P >= 0 && H > 0 && W > 0, RUNIA_E_BADARG, "spatial_mean: bad sizes");
   if (P == 0) return RUNIA_OK;
   RUNIA_REQUIRE(x && out, RUNIA_E_BADARG, "spatial_mean: null pointer");

@@ -544,6 +544,7 @@ extern "C" int64_t runia_sort_f32_workspace_bytes(int64_t n) { return n > 0 ? (i
 
 extern "C" int runia_sort_f32(const float *x, int64_t n, float *out_sorted, void *workspace, int64_t workspace_bytes,
                               void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(n >= 0 && n < (int64_t)0x7fffffff, RUNIA_E_BADARG, "sort_f32: bad size");
   if (n == 0) return RUNIA_OK;
   RUNIA_REQUIRE(x && out_sorted && workspace, RUNIA_E_BADARG, "sort_f32: null pointer");
@@ -585,6 +586,7 @@ extern "C" int64_t runia_ood_metrics_workspace_bytes(int64_t n_ind, int64_t n_oo
 extern "C" int runia_ood_metrics(const void *ind, int64_t n_ind, const void *ood, int64_t n_ood, int is_f64,
                                  double *out4, float *fpr_out, float *tpr_out, void *workspace,
                                  int64_t workspace_bytes, void *stream) {
+  RUNIA_NVTX();
   if (is_f64)
     return ood_metrics_impl<double>((const double *)ind, n_ind, (const double *)ood, n_ood, out4, fpr_out, tpr_out,
                                     workspace, workspace_bytes, (cudaStream_t)stream);

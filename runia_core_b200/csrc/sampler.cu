@@ -165,6 +165,7 @@ extern "C" size_t runia_mc_dropblock_workspace_bytes(int B, int H, int W, int n_
 
 extern "C" int runia_mc_dropblock_mean_f32(const float *x, const uint8_t *seed, int B, int C, int H, int W, int n_mc,
                                            int block_size, float *out, void *ws, size_t ws_bytes, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(B >= 1 && C >= 1 && H >= 1 && W >= 1 && n_mc >= 1 && block_size >= 1, RUNIA_E_BADARG,
                 "mc_dropblock: needs B, C, H, W, n_mc, block_size >= 1");
   RUNIA_REQUIRE(n_mc <= 32, RUNIA_E_UNSUPPORTED, "mc_dropblock: n_mc=%d not supported (max 32)", n_mc);

@@ -233,6 +233,7 @@ using namespace runia;
 extern "C" int runia_pca_transform_f32(const float *X, int64_t N, int D0, const float *mean,
                                        const float *components, int d, const float *inv_scale, float *Z,
                                        void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && D0 > 0 && d > 0, RUNIA_E_BADARG, "pca_transform: bad sizes N=%lld D0=%d d=%d",
                 (long long)N, D0, d);
   if (N == 0) return RUNIA_OK;
@@ -246,6 +247,7 @@ extern "C" int runia_pca_transform_f32(const float *X, int64_t N, int D0, const 
 
 extern "C" int runia_linear_f32(const float *X, int64_t N, int d, const float *W, const float *b, int C, float *out,
                                 void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && d > 0 && C > 0, RUNIA_E_BADARG, "linear: bad sizes N=%lld d=%d C=%d", (long long)N, d, C);
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(X && W && out, RUNIA_E_BADARG, "linear: null pointer");
@@ -258,6 +260,7 @@ extern "C" int runia_linear_f32(const float *X, int64_t N, int d, const float *W
 extern "C" int runia_rownorm_score_f32(const float *X, int64_t N, int d, const float *mu, const float *Wt,
                                        int r, const float *sign, int mode, const float *logits, int C,
                                        float alpha, double *out_f64, float *out_f32, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && d > 0 && r > 0, RUNIA_E_BADARG, "rownorm_score: bad sizes N=%lld d=%d r=%d",
                 (long long)N, d, r);
   RUNIA_REQUIRE(mode == RUNIA_ROWNORM_MD || mode == RUNIA_ROWNORM_VIM, RUNIA_E_BADARG, "rownorm_score: bad mode");
@@ -275,6 +278,7 @@ extern "C" int runia_classcond_mahalanobis_f32(const float *X, int64_t N, int d,
                                                const float *Wt, int r, const float *sign, const float *Mc,
                                                const int32_t *class_valid, int C, double *out_f64,
                                                float *out_f32, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && d > 0 && r > 0 && C > 0, RUNIA_E_BADARG, "classcond: bad sizes");
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(X && Wt && Mc && class_valid && (out_f64 || out_f32), RUNIA_E_BADARG, "classcond: null pointer");
@@ -296,6 +300,7 @@ extern "C" int runia_classcond_mahalanobis_f32(const float *X, int64_t N, int d,
 
 extern "C" int runia_gmm_lse_f32(const float *X, int64_t N, int d, const float *At, const float *off, int dpad,
                                  const float *logconst, int C, float *out, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && d > 0 && C > 0 && dpad > 0 && dpad % BN == 0, RUNIA_E_BADARG,
                 "gmm_lse: bad sizes (dpad must be a multiple of %d)", BN);
   if (N == 0) return RUNIA_OK;

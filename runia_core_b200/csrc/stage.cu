@@ -2,12 +2,14 @@
 // evaluation/metrics.py:322-340).  cudaMemcpy from pageable memory is staged by the driver through one bounce buffer
 // with a single-threaded memcpy (13-17 GB/s measured on the B200 boxes); this engine does the staging itself:
 //   * a ring of pinned slots (4 x 4 MiB, allocated once per process),
-//   * a persistent pool of worker threads that memcpy disjoint pieces of a chunk into its slot in parallel,
+//   * a persistent pool of worker threads that claim 256 KiB pieces of a chunk and memcpy them into its slot in
+//     parallel with the caller (the caller never waits for a sleeping worker to wake up),
 //   * one cudaMemcpyAsync per chunk on the caller's stream, an event per slot guarding its reuse,
 // so the CPU copy of chunk k+1 overlaps the PCIe transfer of chunk k and the copy rate is that of several cores.
 // The call returns once every chunk is enqueued (the last transfers are still in flight; the source may be reused
 // immediately -- it has been copied out).  One call at a time per process (mutex); the GIL is not held by ctypes callers.
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <mutex>
@@ -21,13 +23,32 @@ namespace {
 
 constexpr size_t kSlotBytes = 4u << 20;
 constexpr int kSlots = 4;
+constexpr size_t kPieceBytes = 256u << 10;  // unit of work the threads claim (16 per full chunk)
 
-struct Piece {
-  char *dst;
-  const char *src;
-  size_t n;
+struct Desc {  // one chunk to copy: pieces [i * kPieceBytes, ...) of n bytes.  `gen` brackets the fields like a seqlock:
+  // a thread that overshot the piece count of an old generation may look at a slot that is being rewritten for a
+  // newer one, and must not act on it
+  std::atomic<char *> dst{nullptr};
+  std::atomic<const char *> src{nullptr};
+  std::atomic<size_t> n{0};
+  std::atomic<uint32_t> npieces{0};
+  std::atomic<uint64_t> gen{0};
 };
 
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#else
+  std::this_thread::yield();
+#endif
+}
+
+// Work distribution: `ticket_` = (generation << 32) | next piece index.  Every thread -- the caller included --
+// claims pieces of the current chunk with one fetch_add; a chunk is done when `done_` reaches its piece count.
+// The caller never waits for a worker to WAKE UP: if the workers are asleep it simply copies the pieces itself
+// (the speed of a plain cudaMemcpy from pageable memory) and they join as they arrive.  After their last piece the
+// workers spin for `spin_us_` before they go back to sleep on the condition variable, so that back-to-back calls
+// (a sweep of postprocess() calls, the chunks of one large upload) always find them hot.
 class Stager {
  public:
   static Stager &get() {  // one engine per device (its events belong to that device's context)
@@ -56,15 +77,12 @@ class Stager {
     return RUNIA_OK;
   }
 
-  int threads() const { return (int)workers_.size() + 1; }
-
  private:
   Stager() = default;
   ~Stager() {
+    stop_.store(true);
     {
       std::lock_guard<std::mutex> lk(mu_);
-      stop_ = true;
-      ++gen_;
     }
     cv_.notify_all();
     for (auto &t : workers_) t.join();
@@ -81,58 +99,101 @@ class Stager {
     unsigned hw = std::thread::hardware_concurrency();
     int n = hw >= 16 ? 7 : hw >= 8 ? 3 : hw >= 4 ? 1 : 0;  // + the calling thread
     if (const char *e = getenv("RUNIA_B200_STAGE_THREADS")) n = std::max(0, atoi(e) - 1);
-    pieces_.resize(n + 1);
-    for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { worker(i + 1); });
+    if (const char *e = getenv("RUNIA_B200_STAGE_SPIN_US")) spin_us_ = std::max(0, atoi(e));
+    for (int i = 0; i < n; ++i) workers_.emplace_back([this] { worker(); });
     ready_ = true;
     return RUNIA_OK;
   }
 
-  // parallel memcpy of one chunk: piece 0 is copied by the caller, pieces 1.. by the workers
+  bool work_available() const {
+    const uint64_t t = ticket_.load(std::memory_order_seq_cst);
+    const uint64_t g = t >> 32;
+    const Desc &d = ring_[g & 3];
+    return g != 0 && d.gen.load(std::memory_order_acquire) == g && (uint32_t)t < d.npieces.load(std::memory_order_relaxed);
+  }
+
+  // claims and copies pieces until none is left; returns true if it copied at least one
+  bool claim_loop() {
+    bool any = false;
+    for (;;) {
+      if (!work_available()) return any;
+      const uint64_t t = ticket_.fetch_add(1, std::memory_order_acq_rel);
+      const uint64_t g = t >> 32;
+      const uint32_t i = (uint32_t)t;
+      const Desc &d = ring_[g & 3];  // written before the ticket of generation g was published
+      if (g == 0 || d.gen.load(std::memory_order_acquire) != g) continue;
+      char *dst = d.dst.load(std::memory_order_relaxed);
+      const char *src = d.src.load(std::memory_order_relaxed);
+      const size_t n = d.n.load(std::memory_order_relaxed);
+      const uint32_t np = d.npieces.load(std::memory_order_relaxed);
+      if (d.gen.load(std::memory_order_acquire) != g) continue;  // the slot moved on: this was an overshoot of an old chunk
+      if (i < np) {  // a valid claim pins the generation: the caller cannot advance before `done_` counts this piece
+        const size_t off = (size_t)i * kPieceBytes;
+        memcpy(dst + off, src + off, n - off < kPieceBytes ? n - off : kPieceBytes);
+        done_[g & 3].fetch_add(1, std::memory_order_release);
+        any = true;
+      }
+    }
+  }
+
   void fill(char *dst, const char *src, size_t n) {
-    const size_t parts = pieces_.size();
-    if (parts == 1 || n < (256u << 10)) {
+    if (workers_.empty() || n <= kPieceBytes) {
       memcpy(dst, src, n);
       return;
     }
-    const size_t per = (n / parts + 4095) & ~(size_t)4095;
-    size_t off = 0;
-    for (size_t p = 0; p < parts; ++p) {
-      const size_t m = off >= n ? 0 : (n - off < per || p + 1 == parts ? n - off : per);
-      pieces_[p] = Piece{dst + off, src + off, m};
-      off += m;
+    const uint64_t g = ++gen_;
+    const uint32_t np = (uint32_t)((n + kPieceBytes - 1) / kPieceBytes);
+    Desc &d = ring_[g & 3];
+    d.gen.store(0, std::memory_order_release);  // invalidate while the fields change
+    d.dst.store(dst, std::memory_order_relaxed);
+    d.src.store(src, std::memory_order_relaxed);
+    d.n.store(n, std::memory_order_relaxed);
+    d.npieces.store(np, std::memory_order_relaxed);
+    done_[g & 3].store(0, std::memory_order_relaxed);
+    d.gen.store(g, std::memory_order_release);
+    ticket_.store(g << 32, std::memory_order_seq_cst);
+    if (sleepers_.load(std::memory_order_seq_cst) > 0) {
+      { std::lock_guard<std::mutex> lk(mu_); }
+      cv_.notify_all();
     }
-    remaining_.store((int)parts - 1, std::memory_order_release);
-    {
-      std::lock_guard<std::mutex> lk(mu_);
-      ++gen_;
-    }
-    cv_.notify_all();
-    if (pieces_[0].n) memcpy(pieces_[0].dst, pieces_[0].src, pieces_[0].n);
-    while (remaining_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+    claim_loop();
+    while (done_[g & 3].load(std::memory_order_acquire) != np) cpu_relax();
   }
 
-  void worker(int idx) {
-    uint64_t seen = 0;
+  void worker() {
+    using clock = std::chrono::steady_clock;
+    auto last = clock::now();
     for (;;) {
+      if (stop_.load(std::memory_order_relaxed)) return;
+      if (claim_loop()) {
+        last = clock::now();
+        continue;
+      }
+      if (std::chrono::duration_cast<std::chrono::microseconds>(clock::now() - last).count() < spin_us_) {
+        cpu_relax();
+        continue;
+      }
+      sleepers_.fetch_add(1, std::memory_order_seq_cst);
       {
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return gen_ != seen; });
-        seen = gen_;
-        if (stop_) return;
+        cv_.wait_for(lk, std::chrono::milliseconds(100), [&] { return stop_.load() || work_available(); });
       }
-      const Piece p = pieces_[idx];
-      if (p.n) memcpy(p.dst, p.src, p.n);
-      remaining_.fetch_sub(1, std::memory_order_acq_rel);
+      sleepers_.fetch_sub(1, std::memory_order_seq_cst);
+      last = clock::now();
     }
   }
 
   std::mutex call_mu_, mu_;
   std::condition_variable cv_;
+  std::atomic<bool> stop_{false};
+  bool ready_ = false;
+  int spin_us_ = 2000;
   uint64_t gen_ = 0;
-  bool stop_ = false, ready_ = false;
-  std::atomic<int> remaining_{0};
+  std::atomic<uint64_t> ticket_{0};
+  std::atomic<uint32_t> done_[4];
+  std::atomic<int> sleepers_{0};
+  Desc ring_[4];
   std::vector<std::thread> workers_;
-  std::vector<Piece> pieces_;
   char *slot_[kSlots] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_[kSlots];
   bool busy_[kSlots] = {false, false, false, false};
@@ -143,6 +204,7 @@ class Stager {
 }  // namespace runia
 
 extern "C" int runia_stage_h2d(void *dst_dev, const void *src_host, int64_t bytes, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(bytes >= 0, RUNIA_E_BADARG, "stage_h2d: negative size");
   if (bytes == 0) return RUNIA_OK;
   RUNIA_REQUIRE(dst_dev && src_host, RUNIA_E_BADARG, "stage_h2d: null pointer");

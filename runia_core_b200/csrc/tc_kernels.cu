@@ -894,6 +894,7 @@ using namespace runia;
 using namespace runia::tc;
 
 extern "C" int runia_split_tf32(const float *x, int64_t total, float *hi, float *lo, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(total >= 0, RUNIA_E_BADARG, "split_tf32: bad size");
   if (total == 0) return RUNIA_OK;
   RUNIA_REQUIRE(x && hi && lo, RUNIA_E_BADARG, "split_tf32: null pointer");
@@ -906,6 +907,7 @@ extern "C" int runia_split_tf32(const float *x, int64_t total, float *hi, float 
 extern "C" int runia_rownorm_score_tc(const float *X, int64_t N, int d, const float *mu, const float *Wt_hi,
                                       const float *Wt_lo, int r, const float *sign, int mode, const float *logits,
                                       int C, float alpha, double *out_f64, float *out_f32, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && d > 0 && r > 0, RUNIA_E_BADARG, "rownorm_score_tc: bad sizes");
   RUNIA_REQUIRE(mode == RUNIA_ROWNORM_MD || mode == RUNIA_ROWNORM_VIM, RUNIA_E_BADARG, "rownorm_score_tc: bad mode");
   if (N == 0) return RUNIA_OK;
@@ -937,6 +939,7 @@ extern "C" int runia_rownorm_score_tc(const float *X, int64_t N, int d, const fl
 
 extern "C" int runia_clip_linear_lse_tc(const float *X, int64_t N, int d, const float *W_hi, const float *W_lo,
                                         const float *b, int C, float clip, float *out, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && d > 0 && C > 0, RUNIA_E_BADARG, "clip_linear_lse_tc: bad sizes");
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(X && W_hi && W_lo && b && out, RUNIA_E_BADARG, "clip_linear_lse_tc: null pointer");
@@ -994,6 +997,7 @@ extern "C" int runia_clip_linear_lse_tc(const float *X, int64_t N, int d, const 
 }
 
 extern "C" int runia_tf32_peak_probe(int iters, double *flop_out, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(iters >= 1 && iters <= (1 << 24), RUNIA_E_BADARG, "tf32_peak_probe: iters out of range");
   const size_t smem = (size_t)A_PLANE_BYTES + B_PLANE_BYTES + 64 + SMEM_ALIGN;
   static PerDeviceFlag attr;
@@ -1011,6 +1015,7 @@ extern "C" int runia_tf32_peak_probe(int iters, double *flop_out, void *stream) 
 
 extern "C" int runia_pca_transform_tc(const float *X, int64_t N, int D0, const float *mean, const float *C_hi,
                                       const float *C_lo, int d, const float *inv_scale, float *Z, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && D0 > 0 && d > 0, RUNIA_E_BADARG, "pca_transform_tc: bad sizes");
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(X && C_hi && C_lo && Z, RUNIA_E_BADARG, "pca_transform_tc: null pointer");
@@ -1046,6 +1051,7 @@ extern "C" int runia_classcond_mahalanobis_tc(const float *X, int64_t N, int d, 
                                               const float *Wt_lo, int r, const float *sign, const float *Mc,
                                               const int32_t *class_valid, int C, double *out_f64, float *out_f32,
                                               void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && d > 0 && r > 0 && C > 0, RUNIA_E_BADARG, "classcond_mahalanobis_tc: bad sizes");
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(X && Wt_hi && Wt_lo && Mc && class_valid && (out_f64 || out_f32), RUNIA_E_BADARG,
@@ -1079,6 +1085,7 @@ extern "C" int runia_classcond_mahalanobis_tc(const float *X, int64_t N, int d, 
 
 extern "C" int runia_gmm_lse_tc(const float *X, int64_t N, int d, const float *At_hi, const float *At_lo,
                                 const float *off, int dpad, const float *logconst, int C, float *out, void *stream) {
+  RUNIA_NVTX();
   RUNIA_REQUIRE(N >= 0 && d > 0 && C > 0 && dpad >= d && dpad % 128 == 0, RUNIA_E_BADARG, "gmm_lse_tc: bad sizes");
   if (N == 0) return RUNIA_OK;
   RUNIA_REQUIRE(X && At_hi && At_lo && off && logconst && out, RUNIA_E_BADARG, "gmm_lse_tc: null pointer");

@@ -30,7 +30,10 @@ class MCSamplerModule(torch.nn.Module):
         """[n_mc, B, H, W] uint8: the `(torch.rand(B, H, W) < gamma)` draws of the n_mc DropBlock2D layers."""
         gamma = self.drop_prob / (self.block_size**2)
         shape = (latent_rep.shape[0], *latent_rep.shape[2:])
-        return torch.stack([(torch.rand(*shape) < gamma) for _ in range(self.mc_samples)]).to(torch.uint8)
+        # ONE draw of [n_mc, B, H, W]: torch's CPU uniform_ fills serially from the generator, so this is exactly the
+        # sequence of the n_mc per-layer `torch.rand(B, H, W)` calls (tests/test_cabi_and_host.py checks it), at a tenth
+        # of their cost
+        return (torch.rand(self.mc_samples, *shape) < gamma).to(torch.uint8)
 
     def sample_batch(self, latent_rep: torch.Tensor, seeds: torch.Tensor = None) -> torch.Tensor:
         """[B, C, H, W] -> device rows [B * n_mc, C], item-major (rows b * n_mc .. b * n_mc + n_mc - 1 are image b):

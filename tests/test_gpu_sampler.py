@@ -106,6 +106,27 @@ def test_larex_online_chain_matches_staged_api():
     staged = md.postprocess(R.apply_pca_transform(hz1, pca))
     assert out.shape == (1, 10) and score.shape == (1,) and score.dtype == np.float64
     np.testing.assert_allclose(score, staged, rtol=1e-5)
+    # the CUDA-graph replay (default) and the launch-by-launch chain give the same bits on the same seeds, image
+    # after image (static buffers are refilled, not re-captured), for a second map shape too
+    assert inf.use_cuda_graph and len(inf._graphs) == 1
+    for i in (1, 2, 3):
+        torch.manual_seed(40 + i)
+        _, s_graph = inf.get_score(imgs[i:i + 1], hook)
+        inf.use_cuda_graph = False
+        torch.manual_seed(40 + i)
+        _, s_plain = inf.get_score(imgs[i:i + 1], hook)
+        inf.use_cuda_graph = True
+        assert np.array_equal(s_graph, s_plain)
+    torch.manual_seed(50)
+    _, s4 = inf.get_score(imgs[:4], hook)  # a batch of four maps: its own captured graph
+    assert s4.shape == (4,) and len(inf._graphs) == 2
+    res, secs = inf.test_time_inference(imgs[:1], hook)
+    assert res[1].shape == (1,) and secs > 0
+    # LaRD (no MC sampling, no entropy): mean map -> PCA -> LaREM on the device == the staged public calls
+    lard = R.inference.LaRDInference(net, md, pca_transform=pca, layer_type="Conv")
+    out_d, sc_d = lard.get_score(imgs[:1], hook)
+    z = hook.output.mean((2, 3)).cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(sc_d, md.postprocess(R.apply_pca_transform(z, pca)), rtol=1e-4)
 
 
 def test_folded_pca_larem_matches_staged():
