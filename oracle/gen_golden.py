@@ -219,6 +219,44 @@ def wide_case(ref, seed):
     return out
 
 
+def all_baselines_case(ref, seed):
+    """The reference's own driver, `calculate_all_baselines` (evaluation/baselines.py:713-854), over every baseline
+    it knows, two OoD sets, 10 classes + a background logit column (11 columns: `get_labels_from_logits` drops the
+    last one, baselines.py:645-676).  Inputs and every "<ood> <baseline>" / InD score array are stored."""
+    rng = np.random.RandomState(seed)
+    C, d, n_train, n_valid, n_ood = 10, 48, 1500, 120, 90
+    centers = rng.randn(C, d)
+    mk_x = lambda y, n: (np.maximum(centers[y] + rng.randn(n, d), 0) + 0.05 * rng.rand(n, d)).astype(np.float32)  # noqa: E731
+    ytr = rng.randint(0, C, n_train)
+    train, valid = mk_x(ytr, n_train), mk_x(rng.randint(0, C, n_valid), n_valid)
+    oods = {"ood_a": (np.maximum(1.5 * rng.randn(n_ood, d), 0) + 0.05 * rng.rand(n_ood, d)).astype(np.float32),
+            "ood_b": (np.maximum(0.3 + rng.randn(n_ood, d), 0)).astype(np.float32)}
+    W = (0.2 * rng.randn(C + 1, d)).astype(np.float32)
+    b = rng.randn(C + 1).astype(np.float32)
+    lg = lambda x: (x @ W.T + b).astype(np.float32)  # noqa: E731
+    ind = {"train features": train, "valid features": valid, "train logits": lg(train), "valid logits": lg(valid)}
+    ood = {}
+    for name, x in oods.items():
+        ood[f"{name} features"], ood[f"{name} logits"] = x, lg(x)
+    out = {f"in::{k}": v for k, v in {**ind, **ood}.items()}
+    out["W"], out["b"], out["num_classes"] = W, b, C + 1
+    names = ["vim", "msp", "raw", "knn", "energy", "ash", "gen", "react", "dice", "dice_react", "mdist", "ddu"]
+    cfg = ref.DictConfig(ood_datasets=list(oods), k_neighbors=10, ash_percentile=85, gen_gamma=0.1, react_percentile=90,
+                         dice_percentile=90)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ind2, ood2, scores = ref.baselines.calculate_all_baselines(
+            baselines_names=names, ind_data_dict=dict(ind), ood_data_dict=dict(ood), fc_params={"weight": W, "bias": b},
+            cfg=cfg, num_classes=C + 1)
+    for k in names:
+        out[f"ind::{k}"] = np.asarray(ind2[k])
+    for k, v in scores.items():
+        out[f"ood::{k}"] = np.asarray(v)
+    out["ind::train labels"], out["ind::valid labels"] = ind2["train labels"], ind2["valid labels"]
+    out["ood::ood_a labels"] = ood2["ood_a labels"]
+    return out
+
+
 def entropy_case(ref, seed):
     rng = np.random.RandomState(seed)
     out = {}
@@ -276,6 +314,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "pca.npz"), **pca_case(ref, 1))
     np.savez_compressed(os.path.join(OUT, "baselines_flip.npz"), **flip_case(ref, 22, 700, 96, 32, 5, 10))
     np.savez_compressed(os.path.join(OUT, "wide_shapes.npz"), **wide_case(ref, 23))
+    np.savez_compressed(os.path.join(OUT, "all_baselines.npz"), **all_baselines_case(ref, 24))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

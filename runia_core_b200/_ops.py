@@ -122,6 +122,8 @@ def pca_prepare(mean, components, explained_variance, whiten) -> PCAState:
 
 
 def pca_transform(x, st: PCAState) -> torch.Tensor:
+    if x.ndim != 2 or x.shape[1] != st.D0:
+        raise ValueError(f"expected rows of width {st.D0}, got an array of shape {tuple(x.shape)}")
     z = _empty((x.shape[0], st.d), torch.float32)
 
     def run(xc, lo, hi):
@@ -218,6 +220,8 @@ def md_score(x, st: MDState, out_dtype=torch.float64, out: Optional[torch.Tensor
     """LaREM scores of the rows of x (into `out` when given: a contiguous [N] device tensor of `out_dtype`).  Host
     matrices (what `MDLatentSpace.postprocess` receives, evaluation/metrics.py:331-340) stream through the pinned
     staging ring: the kernel scores chunk k while chunk k + 1 crosses PCIe and chunk k + 2 is copied into its slot."""
+    if x.ndim != 2 or x.shape[1] != st.d:
+        raise ValueError(f"expected rows of width {st.d}, got an array of shape {tuple(x.shape)}")
     if out is None:
         out = _empty((x.shape[0],), out_dtype)
     assert out.dtype == out_dtype and out.is_contiguous() and out.shape[0] == x.shape[0]
@@ -255,6 +259,8 @@ def vim_prepare(u, NS, alpha) -> VimState:
 
 
 def vim_score(x, logits, st: VimState) -> torch.Tensor:
+    if x.ndim != 2 or x.shape[1] != st.d:
+        raise ValueError(f"expected rows of width {st.d}, got an array of shape {tuple(x.shape)}")
     xf, centered = as_f32_rows(x, st.u_f64)
     lg = to_device(logits, torch.float32)
     n = xf.shape[0]
@@ -306,6 +312,8 @@ def classcond_prepare(class_mean, precision) -> ClassCondState:
 
 
 def classcond_score(x, st: ClassCondState, out_dtype=torch.float64) -> torch.Tensor:
+    if x.ndim != 2 or x.shape[1] != st.d:
+        raise ValueError(f"expected rows of width {st.d}, got an array of shape {tuple(x.shape)}")
     xf, centered = as_f32_rows(x, st.g_f64)
     n = xf.shape[0]
     out = _empty((n,), out_dtype)
@@ -359,6 +367,8 @@ def gmm_prepare(means, scale_tril) -> GMMState:
 
 
 def gmm_lse(x, st: GMMState) -> torch.Tensor:
+    if x.ndim != 2 or x.shape[1] != st.d:
+        raise ValueError(f"expected rows of width {st.d}, got an array of shape {tuple(x.shape)}")
     xf, _ = as_f32_rows(x, None)
     n = xf.shape[0]
     out = _empty((n,), torch.float32)

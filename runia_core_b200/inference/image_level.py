@@ -148,6 +148,9 @@ class LaRExInference(ProbabilisticInferenceModule):
             latent_rep.is_cuda and latent_rep.dtype == torch.float32 else None
         if st is not None:
             return self._score_graph(st, latent_rep)
+        if getattr(self.mc_sampler, "layer_type", None) == "Conv" and hasattr(self.mc_sampler, "sample_batch") and \
+                isinstance(latent_rep, torch.Tensor) and latent_rep.dim() == 4:
+            return self.score_samples(self.mc_sampler.sample_batch(latent_rep))  # item-major rows: one score per map
         return self.score_samples(self.mc_sampler(latent_rep))
 
     @record_time

@@ -3,6 +3,7 @@ reference-facing boundary behaves like the reference where no compute is involve
 multi-GPU exchange logic runs over gloo with world_size 2."""
 import inspect
 import os
+import sys
 import re
 
 import numpy as np
@@ -327,3 +328,60 @@ def test_mc_sampler_module_fc_layer_and_seed_stream():
         MCSamplerModule(mc_samples=2, block_size=1, drop_prob=0.1, layer_type="Linear")
     smp.eval()
     assert torch.equal(smp(x), x.reshape(1, -1).repeat(n_mc, 1))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/runia_core/evaluation/baselines.py"),
+                    reason="the reference tree only exists in the build container")
+def test_reference_callers_bind_to_the_product_unchanged():
+    """the reference's own driver module must keep working on top of the drop-in.  The
+    UNMODIFIED source of `runia_core/evaluation/baselines.py` is executed with `runia_core` aliased to this package
+    (`install_as_runia_core()`): its `from runia_core.inference.postprocessors import DICE, ReAct, ...` must resolve to
+    the product's classes, and every call it makes (constructor keywords, setup / postprocess keywords) must be
+    accepted by their signatures.  (Its numerical output on the product is checked on the GPU against the reference's
+    own output: tests/test_gpu_shapes.py::test_calculate_all_baselines_matches_reference_driver.)"""
+    import ast
+    import importlib.util
+    import types
+
+    import runia_core_b200 as R
+
+    saved = {k: v for k, v in sys.modules.items() if k == "runia_core" or k.startswith("runia_core.") or k == "omegaconf"}
+    try:
+        R.install_as_runia_core()
+        if "omegaconf" not in sys.modules:
+            sys.modules["omegaconf"] = types.SimpleNamespace(DictConfig=dict)
+        path = "/root/reference/runia_core/evaluation/baselines.py"
+        spec = importlib.util.spec_from_file_location("reference_baselines_on_product", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        P = R.inference.postprocessors
+        for name in ("DICE", "ReAct", "ASH", "GEN", "ViM", "MSP", "Energy", "Mahalanobis", "KNN", "DDU", "DICEReAct"):
+            assert getattr(mod, name) is getattr(P, name), name
+        # every keyword the reference passes to a constructor / setup / postprocess exists in the product's signature
+        tree = ast.parse(open(path).read())
+        ctor_kw = {}
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and hasattr(P, node.func.id) and \
+                    node.func.id[0].isupper():
+                ctor_kw.setdefault(node.func.id, set()).update(k.arg for k in node.keywords)
+        assert len(ctor_kw) == 11
+        for cls, kws in ctor_kw.items():
+            params = set(inspect.signature(getattr(P, cls).__init__).parameters)
+            assert kws <= params, (cls, kws - params)
+        for cls in ctor_kw:
+            sig = inspect.signature(getattr(P, cls).setup).parameters
+            assert "ind_train_data" in sig and any(p.kind == p.VAR_KEYWORD for p in sig.values()), cls
+            sig = inspect.signature(getattr(P, cls).postprocess).parameters
+            assert "test_data" in sig and any(p.kind == p.VAR_KEYWORD for p in sig.values()), cls
+        # and the product ships the same driver entry points
+        from runia_core_b200.evaluation import baselines as mine
+
+        for fn in mod.__all__:
+            if fn != "baseline_name_dict":
+                assert list(inspect.signature(getattr(mine, fn)).parameters) == \
+                    list(inspect.signature(getattr(mod, fn)).parameters), fn
+    finally:
+        for k in [k for k in sys.modules if k == "runia_core" or k.startswith("runia_core.")]:
+            del sys.modules[k]
+        sys.modules.pop("omegaconf", None)
+        sys.modules.update(saved)

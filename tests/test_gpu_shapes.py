@@ -347,3 +347,54 @@ def test_fixture_wide_shapes(R, golden):
                  gen_M=int(w["gen_M"]))
     hm, hz = R.evaluation.get_dl_h_z(w["n40_z"], int(w["n40_n_mc"]))
     assert rel_err(hz, w["n40_h_z"]) < RTOL and rel_err(hm, w["n40_h_mvn"]) < RTOL
+
+
+def test_entropy_very_wide_rows(R):
+    """Row widths far beyond a latent vector (a whole flattened map handed to get_dl_h_z): no size assumption."""
+    rng = np.random.RandomState(5)
+    n_items, n_mc, D = 3, 16, 70_000
+    z = (rng.randn(n_items, 1, D) + 0.1 * rng.randn(n_items, n_mc, D)).astype(np.float32).reshape(-1, D)
+    hm, hz = R.evaluation.get_dl_h_z(z, n_mc)
+    rm, rz = O.get_dl_h_z(z[: 16], n_mc, chunk=1)
+    assert rel_err(hz[:1], rz) < RTOL and rel_err(hm[:1], rm) < RTOL
+    md = R.inference.MDLatentSpace()
+    md.setup(rng.randn(100, 8).astype(np.float32))
+    with pytest.raises(ValueError, match="width 8"):
+        md.postprocess(rng.randn(4, 9).astype(np.float32))
+
+
+def test_calculate_all_baselines_matches_reference_driver(R, golden):
+    """tests/golden/all_baselines.npz: the REFERENCE's `calculate_all_baselines` (evaluation/baselines.py:713-854, run
+    unmodified on its own postprocessors) over all twelve baselines, two OoD sets and an 11-column head (background
+    column dropped for the labels); the product's driver on the same dictionaries must return the same arrays under
+    the same keys."""
+    from runia_core_b200.evaluation import calculate_all_baselines
+
+    class Cfg(dict):
+        __getattr__ = dict.__getitem__
+
+    f = golden("all_baselines")
+    ind = {k[4:]: f[k] for k in f.files if k.startswith("in::") and not k[4:].startswith("ood_")}
+    ood = {k[4:]: f[k] for k in f.files if k.startswith("in::") and k[4:].startswith("ood_")}
+    names = ["vim", "msp", "raw", "knn", "energy", "ash", "gen", "react", "dice", "dice_react", "mdist", "ddu"]
+    cfg = Cfg(ood_datasets=["ood_a", "ood_b"], k_neighbors=10, ash_percentile=85, gen_gamma=0.1, react_percentile=90,
+              dice_percentile=90)
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ind2, ood2, scores = calculate_all_baselines(baselines_names=names, ind_data_dict=ind, ood_data_dict=ood,
+                                                     fc_params={"weight": f["W"], "bias": f["b"]}, cfg=cfg,
+                                                     num_classes=int(f["num_classes"]))
+    assert sorted(scores) == sorted(k[5:] for k in f.files if k.startswith("ood::") and not k.endswith("labels"))
+    for k, v in scores.items():
+        ref = f[f"ood::{k}"]
+        assert v.shape == ref.shape and v.dtype == ref.dtype, (k, v.dtype, ref.dtype)
+        assert rel_err(v, ref) < RTOL, (k, rel_err(v, ref))
+    for k in names:
+        assert rel_err(ind2[k], f[f"ind::{k}"]) < RTOL, k
+    assert "train logits" not in ind2 and np.array_equal(ind2["train labels"], f["ind::train labels"])
+    assert np.array_equal(ind2["valid labels"], f["ind::valid labels"])
+    assert np.array_equal(ood2["ood_a labels"], f["ood::ood_a labels"])
+    with pytest.raises(ValueError, match="num_classes greater than 21"):
+        calculate_all_baselines(["gen"], {}, {}, None, cfg, 22)
