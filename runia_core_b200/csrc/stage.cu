@@ -47,8 +47,14 @@ static inline void cpu_relax() {
 // claims pieces of the current chunk with one fetch_add; a chunk is done when `done_` reaches its piece count.
 // The caller never waits for a worker to WAKE UP: if the workers are asleep it simply copies the pieces itself
 // (the speed of a plain cudaMemcpy from pageable memory) and they join as they arrive.  After their last piece the
-// workers spin for `spin_us_` before they go back to sleep on the condition variable, so that back-to-back calls
-// (a sweep of postprocess() calls, the chunks of one large upload) always find them hot.
+// workers spin for `spin_us_` before they go back to sleep on the condition variable, so that the chunks of one
+// upload and back-to-back postprocess() calls find them hot (a futex wake-up costs 100-300 us on the B200 boxes'
+// virtual CPUs: with sleeping workers a 20 MB call takes 1.1-2.3 ms, with hot ones 0.6 ms; plain cudaMemcpy: 1.0 ms).
+// Measured trade-off (profiles/r2_h2d_probe.jsonl, scripts/sweep_probe.py, 16 vCPUs): 4 threads already reach the PCIe
+// rate (51 GB/s on 20 MB, 42-52 GB/s on 1 GB); with 8 threads and a 2 ms spin the MEDIAN call is the same but one
+// call in ten waits 5-15 ms for a worker that was descheduled while it held a claimed piece (the host also runs the
+// BLAS threads of the callers' fits).  The caller must wait for such a straggler -- it reads the caller's buffer, which
+// may be unmapped the moment the call returns -- so the defaults keep the number of spinning threads small.
 class Stager {
  public:
   static Stager &get() {  // one engine per device (its events belong to that device's context)
@@ -97,7 +103,7 @@ class Stager {
       busy_[s] = false;
     }
     unsigned hw = std::thread::hardware_concurrency();
-    int n = hw >= 16 ? 7 : hw >= 8 ? 3 : hw >= 4 ? 1 : 0;  // + the calling thread
+    int n = hw >= 8 ? 3 : hw >= 4 ? 1 : 0;  // + the calling thread (measured: 4 threads reach PCIe rate, see below)
     if (const char *e = getenv("RUNIA_B200_STAGE_THREADS")) n = std::max(0, atoi(e) - 1);
     if (const char *e = getenv("RUNIA_B200_STAGE_SPIN_US")) spin_us_ = std::max(0, atoi(e));
     for (int i = 0; i < n; ++i) workers_.emplace_back([this] { worker(); });
@@ -187,7 +193,7 @@ class Stager {
   std::condition_variable cv_;
   std::atomic<bool> stop_{false};
   bool ready_ = false;
-  int spin_us_ = 2000;
+  int spin_us_ = 1000;  // keeps the workers hot across back-to-back calls; see the measurements above
   uint64_t gen_ = 0;
   std::atomic<uint64_t> ticket_{0};
   std::atomic<uint32_t> done_[4];
