@@ -8,6 +8,7 @@
 // distance" proves that no rejected row could belong to the top-k.  Rows that fail the proof
 // (near-duplicates at rank k) go through an exhaustive exact pass.
 #include <algorithm>
+#include <mutex>
 
 #include "rowgemm.cuh"
 
@@ -213,6 +214,7 @@ knn_candidates_kernel(const float *__restrict__ Q, const float *__restrict__ qn,
 // --------------------------------------------------------------------------------------------
 struct KnnRerankArgs {
   const float *Q, *B;
+  int64_t row0;  // this launch covers query rows [row0, Nq)
   int64_t Nq, Nb;
   int d, k;
   KnnPlan plan;
@@ -238,7 +240,7 @@ constexpr int RERANK_WARPS = 8;  // at most; fewer for large kcap (the per-warp 
 __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerankArgs a) {
   extern __shared__ unsigned char dyn[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  const int64_t row = a.row0 + (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= a.Nq) return;
   const int kcap = a.plan.kcap, S = a.plan.splits, capp = a.plan.capp;
   const int nbuf_max = 2 * kcap;
@@ -671,12 +673,35 @@ static KnnWorkspace knn_layout(int64_t Nq, const KnnPlan &p) {
   return w;
 }
 
+// One side stream + events per device for the fork / join inside runia_knn_search_f32 (re-rank of one query group
+// beside the candidate pass of the next).  Work on it is ordered after an event of the caller's stream and the
+// caller's stream waits for it before the call's last kernel, so the entry point stays "asynchronous on `stream`".
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}, done = nullptr;
+  static SideStream *get() {
+    static SideStream per_dev[16];
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SideStream &s = per_dev[dev & 15];
+    std::lock_guard<std::mutex> lk(mu);
+    if (!s.stream) {
+      if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      for (auto &e : s.ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return &s;
+  }
+};
+
 namespace tc {
 bool usable(const void *A, int K, const void *B_hi, const void *B_lo);
 int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                              const float *bn, int64_t Nb, int d, int kcap, int fin_max, int capp, int splits,
                              int64_t panels_per_split, float *buf_d, int32_t *buf_i, int32_t *counts,
-                             uint32_t *thr_key, cudaStream_t st);
+                             uint32_t *thr_key, const uint32_t *bn_max, cudaStream_t st);
 int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                           const float *bn, int64_t Nb, int d, float scale, int splits, int64_t panels_per_split,
                           float *part_m, float *part_s, cudaStream_t st);
@@ -765,24 +790,8 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   max_sqnorm_kernel<<<(unsigned)std::min<int64_t>(ceil_div(Nb, 256 * 8), 4 * kNumSMs), 256, 0, st>>>(
       Bn_sqnorm, Nb, (uint32_t *)flag_count + 1);
 
-  if (tensor) {
-    const int rc = tc::launch_knn_candidates_tc(Qn, qn, Nq, Bn_hi, Bn_lo, Bn_sqnorm, Nb, d, plan.kcap, plan.fin_max,
-                                                plan.capp, plan.splits, plan.panels_per_split, buf_d, buf_i,
-                                                (int32_t *)(ws + w.counts), (uint32_t *)(ws + w.thr_key), st);
-    if (rc) return rc;
-  } else {
-    const size_t dyn1 = (size_t)8 * plan.capp * 8;
-    static PerDeviceFlag attr1;
-    if (!attr1) {
-      RUNIA_CUDA(cudaFuncSetAttribute(knn_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
-      attr1 = true;
-    }
-    dim3 grid1((unsigned)ceil_div(Nq, BM), (unsigned)plan.splits);
-    knn_candidates_kernel<<<grid1, GEMM_THREADS, dyn1, st>>>(Qn, qn, Nq, Bn, Bn_sqnorm, Nb, d, plan, buf_d, buf_i);
-  }
-
   KnnRerankArgs a;
-  a.Q = Qn; a.B = Bn; a.Nq = Nq; a.Nb = Nb; a.d = d; a.k = k; a.plan = plan;
+  a.Q = Qn; a.B = Bn; a.row0 = 0; a.Nq = Nq; a.Nb = Nb; a.d = d; a.k = k; a.plan = plan;
   a.buf_d = buf_d; a.buf_i = buf_i;
   a.counts = plan.counted ? (const int32_t *)(ws + w.counts) : nullptr;
   // |approx - exact| <= (2K + 8) * 2^-24 for unit-norm rows (DESIGN.md "kNN certification")
@@ -805,9 +814,73 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
     RUNIA_CUDA(cudaFuncSetAttribute(knn_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr2 = true;
   }
-  knn_rerank_kernel<<<(unsigned)ceil_div(Nq, rw), rw * 32, dyn2, st>>>(a);
+  auto rerank = [&](int64_t r0, int64_t r1, cudaStream_t s2) {
+    KnnRerankArgs g = a;
+    g.row0 = r0;
+    g.Nq = r1;
+    knn_rerank_kernel<<<(unsigned)ceil_div(r1 - r0, rw), rw * 32, dyn2, s2>>>(g);
+    count_launch();
+  };
+
+  if (tensor) {
+    // Query groups: the candidate pass of group g + 1 (tensor-bound, one CTA pair per SM pair) runs while the
+    // re-rank of group g (gather- and latency-bound, small blocks) runs on a side stream.  The number of groups is the
+    // largest of 1..4 whose launches still fill whole waves of the 74 CTA-pair slots.
+    const int64_t tiles = ceil_div(Nq, 256);
+    const int64_t slots = kNumSMs / 2;
+    int groups = 1;
+    double best = 0.0;
+    for (int g = 1; g <= 4 && g <= tiles; ++g) {
+      int64_t waves = 0;
+      for (int i = 0; i < g; ++i) {
+        const int64_t t = tiles / g + (i < tiles % g ? 1 : 0);
+        waves += ceil_div(t * plan.splits, slots);
+      }
+      const double eff = (double)(tiles * plan.splits) / (double)(waves * slots);
+      if (eff >= best - 0.03) {  // prefer more groups unless they cost more than 3 % of wave efficiency
+        if (eff > best) best = eff;
+        groups = g;
+      }
+    }
+    SideStream *side = groups > 1 ? SideStream::get() : nullptr;
+    if (groups > 1 && !side) groups = 1;
+    int64_t t0 = 0;
+    for (int g = 0; g < groups; ++g) {
+      const int64_t t1 = t0 + tiles / groups + (g < tiles % groups ? 1 : 0);
+      const int64_t r0 = t0 * 256, r1 = std::min<int64_t>(Nq, t1 * 256);
+      const size_t boff = (size_t)r0 * plan.splits * plan.capp;
+      const int rc = tc::launch_knn_candidates_tc(Qn + r0 * d, qn + r0, r1 - r0, Bn_hi, Bn_lo, Bn_sqnorm, Nb, d, plan.kcap,
+                                                  plan.fin_max, plan.capp, plan.splits, plan.panels_per_split,
+                                                  buf_d + 2 * boff, buf_i, (int32_t *)(ws + w.counts) + r0 * plan.splits,
+                                                  (uint32_t *)(ws + w.thr_key) + r0, (const uint32_t *)flag_count + 1, st);
+      if (rc) return rc;
+      if (side && g + 1 < groups) {  // the last group's re-rank has nothing left to hide behind
+        RUNIA_CUDA(cudaEventRecord(side->ev[g], st));
+        RUNIA_CUDA(cudaStreamWaitEvent(side->stream, side->ev[g], 0));
+        rerank(r0, r1, side->stream);
+      } else {
+        rerank(r0, r1, st);
+      }
+      t0 = t1;
+    }
+    if (side && groups > 1) {  // join: the exhaustive pass needs every group's flags
+      RUNIA_CUDA(cudaEventRecord(side->done, side->stream));
+      RUNIA_CUDA(cudaStreamWaitEvent(st, side->done, 0));
+    }
+  } else {
+    const size_t dyn1 = (size_t)8 * plan.capp * 8;
+    static PerDeviceFlag attr1;
+    if (!attr1) {
+      RUNIA_CUDA(cudaFuncSetAttribute(knn_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
+      attr1 = true;
+    }
+    dim3 grid1((unsigned)ceil_div(Nq, BM), (unsigned)plan.splits);
+    knn_candidates_kernel<<<grid1, GEMM_THREADS, dyn1, st>>>(Qn, qn, Nq, Bn, Bn_sqnorm, Nb, d, plan, buf_d, buf_i);
+    count_launch();
+    rerank(0, Nq, st);
+  }
   knn_fallback_kernel<<<FB_GRID, FB_THREADS, 0, st>>>(a, status, (double *)(ws + w.fb_d), (int32_t *)(ws + w.fb_i));
-  count_launch(5);
+  count_launch(3);
   return finish_launch("knn_search");
 }
 

@@ -244,7 +244,9 @@ struct Work {
 // an instruction costs its fixed minimum, not its FLOPs).  Accumulator columns: [0, TNV/2) hi x classes of CTA 0,
 // [TNV/2, TNV) lo x the same classes, [TNV, 3TNV/2) hi x classes of CTA 1, [3TNV/2, 2TNV) lo x those; [2TNV, 3TNV)
 // A_lo x B_hi in class order.  The epilogue receives all 3 TNV columns and adds the three products.
-template <class E, int TNV = TN, int NSTAGES = STAGES, bool NCAT = false>
+// NPROD = 1 (the kNN seed only): a single TF32 product A_hi x B_hi -- a third of the MMAs, no B_lo traffic, no A_lo
+// store; the caller widens whatever it derives from the result by the split's rounding bound (see KnnSeedEpi).
+template <class E, int TNV = TN, int NSTAGES = STAGES, bool NCAT = false, int NPROD = 3>
 __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const Prologue pro,
                                           const CUtensorMap *tmB_hi, const CUtensorMap *tmB_lo, const Work work,
                                           E &epi, unsigned char *smem_raw) {
@@ -324,10 +326,10 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
             mbar_wait(empty_bar(s), ph ^ 1);
             mbar_expect_tx(raw_bar(s), A_PLANE_BYTES);
             tma_load_2d_local(sA_hi(s), tmA, raw_bar(s), kb * TK, row0);
-            if (rank == 0) mbar_expect_tx(full_bar(s), 4 * (TNV / 2) * TK * 4);  // both planes, both CTAs
+            if (rank == 0) mbar_expect_tx(full_bar(s), (NPROD == 1 ? 2 : 4) * (TNV / 2) * TK * 4);  // plane(s) of both CTAs
             const uint32_t lbar = map_to_cta(full_bar(s), 0);
             tma_load_2d_pair(sB_hi(s), tmB_hi, lbar, kb * TK, n0);
-            tma_load_2d_pair(sB_lo(s), tmB_lo, lbar, kb * TK, n0);
+            if constexpr (NPROD != 1) tma_load_2d_pair(sB_lo(s), tmB_lo, lbar, kb * TK, n0);
           }
         }
       }
@@ -354,7 +356,9 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
 #pragma unroll
             for (int k4 = 0; k4 < TK / 8; ++k4) {
               const uint64_t adv = (uint64_t)((k4 * 8 * 4) >> 4);  // 32 bytes per UMMA_K=8 step
-              if constexpr (NCAT) {
+              if constexpr (NPROD == 1) {
+                umma_tf32(tacc, dA_hi + adv, dB_hi + adv, InstrDesc<TNV>::value, (kb | k4) != 0 ? 1u : 0u);
+              } else if constexpr (NCAT) {
                 umma_tf32(tacc, dA_hi + adv, dB_hi + adv, InstrDesc<2 * TNV>::value, (kb | k4) != 0 ? 1u : 0u);
                 umma_tf32(tacc + 2 * TNV, dA_lo + adv, dB_hi + adv, InstrDesc<TNV>::value, (kb | k4) != 0 ? 1u : 0u);
               } else {
@@ -440,9 +444,10 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + (uint32_t)i * 4096u), "f"(h[0]), "f"(h[1]),
                      "f"(h[2]), "f"(h[3])
                      : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + (uint32_t)i * 4096u), "f"(l[0]), "f"(l[1]),
-                     "f"(l[2]), "f"(l[3])
-                     : "memory");
+        if constexpr (NPROD != 1)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + (uint32_t)i * 4096u), "f"(l[0]), "f"(l[1]),
+                       "f"(l[2]), "f"(l[3])
+                       : "memory");
       }
       fence_proxy_async();  // make the generic-proxy stores visible to the tensor core
       __syncwarp();

@@ -614,10 +614,17 @@ struct KnnEpi {
 // kcap bank rows at distance <= B, so the main pass starts with the threshold nextafter(B) and only
 // ever buffers rows that can still matter.  Groups are independent: they are split over several CTA
 // pairs and combined with an atomic max on the order-preserving key.
+// The seed contraction is a SINGLE TF32 product (A_hi x B_hi): its distances differ from the 3xTF32 ones the candidate
+// pass compares with the threshold by at most kSeedSlack * (|q|^2 + max|b|^2) / 2 (A_hi is a 19-bit truncation: 2^-10
+// relative, B_hi rounds to nearest: 2^-11; |q.b| <= (|q|^2 + |b|^2) / 2; doubled for the -2 q.b term), so the bound is
+// widened by that much and stays an upper bound on the kcap-th smallest 3xTF32 distance.
+constexpr float kSeedSlack = 3.2e-3f;
+
 struct KnnSeedEpi {
   const float *qn, *bn;
   int64_t Nq, b_hi;
   uint32_t *thr_key;
+  const uint32_t *bn_max;  // [1] bit pattern of max_b |b|^2
   int ppg;  // panels per group
   int64_t row;
   float q2, m0, m1, m2, m3, bound;
@@ -675,6 +682,7 @@ struct KnnSeedEpi {
   __device__ void finish() {
     if (!live) return;
     if (in_group != 0) bound = INFINITY;  // a partial group proves nothing (the launcher never produces one)
+    bound += kSeedSlack * 0.5f * (q2 + __uint_as_float(__ldg(bn_max)));
     const uint32_t key = ord_key(bound);
     atomicMax(thr_key + row, key < 0xfffffffeu ? key + 1u : key);  // exclusive bound: the filter is strict
   }
@@ -691,7 +699,7 @@ tc_knn_seed_kernel(const __grid_constant__ CUtensorMap tmA, int K, const __grid_
   w.panel_lo = (int)blockIdx.y * panels_per_split;
   w.panel_hi = min(seed_panels, w.panel_lo + panels_per_split);
   const Prologue pro{nullptr, INFINITY};
-  run_tiles(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
+  run_tiles<KnnSeedEpi, TN, STAGES, false, 1>(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
 template <class E>
@@ -1120,7 +1128,7 @@ namespace tc {
 int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                              const float *bn, int64_t Nb, int d, int kcap, int fin_max, int capp, int splits,
                              int64_t panels_per_split, float *buf_d, int32_t *buf_i, int32_t *counts,
-                             uint32_t *thr_key, cudaStream_t st) {
+                             uint32_t *thr_key, const uint32_t *bn_max, cudaStream_t st) {
   CUtensorMap ma, mh, ml;
   int rc = make_a_map(&ma, Q, Nq, d);
   if (rc) return rc;
@@ -1154,7 +1162,7 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
     ss = (int)ceil_div(groups, gps);
     const int pps = gps * ppg;
     KnnSeedEpi seed{};
-    seed.qn = qn; seed.bn = bn; seed.Nq = Nq; seed.b_hi = Nb; seed.thr_key = thr_key; seed.ppg = ppg;
+    seed.qn = qn; seed.bn = bn; seed.Nq = Nq; seed.b_hi = Nb; seed.thr_key = thr_key; seed.bn_max = bn_max; seed.ppg = ppg;
     dim3 grid0(2 * (unsigned)tiles, (unsigned)ss);
     tc_knn_seed_kernel<<<grid0, THREADS, smem, st>>>(ma, d, mh, ml, seed_panels, pps, seed);
     count_launch();
