@@ -35,7 +35,7 @@ def ptr(t):
 
 
 PIPE_MIN_BYTES = 256 << 10                                                    # below this a plain copy is as fast
-PIPE_CHUNK_BYTES = int(os.environ.get("RUNIA_B200_PIPE_CHUNK_BYTES", 32 << 20))  # rows per kernel launch when streaming
+PIPE_CHUNK_BYTES = int(os.environ.get("RUNIA_B200_PIPE_CHUNK_BYTES", 64 << 20))  # rows per kernel launch when streaming
 
 
 class HostPipe:

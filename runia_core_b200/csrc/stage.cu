@@ -50,11 +50,11 @@ static inline void cpu_relax() {
 // workers spin for `spin_us_` before they go back to sleep on the condition variable, so that the chunks of one
 // upload and back-to-back postprocess() calls find them hot (a futex wake-up costs 100-300 us on the B200 boxes'
 // virtual CPUs: with sleeping workers a 20 MB call takes 1.1-2.3 ms, with hot ones 0.6 ms; plain cudaMemcpy: 1.0 ms).
-// Measured trade-off (profiles/r2_h2d_probe.jsonl, scripts/sweep_probe.py, 16 vCPUs): 4 threads already reach the PCIe
-// rate (51 GB/s on 20 MB, 42-52 GB/s on 1 GB); with 8 threads and a 2 ms spin the MEDIAN call is the same but one
-// call in ten waits 5-15 ms for a worker that was descheduled while it held a claimed piece (the host also runs the
-// BLAS threads of the callers' fits).  The caller must wait for such a straggler -- it reads the caller's buffer, which
-// may be unmapped the moment the call returns -- so the defaults keep the number of spinning threads small.
+// Measured trade-off (profiles/r2_h2d_probe.jsonl, scripts/sweep_probe.py, 16 vCPUs): 4 threads reach the PCIe rate on
+// a 20 MB call (51 GB/s) but only 29 GB/s on 1 GB, 8 threads 52 GB/s on both; with 8 spinning threads one 20 MB call in
+// ten waits 5-15 ms for a worker that was descheduled while it held a claimed piece (the host also runs the BLAS
+// threads of the callers' fits).  The caller must wait for such a straggler -- it reads the caller's buffer, which may
+// be unmapped the moment the call returns -- so uploads below 32 MB enlist three workers, longer ones all seven.
 class Stager {
  public:
   static Stager &get() {  // one engine per device (its events belong to that device's context)
@@ -70,6 +70,10 @@ class Stager {
     if (rc) return rc;
     const char *src = static_cast<const char *>(src_host);
     char *dst = static_cast<char *>(dst_dev);
+    // 4 threads reach the PCIe rate on a 20 MB call and keep the number of spinning threads small (fewer stragglers);
+    // a long upload needs 8 to stay at 50 GB/s (4 threads: 29 GB/s on 1 GB) and can absorb a straggler in its ring
+    active_.store(bytes >= (32u << 20) ? (int)workers_.size() : std::min<int>(3, (int)workers_.size()),
+                  std::memory_order_relaxed);
     for (size_t off = 0; off < bytes; off += kSlotBytes) {
       const size_t n = bytes - off < kSlotBytes ? bytes - off : kSlotBytes;
       const int s = next_slot_;
@@ -103,10 +107,10 @@ class Stager {
       busy_[s] = false;
     }
     unsigned hw = std::thread::hardware_concurrency();
-    int n = hw >= 8 ? 3 : hw >= 4 ? 1 : 0;  // + the calling thread (measured: 4 threads reach PCIe rate, see below)
+    int n = hw >= 16 ? 7 : hw >= 8 ? 3 : hw >= 4 ? 1 : 0;  // + the calling thread; small uploads enlist only three of them
     if (const char *e = getenv("RUNIA_B200_STAGE_THREADS")) n = std::max(0, atoi(e) - 1);
     if (const char *e = getenv("RUNIA_B200_STAGE_SPIN_US")) spin_us_ = std::max(0, atoi(e));
-    for (int i = 0; i < n; ++i) workers_.emplace_back([this] { worker(); });
+    for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { worker(i); });
     ready_ = true;
     return RUNIA_OK;
   }
@@ -166,12 +170,12 @@ class Stager {
     while (done_[g & 3].load(std::memory_order_acquire) != np) cpu_relax();
   }
 
-  void worker() {
+  void worker(int idx) {
     using clock = std::chrono::steady_clock;
     auto last = clock::now();
     for (;;) {
       if (stop_.load(std::memory_order_relaxed)) return;
-      if (claim_loop()) {
+      if (idx < active_.load(std::memory_order_relaxed) && claim_loop()) {
         last = clock::now();
         continue;
       }
@@ -182,7 +186,9 @@ class Stager {
       sleepers_.fetch_add(1, std::memory_order_seq_cst);
       {
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait_for(lk, std::chrono::milliseconds(100), [&] { return stop_.load() || work_available(); });
+        cv_.wait_for(lk, std::chrono::milliseconds(100), [&] {
+          return stop_.load() || (idx < active_.load(std::memory_order_relaxed) && work_available());
+        });
       }
       sleepers_.fetch_sub(1, std::memory_order_seq_cst);
       last = clock::now();
@@ -198,6 +204,7 @@ class Stager {
   std::atomic<uint64_t> ticket_{0};
   std::atomic<uint32_t> done_[4];
   std::atomic<int> sleepers_{0};
+  std::atomic<int> active_{0};  // workers [0, active_) take part in the current upload
   Desc ring_[4];
   std::vector<std::thread> workers_;
   char *slot_[kSlots] = {nullptr, nullptr, nullptr, nullptr};
