@@ -322,6 +322,26 @@ int runia_centered_gram_f64(const float *X, const int32_t *labels, const float *
 size_t runia_mc_dropblock_workspace_bytes(int B, int H, int W, int n_mc);
 int runia_mc_dropblock_mean_f32(const float *x, const uint8_t *seed, int B, int C, int H, int W, int n_mc,
                                 int block_size, float *out, void *workspace, size_t workspace_bytes, void *stream);
+/* The same sampler for layer_type "FC" / "RPN" (no spatial reduction): out [n_mc, B * C * H * W] =
+ * x * block_mask(m) * (B * H * W) / sum(block_mask(m)), the mask normalised over the whole batch like DropBlock2D. */
+int runia_mc_dropblock_apply_f32(const float *x, const uint8_t *seed, int B, int C, int H, int W, int n_mc,
+                                 int block_size, float *out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (f3) Object-level reducers -- feature_extraction/object_level.py:254-309 (`_reduce_features_to_rois`) and :312-366
+ * (`_dropblock_rois_get_entropy`): torchvision.ops.roi_align(feat, [boxes], output_size, spatial_scale,
+ * sampling_ratio, aligned) and the per-(box, channel) mean / unbiased std over the pooled bins.
+ *   feat [B, C, H, W] float32; boxes [K, 4] float32 xyxy in image coordinates; batch_idx [K] int32 (NULL: image 0)
+ *   sampling_ratio <= 0: adaptive ceil(roi_size / pooled_size) like torchvision; aligned: half-pixel shift
+ *   runia_roi_align_f32: out [K, C, pooled_h, pooled_w]
+ *   runia_roi_align_mean_f32: out_mean [K, C], out_std [K, C] (nullable), the maps are never materialised
+ */
+int runia_roi_align_f32(const float *feat, int B, int C, int H, int W, const float *boxes, const int32_t *batch_idx,
+                        int64_t K, int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, int aligned,
+                        float *out, void *stream);
+int runia_roi_align_mean_f32(const float *feat, int B, int C, int H, int W, const float *boxes, const int32_t *batch_idx,
+                             int64_t K, int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, int aligned,
+                             float *out_mean, float *out_std, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host -> device staging of PAGEABLE host memory (the NumPy arrays the reference's callers hand to postprocess(),

@@ -74,6 +74,7 @@ _SIGS = {
     "runia_centered_gram_f64": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "runia_mc_dropblock_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "runia_mc_dropblock_mean_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
+    "runia_mc_dropblock_apply_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "runia_logit_scores_f32": (c_int, [_P, c_int64, c_int, c_float, c_int, _P, _P, _P, _P]),
     "runia_clip_linear_lse_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, c_float, _P, _P]),
     "runia_tf32_peak_probe": (c_int, [c_int, _P, _P]),
@@ -83,6 +84,10 @@ _SIGS = {
     "runia_gen_entropy_f32": (c_int, [_P, c_int64, c_int, c_float, c_int, _P, _P]),
     "runia_linear_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P]),
     "runia_stage_h2d": (c_int, [_P, _P, c_int64, _P]),
+    "runia_roi_align_f32": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int64, c_int, c_int, c_float, c_int, c_int,
+                                    _P, _P]),
+    "runia_roi_align_mean_f32": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int64, c_int, c_int, c_float, c_int,
+                                         c_int, _P, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)
 

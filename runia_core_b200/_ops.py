@@ -781,3 +781,52 @@ def mc_dropblock_mean(x, seed, block_size: int) -> torch.Tensor:
     _lib.call("runia_mc_dropblock_mean_f32", xf.data_ptr(), sd.data_ptr(), B, C, H, W, n_mc, int(block_size), out.data_ptr(),
               ws.data_ptr(), ws_bytes, stream_ptr())
     return out
+
+
+def mc_dropblock_apply(x, seed, block_size: int) -> torch.Tensor:
+    """x [B, C, H, W] float32, seed [n_mc, B, H, W] -> [n_mc, B * C * H * W]: the DropBlock2D-masked, renormalised maps
+    themselves (MCSamplerModule layer types "FC" / "RPN")."""
+    xf = to_device(x, torch.float32)
+    sd = seed.to(device=device(), dtype=torch.uint8).contiguous() if isinstance(seed, torch.Tensor) else \
+        torch.from_numpy(np.ascontiguousarray(np.asarray(seed) != 0).astype(np.uint8)).to(device())
+    B, C, H, W = xf.shape
+    n_mc = sd.shape[0]
+    out = _empty((n_mc, B * C * H * W), torch.float32)
+    ws_bytes = int(_lib.raw("runia_mc_dropblock_workspace_bytes")(B, H, W, n_mc))
+    ws = _empty((ws_bytes,), torch.uint8)
+    _lib.call("runia_mc_dropblock_apply_f32", xf.data_ptr(), sd.data_ptr(), B, C, H, W, n_mc, int(block_size),
+              out.data_ptr(), ws.data_ptr(), ws_bytes, stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# (f3) object-level reducers: RoIAlign maps and their per-channel means
+# ------------------------------------------------------------------------------------------
+def _roi_args(feat, boxes, output_size):
+    x = to_device(feat, torch.float32)
+    if x.dim() == 3:
+        x = x.unsqueeze(0)
+    bx = to_device(boxes, torch.float32).reshape(-1, 4).contiguous()
+    ph, pw = (output_size, output_size) if isinstance(output_size, int) else tuple(output_size)
+    return x, bx, int(ph), int(pw)
+
+
+def roi_align(feat, boxes, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=False) -> torch.Tensor:
+    """torchvision.ops.roi_align(feat, [boxes], ...) for the boxes of image 0: [K, C, P, P] float32."""
+    x, bx, ph, pw = _roi_args(feat, boxes, output_size)
+    B, C, H, W = x.shape
+    out = _empty((bx.shape[0], C, ph, pw), torch.float32)
+    _lib.call("runia_roi_align_f32", x.data_ptr(), B, C, H, W, bx.data_ptr(), None, bx.shape[0], ph, pw,
+              float(spatial_scale), int(sampling_ratio), 1 if aligned else 0, out.data_ptr(), stream_ptr())
+    return out
+
+
+def roi_align_mean(feat, boxes, output_size, spatial_scale=1.0, sampling_ratio=-1, aligned=False, want_std=False):
+    """mean (and unbiased std) over the pooled bins of every (box, channel): ([K, C], [K, C] or None) float32."""
+    x, bx, ph, pw = _roi_args(feat, boxes, output_size)
+    B, C, H, W = x.shape
+    mean = _empty((bx.shape[0], C), torch.float32)
+    std = _empty((bx.shape[0], C), torch.float32) if want_std else None
+    _lib.call("runia_roi_align_mean_f32", x.data_ptr(), B, C, H, W, bx.data_ptr(), None, bx.shape[0], ph, pw,
+              float(spatial_scale), int(sampling_ratio), 1 if aligned else 0, mean.data_ptr(), ptr(std), stream_ptr())
+    return mean, std

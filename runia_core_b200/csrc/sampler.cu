@@ -153,6 +153,24 @@ static int launch_sampler(const float *x, const float *maskT, const int *kept, i
 
 static int nmc_padded(int n_mc) { return n_mc <= 8 ? 8 : (n_mc <= 16 ? 16 : 32); }
 
+// "FC" / "RPN" layers (feature_extraction/abstract_classes.py:81-101 without the spatial mean): the masked maps
+// themselves, out[m, ((b * C + c) * HW + p)] = x[b, c, p] * mask(m, b, p) * (B * HW) / sum_{b, p} mask(m, ., .)
+// (DropBlock2D normalises over the whole batch mask it is given).
+__global__ void __launch_bounds__(256)
+dropblock_apply_kernel(const float *__restrict__ x, const float *__restrict__ maskT, const int *__restrict__ kept, int B, int C,
+                       int HW, int n_mc, int nmc_pad, float *__restrict__ out) {
+  const int64_t per = (int64_t)B * C * HW, total = per * n_mc;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(e / per);
+    const int64_t r = e - (int64_t)m * per;
+    const int p = (int)(r % HW), b = (int)(r / ((int64_t)C * HW));
+    int tot = 0;
+    for (int bb = 0; bb < B; ++bb) tot += kept[(size_t)m * B + bb];
+    const float mk = maskT[((size_t)b * HW + p) * nmc_pad + m];
+    out[e] = __ldg(x + r) * mk * (float)((int64_t)B * HW) / (float)tot;  // tot == 0: 0 * inf = NaN, like upstream
+  }
+}
+
 }  // namespace runia
 
 using namespace runia;
@@ -192,4 +210,27 @@ extern "C" int runia_mc_dropblock_mean_f32(const float *x, const uint8_t *seed, 
   if (rc != RUNIA_OK) return rc;
   count_launch(2);
   return finish_launch("mc_dropblock");
+}
+
+extern "C" int runia_mc_dropblock_apply_f32(const float *x, const uint8_t *seed, int B, int C, int H, int W, int n_mc,
+                                            int block_size, float *out, void *ws, size_t ws_bytes, void *stream) {
+  RUNIA_NVTX();
+  RUNIA_REQUIRE(B >= 1 && C >= 1 && H >= 1 && W >= 1 && n_mc >= 1 && block_size >= 1, RUNIA_E_BADARG,
+                "mc_dropblock_apply: needs B, C, H, W, n_mc, block_size >= 1");
+  RUNIA_REQUIRE(n_mc <= 32, RUNIA_E_UNSUPPORTED, "mc_dropblock_apply: n_mc=%d not supported (max 32)", n_mc);
+  RUNIA_REQUIRE(x && seed && out && ws, RUNIA_E_BADARG, "mc_dropblock_apply: null pointer");
+  const size_t need = runia_mc_dropblock_workspace_bytes(B, H, W, n_mc);
+  RUNIA_REQUIRE(ws_bytes >= need, RUNIA_E_BADARG, "mc_dropblock_apply: workspace of %zu bytes, %zu needed", ws_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = H * W, pad = nmc_padded(n_mc);
+  const size_t kept_bytes = (((size_t)n_mc * B * sizeof(int)) + 255) / 256 * 256;
+  int *kept = (int *)ws;
+  float *maskT = (float *)((char *)ws + kept_bytes);
+  RUNIA_CUDA(cudaMemsetAsync(ws, 0, need, st));
+  dropblock_mask_kernel<<<(unsigned)(n_mc * B), 128, 0, st>>>(seed, B, H, W, block_size, pad, maskT, kept);
+  const int64_t total = (int64_t)n_mc * B * C * HW;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)kNumSMs * 16);
+  dropblock_apply_kernel<<<grid, 256, 0, st>>>(x, maskT, kept, B, C, HW, n_mc, pad, out);
+  count_launch(2);
+  return finish_launch("mc_dropblock_apply");
 }

@@ -50,24 +50,11 @@ class MCSamplerModule(torch.nn.Module):
         """Reference semantics (one image per call): "Conv": [1, C, H, W] -> [n_mc, C] (fused kernel);
         "FC" / "RPN": the unreduced masked maps [n_mc, numel]."""
         if self.layer_type != "Conv":
-            # "FC" / "RPN": the masked maps themselves, flattened ([n_mc, B*C*H*W]); no reduction follows, so this is
-            # DropBlock2D's published forward in torch ops on the same seeds (not a hot path: nothing downstream
-            # of it is on the scoring path of SURVEY section 8)
-            import torch.nn.functional as F
-
+            # "FC" / "RPN": the masked maps themselves, flattened ([n_mc, B*C*H*W]); no reduction follows
             if not self.training or self.drop_prob == 0.0:
                 return latent_rep.reshape(1, -1).repeat(self.mc_samples, 1)
-            seeds = self.draw_seeds(latent_rep).to(latent_rep.device)
-            bs = self.block_size
-            out = []
-            for m in range(self.mc_samples):
-                bm = F.max_pool2d(seeds[m].float()[:, None], kernel_size=(bs, bs), stride=(1, 1), padding=bs // 2)
-                if bs % 2 == 0:
-                    bm = bm[:, :, :-1, :-1]
-                bm = 1 - bm.squeeze(1)
-                o = latent_rep * bm[:, None, :, :]
-                out.append((o * bm.numel() / bm.sum()).reshape(1, -1))
-            return torch.cat(out)
+            out = _ops.mc_dropblock_apply(latent_rep, self.draw_seeds(latent_rep), self.block_size)
+            return out if latent_rep.is_cuda else out.cpu()
         rows = self.sample_batch(latent_rep)
         if latent_rep.shape[0] == 1:
             return rows

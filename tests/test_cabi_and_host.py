@@ -298,36 +298,30 @@ def test_widening_boundary_signatures_and_argument_checks():
         get_mean_or_fullmean_ls_sample(torch.zeros(2, 3, 4, 5), method="median")
 
 
-def test_mc_sampler_module_fc_layer_and_seed_stream():
+def test_mc_sampler_module_seed_stream():
     """MCSamplerModule (feature_extraction/abstract_classes.py:32-101): the seeds are the n_mc sequential
-    `torch.rand(B, H, W) < drop_prob / block_size**2` draws of the DropBlock2D layers; "FC" / "RPN" return the
-    masked maps unreduced (host-only path, no CUDA needed)."""
+    `torch.rand(B, H, W) < drop_prob / block_size**2` draws of the DropBlock2D layers (drawn here with ONE
+    `torch.rand(n_mc, B, H, W)`: torch's CPU uniform_ fills serially from the generator, so the stream is the same);
+    eval mode is the identity (host-only paths, no CUDA needed)."""
     import torch
-    import torch.nn.functional as F
 
     from runia_core_b200.feature_extraction import MCSamplerModule
 
-    n_mc, bs, p = 5, 2, 0.4
-    smp = MCSamplerModule(mc_samples=n_mc, block_size=bs, drop_prob=p, layer_type="FC").train()
-    x = torch.randn(1, 6, 5, 4)
-    torch.manual_seed(3)
-    got = smp(x)
-    torch.manual_seed(3)
-    rows = []
-    for _ in range(n_mc):
-        mask = (torch.rand(1, 5, 4) < p / bs**2).float()
-        bm = F.max_pool2d(mask[:, None], kernel_size=(bs, bs), stride=(1, 1), padding=bs // 2)[:, :, :-1, :-1]
-        bm = 1 - bm.squeeze(1)
-        out = x * bm[:, None] * bm.numel() / bm.sum()
-        rows.append(out.reshape(1, -1))
-    assert got.shape == (n_mc, 6 * 5 * 4) and torch.equal(got, torch.cat(rows))
-    torch.manual_seed(3)
-    seeds = smp.draw_seeds(x)
-    assert seeds.shape == (n_mc, 1, 5, 4) and seeds.dtype == torch.uint8
+    for shape in ((1, 6, 5, 4), (3, 2, 7, 7), (2, 4, 1, 1), (1, 3, 14, 3)):
+        for n_mc, bs, p in ((5, 2, 0.4), (16, 3, 0.3), (32, 1, 0.9)):
+            smp = MCSamplerModule(mc_samples=n_mc, block_size=bs, drop_prob=p, layer_type="FC").train()
+            x = torch.randn(*shape)
+            torch.manual_seed(3)
+            seeds = smp.draw_seeds(x)
+            torch.manual_seed(3)
+            ref = torch.stack([(torch.rand(shape[0], *shape[2:]) < p / bs**2) for _ in range(n_mc)]).to(torch.uint8)
+            assert seeds.shape == (n_mc, shape[0], *shape[2:]) and seeds.dtype == torch.uint8
+            assert torch.equal(seeds, ref)
     with pytest.raises(AssertionError):
         MCSamplerModule(mc_samples=2, block_size=1, drop_prob=0.1, layer_type="Linear")
-    smp.eval()
-    assert torch.equal(smp(x), x.reshape(1, -1).repeat(n_mc, 1))
+    smp = MCSamplerModule(mc_samples=5, block_size=2, drop_prob=0.4, layer_type="FC").eval()
+    x = torch.randn(1, 6, 5, 4)
+    assert torch.equal(smp(x), x.reshape(1, -1).repeat(5, 1))
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/runia_core/evaluation/baselines.py"),

@@ -151,3 +151,92 @@ def test_folded_pca_larem_matches_staged():
     md2.setup((z_train + 3.0).astype(np.float32))  # a LaREM centre away from the PCA origin
     np.testing.assert_allclose(R.inference.FoldedLaREM(pca, md2).postprocess(test),
                                md2.postprocess(R.apply_pca_transform(test, pca)), rtol=2e-5)
+
+
+@pytest.mark.parametrize("shape,bs", [((1, 6, 5, 4), 2), ((3, 8, 7, 7), 3), ((2, 5, 9, 6), 4)])
+def test_mc_sampler_fc_layer_masked_maps(shape, bs):
+    """layer_type "FC" / "RPN" (abstract_classes.py:81-101 without the reduction): the DropBlock2D-masked maps
+    themselves, normalised over the whole batch mask, == the published DropBlock2D forward on the same seeds."""
+    import torch.nn.functional as F
+
+    from runia_core_b200.feature_extraction import MCSamplerModule
+
+    n_mc, p = 7, 0.4
+    smp = MCSamplerModule(mc_samples=n_mc, block_size=bs, drop_prob=p, layer_type="FC").train()
+    x = torch.randn(*shape)
+    torch.manual_seed(3)
+    got = smp(x.cuda()).cpu()
+    torch.manual_seed(3)
+    rows = []
+    for _ in range(n_mc):
+        mask = (torch.rand(shape[0], *shape[2:]) < p / bs**2).float()
+        bm = F.max_pool2d(mask[:, None], kernel_size=(bs, bs), stride=(1, 1), padding=bs // 2)
+        if bs % 2 == 0:
+            bm = bm[:, :, :-1, :-1]
+        bm = 1 - bm.squeeze(1)
+        rows.append((x * bm[:, None] * bm.numel() / bm.sum()).reshape(1, -1))
+    ref = torch.cat(rows)
+    assert got.shape == ref.shape
+    torch.testing.assert_close(got, ref, rtol=1e-6, atol=1e-6, equal_nan=True)
+
+
+@pytest.mark.parametrize("P,sr,C,H,W", [(7, 2, 64, 25, 34), (14, 2, 16, 50, 68), (7, 0, 8, 13, 17), (5, 4, 33, 10, 10)])
+def test_roi_align_and_object_means_vs_torchvision(P, sr, C, H, W):
+    """object_level.py:254-309: torchvision.ops.roi_align(aligned=True) + per-object mean / std over the RoI, and the
+    RoI maps themselves; boxes that leave the image, degenerate boxes, adaptive sampling (sampling_ratio 0)."""
+    from torchvision.ops import roi_align as tv_roi_align
+
+    from runia_core_b200 import _ops
+    from runia_core_b200.feature_extraction.object_level import _reduce_features_to_rois
+
+    rng = np.random.RandomState(P + C)
+    img_shape = (H * 16, W * 16)
+    feat = torch.from_numpy(rng.randn(1, C, H, W).astype(np.float32))
+    K = 23
+    x1 = rng.rand(K) * img_shape[1] * 0.8
+    y1 = rng.rand(K) * img_shape[0] * 0.8
+    boxes = np.stack([x1, y1, x1 + 8 + rng.rand(K) * img_shape[1] * 0.5, y1 + 8 + rng.rand(K) * img_shape[0] * 0.5], 1)
+    boxes[0] = [-30.0, -20.0, 40.0, 50.0]                       # leaves the image on the top left
+    boxes[1] = [img_shape[1] - 10.0, img_shape[0] - 10.0, img_shape[1] + 90.0, img_shape[0] + 60.0]
+    boxes[2] = [100.0, 100.0, 100.0, 100.0]                     # zero area
+    boxes = torch.from_numpy(boxes.astype(np.float32))
+    scale = W / img_shape[1]
+    ref = tv_roi_align(feat, [boxes], output_size=P, spatial_scale=scale, sampling_ratio=sr, aligned=True)
+    got = _ops.roi_align(feat, boxes, P, scale, sr, aligned=True).cpu()
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+    means, stds = _reduce_features_to_rois([feat.cuda(), (2 * feat).cuda()], (P, P), boxes.cuda(), img_shape, sr, 2, K,
+                                           return_stds=True)
+    assert len(means) == K and means[0].shape == (1, 2 * C)
+    ref_m = torch.cat([ref.mean((2, 3)), 2 * ref.mean((2, 3))], 1)
+    ref_s = torch.cat([ref.std((2, 3)), 2 * ref.std((2, 3))], 1)
+    torch.testing.assert_close(torch.cat(means).cpu(), ref_m, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(torch.cat(stds).cpu(), ref_s, rtol=1e-4, atol=1e-5)
+    ref_na = tv_roi_align(feat, [boxes], output_size=(P, P + 1), spatial_scale=scale, sampling_ratio=sr, aligned=False)
+    got_na = _ops.roi_align(feat, boxes, (P, P + 1), scale, sr, aligned=False).cpu()
+    torch.testing.assert_close(got_na, ref_na, rtol=1e-5, atol=1e-5)
+
+
+def test_dropblock_rois_entropy_chain():
+    """object_level.py:312-366: RoIAlign -> MC-DropBlock per detection -> get_dl_h_z, against the staged public
+    pieces (torchvision RoIs, MCSamplerModule per detection, get_dl_h_z) on the same seeds."""
+    from torchvision.ops import roi_align as tv_roi_align
+
+    import runia_core_b200 as R
+    from runia_core_b200.feature_extraction import MCSamplerModule
+    from runia_core_b200.feature_extraction.object_level import _dropblock_rois_get_entropy
+
+    rng = np.random.RandomState(2)
+    C, H, W, P, K, n_mc = 32, 20, 30, 7, 9, 16
+    img_shape = (H * 8, W * 8)
+    feat = torch.from_numpy(rng.randn(1, C, H, W).astype(np.float32))
+    x1, y1 = rng.rand(K) * 100, rng.rand(K) * 60
+    boxes = torch.from_numpy(np.stack([x1, y1, x1 + 40 + 60 * rng.rand(K), y1 + 30 + 50 * rng.rand(K)], 1).astype(np.float32))
+    smp = MCSamplerModule(mc_samples=n_mc, block_size=3, drop_prob=0.3).train()
+    torch.manual_seed(9)
+    got = _dropblock_rois_get_entropy([feat.cuda()], (P,), boxes.cuda(), img_shape, 2, 1, n_mc, smp)
+    rois = tv_roi_align(feat, [boxes], output_size=P, spatial_scale=W / img_shape[1], sampling_ratio=2, aligned=True)
+    torch.manual_seed(9)
+    rows = torch.cat([smp(det.unsqueeze(0).cuda()) for det in rois])  # upstream's loop: detection after detection
+    _, hz = R.evaluation.get_dl_h_z(rows, n_mc)
+    assert got.shape == (K, C) and got.dtype == torch.float32
+    np.testing.assert_allclose(got.numpy(), hz, rtol=1e-4, atol=1e-4)
