@@ -23,10 +23,10 @@ struct RoiGeom {
 __device__ __forceinline__ RoiGeom roi_geom(const float *box, float scale, int ph, int pw, int sampling_ratio, int aligned) {
   const float off = aligned ? 0.5f : 0.f;
   RoiGeom g;
-  g.start_w = box[0] * scale - off;
-  g.start_h = box[1] * scale - off;
-  float roi_w = box[2] * scale - off - g.start_w;
-  float roi_h = box[3] * scale - off - g.start_h;
+  g.start_w = __fsub_rn(__fmul_rn(box[0], scale), off);
+  g.start_h = __fsub_rn(__fmul_rn(box[1], scale), off);
+  float roi_w = __fsub_rn(__fsub_rn(__fmul_rn(box[2], scale), off), g.start_w);
+  float roi_h = __fsub_rn(__fsub_rn(__fmul_rn(box[3], scale), off), g.start_h);
   if (!aligned) {  // legacy behaviour: RoIs are at least one pixel wide
     roi_w = fmaxf(roi_w, 1.f);
     roi_h = fmaxf(roi_h, 1.f);
@@ -71,16 +71,27 @@ __device__ __forceinline__ void bilinear_setup(float y, float x, int H, int W, i
   w[3] = ly * lx;
 }
 
+// Sample coordinate and bilinear sum with every product and sum rounded on its own (no FMA contraction), in the order
+// of torchvision's CPU kernel, so that RoI values with cancellation agree with it to the last bits
+__device__ __forceinline__ float sample_coord(float start, int p, float bin, int i, int grid) {
+  return __fadd_rn(__fadd_rn(start, __fmul_rn((float)p, bin)), __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), (float)grid));
+}
+__device__ __forceinline__ float bilinear_sum(const float *__restrict__ plane, const int *o, const float *w) {
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w[0], __ldg(plane + o[0])), __fmul_rn(w[1], __ldg(plane + o[1]))),
+                             __fmul_rn(w[2], __ldg(plane + o[2]))),
+                   __fmul_rn(w[3], __ldg(plane + o[3])));
+}
+
 __device__ __forceinline__ float bin_value(const float *__restrict__ plane, const RoiGeom &g, int H, int W, int ph_i, int pw_i) {
   float acc = 0.f;
   for (int iy = 0; iy < g.grid_h; ++iy) {
-    const float y = g.start_h + (float)ph_i * g.bin_h + ((float)iy + 0.5f) * g.bin_h / (float)g.grid_h;
+    const float y = sample_coord(g.start_h, ph_i, g.bin_h, iy, g.grid_h);
     for (int ix = 0; ix < g.grid_w; ++ix) {
-      const float x = g.start_w + (float)pw_i * g.bin_w + ((float)ix + 0.5f) * g.bin_w / (float)g.grid_w;
+      const float x = sample_coord(g.start_w, pw_i, g.bin_w, ix, g.grid_w);
       int o[4];
       float w[4];
       bilinear_setup(y, x, H, W, o, w);
-      acc += w[0] * __ldg(plane + o[0]) + w[1] * __ldg(plane + o[1]) + w[2] * __ldg(plane + o[2]) + w[3] * __ldg(plane + o[3]);
+      acc = __fadd_rn(acc, bilinear_sum(plane, o, w));
     }
   }
   const int count = g.grid_h * g.grid_w;
@@ -120,8 +131,8 @@ roi_align_mean_kernel(const float *__restrict__ feat, int C, int H, int W, const
     for (int s = threadIdx.x; s < (int)n_samples; s += blockDim.x) {
       const int bin = s / per_bin, r = s - bin * per_bin;
       const int ph_i = bin / pw, pw_i = bin - ph_i * pw, iy = r / g.grid_w, ix = r - iy * g.grid_w;
-      const float y = g.start_h + (float)ph_i * g.bin_h + ((float)iy + 0.5f) * g.bin_h / (float)g.grid_h;
-      const float x = g.start_w + (float)pw_i * g.bin_w + ((float)ix + 0.5f) * g.bin_w / (float)g.grid_w;
+      const float y = sample_coord(g.start_h, ph_i, g.bin_h, iy, g.grid_h);
+      const float x = sample_coord(g.start_w, pw_i, g.bin_w, ix, g.grid_w);
       int o[4];
       float w[4];
       bilinear_setup(y, x, H, W, o, w);
@@ -143,8 +154,7 @@ roi_align_mean_kernel(const float *__restrict__ feat, int C, int H, int W, const
       const int s0 = bin * per_bin;
       for (int r = 0; r < per_bin; ++r) {
         const int s = s0 + r;
-        acc += s_w[s][0] * __ldg(plane + s_off[s][0]) + s_w[s][1] * __ldg(plane + s_off[s][1]) +
-               s_w[s][2] * __ldg(plane + s_off[s][2]) + s_w[s][3] * __ldg(plane + s_off[s][3]);
+        acc = __fadd_rn(acc, bilinear_sum(plane, s_off[s], s_w[s]));
       }
       return acc / count_f;  // a division, like torchvision's output_val / count
     };
