@@ -13,11 +13,17 @@
 // of the joint (Chebyshev) estimator, reduced across the warp through a transposed
 // shared-memory pass once per item -- so z is read from HBM exactly once.
 // Generic path (any 2 <= n_mc <= 32, 1 <= k < n_mc): same numbers, local-memory arrays.
+#include <cuda.h>
+
 #include <algorithm>
 
 #include "common.cuh"
 
 namespace runia {
+
+namespace tc {
+int make_plain_map(CUtensorMap *map, const float *ptr, int64_t rows, int K, int box_rows, int box_cols);
+}
 
 constexpr float kLn2 = 0.693147180559945309f;
 
@@ -205,41 +211,72 @@ constexpr int E16_STEP_FLOATS = 16 * 64;                                    // o
 constexpr int E16_NREG = 60;                                                // pair maxima kept in registers
 constexpr int E16_NSM = 120 - E16_NREG;                                     // pair maxima kept in shared memory ([q][lane] float4)
 constexpr int E16_WARP_FLOATS = E16_RING * E16_STEP_FLOATS + 16 * 16 + E16_NSM * 32;  // ring + Chebyshev matrix + maxima
-constexpr size_t kEntropy16Smem = (size_t)E16_WARPS * E16_WARP_FLOATS * sizeof(float);
+constexpr size_t kEntropy16Smem = (size_t)E16_WARPS * E16_WARP_FLOATS * sizeof(float) + E16_WARPS * E16_RING * 8;  // + mbarriers
 
+// (a, b) of pair p in the row-major upper triangle of the 16 x 16 matrix
+__constant__ uint8_t kPairA16[120], kPairB16[120];
+
+__device__ __forceinline__ uint32_t e16_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void e16_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "E16_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra E16_DONE;\n\t"
+      "bra E16_WAIT;\n\t"
+      "E16_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+// z is streamed by the TMA unit: one elected lane per warp issues ONE cp.async.bulk.tensor per step (a 16 x 64 box of
+// the [rows, D] matrix, columns past D zero-filled) into the warp's 2-slot ring, completion on a per-slot mbarrier;
+// the warp's instruction stream carries no address arithmetic and no per-lane copies for the loads any more
+// (8 LDGSTS + ~60 integer instructions per step before).
 __global__ void __launch_bounds__(E16_WARPS * 32, 3)
-entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_dist, double c_term,
+entropy16_kernel(const __grid_constant__ CUtensorMap tmZ, int64_t n_items, int D, float min_dist, double c_term,
                  double *__restrict__ h_z, double *__restrict__ h_mvn) {
-  constexpr int N = 16, K = 5, NPAIR = N * (N - 1) / 2;
-  extern __shared__ __align__(16) float smem[];
+  constexpr int N = 16, K = 5;
+  extern __shared__ __align__(128) float smem16[];  // per warp: ring | Chebyshev matrix | maxima; then the mbarriers
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float *ring = smem + (size_t)warp * E16_WARP_FLOATS;
+  float *ring = smem16 + (size_t)warp * E16_WARP_FLOATS;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem16 + (size_t)E16_WARPS * E16_WARP_FLOATS) + warp * E16_RING;
   float *dm = ring + E16_RING * E16_STEP_FLOATS;
-  float4 *pms = reinterpret_cast<float4 *>(dm + 16 * 16) + lane;  // this lane's maxima: pms[32 * q], q < E16_NSM / 4
-  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  float *pmsf = dm + 16 * 16;                            // [q][lane][4]: shared-memory half of the pair maxima
+  float4 *pms = reinterpret_cast<float4 *>(pmsf) + lane;  // this lane's maxima: pms[32 * q], q < E16_NSM / 4
+  const uint32_t ring_u32 = e16_smem_u32(ring);
+  const uint32_t bar_u32 = e16_smem_u32(bars);
   const int64_t gw = (int64_t)blockIdx.x * E16_WARPS + warp;  // this warp's first item
   const int64_t GW = (int64_t)gridDim.x * E16_WARPS;          // item stride
   const int spi = (D + 63) >> 6;                              // steps per item
   const int64_t n_my = gw < n_items ? (n_items - gw + GW - 1) / GW : 0;
   const int64_t n_steps = n_my * spi;
 
-  // copy stream (runs two steps ahead of the compute stream)
+  if (lane == 0) {
+    for (int s = 0; s < E16_RING; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_u32 + 8u * s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmZ) : "memory");
+  }
+  __syncwarp();
+
+  // copy stream (runs E16_RING - 1 steps ahead of the compute stream), driven by lane 0
   int64_t c_item = gw;
   int c_j = 0, c_buf = 0;
   int64_t c_step = 0;
   auto issue = [&]() {
     if (c_step < n_steps) {
-      const float *src0 = z + c_item * (int64_t)N * D;
-      const int col = c_j * 64 + (lane & 15) * 4;
-      const uint32_t dst0 = ring_u32 + (uint32_t)(c_buf * E16_STEP_FLOATS + (lane & 15) * 4) * 4u;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int row = 2 * r + (lane >> 4);
-        const bool in = col < D;  // D % 4 == 0: a 16-byte chunk is entirely inside or outside the row
-        const float *src = in ? src0 + (int64_t)row * D + col : z;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + (uint32_t)row * 256u), "l"(src),
-                     "r"(in ? 16 : 0)
-                     : "memory");
+      if (lane == 0) {
+        const uint32_t bar = bar_u32 + 8u * (uint32_t)c_buf;
+        const uint32_t dst = ring_u32 + (uint32_t)(c_buf * E16_STEP_FLOATS) * 4u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slot's last readers (generic proxy) are done
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(E16_STEP_FLOATS * 4) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+            "l"(&tmZ), "r"(bar), "r"(c_j * 64), "r"((int)(c_item * N))
+            : "memory");
       }
       if (++c_j == spi) {
         c_j = 0;
@@ -248,11 +285,11 @@ entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_
       if (++c_buf == E16_RING) c_buf = 0;
       ++c_step;
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   issue();
 
   int buf = 0;
+  uint32_t phase = 0;
   for (int64_t item = gw; item < n_items; item += GW) {
     // half of the 120 maxima live in registers, half in shared memory: 168 registers -> 12 resident warps
     float pm[E16_NREG];
@@ -262,16 +299,19 @@ entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_
     for (int q = 0; q < E16_NSM / 4; ++q) pms[32 * q] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
     for (int jstep = 0; jstep < spi; ++jstep) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
+      e16_mbar_wait(bar_u32 + 8u * (uint32_t)buf, phase);
       float2 x[N];
       {
         const float2 *b2 = reinterpret_cast<const float2 *>(ring + buf * E16_STEP_FLOATS) + lane;
 #pragma unroll
         for (int i = 0; i < N; ++i) x[i] = b2[i * 32];
       }
-      issue();  // refills the buffer read one step ago (every lane is past that step: __syncwarp above)
-      if (++buf == E16_RING) buf = 0;
+      __syncwarp();  // every lane has read the slot that the next issue() refills (the one read a step ago)
+      issue();
+      if (++buf == E16_RING) {
+        buf = 0;
+        phase ^= 1u;
+      }
       const int j = jstep * 32 + lane;  // float2 column: dimensions 2j, 2j+1
       {
         int p = 0;
@@ -344,30 +384,40 @@ entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_
       }
     }
     // ---- item complete: joint (Chebyshev) estimator from the 120 pair maxima ----
+    // The per-lane maxima are reduced across the lanes through shared memory, 60 pairs at a time in the [q][lane][4]
+    // block the shared-memory half already lives in: lane L takes pairs L and L + 32 of the block and walks the 32
+    // lanes' values of each (rotated by L >> 2 so that the 32 lanes hit 32 banks).
     if (h_mvn != nullptr) {
       __syncwarp();
-      int p = 0;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        if (half == 1) {  // second half: the register-resident maxima take the block's place
+          __syncwarp();
 #pragma unroll
-      for (int a = 0; a < N; ++a) {
-        if (lane == 0) dm[a * N + a] = 0.f;
+          for (int q = 0; q < E16_NREG / 4; ++q) pms[32 * q] = make_float4(pm[4 * q], pm[4 * q + 1], pm[4 * q + 2], pm[4 * q + 3]);
+          __syncwarp();
+        }
 #pragma unroll
-        for (int b = a + 1; b < N; ++b) {
-          float mine;
-          if (p < E16_NREG) {
-            mine = pm[p];
-          } else {
-            const float4 t = pms[32 * ((p - E16_NREG) >> 2)];
-            const int c = (p - E16_NREG) & 3;
-            mine = c == 0 ? t.x : c == 1 ? t.y : c == 2 ? t.z : t.w;
-          }
-          const float m = warp_max_f32(mine);
-          if (lane == 0) {
+        for (int r = 0; r < 2; ++r) {
+          const int pl = lane + 32 * r;  // pair inside the block
+          if (pl < E16_NSM) {
+            const float *col = pmsf + (pl >> 2) * 128 + (pl & 3);
+            const int rot = lane >> 2;
+            float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < 32; t += 2) {
+              m0 = fmaxf(m0, col[((t + rot) & 31) * 4]);
+              m1 = fmaxf(m1, col[((t + 1 + rot) & 31) * 4]);
+            }
+            const int pg = half == 0 ? E16_NREG + pl : pl;  // global pair index
+            const int a = kPairA16[pg], b = kPairB16[pg];
+            const float m = fmaxf(m0, m1);
             dm[a * N + b] = m;
             dm[b * N + a] = m;
           }
-          ++p;
         }
       }
+      if (lane < N) dm[lane * N + lane] = 0.f;
       __syncwarp();
       float lg = 0.f;
       if (lane < N) {
@@ -379,9 +429,9 @@ entropy16_kernel(const float *__restrict__ z, int64_t n_items, int D, float min_
       }
       lg = warp_sum32(lg);
       if (lane == 0) h_mvn[item] = c_term + (double)D * (double)(kLn2 * (1.f + lg * (1.f / N)));
+      __syncwarp();  // dm / pms are rewritten by the next item
     }
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ------------------------- any n_mc in [6, 32], k = 5 (the reference's default is 32) -------------------------
@@ -631,16 +681,31 @@ extern "C" int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, 
   RUNIA_REQUIRE(z && h_z, RUNIA_E_BADARG, "mcd_entropy: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (n_mc == 16 && k == 5 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(h_z) & 15) == 0) {
+      (reinterpret_cast<uintptr_t>(h_z) & 15) == 0 && n_items * 16 < (int64_t)0x7fffffff) {
     static PerDeviceFlag attr16;
     if (!attr16) {
       RUNIA_CUDA(cudaFuncSetAttribute(entropy16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kEntropy16Smem));
+      uint8_t pa[120], pb[120];
+      int p = 0;
+      for (int a = 0; a < 16; ++a)
+        for (int b = a + 1; b < 16; ++b) {
+          pa[p] = (uint8_t)a;
+          pb[p] = (uint8_t)b;
+          ++p;
+        }
+      RUNIA_CUDA(cudaMemcpyToSymbol(kPairA16, pa, sizeof(pa)));
+      RUNIA_CUDA(cudaMemcpyToSymbol(kPairB16, pb, sizeof(pb)));
       attr16 = true;
     }
-    // persistent warps: two CTAs of four warps per SM (register-limited), items round-robin over warps
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n_items, E16_WARPS), (int64_t)3 * kNumSMs);
-    entropy16_kernel<<<grid, E16_WARPS * 32, kEntropy16Smem, st>>>(z, n_items, D, (float)min_dist, digamma_term, h_z,
+    CUtensorMap tmz;
+    int rc = tc::make_plain_map(&tmz, z, n_items * 16, D, 16, 64);
+    if (rc) return rc;
+    // persistent warps: three CTAs of four warps per SM (register-limited), items round-robin over warps
+    int ctas_per_sm = 3;
+    if (const char *e = getenv("RUNIA_B200_E16_CTAS")) ctas_per_sm = atoi(e);  // occupancy experiments
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n_items, E16_WARPS), (int64_t)ctas_per_sm * kNumSMs);
+    entropy16_kernel<<<grid, E16_WARPS * 32, kEntropy16Smem, st>>>(tmz, n_items, D, (float)min_dist, digamma_term, h_z,
                                                                    h_mvn);
     count_launch();
     return finish_launch("mcd_entropy(16)");

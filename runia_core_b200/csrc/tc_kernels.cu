@@ -874,6 +874,27 @@ static int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int K, int
   return RUNIA_OK;
 }
 
+// plain (unswizzled) 2-D box over a row-major fp32 matrix: the streaming kernels outside this file (entropy.cu)
+int make_plain_map(CUtensorMap *map, const float *ptr, int64_t rows, int K, int box_rows, int box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return (int)cudaErrorNotSupported;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (plain) failed with CUresult %d (rows=%lld K=%d)", (int)r, (long long)rows, K);
+    return (int)cudaErrorInvalidValue;
+  }
+  return RUNIA_OK;
+}
+
 static int make_b_map(CUtensorMap *map, const float *ptr, int64_t rows, int K) { return make_map(map, ptr, rows, K, TNH); }
 // streamed operand: box of TM rows x 32 floats, lands in the A_hi plane of a stage as raw fp32
 static int make_a_map(CUtensorMap *map, const float *ptr, int64_t rows, int K) { return make_map(map, ptr, rows, K, TM); }
