@@ -120,3 +120,26 @@ if "sampler" in which:
     for _ in range(REPS):
         rows = _ops.mc_dropblock_mean(xm, seed, bs)
     torch.cuda.synchronize()
+if "wide" in which:  # ImageNet-sized head: 256-column panels with an online log-sum-exp; ASH prune kernel in front of it
+    Xw = torch.relu(torch.randn(500_000, 768, generator=g, device=dev))
+    Ww = 0.05 * torch.randn(1000, 768, generator=g, device=dev)
+    bw = torch.randn(1000, generator=g, device=dev)
+    plw = _ops.linear_planes(Ww)
+    for _ in range(REPS):
+        o = _ops.clip_linear_lse(Xw, Ww, bw, clip=1.0, planes=plw)
+        o = _ops.ash_linear_lse(Xw, Ww, bw, 115, planes=plw)
+    torch.cuda.synchronize()
+    Lw = torch.randn(1_000_000, 1000, generator=g, device=dev)
+    for _ in range(REPS):
+        o = _ops.logit_scores(Lw, gamma=0.1, M=100)
+    torch.cuda.synchronize()
+if "roi" in which:  # 1000 boxes on a 256 x 50 x 68 FPN map, 7 x 7 bins, 2 x 2 samples: means without the RoI maps
+    feat = torch.randn(1, 256, 50, 68, generator=g, device=dev)
+    x1 = torch.rand(1000, generator=g, device=dev) * 800
+    y1 = torch.rand(1000, generator=g, device=dev) * 600
+    boxes = torch.stack([x1, y1, x1 + 30 + 200 * torch.rand(1000, generator=g, device=dev),
+                         y1 + 30 + 150 * torch.rand(1000, generator=g, device=dev)], 1)
+    for _ in range(REPS):
+        m, s = _ops.roi_align_mean(feat, boxes, 7, 68 / 1088, 2, aligned=True)
+        r = _ops.roi_align(feat, boxes, 7, 68 / 1088, 2, aligned=True)
+    torch.cuda.synchronize()
