@@ -309,6 +309,24 @@ int runia_centered_gram_f64(const float *X, const int32_t *labels, const float *
                             double *G, double *colsum, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * (f2) float64 symmetric eigendecomposition and Cholesky factorisation for the setup() fits.
+ *   runia_eigh_f64: A [n, n] symmetric (symmetrised as (A + A^T) / 2) -> evals [n] (unordered) and evecs [n, n] with
+ *     ROW j = the unit eigenvector of evals[j]; one-sided Jacobi, deterministic, |A - V diag V^T| ~ 1e-14 |A|.  This is
+ *     the decomposition behind scipy.linalg.pinvh (sklearn EmpiricalCovariance.precision_: inference/postprocessors.py:
+ *     212-220, 296-314; inference/funcs.py:62-66) and behind PCA(svd_solver="covariance_eigh")
+ *     (dimensionality_reduction.py:52-72).  The call synchronises `stream` once per sweep (the sweep count depends on
+ *     the matrix); *sweeps_out (host, nullable) receives it.  workspace: runia_eigh_workspace_bytes(n).  n <= 8192.
+ *   runia_cholesky_f64: L [batch, n, n] lower with A_b + jitter I = L_b L_b^T; fail[b] = 0, or 1 + the first column whose
+ *     pivot is not positive (or, with rel_pivot > 0, below rel_pivot times its original diagonal entry: numerically
+ *     singular at that resolution) -- the signal gmm_fit's jitter ladder reacts to (inference/funcs.py:296-342).
+ */
+size_t runia_eigh_workspace_bytes(int n);
+int runia_eigh_f64(const double *A, int n, double *evals, double *evecs, void *workspace, size_t workspace_bytes,
+                   int max_sweeps, int *sweeps_out, void *stream);
+int runia_cholesky_f64(const double *A, int batch, int n, double jitter, double rel_pivot, double *L, int32_t *fail,
+                       void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * (f3) MC-DropBlock sampler fused with the spatial mean: MCSamplerModule.forward for layer_type "Conv"
  * (feature_extraction/abstract_classes.py:81-101 = n_mc x [DropBlock2D -> get_mean_or_fullmean_ls_sample
  * "fullmean", feature_extraction/utils.py:70-92]); DropBlock2D is dropblock==0.3.0 (published forward:

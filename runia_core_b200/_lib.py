@@ -84,6 +84,9 @@ _SIGS = {
     "runia_gen_entropy_f32": (c_int, [_P, c_int64, c_int, c_float, c_int, _P, _P]),
     "runia_linear_f32": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P]),
     "runia_stage_h2d": (c_int, [_P, _P, c_int64, _P]),
+    "runia_eigh_workspace_bytes": (c_size_t, [c_int]),
+    "runia_eigh_f64": (c_int, [_P, c_int, _P, _P, _P, c_size_t, c_int, _P, _P]),
+    "runia_cholesky_f64": (c_int, [_P, c_int, c_int, c_double, c_double, _P, _P, _P]),
     "runia_roi_align_f32": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int64, c_int, c_int, c_float, c_int, c_int,
                                     _P, _P]),
     "runia_roi_align_mean_f32": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int64, c_int, c_int, c_float, c_int,

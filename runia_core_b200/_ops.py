@@ -151,7 +151,7 @@ def factor_precision(precision):
     sign 0."""
     P = np.asarray(precision, np.float64)
     P = 0.5 * (P + P.T)
-    lam, V = np.linalg.eigh(P)
+    lam, V = eigh(P) if (P.shape[0] >= 64 and np.isfinite(P).all()) else np.linalg.eigh(P)
     amax = np.abs(lam).max() if lam.size else 0.0
     sign = np.sign(lam)
     sign[np.abs(lam) <= 1e-14 * amax] = 0.0
@@ -830,3 +830,63 @@ def roi_align_mean(feat, boxes, output_size, spatial_scale=1.0, sampling_ratio=-
     _lib.call("runia_roi_align_mean_f32", x.data_ptr(), B, C, H, W, bx.data_ptr(), None, bx.shape[0], ph, pw,
               float(spatial_scale), int(sampling_ratio), 1 if aligned else 0, mean.data_ptr(), ptr(std), stream_ptr())
     return mean, std
+
+
+# ------------------------------------------------------------------------------------------
+# (f2) float64 eigendecomposition / pseudo-inverse / Cholesky for the setup() fits
+# ------------------------------------------------------------------------------------------
+def _eigh_device(a_np):
+    a = to_device(np.ascontiguousarray(a_np, np.float64), torch.float64)
+    n = a.shape[0]
+    evals = _empty((n,), torch.float64)
+    evecs = _empty((n, n), torch.float64)
+    ws_bytes = int(_lib.raw("runia_eigh_workspace_bytes")(n))
+    ws = _empty((ws_bytes,), torch.uint8)
+    _lib.call("runia_eigh_f64", a.data_ptr(), n, evals.data_ptr(), evecs.data_ptr(), ws.data_ptr(), ws_bytes, 0, None,
+              stream_ptr())
+    return evals.cpu().numpy(), evecs.cpu().numpy().T
+
+
+def eigh(A):
+    """Symmetric eigendecomposition on the device: (evals ascending [n], V [n, n] with eigenvectors in the COLUMNS),
+    NumPy float64 -- the contract of numpy.linalg.eigh / scipy.linalg.eigh (eigenvector signs are arbitrary there too).
+    The one-sided Jacobi kernel diagonalises A^T A; for the positive semi-definite matrices of the fits (covariances,
+    precisions) that is the eigenbasis of A itself.  An indefinite A with eigenvalues +x and -x would leave their two
+    eigenvectors mixed: the residual |A V - V diag(lambda)| is checked, and such a matrix is decomposed again as
+    A + sigma I (sigma = its Frobenius norm: positive definite, same eigenvectors)."""
+    A = np.ascontiguousarray(A, np.float64)
+    n = A.shape[0]
+    assert A.ndim == 2 and A.shape[1] == n
+    A = 0.5 * (A + A.T)
+    lam, V = _eigh_device(A)
+    scale = max(float(np.abs(A).max(initial=0.0)), 1e-300)
+    if np.abs(A @ V - V * lam).max() > 1e-9 * scale * max(1.0, np.sqrt(n)):
+        sigma = float(np.linalg.norm(A))
+        lam, V = _eigh_device(A + sigma * np.eye(n))
+        lam = lam - sigma
+    order = np.argsort(lam, kind="stable")
+    return lam[order], np.ascontiguousarray(V[:, order])
+
+
+def pinvh(a):
+    """scipy.linalg.pinvh(a) (sklearn's `_set_covariance` -> `precision_`) from the device eigendecomposition, with
+    scipy's cut-off: eigenvalues with |lambda| <= max(M, N) * eps * max|lambda| are dropped."""
+    a = np.asarray(a, np.float64)
+    lam, V = eigh(a)
+    rtol = max(a.shape) * np.finfo(np.float64).eps
+    keep = np.abs(lam) > rtol * np.abs(lam).max(initial=0.0)
+    u = V[:, keep]
+    return (u * (1.0 / lam[keep])) @ u.T
+
+
+def cholesky_batch(A, jitter: float = 0.0, rel_pivot: float = 0.0):
+    """(L [B, n, n] float64 lower, fail [B] int32) with A_b + jitter I = L_b L_b^T on the device; A: ndarray or CUDA
+    tensor [B, n, n].  rel_pivot > 0 also fails pivots below rel_pivot x their original diagonal entry."""
+    a = A.to(torch.float64).contiguous() if isinstance(A, torch.Tensor) and A.is_cuda else \
+        to_device(np.ascontiguousarray(A, np.float64), torch.float64)
+    B, n, _ = a.shape
+    L = _empty((B, n, n), torch.float64)
+    fail = _empty((B,), torch.int32)
+    _lib.call("runia_cholesky_f64", a.data_ptr(), B, n, float(jitter), float(rel_pivot), L.data_ptr(), fail.data_ptr(),
+              stream_ptr())
+    return L, fail.cpu().numpy()

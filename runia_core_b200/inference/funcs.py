@@ -37,7 +37,7 @@ def mahalanobis_preprocess(ind_data: Dict[str, np.ndarray], num_classes: int) ->
         cov = _ops.centered_covariance(xf, lab, means, int(counts.sum()))
         if not np.isfinite(cov).all():
             raise ValueError("Input X contains NaN or infinity.")
-        return to_host(means), pinvh(cov, check_finite=False)
+        return to_host(means), (_ops.pinvh(cov) if cov.shape[0] >= 64 else pinvh(cov, check_finite=False))
     class_mean, centered = [], []
     for c in range(num_classes):
         xs = feats[labels == c]
@@ -113,10 +113,42 @@ def ash_s_linear_layer(x: np.ndarray, percentile: int = 85):
     return to_host(_ops.ash_prune(x, k))
 
 
+def _gmm_fit_device(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: int):
+    """gmm_fit on the device kernels: NumPy-ordered class means (`runia_class_mean_f32`), the float64 Gram matrix of
+    each class's float32 residuals (`runia_centered_gram_f64`; upstream multiplies them in float32), covariance
+    G / (n - 1), and the jitter ladder on a float64 Cholesky (`runia_cholesky_f64`) that gives up where a float32
+    factorisation would (pivot below 6e-8 of its diagonal entry).  Parity definition: with well-conditioned classes
+    (n_c >> d) the mixture's log-densities agree with the reference's float32 torch fit to 1e-5 relative (fixtures);
+    rank-deficient classes are decided by rounding in the reference itself."""
+    jitters = [0] + [10**e for e in range(-20, 0, 1)]
+    means, counts, xf, lab = _ops.class_means(embeddings, labels, num_classes)
+    keep = [c for c in range(num_classes) if counts[c] > 0]
+    d = xf.shape[1]
+    covs = torch.empty((len(keep), d, d), dtype=torch.float64, device=xf.device)
+    for i, c in enumerate(keep):
+        lab_c = torch.where(lab == c, 0, -1).to(torch.int32)
+        G, _ = _ops.centered_gram(xf, lab_c, means[c:c + 1].contiguous())
+        n = int(counts[c])
+        n = n + 1 if n == 1 else n
+        covs[i] = G / (n - 1)
+    loc = means[keep].contiguous()
+    gmm, jitter_eps = None, None
+    for jitter_eps in jitters:
+        L, fail = _ops.cholesky_batch(covs, jitter=float(jitter_eps), rel_pivot=6e-8)
+        if (fail == 0).all() and bool(torch.isfinite(L).all()):
+            gmm = torch.distributions.MultivariateNormal(loc=loc, scale_tril=L.to(torch.float32))
+            break
+    return gmm, jitter_eps
+
+
 def gmm_fit(embeddings: torch.Tensor, labels: torch.Tensor, num_classes: int):
     """Class-wise Gaussian mixture (funcs.py:265-344): mean and covariance X^T X / (n-1) per class,
     empty classes dropped, smallest jitter of [0, 1e-20 .. 1e-1] for which the Cholesky
-    factorisation exists.  Returns (MultivariateNormal, jitter)."""
+    factorisation exists.  Returns (MultivariateNormal, jitter).  float32 embeddings are fitted by the device kernels
+    (`_gmm_fit_device`); other dtypes keep the reference's torch expression."""
+    if torch.cuda.is_available() and isinstance(embeddings, torch.Tensor) and embeddings.dtype == torch.float32 and \
+            embeddings.dim() == 2 and embeddings.shape[0] > 0 and embeddings.shape[1] <= 2048:
+        return _gmm_fit_device(embeddings.detach(), labels, num_classes)
     jitters = [0] + [10**e for e in range(-20, 0, 1)]
     with torch.no_grad():
         means, covs = [], []

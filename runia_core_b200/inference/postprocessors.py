@@ -85,7 +85,7 @@ def _device_fit(feats, labels, num_classes):
     cov = _ops.centered_covariance(xf, lab, means, n_used)
     if not np.isfinite(cov).all():  # sklearn's validate_data refuses such rows
         raise ValueError("Input X contains NaN or infinity.")
-    return to_host(means), counts, pinvh(cov, check_finite=False)
+    return to_host(means), counts, (_ops.pinvh(cov) if cov.shape[0] >= 64 else pinvh(cov, check_finite=False))
 
 
 class DetectorKDE:

@@ -66,13 +66,52 @@ def main():
     # the single-GPU means are float32 row-by-row sums (NumPy order, ~1e-5 of rounding at 8.5k rows per class); the
     # sharded combination is at least as accurate
     ok_fit = bool(np.array_equal(c2, c1) and np.isnan(m2[3]).all() and mean_err < 5e-5 and prec_err < 1e-6)
-    flags = torch.tensor([int(ok_knn), int(err < 1e-6), int(same), int(ok_fit)], device=dev)
+    # ---- the same partitioning behind the reference-facing classes: setup(..., bank_group=group) ----
+    import runia_core_b200 as R
+    import warnings
+
+    grp = dist.group.WORLD
+    tr_np, q_np = bank[:60_000].cpu().numpy(), q[:500].cpu().numpy()
+    single, sharded = R.inference.KNNLatentSpace(), R.inference.KNNLatentSpace()
+    single.setup(tr_np)
+    sharded.setup(tr_np, bank_group=grp)                      # replicated input: every rank keeps its slice
+    ok_api = np.array_equal(single.postprocess(q_np), sharded.postprocess(q_np))
+    lo2, hi2 = sharding.row_shard(tr_np.shape[0], rank, world)
+    local = R.inference.KNNLatentSpace()
+    local.setup(tr_np[lo2:hi2], bank_group=grp, bank_rows_are_local=True)   # every rank hands in its own rows
+    ok_api = ok_api and np.array_equal(single.postprocess(q_np), local.postprocess(q_np))
+    knn_b = R.inference.KNN(flip_sign=False, k_neighbors=20)
+    knn_s = R.inference.KNN(flip_sign=False, k_neighbors=20)
+    knn_b.setup(tr_np, valid_feats=q_np)
+    knn_s.setup(tr_np, valid_feats=q_np, bank_group=grp)
+    ok_api = ok_api and np.array_equal(knn_b.postprocess(q_np), knn_s.postprocess(q_np)) and knn_b.threshold == knn_s.threshold
+    kde_b, kde_s = R.inference.KDELatentSpace(), R.inference.KDELatentSpace()
+    kde_b.setup(tr_np[:20_000])
+    kde_s.setup(tr_np[:20_000], bank_group=grp)
+    e_kde = float(np.max(np.abs(kde_b.postprocess(q_np) - kde_s.postprocess(q_np)) / np.maximum(1.0, np.abs(kde_b.postprocess(q_np)))))
+    md_b, md_s = R.inference.MDLatentSpace(), R.inference.MDLatentSpace()
+    md_b.setup(tr_np)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        md_s.setup(tr_np, bank_group=grp)
+    e_md = float(np.max(np.abs(md_b.postprocess(q_np) - md_s.postprocess(q_np)) / np.maximum(1.0, np.abs(md_b.postprocess(q_np)))))
+    ok_api = bool(ok_api and e_kde < 1e-6 and e_md < 1e-6)
+    # a rank-local failure must raise on EVERY rank (flag all-reduce before the collectives), not hang the others
+    raised = False
+    try:
+        sharding.knn_search_sharded(qn, shard, k, search_fn=(lambda *a: (_ for _ in ()).throw(ValueError("boom")))
+                                    if rank == world - 1 else None)
+    except RuntimeError:
+        raised = True
+    flags = torch.tensor([int(ok_knn), int(err < 1e-6), int(same), int(ok_fit), int(ok_api), int(raised)], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(json.dumps({"world": world, "bank_rows": nb, "queries": nq, "k": k, "knn_bit_exact": bool(flags[0]),
                           "kde_max_rel_err": err, "kde_ok": bool(flags[1]), "identical_on_all_ranks": bool(flags[2]),
                           "sharded_fit_ok": bool(flags[3]), "sharded_fit_mean_abs_err": mean_err,
-                          "sharded_fit_precision_rel_err": prec_err}))
+                          "sharded_fit_precision_rel_err": prec_err,
+                          "postprocessors_with_bank_group_ok": bool(flags[4]), "api_kde_rel_err": e_kde, "api_md_rel_err": e_md,
+                          "rank_local_failure_raises_everywhere": bool(flags[5])}))
     dist.destroy_process_group()
     sys.exit(0 if bool(flags.min()) else 1)
 

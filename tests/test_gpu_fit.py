@@ -118,3 +118,94 @@ def test_fit_argument_contract():
     G = torch.zeros(4, 4, dtype=torch.float64, device="cuda")
     assert _lib.raw("runia_centered_gram_f64")(x.data_ptr(), None, None, 8, 4, 1, G.data_ptr(), None, out.data_ptr(), 8, None) < 0
     assert b"workspace" in _lib.raw("runia_b200_last_error")()
+
+
+@pytest.mark.parametrize("n", [5, 64, 257, 512])
+def test_device_eigh_pinvh_cholesky(n):
+    """csrc/eigh.cu: the float64 Jacobi eigendecomposition behind pinvh(covariance) (sklearn EmpiricalCovariance ->
+    scipy.linalg.pinvh, postprocessors.py:212-220), and the batched Cholesky behind gmm_fit (funcs.py:296-342), against
+    NumPy / SciPy: eigenvalues to 1e-12 of |A|, A V = V diag(lambda) to 1e-12, V orthonormal, pinvh to 1e-9 (rank-deficient
+    covariance with scipy's cut-off, an indefinite matrix with +x / -x eigenvalue pairs)."""
+    from scipy.linalg import pinvh
+
+    from runia_core_b200 import _ops
+
+    rng = np.random.RandomState(n)
+    X = rng.randn(3 * n, n) @ (np.eye(n) + 0.3 * rng.randn(n, n) / np.sqrt(n))
+    cov = np.cov(X.T, bias=True)
+    lam, V = _ops.eigh(cov)
+    ref = np.linalg.eigvalsh(cov)
+    assert np.abs(lam - ref).max() < 1e-12 * np.abs(ref).max()
+    assert np.abs(cov @ V - V * lam).max() < 1e-12 * np.abs(cov).max() * n
+    assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12
+    P = _ops.pinvh(cov)
+    assert np.abs(P - pinvh(cov)).max() < 1e-9 * np.abs(P).max()
+    # rank-deficient: fewer rows than columns -> scipy's cut-off drops the null space
+    Xr = rng.randn(max(2, n // 2), n)
+    cr = np.cov(Xr.T, bias=True)
+    Pr, Sr = _ops.pinvh(cr), pinvh(cr)
+    assert np.abs(Pr - Sr).max() < 1e-8 * np.abs(Sr).max()
+    # indefinite with +x / -x pairs (Q diag(+-) Q^T): the residual check re-decomposes it with a shift
+    Q = np.linalg.qr(rng.randn(n, n))[0]
+    d = np.concatenate([np.linspace(1, 2, n // 2), -np.linspace(1, 2, n - n // 2)])
+    Ai = (Q * d) @ Q.T
+    li, Vi = _ops.eigh(Ai)
+    assert np.abs(li - np.sort(d)).max() < 1e-10 and np.abs(Ai @ Vi - Vi * li).max() < 1e-10
+    # batched Cholesky with the failure flag
+    mats = np.stack([cov + 0.1 * np.eye(n), cr, Ai])
+    L, fail = _ops.cholesky_batch(mats)
+    assert fail[1] > 0 or n <= 5  # rank-deficient
+    L = L.cpu().numpy()
+    assert fail[0] == 0 and np.abs(L[0] - np.linalg.cholesky(mats[0])).max() < 1e-10 * np.abs(L[0]).max()
+    assert fail[2] > 0  # indefinite
+    L2, fail2 = _ops.cholesky_batch(mats[1:2], jitter=1e-3)
+    assert fail2[0] == 0 and np.abs(L2[0].cpu().numpy() - np.linalg.cholesky(cr + 1e-3 * np.eye(n))).max() < 1e-9
+
+
+def test_pca_covariance_eigh_fit_on_device():
+    """apply_pca_ds_split(..., svd_solver="covariance_eigh") (dimensionality_reduction.py:52-72 passes the solver name
+    to sklearn) fitted on the device == sklearn's own covariance_eigh solver on the same data in float64."""
+    from sklearn.decomposition import PCA
+
+    import runia_core_b200 as R
+
+    rng = np.random.RandomState(8)
+    X = (0.5 + rng.randn(20_000, 96) @ (np.eye(96) + 0.4 * rng.randn(96, 96) / 10)).astype(np.float32)
+    Z, pca = R.apply_pca_ds_split(X, nro_components=24, svd_solver="covariance_eigh")
+    ref = PCA(n_components=24, svd_solver="covariance_eigh", whiten=True).fit(X.astype(np.float64))
+    np.testing.assert_allclose(pca.explained_variance_, ref.explained_variance_, rtol=1e-6)
+    np.testing.assert_allclose(pca.components_, ref.components_, atol=2e-6)
+    np.testing.assert_allclose(pca.explained_variance_ratio_, ref.explained_variance_ratio_, rtol=1e-6)
+    np.testing.assert_allclose(pca.singular_values_, ref.singular_values_, rtol=1e-6)
+    assert abs(pca.noise_variance_ - ref.noise_variance_) < 1e-6 * ref.noise_variance_
+    np.testing.assert_allclose(Z, ref.transform(X.astype(np.float64)), atol=2e-5)
+    assert Z.dtype == np.float32 and pca.n_components_ == 24 and pca.n_samples_ == 20_000
+    np.testing.assert_allclose(R.apply_pca_transform(X[:100], pca), Z[:100], atol=1e-6)
+
+
+def test_gmm_fit_on_device_matches_torch_expression():
+    """gmm_fit (funcs.py:265-344) on the device kernels vs the reference's float32 torch expression on the same data:
+    means, Cholesky factors and DDU log-densities (well-conditioned classes; an empty class is dropped)."""
+    import torch
+
+    from runia_core_b200 import _ops
+    from runia_core_b200.inference.funcs import gmm_fit
+
+    rng = np.random.RandomState(9)
+    C, d, n = 6, 48, 6000
+    y = rng.randint(0, C, n)
+    y[y == 4] = 5  # class 4 empty
+    mu = rng.randn(C, d)
+    x = (mu[y] + rng.randn(n, d) @ (np.eye(d) + 0.2 * rng.randn(d, d) / 7)).astype(np.float32)
+    gmm, jit = gmm_fit(torch.from_numpy(x), torch.from_numpy(y.astype(np.float32)), C)
+    assert jit == 0 and gmm.loc.shape == (C - 1, d) and gmm.loc.is_cuda
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    means = torch.stack([xt[yt == c].mean(0) for c in range(C) if (yt == c).any()])
+    covs = torch.stack([torch.cov(xt[yt == c].T.double()) for c in range(C) if (yt == c).any()])
+    ref = torch.distributions.MultivariateNormal(means.double(), covariance_matrix=covs)
+    np.testing.assert_allclose(gmm.loc.cpu().numpy(), means.numpy(), atol=2e-6)
+    np.testing.assert_allclose(gmm.scale_tril.cpu().numpy(), ref.scale_tril.numpy(), rtol=1e-4, atol=1e-5)
+    st = _ops.gmm_prepare(gmm.loc.cpu().numpy(), gmm.scale_tril.cpu().numpy())
+    got = _ops.gmm_lse(x[:500], st).cpu().numpy()
+    want = torch.logsumexp(ref.log_prob(xt[:500, None, :].double()), dim=1).numpy()
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-4
