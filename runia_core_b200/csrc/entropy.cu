@@ -476,23 +476,33 @@ entropy_np_kernel(const float *__restrict__ z, int64_t n_items, int n, int D, fl
       }
       // ---- per-dimension estimator (lane = dimension) ----
       sort_network<NP>(v);
-      float wd[NP - K];  // window widths: the radius of a window for its two end points (no max needed there)
+      float wd[NP - K];  // window widths, clamped: the radius of a window for its two end points (no max needed there)
 #pragma unroll
-      for (int a = 0; a + K < NP; ++a) wd[a] = v[a + K] - v[a];
+      for (int a = 0; a + K < NP; ++a) wd[a] = fmaxf(v[a + K] - v[a], min_dist);
       float sl = 0.f;
 #pragma unroll
       for (int i = 0; i < NP; ++i) {
-        float r = INFINITY;
+        // candidates of sample i: one per window [a, a + K] containing it; interior points fold the min_dist clamp into a
+        // 3-input max, and the minimum over the (up to six) candidates is a chain of 3-input mins
+        float cand[K + 1];
+        int nc = 0;
 #pragma unroll
         for (int a = 0; a + K < NP; ++a) {
           if (a <= i && i <= a + K) {
             if (i == a || i == a + K)
-              r = fminf(r, wd[a]);
+              cand[nc] = wd[a];
             else
-              r = fminf(r, fmaxf(v[i] - v[a], v[a + K] - v[i]));
+              cand[nc] = fmaxf(fmaxf(v[i] - v[a], v[a + K] - v[i]), min_dist);
+            ++nc;
           }
         }
-        sl += i < n ? lg2_pos(fmaxf(r, min_dist)) : 0.f;
+        float r = cand[0];
+        if (nc == 2) r = fminf(r, cand[1]);
+        if (nc >= 3) r = fminf(fminf(r, cand[1]), cand[2]);
+        if (nc == 4) r = fminf(r, cand[3]);
+        if (nc >= 5) r = fminf(fminf(r, cand[3]), cand[4]);
+        if (nc == 6) r = fminf(r, cand[5]);
+        sl += i < n ? lg2_pos(r) : 0.f;
       }
       if (ok) h_z[item * (int64_t)D + j] = c_term + (double)(kLn2 * (1.f + sl / (float)n));
       // ---- joint estimator: fold this step into row `lane` of the Chebyshev matrix (lane = sample) ----
@@ -513,8 +523,8 @@ entropy_np_kernel(const float *__restrict__ z, int64_t n_items, int n, int D, fl
             const float4 o = *reinterpret_cast<const float4 *>(row + 4 * q);  // broadcast
             const float2 d0 = sub2(make_float2(own[q].x, own[q].y), make_float2(o.x, o.y));
             const float2 d1 = sub2(make_float2(own[q].z, own[q].w), make_float2(o.z, o.w));
-            m = fmaxf(m, fmaxf(fabsf(d0.x), fabsf(d0.y)));
-            m = fmaxf(m, fmaxf(fabsf(d1.x), fabsf(d1.y)));
+            m = fmaxf(fmaxf(m, fabsf(d0.x)), fabsf(d0.y));  // one 3-input FMNMX3 each (ptxas fuses this nesting only)
+            m = fmaxf(fmaxf(m, fabsf(d1.x)), fabsf(d1.y));
           }
           acc[jj * 32] = m;
         }

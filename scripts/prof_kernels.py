@@ -12,7 +12,7 @@ from runia_core_b200 import _ops  # noqa: E402
 which = set(sys.argv[1:]) or {"larem", "entropy", "knn", "pca"}
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev).manual_seed(0)
-REPS = 2
+REPS = int(os.environ.get("PROF_REPS", "2"))
 
 if "larem" in which:
     rng = np.random.RandomState(1)
