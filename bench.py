@@ -249,8 +249,10 @@ def run_b200(args):
         return float(t.item())
 
     import runia_core_b200 as R
-    from runia_core_b200 import _lib, _ops
+    from runia_core_b200 import _device, _lib, _ops
 
+    # several ranks on one host: keep each rank's staging threads and pinned slots on its GPU's NUMA node
+    numa = _device.bind_to_gpu_numa_node(local) if world > 1 else {"numa_node": None}
     hbm_peak, bf16_peak, peak_src = _peaks()
     dev = torch.device("cuda", local)
     md = R.inference.MDLatentSpace()
@@ -383,6 +385,7 @@ def run_b200(args):
     e2e = {"value": head["embeddings_per_s"], "unit": "embeddings/s", "h2d_bytes_per_step": n_e2e * D_LATENT * 4,
            "d2h_bytes_per_step": n_e2e * 8, "rows_per_step": n_e2e,
            "source": "pageable numpy.ndarray -> MDLatentSpace.postprocess -> numpy.ndarray (pinned staging ring inside)",
+           "h2d_GBps_all_gpus": head["h2d_GBps_per_gpu"] * world, "host_cpus": os.cpu_count(), "numa": numa,
            "variants": variants}
 
     extra = {}

@@ -34,6 +34,35 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def bind_to_gpu_numa_node(dev_index: int = None) -> dict:
+    """Pins the calling process (its future threads included: the staging workers are created on first use) to the CPUs
+    of the NUMA node the GPU hangs off, so that pinned slots and staging copies stay node-local when several ranks share
+    a host.  Returns what it found ({"numa_node": -1} on hosts that expose no topology, e.g. single-node VMs: no-op)."""
+    require_cuda()
+    dev_index = torch.cuda.current_device() if dev_index is None else dev_index
+    info = {"numa_node": -1, "cpus": len(os.sched_getaffinity(0))}
+    try:
+        pr = torch.cuda.get_device_properties(dev_index)
+        addr = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{addr}/numa_node") as f:
+            node = int(f.read().strip())
+        info["pci"] = addr
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(numa_node=node, cpus=len(cpus))
+    except Exception as e:  # noqa: BLE001 -- topology files are optional
+        info["error"] = repr(e)
+    return info
+
+
 PIPE_MIN_BYTES = 256 << 10                                                    # below this a plain copy is as fast
 PIPE_CHUNK_BYTES = int(os.environ.get("RUNIA_B200_PIPE_CHUNK_BYTES", 64 << 20))  # rows per kernel launch when streaming
 
