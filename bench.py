@@ -236,6 +236,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # the ranks share the host's cores: give each rank's staging engine its share (read once, at first use)
+        os.environ.setdefault("RUNIA_B200_STAGE_THREADS", str(max(2, min(8, (os.cpu_count() or 8) // world))))
 
     def barrier():
         if world > 1:
