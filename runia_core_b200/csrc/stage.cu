@@ -72,8 +72,11 @@ class Stager {
     char *dst = static_cast<char *>(dst_dev);
     // 4 threads reach the PCIe rate on a 20 MB call and keep the number of spinning threads small (fewer stragglers);
     // a long upload needs 8 to stay at 50 GB/s (4 threads: 29 GB/s on 1 GB) and can absorb a straggler in its ring
-    active_.store(bytes >= (32u << 20) ? (int)workers_.size() : std::min<int>(3, (int)workers_.size()),
-                  std::memory_order_relaxed);
+    int want = bytes >= (32u << 20) ? (int)workers_.size() : std::min<int>(3, (int)workers_.size());
+    // a worker that was descheduled while it held a claimed piece made the previous call wait: the host's cores are
+    // taken (BLAS threads of a fit spin for ~100 ms after their last call) -- copy alone until that has passed
+    if (std::chrono::steady_clock::now() < solo_until_) want = 0;
+    active_.store(want, std::memory_order_relaxed);
     for (size_t off = 0; off < bytes; off += kSlotBytes) {
       const size_t n = bytes - off < kSlotBytes ? bytes - off : kSlotBytes;
       const int s = next_slot_;
@@ -147,7 +150,7 @@ class Stager {
   }
 
   void fill(char *dst, const char *src, size_t n) {
-    if (workers_.empty() || n <= kPieceBytes) {
+    if (workers_.empty() || n <= kPieceBytes || active_.load(std::memory_order_relaxed) == 0) {
       memcpy(dst, src, n);
       return;
     }
@@ -167,7 +170,13 @@ class Stager {
       cv_.notify_all();
     }
     claim_loop();
-    while (done_[g & 3].load(std::memory_order_acquire) != np) cpu_relax();
+    if (done_[g & 3].load(std::memory_order_acquire) != np) {
+      const auto t0 = std::chrono::steady_clock::now();
+      while (done_[g & 3].load(std::memory_order_acquire) != np) cpu_relax();
+      const auto waited = std::chrono::steady_clock::now() - t0;
+      if (waited > std::chrono::microseconds(150))  // a piece takes ~15 us to copy: its holder lost its core
+        solo_until_ = std::chrono::steady_clock::now() + std::chrono::milliseconds(25);
+    }
   }
 
   void worker(int idx) {
@@ -205,6 +214,7 @@ class Stager {
   std::atomic<uint32_t> done_[4];
   std::atomic<int> sleepers_{0};
   std::atomic<int> active_{0};  // workers [0, active_) take part in the current upload
+  std::chrono::steady_clock::time_point solo_until_{};  // stragglers seen: no workers before this time
   Desc ring_[4];
   std::vector<std::thread> workers_;
   char *slot_[kSlots] = {nullptr, nullptr, nullptr, nullptr};
