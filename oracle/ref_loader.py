@@ -3,7 +3,7 @@
 
 Nothing in the product (`runia_core_b200/`), in `-m gpu` tests, in `smoke()` or in
 `bench.py` may import this file: `/root/reference` does not exist on the GPU box.
-It is used by `oracle/gen_golden.py` and by `tests/test_oracle_vs_reference.py`
+It is used by `oracle/gen_golden.py` (the fixtures under `tests/golden/` are what the tests consume)
 (which skips itself when `/root/reference` is absent).
 
 How it works: the reference's package `__init__`

@@ -775,12 +775,19 @@ def mc_dropblock_mean(x, seed, block_size: int) -> torch.Tensor:
     n_mc = sd.shape[0]
     if tuple(sd.shape) != (n_mc, B, H, W):
         raise ValueError(f"seed shape {tuple(sd.shape)} does not match (n_mc, {B}, {H}, {W})")
+    if n_mc > MC_SAMPLER_MAX:  # the kernel keeps one accumulator per sample in registers (<= 32): more samples in passes
+        parts = [mc_dropblock_mean(xf, sd[m0:m0 + MC_SAMPLER_MAX], block_size).reshape(B, -1, C)
+                 for m0 in range(0, n_mc, MC_SAMPLER_MAX)]
+        return torch.cat(parts, dim=1).reshape(B * n_mc, C)
     out = _empty((B * n_mc, C), torch.float32)
     ws_bytes = int(_lib.raw("runia_mc_dropblock_workspace_bytes")(B, H, W, n_mc))
     ws = _empty((ws_bytes,), torch.uint8)
     _lib.call("runia_mc_dropblock_mean_f32", xf.data_ptr(), sd.data_ptr(), B, C, H, W, n_mc, int(block_size), out.data_ptr(),
               ws.data_ptr(), ws_bytes, stream_ptr())
     return out
+
+
+MC_SAMPLER_MAX = 32  # sampler.cu: MC samples per launch
 
 
 def mc_dropblock_apply(x, seed, block_size: int) -> torch.Tensor:
@@ -791,6 +798,9 @@ def mc_dropblock_apply(x, seed, block_size: int) -> torch.Tensor:
         torch.from_numpy(np.ascontiguousarray(np.asarray(seed) != 0).astype(np.uint8)).to(device())
     B, C, H, W = xf.shape
     n_mc = sd.shape[0]
+    if n_mc > MC_SAMPLER_MAX:
+        return torch.cat([mc_dropblock_apply(xf, sd[m0:m0 + MC_SAMPLER_MAX], block_size)
+                          for m0 in range(0, n_mc, MC_SAMPLER_MAX)], dim=0)
     out = _empty((n_mc, B * C * H * W), torch.float32)
     ws_bytes = int(_lib.raw("runia_mc_dropblock_workspace_bytes")(B, H, W, n_mc))
     ws = _empty((ws_bytes,), torch.uint8)

@@ -29,7 +29,7 @@ def _dropblock_fullmean(x, seed, bs):
 
 
 @pytest.mark.parametrize("B,C,H,W,n_mc,bs,p", [(1, 512, 7, 7, 16, 3, 0.3), (5, 100, 16, 12, 16, 4, 0.4), (3, 33, 1, 1, 5, 1, 0.5),
-                                               (2, 64, 24, 24, 32, 7, 0.5), (2, 40, 9, 9, 8, 6, 0.9), (64, 512, 7, 7, 16, 3, 0.3)])
+                                               (2, 64, 24, 24, 32, 7, 0.5), (2, 40, 9, 9, 8, 6, 0.9), (64, 512, 7, 7, 16, 3, 0.3), (3, 48, 7, 7, 40, 3, 0.3)])
 def test_mc_dropblock_mean_matches_dropblock2d(B, C, H, W, n_mc, bs, p):
     from runia_core_b200 import _ops
 

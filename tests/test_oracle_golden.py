@@ -12,7 +12,11 @@ TOL = 1e-6  # the reference's own TOLERANCE (tests/unit_test_postprocessors.py:5
 
 
 def _sumdiff(a, b):
-    return abs(float((np.asarray(a, np.float64) - np.asarray(b, np.float64)).sum()))
+    """The reference's own assertion (a signed sum of differences, tests/unit_test_postprocessors.py) AND an
+    element-wise one: a signed sum cancels errors of opposite sign, so each value is also compared on its own."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    elem = float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) if a.size else 0.0
+    return max(abs(float((a - b).sum())), elem)
 
 
 # ------------------------------- reference KATs -------------------------------------------
