@@ -301,12 +301,17 @@ int runia_sort_f32(const float *x, int64_t n, float *out_sorted, void *workspace
  *     (centers NULL: r_i = x_i; labels NULL: every row uses centers[0]; rows whose label is outside [0, C)
  *     are skipped), colsum [d] (nullable) = sum_i r_i.  np.cov(R.T, bias=1) = (G - n a a^T) / n, a = colsum / n.
  *     Deterministic (fixed-order split reduction).  workspace: runia_centered_gram_workspace_bytes(N, d).
+ *   runia_shifted_gram_f64: the same with ONE float64 centre u [d] (device): r_i = f64(x_i) - u, exact in float64 -- the
+ *     rows ViM.setup hands EmpiricalCovariance(assume_centered=True) (inference/postprocessors.py:1060-1064:
+ *     `ec.fit(train - self.u)`, u float64); covariance = G / N.  Same workspace.
  */
 int runia_class_mean_f32(const float *X, const int32_t *labels, int64_t N, int d, int C, float *means,
                          int64_t *counts, void *stream);
 size_t runia_centered_gram_workspace_bytes(int64_t N, int d);
 int runia_centered_gram_f64(const float *X, const int32_t *labels, const float *centers, int64_t N, int d, int C,
                             double *G, double *colsum, void *workspace, size_t workspace_bytes, void *stream);
+int runia_shifted_gram_f64(const float *X, const double *center, int64_t N, int d, double *G, double *colsum,
+                           void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (f2) float64 symmetric eigendecomposition and Cholesky factorisation for the setup() fits.
@@ -319,12 +324,15 @@ int runia_centered_gram_f64(const float *X, const int32_t *labels, const float *
  *   runia_cholesky_f64: L [batch, n, n] lower with A_b + jitter I = L_b L_b^T; fail[b] = 0, or 1 + the first column whose
  *     pivot is not positive (or, with rel_pivot > 0, below rel_pivot times its original diagonal entry: numerically
  *     singular at that resolution) -- the signal gmm_fit's jitter ladder reacts to (inference/funcs.py:296-342).
+ *   runia_tril_inverse_f64: X_b = L_b^{-1} for a batch of lower-triangular factors (X != L): the whitening blocks the
+ *     GMM scorer contracts against (DDU.setup, inference/postprocessors.py:751-760 -> MultivariateNormal.log_prob).
  */
 size_t runia_eigh_workspace_bytes(int n);
 int runia_eigh_f64(const double *A, int n, double *evals, double *evecs, void *workspace, size_t workspace_bytes,
                    int max_sweeps, int *sweeps_out, void *stream);
 int runia_cholesky_f64(const double *A, int batch, int n, double jitter, double rel_pivot, double *L, int32_t *fail,
                        void *stream);
+int runia_tril_inverse_f64(const double *L, int batch, int n, double *X, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (f3) MC-DropBlock sampler fused with the spatial mean: MCSamplerModule.forward for layer_type "Conv"

@@ -72,6 +72,7 @@ _SIGS = {
     "runia_class_mean_f32": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P]),
     "runia_centered_gram_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "runia_centered_gram_f64": (c_int, [_P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, c_size_t, _P]),
+    "runia_shifted_gram_f64": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P, c_size_t, _P]),
     "runia_mc_dropblock_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "runia_mc_dropblock_mean_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
     "runia_mc_dropblock_apply_f32": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t, _P]),
@@ -87,6 +88,7 @@ _SIGS = {
     "runia_eigh_workspace_bytes": (c_size_t, [c_int]),
     "runia_eigh_f64": (c_int, [_P, c_int, _P, _P, _P, c_size_t, c_int, _P, _P]),
     "runia_cholesky_f64": (c_int, [_P, c_int, c_int, c_double, c_double, _P, _P, _P]),
+    "runia_tril_inverse_f64": (c_int, [_P, c_int, c_int, _P, _P]),
     "runia_roi_align_f32": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int64, c_int, c_int, c_float, c_int, c_int,
                                     _P, _P]),
     "runia_roi_align_mean_f32": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int64, c_int, c_int, c_float, c_int,

@@ -4,6 +4,7 @@ device copies of what `setup()` computed on the host.  The reference-facing clas
 `inference/postprocessors.py` and the free functions in `evaluation/entropy.py` /
 `dimensionality_reduction.py` are built on these; `bench.py` times them directly for the
 device-resident number."""
+import contextlib
 import os
 from dataclasses import dataclass
 from typing import Optional
@@ -145,13 +146,49 @@ def pca_transform(x, st: PCAState) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------
 # (a3) LaREM Mahalanobis / (a6) class-conditional Mahalanobis: factor the precision once
 # ------------------------------------------------------------------------------------------
+_blas_ctl = None
+
+
+@contextlib.contextmanager
+def host_blas_single_thread():
+    """Keeps the SMALL host linear algebra that remains in setup() (a [C, d] pseudo-inverse, a least-squares solve of
+    the fold) on the calling thread.  A multi-threaded BLAS call leaves its worker threads busy-waiting for ~100 ms
+    (OpenBLAS pthreads, measured on the B200 boxes: scripts/sweep_diag2.py); the postprocess() calls that follow a
+    setup() then find the cores the staging engine's copy threads need taken, and a 0.6 ms call takes 1.3-6 ms."""
+    global _blas_ctl
+    try:
+        from threadpoolctl import ThreadpoolController
+    except ImportError:  # pragma: no cover
+        yield
+        return
+    if _blas_ctl is None:
+        _blas_ctl = ThreadpoolController()
+    with _blas_ctl.limit(limits=1, user_api="blas"):
+        yield
+
+
+def mm64(a, b) -> np.ndarray:
+    """a @ b in float64 on the device, NumPy in / NumPy out: the matrix products of the setup() fits (a plain library
+    GEMM through torch -- not on the scoring path).  Products with a dimension below 32 stay on the calling thread."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    if min(a.shape + b.shape) < 32:
+        with host_blas_single_thread():
+            return a @ b
+    return (to_device(np.ascontiguousarray(a), torch.float64) @ to_device(np.ascontiguousarray(b), torch.float64)).cpu().numpy()
+
+
 def factor_precision(precision):
     """P (symmetric, float64) -> (Wt [r, d] float64, sign [r]) with P = sum_j sign_j w_j w_j^T.
     Eigenvalues below 1e-14 * max|lambda| are rounding residue of pinvh's rank cut and get
     sign 0."""
     P = np.asarray(precision, np.float64)
     P = 0.5 * (P + P.T)
-    lam, V = eigh(P) if (P.shape[0] >= 64 and np.isfinite(P).all()) else np.linalg.eigh(P)
+    if P.shape[0] >= 64 and np.isfinite(P).all():
+        lam, V = eigh(P)
+    else:
+        with host_blas_single_thread():
+            lam, V = np.linalg.eigh(P)
     amax = np.abs(lam).max() if lam.size else 0.0
     sign = np.sign(lam)
     sign[np.abs(lam) <= 1e-14 * amax] = 0.0
@@ -194,10 +231,12 @@ def md_fold_pca(pca_mean, components, explained_variance, whiten, md_mean, preci
         eps = np.finfo(np.asarray(explained_variance).dtype).eps
         A = comp / np.where(scale < eps, eps, scale)[:, None]
     Wt, sign = factor_precision(precision)
-    Wf = Wt @ A                                                   # [r, D0]
-    v = Wt @ np.asarray(md_mean, np.float64).reshape(-1)          # [r]
-    delta = np.linalg.lstsq(Wf, v, rcond=None)[0]
-    if np.abs(Wf @ delta - v).max() > 1e-9 * (1.0 + np.abs(v).max()):
+    Wf = mm64(Wt, A)                                              # [r, D0]
+    with host_blas_single_thread():
+        v = Wt @ np.asarray(md_mean, np.float64).reshape(-1)      # [r]
+        delta = np.linalg.lstsq(Wf, v, rcond=None)[0]
+        bad = np.abs(Wf @ delta - v).max() > 1e-9 * (1.0 + np.abs(v).max())
+    if bad:
         return None
     m = (0.0 if pca_mean is None else np.asarray(pca_mean, np.float64).reshape(-1)) + delta
     mu64 = to_device(m)
@@ -301,7 +340,7 @@ def classcond_prepare(class_mean, precision) -> ClassCondState:
     Wt, sign = factor_precision(precision)
     g = cm[valid].mean(0) if valid.any() else np.zeros(cm.shape[1])
     Mc = np.zeros((cm.shape[0], Wt.shape[0]))
-    Mc[valid] = (cm[valid] - g) @ Wt.T
+    Mc[valid] = mm64(cm[valid] - g, Wt.T)
     g64 = to_device(g)
     sg = None if np.all(sign == 1.0) else to_device(sign.astype(np.float32))
     w32 = to_device(Wt.astype(np.float32))
@@ -344,26 +383,37 @@ class GMMState:
     planes: Optional[tuple] = None
 
 
-def gmm_prepare(means, scale_tril) -> GMMState:
-    """means [C, d], scale_tril [C, d, d] (lower Cholesky factors) -> whitening blocks."""
-    from scipy.linalg import solve_triangular
+def _dev64(a) -> torch.Tensor:
+    if isinstance(a, torch.Tensor):
+        return a.detach().to(device=device(), dtype=torch.float64).contiguous()
+    return to_device(np.ascontiguousarray(a, np.float64), torch.float64)
 
-    mu = np.asarray(means, np.float64)
-    L = np.asarray(scale_tril, np.float64)
+
+def tril_inverse(L) -> torch.Tensor:
+    """L^{-1} for a batch [B, n, n] of lower-triangular float64 factors, on the device (`runia_tril_inverse_f64`)."""
+    l = _dev64(L)
+    B, n, _ = l.shape
+    X = _empty((B, n, n), torch.float64)
+    _lib.call("runia_tril_inverse_f64", l.data_ptr(), B, n, X.data_ptr(), stream_ptr())
+    return X
+
+
+def gmm_prepare(means, scale_tril) -> GMMState:
+    """means [C, d], scale_tril [C, d, d] (lower Cholesky factors; ndarray or tensor) -> whitening blocks
+    A_c = L_c^{-1} (float64 forward substitution on the device), offsets A_c mu_c and the log-normalisers."""
+    mu = _dev64(means)
+    L = _dev64(scale_tril)
     C, d = mu.shape
     dpad = (d + 127) // 128 * 128
-    At = np.zeros((C, dpad, d))
-    off = np.zeros((C, dpad))
-    logconst = np.empty(C)
-    eye = np.eye(d)
-    for c in range(C):
-        A = solve_triangular(L[c], eye, lower=True)  # L^{-1}
-        At[c, :d] = A
-        off[c, :d] = A @ mu[c]
-        logconst[c] = -np.log(np.diag(L[c])).sum() - 0.5 * d * np.log(2 * np.pi)
-    a32 = to_device(At.reshape(C * dpad, d).astype(np.float32))
-    return GMMState(a32, to_device(off.reshape(-1).astype(np.float32)),
-                    to_device(logconst.astype(np.float32)), C, d, dpad, split_tf32(a32) if d % 4 == 0 else None)
+    Linv = tril_inverse(L)
+    At = torch.zeros((C, dpad, d), dtype=torch.float64, device=mu.device)
+    At[:, :d] = Linv
+    off = torch.zeros((C, dpad), dtype=torch.float64, device=mu.device)
+    off[:, :d] = torch.bmm(Linv, mu[:, :, None])[:, :, 0]
+    logconst = -torch.log(torch.diagonal(L, dim1=1, dim2=2)).sum(1) - 0.5 * d * float(np.log(2 * np.pi))
+    a32 = At.reshape(C * dpad, d).to(torch.float32)
+    return GMMState(a32, off.reshape(-1).to(torch.float32), logconst.to(torch.float32), C, d, dpad,
+                    split_tf32(a32) if d % 4 == 0 else None)
 
 
 def gmm_lse(x, st: GMMState) -> torch.Tensor:
@@ -744,6 +794,21 @@ def centered_gram(xf: torch.Tensor, lab, centers: torch.Tensor):
     return G, cs
 
 
+def shifted_covariance(xf: torch.Tensor, center) -> np.ndarray:
+    """(x - u)^T (x - u) / N in float64 for float32 device rows x and ONE float64 centre u: what sklearn's
+    EmpiricalCovariance(assume_centered=True).fit(x - u).covariance_ holds (ViM.setup)."""
+    n, d = xf.shape
+    u = to_device(np.ascontiguousarray(center, np.float64).reshape(-1), torch.float64)
+    if u.numel() != d:
+        raise ValueError(f"centre of {u.numel()} entries for rows of width {d}")
+    G = _empty((d, d), torch.float64)
+    ws_bytes = int(_lib.raw("runia_centered_gram_workspace_bytes")(n, d))
+    ws = _empty((ws_bytes,), torch.uint8)
+    _lib.call("runia_shifted_gram_f64", xf.data_ptr(), u.data_ptr(), n, d, G.data_ptr(), None, ws.data_ptr(), ws_bytes,
+              stream_ptr())
+    return (G / n).cpu().numpy()
+
+
 def covariance_from_gram(G, cs, n_used: int) -> np.ndarray:
     """np.cov(R.T, bias=1) from the Gram matrix and column sums of the residual rows: np.cov's own re-centring
     and 1/n scaling on the d x d result."""
@@ -854,7 +919,8 @@ def _eigh_device(a_np):
     ws = _empty((ws_bytes,), torch.uint8)
     _lib.call("runia_eigh_f64", a.data_ptr(), n, evals.data_ptr(), evecs.data_ptr(), ws.data_ptr(), ws_bytes, 0, None,
               stream_ptr())
-    return evals.cpu().numpy(), evecs.cpu().numpy().T
+    resid = float((a @ evecs.T - evecs.T * evals).abs().max()) if n else 0.0  # |A V - V diag(lambda)|, V = evecs^T
+    return evals.cpu().numpy(), evecs.cpu().numpy().T, resid
 
 
 def eigh(A):
@@ -868,11 +934,11 @@ def eigh(A):
     n = A.shape[0]
     assert A.ndim == 2 and A.shape[1] == n
     A = 0.5 * (A + A.T)
-    lam, V = _eigh_device(A)
+    lam, V, resid = _eigh_device(A)
     scale = max(float(np.abs(A).max(initial=0.0)), 1e-300)
-    if np.abs(A @ V - V * lam).max() > 1e-9 * scale * max(1.0, np.sqrt(n)):
-        sigma = float(np.linalg.norm(A))
-        lam, V = _eigh_device(A + sigma * np.eye(n))
+    if resid > 1e-9 * scale * max(1.0, np.sqrt(n)):
+        sigma = float(np.sqrt((A * A).sum()))
+        lam, V, _ = _eigh_device(A + sigma * np.eye(n))
         lam = lam - sigma
     order = np.argsort(lam, kind="stable")
     return lam[order], np.ascontiguousarray(V[:, order])
@@ -886,7 +952,7 @@ def pinvh(a):
     rtol = max(a.shape) * np.finfo(np.float64).eps
     keep = np.abs(lam) > rtol * np.abs(lam).max(initial=0.0)
     u = V[:, keep]
-    return (u * (1.0 / lam[keep])) @ u.T
+    return mm64(u * (1.0 / lam[keep]), u.T)
 
 
 def cholesky_batch(A, jitter: float = 0.0, rel_pivot: float = 0.0):

@@ -145,9 +145,44 @@ __global__ void __launch_bounds__(256) cholesky_kernel(const double *__restrict_
   if (threadIdx.x == 0) fail[blockIdx.x] = bad;
 }
 
+// X = L^{-1} for a batch of lower-triangular factors (gmm_prepare's whitening blocks: the reference evaluates the
+// mixture through torch's MultivariateNormal, i.e. triangular solves against scale_tril).  Thread j of a CTA owns column j
+// of X: forward substitution down the rows, X[i][j] = -(sum_{k=j}^{i-1} L[i][k] X[k][j]) / L[i][i]; the loads of L are
+// warp-wide broadcasts, those of X coalesced; the summation order is fixed.
+__global__ void __launch_bounds__(128) tril_inverse_kernel(const double *__restrict__ L, double *__restrict__ X, int n) {
+  const double *l = L + (size_t)blockIdx.y * n * n;
+  double *x = X + (size_t)blockIdx.y * n * n;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  for (int i = 0; i < j; ++i) x[(size_t)i * n + j] = 0.0;
+  x[(size_t)j * n + j] = 1.0 / l[(size_t)j * n + j];
+  for (int i = j + 1; i < n; ++i) {
+    const double *li = l + (size_t)i * n;
+    double s0 = 0.0, s1 = 0.0;
+    int k = j;
+    for (; k + 1 < i; k += 2) {
+      s0 = fma(li[k], x[(size_t)k * n + j], s0);
+      s1 = fma(li[k + 1], x[(size_t)(k + 1) * n + j], s1);
+    }
+    if (k < i) s0 = fma(li[k], x[(size_t)k * n + j], s0);
+    x[(size_t)i * n + j] = -(s0 + s1) / li[i];
+  }
+}
+
 }  // namespace runia
 
 using namespace runia;
+
+extern "C" int runia_tril_inverse_f64(const double *L, int batch, int n, double *X, void *stream) {
+  RUNIA_NVTX();
+  RUNIA_REQUIRE(batch >= 0 && n >= 1, RUNIA_E_BADARG, "tril_inverse: bad sizes");
+  if (batch == 0) return RUNIA_OK;
+  RUNIA_REQUIRE(L && X && L != X, RUNIA_E_BADARG, "tril_inverse: null or aliased pointer");
+  RUNIA_REQUIRE(batch <= 65535, RUNIA_E_UNSUPPORTED, "tril_inverse: batch=%d not supported (max 65535)", batch);
+  tril_inverse_kernel<<<dim3((unsigned)ceil_div(n, 128), (unsigned)batch), 128, 0, (cudaStream_t)stream>>>(L, X, n);
+  count_launch();
+  return finish_launch("tril_inverse");
+}
 
 extern "C" size_t runia_eigh_workspace_bytes(int n) {
   if (n < 1) return 0;

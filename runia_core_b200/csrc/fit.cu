@@ -13,6 +13,7 @@
 //    The column sums of the residuals come out of the diagonal tiles so the host can apply np.cov's own
 //    re-centring: cov = (G - n a a^T) / n, a = colsum / n.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -82,10 +83,21 @@ __device__ __forceinline__ float gram_fetch(const float *__restrict__ X, const f
   return centers ? __fsub_rn(x, __ldg(centers + (size_t)lab * d + col)) : x;
 }
 
+// same with ONE float64 centre: r = f64(x) - u, exact in float64 (what NumPy computes for `train_f32 - u_f64`:
+// ViM.setup's EmpiricalCovariance(assume_centered=True).fit(train - u), postprocessors.py:1060-1064)
+__device__ __forceinline__ double gram_fetch64(const float *__restrict__ X, const double *__restrict__ center, int d, int64_t row,
+                                               int col, bool ok) {
+  if (!ok) return 0.0;
+  return __dsub_rn((double)__ldg(X + (size_t)row * d + col), __ldg(center + col));
+}
+
+template <bool F64C>
 __global__ void __launch_bounds__(G_THREADS) gram_f64_kernel(const float *__restrict__ X, const int32_t *__restrict__ labels,
-                                                             const float *__restrict__ centers, int64_t N, int d, int C,
+                                                             const float *__restrict__ centers,
+                                                             const double *__restrict__ center64, int64_t N, int d, int C,
                                                              int nt, int64_t rows_per_split, double *__restrict__ part,
                                                              double *__restrict__ part_cs) {
+  using RT = typename std::conditional<F64C, double, float>::type;
   __shared__ __align__(16) double As[GK][GT];
   __shared__ __align__(16) double Bs[GK][GT];
   // blockIdx.x enumerates the upper-triangular tile pairs (ti <= tj)
@@ -106,7 +118,7 @@ __global__ void __launch_bounds__(G_THREADS) gram_f64_kernel(const float *__rest
 
   double acc[4][4] = {};
   double cs[4] = {};
-  float ra[GQ], rb[GQ];
+  RT ra[GQ], rb[GQ];
   auto fetch = [&](int64_t rbase) {
 #pragma unroll
     for (int q = 0; q < GQ; ++q) {
@@ -117,8 +129,13 @@ __global__ void __launch_bounds__(G_THREADS) gram_f64_kernel(const float *__rest
         lab = labels[row];
         in = lab >= 0 && lab < C;
       }
-      ra[q] = gram_fetch(X, centers, d, row, lab, colA, in && okA);
-      rb[q] = diag ? 0.f : gram_fetch(X, centers, d, row, lab, colB, in && okB);
+      if constexpr (F64C) {
+        ra[q] = gram_fetch64(X, center64, d, row, colA, in && okA);
+        rb[q] = diag ? 0.0 : gram_fetch64(X, center64, d, row, colB, in && okB);
+      } else {
+        ra[q] = gram_fetch(X, centers, d, row, lab, colA, in && okA);
+        rb[q] = diag ? 0.f : gram_fetch(X, centers, d, row, lab, colB, in && okB);
+      }
     }
   };
   if (r0 < r1) fetch(r0);
@@ -238,10 +255,29 @@ extern "C" int runia_centered_gram_f64(const float *X, const int32_t *labels, co
                 p.part_bytes + p.cs_bytes);
   double *part = (double *)ws, *part_cs = (double *)((char *)ws + p.part_bytes);
   cudaStream_t st = (cudaStream_t)stream;
-  gram_f64_kernel<<<dim3((unsigned)p.npairs, (unsigned)p.splits), G_THREADS, 0, st>>>(X, labels, centers, N, d, C, p.nt,
-                                                                                    p.rows_per_split, part, part_cs);
+  gram_f64_kernel<false><<<dim3((unsigned)p.npairs, (unsigned)p.splits), G_THREADS, 0, st>>>(
+      X, labels, centers, nullptr, N, d, C, p.nt, p.rows_per_split, part, part_cs);
   const int64_t total = (int64_t)d * d;
   gram_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(part, part_cs, d, p.nt, p.npairs, p.splits, G, colsum);
   count_launch(2);
   return finish_launch("centered_gram");
+}
+
+extern "C" int runia_shifted_gram_f64(const float *X, const double *center, int64_t N, int d, double *G, double *colsum, void *ws,
+                                      size_t ws_bytes, void *stream) {
+  RUNIA_NVTX();
+  RUNIA_REQUIRE(N >= 1 && d >= 1, RUNIA_E_BADARG, "shifted_gram: needs N >= 1, d >= 1");
+  RUNIA_REQUIRE(X && center && G && ws, RUNIA_E_BADARG, "shifted_gram: null pointer");
+  RUNIA_REQUIRE(d <= 8192, RUNIA_E_UNSUPPORTED, "shifted_gram: d=%d not supported (max 8192)", d);
+  const GramPlan p = gram_plan(N, d);
+  RUNIA_REQUIRE(ws_bytes >= p.part_bytes + p.cs_bytes, RUNIA_E_BADARG, "shifted_gram: workspace of %zu bytes, %zu needed", ws_bytes,
+                p.part_bytes + p.cs_bytes);
+  double *part = (double *)ws, *part_cs = (double *)((char *)ws + p.part_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  gram_f64_kernel<true><<<dim3((unsigned)p.npairs, (unsigned)p.splits), G_THREADS, 0, st>>>(
+      X, nullptr, nullptr, center, N, d, 1, p.nt, p.rows_per_split, part, part_cs);
+  const int64_t total = (int64_t)d * d;
+  gram_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(part, part_cs, d, p.nt, p.npairs, p.splits, G, colsum);
+  count_launch(2);
+  return finish_launch("shifted_gram");
 }

@@ -353,7 +353,7 @@ class KNNLatentSpace(Postprocessor):
 # GMM (LaREG) and DDU: class-wise Gaussian mixture log-density   postprocessors.py:426-492, 694-786
 # ------------------------------------------------------------------------------------------------
 def _gmm_state(gmm):
-    return _ops.gmm_prepare(gmm.loc.detach().cpu().numpy(), gmm.scale_tril.detach().cpu().numpy())
+    return _ops.gmm_prepare(gmm.loc, gmm.scale_tril)
 
 
 @register_postprocessor("GMM", postprocessor_input=["latent_space_means"])
@@ -505,8 +505,9 @@ class Mahalanobis(OodPostprocessor):
 
 @register_postprocessor("vim", postprocessor_input=["features", "logits"])
 class ViM(OodPostprocessor):
-    """-alpha * ||(x-u) NS|| + logsumexp(logits) (postprocessors.py:983-1112).  setup keeps the
-    reference's host fit (pinv, EmpiricalCovariance(assume_centered=True), np.linalg.eig)."""
+    """-alpha * ||(x-u) NS|| + logsumexp(logits) (postprocessors.py:983-1112).  setup: pinv of the head on the host
+    ([C, d]); covariance of the shifted rows and its eigendecomposition on the device for float32 features of width
+    >= 64 (otherwise the reference's host expressions: EmpiricalCovariance(assume_centered=True), np.linalg.eig)."""
 
     def __init__(self, flip_sign: bool, cfg=None):
         super().__init__(flip_sign, cfg)
@@ -523,16 +524,25 @@ class ViM(OodPostprocessor):
         assert "valid_logits" in kwargs, "valid_logits must be provided for ViM"
         w, b = _linear_params(kwargs)
         train = _np(ind_train_data)
-        self.u = -np.matmul(np.linalg.pinv(w), b)
+        with _ops.host_blas_single_thread():
+            self.u = -np.matmul(np.linalg.pinv(w), b)
         if train.shape[-1] >= 2048:
             self.DIM = 1000
         elif train.shape[-1] >= 768:
             self.DIM = 512
         else:
             self.DIM = train.shape[-1] // 2
-        ec = EmpiricalCovariance(assume_centered=True)
-        ec.fit(train - self.u)
-        eig_vals, eigen_vectors = np.linalg.eig(ec.covariance_)
+        if train.dtype == np.float32 and train.ndim == 2 and train.shape[1] >= 64 and train.shape[0] > 0 \
+                and np.asarray(self.u).dtype == np.float64:
+            # device fit: float64 Gram matrix of the exactly shifted rows (`runia_shifted_gram_f64`) and the Jacobi
+            # eigensolver; the residual norm only depends on the SPAN of the discarded eigenvectors, which a symmetric
+            # solver and the reference's np.linalg.eig agree on
+            train = to_device(train)
+            eig_vals, eigen_vectors = _ops.eigh(_ops.shifted_covariance(train, self.u))
+        else:
+            ec = EmpiricalCovariance(assume_centered=True)
+            ec.fit(train - self.u)
+            eig_vals, eigen_vectors = np.linalg.eig(ec.covariance_)
         self.NS = np.ascontiguousarray((eigen_vectors.T[np.argsort(eig_vals * -1)[self.DIM:]]).T)
         st = _ops.vim_prepare(self.u, self.NS, 1.0)
         vlogit_train = to_host(_ops.residual_norm(train, st))

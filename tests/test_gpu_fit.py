@@ -209,3 +209,68 @@ def test_gmm_fit_on_device_matches_torch_expression():
     got = _ops.gmm_lse(x[:500], st).cpu().numpy()
     want = torch.logsumexp(ref.log_prob(xt[:500, None, :].double()), dim=1).numpy()
     assert np.abs(got - want).max() / np.abs(want).max() < 1e-4
+
+
+@pytest.mark.parametrize("n,d", [(50_000, 512), (3001, 70), (9, 5)])
+def test_shifted_gram_matches_float64_numpy(n, d):
+    """ViM.setup's covariance: EmpiricalCovariance(assume_centered=True).fit(train - u) with a float64 u
+    (postprocessors.py:1060-1064) = (x - u)^T (x - u) / N in float64."""
+    from runia_core_b200 import _device, _ops
+
+    rng = np.random.RandomState(3)
+    x = (rng.standard_normal((n, d)) * 2 + 1).astype(np.float32)
+    u = rng.standard_normal(d)
+    got = _ops.shifted_covariance(_device.to_device(x), u)
+    ec = EmpiricalCovariance(assume_centered=True).fit(x - u)
+    np.testing.assert_allclose(got, ec.covariance_, rtol=1e-12, atol=1e-12 * np.abs(ec.covariance_).max())
+
+
+@pytest.mark.parametrize("B,n", [(10, 512), (3, 130), (1, 1), (4, 7)])
+def test_tril_inverse_matches_scipy(B, n):
+    from scipy.linalg import solve_triangular
+
+    from runia_core_b200 import _ops
+
+    rng = np.random.RandomState(B * n)
+    L = np.tril(rng.standard_normal((B, n, n)) / np.sqrt(n)) + np.eye(n) * (1.0 + rng.rand(B, n))[:, :, None] * np.eye(n)
+    got = _ops.tril_inverse(L).cpu().numpy()
+    for b in range(B):
+        want = solve_triangular(L[b], np.eye(n), lower=True)
+        np.testing.assert_allclose(got[b], want, rtol=1e-10, atol=1e-12 * np.abs(want).max())
+        assert np.array_equal(np.triu(got[b], 1), np.zeros((n, n)))
+
+
+def test_vim_device_fit_scores_match_the_host_fit():
+    """ViM.setup with the device covariance + Jacobi eigensolver against the reference's host expressions
+    (EmpiricalCovariance + np.linalg.eig, postprocessors.py:1045-1080): same alpha and scores to 1e-6 relative -- the
+    residual norm depends on the span of the discarded eigenvectors only."""
+    from sklearn.covariance import EmpiricalCovariance as EC
+
+    from runia_core_b200 import inference as I
+
+    rng = np.random.RandomState(8)
+    C, d, n = 10, 128, 20_000
+    mix = np.eye(d) + 0.3 * rng.standard_normal((d, d)) / np.sqrt(d)
+    train = (rng.standard_normal((n, d)) @ mix * np.linspace(0.3, 2.0, d)).astype(np.float32)
+    test = (1.3 * rng.standard_normal((3000, d)) @ mix).astype(np.float32)
+    W = (0.1 * rng.standard_normal((C, d))).astype(np.float32)
+    b = rng.standard_normal(C).astype(np.float32)
+    lg = lambda x: (x @ W.T + b).astype(np.float32)  # noqa: E731
+    p = I.ViM(flip_sign=False)
+    p.setup(train, valid_feats=test, train_logits=lg(train), valid_logits=lg(test),
+            final_linear_layer_params={"weight": W, "bias": b})
+    got = p.postprocess(test, logits=lg(test))
+    # the reference's expressions on the host
+    u = -np.matmul(np.linalg.pinv(W), b)
+    DIM = d // 2
+    ec = EC(assume_centered=True).fit(train - u)
+    ev, V = np.linalg.eig(ec.covariance_)
+    NS = np.ascontiguousarray((V.T[np.argsort(ev * -1)[DIM:]]).T)
+    vl_train = np.linalg.norm(np.matmul(train - u, NS), axis=-1)
+    alpha = lg(train).max(axis=-1).mean() / vl_train.mean()
+    from scipy.special import logsumexp
+
+    want = -(np.linalg.norm(np.matmul(test - u, NS), axis=-1) * alpha) + logsumexp(lg(test), axis=-1)
+    assert abs(p.alpha - alpha) / alpha < 1e-6
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-6
