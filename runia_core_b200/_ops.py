@@ -147,6 +147,7 @@ def pca_transform(x, st: PCAState) -> torch.Tensor:
 # (a3) LaREM Mahalanobis / (a6) class-conditional Mahalanobis: factor the precision once
 # ------------------------------------------------------------------------------------------
 _blas_ctl = None
+_PINVH_FACTORS = {}  # id(precision ndarray) -> (that ndarray, eigenvalues, eigenvectors in columns, checksum); see pinvh()
 
 
 @contextlib.contextmanager
@@ -182,9 +183,12 @@ def factor_precision(precision):
     """P (symmetric, float64) -> (Wt [r, d] float64, sign [r]) with P = sum_j sign_j w_j w_j^T.
     Eigenvalues below 1e-14 * max|lambda| are rounding residue of pinvh's rank cut and get
     sign 0."""
+    cached = _PINVH_FACTORS.get(id(precision))
     P = np.asarray(precision, np.float64)
     P = 0.5 * (P + P.T)
-    if P.shape[0] >= 64 and np.isfinite(P).all():
+    if cached is not None and cached[0] is precision and cached[3] == float(P.sum()):  # same object, not edited in place
+        lam, V = cached[1], cached[2]  # this precision came out of pinvh(): its eigenpairs are already known
+    elif P.shape[0] >= 64 and np.isfinite(P).all():
         lam, V = eigh(P)
     else:
         with host_blas_single_thread():
@@ -952,7 +956,13 @@ def pinvh(a):
     rtol = max(a.shape) * np.finfo(np.float64).eps
     keep = np.abs(lam) > rtol * np.abs(lam).max(initial=0.0)
     u = V[:, keep]
-    return mm64(u * (1.0 / lam[keep]), u.T)
+    P = mm64(u * (1.0 / lam[keep]), u.T)
+    # the scorers factor the precision right after the fit (factor_precision): P = u diag(1 / lambda) u^T is that
+    # factorisation -- remembered for the array object returned here (a few entries; a copy of P misses and is redone)
+    if len(_PINVH_FACTORS) >= 4:
+        _PINVH_FACTORS.pop(next(iter(_PINVH_FACTORS)))
+    _PINVH_FACTORS[id(P)] = (P, 1.0 / lam[keep], np.ascontiguousarray(u), float((0.5 * (P + P.T)).sum()))
+    return P
 
 
 def cholesky_batch(A, jitter: float = 0.0, rel_pivot: float = 0.0):

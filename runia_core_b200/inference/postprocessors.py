@@ -533,12 +533,18 @@ class ViM(OodPostprocessor):
         else:
             self.DIM = train.shape[-1] // 2
         if train.dtype == np.float32 and train.ndim == 2 and train.shape[1] >= 64 and train.shape[0] > 0 \
-                and np.asarray(self.u).dtype == np.float64:
-            # device fit: float64 Gram matrix of the exactly shifted rows (`runia_shifted_gram_f64`) and the Jacobi
-            # eigensolver; the residual norm only depends on the SPAN of the discarded eigenvectors, which a symmetric
-            # solver and the reference's np.linalg.eig agree on
+                and np.asarray(self.u).dtype in (np.float32, np.float64):
+            # device fit: float64 Gram matrix of the shifted rows -- r = f32(x - u) for a float32 u (a float32 head:
+            # NumPy subtracts in float32; `runia_centered_gram_f64`), r = f64(x) - u for a float64 one
+            # (`runia_shifted_gram_f64`) -- and the Jacobi eigensolver.  The residual norm only depends on the SPAN of
+            # the discarded eigenvectors, which a symmetric solver and the reference's np.linalg.eig agree on.
             train = to_device(train)
-            eig_vals, eigen_vectors = _ops.eigh(_ops.shifted_covariance(train, self.u))
+            if np.asarray(self.u).dtype == np.float64:
+                cov = _ops.shifted_covariance(train, self.u)
+            else:
+                G, _ = _ops.centered_gram(train, None, to_device(np.ascontiguousarray(self.u, np.float32).reshape(1, -1)))
+                cov = (G / train.shape[0]).cpu().numpy()
+            eig_vals, eigen_vectors = _ops.eigh(cov)
         else:
             ec = EmpiricalCovariance(assume_centered=True)
             ec.fit(train - self.u)

@@ -240,7 +240,8 @@ def test_tril_inverse_matches_scipy(B, n):
         assert np.array_equal(np.triu(got[b], 1), np.zeros((n, n)))
 
 
-def test_vim_device_fit_scores_match_the_host_fit():
+@pytest.mark.parametrize("head_dtype,tol", [(np.float64, 2e-6), (np.float32, 1e-4)])
+def test_vim_device_fit_scores_match_the_host_fit(head_dtype, tol):
     """ViM.setup with the device covariance + Jacobi eigensolver against the reference's host expressions
     (EmpiricalCovariance + np.linalg.eig, postprocessors.py:1045-1080): same alpha and scores to 1e-6 relative -- the
     residual norm depends on the span of the discarded eigenvectors only."""
@@ -253,8 +254,9 @@ def test_vim_device_fit_scores_match_the_host_fit():
     mix = np.eye(d) + 0.3 * rng.standard_normal((d, d)) / np.sqrt(d)
     train = (rng.standard_normal((n, d)) @ mix * np.linspace(0.3, 2.0, d)).astype(np.float32)
     test = (1.3 * rng.standard_normal((3000, d)) @ mix).astype(np.float32)
-    W = (0.1 * rng.standard_normal((C, d))).astype(np.float32)
-    b = rng.standard_normal(C).astype(np.float32)
+    # a float64 head gives a float64 u and float64 host arithmetic upstream; a float32 head float32 throughout
+    W = (0.1 * rng.standard_normal((C, d))).astype(head_dtype)
+    b = rng.standard_normal(C).astype(head_dtype)
     lg = lambda x: (x @ W.T + b).astype(np.float32)  # noqa: E731
     p = I.ViM(flip_sign=False)
     p.setup(train, valid_feats=test, train_logits=lg(train), valid_logits=lg(test),
@@ -271,6 +273,6 @@ def test_vim_device_fit_scores_match_the_host_fit():
     from scipy.special import logsumexp
 
     want = -(np.linalg.norm(np.matmul(test - u, NS), axis=-1) * alpha) + logsumexp(lg(test), axis=-1)
-    assert abs(p.alpha - alpha) / alpha < 1e-6
-    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
-    assert np.abs(got - want).max() / np.abs(want).max() < 2e-6
+    assert u.dtype == head_dtype
+    assert abs(p.alpha - alpha) / alpha < tol
+    assert np.abs(got - want).max() / np.abs(want).max() < tol
