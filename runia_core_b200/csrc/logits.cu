@@ -144,14 +144,60 @@ logit_scores_small_kernel(const float *__restrict__ logits, int64_t N, int C, fl
 
 // Any C: one warp per row.  The row is staged in shared memory when it fits (8 rows per block), else re-read from
 // global memory (L1 / L2).  GEN over the M largest probabilities (funcs.py:371: np.sort(probs)[:, -M:]): the M-th
-// largest logit is found by a radix select on order-preserving keys (softmax is monotone, so the logits order the
-// probabilities), one warp-wide count per bit, stopping at the first bit where exactly M keys lie at or above the
+// largest logit is found by select_kth_key on order-preserving keys (softmax is monotone, so the logits order the
+// probabilities), one warp-wide count per round, stopping as soon as exactly M keys lie at or above the
 // candidate; elements tied with the M-th value have equal terms, so only their number matters.
 // PROBS: the row already holds probabilities (generalized_entropy(probs, ...) called directly, funcs.py:347-375):
 // no softmax, terms p^gamma (1 - p)^gamma with powf like NumPy's float32 power.
 __device__ __forceinline__ uint32_t okey(float v) {
   const uint32_t u = __float_as_uint(v);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// k-th largest of a row's order-preserving keys, warp-cooperative.  `count_ge(c)` returns (to every lane) how many
+// keys of the row are >= c; [kmin, kmax] are the row's smallest and largest key, n the number of keys, 1 <= k <= n.
+// Returns P with count_ge(P) >= k; exact = (count_ge(P) == k): the top k are exactly the keys >= P (P itself need
+// not be a key).  Otherwise P IS the k-th largest key and it is tied across the cut.
+// Search: an interval (lo, hi) with count_ge(lo) >= k > count_ge(hi) shrinks by alternating an interpolation step
+// (the count is assumed linear in the key between the two ends -- activations are spread over a few binades, where
+// the float bit pattern is piecewise linear in the value) with a bisection step (which bounds the rounds by 64 for
+// any input).  Typical rows of 512 activations need 5-8 rounds where a bit-by-bit radix select needs ~22 (the sign
+// and exponent bits alone are 9 rounds).
+template <class CountGE>
+__device__ __forceinline__ uint32_t select_kth_key(CountGE count_ge, uint32_t kmin, uint32_t kmax, int n, int k, bool &exact) {
+  int c_hi = count_ge(kmax);  // multiplicity of the maximum
+  if (c_hi >= k) {
+    exact = c_hi == k;
+    return kmax;
+  }
+  uint32_t lo = kmin, hi = kmax;
+  int c_lo = n;
+  for (int round = 0;; ++round) {
+    if (c_lo == k) {
+      exact = true;
+      return lo;
+    }
+    const uint32_t span = hi - lo;
+    if (span == 1u) {  // count_ge(lo) > k > count_ge(lo + 1): lo is the k-th largest key, tied
+      exact = false;
+      return lo;
+    }
+    uint32_t step = span >> 1;
+    if (!(round & 1)) {
+      const float frac = ((float)(c_lo - k) + 0.5f) / (float)(c_lo - c_hi);
+      step = (uint32_t)__float2uint_rd(__uint2float_rz(span) * frac);
+    }
+    step = min(max(step, 1u), span - 1u);
+    const uint32_t cand = lo + step;
+    const int c = count_ge(cand);
+    if (c >= k) {
+      lo = cand;
+      c_lo = c;
+    } else {
+      hi = cand;
+      c_hi = c;
+    }
+  }
 }
 
 template <bool PROBS>
@@ -193,19 +239,22 @@ logit_scores_wide_kernel(const float *__restrict__ logits, int64_t N, int C, flo
   if (M <= 0 || M >= C) {  // [:, -M:] with M >= C (or M = 0) is the whole row
     for (int c = lane; c < C; c += 32) g += term(l[c]);
   } else {
-    uint32_t prefix = 0;
-    bool exact = false;
-    for (int bit = 31; bit >= 0; --bit) {
-      const uint32_t cand = prefix | (1u << bit);
-      int cnt = 0;
-      for (int c = lane; c < C; c += 32) cnt += okey(l[c]) >= cand ? 1 : 0;
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      if (cnt >= M) prefix = cand;
-      if (cnt == M) {
-        exact = true;
-        break;
-      }
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
+    for (int c = lane; c < C; c += 32) {
+      const uint32_t k = okey(l[c]);
+      kmin = min(kmin, k);
+      kmax = max(kmax, k);
     }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    bool exact = false;
+    const uint32_t prefix = select_kth_key(
+        [&](uint32_t cand) {
+          int cnt = 0;
+          for (int c = lane; c < C; c += 32) cnt += okey(l[c]) >= cand ? 1 : 0;
+          return __reduce_add_sync(0xffffffffu, cnt);
+        },
+        kmin, kmax, C, M, exact);
     if (exact) {
       for (int c = lane; c < C; c += 32) g += okey(l[c]) >= prefix ? term(l[c]) : 0.f;
     } else {  // prefix = key of the M-th largest value, and it is tied
@@ -371,12 +420,12 @@ linear_lse_c16_kernel(const float *__restrict__ X, int64_t N, int d, const float
 // ASH-S head for C <= 16, d <= 1024: keep the k largest activations of the row, scale by
 // exp(sum_all / sum_kept), linear layer, log-sum-exp (funcs.py:230-261 + postprocessors.py:1212-1220).
 // The row lives in registers (lane l owns elements 4l + 128 i + q); the k-th largest value is found by
-// a radix select on order-preserving integer keys, one warp-wide REDUX per bit, which stops at the
-// first bit where exactly k keys lie at or above the candidate (distinct activations: ~12-16 bits);
-// only when the k-th value is tied does it run all 32 bits and rank the ties by index.
+// an interpolation / bisection search on order-preserving integer keys (select_kth_key: one warp-wide REDUX per
+// round, 5-8 rounds for distinct activations), which stops as soon as exactly k keys lie at or above the
+// candidate; only when the k-th value is tied does it narrow down to that key and rank the ties by index.
 // ------------------------------------------------------------------------------------------
 template <int CN, int NCH>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, (NCH == 1 ? 2 : 1))  // two chunks: row + keys + prefetched row need > 128 registers
 ash_lse_c16_kernel(const float *__restrict__ X, int64_t N, int d, const float *__restrict__ W,
                    const float *__restrict__ b, int C, int k_keep, float *__restrict__ out) {
   constexpr int NV = NCH * 16;
@@ -392,23 +441,35 @@ ash_lse_c16_kernel(const float *__restrict__ X, int64_t N, int d, const float *_
   const float my_bias = my_class < C ? __ldg(b + my_class) : 0.f;
   const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
   const int64_t wstride = (int64_t)gridDim.x * 8;
-  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < N; row += wstride) {
+  // the next row of this warp is in flight while the current one is selected and scored: the selection is a chain of
+  // dependent warp reductions, and without the prefetch the SM holds too few bytes in flight to cover HBM latency
+  auto load_row = [&](int64_t row, float4 (&u)[NV / 4]) {
     const float *x = X + row * (int64_t)d;
-    float v[NV];
-    uint32_t key[NV];
 #pragma unroll
     for (int g = 0; g < NV / 4; ++g) {  // g = 4 ch + i: elements 128 g + 4 lane + q
       const int j = 128 * g + 4 * lane;
-      float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (vec && j + 3 < d) {
-        u = __ldg(reinterpret_cast<const float4 *>(x + j));
-      } else {
-        if (j + 0 < d) u.x = __ldg(x + j + 0);
-        if (j + 1 < d) u.y = __ldg(x + j + 1);
-        if (j + 2 < d) u.z = __ldg(x + j + 2);
-        if (j + 3 < d) u.w = __ldg(x + j + 3);
+      u[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < N) {
+        if (vec && j + 3 < d) {
+          u[g] = __ldg(reinterpret_cast<const float4 *>(x + j));
+        } else {
+          if (j + 0 < d) u[g].x = __ldg(x + j + 0);
+          if (j + 1 < d) u[g].y = __ldg(x + j + 1);
+          if (j + 2 < d) u[g].z = __ldg(x + j + 2);
+          if (j + 3 < d) u[g].w = __ldg(x + j + 3);
+        }
       }
-      v[4 * g + 0] = u.x; v[4 * g + 1] = u.y; v[4 * g + 2] = u.z; v[4 * g + 3] = u.w;
+    }
+  };
+  float4 nx[NV / 4];
+  load_row((int64_t)blockIdx.x * 8 + warp, nx);
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < N; row += wstride) {
+    float v[NV];
+    uint32_t key[NV];
+#pragma unroll
+    for (int g = 0; g < NV / 4; ++g) {
+      const int j = 128 * g + 4 * lane;
+      v[4 * g + 0] = nx[g].x; v[4 * g + 1] = nx[g].y; v[4 * g + 2] = nx[g].z; v[4 * g + 3] = nx[g].w;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const uint32_t bits = __float_as_uint(v[4 * g + q]);
@@ -416,25 +477,29 @@ ash_lse_c16_kernel(const float *__restrict__ X, int64_t N, int d, const float *_
         key[4 * g + q] = (j + q < d) ? k : 0u;  // padding can never be selected (real keys are > 0)
       }
     }
+    load_row(row + wstride, nx);
     float s1 = 0.f;
 #pragma unroll
     for (int e = 0; e < NV; ++e) s1 += v[e];
     s1 = warp_sum32(s1);
-    // radix select of the k-th largest key
-    uint32_t prefix = 0;
-    bool exact = false;
-    for (int bit = 31; bit >= 0; --bit) {
-      const uint32_t cand = prefix | (1u << bit);
-      int cnt = 0;
+    // the k-th largest key (padding keys are 0: below every real key, never counted for a candidate >= kmin > 0)
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
 #pragma unroll
-      for (int e = 0; e < NV; ++e) cnt += (key[e] >= cand) ? 1 : 0;
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      if (cnt >= k_keep) prefix = cand;
-      if (cnt == k_keep) {
-        exact = true;  // exactly the top k lie at or above cand
-        break;
-      }
+    for (int e = 0; e < NV; ++e) {
+      kmin = min(kmin, key[e] ? key[e] : 0xffffffffu);
+      kmax = max(kmax, key[e]);
     }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    bool exact = false;
+    const uint32_t prefix = select_kth_key(
+        [&](uint32_t cand) {
+          int cnt = 0;
+#pragma unroll
+          for (int e = 0; e < NV; ++e) cnt += (key[e] >= cand) ? 1 : 0;
+          return __reduce_add_sync(0xffffffffu, cnt);
+        },
+        kmin, kmax, d, k_keep, exact);
     float s2 = 0.f;
     if (exact) {
 #pragma unroll
@@ -532,20 +597,27 @@ linear_lse_kernel(const float *__restrict__ X, int64_t N, int d, const float *__
     uint32_t tkey = 0;   // ASH: order-preserving key of the k-th largest activation
     int n_ties_keep = 0; // ASH: how many elements equal to the threshold are kept (lowest indices)
     if (ASH) {
-      // radix select on order-preserving integer keys
+      // k-th largest order-preserving integer key
       auto keyof = [](float v) -> uint32_t {
         const uint32_t u = __float_as_uint(v);
         return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
       };
-      uint32_t prefix = 0;
-      for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t cand = prefix | (1u << bit);
-        int cnt = 0;
-        for (int j = lane; j < d; j += 32) cnt += (keyof(__ldg(x + j)) >= cand) ? 1 : 0;
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (cnt >= k_keep) prefix = cand;
+      uint32_t kmin = 0xffffffffu, kmax = 0u;
+      for (int j = lane; j < d; j += 32) {
+        const uint32_t k = keyof(__ldg(x + j));
+        kmin = min(kmin, k);
+        kmax = max(kmax, k);
       }
-      tkey = prefix;
+      kmin = __reduce_min_sync(0xffffffffu, kmin);
+      kmax = __reduce_max_sync(0xffffffffu, kmax);
+      bool exact = false;  // exact: the top k are the keys >= tkey (tkey need not be a key: then no element ties with it)
+      tkey = select_kth_key(
+          [&](uint32_t cand) {
+            int cnt = 0;
+            for (int j = lane; j < d; j += 32) cnt += (keyof(__ldg(x + j)) >= cand) ? 1 : 0;
+            return __reduce_add_sync(0xffffffffu, cnt);
+          },
+          kmin, kmax, d, k_keep, exact);
       int n_gt = 0;
       float s1 = 0.f, s_gt = 0.f;
       for (int j = lane; j < d; j += 32) {
@@ -562,7 +634,7 @@ linear_lse_kernel(const float *__restrict__ X, int64_t N, int d, const float *__
       n_ties_keep = k_keep - n_gt;
       uint32_t tb = tkey;
       const float tval = __uint_as_float((tb & 0x80000000u) ? (tb & 0x7fffffffu) : ~tb);
-      const float s2 = s_gt + (float)n_ties_keep * tval;
+      const float s2 = s_gt + (n_ties_keep > 0 ? (float)n_ties_keep * tval : 0.f);
       scale = expf(s1 / s2);
     }
     float mx = -INFINITY, sm = 0.f;
@@ -662,7 +734,7 @@ linear_lse_rows4_kernel(const float *__restrict__ X, int64_t N, int d, const flo
 // ------------------------------------------------------------------------------------------
 // ASH-S pruning for any row width (funcs.py:230-261): keep the k largest activations of the row (ties with the
 // k-th value: lowest indices first), zero the rest, scale by exp(sum_all / sum_kept).  One warp per row; the
-// k-th largest value by radix select on order-preserving keys.  Feeds the general heads above (C > 16 or
+// k-th largest value by select_kth_key on order-preserving keys.  Feeds the general heads above (C > 16 or
 // d > 1024); the small heads fuse the same selection into the head kernel (ash_lse_c16_kernel).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -670,15 +742,22 @@ ash_prune_kernel(const float *__restrict__ X, int64_t N, int d, int k_keep, floa
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < N; row += (int64_t)gridDim.x * 8) {
     const float *x = X + row * (int64_t)d;
-    uint32_t prefix = 0;
-    for (int bit = 31; bit >= 0; --bit) {
-      const uint32_t cand = prefix | (1u << bit);
-      int cnt = 0;
-      for (int j = lane; j < d; j += 32) cnt += okey(__ldg(x + j)) >= cand ? 1 : 0;
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      if (cnt >= k_keep) prefix = cand;
-      if (cnt == k_keep) break;  // exactly the top k lie at or above the candidate: no tie at the cut
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
+    for (int j = lane; j < d; j += 32) {
+      const uint32_t k = okey(__ldg(x + j));
+      kmin = min(kmin, k);
+      kmax = max(kmax, k);
     }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    bool exact = false;
+    const uint32_t prefix = select_kth_key(
+        [&](uint32_t cand) {
+          int cnt = 0;
+          for (int j = lane; j < d; j += 32) cnt += okey(__ldg(x + j)) >= cand ? 1 : 0;
+          return __reduce_add_sync(0xffffffffu, cnt);
+        },
+        kmin, kmax, d, k_keep, exact);  // exact or tied, the code below only needs count(>= prefix) >= k
     int n_gt = 0;
     float s1 = 0.f, s_gt = 0.f;
     for (int j = lane; j < d; j += 32) {
@@ -827,7 +906,7 @@ static int launch_linear_lse(bool ash, const float *X, int64_t N, int d, const f
   if (ash && C <= LH_C && d <= 1024) {
     const int nch = d <= 512 ? 1 : 2;
     const size_t smem_a = (size_t)cn * nch * 512 * sizeof(float);
-    const unsigned blocks_a = (unsigned)std::min<int64_t>(ceil_div(N, 8), (int64_t)kNumSMs * 2);
+    const unsigned blocks_a = (unsigned)std::min<int64_t>(ceil_div(N, 8), (int64_t)kNumSMs * (nch == 1 ? 2 : 1));
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (cn == 4) rc = launch_ash16<4>(nch, blocks_a, smem_a, st, X, N, d, W, b, C, k_keep, out);

@@ -104,10 +104,12 @@ def test_react_dice_ash_postprocessors_imagenet_head(R):
     np.testing.assert_allclose(lg, test[:64] @ mw.T + b, rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("d,C,pct", [(768, 1000, 85), (1024, 80, 90), (2048, 10, 65), (1030, 40, 85), (130, 200, 50)])
+@pytest.mark.parametrize("d,C,pct", [(768, 1000, 85), (1024, 80, 90), (2048, 10, 65), (1030, 40, 85), (130, 200, 50),
+                                     (512, 10, 90), (1000, 16, 35), (64, 3, 99)])
 def test_ash_any_head_vs_intended_rule(R, d, C, pct):
-    """ASH-S for heads outside the fused kernel: prune kernel (radix select, ties by lowest index) + general head.
-    Rows with many exact zeros, all-equal rows, quantised rows (ties around the cut), negative activations."""
+    """ASH-S for every head: prune kernel (k-th largest by interpolation / bisection on integer keys, ties by lowest
+    index) + general head, and the fused small-head kernel.  Rows with many exact zeros, all-equal rows, quantised
+    rows (ties around the cut), negative activations, 60 binades of dynamic range, two-valued and sorted rows."""
     from runia_core_b200 import _ops
     from runia_core_b200.inference.funcs import ash_s_linear_layer
 
@@ -119,6 +121,13 @@ def test_ash_any_head_vs_intended_rule(R, d, C, pct):
     x[9::11] = np.round(x[9::11], 1)
     x[10::11] = np.round(x[10::11] * 2) / 2
     x[11] = -x[11] - 3.0
+    x[12::97] = np.exp(9.0 * rng.randn(*x[12::97].shape)).astype(np.float32)       # values over ~60 binades
+    x[13::97] = np.where(rng.rand(*x[13::97].shape) < 0.5, 0.25, 4.0)              # two values only
+    x[14::97] = np.sort(x[14::97], axis=1)                                         # ascending
+    x[15::97] = -np.sort(-x[15::97], axis=1)                                       # descending
+    x[16] = np.arange(d, dtype=np.float32) * 1e-3                                  # equidistant
+    x[17] = 1e30
+    x[17, ::3] = 1e-30
     W = (0.05 * rng.randn(C, d)).astype(np.float32)
     b = rng.randn(C).astype(np.float32)
     Wd, bd = torch.from_numpy(W).cuda(), torch.from_numpy(b).cuda()
