@@ -154,17 +154,24 @@ __device__ __forceinline__ uint32_t okey(float v) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// k-th largest of a row's order-preserving keys, warp-cooperative.  `count_ge(c)` returns (to every lane) how many
-// keys of the row are >= c; [kmin, kmax] are the row's smallest and largest key, n the number of keys, 1 <= k <= n.
-// Returns P with count_ge(P) >= k; exact = (count_ge(P) == k): the top k are exactly the keys >= P (P itself need
+// k-th largest of a row's order-preserving keys, warp-cooperative.  `for_each(f)` calls f(key) for every key this
+// lane holds; [kmin, kmax] are the row's smallest and largest key, n the number of keys, 1 <= k <= n.
+// Returns P with count(key >= P) >= k; exact = (that count == k): the top k are exactly the keys >= P (P itself need
 // not be a key).  Otherwise P IS the k-th largest key and it is tied across the cut.
-// Search: an interval (lo, hi) with count_ge(lo) >= k > count_ge(hi) shrinks by alternating an interpolation step
+// Search: an interval [lo, hi) with count(>= lo) >= k > count(>= hi) shrinks by alternating an interpolation step
 // (the count is assumed linear in the key between the two ends -- activations are spread over a few binades, where
-// the float bit pattern is piecewise linear in the value) with a bisection step (which bounds the rounds by 64 for
-// any input).  Typical rows of 512 activations need 5-8 rounds where a bit-by-bit radix select needs ~22 (the sign
-// and exponent bits alone are 9 rounds).
-template <class CountGE>
-__device__ __forceinline__ uint32_t select_kth_key(CountGE count_ge, uint32_t kmin, uint32_t kmax, int n, int k, bool &exact) {
+// the float bit pattern is piecewise linear in the value) with a bisection step (which bounds the rounds for any
+// input).  A candidate that lands in a gap of the key set (the count equals that of an end point) is replaced by the
+// nearest key on the far side of the gap, found with one more reduction: rows with an atom at the cut (post-ReLU
+// zeros, quantised activations) then finish in 4-5 rounds instead of walking the gap down to one ulp.  Typical rows
+// of 512 activations need 8-10 rounds where a bit-by-bit radix select needs ~22 (sign and exponent bits alone: 9).
+template <class ForEach>
+__device__ __forceinline__ uint32_t select_kth_key(ForEach for_each, uint32_t kmin, uint32_t kmax, int n, int k, bool &exact) {
+  auto count_ge = [&](uint32_t c) {
+    int m = 0;
+    for_each([&](uint32_t key) { m += key >= c ? 1 : 0; });
+    return __reduce_add_sync(0xffffffffu, m);
+  };
   int c_hi = count_ge(kmax);  // multiplicity of the maximum
   if (c_hi >= k) {
     exact = c_hi == k;
@@ -178,7 +185,7 @@ __device__ __forceinline__ uint32_t select_kth_key(CountGE count_ge, uint32_t km
       return lo;
     }
     const uint32_t span = hi - lo;
-    if (span == 1u) {  // count_ge(lo) > k > count_ge(lo + 1): lo is the k-th largest key, tied
+    if (span == 1u) {  // count(>= lo) > k > count(>= lo + 1): lo is the k-th largest key, tied
       exact = false;
       return lo;
     }
@@ -188,11 +195,27 @@ __device__ __forceinline__ uint32_t select_kth_key(CountGE count_ge, uint32_t km
       step = (uint32_t)__float2uint_rd(__uint2float_rz(span) * frac);
     }
     step = min(max(step, 1u), span - 1u);
-    const uint32_t cand = lo + step;
+    uint32_t cand = lo + step;
     const int c = count_ge(cand);
     if (c >= k) {
+      if (c == c_lo) {  // no key in [lo, cand): move up to the smallest key >= cand (same count)
+        uint32_t m = 0xffffffffu;
+        for_each([&](uint32_t key) { m = key >= cand ? min(m, key) : m; });
+        cand = __reduce_min_sync(0xffffffffu, m);
+      }
       lo = cand;
       c_lo = c;
+    } else if (c == c_hi) {  // no key in [cand, hi): the largest key below cand decides
+      uint32_t m = 0u;
+      for_each([&](uint32_t key) { m = key < cand ? max(m, key) : m; });
+      const uint32_t below = __reduce_max_sync(0xffffffffu, m);  // >= lo: count(>= lo) >= k > c
+      const int cb = count_ge(below);
+      if (cb >= k) {  // count(>= below) >= k > count(>= below + 1): `below` is the k-th largest key
+        exact = cb == k;
+        return below;
+      }
+      hi = below;
+      c_hi = cb;
     } else {
       hi = cand;
       c_hi = c;
@@ -249,10 +272,8 @@ logit_scores_wide_kernel(const float *__restrict__ logits, int64_t N, int C, flo
     kmax = __reduce_max_sync(0xffffffffu, kmax);
     bool exact = false;
     const uint32_t prefix = select_kth_key(
-        [&](uint32_t cand) {
-          int cnt = 0;
-          for (int c = lane; c < C; c += 32) cnt += okey(l[c]) >= cand ? 1 : 0;
-          return __reduce_add_sync(0xffffffffu, cnt);
+        [&](auto f) {
+          for (int c = lane; c < C; c += 32) f(okey(l[c]));
         },
         kmin, kmax, C, M, exact);
     if (exact) {
@@ -493,11 +514,9 @@ ash_lse_c16_kernel(const float *__restrict__ X, int64_t N, int d, const float *_
     kmax = __reduce_max_sync(0xffffffffu, kmax);
     bool exact = false;
     const uint32_t prefix = select_kth_key(
-        [&](uint32_t cand) {
-          int cnt = 0;
+        [&](auto f) {
 #pragma unroll
-          for (int e = 0; e < NV; ++e) cnt += (key[e] >= cand) ? 1 : 0;
-          return __reduce_add_sync(0xffffffffu, cnt);
+          for (int e = 0; e < NV; ++e) f(key[e]);
         },
         kmin, kmax, d, k_keep, exact);
     float s2 = 0.f;
@@ -612,10 +631,8 @@ linear_lse_kernel(const float *__restrict__ X, int64_t N, int d, const float *__
       kmax = __reduce_max_sync(0xffffffffu, kmax);
       bool exact = false;  // exact: the top k are the keys >= tkey (tkey need not be a key: then no element ties with it)
       tkey = select_kth_key(
-          [&](uint32_t cand) {
-            int cnt = 0;
-            for (int j = lane; j < d; j += 32) cnt += (keyof(__ldg(x + j)) >= cand) ? 1 : 0;
-            return __reduce_add_sync(0xffffffffu, cnt);
+          [&](auto f) {
+            for (int j = lane; j < d; j += 32) f(keyof(__ldg(x + j)));
           },
           kmin, kmax, d, k_keep, exact);
       int n_gt = 0;
@@ -752,10 +769,8 @@ ash_prune_kernel(const float *__restrict__ X, int64_t N, int d, int k_keep, floa
     kmax = __reduce_max_sync(0xffffffffu, kmax);
     bool exact = false;
     const uint32_t prefix = select_kth_key(
-        [&](uint32_t cand) {
-          int cnt = 0;
-          for (int j = lane; j < d; j += 32) cnt += okey(__ldg(x + j)) >= cand ? 1 : 0;
-          return __reduce_add_sync(0xffffffffu, cnt);
+        [&](auto f) {
+          for (int j = lane; j < d; j += 32) f(okey(__ldg(x + j)));
         },
         kmin, kmax, d, k_keep, exact);  // exact or tied, the code below only needs count(>= prefix) >= k
     int n_gt = 0;
