@@ -343,7 +343,8 @@ int runia_tril_inverse_f64(const double *L, int batch, int n, double *X, void *s
  *   x [B, C, H, W] float32; seed [n_mc, B, H, W] uint8 (non-zero = Bernoulli hit, drawn by the caller so that
  *   the RNG stream is torch's); out [B * n_mc, C] float32, row b * n_mc + m =
  *   sum over the cells kept by mask (m, b) of x[b, c] / number of kept cells   (normalised per image).
- *   n_mc <= 32.  workspace: runia_mc_dropblock_workspace_bytes(B, H, W, n_mc).
+ *   n_mc <= 32 per call (more samples: one call per 32 seeds, as the Python mirror does).  workspace:
+ *   runia_mc_dropblock_workspace_bytes(B, H, W, n_mc).
  */
 size_t runia_mc_dropblock_workspace_bytes(int B, int H, int W, int n_mc);
 int runia_mc_dropblock_mean_f32(const float *x, const uint8_t *seed, int B, int C, int H, int W, int n_mc,
