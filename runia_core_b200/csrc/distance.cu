@@ -108,7 +108,9 @@ __device__ __forceinline__ void warp_bitonic_sort(KT *key, IT *idx, int n /* pow
 // --------------------------------------------------------------------------------------------
 
 struct KnnPlan {
-  int kcap;     // candidates that survive the merge: power of two >= k + 8
+  int kseed;    // power of two >= k + 8: the seed's bound has at least this many bank rows below it
+  int kcap;     // candidates that survive the merge (re-rank capacity): kseed for the FP32 pass, a multiple of it for
+                // the single-TF32-product pass, whose wider rounding bound asks for more exact evaluations
   int fin_max;  // most entries the candidate pass may leave per (row, split); SIMT pass: exactly kcap (padded)
   int capp;     // buffer entries per (row, split): power of two, >= max(fin_max, 2 kcap + panel width)
   int splits;  // bank splits (grid.y)
@@ -222,6 +224,7 @@ struct KnnRerankArgs {
   const int32_t *buf_i;
   const int32_t *counts;  // [Nq, splits] list lengths (plan.counted) or nullptr
   float eps;                 // rounding bound of the approximate pass per unit of (|q|^2 + max_b |b|^2) / 2
+  const float *thr_fin;      // [Nq, splits] final threshold of every list of the tensor-core pass, or nullptr
   const float *qn;           // [Nq] |q|^2
   const uint32_t *bn_max;    // [1] bit pattern of max_b |b|^2 (non-negative floats order like their bits)
   int64_t idx_offset;
@@ -235,7 +238,8 @@ struct KnnRerankArgs {
   int32_t *flag_I;       // [Nq] its index
 };
 
-constexpr int RERANK_WARPS = 8;  // at most; fewer for large kcap (the per-warp scratch is 28 kcap bytes)
+constexpr int RERANK_WARPS = 8;  // at most; fewer for large kcap (the per-warp scratch is 40 kcap bytes)
+__host__ __device__ inline size_t knn_rerank_scratch(int kcap) { return (size_t)2 * kcap * 20; }  // multiple of 16
 
 __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerankArgs a) {
   extern __shared__ unsigned char dyn[];
@@ -244,26 +248,42 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerank
   if (row >= a.Nq) return;
   const int kcap = a.plan.kcap, S = a.plan.splits, capp = a.plan.capp;
   const int nbuf_max = 2 * kcap;
-  // per-warp scratch: running selection buffer keys/idx [2 kcap], exact keys [kcap] + idx [kcap]
-  const size_t per_warp = (size_t)nbuf_max * 8 + (size_t)kcap * 12;
-  unsigned char *base = dyn + (size_t)warp * ((per_warp + 15) / 16 * 16);
+  // per-warp scratch: selection buffer keys / idx [2 kcap], exact keys / idx [2 kcap]
+  unsigned char *base = dyn + (size_t)warp * knn_rerank_scratch(kcap);
   float *akey = reinterpret_cast<float *>(base);
   int32_t *aidx = reinterpret_cast<int32_t *>(base + (size_t)nbuf_max * 4);
   double *ekey = reinterpret_cast<double *>(base + (size_t)nbuf_max * 8);
-  int32_t *eidx = reinterpret_cast<int32_t *>(base + (size_t)nbuf_max * 8 + (size_t)kcap * 8);
+  int32_t *eidx = reinterpret_cast<int32_t *>(base + (size_t)nbuf_max * 16);
+
+  // one (distance, index) entry of list `s` per lane; index -1 = none
+  auto load_entry = [&](int s, int c, int n_s, float &kd, int32_t &ki) {
+    kd = INFINITY;
+    ki = -1;
+    if (c < n_s) {
+      const size_t p0 = ((size_t)row * S + s) * capp;
+      if (a.counts) {  // tensor-core pass: interleaved (distance, index) pairs
+        const float2 e = reinterpret_cast<const float2 *>(a.buf_d)[p0 + c];
+        kd = e.x;
+        ki = __float_as_int(e.y);
+      } else {         // SIMT pass: separate arrays, lists padded with index -1
+        ki = a.buf_i[p0 + c];
+        kd = a.buf_d[p0 + c];
+      }
+    }
+  };
 
   // Streaming selection of the kcap smallest approximate distances over the row's per-split lists
   // (row-major [row][split][entry]: coalesced loads).  Entries below the running threshold are
   // appended to a 2*kcap buffer in shared memory; when it would overflow it is sorted, cut back to
   // its kcap smallest and the threshold drops to the largest of them.  Entries equal to the
-  // threshold are rejected: they tie with the kcap-th kept value L, which is all the certification
-  // below needs (every rejected entry has approximate distance >= L).
+  // threshold are rejected: they tie with the kcap-th kept value, which is all the certification
+  // below needs (every rejected entry has approximate distance >= it).
   for (int e = lane; e < nbuf_max; e += 32) {
     akey[e] = INFINITY;
     aidx[e] = 0x7fffffff;
   }
   __syncwarp();
-  int n_buf = 0;
+  int n_buf = 0, n_listed = 0;
   float thr = INFINITY;
   auto cut = [&]() {  // sort the buffer, keep its kcap smallest
     warp_bitonic_sort(akey, aidx, nbuf_max);
@@ -278,22 +298,12 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerank
     __syncwarp();
   };
   for (int s = 0; s < S; ++s) {
-    const size_t p0 = ((size_t)row * S + s) * capp;
     const int n_s = a.counts ? a.counts[(size_t)row * S + s] : kcap;
     for (int c0 = 0; c0 < n_s; c0 += 32) {
-      const int c = c0 + lane;
-      float kd = INFINITY;
-      int32_t ki = -1;
-      if (c < n_s) {
-        if (a.counts) {  // tensor-core pass: interleaved (distance, index) pairs
-          const float2 e = reinterpret_cast<const float2 *>(a.buf_d)[p0 + c];
-          kd = e.x;
-          ki = __float_as_int(e.y);
-        } else {         // SIMT pass: separate arrays, lists padded with index -1
-          ki = a.buf_i[p0 + c];
-          kd = a.buf_d[p0 + c];
-        }
-      }
+      float kd;
+      int32_t ki;
+      load_entry(s, c0 + lane, n_s, kd, ki);
+      n_listed += __popc(__ballot_sync(0xffffffffu, ki >= 0));
       bool take = ki >= 0 && kd < thr;
       unsigned m = __ballot_sync(0xffffffffu, take);
       if (n_buf + __popc(m) > nbuf_max) {
@@ -315,20 +325,92 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerank
   for (int e = lane; e < kcap; e += 32) n_real += (aidx[e] != 0x7fffffff) ? 1 : 0;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) n_real += __shfl_xor_sync(0xffffffffu, n_real, off);
-  // lower bound on the approximate distance of every bank row that is NOT a candidate
   const bool list_full = (n_real == kcap);
-  const float L = list_full ? akey[kcap - 1] : INFINITY;
 
-  // exact float64 distances of the survivors, four candidates at a time (independent loads in
+  // Lower bound on the approximate distance of every bank row that is in NO list.  Tensor-core pass: the smallest of
+  // the splits' final thresholds (the seed bound, lowered where a split had to shrink its list; +inf for an unseeded
+  // split that never shrank: it listed its whole range).  SIMT pass: every split keeps its kcap smallest, so a full
+  // merged list bounds the rest by its last entry, and a merged list that is not full holds the whole bank.
+  float L_lists = INFINITY;
+  if (a.thr_fin) {
+    for (int s = lane; s < S; s += 32) L_lists = fminf(L_lists, a.thr_fin[(size_t)row * S + s]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) L_lists = fminf(L_lists, __shfl_xor_sync(0xffffffffu, L_lists, off));
+  } else if (list_full) {
+    L_lists = akey[kcap - 1];
+  }
+
+  // Which entries need their exact distance?  With |approx - exact| <= s, every true neighbour has an approximate
+  // distance <= a_k + 2 s (a_k = k-th smallest approximate distance: k rows are exactly <= a_k + s, so the exact k-th
+  // is, and a row beyond a_k + 2 s is exactly > a_k + s).  The FP32 pass has s ~ 1e-4 and this is k plus the ties; the
+  // single-TF32-product pass has s ~ 3e-3 per unit of squared norm and evaluates a few tens more.
+  const double s_row = (double)a.eps * 0.5 * ((double)a.qn[row] + (double)__uint_as_float(*a.bn_max));
+  int n_eval = n_real;
+  float L_miss = INFINITY;  // smallest approximate distance among the LISTED entries that are not evaluated
+  bool overflow = false;
+  if (n_real > a.k) {
+    const double cut_at = (double)akey[a.k - 1] + 2.0 * s_row;
+    int c = 0;
+    for (int e = lane; e < n_real; e += 32) c += ((double)akey[e] <= cut_at) ? 1 : 0;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if (c < n_real) {  // akey is sorted: the evaluated entries are [0, c), everything the selection dropped is beyond
+      n_eval = c;
+      L_miss = akey[c];
+    } else if (n_listed > n_real && a.counts) {
+      // all kcap selected entries lie within the band and the selection dropped others: a second pass over the lists
+      // collects the whole band (unsorted; up to 2 kcap entries) and the smallest distance beyond it
+      __syncwarp();
+      n_buf = 0;
+      float miss = INFINITY;
+      for (int s = 0; s < S && !overflow; ++s) {
+        const int n_s = a.counts[(size_t)row * S + s];
+        for (int c0 = 0; c0 < n_s; c0 += 32) {
+          float kd;
+          int32_t ki;
+          load_entry(s, c0 + lane, n_s, kd, ki);
+          const bool in_band = ki >= 0 && (double)kd <= cut_at;
+          if (ki >= 0 && !in_band) miss = fminf(miss, kd);
+          const unsigned m = __ballot_sync(0xffffffffu, in_band);
+          if (n_buf + __popc(m) > nbuf_max) {
+            overflow = true;  // a neighbourhood denser than the scratch: the exhaustive pass decides this row
+            break;
+          }
+          if (in_band) {
+            const int pos = n_buf + __popc(m & ((1u << lane) - 1u));
+            akey[pos] = kd;
+            aidx[pos] = ki;
+          }
+          n_buf += __popc(m);
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) miss = fminf(miss, __shfl_xor_sync(0xffffffffu, miss, off));
+      L_miss = miss;
+      n_eval = n_buf;
+      __syncwarp();
+    } else if (n_listed > n_real) {
+      L_miss = akey[kcap - 1];  // SIMT pass: what the selection dropped ties with or exceeds the last kept entry
+    }
+  }
+  const float L_rest = overflow ? -INFINITY : fminf(L_miss, L_lists);
+
+  // exact float64 distances of the evaluated entries, four candidates at a time (independent loads in
   // flight); per candidate the summation order is that of exact_sqdist_warp / the oracle
+  int npad = 32;
+  while (npad < n_eval) npad <<= 1;  // <= 2 kcap
+  for (int e = n_eval + lane; e < npad; e += 32) {
+    ekey[e] = (double)INFINITY;
+    eidx[e] = 0x7fffffff;
+  }
   const float *q = a.Q + row * (int64_t)a.d;
-  for (int c0 = 0; c0 < kcap; c0 += 4) {
+  for (int c0 = 0; c0 < n_eval; c0 += 4) {
     const float *bp[4];
     int32_t bi[4];
     double acc[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      bi[u] = aidx[c0 + u];
+      bi[u] = c0 + u < n_eval ? aidx[c0 + u] : 0x7fffffff;
       bp[u] = a.B + (int64_t)(bi[u] != 0x7fffffff ? bi[u] : 0) * a.d;
       acc[u] = 0.0;
     }
@@ -343,37 +425,36 @@ __global__ void __launch_bounds__(RERANK_WARPS * 32) knn_rerank_kernel(KnnRerank
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const double ex = warp_tree_sum_f64(acc[u]);
-      if (lane == 0) {
+      if (lane == 0 && c0 + u < npad) {
         ekey[c0 + u] = bi[u] != 0x7fffffff ? ex : (double)INFINITY;
         eidx[c0 + u] = bi[u];
       }
     }
   }
   __syncwarp();
-  warp_bitonic_sort(ekey, eidx, kcap);
+  warp_bitonic_sort(ekey, eidx, npad);
 
   const int k = a.k;
   for (int e = lane; e < k; e += 32) {
-    const bool real = e < n_real;
+    const bool real = e < n_eval;
     const double dv = real ? ekey[e] : (double)INFINITY;
     if (a.out_dist) a.out_dist[row * k + e] = real ? (float)dv : FLT_MAX;
     if (a.out_dist64) a.out_dist64[row * k + e] = dv;
     if (a.out_idx) a.out_idx[row * k + e] = real ? (int64_t)eidx[e] + a.idx_offset : -1;
   }
   if (lane == 0) {
-    const bool have_k = n_real >= k;
+    const bool have_k = n_eval >= k;
     if (a.out_kth) a.out_kth[row] = have_k ? (float)ekey[k - 1] : FLT_MAX;
-    // all bank rows are candidates when the merged list is not full
-    bool certified = !list_full;
-    // |approx - exact| <= eps * (|q|^2 + |b|^2) / 2 (|q.b| <= (|q|^2 + |b|^2) / 2; the norms themselves are rounded
-    // once): unit-norm rows (every built-in postprocessor) give eps itself, un-normalised FlatL2Index banks scale it
-    const double scale = 0.5 * ((double)a.qn[row] + (double)__uint_as_float(*a.bn_max));
-    if (list_full) certified = ((double)L - (double)a.eps * scale > ekey[k - 1]);
+    // |approx - exact| <= s_row = eps * (|q|^2 + |b|^2) / 2 (|q.b| <= (|q|^2 + |b|^2) / 2; the norms themselves are
+    // rounded once): unit-norm rows (every built-in postprocessor) give eps itself, un-normalised FlatL2Index banks
+    // scale it.  Every row that was not evaluated is exactly >= L_rest - s_row: the result stands if that is beyond the
+    // exact k-th (L_rest = inf: the whole bank was evaluated).
+    const bool certified = !(L_rest < INFINITY) || (have_k && (double)L_rest - s_row > ekey[k - 1]);
     if (!certified) {
       const int slot = atomicAdd(a.flag_count, 1);
       a.flag_rows[slot] = (int32_t)row;
-      a.flag_T[slot] = ekey[k - 1];
-      a.flag_I[slot] = eidx[k - 1];
+      a.flag_T[slot] = have_k ? ekey[k - 1] : (double)INFINITY;
+      a.flag_I[slot] = have_k ? eidx[k - 1] : 0x7fffffff;
     }
   }
 }
@@ -631,8 +712,11 @@ static void pick_splits(int64_t rowblocks, int64_t panels, int max_splits, int64
 // tensor-core pass: 256 x 256 panels per CTA pair, 74 pairs;  SIMT pass: 128 x 128 panels, 2 CTAs / SM
 static KnnPlan make_knn_plan(int64_t Nq, int64_t Nb, int k, bool tensor) {
   KnnPlan p;
-  p.kcap = 64;
-  while (p.kcap < k + 8) p.kcap <<= 1;
+  p.kseed = 64;
+  while (p.kseed < k + 8) p.kseed <<= 1;
+  // selection capacity of the re-rank (and the floor a shrinking list keeps): the single-product pass certifies
+  // through a ~50x wider rounding bound than the FP32 pass, so more rows lie within it of the k-th distance
+  p.kcap = tensor ? std::min(1024, 2 * p.kseed) : p.kseed;
   const int pw = tensor ? 256 : BN;
   p.capp = 256;
   while (p.capp < (tensor ? 2 * p.kcap : p.kcap) + pw) p.capp <<= 1;
@@ -645,7 +729,7 @@ static KnnPlan make_knn_plan(int64_t Nq, int64_t Nb, int k, bool tensor) {
 }
 
 struct KnnWorkspace {
-  size_t qn, thr_key, counts, buf_d, buf_i, flag_count, flag_rows, flag_T, flag_I, fb_d, fb_i, total;
+  size_t qn, thr_key, thr_fin, counts, buf_d, buf_i, flag_count, flag_rows, flag_T, flag_I, fb_d, fb_i, total;
 };
 constexpr int FB_GRID = 64;
 constexpr int kKnnMaxK = 1016;  // kcap = 1024 candidates per row survive the merge
@@ -659,6 +743,7 @@ static KnnWorkspace knn_layout(int64_t Nq, const KnnPlan &p) {
   };
   w.qn = take((size_t)Nq * 4);
   w.thr_key = take((size_t)Nq * 4);
+  w.thr_fin = take((size_t)Nq * p.splits * 4);
   w.counts = take((size_t)Nq * p.splits * 4);
   const size_t rows32 = (size_t)ceil_div(Nq, 32) * 32;
   w.buf_d = take(rows32 * p.splits * p.capp * 4);
@@ -699,9 +784,9 @@ struct SideStream {
 namespace tc {
 bool usable(const void *A, int K, const void *B_hi, const void *B_lo);
 int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
-                             const float *bn, int64_t Nb, int d, int kcap, int fin_max, int capp, int splits,
-                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, int32_t *counts,
-                             uint32_t *thr_key, const uint32_t *bn_max, cudaStream_t st);
+                             const float *bn, int64_t Nb, int d, int kseed, float seed_slack, int kcap, int fin_max, int capp,
+                             int splits, int64_t panels_per_split, float *buf_d, int32_t *buf_i, int32_t *counts,
+                             uint32_t *thr_key, float *thr_fin, const uint32_t *bn_max, cudaStream_t st);
 int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                           const float *bn, int64_t Nb, int d, float scale, int splits, int64_t panels_per_split,
                           float *part_m, float *part_s, cudaStream_t st);
@@ -794,10 +879,15 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   a.Q = Qn; a.B = Bn; a.row0 = 0; a.Nq = Nq; a.Nb = Nb; a.d = d; a.k = k; a.plan = plan;
   a.buf_d = buf_d; a.buf_i = buf_i;
   a.counts = plan.counted ? (const int32_t *)(ws + w.counts) : nullptr;
-  // |approx - exact| <= (2K + 8) * 2^-24 for unit-norm rows (DESIGN.md "kNN certification")
-  //   3xTF32: operand split error 2^-20 per unit of sum|q_i b_i| plus FP32 accumulation -> doubled bound;
-  // the re-rank kernel scales it by (|q|^2 + max|b|^2) / 2 for rows that are not unit-norm
-  a.eps = (float)((2.0 * d + 8.0) * 5.9604644775390625e-08 * (tensor ? 2.5 : 1.25));
+  // |approx - exact| per unit of (|q|^2 + max|b|^2) / 2 (DESIGN.md "kNN certification"; the re-rank kernel applies
+  // the scale, 1 for unit-norm rows):
+  //   FP32 SIMT pass: accumulation and the norm terms, (2K + 8) * 2^-24 * 1.25;
+  //   single TF32 product: the operands first -- A_hi truncates to 19 bits (2^-10 relative), B_hi rounds to nearest
+  //   (2^-11), on sum |q_i b_i| <= (|q|^2 + |b|^2) / 2 and doubled by the -2 q.b term -- then the same accumulation.
+  const double acc_eps = (2.0 * d + 8.0) * 5.9604644775390625e-08;
+  const double op_eps = 2.0 * (9.765625e-4 + 4.8828125e-4 + 4.76837158203125e-7);
+  a.eps = (float)(tensor ? op_eps * 1.0005 + 2.5 * acc_eps : 1.25 * acc_eps);
+  a.thr_fin = tensor ? (const float *)(ws + w.thr_fin) : nullptr;
   a.qn = qn;
   a.bn_max = (const uint32_t *)flag_count + 1;
   a.idx_offset = idx_offset;
@@ -806,8 +896,8 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   a.flag_rows = (int32_t *)(ws + w.flag_rows);
   a.flag_T = (double *)(ws + w.flag_T);
   a.flag_I = (int32_t *)(ws + w.flag_I);
-  const size_t per_warp = (((size_t)2 * plan.kcap * 8 + (size_t)plan.kcap * 12) + 15) / 16 * 16;
-  const int rw = plan.kcap <= 256 ? RERANK_WARPS : plan.kcap <= 512 ? 4 : 2;  // <= 56 KB of scratch per block
+  const size_t per_warp = knn_rerank_scratch(plan.kcap);
+  const int rw = plan.kcap <= 128 ? RERANK_WARPS : plan.kcap <= 256 ? 4 : plan.kcap <= 512 ? 2 : 1;  // <= 40 KB per block
   const size_t dyn2 = per_warp * rw;
   static PerDeviceFlag attr2;
   if (!attr2) {
@@ -849,10 +939,13 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
       const int64_t t1 = t0 + tiles / groups + (g < tiles % groups ? 1 : 0);
       const int64_t r0 = t0 * 256, r1 = std::min<int64_t>(Nq, t1 * 256);
       const size_t boff = (size_t)r0 * plan.splits * plan.capp;
-      const int rc = tc::launch_knn_candidates_tc(Qn + r0 * d, qn + r0, r1 - r0, Bn_hi, Bn_lo, Bn_sqnorm, Nb, d, plan.kcap,
+      const int rc = tc::launch_knn_candidates_tc(Qn + r0 * d, qn + r0, r1 - r0, Bn_hi, Bn_lo, Bn_sqnorm, Nb, d, plan.kseed,
+                                                  2.0f * a.eps * 1.0001f, plan.kcap,
                                                   plan.fin_max, plan.capp, plan.splits, plan.panels_per_split,
                                                   buf_d + 2 * boff, buf_i, (int32_t *)(ws + w.counts) + r0 * plan.splits,
-                                                  (uint32_t *)(ws + w.thr_key) + r0, (const uint32_t *)flag_count + 1, st);
+                                                  (uint32_t *)(ws + w.thr_key) + r0,
+                                                  (float *)(ws + w.thr_fin) + r0 * plan.splits,
+                                                  (const uint32_t *)flag_count + 1, st);
       if (rc) return rc;
       if (side && g + 1 < groups) {  // the last group's re-rank has nothing left to hide behind
         RUNIA_CUDA(cudaEventRecord(side->ev[g], st));

@@ -244,15 +244,23 @@ struct Work {
 // an instruction costs its fixed minimum, not its FLOPs).  Accumulator columns: [0, TNV/2) hi x classes of CTA 0,
 // [TNV/2, TNV) lo x the same classes, [TNV, 3TNV/2) hi x classes of CTA 1, [3TNV/2, 2TNV) lo x those; [2TNV, 3TNV)
 // A_lo x B_hi in class order.  The epilogue receives all 3 TNV columns and adds the three products.
-// NPROD = 1 (the kNN seed only): a single TF32 product A_hi x B_hi -- a third of the MMAs, no B_lo traffic, no A_lo
-// store; the caller widens whatever it derives from the result by the split's rounding bound (see KnnSeedEpi).
-template <class E, int TNV = TN, int NSTAGES = STAGES, bool NCAT = false, int NPROD = 3>
+// NPROD = 1 (the kNN seed and candidate filter): a single TF32 product A_hi x B_hi -- a third of the MMAs, no B_lo
+// traffic, no A_lo store; the caller widens whatever it derives from the result by the split's rounding bound (see
+// KnnSeedEpi).
+// DIRECT (with NPROD = 1, no prologue): the raw fp32 A tile IS the operand -- kind::tf32 reads the top 19 bits of each
+// 32-bit word, which is the truncation the converters would have written -- so the TMA load completes on the leader's
+// `full` barrier like the B planes, the converter warps have nothing to do, and a stage is one A plane + one B plane
+// (32 KB: twice the stages in the same shared memory, which is what hides the L2 -> SM latency once a stage holds only
+// 4 MMAs).
+template <class E, int TNV = TN, int NSTAGES = STAGES, bool NCAT = false, int NPROD = 3, bool DIRECT = false>
 __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const Prologue pro,
                                           const CUtensorMap *tmB_hi, const CUtensorMap *tmB_lo, const Work work,
                                           E &epi, unsigned char *smem_raw) {
   // stage = raw/hi A plane, lo A plane, this CTA's halves of the two B planes (narrow panels: smaller B planes, more stages)
   constexpr int BPLANE = (TNV / 2) * TK * 4;
-  constexpr int STG = 2 * A_PLANE_BYTES + 2 * BPLANE;
+  static_assert(!DIRECT || NPROD == 1, "the raw tile can only stand in for A_hi");
+  constexpr int STG = DIRECT ? A_PLANE_BYTES + BPLANE : 2 * A_PLANE_BYTES + 2 * BPLANE;
+  constexpr int B_OFF = DIRECT ? A_PLANE_BYTES : 2 * A_PLANE_BYTES;
   static_assert(!NCAT || 3 * TNV <= TN, "concatenated panels must fit one accumulator slot");
   static_assert(BPLANE % 1024 == 0, "B planes must keep the 1024-byte alignment of the 128B swizzle");
   static_assert(8 * (3 * NSTAGES + 4) + 8 <= SMEM_BAR_BYTES, "barrier block too small");
@@ -265,8 +273,8 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
   const uint32_t bar0 = epi_stage0 + EPI_STAGE_BYTES;
   auto sA_hi = [&](int s) { return base + s * STG; };
   auto sA_lo = [&](int s) { return base + s * STG + A_PLANE_BYTES; };
-  auto sB_hi = [&](int s) { return base + s * STG + 2 * A_PLANE_BYTES; };
-  auto sB_lo = [&](int s) { return base + s * STG + 2 * A_PLANE_BYTES + BPLANE; };
+  auto sB_hi = [&](int s) { return base + s * STG + B_OFF; };
+  auto sB_lo = [&](int s) { return base + s * STG + B_OFF + BPLANE; };  // not used when NPROD == 1
   auto full_bar = [&](int s) { return bar0 + 8 * s; };                      // used in the leader only
   auto empty_bar = [&](int s) { return bar0 + 8 * (NSTAGES + s); };          // one per CTA
   auto tfull_bar = [&](int b) { return bar0 + 8 * (2 * NSTAGES + b); };      // one per CTA
@@ -289,7 +297,7 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
     for (int k = threadIdx.x; k < nkb * TK; k += THREADS) sub_ptr[k] = k < K ? __ldg(pro.sub + k) : 0.f;
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < NSTAGES; ++s) {
-      mbar_init(full_bar(s), 1 + 2 * CONV_WARPS);  // leader's expect_tx arrival + converter warps of both CTAs
+      mbar_init(full_bar(s), DIRECT ? 1 : 1 + 2 * CONV_WARPS);  // leader's expect_tx arrival (+ converter warps of both CTAs)
       mbar_init(empty_bar(s), 1);                  // tcgen05.commit (multicast)
       mbar_init(raw_bar(s), 1);                    // this CTA's TMA warp (expect_tx)
     }
@@ -324,10 +332,15 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
             if (p == 0 && t + work.tile_step < work.tile_end)
               tma_prefetch_2d(tmA, kb * TK, (int)((t + work.tile_step) * TM2 + (int64_t)rank * TM));
             mbar_wait(empty_bar(s), ph ^ 1);
-            mbar_expect_tx(raw_bar(s), A_PLANE_BYTES);
-            tma_load_2d_local(sA_hi(s), tmA, raw_bar(s), kb * TK, row0);
-            if (rank == 0) mbar_expect_tx(full_bar(s), (NPROD == 1 ? 2 : 4) * (TNV / 2) * TK * 4);  // plane(s) of both CTAs
             const uint32_t lbar = map_to_cta(full_bar(s), 0);
+            if constexpr (DIRECT) {
+              if (rank == 0) mbar_expect_tx(full_bar(s), 2 * A_PLANE_BYTES + 2 * BPLANE);  // A tile + B_hi half of both CTAs
+              tma_load_2d_pair(sA_hi(s), tmA, lbar, kb * TK, row0);
+            } else {
+              mbar_expect_tx(raw_bar(s), A_PLANE_BYTES);
+              tma_load_2d_local(sA_hi(s), tmA, raw_bar(s), kb * TK, row0);
+              if (rank == 0) mbar_expect_tx(full_bar(s), (NPROD == 1 ? 2 : 4) * (TNV / 2) * TK * 4);  // plane(s) of both CTAs
+            }
             tma_load_2d_pair(sB_hi(s), tmB_hi, lbar, kb * TK, n0);
             if constexpr (NPROD != 1) tma_load_2d_pair(sB_lo(s), tmB_lo, lbar, kb * TK, n0);
           }
@@ -408,7 +421,7 @@ __device__ __forceinline__ void run_tiles(const CUtensorMap *tmA, int K, const P
     const uint32_t off0 = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((chunk ^ (r0 & 7)) << 4));
     const int64_t n_my_tiles =
         work.tile_first < work.tile_end ? (work.tile_end - work.tile_first + work.tile_step - 1) / work.tile_step : 0;
-    const int64_t n_items = n_my_tiles * (int64_t)n_panels * nkb;  // flat sequence of (tile, panel, k-block)
+    const int64_t n_items = DIRECT ? 0 : n_my_tiles * (int64_t)n_panels * nkb;  // flat sequence of (tile, panel, k-block)
     const uint32_t lfull0 = map_to_cta(full_bar(0), 0);  // leader's full barriers, 8 bytes apart
     const bool has_sub = pro.sub != nullptr;
     const bool has_clip = pro.clip < INFINITY;

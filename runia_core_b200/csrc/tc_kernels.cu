@@ -464,6 +464,8 @@ struct KnnEpi {
   int64_t Nq, b_hi;
   float2 *buf;              // [Nq, splits, capp] entries (approximate distance, bank index as bits)
   int32_t *counts;          // [Nq, splits] entries left in each list
+  float *thr_fin;           // [Nq, splits] final threshold of each list: every bank row of the split that is not listed
+                            // has an approximate distance >= it (+inf: the whole range is listed)
   int kcap, fin_max, capp, splits, split;
   const uint32_t *thr_key;  // [Nq] seed: order-preserving key of an upper bound on the kcap-th distance (0 = none)
   int64_t row;
@@ -471,7 +473,8 @@ struct KnnEpi {
   float q2, thr;
   int cnt;
   bool live;
-  __device__ void set_stage(uint32_t) {}
+  uint32_t stage;           // this warp's 4 KB staging buffer (shared-memory address)
+  __device__ void set_stage(uint32_t smem) { stage = smem; }
   template <class P> __device__ void bind(const P *) {}
   __device__ void begin(int, int64_t row_) {
     row = row_;
@@ -488,21 +491,39 @@ struct KnnEpi {
   // The epilogue warp runs alone on its scheduler: every instruction of this loop is on the critical path
   // of the TMEM hand-back, so a column costs one FFMA, one compare and (predicated) one address, one
   // 8-byte store and one increment; the |b|^2 terms come as eight broadcast LDG.128.
-  __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
+  // The epilogue warp runs alone on its scheduler and a panel's 256 columns must be through before the mainloop has
+  // produced the next-but-one panel (8 k-blocks of 4 MMAs at K = 256: ~5,000 cycles), so the common case -- no
+  // column of the chunk passes the filter -- is straight-line code: eight broadcast LDG.128 for the |b|^2 terms issued
+  // together, 32 FFMA, a 32-bit hit mask.  Only a thread with hits parks its 32 distances in the warp's staging
+  // buffer ([column][lane]: conflict-free) and walks the set bits (registers cannot be indexed by a bit position).
+  __device__ void consume(int64_t col0, const float (&v)[32], int, int lane) {
     if (!live) return;
     if (col0 + 32 <= b_hi) {
+      float4 b4[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) b4[g] = __ldg(reinterpret_cast<const float4 *>(bn + col0) + g);  // same address in every lane
+      float dist[32];
+      uint32_t mask = 0u;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bn + col0) + g);  // same address in every lane
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+        dist[4 * g + 0] = fmaf(-2.f, v[4 * g + 0], q2 + b4[g].x);
+        dist[4 * g + 1] = fmaf(-2.f, v[4 * g + 1], q2 + b4[g].y);
+        dist[4 * g + 2] = fmaf(-2.f, v[4 * g + 2], q2 + b4[g].z);
+        dist[4 * g + 3] = fmaf(-2.f, v[4 * g + 3], q2 + b4[g].w);
+      }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = 4 * g + u;
-          const float dist = fmaf(-2.f, v[j], q2 + bb[u]);
-          if (dist < thr) {
-            mine[cnt] = make_float2(dist, __int_as_float((int)col0 + j));
-            ++cnt;
-          }
+      for (int j = 0; j < 32; ++j) mask |= dist[j] < thr ? (1u << j) : 0u;
+      if (mask) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(stage + (uint32_t)(j * 32 + lane) * 4u), "f"(dist[j]) : "memory");
+        while (mask) {
+          const int j = __ffs((int)mask) - 1;
+          mask &= mask - 1u;
+          float dj;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(dj) : "r"(stage + (uint32_t)(j * 32 + lane) * 4u) : "memory");
+          mine[cnt] = make_float2(dj, __int_as_float((int)col0 + j));
+          ++cnt;
         }
       }
     } else {
@@ -599,12 +620,13 @@ struct KnnEpi {
   }
   __device__ void panel_done(int) {
     // overflow guard: the next panel can append at most TN entries
-    if (live && cnt > capp - TN) shrink(2 * kcap);
+    if (live && cnt > capp - TN) shrink((kcap + capp - TN) / 2);  // to between the floor and the trigger
   }
   __device__ void finish() {
     if (!live) return;
     shrink(fin_max);  // no-op unless the list is longer than the buffer guard allows
     counts[(size_t)row * splits + split] = cnt;
+    thr_fin[(size_t)row * splits + split] = thr;
   }
 };
 
@@ -614,11 +636,13 @@ struct KnnEpi {
 // kcap bank rows at distance <= B, so the main pass starts with the threshold nextafter(B) and only
 // ever buffers rows that can still matter.  Groups are independent: they are split over several CTA
 // pairs and combined with an atomic max on the order-preserving key.
-// The seed contraction is a SINGLE TF32 product (A_hi x B_hi): its distances differ from the 3xTF32 ones the candidate
-// pass compares with the threshold by at most kSeedSlack * (|q|^2 + max|b|^2) / 2 (A_hi is a 19-bit truncation: 2^-10
-// relative, B_hi rounds to nearest: 2^-11; |q.b| <= (|q|^2 + |b|^2) / 2; doubled for the -2 q.b term), so the bound is
-// widened by that much and stays an upper bound on the kcap-th smallest 3xTF32 distance.
-constexpr float kSeedSlack = 3.2e-3f;
+// Seed and candidate pass are the SAME single TF32 product (A_hi x B_hi, same instruction order: the same pair gets
+// the same approximate distance in both), so B bounds the candidate pass's own numbers.  What the single product costs
+// is distance from the EXACT value: |approx - exact| <= s = eps1 * (|q|^2 + max|b|^2) / 2 (A_hi is a 19-bit
+// truncation: 2^-10 relative, B_hi rounds to nearest: 2^-11; |q.b| <= (|q|^2 + |b|^2) / 2; doubled for the -2 q.b
+// term; plus FP32 accumulation).  The re-rank evaluates exactly every candidate within 2 s of the k-th smallest
+// approximate distance a_k, so the lists must hold every bank row below a_k + 2 s: the bound is widened by
+// `slack` = 2 eps1 per unit of (|q|^2 + max|b|^2) / 2 (B >= a_k).
 
 struct KnnSeedEpi {
   const float *qn, *bn;
@@ -626,6 +650,7 @@ struct KnnSeedEpi {
   uint32_t *thr_key;
   const uint32_t *bn_max;  // [1] bit pattern of max_b |b|^2
   int ppg;  // panels per group
+  float slack;  // widening of the bound per unit of (|q|^2 + max|b|^2) / 2
   int64_t row;
   float q2, m0, m1, m2, m3, bound;
   int in_group;
@@ -656,13 +681,28 @@ struct KnnSeedEpi {
   }
   __device__ void consume(int64_t col0, const float (&v)[32], int, int) {
     if (col0 + 32 <= b_hi) {
+      float4 b4[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) b4[g] = __ldg(reinterpret_cast<const float4 *>(bn + col0) + g);  // same address in every lane
+      float dist[32];
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bn + col0) + g);  // same address in every lane
-        insert(fmaf(-2.f, v[4 * g + 0], q2 + b4.x));
-        insert(fmaf(-2.f, v[4 * g + 1], q2 + b4.y));
-        insert(fmaf(-2.f, v[4 * g + 2], q2 + b4.z));
-        insert(fmaf(-2.f, v[4 * g + 3], q2 + b4.w));
+        dist[4 * g + 0] = fmaf(-2.f, v[4 * g + 0], q2 + b4[g].x);
+        dist[4 * g + 1] = fmaf(-2.f, v[4 * g + 1], q2 + b4[g].y);
+        dist[4 * g + 2] = fmaf(-2.f, v[4 * g + 2], q2 + b4[g].z);
+        dist[4 * g + 3] = fmaf(-2.f, v[4 * g + 3], q2 + b4[g].w);
+      }
+      // after the first columns of a group almost no chunk holds a distance below the 4th smallest so far: one
+      // 3-input-min tree decides, the insert chains run only for the groups of four that matter
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float m = fminf(fminf(dist[4 * g], dist[4 * g + 1]), fminf(dist[4 * g + 2], dist[4 * g + 3]));
+        if (m < m3) {
+          insert(dist[4 * g + 0]);
+          insert(dist[4 * g + 1]);
+          insert(dist[4 * g + 2]);
+          insert(dist[4 * g + 3]);
+        }
       }
     } else {
 #pragma unroll
@@ -682,7 +722,7 @@ struct KnnSeedEpi {
   __device__ void finish() {
     if (!live) return;
     if (in_group != 0) bound = INFINITY;  // a partial group proves nothing (the launcher never produces one)
-    bound += kSeedSlack * 0.5f * (q2 + __uint_as_float(__ldg(bn_max)));
+    bound += slack * 0.5f * (q2 + __uint_as_float(__ldg(bn_max)));
     const uint32_t key = ord_key(bound);
     atomicMax(thr_key + row, key < 0xfffffffeu ? key + 1u : key);  // exclusive bound: the filter is strict
   }
@@ -699,7 +739,7 @@ tc_knn_seed_kernel(const __grid_constant__ CUtensorMap tmA, int K, const __grid_
   w.panel_lo = (int)blockIdx.y * panels_per_split;
   w.panel_hi = min(seed_panels, w.panel_lo + panels_per_split);
   const Prologue pro{nullptr, INFINITY};
-  run_tiles<KnnSeedEpi, TN, STAGES, false, 1>(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
+  run_tiles<KnnSeedEpi, TN, 2 * STAGES, false, 1, true>(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
 template <class E>
@@ -829,7 +869,9 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap tmA, int64_t M, int K, const _
   const int64_t hi = (int64_t)w.panel_hi * TN;
   epi.b_hi = hi < NB ? hi : NB;
   const Prologue pro{nullptr, INFINITY};
-  run_tiles(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
+  // a single TF32 product: the pass is a FILTER (the re-rank recomputes every survivor exactly in float64 and certifies
+  // the result against the rounding bound of this product), at a third of the tensor work of the 3xTF32 contraction
+  run_tiles<KnnEpi, TN, 2 * STAGES, false, 1, true>(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1147,9 +1189,9 @@ namespace runia {
 namespace tc {
 // shared with distance.cu
 int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
-                             const float *bn, int64_t Nb, int d, int kcap, int fin_max, int capp, int splits,
-                             int64_t panels_per_split, float *buf_d, int32_t *buf_i, int32_t *counts,
-                             uint32_t *thr_key, const uint32_t *bn_max, cudaStream_t st) {
+                             const float *bn, int64_t Nb, int d, int kseed, float seed_slack, int kcap, int fin_max, int capp,
+                             int splits, int64_t panels_per_split, float *buf_d, int32_t *buf_i, int32_t *counts,
+                             uint32_t *thr_key, float *thr_fin, const uint32_t *bn_max, cudaStream_t st) {
   CUtensorMap ma, mh, ml;
   int rc = make_a_map(&ma, Q, Nq, d);
   if (rc) return rc;
@@ -1168,22 +1210,22 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
   }
   const int64_t tiles = ceil_div(Nq, TM2);
   const int panels = (int)ceil_div(Nb, TN);
-  // Seed: kcap / 4 groups of `ppg` full panels each.  The bound admits a fraction p ~ 10 / (256 ppg)
-  // of the bank, i.e. ~ p Nb / splits appends per (row, split); ppg is chosen to keep that near 200
-  // (no shrink in the main pass with 512-entry buffers) while the seed stays under a quarter of the bank.
-  const int groups = kcap / 4;
+  // Seed: kseed / 4 groups of `ppg` full panels each (kseed >= k + 8: the bound has at least kseed bank rows below
+  // it).  The bound admits a fraction p ~ 10 / (256 ppg) of the bank, i.e. ~ p Nb / splits appends per (row, split);
+  // ppg is chosen to keep that near 200 (no shrink in the main pass) while the seed stays under a quarter of the bank.
+  const int groups = kseed / 4;
   int ppg = (int)std::max<int64_t>(1, ceil_div(Nb, (int64_t)5120 * splits));
   ppg = (int)std::min<int64_t>(ppg, std::max<int64_t>(1, (Nb / TN) / (4 * (int64_t)groups)));
   const int seed_panels = groups * ppg;
   const bool seeded = (Nb / TN) >= 2 * (int64_t)seed_panels;
+  RUNIA_CUDA(cudaMemsetAsync(thr_key, 0, (size_t)Nq * sizeof(uint32_t), st));  // 0 = no seed (the re-rank reads it too)
   if (seeded) {
-    RUNIA_CUDA(cudaMemsetAsync(thr_key, 0, (size_t)Nq * sizeof(uint32_t), st));
     int ss = (int)std::min<int64_t>(groups, std::max<int64_t>(1, ceil_div(kNumSMs, tiles)));
     const int gps = (int)ceil_div(groups, ss);  // whole groups per seed split
     ss = (int)ceil_div(groups, gps);
     const int pps = gps * ppg;
     KnnSeedEpi seed{};
-    seed.qn = qn; seed.bn = bn; seed.Nq = Nq; seed.b_hi = Nb; seed.thr_key = thr_key; seed.bn_max = bn_max; seed.ppg = ppg;
+    seed.qn = qn; seed.bn = bn; seed.Nq = Nq; seed.b_hi = Nb; seed.thr_key = thr_key; seed.bn_max = bn_max; seed.ppg = ppg; seed.slack = seed_slack;
     dim3 grid0(2 * (unsigned)tiles, (unsigned)ss);
     tc_knn_seed_kernel<<<grid0, THREADS, smem, st>>>(ma, d, mh, ml, seed_panels, pps, seed);
     count_launch();
@@ -1193,6 +1235,7 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
   epi.buf = reinterpret_cast<float2 *>(buf_d);  // buf_d and buf_i are contiguous: one (distance, index) pair per entry
   (void)buf_i;
   epi.counts = counts;
+  epi.thr_fin = thr_fin;
   epi.kcap = kcap; epi.fin_max = fin_max; epi.capp = capp; epi.splits = splits; epi.split = 0;
   epi.thr_key = seeded ? thr_key : nullptr;
   dim3 grid(2 * (unsigned)tiles, (unsigned)splits);
