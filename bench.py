@@ -469,7 +469,7 @@ def _extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak, tf32_probe=None, bf1
     full = _ops.knn_search(q, kb, 50)
     out["knn_config2"] = {"queries_per_s": 10_000 / (ms * 1e-3), "ms": ms, "bank": [50_000, 512], "k": 50,
                           "distance_tflops": fl / (ms * 1e-3) / 1e12,
-                          "roofline": _tensor_roofline(fl, ms, tf32_probe, bf16_peak),
+                          "roofline": _tensor_roofline(fl, ms, tf32_probe, bf16_peak, products=1),
                           "exhaustive_rows": full["exhaustive_rows"]}
     # entropy: 16 MC samples x 512 dims, 60k items = 1.97 GB
     n_items, n_mc, D = 60_000, 16, 512

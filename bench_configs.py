@@ -36,15 +36,18 @@ def _hbm(alg_bytes, ms, peak):
     return {"bound": "hbm", "achieved": round(a, 1), "peak": peak, "unit": "GB/s", "frac": round(a / peak, 4)}
 
 
-def _tensor(flop, ms, tf32_probe, bf16_peak):
-    """FP32-equivalent TFLOP/s of a 3xTF32 contraction against (TF32 probe of this run) / 3; the figure derived
-    from MEASURED_PEAKS.json's dense bf16 number (/ 2 / 3) is kept beside it."""
+def _tensor(flop, ms, tf32_probe, bf16_peak, products=3):
+    """FP32-equivalent TFLOP/s of a contraction issued as `products` TF32 products per FLOP (3: the 3xTF32 scorers;
+    1: the kNN candidate filter, whose survivors are re-ranked exactly) against (TF32 probe of this run) / products;
+    the figure derived from MEASURED_PEAKS.json's dense bf16 number (/ 2 / products) is kept beside it."""
     a = flop / (ms * 1e-3) / 1e12
-    peak = (tf32_probe or bf16_peak / 2.0) / 3.0
-    return {"bound": "tensor", "achieved": round(a, 2), "peak": round(peak, 2), "unit": "TFLOP/s",
-            "frac": round(a / peak, 4),
-            "peak_source": "runia_tf32_peak_probe of this run / 3" if tf32_probe else "MEASURED_PEAKS bf16 / 2 / 3",
-            "frac_of_measured_bf16_over_6": round(a / (bf16_peak / 6.0), 4)}
+    peak = (tf32_probe or bf16_peak / 2.0) / products
+    out = {"bound": "tensor", "achieved": round(a, 2), "peak": round(peak, 2), "unit": "TFLOP/s",
+           "frac": round(a / peak, 4), "tf32_products_per_flop": products,
+           "peak_source": f"runia_tf32_peak_probe of this run / {products}" if tf32_probe
+           else f"MEASURED_PEAKS bf16 / 2 / {products}"}
+    out[f"frac_of_measured_bf16_over_{2 * products}"] = round(a / (bf16_peak / (2.0 * products)), 4)
+    return out
 
 
 def _rel(torch, got, ref):
@@ -171,7 +174,7 @@ def config4(torch, dist, _ops, world, rank, barrier, max_over_ranks, tf32_probe,
     res = {"ms": ms, "queries_per_s": nq / (ms * 1e-3), "queries": nq, "bank": [C4_SHARDS * shard_rows, d], "k": k,
            "bank_rows_per_rank": rows, "scaling": "strong (bank fixed, sharded over the ranks)", "ranks": world,
            "distance_tflops_total": round(flop / (ms * 1e-3) / 1e12, 1),
-           "roofline": _tensor(flop / world, ms, tf32_probe, bf16_peak),
+           "roofline": _tensor(flop / world, ms, tf32_probe, bf16_peak, products=1),
            "parity_sample": f"{ns} queries vs float64 brute force over all {C4_SHARDS * shard_rows} bank rows",
            "parity_idx_mismatches": idx_mismatch, "parity_max_rel_err": rel,
            "merged_identical_on_all_ranks": bool(same),

@@ -116,6 +116,7 @@ struct KnnPlan {
   int splits;  // bank splits (grid.y)
   int64_t panels_per_split;
   int counted;  // 1: the pass wrote the list lengths to `counts` (tensor-core pass); 0: lists are padded to kcap
+  int groups;   // tensor-core pass: query-tile groups; the re-rank of group g runs beside the candidate pass of g + 1
 };
 
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
@@ -724,6 +725,28 @@ static KnnPlan make_knn_plan(int64_t Nq, int64_t Nb, int k, bool tensor) {
   p.counted = tensor ? 1 : 0;
   pick_splits(ceil_div(Nq, tensor ? 256 : BM), ceil_div(Nb, pw), 16, tensor ? kNumSMs / 2 : 2 * kNumSMs, p.splits,
               p.panels_per_split);
+  // Query groups (tensor-core pass): the re-rank of group g runs on a side stream beside the candidate pass of group
+  // g + 1.  The two cannot share an SM (the candidate pass takes all of its shared memory), so what a group hides is
+  // the tail of a wave, and each group costs two launches and a pipeline fill: the largest of 1..4 groups whose
+  // launches still fill whole waves of the 74 CTA-pair slots, and only for searches long enough to notice.
+  p.groups = 1;
+  if (tensor) {
+    const int64_t tiles = ceil_div(Nq, 256), slots = kNumSMs / 2;
+    double best = 0.0;
+    for (int g = 1; g <= 4 && g <= tiles; ++g) {
+      int64_t waves = 0;
+      for (int i = 0; i < g; ++i) {
+        const int64_t t = tiles / g + (i < tiles % g ? 1 : 0);
+        waves += ceil_div(t * p.splits, slots);
+      }
+      const double eff = (double)(tiles * p.splits) / (double)(waves * slots);
+      if (g > 1 && (double)waves * (double)p.panels_per_split < 2000.0) break;  // configs[1]: ~110 panel steps
+      if (eff >= best - 0.03) {  // prefer more groups unless they cost more than 3 % of wave efficiency
+        if (eff > best) best = eff;
+        p.groups = g;
+      }
+    }
+  }
   p.fin_max = tensor ? p.capp : p.kcap;
   return p;
 }
@@ -786,7 +809,7 @@ bool usable(const void *A, int K, const void *B_hi, const void *B_lo);
 int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                              const float *bn, int64_t Nb, int d, int kseed, float seed_slack, int kcap, int fin_max, int capp,
                              int splits, int64_t panels_per_split, float *buf_d, int32_t *buf_i, int32_t *counts,
-                             uint32_t *thr_key, float *thr_fin, const uint32_t *bn_max, cudaStream_t st);
+                             uint32_t *thr_key, float *thr_fin, const uint32_t *bn_max, int phase, cudaStream_t st);
 int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                           const float *bn, int64_t Nb, int d, float scale, int splits, int64_t panels_per_split,
                           float *part_m, float *part_s, cudaStream_t st);
@@ -914,26 +937,20 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
 
   if (tensor) {
     // Query groups: the candidate pass of group g + 1 (tensor-bound, one CTA pair per SM pair) runs while the
-    // re-rank of group g (gather- and latency-bound, small blocks) runs on a side stream.  The number of groups is the
-    // largest of 1..4 whose launches still fill whole waves of the 74 CTA-pair slots.
+    // re-rank of group g (gather- and latency-bound, small blocks) runs on a side stream (make_knn_plan picks the
+    // number of groups together with the bank splits).
     const int64_t tiles = ceil_div(Nq, 256);
-    const int64_t slots = kNumSMs / 2;
-    int groups = 1;
-    double best = 0.0;
-    for (int g = 1; g <= 4 && g <= tiles; ++g) {
-      int64_t waves = 0;
-      for (int i = 0; i < g; ++i) {
-        const int64_t t = tiles / g + (i < tiles % g ? 1 : 0);
-        waves += ceil_div(t * plan.splits, slots);
-      }
-      const double eff = (double)(tiles * plan.splits) / (double)(waves * slots);
-      if (eff >= best - 0.03) {  // prefer more groups unless they cost more than 3 % of wave efficiency
-        if (eff > best) best = eff;
-        groups = g;
-      }
-    }
+    int groups = plan.groups;
     SideStream *side = groups > 1 ? SideStream::get() : nullptr;
     if (groups > 1 && !side) groups = 1;
+    if (groups > 1) {  // the seed thresholds of every row in one launch (a per-group seed would pay its latency per group)
+      const int rc = tc::launch_knn_candidates_tc(Qn, qn, Nq, Bn_hi, Bn_lo, Bn_sqnorm, Nb, d, plan.kseed,
+                                                  2.0f * a.eps * 1.0001f, plan.kcap, plan.fin_max, plan.capp, plan.splits,
+                                                  plan.panels_per_split, buf_d, buf_i, (int32_t *)(ws + w.counts),
+                                                  (uint32_t *)(ws + w.thr_key), (float *)(ws + w.thr_fin),
+                                                  (const uint32_t *)flag_count + 1, 1, st);
+      if (rc) return rc;
+    }
     int64_t t0 = 0;
     for (int g = 0; g < groups; ++g) {
       const int64_t t1 = t0 + tiles / groups + (g < tiles % groups ? 1 : 0);
@@ -945,7 +962,7 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
                                                   buf_d + 2 * boff, buf_i, (int32_t *)(ws + w.counts) + r0 * plan.splits,
                                                   (uint32_t *)(ws + w.thr_key) + r0,
                                                   (float *)(ws + w.thr_fin) + r0 * plan.splits,
-                                                  (const uint32_t *)flag_count + 1, st);
+                                                  (const uint32_t *)flag_count + 1, groups > 1 ? 2 : 3, st);
       if (rc) return rc;
       if (side && g + 1 < groups) {  // the last group's re-rank has nothing left to hide behind
         RUNIA_CUDA(cudaEventRecord(side->ev[g], st));

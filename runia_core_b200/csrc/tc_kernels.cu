@@ -1191,7 +1191,9 @@ namespace tc {
 int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                              const float *bn, int64_t Nb, int d, int kseed, float seed_slack, int kcap, int fin_max, int capp,
                              int splits, int64_t panels_per_split, float *buf_d, int32_t *buf_i, int32_t *counts,
-                             uint32_t *thr_key, float *thr_fin, const uint32_t *bn_max, cudaStream_t st) {
+                             uint32_t *thr_key, float *thr_fin, const uint32_t *bn_max, int phase, cudaStream_t st) {
+  // phase 1: the seed thresholds of these rows (thr_key; 0 where the bank is too small to seed); phase 2: the
+  // candidate pass against thresholds written before; 3: both
   CUtensorMap ma, mh, ml;
   int rc = make_a_map(&ma, Q, Nq, d);
   if (rc) return rc;
@@ -1218,8 +1220,8 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
   ppg = (int)std::min<int64_t>(ppg, std::max<int64_t>(1, (Nb / TN) / (4 * (int64_t)groups)));
   const int seed_panels = groups * ppg;
   const bool seeded = (Nb / TN) >= 2 * (int64_t)seed_panels;
-  RUNIA_CUDA(cudaMemsetAsync(thr_key, 0, (size_t)Nq * sizeof(uint32_t), st));  // 0 = no seed (the re-rank reads it too)
-  if (seeded) {
+  if (phase & 1) RUNIA_CUDA(cudaMemsetAsync(thr_key, 0, (size_t)Nq * sizeof(uint32_t), st));  // 0 = no seed
+  if (seeded && (phase & 1)) {
     int ss = (int)std::min<int64_t>(groups, std::max<int64_t>(1, ceil_div(kNumSMs, tiles)));
     const int gps = (int)ceil_div(groups, ss);  // whole groups per seed split
     ss = (int)ceil_div(groups, gps);
@@ -1230,6 +1232,7 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
     tc_knn_seed_kernel<<<grid0, THREADS, smem, st>>>(ma, d, mh, ml, seed_panels, pps, seed);
     count_launch();
   }
+  if (!(phase & 2)) return finish_launch("knn_seed_tc");
   KnnEpi epi{};
   epi.qn = qn; epi.bn = bn; epi.Nq = Nq; epi.b_hi = Nb;
   epi.buf = reinterpret_cast<float2 *>(buf_d);  // buf_d and buf_i are contiguous: one (distance, index) pair per entry
