@@ -512,22 +512,43 @@ entropy_np_kernel(const float *__restrict__ z, int64_t n_items, int n, int D, fl
         const float *mine = stage + (lane < n ? lane : 0) * ENP_STRIDE;
 #pragma unroll
         for (int q = 0; q < 8; ++q) own[q] = *reinterpret_cast<const float4 *>(mine + 4 * q);
-        // a ROLLED loop over the other samples (the accumulators live in shared memory for that): unrolled 32 times
-        // this body alone was 1,300 instructions and the kernel ran out of instruction cache (stall_no_instruction 1.2)
-#pragma unroll 1
-        for (int jj = 0; jj < n; ++jj) {
-          const float *row = stage + jj * ENP_STRIDE;
-          float m = acc[jj * 32];
+        // a loop over the other samples, FOUR rows per trip (the accumulators live in shared memory for that).  Fully
+        // unrolled (32 rows) this body was 1,300 instructions and the kernel ran out of instruction cache
+        // (stall_no_instruction 1.2); one row per trip left a single dependent chain of 16 three-input maxima per row
+        // (plus the LDS / STS of its accumulator) with four warps per scheduler to hide it: 5,300 cycles per step where
+        // the ALU pipe needs 2,300.  Four independent chains per trip fill the pipe.
+        auto fold_row = [&](const float *row, float m) {
+          float ma = m, mb = 0.f;  // two chains per row, merged at the end
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 o = *reinterpret_cast<const float4 *>(row + 4 * q);  // broadcast
-            const float2 d0 = sub2(make_float2(own[q].x, own[q].y), make_float2(o.x, o.y));
-            const float2 d1 = sub2(make_float2(own[q].z, own[q].w), make_float2(o.z, o.w));
-            m = fmaxf(fmaxf(m, fabsf(d0.x)), fabsf(d0.y));  // one 3-input FMNMX3 each (ptxas fuses this nesting only)
-            m = fmaxf(fmaxf(m, fabsf(d1.x)), fabsf(d1.y));
+          for (int q = 0; q < 8; q += 2) {
+            const float4 o0 = *reinterpret_cast<const float4 *>(row + 4 * q);  // broadcast
+            const float4 o1 = *reinterpret_cast<const float4 *>(row + 4 * q + 4);
+            const float2 d0 = sub2(make_float2(own[q].x, own[q].y), make_float2(o0.x, o0.y));
+            const float2 d1 = sub2(make_float2(own[q].z, own[q].w), make_float2(o0.z, o0.w));
+            const float2 d2 = sub2(make_float2(own[q + 1].x, own[q + 1].y), make_float2(o1.x, o1.y));
+            const float2 d3 = sub2(make_float2(own[q + 1].z, own[q + 1].w), make_float2(o1.z, o1.w));
+            ma = fmaxf(fmaxf(ma, fabsf(d0.x)), fabsf(d0.y));  // one 3-input FMNMX3 each (ptxas fuses this nesting only)
+            ma = fmaxf(fmaxf(ma, fabsf(d1.x)), fabsf(d1.y));
+            mb = fmaxf(fmaxf(mb, fabsf(d2.x)), fabsf(d2.y));
+            mb = fmaxf(fmaxf(mb, fabsf(d3.x)), fabsf(d3.y));
           }
-          acc[jj * 32] = m;
+          return fmaxf(ma, mb);
+        };
+        int jj = 0;
+#pragma unroll 1
+        for (; jj + 4 <= n; jj += 4) {
+          const float m0 = acc[(jj + 0) * 32], m1 = acc[(jj + 1) * 32], m2 = acc[(jj + 2) * 32], m3 = acc[(jj + 3) * 32];
+          const float r0 = fold_row(stage + (jj + 0) * ENP_STRIDE, m0);
+          const float r1 = fold_row(stage + (jj + 1) * ENP_STRIDE, m1);
+          const float r2 = fold_row(stage + (jj + 2) * ENP_STRIDE, m2);
+          const float r3 = fold_row(stage + (jj + 3) * ENP_STRIDE, m3);
+          acc[(jj + 0) * 32] = r0;
+          acc[(jj + 1) * 32] = r1;
+          acc[(jj + 2) * 32] = r2;
+          acc[(jj + 3) * 32] = r3;
         }
+#pragma unroll 1
+        for (; jj < n; ++jj) acc[jj * 32] = fold_row(stage + jj * ENP_STRIDE, acc[jj * 32]);
       }
     }
     if (want_joint) {
