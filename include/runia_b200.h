@@ -167,9 +167,19 @@ int runia_gmm_lse_tc(const float *X, int64_t N, int d, const float *At_hi, const
  *   The rounding bound of the certification scales with (|q|^2 + max_b |b|^2) / 2, so un-normalised rows
  *   (FlatL2Index used directly) are certified as strictly as the unit-norm rows of the postprocessors.
  *   Bn_tf32_hi / Bn_tf32_lo: optional pre-split planes of the bank (runia_split_tf32).  When both
- *     are given and d % 4 == 0 the candidate pass runs on the tcgen05 tensor cores (3xTF32, TMA-fed);
+ *     are given and d % 4 == 0 the candidate pass runs on the tcgen05 tensor cores (TMA-fed);
  *     NULL selects the FP32 SIMT pass.  The result is identical either way (exact re-rank).
  *   workspace: runia_knn_workspace_bytes(Nq, Nb, d, k) bytes of device memory.  1 <= k <= 1016.
+ * runia_knn_search_ex_f32: the same with the tensor-core candidate filter's arithmetic chosen by the caller:
+ *     filter_products = 1  one TF32 product (A_hi x B_hi; the raw query tile is the operand): a third of the tensor work;
+ *                          the re-rank evaluates exactly every candidate within twice the product's rounding bound
+ *                          (~3e-3 per unit of squared norm) of the k-th approximate distance and certifies against it;
+ *                          rows with more than 4 x (k + 8 rounded up to a power of two) bank rows inside that band take
+ *                          the exhaustive pass.  This is what runia_knn_search_f32 uses.
+ *     filter_products = 3  the FP32-faithful 3xTF32 contraction (bound ~1e-4): for banks whose neighbourhoods are
+ *                          denser than the single-product bound separates (the Python mirror measures that once per
+ *                          bank: _ops.knn_filter_products).
+ *   Same outputs, same exactness, same workspace size.
  * runia_topk_merge: merges R partial results ([R, Nq, k] float64 dist / int64 idx, each
  *   ascending) into the global top-k under the same total order -- the step after the NCCL
  *   all-gather when the bank is sharded across GPUs.  R <= 64.
@@ -182,6 +192,11 @@ int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn, const flo
                          int64_t idx_offset, float *out_dist, double *out_dist_f64,
                          int64_t *out_idx, float *out_kth, int32_t *status, void *workspace,
                          int64_t workspace_bytes, void *stream);
+int runia_knn_search_ex_f32(const float *Qn, int64_t Nq, const float *Bn, const float *Bn_sqnorm,
+                            const float *Bn_tf32_hi, const float *Bn_tf32_lo, int64_t Nb, int d, int k,
+                            int64_t idx_offset, float *out_dist, double *out_dist_f64,
+                            int64_t *out_idx, float *out_kth, int32_t *status, void *workspace,
+                            int64_t workspace_bytes, int filter_products, void *stream);
 int runia_topk_merge(const double *part_dist, const int64_t *part_idx, int R, int64_t Nq, int k,
                      float *out_dist, int64_t *out_idx, float *out_kth, void *stream);
 

@@ -54,6 +54,7 @@ _SIGS = {
     "runia_knn_workspace_bytes": (c_int64, [c_int64, c_int64, c_int, c_int]),
     "runia_knn_search_f32": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int, c_int, c_int64, _P, _P, _P, _P,
                                      _P, _P, c_int64, _P]),
+    "runia_knn_search_ex_f32": (c_int, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int, c_int, c_int64, _P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "runia_split_tf32": (c_int, [_P, c_int64, _P, _P, _P]),
     "runia_rownorm_score_tc": (c_int, [_P, c_int64, c_int, _P, _P, _P, c_int, _P, c_int, _P, c_int, c_float,
                                        _P, _P, _P]),

@@ -463,6 +463,7 @@ class KNNBank:
     sqnorm: torch.Tensor  # [Nb]
     idx_offset: int = 0
     planes: Optional[tuple] = None  # tf32 (hi, lo) planes for the tensor-core candidate pass
+    filter_products: Optional[dict] = None  # k -> 1 | 3: TF32 products of the candidate filter (knn_filter_products)
 
 
 def knn_bank(bank_normed: torch.Tensor, idx_offset: int = 0, planes: Optional[bool] = None) -> KNNBank:
@@ -476,11 +477,48 @@ class KNNOverflow(RuntimeError):
     """Kept for API compatibility: the exhaustive pass no longer has a tie-buffer limit, nothing raises this."""
 
 
+KNN_DENSITY_ROWS = 256   # bank rows sampled as queries by the density probe
+KNN_DENSITY_BAND = 200   # band population above which a row is likely to leave the single-product filter's scratch
+
+
+def knn_filter_products(bank: KNNBank, k: int) -> int:
+    """1 or 3: how many TF32 products the candidate filter of this bank uses for `k` neighbours.
+    The single-product filter certifies its result through a rounding bound of ~3e-3 per unit of squared norm; every
+    bank row within twice that of the k-th distance gets an exact evaluation, and a row with more than 4 kseed such
+    neighbours (256 at k = 50) goes to the exhaustive pass.  Synthetic high-dimensional data never gets there; a large
+    bank of real embeddings can (neighbour spacing ~1e-6 at a million rows).  So the first search of a bank at a given k
+    samples 256 bank rows as queries, searches them with the FP32-faithful 3xTF32 filter for 256 neighbours and counts
+    how many lie within the band of the k-th (the row itself excluded): if more than a tenth of the sampled rows have
+    more than 200, the bank is searched with three products (the round-1 path: 3x the tensor work, a 50x tighter bound).
+    One device -> host read per (bank, k), then cached on the bank."""
+    if bank.filter_products is None:
+        bank.filter_products = {}
+    if k in bank.filter_products:
+        return bank.filter_products[k]
+    nb, d = bank.bank.shape
+    mode = 1
+    if bank.planes is not None and _tc_ok(d) and nb > 4 * KNN_DENSITY_ROWS and k < 200:
+        m = KNN_DENSITY_ROWS
+        rows = torch.linspace(0, nb - 1, m, device=bank.bank.device, dtype=torch.float64).long()
+        q = bank.bank[rows].contiguous()
+        kk = 256
+        res = {"dist": None, "dist64": _empty((m, kk), torch.float64), "idx": None, "kth": _empty((m,), torch.float32)}
+        _knn_search_chunk(q, bank, kk, res, 0, m, False, products=3)
+        d64 = res["dist64"]
+        eps1 = 2.0 * (2.0 ** -10 + 2.0 ** -11 + 2.0 ** -21) * 1.0005 + 2.5 * (2.0 * d + 8.0) * 2.0 ** -24
+        s_row = eps1 * 0.5 * (bank.sqnorm[rows].double() + bank.sqnorm.max().double())
+        band = (d64 <= (d64[:, k] + 2.0 * s_row)[:, None]).sum(1) - 1  # entry 0 is the row itself
+        dense_rows = int((band > KNN_DENSITY_BAND).sum().item())
+        mode = 3 if dense_rows * 10 > m else 1
+    bank.filter_products[k] = mode
+    return mode
+
+
 KNN_MAX_K = 1016               # distance.cu kKnnMaxK
 KNN_WS_CHUNK_BYTES = 12 << 30  # candidate-list workspace above this is avoided by searching the queries in chunks
 
 
-def _knn_search_chunk(qn, bank, k, res, lo, hi, want_status):
+def _knn_search_chunk(qn, bank, k, res, lo, hi, want_status, products=1):
     nq, d = hi - lo, qn.shape[1]
     nb = bank.bank.shape[0]
     ws_bytes = int(_lib.raw("runia_knn_workspace_bytes")(nq, nb, d, k))
@@ -488,18 +526,19 @@ def _knn_search_chunk(qn, bank, k, res, lo, hi, want_status):
     status = _empty((4,), torch.int32)
     use_tc = _tc_ok(d) and bank.planes is not None
     off = lambda t, w: None if t is None else t.data_ptr() + lo * w * t.element_size()  # noqa: E731
-    _lib.call("runia_knn_search_f32", qn.data_ptr() + lo * d * 4, nq, bank.bank.data_ptr(), bank.sqnorm.data_ptr(),
+    _lib.call("runia_knn_search_ex_f32", qn.data_ptr() + lo * d * 4, nq, bank.bank.data_ptr(), bank.sqnorm.data_ptr(),
               bank.planes[0].data_ptr() if use_tc else None, bank.planes[1].data_ptr() if use_tc else None,
               nb, d, k, bank.idx_offset, off(res["dist"], k), off(res["dist64"], k), off(res["idx"], k),
-              off(res["kth"], 1), status.data_ptr(), ws.data_ptr(), ws_bytes, stream_ptr())
+              off(res["kth"], 1), status.data_ptr(), ws.data_ptr(), ws_bytes, int(products), stream_ptr())
     return status if want_status else None
 
 
 def knn_search(qn: torch.Tensor, bank: KNNBank, k: int, want_idx=True, want_dist=True, want_f64=False,
-               check_status=True):
+               check_status=True, products=None):
     """qn: [Nq, d] float32 CUDA (normalised for the postprocessors; any rows for FlatL2Index).  Returns
     dict(dist [Nq,k] f32, dist64, idx [Nq,k] i64, kth [Nq] f32, exhaustive_rows int).  `check_status` only fills
-    `exhaustive_rows` (one device -> host read); the search itself cannot fail on ties."""
+    `exhaustive_rows` (one device -> host read); the search itself cannot fail on ties.  `products`: TF32 products
+    of the candidate filter (1 or 3); None = what `knn_filter_products` measured for this bank."""
     nq, d = qn.shape
     nb = bank.bank.shape[0]
     res = {"dist": None, "dist64": None, "idx": None, "kth": _empty((nq,), torch.float32), "exhaustive_rows": 0}
@@ -514,10 +553,12 @@ def knn_search(qn: torch.Tensor, bank: KNNBank, k: int, want_idx=True, want_dist
     if not 1 <= k <= KNN_MAX_K:
         raise NotImplementedError(f"kNN: k={k} outside [1, {KNN_MAX_K}]")
     qn = qn.contiguous()
+    if products is None:
+        products = knn_filter_products(bank, k)
     chunk = nq
     while chunk > 256 and int(_lib.raw("runia_knn_workspace_bytes")(chunk, nb, d, k)) > KNN_WS_CHUNK_BYTES:
         chunk = (chunk // 2 + 255) // 256 * 256
-    stats = [_knn_search_chunk(qn, bank, k, res, lo, min(nq, lo + chunk), check_status)
+    stats = [_knn_search_chunk(qn, bank, k, res, lo, min(nq, lo + chunk), check_status, products)
              for lo in range(0, nq, chunk)]
     if check_status:
         res["exhaustive_rows"] = int(torch.stack(stats)[:, 0].sum().item())

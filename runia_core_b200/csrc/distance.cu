@@ -711,17 +711,20 @@ static void pick_splits(int64_t rowblocks, int64_t panels, int max_splits, int64
 }
 
 // tensor-core pass: 256 x 256 panels per CTA pair, 74 pairs;  SIMT pass: 128 x 128 panels, 2 CTAs / SM
-static KnnPlan make_knn_plan(int64_t Nq, int64_t Nb, int k, bool tensor) {
+static KnnPlan make_knn_plan(int64_t Nq, int64_t Nb, int k, bool tensor, int products = 1) {
   KnnPlan p;
   p.kseed = 64;
   while (p.kseed < k + 8) p.kseed <<= 1;
   // selection capacity of the re-rank (and the floor a shrinking list keeps): the single-product pass certifies
   // through a ~50x wider rounding bound than the FP32 pass, so more rows lie within it of the k-th distance
-  p.kcap = tensor ? std::min(1024, 2 * p.kseed) : p.kseed;
+  const bool filter1 = tensor && products == 1;
+  p.kcap = filter1 ? std::min(1024, 2 * p.kseed) : p.kseed;
   const int pw = tensor ? 256 : BN;
   p.capp = 256;
-  while (p.capp < (tensor ? 2 * p.kcap : p.kcap) + pw) p.capp <<= 1;
-  if (tensor && p.capp < 512) p.capp = 512;
+  // tensor-core pass: room for a band of up to 2 kcap + 512 rows around the k-th distance before a list has to shrink
+  // (a shrink lowers the list's final threshold into the band and sends the row to the exhaustive pass)
+  while (p.capp < (filter1 ? std::min(4 * p.kcap, 2 * p.kcap + 512) : tensor ? 2 * p.kcap : p.kcap) + pw) p.capp <<= 1;
+  if (tensor && p.capp < (filter1 ? 1024 : 512)) p.capp = filter1 ? 1024 : 512;
   p.counted = tensor ? 1 : 0;
   pick_splits(ceil_div(Nq, tensor ? 256 : BM), ceil_div(Nb, pw), 16, tensor ? kNumSMs / 2 : 2 * kNumSMs, p.splits,
               p.panels_per_split);
@@ -809,7 +812,8 @@ bool usable(const void *A, int K, const void *B_hi, const void *B_lo);
 int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                              const float *bn, int64_t Nb, int d, int kseed, float seed_slack, int kcap, int fin_max, int capp,
                              int splits, int64_t panels_per_split, float *buf_d, int32_t *buf_i, int32_t *counts,
-                             uint32_t *thr_key, float *thr_fin, const uint32_t *bn_max, int phase, cudaStream_t st);
+                             uint32_t *thr_key, float *thr_fin, const uint32_t *bn_max, int phase, int products,
+                             cudaStream_t st);
 int launch_kde_partial_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                           const float *bn, int64_t Nb, int d, float scale, int splits, int64_t panels_per_split,
                           float *part_m, float *part_s, cudaStream_t st);
@@ -863,16 +867,34 @@ extern "C" int64_t runia_knn_workspace_bytes(int64_t Nq, int64_t Nb, int d, int 
   if (Nq <= 0 || Nb <= 0 || k <= 0 || k > kKnnMaxK) return 0;
   (void)d;
   const size_t a = knn_layout(Nq, make_knn_plan(Nq, Nb, k, false)).total;
-  const size_t b = knn_layout(Nq, make_knn_plan(Nq, Nb, k, true)).total;
-  return (int64_t)(a > b ? a : b);
+  const size_t b = knn_layout(Nq, make_knn_plan(Nq, Nb, k, true, 1)).total;
+  const size_t c = knn_layout(Nq, make_knn_plan(Nq, Nb, k, true, 3)).total;
+  return (int64_t)std::max(a, std::max(b, c));
 }
+
+extern "C" int runia_knn_search_ex_f32(const float *Qn, int64_t Nq, const float *Bn, const float *Bn_sqnorm,
+                                       const float *Bn_hi, const float *Bn_lo, int64_t Nb, int d, int k,
+                                       int64_t idx_offset, float *out_dist, double *out_dist_f64, int64_t *out_idx,
+                                       float *out_kth, int32_t *status, void *workspace, int64_t workspace_bytes,
+                                       int filter_products, void *stream);
 
 extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn, const float *Bn_sqnorm,
                                     const float *Bn_hi, const float *Bn_lo, int64_t Nb, int d, int k,
                                     int64_t idx_offset, float *out_dist,
                                     double *out_dist_f64, int64_t *out_idx, float *out_kth, int32_t *status,
                                     void *workspace, int64_t workspace_bytes, void *stream) {
+  return runia_knn_search_ex_f32(Qn, Nq, Bn, Bn_sqnorm, Bn_hi, Bn_lo, Nb, d, k, idx_offset, out_dist, out_dist_f64, out_idx,
+                                 out_kth, status, workspace, workspace_bytes, 1, stream);
+}
+
+extern "C" int runia_knn_search_ex_f32(const float *Qn, int64_t Nq, const float *Bn, const float *Bn_sqnorm,
+                                       const float *Bn_hi, const float *Bn_lo, int64_t Nb, int d, int k,
+                                       int64_t idx_offset, float *out_dist, double *out_dist_f64, int64_t *out_idx,
+                                       float *out_kth, int32_t *status, void *workspace, int64_t workspace_bytes,
+                                       int filter_products, void *stream) {
   RUNIA_NVTX();
+  RUNIA_REQUIRE(filter_products == 1 || filter_products == 3, RUNIA_E_BADARG, "knn_search: filter_products=%d (1 or 3)",
+                filter_products);
   RUNIA_REQUIRE(Nq >= 0 && Nb > 0 && d > 0, RUNIA_E_BADARG, "knn_search: bad sizes Nq=%lld Nb=%lld d=%d",
                 (long long)Nq, (long long)Nb, d);
   RUNIA_REQUIRE(k >= 1 && k <= kKnnMaxK, RUNIA_E_UNSUPPORTED, "knn_search: k=%d outside [1, %d]", k, kKnnMaxK);
@@ -881,7 +903,7 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   RUNIA_REQUIRE(Qn && Bn && Bn_sqnorm && status && workspace, RUNIA_E_BADARG, "knn_search: null pointer");
   const bool tensor = Bn_hi && Bn_lo && tc::usable(Qn, d, Bn_hi, Bn_lo) &&
                       (reinterpret_cast<uintptr_t>(Bn_sqnorm) & 15) == 0;  // the epilogue reads the norms as float4
-  const KnnPlan plan = make_knn_plan(Nq, Nb, k, tensor);
+  const KnnPlan plan = make_knn_plan(Nq, Nb, k, tensor, filter_products);
   const KnnWorkspace w = knn_layout(Nq, plan);
   RUNIA_REQUIRE((size_t)workspace_bytes >= w.total, RUNIA_E_WORKSPACE, "knn_search: workspace %lld < %lld bytes",
                 (long long)workspace_bytes, (long long)w.total);
@@ -907,9 +929,15 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
   //   FP32 SIMT pass: accumulation and the norm terms, (2K + 8) * 2^-24 * 1.25;
   //   single TF32 product: the operands first -- A_hi truncates to 19 bits (2^-10 relative), B_hi rounds to nearest
   //   (2^-11), on sum |q_i b_i| <= (|q|^2 + |b|^2) / 2 and doubled by the -2 q.b term -- then the same accumulation.
+  //   3xTF32: operand split error 2^-20 per unit of sum |q_i b_i| plus the accumulation -> 2.5 x the FP32 bound.
   const double acc_eps = (2.0 * d + 8.0) * 5.9604644775390625e-08;
   const double op_eps = 2.0 * (9.765625e-4 + 4.8828125e-4 + 4.76837158203125e-7);
-  a.eps = (float)(tensor ? op_eps * 1.0005 + 2.5 * acc_eps : 1.25 * acc_eps);
+  const double eps1 = op_eps * 1.0005 + 2.5 * acc_eps;  // single product (also the seed's, in both modes)
+  a.eps = (float)(!tensor ? 1.25 * acc_eps : filter_products == 1 ? eps1 : 2.5 * acc_eps);
+  // widening of the seed bound B (a single product in both modes), per unit of (|q|^2 + max|b|^2) / 2: the lists must
+  // hold every row whose candidate-pass distance is below a_k + 2 s_c.  Same product in both passes: a_k <= B, so 2 s_1.
+  // 3xTF32 candidates: a_k <= (exact k-th) + s_3 <= B + s_1 + s_3, so s_1 + 3 s_3.
+  const float seed_slack = (float)((filter_products == 1 ? 2.0 * eps1 : eps1 + 3.0 * 2.5 * acc_eps) * 1.0001);
   a.thr_fin = tensor ? (const float *)(ws + w.thr_fin) : nullptr;
   a.qn = qn;
   a.bn_max = (const uint32_t *)flag_count + 1;
@@ -945,10 +973,10 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
     if (groups > 1 && !side) groups = 1;
     if (groups > 1) {  // the seed thresholds of every row in one launch (a per-group seed would pay its latency per group)
       const int rc = tc::launch_knn_candidates_tc(Qn, qn, Nq, Bn_hi, Bn_lo, Bn_sqnorm, Nb, d, plan.kseed,
-                                                  2.0f * a.eps * 1.0001f, plan.kcap, plan.fin_max, plan.capp, plan.splits,
+                                                  seed_slack, plan.kcap, plan.fin_max, plan.capp, plan.splits,
                                                   plan.panels_per_split, buf_d, buf_i, (int32_t *)(ws + w.counts),
                                                   (uint32_t *)(ws + w.thr_key), (float *)(ws + w.thr_fin),
-                                                  (const uint32_t *)flag_count + 1, 1, st);
+                                                  (const uint32_t *)flag_count + 1, 1, filter_products, st);
       if (rc) return rc;
     }
     int64_t t0 = 0;
@@ -957,12 +985,12 @@ extern "C" int runia_knn_search_f32(const float *Qn, int64_t Nq, const float *Bn
       const int64_t r0 = t0 * 256, r1 = std::min<int64_t>(Nq, t1 * 256);
       const size_t boff = (size_t)r0 * plan.splits * plan.capp;
       const int rc = tc::launch_knn_candidates_tc(Qn + r0 * d, qn + r0, r1 - r0, Bn_hi, Bn_lo, Bn_sqnorm, Nb, d, plan.kseed,
-                                                  2.0f * a.eps * 1.0001f, plan.kcap,
+                                                  seed_slack, plan.kcap,
                                                   plan.fin_max, plan.capp, plan.splits, plan.panels_per_split,
                                                   buf_d + 2 * boff, buf_i, (int32_t *)(ws + w.counts) + r0 * plan.splits,
                                                   (uint32_t *)(ws + w.thr_key) + r0,
                                                   (float *)(ws + w.thr_fin) + r0 * plan.splits,
-                                                  (const uint32_t *)flag_count + 1, groups > 1 ? 2 : 3, st);
+                                                  (const uint32_t *)flag_count + 1, groups > 1 ? 2 : 3, filter_products, st);
       if (rc) return rc;
       if (side && g + 1 < groups) {  // the last group's re-rank has nothing left to hide behind
         RUNIA_CUDA(cudaEventRecord(side->ev[g], st));

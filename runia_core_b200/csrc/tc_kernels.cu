@@ -853,6 +853,7 @@ tc_kde_kernel(const __grid_constant__ CUtensorMap tmA, int64_t M, int K, const _
   run_tiles(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
+template <int PRODUCTS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 tc_knn_kernel(const __grid_constant__ CUtensorMap tmA, int64_t M, int K, const __grid_constant__ CUtensorMap tmB_hi,
               const __grid_constant__ CUtensorMap tmB_lo, int panels_total, int panels_per_split, int64_t NB,
@@ -869,9 +870,14 @@ tc_knn_kernel(const __grid_constant__ CUtensorMap tmA, int64_t M, int K, const _
   const int64_t hi = (int64_t)w.panel_hi * TN;
   epi.b_hi = hi < NB ? hi : NB;
   const Prologue pro{nullptr, INFINITY};
-  // a single TF32 product: the pass is a FILTER (the re-rank recomputes every survivor exactly in float64 and certifies
-  // the result against the rounding bound of this product), at a third of the tensor work of the 3xTF32 contraction
-  run_tiles<KnnEpi, TN, 2 * STAGES, false, 1, true>(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
+  // PRODUCTS = 1: the pass is a FILTER (the re-rank recomputes every survivor exactly in float64 and certifies the
+  // result against the rounding bound of this product), at a third of the tensor work of the 3xTF32 contraction.
+  // PRODUCTS = 3: the FP32-faithful contraction, for banks whose neighbourhoods are denser than the single-product
+  // bound can separate (chosen per bank by the caller: `runia_knn_search_ex_f32`).
+  if constexpr (PRODUCTS == 1)
+    run_tiles<KnnEpi, TN, 2 * STAGES, false, 1, true>(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
+  else
+    run_tiles(&tmA, K, pro, &tmB_hi, &tmB_lo, w, epi, smem_raw);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1191,7 +1197,8 @@ namespace tc {
 int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const float *B_hi, const float *B_lo,
                              const float *bn, int64_t Nb, int d, int kseed, float seed_slack, int kcap, int fin_max, int capp,
                              int splits, int64_t panels_per_split, float *buf_d, int32_t *buf_i, int32_t *counts,
-                             uint32_t *thr_key, float *thr_fin, const uint32_t *bn_max, int phase, cudaStream_t st) {
+                             uint32_t *thr_key, float *thr_fin, const uint32_t *bn_max, int phase, int products,
+                             cudaStream_t st) {
   // phase 1: the seed thresholds of these rows (thr_key; 0 where the bank is too small to seed); phase 2: the
   // candidate pass against thresholds written before; 3: both
   CUtensorMap ma, mh, ml;
@@ -1204,7 +1211,9 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
   const size_t smem = smem_bytes(d);
   static PerDeviceFlag attr;
   if (!attr) {
-    rc = set_smem(tc_knn_kernel, kSmemMax);
+    rc = set_smem(tc_knn_kernel<1>, kSmemMax);
+    if (rc) return rc;
+    rc = set_smem(tc_knn_kernel<3>, kSmemMax);
     if (rc) return rc;
     rc = set_smem(tc_knn_seed_kernel, kSmemMax);
     if (rc) return rc;
@@ -1242,7 +1251,10 @@ int launch_knn_candidates_tc(const float *Q, const float *qn, int64_t Nq, const 
   epi.kcap = kcap; epi.fin_max = fin_max; epi.capp = capp; epi.splits = splits; epi.split = 0;
   epi.thr_key = seeded ? thr_key : nullptr;
   dim3 grid(2 * (unsigned)tiles, (unsigned)splits);
-  tc_knn_kernel<<<grid, THREADS, smem, st>>>(ma, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
+  if (products == 1)
+    tc_knn_kernel<1><<<grid, THREADS, smem, st>>>(ma, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
+  else
+    tc_knn_kernel<3><<<grid, THREADS, smem, st>>>(ma, Nq, d, mh, ml, panels, (int)panels_per_split, Nb, 0, epi);
   count_launch();
   return finish_launch("knn_candidates_tc");
 }

@@ -238,6 +238,57 @@ def test_knn_many_rows_tie_at_kth_distance(R):
     assert np.array_equal(s, ref)
 
 
+@pytest.mark.parametrize("cluster,spread,expect_exhaustive", [(90, 2e-3, False), (230, 1e-3, False), (700, 5e-4, True)])
+def test_knn_dense_neighbourhoods_within_the_single_product_bound(R, cluster, spread, expect_exhaustive):
+    """The candidate pass is one TF32 product: its distances are within ~3e-3 of the exact ones for unit-norm rows, and
+    the re-rank evaluates exactly every candidate within twice that of the k-th approximate distance.  Clusters of
+    DISTINCT bank rows packed far more tightly than the bound around each query: 90 rows (a prefix of the 128 kept
+    survivors), 230 rows (all survivors in the band: the second pass over the lists collects it), 700 rows (denser than
+    the scratch: the exhaustive pass).  Neighbours and distances must equal the float64 brute force bit for bit."""
+    from runia_core_b200 import _ops
+
+    rng = np.random.RandomState(cluster)
+    d, k = 256, 50
+    nq = min(300, 60_000 // cluster)  # every query has its own cluster (a query WITHOUT one would see some other
+    bank = rng.randn(60_000, d).astype(np.float32)  # query's whole cluster at one distance: a band of its own)
+    q = rng.randn(nq, d).astype(np.float32)
+    for r in range(nq):  # query r sits next to bank rows [r * cluster, (r + 1) * cluster)
+        bank[r * cluster:(r + 1) * cluster] = q[r] + (spread * np.sqrt(d) * rng.randn(cluster, d)).astype(np.float32)
+    bn, qn = _ops.normalize_rows(bank), _ops.normalize_rows(q)
+    res = _ops.knn_search(qn, _ops.knn_bank(bn), k, products=1)  # the single-product filter, whatever the probe says
+    D, I = O.flat_l2_search_tree(bn.cpu().numpy(), qn.cpu().numpy(), k)
+    assert np.array_equal(res["idx"].cpu().numpy(), I)
+    assert np.array_equal(res["dist"].cpu().numpy(), D)
+    assert (res["exhaustive_rows"] > 0) == expect_exhaustive, res["exhaustive_rows"]
+
+
+def test_knn_dense_bank_selects_the_three_product_filter(R):
+    """A bank whose rows have hundreds of neighbours inside the single-product rounding band (low intrinsic
+    dimension: points on a circle embedded in 64-d) must be searched with the 3xTF32 filter -- chosen by the
+    one-off density probe -- and a spread-out bank with the single product; both exact, few exhaustive rows."""
+    from runia_core_b200 import _ops
+
+    rng = np.random.RandomState(77)
+    d, k = 64, 50
+    t = rng.rand(40_000) * 2 * np.pi
+    basis = np.linalg.qr(rng.randn(d, 2))[0]
+    dense = (np.stack([np.cos(t), np.sin(t)], 1) @ basis.T).astype(np.float32)  # neighbour spacing ~1e-8 in d^2
+    bank = _ops.knn_bank(_ops.normalize_rows(dense))
+    assert _ops.knn_filter_products(bank, k) == 3
+    tq = rng.rand(500) * 2 * np.pi
+    q = _ops.normalize_rows((np.stack([np.cos(tq), np.sin(tq)], 1) @ basis.T).astype(np.float32))
+    res = _ops.knn_search(q, bank, k)
+    D, I = O.flat_l2_search_tree(bank.bank.cpu().numpy(), q.cpu().numpy(), k)
+    assert np.array_equal(res["idx"].cpu().numpy(), I)
+    assert np.array_equal(res["dist"].cpu().numpy(), D)
+    spread = _ops.knn_bank(_ops.normalize_rows(rng.randn(40_000, d).astype(np.float32)))
+    assert _ops.knn_filter_products(spread, k) == 1
+    res1 = _ops.knn_search(q, spread, k, products=1)
+    res3 = _ops.knn_search(q, spread, k, products=3)
+    assert torch.equal(res1["idx"], res3["idx"]) and torch.equal(res1["dist"], res3["dist"])
+    assert res1["exhaustive_rows"] == 0
+
+
 def test_flat_l2_index_unnormalised_vectors(R):
     """FlatL2Index is public (stand-in for faiss.IndexFlatL2): vectors with norms ~30 and squared distances ~1e3.
     The certification bound scales with the norms, so near-ties at rank k still reach the exhaustive pass."""
