@@ -470,7 +470,8 @@ def _extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak, tf32_probe=None, bf1
     out["knn_config2"] = {"queries_per_s": 10_000 / (ms * 1e-3), "ms": ms, "bank": [50_000, 512], "k": 50,
                           "distance_tflops": fl / (ms * 1e-3) / 1e12,
                           "roofline": _tensor_roofline(fl, ms, tf32_probe, bf16_peak, products=1),
-                          "exhaustive_rows": full["exhaustive_rows"]}
+                          "exhaustive_rows": full["exhaustive_rows"],
+                          "filter_tf32_products": _ops.knn_filter_products(kb, 50)}
     # entropy: 16 MC samples x 512 dims, 60k items = 1.97 GB
     n_items, n_mc, D = 60_000, 16, 512
     z = torch.randn(n_items, 1, D, generator=g, device=dev) + 0.1 * torch.randn(n_items, n_mc, D, generator=g, device=dev)

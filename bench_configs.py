@@ -177,6 +177,7 @@ def config4(torch, dist, _ops, world, rank, barrier, max_over_ranks, tf32_probe,
            "roofline": _tensor(flop / world, ms, tf32_probe, bf16_peak, products=1),
            "parity_sample": f"{ns} queries vs float64 brute force over all {C4_SHARDS * shard_rows} bank rows",
            "parity_idx_mismatches": idx_mismatch, "parity_max_rel_err": rel,
+           "filter_tf32_products": _ops.knn_filter_products(kb, k),
            "merged_identical_on_all_ranks": bool(same),
            "exchange_bytes_per_rank": nq * k * 16}
     del kb, bank, q
