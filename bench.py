@@ -492,7 +492,8 @@ def _extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak, tf32_probe=None, bf1
     alg = n_items * (n_mc * D * 4 + D * 8 + 8)
     out["entropy_config1"] = {"items_per_s": n_items / (ms * 1e-3), "ms": ms, "n_mc": n_mc, "D": D,
                               "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak,
-                                           "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}}
+                                           "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak},
+                              "fp32_lane_roofline": _lane_roofline(n_items * D * 625.0, ms)}
     del z
     # PCA 512 -> 256 projection
     from sklearn.decomposition import PCA
@@ -530,9 +531,22 @@ def _extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak, tf32_probe=None, bf1
     alg = n_items * (n_mc * D * 4 + D * 8 + 8)
     out["entropy_n32"] = {"items_per_s": n_items / (ms * 1e-3), "ms": ms, "n_mc": n_mc, "D": D,
                           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak,
-                                       "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak}}
+                                       "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak},
+                          "fp32_lane_roofline": _lane_roofline(n_items * D * 3000.0, ms)}
     del z
     return out
+
+
+def _lane_roofline(lane_ops, ms, sm_mhz=1965.0):
+    """FP32 CUDA-core roofline for the kernels whose arithmetic is adds / min / max (the entropy estimators): every such
+    operation costs one lane-cycle on this GPU (profiles/r2b_fmnmx_probe.jsonl: FADD 1.0, FMNMX 1.0, FMNMX3 2.0,
+    FADD2 2.0 cycles per warp instruction per scheduler, no overlap between the two pipes); peak = 148 SMs x 128 lanes x
+    the maximum SM clock.  `lane_ops` is the estimator's operation count (~625 per dimension at n_mc = 16,
+    ~3,000 at n_mc = 32 for the lane = sample layout)."""
+    peak = 148 * 128 * sm_mhz * 1e6
+    a = lane_ops / (ms * 1e-3)
+    return {"bound": "fp32 lanes", "achieved": round(a / 1e12, 2), "peak": round(peak / 1e12, 2), "unit": "T lane-ops/s",
+            "frac": round(a / peak, 4)}
 
 
 def _time_op(torch, fn, reps=5, warm=2):
