@@ -532,7 +532,7 @@ def _extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak, tf32_probe=None, bf1
     out["entropy_n32"] = {"items_per_s": n_items / (ms * 1e-3), "ms": ms, "n_mc": n_mc, "D": D,
                           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak,
                                        "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak},
-                          "fp32_lane_roofline": _lane_roofline(n_items * D * 3000.0, ms)}
+                          "fp32_lane_roofline": _lane_roofline(n_items * D * 2000.0, ms)}
     del z
     return out
 
@@ -542,7 +542,7 @@ def _lane_roofline(lane_ops, ms, sm_mhz=1965.0):
     operation costs one lane-cycle on this GPU (profiles/r2b_fmnmx_probe.jsonl: FADD 1.0, FMNMX 1.0, FMNMX3 2.0,
     FADD2 2.0 cycles per warp instruction per scheduler, no overlap between the two pipes); peak = 148 SMs x 128 lanes x
     the maximum SM clock.  `lane_ops` is the estimator's operation count (~625 per dimension at n_mc = 16,
-    ~3,000 at n_mc = 32 for the lane = sample layout)."""
+    ~2,000 at n_mc = 32 with every pair evaluated once)."""
     peak = 148 * 128 * sm_mhz * 1e6
     a = lane_ops / (ms * 1e-3)
     return {"bound": "fp32 lanes", "achieved": round(a / 1e12, 2), "peak": round(peak / 1e12, 2), "unit": "T lane-ops/s",

@@ -454,14 +454,14 @@ entropy_np_kernel(const float *__restrict__ z, int64_t n_items, int n, int D, fl
                   double *__restrict__ h_z, double *__restrict__ h_mvn) {
   constexpr int K = 5;
   __shared__ __align__(16) float stage_all[ENP_WARPS][NP * ENP_STRIDE];
-  __shared__ float acc_all[ENP_WARPS][NP * 32];  // [j][lane]: running max_d |x_lane[d] - x_j[d]| (row `lane` of the matrix)
+  __shared__ float acc_all[ENP_WARPS][(NP / 2 + 1) * 32];  // [t][lane]: running max_d |x_lane[d] - x_(lane + t)[d]|
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float *stage = stage_all[warp];
   float *acc = acc_all[warp] + lane;
   const bool want_joint = h_mvn != nullptr;
   for (int64_t item = (int64_t)blockIdx.x * ENP_WARPS + warp; item < n_items; item += (int64_t)gridDim.x * ENP_WARPS) {
     const float *zi = z + item * (int64_t)n * D;
-    for (int jj = 0; jj < n; ++jj) acc[jj * 32] = 0.f;
+    for (int jj = 0; jj <= (n >> 1); ++jj) acc[jj * 32] = 0.f;  // slot t: pair (lane, lane + t), t = 1 .. n / 2
     for (int j0 = 0; j0 < D; j0 += 32) {
       const int j = j0 + lane;
       const bool ok = j < D;
@@ -534,29 +534,51 @@ entropy_np_kernel(const float *__restrict__ z, int64_t n_items, int n, int D, fl
           }
           return fmaxf(ma, mb);
         };
-        int jj = 0;
+        // every unordered pair once: lane i takes the rows i + 1 .. i + n / 2 (mod n); accumulator slot t of lane i
+        // holds the distance of the pair (i, i + t).  (For even n the pairs at t = n / 2 are evaluated from both ends.)
+        // The row loads are no longer broadcasts -- 32 lanes read 32 different rows, four shared-memory wavefronts per
+        // LDS.128 with the 36-float row stride -- but the table's 2,048 lane-ops per dimension become 1,024.
+        const int T = n >> 1;
+        auto row_of = [&](int t) {
+          int r = lane + t;
+          r = r >= n ? r - n : r;
+          return stage + (lane < n ? r : 0) * ENP_STRIDE;
+        };
+        int t = 1;
 #pragma unroll 1
-        for (; jj + 4 <= n; jj += 4) {
-          const float m0 = acc[(jj + 0) * 32], m1 = acc[(jj + 1) * 32], m2 = acc[(jj + 2) * 32], m3 = acc[(jj + 3) * 32];
-          const float r0 = fold_row(stage + (jj + 0) * ENP_STRIDE, m0);
-          const float r1 = fold_row(stage + (jj + 1) * ENP_STRIDE, m1);
-          const float r2 = fold_row(stage + (jj + 2) * ENP_STRIDE, m2);
-          const float r3 = fold_row(stage + (jj + 3) * ENP_STRIDE, m3);
-          acc[(jj + 0) * 32] = r0;
-          acc[(jj + 1) * 32] = r1;
-          acc[(jj + 2) * 32] = r2;
-          acc[(jj + 3) * 32] = r3;
+        for (; t + 3 <= T; t += 4) {
+          const float m0 = acc[(t + 0) * 32], m1 = acc[(t + 1) * 32], m2 = acc[(t + 2) * 32], m3 = acc[(t + 3) * 32];
+          const float r0 = fold_row(row_of(t + 0), m0);
+          const float r1 = fold_row(row_of(t + 1), m1);
+          const float r2 = fold_row(row_of(t + 2), m2);
+          const float r3 = fold_row(row_of(t + 3), m3);
+          acc[(t + 0) * 32] = r0;
+          acc[(t + 1) * 32] = r1;
+          acc[(t + 2) * 32] = r2;
+          acc[(t + 3) * 32] = r3;
         }
 #pragma unroll 1
-        for (; jj < n; ++jj) acc[jj * 32] = fold_row(stage + jj * ENP_STRIDE, acc[jj * 32]);
+        for (; t <= T; ++t) acc[t * 32] = fold_row(row_of(t), acc[t * 32]);
       }
     }
     if (want_joint) {
+      __syncwarp();  // every lane's accumulators are in shared memory: row i also needs the pairs (i - t, i) of other lanes
       float lg = 0.f;
       if (lane < n) {
+        const int T = n >> 1;
+        const bool even = (n & 1) == 0;
         float row[NP];
+        row[0] = 0.f;  // self
 #pragma unroll
-        for (int jj = 0; jj < NP; ++jj) row[jj] = jj < n ? acc[jj * 32] : INFINITY;  // acc[lane] = 0 (self)
+        for (int t = 1; t <= NP / 2; ++t) {
+          int j2 = lane - t;
+          j2 = j2 < 0 ? j2 + n : j2;
+          const bool use = t <= T && t < n;
+          const float v1 = use ? acc_all[warp][t * 32 + lane] : INFINITY;                      // pair (i, i + t)
+          const float v2 = (use && !(even && t == T)) ? acc_all[warp][t * 32 + j2] : INFINITY;  // pair (i - t, i)
+          row[2 * t - 1] = v1;
+          if (2 * t < NP) row[2 * t] = v2;
+        }
         sort_network<NP>(row);  // row[0] = 0 (self); row[K] = k-th neighbour
         lg = lg2_pos(fmaxf(row[K], min_dist));
       }
