@@ -73,6 +73,8 @@ class Stager {
     // 4 threads reach the PCIe rate on a 20 MB call and keep the number of spinning threads small (fewer stragglers);
     // a long upload needs 8 to stay at 50 GB/s (4 threads: 29 GB/s on 1 GB) and can absorb a straggler in its ring
     int want = bytes >= (32u << 20) ? (int)workers_.size() : std::min<int>(3, (int)workers_.size());
+    // below one slot the copy takes less time (~0.1 ms) than a descheduled helper can cost (milliseconds): alone
+    if (bytes < kSlotBytes) want = 0;
     // a worker that was descheduled while it held a claimed piece made the previous call wait: the host's cores are
     // taken (BLAS threads of a fit spin for ~100 ms after their last call) -- copy alone until that has passed
     if (std::chrono::steady_clock::now() < solo_until_) want = 0;
