@@ -151,16 +151,17 @@ entropy_fast_kernel(const float *__restrict__ z, int64_t n_items, int D, float m
 
 // ------------------------------ n_mc = 16, k = 5, D % 4 == 0 ---------------------------------
 // The estimator is bound by the min/max (ALU) pipe, not by HBM: per (item, dimension) it needs
-// 120 pair maxima, a 16-element sort and 66 window radii.  This kernel spends as few ALU-pipe
-// instructions on them as the ISA allows:
+// 120 pair maxima, a 16-element sort and 66 window radii, and every FMNMX / FMNMX3 holds the half-rate
+// ALU pipe for two cycles (scripts/probes/pipe_probe.cu -> profiles/r2c_pipe_probe.jsonl).  This kernel
+// spends as few ALU-pipe instructions on them as the ISA allows:
 //  * a lane owns TWO adjacent dimensions per step; the 120 pair differences of both are one packed
 //    FADD2 each (FMA pipe) and fold into the running Chebyshev maxima with one 3-input FMNMX3
 //    max(pm, |d.x|, |d.y|);
 //  * the sort is the 60-comparator, 10-layer network (optimal size for 16 keys);
 //  * the k-th neighbour distance of sample i is min over the windows [a, a+5] containing it of
 //    max(s_i - s_a, s_{a+5} - s_i); the two end points of a window need no max at all, the four
-//    interior points fold the min_dist clamp into a 3-input max, and the min over (up to) six
-//    windows is a chain of 3-input mins; the differences are packed FADD2 over the two dimensions;
+//    interior points take a two-input max, the min over (up to) six windows is a chain of 3-input
+//    mins and the min_dist clamp is applied once per point; the differences are packed FADD2;
 //  * log2 is the bare MUFU (the radii are >= min_dist > 0: no denormal fix-up).
 // z is streamed HBM -> shared memory with 16-byte cp.async into a per-warp 3-deep ring (one step =
 // 16 samples x 64 dimensions = 4 KB), two steps ahead of the arithmetic, so that no register is spent
@@ -287,6 +288,7 @@ entropy16_kernel(const __grid_constant__ CUtensorMap tmZ, int64_t n_items, int D
     }
   };
   issue();
+  issue();  // both slots in flight: the slot a step has just read is refilled with the step TWO ahead
 
   int buf = 0;
   uint32_t phase = 0;
@@ -349,32 +351,45 @@ entropy16_kernel(const __grid_constant__ CUtensorMap tmZ, int64_t n_items, int D
 #pragma unroll
         for (int i = 0; i < N; ++i) s[i].y = v[i];
       }
-      float2 wc[N - K];  // window widths, clamped
-#pragma unroll
-      for (int a = 0; a < N - K; ++a) {
-        const float2 d = sub2(s[a + K], s[a]);
-        wc[a] = make_float2(fmaxf(d.x, min_dist), fmaxf(d.y, min_dist));
-      }
       float ax = 0.f, ay = 0.f;
+      {
+        // Two-input maxima for the interior points and ONE min_dist clamp per point, after the minimum over the windows.
+        // Every min / max instruction, 2- or 3-input, holds the half-rate ALU pipe for two cycles
+        // (profiles/r2c_pipe_probe.jsonl), so a 3-input form only pays when all three inputs are needed: the clamp
+        // folded into each candidate cost an instruction per candidate (44 per dimension) against 16 now.  Forming the
+        // candidates with adds only (w_a + |L - R| = 2 max(L, R)) and scalar instead of packed differences were both
+        // measured slower (profiles/r2c_entropy_variants.json).
+        float2 wc[N - K];
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        float rx = INFINITY, ry = INFINITY;
+        for (int a = 0; a < N - K; ++a) wc[a] = sub2(s[a + K], s[a]);
 #pragma unroll
-        for (int a = 0; a < N - K; ++a) {
-          if (a <= i && i <= a + K) {
-            if (i == a || i == a + K) {
-              rx = fminf(rx, wc[a].x);
-              ry = fminf(ry, wc[a].y);
-            } else {
-              const float2 L = sub2(s[i], s[a]);
-              const float2 R = sub2(s[a + K], s[i]);
-              rx = fminf(rx, fmaxf(fmaxf(L.x, R.x), min_dist));
-              ry = fminf(ry, fmaxf(fmaxf(L.y, R.y), min_dist));
+        for (int i = 0; i < N; ++i) {
+          float cx[K + 1], cy[K + 1];
+          int nc = 0;
+#pragma unroll
+          for (int a = 0; a < N - K; ++a) {
+            if (a <= i && i <= a + K) {
+              if (i == a || i == a + K) {
+                cx[nc] = wc[a].x;
+                cy[nc] = wc[a].y;
+              } else {
+                const float2 L = sub2(s[i], s[a]);
+                const float2 R = sub2(s[a + K], s[i]);
+                cx[nc] = fmaxf(L.x, R.x);
+                cy[nc] = fmaxf(L.y, R.y);
+              }
+              ++nc;
             }
           }
+          float rx = cx[0], ry = cy[0];
+          if (nc == 2) rx = fminf(rx, cx[1]), ry = fminf(ry, cy[1]);
+          if (nc >= 3) rx = fminf(fminf(rx, cx[1]), cx[2]), ry = fminf(fminf(ry, cy[1]), cy[2]);
+          if (nc == 4) rx = fminf(rx, cx[3]), ry = fminf(ry, cy[3]);
+          if (nc >= 5) rx = fminf(fminf(rx, cx[3]), cx[4]), ry = fminf(fminf(ry, cy[3]), cy[4]);
+          if (nc == 6) rx = fminf(rx, cx[5]), ry = fminf(ry, cy[5]);
+          ax += lg2_pos(fmaxf(rx, min_dist));
+          ay += lg2_pos(fmaxf(ry, min_dist));
         }
-        ax += lg2_pos(rx);
-        ay += lg2_pos(ry);
       }
       if (2 * j < D) {
         double2 o;  // h = -psi(k) + psi(n) + (1/n) sum log(2 r)   [d = 1]
@@ -597,6 +612,207 @@ static void launch_entropy_np(const float *z, int64_t n_items, int n, int D, flo
   entropy_np_kernel<NP><<<grid, ENP_WARPS * 32, 0, st>>>(z, n_items, n, D, min_dist, c_term, h_z, h_mvn);
 }
 
+// ------------------------------ n_mc = 32, k = 5 (the reference's default mcd_samples_nro) -------------------------
+// 496 pair maxima do not fit one lane's registers, so FOUR warps share an item: the CTA streams 32 x 128 tiles of z
+// (one cp.async.bulk.tensor per tile into a 4-slot ring, three tiles ahead, full / empty mbarriers per slot) and every
+// warp does a quarter of each part on the tile, all operands read from shared memory without bank conflicts:
+//  * joint (Chebyshev) part: the pairs are cut cyclically -- warp w holds the samples i = 8w .. 8w + 7 in registers and
+//    streams the samples i + 1 .. i + 16 (mod 32) past them: 8 x 16 = 128 running maxima per lane, a lane owning two
+//    adjacent dimensions per sub-step (FADD2 + max(pm, |d.x|, |d.y|)), two sub-steps of 64 dimensions per tile.
+//    4 x 128 = 512 slots cover the 496 pairs (the 16 pairs at cyclic distance 16 are evaluated from both ends);
+//  * per-dimension part: warp w takes the dimensions 32w .. 32w + 31 of the tile, lane = dimension: 32 keys in
+//    registers, Batcher's 191-comparator network, window minima;
+//  * item end: the 128 maxima are reduced over the lanes (redux.sync.max.f32), scattered into a 32 x 32 table
+//    (double-buffered, one __syncthreads per item) and one warp -- a different one every item -- sorts its row per lane.
+// Per tile and warp: 256 FADD2 + 256 FMNMX3 (pairs), 382 FMNMX (sort), ~220 min / max + ~180 FADD (windows) -- the same
+// arithmetic as entropy_np_kernel<32>, but no operand is read through shared-memory bank conflicts, the load stream is
+// the TMA unit's, and the two parts of a step no longer alternate between a lane = dimension and a lane = sample layout.
+// The bound is the half-rate ALU pipe (every min / max instruction holds it for two cycles: scripts/probes/
+// pipe_probe.cu); 30k x 32 x 512: 1.77 -> 1.24 ms.
+constexpr int E32_WARPS = 4;
+constexpr int E32_RING = 4;
+constexpr int E32_COLS = 128;
+constexpr int E32_SLOT_FLOATS = 32 * E32_COLS;
+constexpr int E32_DM = 32 * 33;
+constexpr int E32_NDM = 2;  // Chebyshev tables, alternating
+constexpr size_t kEntropy32Smem = (size_t)(E32_RING * E32_SLOT_FLOATS + E32_NDM * E32_DM) * sizeof(float) + 2 * E32_RING * 8;
+
+__device__ __forceinline__ void e32_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+// sum_i log2(max(r_i, min_dist)) over the sorted keys, k = 5: r_i = min over the windows [a, a + 5] holding i of
+// max(s_i - s_a, s_(a+5) - s_i); two-input maxima and one clamp per point, after the minimum.
+template <int N>
+__device__ __forceinline__ float sum_log2_knn5_sorted(const float (&s)[N], float min_dist) {
+  constexpr int K = 5;
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    float cand[K + 1];
+    int nc = 0;
+#pragma unroll
+    for (int a = 0; a + K < N; ++a) {
+      if (a <= i && i <= a + K) {
+        if (i == a || i == a + K)
+          cand[nc] = s[a + K] - s[a];
+        else
+          cand[nc] = fmaxf(s[i] - s[a], s[a + K] - s[i]);
+        ++nc;
+      }
+    }
+    float r = cand[0];
+    if (nc == 2) r = fminf(r, cand[1]);
+    if (nc >= 3) r = fminf(fminf(r, cand[1]), cand[2]);
+    if (nc == 4) r = fminf(r, cand[3]);
+    if (nc >= 5) r = fminf(fminf(r, cand[3]), cand[4]);
+    if (nc == 6) r = fminf(r, cand[5]);
+    acc += lg2_pos(fmaxf(r, min_dist));
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(E32_WARPS * 32, 2)
+entropy32_kernel(const __grid_constant__ CUtensorMap tmZ, int64_t n_items, int D, float min_dist, double c_term,
+                 double *__restrict__ h_z, double *__restrict__ h_mvn) {
+  constexpr int N = 32, K = 5;
+  extern __shared__ __align__(128) float smem32[];  // ring | Chebyshev tables | full[RING], empty[RING] mbarriers
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *ring = smem32;
+  float *dm = ring + E32_RING * E32_SLOT_FLOATS;
+  const uint32_t ring_u32 = e16_smem_u32(ring);
+  const uint32_t full_u32 = e16_smem_u32(dm + E32_NDM * E32_DM);
+  const uint32_t empty_u32 = full_u32 + 8u * E32_RING;
+  const int spi = (D + E32_COLS - 1) / E32_COLS;  // tiles per item
+  const int64_t G = gridDim.x;
+  const int64_t n_my = (int64_t)blockIdx.x < n_items ? (n_items - blockIdx.x + G - 1) / G : 0;
+  const int64_t n_steps = n_my * spi;
+  const bool want_joint = h_mvn != nullptr;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < E32_RING; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_u32 + 8u * s) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty_u32 + 8u * s), "r"(E32_WARPS) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmZ) : "memory");
+  }
+  for (int e = threadIdx.x; e < E32_NDM * E32_DM; e += E32_WARPS * 32) dm[e] = 0.f;  // the diagonals stay zero
+  __syncthreads();
+
+  // copy stream: thread 0, three tiles ahead of the arithmetic
+  int64_t c_item = blockIdx.x, c_step = 0;
+  int c_j = 0;
+  auto issue = [&]() {
+    if (c_step < n_steps) {
+      if (threadIdx.x == 0) {
+        const uint32_t slot = (uint32_t)c_step & (E32_RING - 1);
+        if (c_step >= E32_RING) e32_mbar_wait(empty_u32 + 8u * slot, (uint32_t)((c_step >> 2) - 1) & 1u);
+        const uint32_t bar = full_u32 + 8u * slot;
+        const uint32_t dst = ring_u32 + slot * (uint32_t)(E32_SLOT_FLOATS * 4);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(E32_SLOT_FLOATS * 4) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+            "l"(&tmZ), "r"(bar), "r"(c_j * E32_COLS), "r"((int)(c_item * N))
+            : "memory");
+      }
+      if (++c_j == spi) {
+        c_j = 0;
+        c_item += G;
+      }
+      ++c_step;
+    }
+  };
+  if (warp == 0) {
+    issue();
+    issue();
+    issue();
+  }
+
+  int64_t step = 0;
+  int it = 0;
+  for (int64_t item = blockIdx.x; item < n_items; item += G, ++it) {
+    float acc[128];  // slot 16 h + t - 1: max over the lane's dimensions of |x_(8w+h) - x_(8w+h+t)|, t = 1 .. 16
+#pragma unroll
+    for (int p = 0; p < 128; ++p) acc[p] = 0.f;
+#pragma unroll 1
+    for (int jstep = 0; jstep < spi; ++jstep, ++step) {
+      const uint32_t slot = (uint32_t)step & (E32_RING - 1);
+      if (warp == 0) issue();  // tile step + 3 goes to the slot every warp released at the end of step - 1
+      e32_mbar_wait(full_u32 + 8u * slot, (uint32_t)(step >> 2) & 1u);
+      const float *tile = ring + slot * E32_SLOT_FLOATS;
+      if (want_joint) {
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          const float2 *t2 = reinterpret_cast<const float2 *>(tile) + sub * 32 + lane;  // row stride: 64 float2
+          const int base = warp * 8;
+          float2 x[8];
+#pragma unroll
+          for (int h = 0; h < 8; ++h) x[h] = t2[(base + h) * 64];
+#pragma unroll
+          for (int r = 1; r <= 23; ++r) {
+            const float2 y = t2[((base + r) & 31) * 64];
+#pragma unroll
+            for (int h = 0; h < 8; ++h) {
+              const int t = r - h;
+              if (t >= 1 && t <= 16) {
+                const float2 d = sub2(x[h], y);
+                acc[16 * h + t - 1] = fmaxf(fmaxf(acc[16 * h + t - 1], fabsf(d.x)), fabsf(d.y));
+              }
+            }
+          }
+        }
+      }
+      {
+        float v[N];
+        const float *col = tile + warp * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = col[i * E32_COLS];
+        sort_network<N>(v);
+        const float sl = sum_log2_knn5_sorted<N>(v, min_dist);
+        const int j = jstep * E32_COLS + warp * 32 + lane;
+        if (j < D) h_z[item * (int64_t)D + j] = c_term + (double)(kLn2 * (1.f + sl * (1.f / N)));
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_u32 + 8u * slot) : "memory");
+    }
+    if (want_joint) {
+      float *dmb = dm + (it & 1) * E32_DM;
+      float keep[4];
+#pragma unroll
+      for (int p = 0; p < 128; ++p) {
+        const float m = warp_max_f32(acc[p]);
+        if ((p & 31) == lane) keep[p >> 5] = m;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int p = lane + 32 * q;
+        const int a = warp * 8 + (p >> 4), b = (a + (p & 15) + 1) & 31;
+        dmb[a * 33 + b] = keep[q];
+        dmb[b * 33 + a] = keep[q];
+      }
+      __syncthreads();  // the table two items back is only rewritten after this barrier: its reader has passed it
+      if (warp == (it & 3)) {
+        float v[N];
+#pragma unroll
+        for (int b = 0; b < N; ++b) v[b] = dmb[lane * 33 + b];
+        sort_network<N>(v);  // v[0] = 0 (self); v[K] = k-th neighbour
+        float lg = lg2_pos(fmaxf(v[K], min_dist));
+        lg = warp_sum32(lg);
+        if (lane == 0) h_mvn[item] = c_term + (double)D * (double)(kLn2 * (1.f + lg * (1.f / N)));
+      }
+    }
+  }
+}
+
 // ---------------------------------- generic path ------------------------------------------
 constexpr int kEntropyMaxN = 128;  // largest n_mc of the generic kernels (local arrays / the n x n matrix in shared memory)
 
@@ -737,8 +953,7 @@ extern "C" int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, 
       (reinterpret_cast<uintptr_t>(h_z) & 15) == 0 && n_items * 16 < (int64_t)0x7fffffff) {
     static PerDeviceFlag attr16;
     if (!attr16) {
-      RUNIA_CUDA(cudaFuncSetAttribute(entropy16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)kEntropy16Smem));
+      RUNIA_CUDA(cudaFuncSetAttribute(entropy16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEntropy16Smem));
       uint8_t pa[120], pb[120];
       int p = 0;
       for (int a = 0; a < 16; ++a)
@@ -776,6 +991,23 @@ extern "C" int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, 
         z, n_items, D, (float)min_dist, digamma_term, h_z, h_mvn);
     count_launch();
     return finish_launch("mcd_entropy(fast)");
+  }
+  if (n_mc == 32 && k == 5 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 &&
+      n_items * 32 < (int64_t)0x7fffffff && !getenv("RUNIA_B200_E32_OFF")) {
+    static PerDeviceFlag attr32;
+    if (!attr32) {
+      RUNIA_CUDA(cudaFuncSetAttribute(entropy32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEntropy32Smem));
+      attr32 = true;
+    }
+    CUtensorMap tmz;
+    int rc = tc::make_plain_map(&tmz, z, n_items * 32, D, 32, E32_COLS);
+    if (rc) return rc;
+    // one item per CTA at a time, two CTAs of four warps per SM (register-limited), items round-robin over CTAs
+    const unsigned grid = (unsigned)std::min<int64_t>(n_items, (int64_t)2 * kNumSMs);
+    entropy32_kernel<<<grid, E32_WARPS * 32, kEntropy32Smem, st>>>(tmz, n_items, D, (float)min_dist, digamma_term, h_z,
+                                                                   h_mvn);
+    count_launch();
+    return finish_launch("mcd_entropy(32)");
   }
   if (k == 5 && n_mc >= 6 && n_mc <= 32) {  // the reference's k for every n_mc > 5 (evaluation/entropy.py:66)
     if (n_mc <= 8)

@@ -394,6 +394,25 @@ def test_react_head_tensor_path_vs_oracle(R, d, C, clip):
     np.testing.assert_allclose(simt, got[:5000], rtol=2e-5, atol=2e-5)
 
 
+@pytest.mark.parametrize("n_items,D", [(1300, 256), (601, 132), (3, 4)])
+def test_entropy_n32_many_items_vs_oracle(R, n_items, D):
+    """entropy32_kernel (four warps per item, the reference's default mcd_samples_nro = 32): more items than resident
+    CTAs, so that the tile ring runs across item boundaries and both Chebyshev tables are reused; ragged last tile;
+    duplicates (min_dist clamp) and an all-equal item."""
+    n_mc = 32
+    rng = np.random.RandomState(n_items + D)
+    z = (rng.randn(n_items, 1, D) + 0.1 * rng.randn(n_items, n_mc, D)).astype(np.float32)
+    z[rng.rand(n_items, n_mc, D) < 0.3] = 0.0
+    z[min(7, n_items - 1)] = 1.25
+    z = z.reshape(-1, D)
+    hm, hz = R.evaluation.get_dl_h_z(z, n_mc)
+    rm, rz = O.get_dl_h_z(z, n_mc, chunk=64)
+    assert hz.shape == (n_items, D) and hm.shape == (n_items, 1)
+    assert rel_err(hz, rz) < RTOL and rel_err(hm, rm) < RTOL
+    np.testing.assert_allclose(hz, rz, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(hm, rm, rtol=1e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("n_mc,D", [(32, 512), (32, 100), (20, 36), (10, 512), (8, 65), (6, 512), (16, 510)])
 def test_entropy_any_n_mc_vs_oracle(R, n_mc, D):
     """entropy_np_kernel: every n_mc in [6, 32] (k = 5; 32 is the reference's default mcd_samples_nro), power-of-two
