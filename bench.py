@@ -493,7 +493,7 @@ def _extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak, tf32_probe=None, bf1
     out["entropy_config1"] = {"items_per_s": n_items / (ms * 1e-3), "ms": ms, "n_mc": n_mc, "D": D,
                               "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak,
                                            "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak},
-                              "fp32_lane_roofline": _lane_roofline(n_items * D * 625.0, ms)}
+                              "alu_pipe_roofline": _alu_pipe_roofline(n_items * (D / 64.0) * 540.0, ms)}
     del z
     # PCA 512 -> 256 projection
     from sklearn.decomposition import PCA
@@ -532,21 +532,22 @@ def _extra_single_gpu(args, torch, R, _ops, _lib, hbm_peak, tf32_probe=None, bf1
     out["entropy_n32"] = {"items_per_s": n_items / (ms * 1e-3), "ms": ms, "n_mc": n_mc, "D": D,
                           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak,
                                        "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak},
-                          "fp32_lane_roofline": _lane_roofline(n_items * D * 2000.0, ms)}
+                          "alu_pipe_roofline": _alu_pipe_roofline(n_items * (D / 128.0) * 4 * 856.0, ms)}
     del z
     return out
 
 
-def _lane_roofline(lane_ops, ms, sm_mhz=1965.0):
-    """FP32 CUDA-core roofline for the kernels whose arithmetic is adds / min / max (the entropy estimators): every such
-    operation costs one lane-cycle on this GPU (profiles/r2b_fmnmx_probe.jsonl: FADD 1.0, FMNMX 1.0, FMNMX3 2.0,
-    FADD2 2.0 cycles per warp instruction per scheduler, no overlap between the two pipes); peak = 148 SMs x 128 lanes x
-    the maximum SM clock.  `lane_ops` is the estimator's operation count (~625 per dimension at n_mc = 16,
-    ~2,000 at n_mc = 32 with every pair evaluated once)."""
-    peak = 148 * 128 * sm_mhz * 1e6
-    a = lane_ops / (ms * 1e-3)
-    return {"bound": "fp32 lanes", "achieved": round(a / 1e12, 2), "peak": round(peak / 1e12, 2), "unit": "T lane-ops/s",
-            "frac": round(a / peak, 4)}
+def _alu_pipe_roofline(alu_warp_instructions, ms, sm_mhz=1965.0):
+    """ALU-pipe roofline of the entropy kernels, whose arithmetic is min / max: on this GPU every FMNMX / FMNMX3 (2- or
+    3-input) holds the ALU pipe of its scheduler for two cycles (scripts/probes/pipe_probe.cu ->
+    profiles/r2c_pipe_probe.jsonl: 2 FMNMX 4.0 cycles, 1 FMNMX3 2.0, 2 FMNMX + 2 FADD 4.25), so the peak is
+    148 SMs x 4 schedulers x 0.5 instructions per cycle at the maximum SM clock.  `alu_warp_instructions` is counted from
+    the shipped SASS (cuobjdump): 540 FMNMX + FMNMX3 per 64-dimension step of a warp at n_mc = 16
+    (entropy16_kernel), 856 per 128-dimension tile and warp at n_mc = 32 (entropy32_kernel, four warps per tile)."""
+    peak = 148 * 4 * 0.5 * sm_mhz * 1e6
+    a = alu_warp_instructions / (ms * 1e-3)
+    return {"bound": "alu pipe (min/max)", "achieved": round(a / 1e9, 1), "peak": round(peak / 1e9, 1),
+            "unit": "G warp-instructions/s", "frac": round(a / peak, 4)}
 
 
 def _time_op(torch, fn, reps=5, warm=2):

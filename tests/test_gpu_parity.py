@@ -413,6 +413,23 @@ def test_entropy_n32_many_items_vs_oracle(R, n_items, D):
     np.testing.assert_allclose(hm, rm, rtol=1e-5, atol=1e-4)
 
 
+@pytest.mark.parametrize("n_mc", [16, 32])
+def test_entropy_without_joint_estimate_matches_with(R, n_mc):
+    """want_joint=False (per-dimension entropies only) skips the pair maxima and the item end: h_z must not change,
+    on device-resident samples and for more items than resident CTAs / warps."""
+    import torch
+
+    from runia_core_b200 import _ops
+
+    g = torch.Generator(device="cuda").manual_seed(n_mc)
+    z = torch.randn(2100 * n_mc, 192, generator=g, device="cuda")
+    hm, hz = _ops.mcd_entropy(z, n_mc)
+    hz = hz.clone()
+    hm0, hz0 = _ops.mcd_entropy(z, n_mc, want_joint=False)
+    assert hm is not None and hm0 is None
+    assert torch.equal(hz, hz0)
+
+
 @pytest.mark.parametrize("n_mc,D", [(32, 512), (32, 100), (20, 36), (10, 512), (8, 65), (6, 512), (16, 510)])
 def test_entropy_any_n_mc_vs_oracle(R, n_mc, D):
     """entropy_np_kernel: every n_mc in [6, 32] (k = 5; 32 is the reference's default mcd_samples_nro), power-of-two
