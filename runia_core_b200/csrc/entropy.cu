@@ -650,9 +650,10 @@ __device__ __forceinline__ void e32_mbar_wait(uint32_t bar, uint32_t parity) {
 
 // sum_i log2(max(r_i, min_dist)) over the sorted keys, k = 5: r_i = min over the windows [a, a + 5] holding i of
 // max(s_i - s_a, s_(a+5) - s_i); two-input maxima and one clamp per point, after the minimum.
-template <int N>
-__device__ __forceinline__ float sum_log2_knn5_sorted(const float (&s)[N], float min_dist) {
-  constexpr int K = 5;
+template <int N, bool FULL = true>
+__device__ __forceinline__ float sum_log2_knn5_sorted(const float (&s)[N], float min_dist, int n = N) {
+  constexpr int K = 5;  // !FULL: only the first n keys are samples, the rest +inf sentinels (they sort to the end; a
+                        // window that touches one has an infinite radius and drops out of a sample's minimum)
   float acc = 0.f;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
@@ -674,15 +675,21 @@ __device__ __forceinline__ float sum_log2_knn5_sorted(const float (&s)[N], float
     if (nc == 4) r = fminf(r, cand[3]);
     if (nc >= 5) r = fminf(fminf(r, cand[3]), cand[4]);
     if (nc == 6) r = fminf(r, cand[5]);
-    acc += lg2_pos(fmaxf(r, min_dist));
+    const float lg = lg2_pos(fmaxf(r, min_dist));
+    acc += (FULL || i < n) ? lg : 0.f;
   }
   return acc;
 }
 
+// FULL: n = 32.  Otherwise 17 <= n < 32 samples per item: the TMA box has n rows and the rows n .. 31 of every ring
+// slot hold +inf, written once -- a pair with a sentinel gets an infinite (or, sentinel with sentinel, NaN -> ignored)
+// distance and sorts behind the real ones, the sentinel keys of a dimension sort to the end (see above).
+template <bool FULL>
 __global__ void __launch_bounds__(E32_WARPS * 32, 2)
-entropy32_kernel(const __grid_constant__ CUtensorMap tmZ, int64_t n_items, int D, float min_dist, double c_term,
+entropy32_kernel(const __grid_constant__ CUtensorMap tmZ, int64_t n_items, int n, int D, float min_dist, double c_term,
                  double *__restrict__ h_z, double *__restrict__ h_mvn) {
   constexpr int N = 32, K = 5;
+  const float inv_n = FULL ? 1.f / N : 1.f / (float)n;
   extern __shared__ __align__(128) float smem32[];  // ring | Chebyshev tables | full[RING], empty[RING] mbarriers
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float *ring = smem32;
@@ -705,6 +712,10 @@ entropy32_kernel(const __grid_constant__ CUtensorMap tmZ, int64_t n_items, int D
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmZ) : "memory");
   }
   for (int e = threadIdx.x; e < E32_NDM * E32_DM; e += E32_WARPS * 32) dm[e] = 0.f;  // the diagonals stay zero
+  if (!FULL) {
+    for (int s = 0; s < E32_RING; ++s)
+      for (int e = n * E32_COLS + threadIdx.x; e < E32_SLOT_FLOATS; e += E32_WARPS * 32) ring[s * E32_SLOT_FLOATS + e] = INFINITY;
+  }
   __syncthreads();
 
   // copy stream: thread 0, three tiles ahead of the arithmetic
@@ -718,10 +729,12 @@ entropy32_kernel(const __grid_constant__ CUtensorMap tmZ, int64_t n_items, int D
         const uint32_t bar = full_u32 + 8u * slot;
         const uint32_t dst = ring_u32 + slot * (uint32_t)(E32_SLOT_FLOATS * 4);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(E32_SLOT_FLOATS * 4) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                     "r"((FULL ? N : n) * E32_COLS * 4)
+                     : "memory");
         asm volatile(
             "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-            "l"(&tmZ), "r"(bar), "r"(c_j * E32_COLS), "r"((int)(c_item * N))
+            "l"(&tmZ), "r"(bar), "r"(c_j * E32_COLS), "r"((int)(c_item * (FULL ? N : n)))
             : "memory");
       }
       if (++c_j == spi) {
@@ -777,9 +790,9 @@ entropy32_kernel(const __grid_constant__ CUtensorMap tmZ, int64_t n_items, int D
 #pragma unroll
         for (int i = 0; i < N; ++i) v[i] = col[i * E32_COLS];
         sort_network<N>(v);
-        const float sl = sum_log2_knn5_sorted<N>(v, min_dist);
+        const float sl = sum_log2_knn5_sorted<N, FULL>(v, min_dist, n);
         const int j = jstep * E32_COLS + warp * 32 + lane;
-        if (j < D) h_z[item * (int64_t)D + j] = c_term + (double)(kLn2 * (1.f + sl * (1.f / N)));
+        if (j < D) h_z[item * (int64_t)D + j] = c_term + (double)(kLn2 * (1.f + sl * inv_n));
       }
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_u32 + 8u * slot) : "memory");
@@ -806,8 +819,9 @@ entropy32_kernel(const __grid_constant__ CUtensorMap tmZ, int64_t n_items, int D
         for (int b = 0; b < N; ++b) v[b] = dmb[lane * 33 + b];
         sort_network<N>(v);  // v[0] = 0 (self); v[K] = k-th neighbour
         float lg = lg2_pos(fmaxf(v[K], min_dist));
+        if (!FULL && lane >= n) lg = 0.f;  // sentinel rows
         lg = warp_sum32(lg);
-        if (lane == 0) h_mvn[item] = c_term + (double)D * (double)(kLn2 * (1.f + lg * (1.f / N)));
+        if (lane == 0) h_mvn[item] = c_term + (double)D * (double)(kLn2 * (1.f + lg * inv_n));
       }
     }
   }
@@ -992,20 +1006,25 @@ extern "C" int runia_mcd_entropy_f32(const float *z, int64_t n_items, int n_mc, 
     count_launch();
     return finish_launch("mcd_entropy(fast)");
   }
-  if (n_mc == 32 && k == 5 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 &&
-      n_items * 32 < (int64_t)0x7fffffff && !getenv("RUNIA_B200_E32_OFF")) {
+  if (n_mc > 16 && n_mc <= 32 && k == 5 && D % 4 == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0 &&
+      n_items * n_mc < (int64_t)0x7fffffff && !getenv("RUNIA_B200_E32_OFF")) {
     static PerDeviceFlag attr32;
     if (!attr32) {
-      RUNIA_CUDA(cudaFuncSetAttribute(entropy32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEntropy32Smem));
+      RUNIA_CUDA(cudaFuncSetAttribute(entropy32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEntropy32Smem));
+      RUNIA_CUDA(cudaFuncSetAttribute(entropy32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEntropy32Smem));
       attr32 = true;
     }
     CUtensorMap tmz;
-    int rc = tc::make_plain_map(&tmz, z, n_items * 32, D, 32, E32_COLS);
+    int rc = tc::make_plain_map(&tmz, z, n_items * n_mc, D, n_mc, E32_COLS);
     if (rc) return rc;
     // one item per CTA at a time, two CTAs of four warps per SM (register-limited), items round-robin over CTAs
     const unsigned grid = (unsigned)std::min<int64_t>(n_items, (int64_t)2 * kNumSMs);
-    entropy32_kernel<<<grid, E32_WARPS * 32, kEntropy32Smem, st>>>(tmz, n_items, D, (float)min_dist, digamma_term, h_z,
-                                                                   h_mvn);
+    if (n_mc == 32)
+      entropy32_kernel<true><<<grid, E32_WARPS * 32, kEntropy32Smem, st>>>(tmz, n_items, n_mc, D, (float)min_dist,
+                                                                           digamma_term, h_z, h_mvn);
+    else
+      entropy32_kernel<false><<<grid, E32_WARPS * 32, kEntropy32Smem, st>>>(tmz, n_items, n_mc, D, (float)min_dist,
+                                                                            digamma_term, h_z, h_mvn);
     count_launch();
     return finish_launch("mcd_entropy(32)");
   }

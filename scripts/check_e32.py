@@ -51,6 +51,14 @@ ms_old = timed(lambda: _ops.mcd_entropy(z, 32))
 os.environ.pop("RUNIA_B200_E32_OFF", None)
 out["n32"] = {"ms": ms, "hbm_frac": alg / ms / 1e6 / 6553.0, "ms_one_warp_per_item": ms_old}
 del z
+n_items = 40000
+z = torch.randn(n_items * 24, D, device="cuda")
+ms = timed(lambda: _ops.mcd_entropy(z, 24))
+os.environ["RUNIA_B200_E32_OFF"] = "1"
+ms_old = timed(lambda: _ops.mcd_entropy(z, 24))
+os.environ.pop("RUNIA_B200_E32_OFF", None)
+out["n24"] = {"ms": ms, "ms_one_warp_per_item": ms_old}
+del z
 n_items = 60000
 z = torch.randn(n_items * 16, D, device="cuda")
 alg = n_items * (16 * D * 4 + D * 8 + 8)

@@ -394,12 +394,11 @@ def test_react_head_tensor_path_vs_oracle(R, d, C, clip):
     np.testing.assert_allclose(simt, got[:5000], rtol=2e-5, atol=2e-5)
 
 
-@pytest.mark.parametrize("n_items,D", [(1300, 256), (601, 132), (3, 4)])
-def test_entropy_n32_many_items_vs_oracle(R, n_items, D):
-    """entropy32_kernel (four warps per item, the reference's default mcd_samples_nro = 32): more items than resident
-    CTAs, so that the tile ring runs across item boundaries and both Chebyshev tables are reused; ragged last tile;
-    duplicates (min_dist clamp) and an all-equal item."""
-    n_mc = 32
+@pytest.mark.parametrize("n_items,D,n_mc", [(1300, 256, 32), (601, 132, 32), (3, 4, 32), (900, 192, 24), (700, 128, 17)])
+def test_entropy_n32_many_items_vs_oracle(R, n_items, D, n_mc):
+    """entropy32_kernel (four warps per item, the reference's default mcd_samples_nro = 32; 17 .. 31 samples with +inf
+    sentinel rows): more items than resident CTAs, so that the tile ring runs across item boundaries and both Chebyshev
+    tables are reused; ragged last tile; duplicates (min_dist clamp) and an all-equal item."""
     rng = np.random.RandomState(n_items + D)
     z = (rng.randn(n_items, 1, D) + 0.1 * rng.randn(n_items, n_mc, D)).astype(np.float32)
     z[rng.rand(n_items, n_mc, D) < 0.3] = 0.0
@@ -430,7 +429,8 @@ def test_entropy_without_joint_estimate_matches_with(R, n_mc):
     assert torch.equal(hz, hz0)
 
 
-@pytest.mark.parametrize("n_mc,D", [(32, 512), (32, 100), (20, 36), (10, 512), (8, 65), (6, 512), (16, 510)])
+@pytest.mark.parametrize("n_mc,D", [(32, 512), (32, 100), (20, 36), (10, 512), (8, 65), (6, 512), (16, 510),
+                                    (17, 512), (31, 260), (24, 64), (25, 30)])
 def test_entropy_any_n_mc_vs_oracle(R, n_mc, D):
     """entropy_np_kernel: every n_mc in [6, 32] (k = 5; 32 is the reference's default mcd_samples_nro), power-of-two
     padding with +inf sentinels, ragged last 32-dimension step, exact duplicates (min_dist clamp)."""
