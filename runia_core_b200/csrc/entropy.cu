@@ -623,7 +623,7 @@ static void launch_entropy_np(const float *z, int64_t n_items, int n, int D, flo
 //  * per-dimension part: warp w takes the dimensions 32w .. 32w + 31 of the tile, lane = dimension: 32 keys in
 //    registers, Batcher's 191-comparator network, window minima;
 //  * item end: the 128 maxima are reduced over the lanes (redux.sync.max.f32), scattered into a 32 x 32 table
-//    (double-buffered, one __syncthreads per item) and one warp -- a different one every item -- sorts its row per lane.
+//    (eight of them), and every fourth item the CTA meets at a barrier and each warp sorts the rows of one table.
 // Per tile and warp: 256 FADD2 + 256 FMNMX3 (pairs), 382 FMNMX (sort), ~220 min / max + ~180 FADD (windows) -- the same
 // arithmetic as entropy_np_kernel<32>, but no operand is read through shared-memory bank conflicts, the load stream is
 // the TMA unit's, and the two parts of a step no longer alternate between a lane = dimension and a lane = sample layout.
@@ -634,7 +634,7 @@ constexpr int E32_RING = 4;
 constexpr int E32_COLS = 128;
 constexpr int E32_SLOT_FLOATS = 32 * E32_COLS;
 constexpr int E32_DM = 32 * 33;
-constexpr int E32_NDM = 2;  // Chebyshev tables, alternating
+constexpr int E32_NDM = 8;  // Chebyshev tables: two groups of four (see the item end)
 constexpr size_t kEntropy32Smem = (size_t)(E32_RING * E32_SLOT_FLOATS + E32_NDM * E32_DM) * sizeof(float) + 2 * E32_RING * 8;
 
 __device__ __forceinline__ void e32_mbar_wait(uint32_t bar, uint32_t parity) {
@@ -798,7 +798,7 @@ entropy32_kernel(const __grid_constant__ CUtensorMap tmZ, int64_t n_items, int n
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_u32 + 8u * slot) : "memory");
     }
     if (want_joint) {
-      float *dmb = dm + (it & 1) * E32_DM;
+      float *dmb = dm + (it & (E32_NDM - 1)) * E32_DM;
       float keep[4];
 #pragma unroll
       for (int p = 0; p < 128; ++p) {
@@ -812,16 +812,25 @@ entropy32_kernel(const __grid_constant__ CUtensorMap tmZ, int64_t n_items, int n
         dmb[a * 33 + b] = keep[q];
         dmb[b * 33 + a] = keep[q];
       }
-      __syncthreads();  // the table two items back is only rewritten after this barrier: its reader has passed it
-      if (warp == (it & 3)) {
-        float v[N];
+      // The tables are finished FOUR items at a time, one per warp: a finishing warp that sorts its table while the
+      // other three wait at the next barrier cost a sort per item; four warps sorting four tables side by side cost a
+      // quarter of that, and the CTA meets at a barrier once per four items.  Eight tables in two groups: a group is
+      // rewritten after the NEXT group's barrier, which every warp passes only after its own sort of this one.
+      if ((it & 3) == 3 || item + G >= n_items) {
+        __syncthreads();
+        const int t = (it & ~3) + warp;  // the item (counted per CTA) this warp finishes
+        if (t <= it) {
+          const float *tb = dm + (t & (E32_NDM - 1)) * E32_DM;
+          float v[N];
 #pragma unroll
-        for (int b = 0; b < N; ++b) v[b] = dmb[lane * 33 + b];
-        sort_network<N>(v);  // v[0] = 0 (self); v[K] = k-th neighbour
-        float lg = lg2_pos(fmaxf(v[K], min_dist));
-        if (!FULL && lane >= n) lg = 0.f;  // sentinel rows
-        lg = warp_sum32(lg);
-        if (lane == 0) h_mvn[item] = c_term + (double)D * (double)(kLn2 * (1.f + lg * inv_n));
+          for (int b = 0; b < N; ++b) v[b] = tb[lane * 33 + b];
+          sort_network<N>(v);  // v[0] = 0 (self); v[K] = k-th neighbour
+          float lg = lg2_pos(fmaxf(v[K], min_dist));
+          if (!FULL && lane >= n) lg = 0.f;  // sentinel rows
+          lg = warp_sum32(lg);
+          if (lane == 0)
+            h_mvn[(int64_t)blockIdx.x + (int64_t)t * G] = c_term + (double)D * (double)(kLn2 * (1.f + lg * inv_n));
+        }
       }
     }
   }
